@@ -1,0 +1,231 @@
+/*
+ * mdc_b200.h -- C ABI of the B200-native (sm_100a) MDC-Net inference hot path.
+ *
+ * The reference (ashys2012/MDC-Net...) is pure Python/PyTorch and has NO FFI of its own
+ * (SURVEY.md section 8b); its boundary is the Python surface of model.py / axial_model.py /
+ * iou_calcualtions.py / iou_bbox.py / inference_p.py.  The Python host layer in
+ * mdc-net-..._b200/ mirrors that surface one-to-one and binds THIS library through ctypes;
+ * each entry point below names the reference code it replaces (paths relative to the
+ * reference tree).  INTEGRATION.md shows the ctypes stub a maintainer would add.
+ *
+ * Conventions
+ *   - every function returns 0 on success, <0 on error; mdc_last_error() gives the text
+ *     (thread-local).  There is no CPU fallback: without a CUDA device every compute call fails.
+ *   - no allocation inside: weights, activations, workspaces, KV pages and page tables are
+ *     caller-owned DEVICE buffers (torch tensors on the Python side); sizes come from the
+ *     *_workspace_bytes() queries.  Only mdc_ctx/mdc_model (small host structs + cached
+ *     CUtensorMap descriptors) are heap objects.
+ *   - everything is asynchronous on the cudaStream_t passed as `stream` (void* here so that the
+ *     header needs no CUDA include); calls are capturable into a CUDA graph.
+ *   - plain pointers and sizes only; no torch types.
+ */
+#ifndef MDC_B200_H
+#define MDC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MDC_ABI_VERSION 1
+
+/* element types of activations / weights */
+enum { MDC_F32 = 0, MDC_BF16 = 1 };
+
+/* GEMM epilogues: D = epi(A[M,K] . W[N,K]^T) */
+enum {
+  MDC_EPI_BIAS = 0,       /* D = acc + bias                                  (attn.qkv, cross K/V in-proj) */
+  MDC_EPI_BIAS_GELU = 1,  /* D = gelu_erf(acc + bias)                        (timm Mlp.fc1 + nn.GELU)       */
+  MDC_EPI_BIAS_RELU = 2,  /* D = relu(acc + bias)                            (TransformerDecoderLayer.linear1) */
+  MDC_EPI_LS_RESIDUAL = 3,/* R(f32,in place) += gamma * (acc + bias)         (attn.proj / mlp.fc2 + LayerScale + residual) */
+  MDC_EPI_PATCH = 4       /* R(f32)[row + row/period + 1] = acc + bias + pos[row % period]
+                             (patch_embed.proj + pos_embed, rows shifted past each image's cls slot) */
+};
+
+/* IoU modes */
+enum {
+  MDC_IOU_EPS = 0,     /* inter / (union + 1e-6)         iou_calcualtions.py:5-40  bbox_iou            */
+  MDC_IOU_PLAIN = 1,   /* inter / union  (0/0 = NaN)     iou_bbox.py:3-43          calculate_iou       */
+  MDC_IOU_NAN0 = 2,    /* inter / union, NaN -> 0        iou_calcualtions.py:78-105 (torchvision.box_iou + nan_to_num) */
+  MDC_IOU_GIOU = 3     /* iou - (enclose-union)/enclose  iou_calcualtions.py:220-255 giou_pairwise     */
+};
+
+typedef struct mdc_ctx mdc_ctx;
+typedef struct mdc_model mdc_model;
+
+/* ---- library / context ------------------------------------------------------------------ */
+int mdc_abi_version(void);
+const char* mdc_last_error(void);
+/* One context per device (and per host thread that drives it).  Caches TMA descriptors. */
+int mdc_ctx_create(int device, mdc_ctx** out);
+int mdc_ctx_destroy(mdc_ctx* ctx);
+/* number of kernels this library has launched through `ctx` since creation (bench.py's gpu_launches) */
+int64_t mdc_ctx_launch_count(const mdc_ctx* ctx);
+
+/* ---- (a) dense contractions ---------------------------------------------------------------
+ * Replaces every nn.Linear / Conv2d(k=s=16) on the path: timm patch_embed.proj, attn.qkv,
+ * attn.proj, mlp.fc1/fc2 (reached from model.py:17-22), and MultiheadAttention in-proj of the
+ * memory (torch functional.py multi_head_attention_forward, reached from model.py:110-113).
+ *   A [M,K] row-major (lda elements), W [N,K] row-major (nn.Linear layout), bias f32 [N] or NULL.
+ *   dtype: MDC_BF16 -> A,W bf16, tcgen05.mma kind::f16 with fp32 TMEM accumulators, TMA-fed;
+ *          MDC_F32  -> A,W f32, FFMA with fp32 accumulation in K order (the token-exact path).
+ *   D is `dtype` for BIAS/GELU/RELU; for LS_RESIDUAL / PATCH the output is the f32 stream R.
+ *   aux0: gamma f32[N] (LS_RESIDUAL) or pos f32[period,N] (PATCH); period: PATCH only.
+ */
+int mdc_gemm(mdc_ctx* ctx, int dtype, int epilogue,
+             const void* A, int64_t lda, const void* W, int64_t ldw,
+             void* D, int64_t ldd, const float* bias, const float* aux0, int period,
+             int M, int N, int K, void* stream);
+
+/* ---- (b) strip attention --------------------------------------------------------------------
+ * softmax(q k^T * scale) v over independent strips, un-masked.  One kernel for
+ *   (i)   axial_model.py:28-40 AxialAttention (one strip = whole token sequence, scale 0.125),
+ *   (ii)  timm Attention inside the ViT blocks (strip = 197 tokens, head_dim 64, scale 1/8),
+ *   (iii) true row / column strips of a patch grid (strip_len 14, n_strips = B*14).
+ * qkv: [n_strips*strip_len, 3*heads*head_dim] packed q|k|v (row stride ld_qkv), out:
+ * [n_strips*strip_len, heads*head_dim].  softmax_over_queries != 0 selects softmax over the query
+ * axis (AxialAttention.forward(axis=-2)); it requires strip_len <= 128.
+ */
+int mdc_strip_attention(mdc_ctx* ctx, int dtype, const void* qkv, int64_t ld_qkv, void* out, int64_t ld_out,
+                        int n_strips, int strip_len, int heads, int head_dim, float scale,
+                        int softmax_over_queries, void* stream);
+
+/* LayerNorm over the last axis of an f32 matrix, output `out_dtype` (timm norm1/norm2). */
+int mdc_layernorm(mdc_ctx* ctx, const float* x, int64_t ldx, const float* w, const float* b, float eps,
+                  void* out, int64_t ldo, int out_dtype, int rows, int cols, void* stream);
+
+/* u8 grayscale (B,h,w) -> 3 equal channels -> bilinear (half-pixel) resize -> /255 -> ImageNet
+ * normalise -> f32 NCHW (B,3,size,size).  inference_p.py:148-158 / dataset.py:109-113 semantics. */
+int mdc_preprocess_gray(mdc_ctx* ctx, const uint8_t* gray, int B, int h, int w, float* out, int size, void* stream);
+
+/* F.interpolate(mode='linear', align_corners=False) of a (n_in, dim) table to (n_out, dim): model.py:64-68 */
+int mdc_interp_rows(mdc_ctx* ctx, const float* in, int n_in, float* out, int n_out, int dim, void* stream);
+
+/* ---- model handle ----------------------------------------------------------------------------
+ * Geometry of Encoder (model.py:14-23), Decoder (model.py:26-56) and the globals the reference
+ * reads from CFG (model.py:32,60,94,117; utils.py:29).
+ */
+typedef struct mdc_dims {
+  int32_t precision;     /* MDC_F32 or MDC_BF16 */
+  int32_t img_size, patch, in_chans;
+  int32_t enc_dim, enc_depth, enc_heads, enc_mlp;   /* deit3_medium: 512, 12, 8, 2048 */
+  int32_t n_patches;     /* (img_size/patch)^2 = Decoder encoder_length */
+  int32_t dim;           /* Encoder out_dim == Decoder dim */
+  int32_t dec_heads, dec_layers, dec_ffn, vocab;
+  int32_t max_pos;       /* CFG.max_len - 1 rows of decoder_pos_embed */
+  int32_t pad_idx, bos_idx;
+  int32_t has_axial;     /* axial_model.Decoder.axial_attention present */
+  int32_t page_tokens;   /* self-attention KV page size in tokens (16) */
+} mdc_dims;
+
+/* Weight table: device pointers in the order of enum mdc_weight_slot, per-layer slots repeated.
+ * GEMM weights are `precision` typed [N,K]; everything else (biases, norms, gammas, positional
+ * tables, embedding, cls token) is f32.  The library keeps the pointers, never copies. */
+enum mdc_enc_slot {  /* encoder globals */
+  MDC_W_PATCH = 0, MDC_B_PATCH, MDC_CLS, MDC_POS, MDC_NORM_W, MDC_NORM_B, MDC_ENC_GLOBAL_SLOTS
+};
+enum mdc_enc_block_slot {  /* per ViT block, after the globals */
+  MDC_N1_W = 0, MDC_N1_B, MDC_QKV_W, MDC_QKV_B, MDC_PROJ_W, MDC_PROJ_B, MDC_LS1,
+  MDC_N2_W, MDC_N2_B, MDC_FC1_W, MDC_FC1_B, MDC_FC2_W, MDC_FC2_B, MDC_LS2, MDC_ENC_BLOCK_SLOTS
+};
+enum mdc_dec_slot {  /* decoder globals, after all encoder slots */
+  MDC_EMB = 0, MDC_DEC_POS, MDC_ENC_POS, MDC_OUT_W, MDC_OUT_B, MDC_AX_QKV_W, MDC_AX_OUT_W, MDC_AX_OUT_B,
+  MDC_DEC_GLOBAL_SLOTS
+};
+enum mdc_dec_layer_slot {  /* per decoder layer, after the decoder globals */
+  MDC_SA_IN_W = 0, MDC_SA_IN_B, MDC_SA_OUT_W, MDC_SA_OUT_B, MDC_LN1_W, MDC_LN1_B,
+  MDC_CA_IN_W, MDC_CA_IN_B, MDC_CA_OUT_W, MDC_CA_OUT_B, MDC_LN2_W, MDC_LN2_B,
+  MDC_FF1_W, MDC_FF1_B, MDC_FF2_W, MDC_FF2_B, MDC_LN3_W, MDC_LN3_B, MDC_DEC_LAYER_SLOTS
+};
+
+int mdc_model_create(mdc_ctx* ctx, const mdc_dims* dims, const void* const* weights, int n_weights,
+                     mdc_model** out);
+int mdc_model_destroy(mdc_model* m);
+int mdc_model_num_weights(const mdc_dims* dims);
+
+/* ---- encoder: Encoder.forward, model.py:21-23 (timm VisionTransformer + AdaptiveAvgPool1d) ---
+ * image f32 NCHW (B,3,img,img) -> enc_out f32 (B,n_patches,dim)  [what Encoder.forward returns]
+ *                               -> memory `precision` (B,n_patches,dim) = enc_out + encoder_pos_embed
+ *                                  (model.py:103-105), either output may be NULL.
+ */
+size_t mdc_encode_workspace_bytes(const mdc_model* m, int B);
+int mdc_encode(mdc_model* m, const float* image, int B, float* enc_out, void* memory,
+               void* workspace, size_t workspace_bytes, void* stream);
+/* memory from a caller-provided encoder_out (Decoder.forward/predict entry): mem = enc_out + enc_pos */
+int mdc_memory_from_encoder_out(mdc_model* m, const float* enc_out, int B, void* memory, void* stream);
+
+/* ---- (c) cross-attention K/V, once per image, HBM resident -----------------------------------
+ * cross_kv[l][b*S+s][0:dim]=K, [dim:2dim]=V  (`precision`), from rows [dim:3dim] of
+ * multihead_attn.in_proj_weight (torch functional.py in-proj packing q|k|v). */
+size_t mdc_cross_kv_bytes(const mdc_model* m, int B);
+int mdc_cross_kv_build(mdc_model* m, const void* memory, int B, void* cross_kv, void* stream);
+
+/* ---- (c,d) autoregressive decode ---------------------------------------------------------------
+ * State of one batch being decoded.  All device buffers caller-owned.
+ *   tokens   int32 [B, tokens_ld]   column 0..t are known when step t runs; step t writes column t+1
+ *   kv_pool  `precision` [n_pages][dec_layers][2][page_tokens][dim]   paged self-attention cache
+ *   page_table int32 [B, pages_per_seq]  physical page of logical page j of image b
+ *   logits   f32 [B, logits_ld, vocab] or NULL: row (t+1) receives the step-t logits
+ *            (= predict(x, prefix)[:, t+1], the reference's shifted layout, model.py:116-123)
+ *   confs    f32 [B, confs_ld] or NULL: max softmax prob of steps with t % 4 == 0 at column t/4
+ *            (inference_p.py:84-86)
+ *   uniforms f32 [B, uniforms_ld] or NULL: u in [0,1) per (image, step) for top-k/top-p sampling
+ *   scratch  decode workspace, mdc_decode_workspace_bytes()
+ */
+typedef struct mdc_decode_state {
+  int32_t B;
+  int32_t* tokens; int32_t tokens_ld;
+  void* kv_pool; const int32_t* page_table; int32_t pages_per_seq;
+  const void* cross_kv;
+  float* logits; int32_t logits_ld;
+  int32_t logits_row_offset;        /* step t writes logits row t + offset: 1 = predict's shifted layout, 0 = forward's */
+  float* confs; int32_t confs_ld;
+  const float* uniforms; int32_t uniforms_ld;
+  int32_t top_k; float top_p;       /* 0 / 1.0 = greedy argmax (first max index on ties) */
+  int32_t forced;                   /* 1 = teacher-forced: never write tokens (predict/forward) */
+  const float* pos_override;        /* optional (n,dim) positional table (interpolated, model.py:64-68) */
+  const float* x_override;          /* optional (B, n, dim) pre-computed input embeddings incl. pos (axial path) */
+  int32_t x_override_ld;            /* n */
+  void* scratch; size_t scratch_bytes;
+} mdc_decode_state;
+
+size_t mdc_decode_workspace_bytes(const mdc_model* m, int B);
+size_t mdc_kv_page_bytes(const mdc_model* m);
+/* steps t = t_begin .. t_end-1, back to back on `stream`, no host synchronisation inside. */
+int mdc_decode_steps(mdc_model* m, const mdc_decode_state* st, int t_begin, int t_end, void* stream);
+
+/* (d) head + select as a stand-alone op: logits f32 [B,V] -> token, max prob.
+ * greedy: argmax(softmax(logits)) = first max index (inference_p.py:77);
+ * top_k/top_p: transformers top_k_top_p_filtering (inference_p.py:83) then inverse-CDF draw with u. */
+int mdc_select(mdc_ctx* ctx, const float* logits, int64_t ld, int B, int V, int top_k, float top_p,
+               const float* uniforms, int32_t* token_out, float* conf_out, void* stream);
+
+/* AxialAttention.forward as a whole (axial_model.py:28-40): x f32 (B,n,dim) -> f32 (B,n,dim). */
+size_t mdc_axial_workspace_bytes(const mdc_model* m, int B, int n);
+int mdc_axial_attention(mdc_model* m, const float* x, int B, int n, int softmax_over_queries, float* out,
+                        void* workspace, size_t workspace_bytes, void* stream);
+
+/* axial_model.Decoder.forward front end (axial_model.py:100-103): out f32 (B,n,dim) =
+ * AxialAttention(embedding[tokens]) + pos (pos NULL -> decoder_pos_embed, then n must equal max_pos). */
+size_t mdc_axial_embed_workspace_bytes(const mdc_model* m, int B, int n);
+int mdc_axial_embed(mdc_model* m, const int32_t* tokens, int tokens_ld, int B, int n, const float* pos,
+                    int softmax_over_queries, float* out, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- (e) batched box scores --------------------------------------------------------------------
+ * pred f32 [B,N,4], gt f32 [B,M,4] xyxy, zero rows = padding (data_processing.py:596 pad_sequence).
+ * iou_out f32 [B,N,M] or NULL; max_out f32 [B,N] row-max over GT or NULL (iou_calcualtions.py:59-75,
+ * zero rows included, Q13).  One 128-bit load per box. */
+int mdc_iou_batch(mdc_ctx* ctx, int mode, const float* pred, const float* gt, int B, int N, int M,
+                  float* iou_out, float* max_out, void* stream);
+/* giou_loss_with_scores (iou_calcualtions.py:165-208): per-image loss f32 [B] (zero-sum rows
+ * filtered, penalty = #GT rows when nothing predicted) and the masked GIoU matrix f32 [B,N,M]
+ * (NaN-free: entries of filtered rows/cols are written as 0 and flagged in valid u8 [B,N,M]). */
+int mdc_giou_loss(mdc_ctx* ctx, const float* pred, const float* gt, int B, int N, int M, float no_detection_penalty,
+                  float* loss_per_image, float* giou_out, uint8_t* valid_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MDC_B200_H */

@@ -1,0 +1,205 @@
+// elementwise.cu -- bandwidth-bound pieces of the encoder: im2col for the stride-16 patch conv,
+// LayerNorm, the fused encoder tail (final norm + drop cls + channel pooling + encoder_pos_embed),
+// grayscale preprocessing and positional-table interpolation.  All rows are handled warp-per-row
+// with 128-bit accesses; grids are sized in units of warps so every SM gets work.
+#include "common.cuh"
+#include "kernels.cuh"
+
+namespace {
+
+// ---- patches: (B,C,H,W) f32 -> [B*n, C*p*p], patch flattened (ch, dy, dx) -- timm PatchEmbed.proj as a GEMM operand
+template <typename TO>
+__global__ void im2col_kernel(const float* __restrict__ x, TO* __restrict__ P, int B, int C, int img, int p) {
+  const int G = img / p, n = G * G, Kc = C * p * p;
+  const int chunks_per_row = Kc / 8;
+  int64_t total = (int64_t)B * n * chunks_per_row;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int ck = (int)(i % chunks_per_row);
+    int64_t row = i / chunks_per_row;
+    int b = (int)(row / n), pi = (int)(row % n);
+    int r = pi / G, c = pi % G;
+    int col = ck * 8;
+    int ch = col / (p * p), rem = col % (p * p), dy = rem / p, dx = rem % p;
+    const float* src = x + (((int64_t)b * C + ch) * img + (r * p + dy)) * img + c * p + dx;
+    float v[8]; load8(src, v);
+    store8(P + row * Kc + col, v);
+  }
+}
+
+__global__ void set_cls_rows_kernel(float* __restrict__ h, const float* __restrict__ cls, int B, int rows_per_img, int D) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < B * D) { int b = i / D, c = i % D; h[(int64_t)b * rows_per_img * D + c] = cls[c]; }
+}
+
+// ---- LayerNorm: warp per row, two-pass statistics (mean, then centred variance) like torch
+template <typename TO>
+__global__ void layernorm_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict__ w,
+                                 const float* __restrict__ b, float eps, TO* __restrict__ out, int64_t ldo,
+                                 int rows, int cols) {
+  int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= rows) return;
+  const float* xr = x + (int64_t)warp * ldx;
+  float s = 0.f;
+  for (int c = lane * 4; c < cols; c += 128) { float4 v = *reinterpret_cast<const float4*>(xr + c); s += (v.x + v.y) + (v.z + v.w); }
+  float mean = warp_sum(s) / (float)cols;
+  float q = 0.f;
+  for (int c = lane * 4; c < cols; c += 128) {
+    float4 v = *reinterpret_cast<const float4*>(xr + c);
+    float a0 = v.x - mean, a1 = v.y - mean, a2 = v.z - mean, a3 = v.w - mean;
+    q += (a0 * a0 + a1 * a1) + (a2 * a2 + a3 * a3);
+  }
+  float rstd = 1.0f / sqrtf(warp_sum(q) / (float)cols + eps);
+  TO* orow = out + (int64_t)warp * ldo;
+  for (int c = lane * 4; c < cols; c += 128) {
+    float4 v = *reinterpret_cast<const float4*>(xr + c);
+    float4 g = *reinterpret_cast<const float4*>(w + c), bb = *reinterpret_cast<const float4*>(b + c);
+    orow[c + 0] = from_f<TO>((v.x - mean) * rstd * g.x + bb.x);
+    orow[c + 1] = from_f<TO>((v.y - mean) * rstd * g.y + bb.y);
+    orow[c + 2] = from_f<TO>((v.z - mean) * rstd * g.z + bb.z);
+    orow[c + 3] = from_f<TO>((v.w - mean) * rstd * g.w + bb.w);
+  }
+}
+
+// ---- encoder tail: final LN (eps 1e-6), drop cls (model.py:23 features[:,1:]), AdaptiveAvgPool1d over
+// channels (model.py:19), + encoder_pos_embed (model.py:103-105).  Warp per patch token.
+template <typename TO>
+__global__ void encoder_tail_kernel(const float* __restrict__ h, const float* __restrict__ w, const float* __restrict__ b,
+                                    float eps, const float* __restrict__ enc_pos, float* __restrict__ enc_out,
+                                    TO* __restrict__ memory, int B, int n, int D, int out_dim) {
+  extern __shared__ float sm[];   // warps_per_block * D
+  int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int warp = blockIdx.x * (blockDim.x >> 5) + wib;
+  if (warp >= B * n) return;
+  int bi = warp / n, pi = warp % n;
+  const float* xr = h + ((int64_t)bi * (n + 1) + 1 + pi) * D;
+  float* row = sm + wib * D;
+  float s = 0.f;
+  for (int c = lane * 4; c < D; c += 128) { float4 v = *reinterpret_cast<const float4*>(xr + c); s += (v.x + v.y) + (v.z + v.w); }
+  float mean = warp_sum(s) / (float)D;
+  float q = 0.f;
+  for (int c = lane * 4; c < D; c += 128) {
+    float4 v = *reinterpret_cast<const float4*>(xr + c);
+    float a0 = v.x - mean, a1 = v.y - mean, a2 = v.z - mean, a3 = v.w - mean;
+    q += (a0 * a0 + a1 * a1) + (a2 * a2 + a3 * a3);
+  }
+  float rstd = 1.0f / sqrtf(warp_sum(q) / (float)D + eps);
+  for (int c = lane; c < D; c += 32) row[c] = (xr[c] - mean) * rstd * w[c] + b[c];
+  __syncwarp();
+  for (int o = lane; o < out_dim; o += 32) {
+    int st = (int)(((int64_t)o * D) / out_dim);
+    int en = (int)((((int64_t)(o + 1)) * D + out_dim - 1) / out_dim);
+    float acc = 0.f;
+    for (int c = st; c < en; ++c) acc += row[c];
+    float v = acc / (float)(en - st);
+    int64_t oi = ((int64_t)bi * n + pi) * out_dim + o;
+    if (enc_out) enc_out[oi] = v;
+    if (memory) memory[oi] = from_f<TO>(v + enc_pos[(int64_t)pi * out_dim + o]);
+  }
+}
+
+template <typename TO>
+__global__ void add_pos_kernel(const float* __restrict__ enc_out, const float* __restrict__ pos, TO* __restrict__ mem,
+                               int64_t total, int64_t per_img) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x)
+    mem[i] = from_f<TO>(enc_out[i] + pos[i % per_img]);
+}
+
+// ---- u8 gray -> normalised 3-channel f32 at model size (bilinear, half-pixel centres)
+__global__ void preprocess_gray_kernel(const uint8_t* __restrict__ g, int B, int h, int w, float* __restrict__ out, int size) {
+  const float sy = (float)h / (float)size, sx = (float)w / (float)size;
+  int64_t total = (int64_t)B * size * size;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int x = (int)(i % size), y = (int)((i / size) % size), b = (int)(i / ((int64_t)size * size));
+    float fy = fmaxf(sy * ((float)y + 0.5f) - 0.5f, 0.f), fx = fmaxf(sx * ((float)x + 0.5f) - 0.5f, 0.f);
+    int y0 = (int)fy, x0 = (int)fx;
+    int y1 = y0 + (y0 < h - 1 ? 1 : 0), x1 = x0 + (x0 < w - 1 ? 1 : 0);
+    float ly = fy - (float)y0, lx = fx - (float)x0;
+    const uint8_t* im = g + (int64_t)b * h * w;
+    float v00 = im[y0 * w + x0], v01 = im[y0 * w + x1], v10 = im[y1 * w + x0], v11 = im[y1 * w + x1];
+    float v = (1.f - ly) * ((1.f - lx) * v00 + lx * v01) + ly * ((1.f - lx) * v10 + lx * v11);
+    v = v / 255.0f;
+    const float mean[3] = {0.485f, 0.456f, 0.406f}, sd[3] = {0.229f, 0.224f, 0.225f};
+#pragma unroll
+    for (int c = 0; c < 3; ++c) out[(((int64_t)b * 3 + c) * size + y) * size + x] = (v - mean[c]) / sd[c];
+  }
+}
+
+__global__ void interp_rows_kernel(const float* __restrict__ in, int n_in, float* __restrict__ out, int n_out, int dim) {
+  const float scale = (float)n_in / (float)n_out;
+  int total = n_out * dim;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    int r = i / dim, c = i % dim;
+    float src = fmaxf(scale * ((float)r + 0.5f) - 0.5f, 0.f);
+    int i0 = min((int)src, n_in - 1), i1 = i0 + (i0 < n_in - 1 ? 1 : 0);
+    float l1 = src - (float)i0, l0 = 1.f - l1;
+    out[i] = l0 * in[(int64_t)i0 * dim + c] + l1 * in[(int64_t)i1 * dim + c];
+  }
+}
+
+inline int blocks_for(int64_t threads, int block, int sm_count) {
+  int64_t b = (threads + block - 1) / block;
+  int64_t cap = (int64_t)sm_count * 16;
+  return (int)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+}  // namespace
+
+int k_im2col(mdc_ctx* ctx, int dtype, const float* x, void* P, int B, int C, int img, int p, cudaStream_t s) {
+  MDC_CHECK_ARG(p % 8 == 0 && img % p == 0 && img % 4 == 0);
+  int64_t total = (int64_t)B * (img / p) * (img / p) * (C * p * p / 8);
+  int grid = blocks_for(total, 256, ctx->sm_count);
+  if (dtype == MDC_F32) im2col_kernel<float><<<grid, 256, 0, s>>>(x, (float*)P, B, C, img, p);
+  else im2col_kernel<bf16><<<grid, 256, 0, s>>>(x, (bf16*)P, B, C, img, p);
+  MDC_LAUNCH_CHECK(ctx); return 0;
+}
+
+int k_set_cls_rows(mdc_ctx* ctx, float* h, const float* cls, int B, int rows_per_img, int D, cudaStream_t s) {
+  set_cls_rows_kernel<<<(B * D + 255) / 256, 256, 0, s>>>(h, cls, B, rows_per_img, D);
+  MDC_LAUNCH_CHECK(ctx); return 0;
+}
+
+int k_encoder_tail(mdc_ctx* ctx, int dtype, const float* h, const float* w, const float* b, float eps, const float* enc_pos,
+                   float* enc_out, void* memory, int B, int n, int D, int out_dim, cudaStream_t s) {
+  MDC_CHECK_ARG(D % 4 == 0);
+  const int wpb = 8;
+  int grid = (B * n + wpb - 1) / wpb;
+  size_t smem = (size_t)wpb * D * sizeof(float);
+  if (dtype == MDC_F32) encoder_tail_kernel<float><<<grid, wpb * 32, smem, s>>>(h, w, b, eps, enc_pos, enc_out, (float*)memory, B, n, D, out_dim);
+  else encoder_tail_kernel<bf16><<<grid, wpb * 32, smem, s>>>(h, w, b, eps, enc_pos, enc_out, (bf16*)memory, B, n, D, out_dim);
+  MDC_LAUNCH_CHECK(ctx); return 0;
+}
+
+int k_add_pos(mdc_ctx* ctx, int dtype, const float* enc_out, const float* pos, void* mem, int64_t total, int64_t per_img, cudaStream_t s) {
+  int grid = blocks_for(total, 256, ctx->sm_count);
+  if (dtype == MDC_F32) add_pos_kernel<float><<<grid, 256, 0, s>>>(enc_out, pos, (float*)mem, total, per_img);
+  else add_pos_kernel<bf16><<<grid, 256, 0, s>>>(enc_out, pos, (bf16*)mem, total, per_img);
+  MDC_LAUNCH_CHECK(ctx); return 0;
+}
+
+extern "C" int mdc_layernorm(mdc_ctx* ctx, const float* x, int64_t ldx, const float* w, const float* b, float eps,
+                             void* out, int64_t ldo, int out_dtype, int rows, int cols, void* stream) {
+  MDC_CHECK_ARG(ctx && x && w && b && out);
+  MDC_CHECK_ARG(cols % 4 == 0 && ldx % 4 == 0 && rows >= 0);
+  if (rows == 0) return 0;
+  cudaStream_t s = (cudaStream_t)stream;
+  int grid = (rows + 7) / 8;
+  if (out_dtype == MDC_F32) layernorm_kernel<float><<<grid, 256, 0, s>>>(x, ldx, w, b, eps, (float*)out, ldo, rows, cols);
+  else if (out_dtype == MDC_BF16) layernorm_kernel<bf16><<<grid, 256, 0, s>>>(x, ldx, w, b, eps, (bf16*)out, ldo, rows, cols);
+  else MDC_FAIL(-2, "layernorm: bad out_dtype %d", out_dtype);
+  MDC_LAUNCH_CHECK(ctx); return 0;
+}
+
+extern "C" int mdc_preprocess_gray(mdc_ctx* ctx, const uint8_t* gray, int B, int h, int w, float* out, int size, void* stream) {
+  MDC_CHECK_ARG(ctx && gray && out && B >= 0 && h > 0 && w > 0 && size > 0);
+  if (B == 0) return 0;
+  int grid = blocks_for((int64_t)B * size * size, 256, ctx->sm_count);
+  preprocess_gray_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(gray, B, h, w, out, size);
+  MDC_LAUNCH_CHECK(ctx); return 0;
+}
+
+extern "C" int mdc_interp_rows(mdc_ctx* ctx, const float* in, int n_in, float* out, int n_out, int dim, void* stream) {
+  MDC_CHECK_ARG(ctx && in && out && n_in > 0 && n_out > 0 && dim > 0);
+  int grid = blocks_for((int64_t)n_out * dim, 256, ctx->sm_count);
+  interp_rows_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(in, n_in, out, n_out, dim);
+  MDC_LAUNCH_CHECK(ctx); return 0;
+}

@@ -1,0 +1,348 @@
+// gemm_tcgen05.cu -- bf16 GEMM D = epi(A[M,K] . W[N,K]^T) on the 5th-gen tensor cores (north_star (a)).
+//
+//   * persistent: one CTA per SM walks output tiles (n fastest so neighbouring CTAs share the A panel in L2)
+//   * warp-specialised: warp 0 = TMA producer (cp.async.bulk.tensor, SWIZZLE_128B, OOB rows/cols zero-filled),
+//     warp 1 = MMA issuer (one elected lane issues tcgen05.mma.cta_group::1.kind::f16, 128 x BN x 16),
+//     warps 2..5 = epilogue (tcgen05.ld 32x32b from TMEM -> bias / GELU / ReLU / LayerScale+residual / patch+pos)
+//   * three mbarrier pipelines: smem full/empty (kStages deep), TMEM full/empty (2 accumulator stages, so the
+//     epilogue of tile i overlaps the main loop of tile i+1)
+//   * accumulators live in TMEM (2 x BN fp32 columns), never in registers.
+// Both operands are K-major (A row-major [M,K]; W in nn.Linear layout [N,K]), one 128-byte swizzle atom per
+// BLOCK_K = 64 bf16.
+#include "common.cuh"
+#include <cuda.h>
+#include <cudaTypedefs.h>
+#include <mutex>
+#include <unordered_map>
+#include <string.h>
+
+namespace {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;           // 64 bf16 = 128 B = one SWIZZLE_128B atom
+constexpr int UMMA_K = 16;
+constexpr int NUM_THREADS = 192;      // warp0 TMA, warp1 MMA, warps 2-5 epilogue
+constexpr int EPI_THREADS = 128;
+
+template <int BN> struct Cfg {
+  static constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int kABytes = BLOCK_M * BLOCK_K * 2;
+  static constexpr int kBBytes = BN * BLOCK_K * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kTmemCols = (2 * BN <= 32) ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+// ---- PTX wrappers --------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}\n" : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// bounded wait: a protocol bug traps (reported as a launch failure) instead of hanging the GPU box
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0, spins = 0;
+  long long t0 = 0;
+  while (true) {
+    asm volatile("{\n\t.reg .pred P1;\n\tmbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\tselp.u32 %0, 1, 0, P1;\n\t}\n"
+                 : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    if (done) break;
+    if ((++spins & 1023u) == 0) {
+      long long now = clock64();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 4000000000LL) __trap();   // ~2 s
+    }
+  }
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint32_t bar, uint32_t dst, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
+               ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t addr, uint32_t* v) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+               "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+               "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                 "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                 "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                 "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+               : "r"(addr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major SWIZZLE_128B operand tile: rows of 128 B, 8-row groups 1024 B apart (SBO); LBO unused.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);          // start address        bits [0,14)
+  d |= (uint64_t)(1024 >> 4) << 32;                // stride byte offset   bits [32,46)
+  d |= (uint64_t)1 << 46;                          // descriptor version 1 (sm_100)
+  d |= (uint64_t)2 << 61;                          // layout type SWIZZLE_128B
+  return d;
+}
+// kind::f16: D=f32 (bits 4-5 =1), A=B=bf16 (bits 7-9, 10-12 = 1), both K-major, N>>3 at 17, M>>4 at 24
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+struct EpiArgs {
+  void* D; int64_t ldd; const float* bias; const float* aux0; int period; int epilogue;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, EpiArgs ep, int M, int N, int K) {
+  using C = Cfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + C::kStages * C::kABytes;
+  uint64_t* bars = (uint64_t*)(smem + C::kStages * C::kStageBytes);
+  uint64_t* full = bars;                         // [kStages]
+  uint64_t* empty = bars + C::kStages;           // [kStages]
+  uint64_t* tmem_full = bars + 2 * C::kStages;   // [2]
+  uint64_t* tmem_empty = tmem_full + 2;          // [2]
+  uint32_t* tmem_ptr_smem = (uint32_t*)(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tiles_n = (N + BN - 1) / BN, tiles_m = (M + BLOCK_M - 1) / BLOCK_M;
+  const int num_tiles = tiles_m * tiles_n;
+  const int num_kb = (K + BLOCK_K - 1) / BLOCK_K;
+
+  if (warp == 0 && elect_one()) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
+    for (int i = 0; i < C::kStages; ++i) { mbar_init(smem_u32(&full[i]), 1); mbar_init(smem_u32(&empty[i]), 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&tmem_full[i]), 1); mbar_init(smem_u32(&tmem_empty[i]), EPI_THREADS); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  } else if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "r"(C::kTmemCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (elect_one()) {
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = (tile / tiles_n) * BLOCK_M, n0 = (tile % tiles_n) * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(smem_u32(&empty[stage]), phase ^ 1);
+          const uint32_t fb = smem_u32(&full[stage]);
+          mbar_expect_tx(fb, C::kStageBytes);
+          tma_load_2d(&map_a, fb, smem_u32(smem_a + stage * C::kABytes), kb * BLOCK_K, m0);
+          tma_load_2d(&map_w, fb, smem_u32(smem_b + stage * C::kBBytes), kb * BLOCK_K, n0);
+          if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    constexpr uint32_t idesc = make_idesc(BLOCK_M, BN);
+    int stage = 0; uint32_t phase = 0; int iter = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++iter) {
+      const int as = iter & 1; const uint32_t aphase = (iter >> 1) & 1;
+      mbar_wait(smem_u32(&tmem_empty[as]), aphase ^ 1);
+      tcgen05_fence_after();
+      const uint32_t tmem_d = tmem_base + as * BN;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(smem_u32(&full[stage]), phase);
+        tcgen05_fence_after();
+        if (elect_one()) {
+          const uint64_t adesc = make_smem_desc(smem_u32(smem_a + stage * C::kABytes));
+          const uint64_t bdesc = make_smem_desc(smem_u32(smem_b + stage * C::kBBytes));
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k)   // +32 B per UMMA_K inside the swizzle atom -> +2 in the >>4 address field
+            umma_f16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+          umma_commit(smem_u32(&empty[stage]));                       // frees the smem slot when these MMAs retire
+          if (kb == num_kb - 1) umma_commit(smem_u32(&tmem_full[as])); // accumulator ready for the epilogue
+        }
+        __syncwarp();
+        if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else {
+    // ===== epilogue: warp w may only touch TMEM lanes [32*(w%4), +32) =====
+    const int quad = warp & 3;
+    int iter = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++iter) {
+      const int as = iter & 1; const uint32_t aphase = (iter >> 1) & 1;
+      const int m0 = (tile / tiles_n) * BLOCK_M, n0 = (tile % tiles_n) * BN;
+      mbar_wait(smem_u32(&tmem_full[as]), aphase);
+      tcgen05_fence_after();
+      const int row = m0 + quad * 32 + lane;
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + as * BN;
+      int64_t orow = row; const float* posrow = nullptr;
+      if (ep.epilogue == MDC_EPI_PATCH) { int img = row / ep.period; orow = row + img + 1; posrow = ep.aux0 + (int64_t)(row - img * ep.period) * ep.ldd; }
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(taddr + c0, v);
+        tmem_ld_wait();
+        const int col0 = n0 + c0;
+        if (row < M && col0 < N) {
+          const bool full32 = (col0 + 32 <= N);
+          if (ep.epilogue == MDC_EPI_LS_RESIDUAL || ep.epilogue == MDC_EPI_PATCH) {
+            float* dst = reinterpret_cast<float*>(ep.D) + orow * ep.ldd + col0;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              if (full32 || col0 + j + 3 < N) {
+                float4 b4 = ep.bias ? *reinterpret_cast<const float4*>(ep.bias + col0 + j) : make_float4(0, 0, 0, 0);
+                float4 o;
+                if (ep.epilogue == MDC_EPI_LS_RESIDUAL) {
+                  float4 g4 = *reinterpret_cast<const float4*>(ep.aux0 + col0 + j);
+                  float4 r4 = *reinterpret_cast<const float4*>(dst + j);
+                  o.x = r4.x + g4.x * (__uint_as_float(v[j]) + b4.x); o.y = r4.y + g4.y * (__uint_as_float(v[j + 1]) + b4.y);
+                  o.z = r4.z + g4.z * (__uint_as_float(v[j + 2]) + b4.z); o.w = r4.w + g4.w * (__uint_as_float(v[j + 3]) + b4.w);
+                } else {
+                  float4 p4 = *reinterpret_cast<const float4*>(posrow + col0 + j);
+                  o.x = __uint_as_float(v[j]) + b4.x + p4.x; o.y = __uint_as_float(v[j + 1]) + b4.y + p4.y;
+                  o.z = __uint_as_float(v[j + 2]) + b4.z + p4.z; o.w = __uint_as_float(v[j + 3]) + b4.w + p4.w;
+                }
+                *reinterpret_cast<float4*>(dst + j) = o;
+              } else {
+                for (int jj = j; jj < j + 4 && col0 + jj < N; ++jj) {
+                  float a = __uint_as_float(v[jj]) + (ep.bias ? ep.bias[col0 + jj] : 0.f);
+                  if (ep.epilogue == MDC_EPI_LS_RESIDUAL) dst[jj] = dst[jj] + ep.aux0[col0 + jj] * a;
+                  else dst[jj] = a + posrow[col0 + jj];
+                }
+              }
+            }
+          } else {
+            bf16* dst = reinterpret_cast<bf16*>(ep.D) + orow * ep.ldd + col0;
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              float o[8];
+#pragma unroll
+              for (int jj = 0; jj < 8; ++jj) {
+                float a = __uint_as_float(v[j + jj]);
+                if (ep.bias && col0 + j + jj < N) a += __ldg(ep.bias + col0 + j + jj);
+                if (ep.epilogue == MDC_EPI_BIAS_GELU) a = gelu_erf(a);
+                else if (ep.epilogue == MDC_EPI_BIAS_RELU) a = fmaxf(a, 0.f);
+                o[jj] = a;
+              }
+              if (full32 || col0 + j + 7 < N) store8(dst + j, o);
+              else for (int jj = 0; jj < 8 && col0 + j + jj < N; ++jj) dst[j + jj] = __float2bfloat16_rn(o[jj]);
+            }
+          }
+        }
+      }
+      tcgen05_fence_before();
+      mbar_arrive(smem_u32(&tmem_empty[as]));
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(C::kTmemCols) : "memory");
+  }
+}
+
+// ---- host side: tensor-map cache --------------------------------------------------------------------
+struct TmapKey {
+  const void* ptr; int64_t rows, cols, ld; int box_rows;
+  bool operator==(const TmapKey& o) const { return ptr == o.ptr && rows == o.rows && cols == o.cols && ld == o.ld && box_rows == o.box_rows; }
+};
+struct TmapHash {
+  size_t operator()(const TmapKey& k) const {
+    size_t h = (size_t)k.ptr; h ^= (size_t)k.rows * 0x9E3779B97F4A7C15ull; h ^= (size_t)k.cols * 0xC2B2AE3D27D4EB4Full;
+    h ^= (size_t)k.ld * 0x165667B19E3779F9ull; h ^= (size_t)k.box_rows << 7; return h;
+  }
+};
+struct TmapCache { std::unordered_map<TmapKey, CUtensorMap, TmapHash> map; std::mutex mu; };
+
+int get_tmap(mdc_ctx* ctx, const void* ptr, int64_t rows, int64_t cols, int64_t ld, int box_rows, CUtensorMap* out) {
+  if (!ctx->encode_fn) {
+    void* fn = nullptr; cudaDriverEntryPointQueryResult qres;
+    MDC_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    if (qres != cudaDriverEntryPointSuccess || !fn) MDC_FAIL(-3, "cuTensorMapEncodeTiled entry point unavailable");
+    ctx->encode_fn = fn;
+  }
+  if (!ctx->tmap_cache) ctx->tmap_cache = new TmapCache();
+  TmapCache* c = (TmapCache*)ctx->tmap_cache;
+  TmapKey key{ptr, rows, cols, ld, box_rows};
+  std::lock_guard<std::mutex> lk(c->mu);
+  auto it = c->map.find(key);
+  if (it != c->map.end()) { *out = it->second; return 0; }
+  auto encode = (PFN_cuTensorMapEncodeTiled_v12000)ctx->encode_fn;
+  CUtensorMap m;
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstride[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = encode(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstride, box, estr,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) MDC_FAIL(-3, "cuTensorMapEncodeTiled failed (%d) ptr=%p rows=%lld cols=%lld ld=%lld", (int)r, ptr, (long long)rows, (long long)cols, (long long)ld);
+  if (c->map.size() > 4096) c->map.clear();
+  c->map.emplace(key, m);
+  *out = m; return 0;
+}
+
+template <int BN>
+int launch_bn(mdc_ctx* ctx, const CUtensorMap& ma, const CUtensorMap& mw, const EpiArgs& ep, int M, int N, int K, cudaStream_t s) {
+  using C = Cfg<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    MDC_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
+    attr_set = true;
+  }
+  int tiles = ((M + BLOCK_M - 1) / BLOCK_M) * ((N + BN - 1) / BN);
+  int grid = tiles < ctx->sm_count ? tiles : ctx->sm_count;
+  gemm_tc_kernel<BN><<<grid, NUM_THREADS, C::kSmemBytes, s>>>(ma, mw, ep, M, N, K);
+  MDC_LAUNCH_CHECK(ctx);
+  return 0;
+}
+
+}  // namespace
+
+int gemm_tc_supported(int M, int N, int K, int64_t lda, int64_t ldw) {
+  // TMA: 16-byte aligned row pitch; epilogue vector paths want N % 8 == 0
+  return (K % 8 == 0) && (lda % 8 == 0) && (ldw % 8 == 0) && (N % 8 == 0) && M >= 1;
+}
+
+int gemm_tc_launch(mdc_ctx* ctx, int epilogue, const void* A, int64_t lda, const void* W, int64_t ldw, void* D, int64_t ldd,
+                   const float* bias, const float* aux0, int period, int M, int N, int K, cudaStream_t s) {
+  MDC_CHECK_ARG(((uintptr_t)A & 15) == 0 && ((uintptr_t)W & 15) == 0 && ((uintptr_t)D & 15) == 0);
+  MDC_CHECK_ARG(ldd % 8 == 0);
+  // tile width: prefer the widest tile that still gives every SM work; narrow N uses narrow tiles
+  const int tiles_m = (M + BLOCK_M - 1) / BLOCK_M;
+  int bn = 128;
+  if (N % 256 == 0 && tiles_m * (N / 256) >= 2 * ctx->sm_count) bn = 256;
+  if (N <= 64 || tiles_m * ((N + 127) / 128) < ctx->sm_count) bn = 64;
+  CUtensorMap ma, mw;
+  MDC_TRY(get_tmap(ctx, A, M, K, lda, BLOCK_M, &ma));
+  MDC_TRY(get_tmap(ctx, W, N, K, ldw, bn, &mw));
+  EpiArgs ep{D, ldd, bias, aux0, period, epilogue};
+  if (bn == 256) return launch_bn<256>(ctx, ma, mw, ep, M, N, K, s);
+  if (bn == 128) return launch_bn<128>(ctx, ma, mw, ep, M, N, K, s);
+  return launch_bn<64>(ctx, ma, mw, ep, M, N, K, s);
+}
+
+void gemm_tc_ctx_destroy(mdc_ctx* ctx) {
+  if (ctx && ctx->tmap_cache) { delete (TmapCache*)ctx->tmap_cache; ctx->tmap_cache = nullptr; }
+}

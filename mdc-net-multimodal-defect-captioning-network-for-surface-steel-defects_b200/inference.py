@@ -1,0 +1,59 @@
+"""`generate()` and `postprocess()` with the reference's signatures (inference_p.py:69-115; the same
+text lives in inference_trail_after_good_map.py:26-76), driving the incremental B200 decode loop:
+encoder once, cross-attention K/V once, one fused decode step per new token, NO host
+synchronisation inside the loop (the reference re-runs the whole model and syncs every 4th step).
+
+Reference defects handled as SURVEY 0.2 prescribes: Q2 (`top_k_top_p_filtering` no longer exists in
+transformers; its semantics are implemented inside the select kernel), Q5 (next-token logits :=
+predict(x, prefix)[:, L]), Q6 (max_len <= CFG.max_len-1), Q9 (encoder hoisted out of the loop).
+"""
+from __future__ import annotations
+
+import torch
+
+from .config import CFG
+
+
+@torch.no_grad()
+def generate(model, x, tokenizer, max_len=50, top_k=0, top_p=1, uniforms=None):
+    """Returns (LongTensor (B, 1+max_len) on CPU, list of ceil(max_len/4) float tensors (B,) on CPU).
+
+    `uniforms` (B, max_len) in [0,1) is an optional superset argument: the per-step uniform variates
+    of the top-k/top-p sampler (inverse-CDF draw), so that sampling is reproducible; by default they
+    are drawn with torch.rand on the device (the reference uses torch.multinomial, inference_p.py:74)."""
+    bos = int(getattr(tokenizer, "BOS_code", CFG.bos_idx))
+    if bos != int(CFG.bos_idx):
+        raise ValueError("tokenizer.BOS_code must equal CFG.bos_idx (model.py:117 reads the global)")
+    if not hasattr(model, "generate_tokens"):
+        raise TypeError("generate() needs the B200 EncoderDecoder; there is no PyTorch fallback path")
+    tokens, confs = model.generate_tokens(x, max_len, top_k=top_k, top_p=top_p, uniforms=uniforms)
+    host = torch.empty(tokens.shape, dtype=torch.int32, pin_memory=True)
+    host_c = torch.empty(confs.shape, dtype=torch.float32, pin_memory=True)
+    host.copy_(tokens, non_blocking=True)
+    host_c.copy_(confs, non_blocking=True)
+    torch.cuda.current_stream(tokens.device).synchronize()      # the ONE sync of the whole call
+    n_conf = (max_len + 3) // 4
+    return host.long(), [host_c[:, i].clone() for i in range(n_conf)]
+
+
+def postprocess(batch_preds, batch_confs, tokenizer):
+    """inference_trail_after_good_map.py:50-76 (caption-aware twin of inference_p.py:93-115): first EOS,
+    the reference's `(EOS-1) % 5` sanity rule (Q12, kept verbatim), then tokenizer.decode per sample.
+    Host-side Python, as in the reference."""
+    EOS_idxs = (batch_preds == tokenizer.EOS_code).float().argmax(dim=-1)
+    invalid_idxs = ((EOS_idxs - 1) % 5 != 0).nonzero().view(-1)
+    EOS_idxs[invalid_idxs] = 0
+    all_bboxes, all_labels, all_captions, all_confs = [], [], [], []
+    for i, EOS_idx in enumerate(EOS_idxs.tolist()):
+        if EOS_idx == 0:
+            all_bboxes.append(None); all_labels.append(None); all_captions.append(None); all_confs.append(None)
+            continue
+        decoded = tokenizer.decode(batch_preds[i, :EOS_idx + 1])
+        if len(decoded) == 3:
+            labels, bboxes, captions = decoded
+        else:                                   # caption-less tokenizer API of inference_p.py:108
+            labels, bboxes = decoded
+            captions = None
+        confs = [round(batch_confs[j][i].item(), 3) for j in range(len(bboxes))]
+        all_bboxes.append(bboxes); all_labels.append(labels); all_captions.append(captions); all_confs.append(confs)
+    return all_bboxes, all_labels, all_captions, all_confs
