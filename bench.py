@@ -1,0 +1,281 @@
+#!/usr/bin/env python
+"""bench.py -- images/sec of MDC-Net's batched inference hot path (encode + greedy decode) on B200.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+A "step" = one batch of 64 synthetic NEU-DET-shaped images (200x200 gray -> 3x224x224 normalised)
+through encoder -> cross-K/V -> 99 greedy decode steps (BASELINE.json configs[1]: config P, B=64, bf16).
+N>1 (torchrun): every rank owns its own 64 images (weak scaling; configs[2] at 8 ranks = B 512) and the
+step ends with ONE all-gather of the packed results.  Prints ONE JSON line on rank 0.
+
+  value  : device-resident inputs, CUDA-event time of the step (max over ranks)
+  e2e    : the public API generate(model, x_host_pinned, tokenizer, max_len) incl. H2D of x and D2H of results
+  roofline: the dominant kernel timed alone with CUDA events (algorithmic bytes or flops / time)
+  cpu_baseline: the oracle port of the reference's own loop (encoder recomputed every step, model.py:177-181)
+              on the host cores, bounded sample.   --impl reference prints only that arm.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+B_PER_GPU = 64
+T_NEW = 99
+METRIC = "images/sec end-to-end encode+greedy decode"
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"], "bf16_tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                "src": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "src": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=3)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) >= 7 and r[3 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+def cpu_reference_arm(steps, warmup, sample_steps=6):
+    """The reference's own CPU path, restated (oracle port): generate() loop with the encoder recomputed every
+    step (Q9) and the full padded decoder (here: its causal-equivalent prefix form), fp32, all host threads.
+    Bounded sample: B=1 image, `sample_steps` of the 99 decode steps, extrapolated linearly to 99."""
+    from oracle import cases, mdc_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    model = cases.build_product_model("P", seed=0, gamma_seed=5)
+    sd, cfg = cases.state_dict_of(model), cases.oracle_cfg("P")
+    x = cases.images(1)
+    times = []
+    with torch.no_grad():
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            O.generate(sd, x, cfg, max_len=sample_steps, recompute_encoder=True)
+            dt = time.perf_counter() - t0
+            if i >= warmup:
+                times.append(dt)
+    per_step = statistics.mean(times) / sample_steps
+    img_s = 1.0 / (per_step * T_NEW)
+    return {"value": img_s, "unit": "images/s", "cores": cores, "kind": "port",
+            "sample": f"B=1, {sample_steps} of {T_NEW} decode steps of the reference loop (encoder recomputed each step), "
+                      f"extrapolated x{T_NEW}/{sample_steps}; {per_step * 1e3:.1f} ms/token"}, statistics.mean(times)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--profile", action="store_true", help="1 warm-up + 1 step only (for an ncu launch list)")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    cfg = {"workload": f"MDC-Net config P (deit3_medium 224 + 6-layer dim-256 decoder, V=305), batch {B_PER_GPU}/GPU, "
+                       f"{T_NEW} greedy tokens, synthetic 200x200 gray -> 3x224x224", "global_batch": B_PER_GPU * world,
+           "new_tokens": T_NEW, "parallelism": f"dp{world}", "l2": "256 MiB L2 flush between timed steps (untimed)"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        base, step_s = cpu_reference_arm(max(1, min(args.steps, 3)), min(args.warmup, 1))
+        out = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps,
+               "warmup": args.warmup, "ms_per_step": step_s * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+               "dtype": "f32", "data": "synthetic", "config": cfg, "cpu_baseline": base,
+               "e2e": {"value": base["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(out))
+        return
+
+    import torch.distributed as dist
+    import mdcnet_b200 as M
+    from oracle import cases           # seeded weights / synthetic inputs only (no oracle compute on this arm)
+    assert torch.cuda.is_available(), "bench.py needs a B200"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    peaks = load_peaks()
+    model = cases.build_product_model("P", seed=0, gamma_seed=5).to(dev).set_precision("bf16")
+    tok = M.Tokenizer()
+    B = B_PER_GPU
+    x_host = cases.images(B, seed=1234 + rank).pin_memory()
+    x_dev = x_host.to(dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    T1, C = T_NEW + 1, (T_NEW + 3) // 4
+
+    def step_device():
+        toks, confs = model.generate_tokens(x_dev, T_NEW)
+        packed = M.parallel.pack_results(toks, confs)
+        return M.parallel.all_gather_results(packed, B * world)
+
+    def step_e2e():
+        bp, cf = M.generate(model, x_host, tok, max_len=T_NEW)       # H2D of x inside, D2H of tokens+confs inside
+        return bp
+
+    if args.profile:
+        step_device(); torch.cuda.synchronize()
+        n0 = M._lib.launch_count(dev)
+        step_device(); torch.cuda.synchronize()
+        print(json.dumps({"profile_step_launches": int(M._lib.launch_count(dev) - n0)}))
+        return
+
+    # warm-up (also builds the engine / tensor maps)
+    for _ in range(max(3, args.warmup)):
+        out = step_device()
+    torch.cuda.synchronize()
+
+    sampler = ClockSampler(local)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler.start()
+    n0 = M._lib.launch_count(dev)
+    for a, b in ev:
+        flush.fill_(1)
+        a.record()
+        out = step_device()
+        b.record()
+    torch.cuda.synchronize()
+    n1 = M._lib.launch_count(dev)
+    if world > 1:
+        dist.barrier()
+    clocks = sampler.stop()
+    total_ms = sum(a.elapsed_time(b) for a, b in ev)
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = t.item()
+    value = B * world * args.steps / (total_ms / 1e3)
+
+    # end-to-end through the public API with host buffers
+    for _ in range(2):
+        step_e2e()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_e2e()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_val = B * world * args.steps / t.item()
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # roofline of the dominant kernel, timed alone with CUDA events on this stream
+    roof = roofline_probe(M, dev, peaks, B)
+    out = {"metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+           "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+           "data": "synthetic", "config": cfg, "clocks": clocks,
+           "e2e": {"value": e2e_val, "unit": "images/s", "h2d_bytes_per_step": x_host.numel() * 4, "d2h_bytes_per_step": B * (T1 * 4 + C * 4)},
+           "gpu_launches": int(n1 - n0), "ms_per_decode_token": None, "roofline": roof}
+    # decode-only timing (ms per decode token at this batch)
+    out["ms_per_decode_token"] = decode_token_ms(M, model, x_dev, dev)
+    if not args.no_cpu_baseline:
+        out["cpu_baseline"], _ = cpu_reference_arm(1, 1)
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def decode_token_ms(M, model, x_dev, dev):
+    eng = model._engine(dev)
+    _, memory = eng.encode(x_dev, want_enc_out=False, want_memory=True)
+    ckv = eng.cross_kv(memory)
+    Bn = x_dev.shape[0]
+    tokens = torch.full((Bn, T_NEW + 1), 302, dtype=torch.int32, device=dev); tokens[:, 0] = 300
+    kv, scratch = eng.decode(ckv, tokens, 0, T_NEW, max_tokens=T_NEW, forced=False)
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    eng.decode(ckv, tokens, 0, T_NEW, max_tokens=T_NEW, forced=False, kv=kv, scratch=scratch)
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / T_NEW
+
+
+def roofline_probe(M, dev, peaks, B):
+    """Times the encoder's largest GEMM (mlp.fc1: M=B*197, N=2048, K=512, bias+GELU epilogue) alone."""
+    L = M._lib
+    Mr, N, K = B * 197, 2048, 512
+    A = (torch.randn(Mr, K, device=dev) * 0.5).to(torch.bfloat16)
+    W = (torch.randn(N, K, device=dev) * 0.05).to(torch.bfloat16)
+    bias = torch.zeros(N, device=dev)
+    D = torch.empty(Mr, N, dtype=torch.bfloat16, device=dev)
+
+    def run():
+        L.check(L.lib().mdc_gemm(L.ctx(dev), L.MDC_BF16, L.EPI_BIAS_GELU, L.ptr(A), K, L.ptr(W), K, L.ptr(D), N, L.ptr(bias), None, 0,
+                                 Mr, N, K, L.stream_ptr()))
+    for _ in range(5):
+        run()
+    torch.cuda.synchronize()
+    reps = 20
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(reps):
+        run()
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / reps
+    flops = 2.0 * Mr * N * K
+    ach = flops / (ms / 1e3) / 1e12
+    return {"kernel": "gemm_tc_kernel (mlp.fc1 shape, bias+GELU)", "bound": "tensor", "achieved": ach, "peak": peaks["bf16_tflops"],
+            "unit": "TFLOP/s", "frac": ach / peaks["bf16_tflops"], "traffic": None, "peak_src": peaks["src"] + " burst (kernel timed alone)",
+            "ms_per_launch": ms}
+
+
+if __name__ == "__main__":
+    main()

@@ -165,7 +165,7 @@ int launch_rows(mdc_ctx* ctx, const void* qkv, int64_t ld, void* out, int64_t ld
 #define MDC_ATTN_CASE(H)                                                                                         \
   {                                                                                                              \
     size_t smem = (size_t)(2 * H * KT + QB * H) * sizeof(float);                                                 \
-    MDC_CUDA(cudaFuncSetAttribute(strip_attn_kernel<T, H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    MDC_ENSURE_SMEM((strip_attn_kernel<T, H>), smem);                                                            \
     strip_attn_kernel<T, H><<<grid, block, smem, s>>>(in, ld, o, ldo, strip_len, heads, scale);                    \
   }
   if (hd == 32) MDC_ATTN_CASE(32)
@@ -180,7 +180,7 @@ template <typename T>
 int launch_cols(mdc_ctx* ctx, const void* qkv, int64_t ld, void* out, int64_t ldo, int n_strips, int n, int heads, int hd,
                 float scale, cudaStream_t s) {
   size_t smem = ((size_t)n * (n + 1) + 3 * (size_t)n * hd) * sizeof(float);
-  MDC_CUDA(cudaFuncSetAttribute(strip_attn_colsoftmax_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  MDC_ENSURE_SMEM(strip_attn_colsoftmax_kernel<T>, smem);
   strip_attn_colsoftmax_kernel<T><<<dim3(heads, n_strips), 256, smem, s>>>((const T*)qkv, ld, (T*)out, ldo, n, heads, hd, scale);
   MDC_LAUNCH_CHECK(ctx); return 0;
 }

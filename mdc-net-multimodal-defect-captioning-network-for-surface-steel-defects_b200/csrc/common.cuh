@@ -83,6 +83,16 @@ __device__ __forceinline__ void store8(bf16* p, const float* v) {
   *reinterpret_cast<uint4*>(p) = r;
 }
 
+// raise a kernel's dynamic-smem limit only when a launch needs more than any launch before it (one driver call, not one per launch)
+#define MDC_ENSURE_SMEM(kernel, bytes)                                                                          \
+  do {                                                                                                          \
+    static int cur__ = 48 * 1024;                                                                               \
+    if ((int)(bytes) > cur__) {                                                                                 \
+      MDC_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes)));        \
+      cur__ = (int)(bytes);                                                                                     \
+    }                                                                                                           \
+  } while (0)
+
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 static inline size_t esize(int dtype) { return dtype == MDC_BF16 ? 2 : 4; }
 

@@ -414,7 +414,7 @@ int launch_linear(mdc_ctx* ctx, const XSrc& xs, const void* W, const float* bias
   dim3 grid((N + LIN_WARPS * rw - 1) / (LIN_WARPS * rw), (B + BT - 1) / BT), block(LIN_THREADS);
 #define MDC_LIN(RW_, RELU_)                                                                                                  \
   {                                                                                                                          \
-    MDC_CUDA(cudaFuncSetAttribute(dec_linear_kernel<TW, RW_, RELU_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    MDC_ENSURE_SMEM((dec_linear_kernel<TW, RW_, RELU_>), smem);                                                              \
     dec_linear_kernel<TW, RW_, RELU_><<<grid, block, smem, s>>>(xs, (const TW*)W, bias, Y, ldy, B, N, K);                       \
   }
   if (rw == 4) { if (relu) MDC_LIN(4, true) else MDC_LIN(4, false) }
@@ -458,6 +458,7 @@ int decode_step_typed(mdc_model* m, const mdc_decode_state* st, int t, cudaStrea
     MDC_TRY(launch_linear<T>(ctx, x1, lw[MDC_SA_IN_W], (const float*)lw[MDC_SA_IN_B], sc.qkv, 3 * dim, B, 3 * dim, dim, false, s));
     {
       size_t smem = (size_t)d.dec_heads * (hd + t + 1) * sizeof(float);
+      MDC_ENSURE_SMEM(dec_self_attn_kernel<T>, smem);
       dec_self_attn_kernel<T><<<B, d.dec_heads * 32, smem, s>>>(sc.qkv, (T*)st->kv_pool, st->page_table, st->pages_per_seq, d.page_tokens,
                                                                d.dec_layers, l, st->tokens, st->tokens_ld, d.pad_idx, t, dim, hd, scale, sc.o);
       MDC_LAUNCH_CHECK(ctx);
@@ -471,7 +472,7 @@ int decode_step_typed(mdc_model* m, const mdc_decode_state* st, int t, cudaStrea
     {
       size_t smem = (size_t)d.dec_heads * (hd + d.n_patches) * sizeof(float);
       const T* ckv = (const T*)st->cross_kv + (int64_t)l * B * d.n_patches * 2 * dim;
-      if (smem > 48 * 1024) MDC_CUDA(cudaFuncSetAttribute(dec_cross_attn_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      MDC_ENSURE_SMEM(dec_cross_attn_kernel<T>, smem);
       dec_cross_attn_kernel<T><<<B, d.dec_heads * 32, smem, s>>>(sc.qc, ckv, d.n_patches, dim, hd, scale, sc.oc);
       MDC_LAUNCH_CHECK(ctx);
     }
@@ -489,7 +490,7 @@ int decode_step_typed(mdc_model* m, const mdc_decode_state* st, int t, cudaStrea
   {
     const int V = d.vocab, Vp2 = next_pow2(V);
     size_t smem = (size_t)(dim + V + Vp2) * sizeof(float);
-    MDC_CUDA(cudaFuncSetAttribute(dec_head_select_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MDC_ENSURE_SMEM(dec_head_select_kernel<T>, smem);
     dec_head_select_kernel<T><<<B, SEL_THREADS, smem, s>>>(prev, (const T*)gw[MDC_OUT_W], (const float*)gw[MDC_OUT_B], V, Vp2, dim, t,
                                                           st->logits, (int64_t)st->logits_ld * V, t + st->logits_row_offset, st->tokens,
                                                           st->tokens_ld, st->forced, st->confs, st->confs_ld, st->uniforms, st->uniforms_ld,

@@ -122,7 +122,7 @@ extern "C" int mdc_iou_batch(mdc_ctx* ctx, int mode, const float* pred, const fl
   int imgs_per_block = IOU_THREADS / (N > 0 ? N : 1) + 2;
   size_t smem = (size_t)imgs_per_block * M * sizeof(float4);
   MDC_CHECK_ARG(smem <= 200 * 1024);
-  if (smem > 48 * 1024) MDC_CUDA(cudaFuncSetAttribute(iou_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  MDC_ENSURE_SMEM(iou_batch_kernel, smem);
   iou_batch_kernel<<<grid, IOU_THREADS, smem, (cudaStream_t)stream>>>(mode, (const float4*)pred, (const float4*)gt, B, N, M, iou_out, max_out);
   MDC_LAUNCH_CHECK(ctx); return 0;
 }

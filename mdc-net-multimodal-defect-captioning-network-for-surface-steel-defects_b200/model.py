@@ -188,7 +188,7 @@ class Engine:
                 fw(l.norm3.weight); fw(l.norm3.bias)
         else:
             d.dim = d.dim or 32
-            d.dec_heads, d.dec_layers, d.dec_ffn, d.vocab, d.max_pos = 1, 0, 8, 1, 1
+            d.dec_heads, d.dec_layers, d.dec_ffn, d.vocab, d.max_pos = max(1, d.dim // 32), 0, 8, 1, 1
             table.extend([0] * len(L.DEC_GLOBAL))
         self.dims = d
         n = self.lib.mdc_model_num_weights(C.byref(d))
@@ -312,8 +312,13 @@ class _EngineOwner:
         return cache["engine"]
 
     def set_precision(self, precision):
+        """'bf16' (tcgen05 fast path) or 'fp32' (token-exact path); applies to every sub-module that owns an engine."""
         _precision_dtype(precision)
         self.precision = precision
+        if isinstance(self, nn.Module):
+            for m in self.modules():
+                if m is not self and isinstance(m, _EngineOwner):
+                    m.precision = precision
         return self
 
 

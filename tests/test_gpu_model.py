@@ -1,0 +1,160 @@
+"""GPU: the whole hot path behind the reference's API against (i) golden vectors produced by the
+UNMODIFIED reference and (ii) the oracle restatement on the same seeded weights/inputs.
+
+Contract (BASELINE.json north_star): fp32 path -> greedy token ids identical; bf16 path -> logits
+max-abs <= 2e-2 and cosine >= 0.999; IoU within 1e-6."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+import mdcnet_b200 as M  # noqa: E402
+from oracle import cases, mdc_oracle as O  # noqa: E402
+from tests import gpu_util as G  # noqa: E402
+
+DEV = "cuda"
+FP32_LOGIT_TOL = 2e-4     # fp32 CUDA vs fp32 CPU reference: summation-order noise only
+BF16_MAXABS, BF16_COS = 2e-2, 0.999
+
+
+@pytest.fixture(scope="module")
+def model_p():
+    return cases.build_product_model("P", seed=0, gamma_seed=5).to(DEV)
+
+
+@pytest.fixture(scope="module")
+def x2():
+    return cases.images(2).to(DEV)
+
+
+def test_fp32_encoder_predict_forward_vs_reference_golden(model_p, x2, golden):
+    g = golden("case_P_gamma.pt")
+    model_p.set_precision("fp32")
+    enc = model_p.encoder(x2)
+    assert (enc.cpu() - g["enc_out"]).abs().max().item() < 1e-4
+    pred = model_p.predict(x2, g["prefix"].to(DEV))
+    assert pred.shape == (2, 99, 305) and torch.all(pred[:, 0] == 300.0)
+    assert (pred.cpu() - g["predict"]).abs().max().item() < FP32_LOGIT_TOL
+    fwd = model_p(x2, g["prefix"][:, 1:].to(DEV))
+    assert fwd.shape == (2, 4, 305)
+    assert (fwd.cpu() - g["forward"]).abs().max().item() < FP32_LOGIT_TOL
+    # Decoder-level entry points with a caller-provided encoder_out
+    pred2 = model_p.decoder.predict(g["enc_out"].to(DEV), g["prefix"].to(DEV))
+    assert (pred2.cpu() - g["predict"]).abs().max().item() < FP32_LOGIT_TOL
+
+
+def test_fp32_greedy_tokens_exact_vs_reference_golden(model_p, x2, golden):
+    g = golden("case_P_gamma.pt")
+    model_p.set_precision("fp32")
+    toks, confs, logits = model_p.generate_tokens(x2, 24, return_logits=True)
+    err = (logits.cpu() - g["logits"]).abs().max().item()
+    top2 = g["logits"].topk(2, dim=-1)[0]
+    margin = (top2[..., 0] - top2[..., 1]).min().item()
+    print(f"fp32 path: max|dlogit| = {err:.2e}; reference min top1-top2 margin = {margin:.2e}")
+    assert err < FP32_LOGIT_TOL and err < margin
+    assert torch.equal(toks.cpu().long(), g["tokens"])
+    assert (confs.cpu() - g["confs"]).abs().max().item() < 1e-5
+    # public API: generate() -> CPU LongTensor + list of conf tensors (inference_p.py:90)
+    bp, cf = M.generate(model_p, x2, M.Tokenizer(), max_len=24)
+    assert bp.dtype == torch.long and bp.device.type == "cpu" and torch.equal(bp, g["tokens"])
+    assert len(cf) == 6 and all(c.shape == (2,) for c in cf)
+
+
+def test_fp32_as_constructed_weights_vs_reference_golden(x2, golden):
+    g = golden("case_P_init.pt")
+    m = cases.build_product_model("P", seed=0, gamma_seed=None).to(DEV).set_precision("fp32")
+    assert (m.encoder(x2).cpu()[:, ::7] - g["enc_out"]).abs().max().item() < 1e-4
+    toks, confs, logits = m.generate_tokens(x2, 12, return_logits=True)
+    assert (logits.cpu() - g["logits"]).abs().max().item() < FP32_LOGIT_TOL
+    assert torch.equal(toks.cpu().long(), g["tokens"])
+
+
+def test_fp32_full_length_decode_config_S(golden):
+    """T = 98 = the longest decode the reference's predict()[:, L] can express; pages cross 6 boundaries."""
+    g = golden("case_S_T98.pt")
+    m = cases.build_product_model("S", seed=1, gamma_seed=6).to(DEV).set_precision("fp32")
+    x = cases.images(3, seed=77).to(DEV)
+    toks, confs, logits = m.generate_tokens(x, 98, return_logits=True)
+    assert (logits.cpu()[:, ::3] - g["logits"]).abs().max().item() < FP32_LOGIT_TOL
+    assert torch.equal(toks.cpu().long(), g["tokens"])
+    assert (confs.cpu() - g["confs"]).abs().max().item() < 1e-5
+    # superset: one more step than the reference can index (position 98 exists in the pos table)
+    toks99, _ = m.generate_tokens(x, 99)
+    assert torch.equal(toks99[:, :99].cpu().long(), g["tokens"])
+    with pytest.raises(RuntimeError):
+        m.generate_tokens(x, 100)                          # Q6: no positional row left
+
+
+def test_bf16_logits_within_contract(model_p, x2, golden):
+    g = golden("case_P_gamma.pt")
+    model_p.set_precision("bf16")
+    enc = model_p.encoder(x2)
+    e_err = (enc.cpu() - g["enc_out"]).abs().max().item()
+    pred = model_p.predict(x2, g["prefix"].to(DEV))
+    err = (pred.cpu()[:, 1:] - g["predict"][:, 1:]).abs().max().item()
+    c = G.cos(pred.cpu()[:, 1:], g["predict"][:, 1:])
+    print(f"bf16 path: encoder max|d| = {e_err:.3e}; logits max|d| = {err:.3e}, cosine = {c:.6f}")
+    assert err <= BF16_MAXABS and c >= BF16_COS
+    # teacher-forced per-step logits along the reference's own greedy trajectory
+    toks = g["tokens"].to(DEV)
+    full = model_p.predict(x2, toks[:, :24])
+    step_logits = full[:, 1:25].cpu()
+    err2 = (step_logits - g["logits"]).abs().max().item()
+    assert err2 <= BF16_MAXABS and G.cos(step_logits, g["logits"]) >= BF16_COS
+
+
+def test_axial_variant_vs_reference_golden(x2, golden):
+    g = golden("case_axial.pt")
+    m = cases.build_product_model("P", seed=2, gamma_seed=7, axial=True).to(DEV).set_precision("fp32")
+    ax1 = m.decoder.axial_attention(g["xa"].to(DEV))
+    ax2 = m.decoder.axial_attention(g["xa"].to(DEV), axis=-2)
+    assert (ax1.cpu() - g["ax1"]).abs().max().item() < 2e-5
+    assert (ax2.cpu() - g["ax2"]).abs().max().item() < 2e-5
+    f12 = m(x2, g["tgt12"].to(DEV))
+    assert f12.shape == (2, 12, 305) and (f12.cpu() - g["f12"]).abs().max().item() < FP32_LOGIT_TOL
+    f99 = m(x2, g["tgt99"].to(DEV))
+    assert (f99.cpu()[:, ::9] - g["f99"]).abs().max().item() < FP32_LOGIT_TOL
+    m.set_precision("bf16")
+    f12b = m(x2, g["tgt12"].to(DEV))
+    assert (f12b.cpu() - g["f12"]).abs().max().item() <= BF16_MAXABS
+
+
+def test_topk_sampling_matches_oracle_draws(model_p, x2):
+    """top-k=5 (train_val_epoch.py:81) with shared uniforms: token-exact vs the oracle's inverse-CDF draw (fp32 path)."""
+    model_p.set_precision("fp32")
+    u = torch.rand(2, 16, generator=torch.Generator().manual_seed(4))
+    toks, confs = model_p.generate_tokens(x2, 16, top_k=5, uniforms=u.to(DEV))
+    sd = cases.state_dict_of(model_p.cpu()); model_p.to(DEV)
+    otoks, oconfs = O.generate(sd, x2.cpu(), cases.oracle_cfg("P"), max_len=16, top_k=5, uniforms=u)
+    assert torch.equal(toks.cpu().long(), otoks)
+    assert (confs.cpu() - torch.stack(oconfs, 1)).abs().max().item() < 1e-5
+
+
+def test_batch_invariance_at_bench_size(model_p):
+    """Config 2 size (B=64, T=99): every image's tokens must equal what it gets alone / in another slot
+    (no cross-image leakage through the paged KV pool, cross-K/V or workspace)."""
+    model_p.set_precision("bf16")
+    x = cases.images(64, seed=5).to(DEV)
+    toks, confs = model_p.generate_tokens(x, 99)
+    assert toks.shape == (64, 100) and torch.all(toks[:, 0] == 300)
+    assert torch.all((toks >= 0) & (toks < 305))
+    sub = torch.tensor([63, 0, 17])
+    toks_s, confs_s = model_p.generate_tokens(x[sub], 99)
+    assert torch.equal(toks_s, toks[sub])
+    assert torch.equal(confs_s, confs[sub])
+
+
+def test_load_state_dict_invalidates_prepared_weights(x2):
+    m = cases.build_product_model("S", seed=1, gamma_seed=6).to(DEV).set_precision("fp32")
+    a = m.predict(x2, torch.tensor([[300], [300]], device=DEV))
+    other = cases.build_product_model("S", seed=9, gamma_seed=6)
+    m.load_state_dict(other.state_dict())
+    b = m.predict(x2, torch.tensor([[300], [300]], device=DEV))
+    assert (a - b).abs().max().item() > 1e-3
+    want = O.model_predict(cases.state_dict_of(other), x2.cpu(), torch.tensor([[300], [300]]), cases.oracle_cfg("S"))
+    assert (b.cpu() - want).abs().max().item() < 2e-4
+
+
+def test_input_size_mismatch_raises_like_timm(model_p):
+    with pytest.raises(AssertionError):
+        model_p.encoder(torch.zeros(1, 3, 200, 200, device=DEV))

@@ -1,0 +1,179 @@
+"""GPU: every kernel behind the C ABI against a plain fp32/fp64 torch statement of the same op (and
+the reference-derived golden vectors for IoU).  Tolerances are stated per test."""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+import mdcnet_b200 as M  # noqa: E402
+from oracle import cases, mdc_oracle as O  # noqa: E402
+from tests import gpu_util as G  # noqa: E402
+
+L = M._lib
+DEV = "cuda"
+
+# (M, N, K): the encoder/decoder GEMM shapes of SURVEY 2.1 at small batch, ragged tails, and skinny cases
+GEMM_SHAPES = [(392, 512, 768), (394, 1536, 512), (394, 512, 512), (394, 2048, 512), (394, 512, 2048), (392, 512, 256),
+               (1, 512, 512), (127, 64, 64), (129, 72, 128), (300, 136, 192), (2000, 1536, 512)]
+
+
+def _mk(shape, dtype, seed):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return (torch.randn(shape, generator=g) * 0.5).to(DEV, dtype)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("shape", GEMM_SHAPES)
+def test_gemm_bias_epilogues(dtype, shape):
+    Mr, N, K = shape
+    A, W = _mk((Mr, K), dtype, 1), _mk((N, K), dtype, 2)
+    bias = _mk((N,), torch.float32, 3)
+    ref = A.double() @ W.double().T + bias.double()
+    # fp32: FFMA, K-ordered accumulation -> 1e-4 abs at |ref| ~ sqrt(K)/4; bf16: inputs exact in bf16, fp32 accumulate,
+    # output rounded to bf16 (rel 2^-8)
+    for epi, fn in [(L.EPI_BIAS, lambda r: r), (L.EPI_BIAS_RELU, torch.relu),
+                    (L.EPI_BIAS_GELU, lambda r: torch.nn.functional.gelu(r))]:
+        D = G.gemm(A, W, dtype, epi, bias=bias)
+        want = fn(ref)
+        err = (D.double() - want).abs().max().item()
+        tol = 2e-4 if dtype == torch.float32 else 2e-2 + want.abs().max().item() * 2 ** -8
+        assert err <= tol, (shape, dtype, epi, err, tol)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_gemm_layerscale_residual_and_patch_epilogues(dtype):
+    Mr, N, K = 394, 512, 2048
+    A, W = _mk((Mr, K), dtype, 1), _mk((N, K), dtype, 2)
+    bias, gamma = _mk((N,), torch.float32, 3), _mk((N,), torch.float32, 4)
+    R0 = _mk((Mr, N), torch.float32, 5)
+    R = R0.clone()
+    G.gemm(A, W, dtype, L.EPI_LS_RESIDUAL, bias=bias, aux0=gamma, R=R)
+    want = R0.double() + gamma.double() * (A.double() @ W.double().T + bias.double())
+    assert (R.double() - want).abs().max().item() < (5e-4 if dtype == torch.float32 else 5e-3)
+    # patch epilogue: 2 images x 196 patches -> rows shifted past each image's cls slot, + pos
+    Mr, K = 392, 768
+    A, W = _mk((Mr, K), dtype, 6), _mk((N, K), dtype, 7)
+    pos = _mk((196, N), torch.float32, 8)
+    R = torch.full((2 * 197, N), 7.0, dtype=torch.float32, device=DEV)
+    G.gemm(A, W, dtype, L.EPI_PATCH, bias=bias, aux0=pos, period=196, R=R)
+    want = (A.double() @ W.double().T + bias.double()).reshape(2, 196, N) + pos.double()
+    got = R.reshape(2, 197, N)
+    assert torch.all(got[:, 0] == 7.0)                      # cls rows untouched
+    assert (got[:, 1:].double() - want).abs().max().item() < (5e-4 if dtype == torch.float32 else 5e-3)
+
+
+def test_gemm_tcgen05_matches_ffma_on_same_bf16_inputs():
+    """The tensor-core kernel and the FFMA kernel see identical bf16 operands; only the summation order differs."""
+    A, W = _mk((1000, 512), torch.bfloat16, 1), _mk((1536, 512), torch.bfloat16, 2)
+    ref = (A.float() @ W.float().T)
+    D = G.gemm(A, W, torch.bfloat16, L.EPI_BIAS)
+    assert (D.float() - ref).abs().max().item() <= ref.abs().max().item() * 2 ** -7
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_layernorm(dtype):
+    x = _mk((777, 512), torch.float32, 1) * 3 + 1
+    w, b = _mk((512,), torch.float32, 2), _mk((512,), torch.float32, 3)
+    got = G.layernorm(x, w, b, 1e-6, dtype)
+    want = torch.nn.functional.layer_norm(x.double(), (512,), w.double(), b.double(), 1e-6)
+    assert (got.double() - want).abs().max().item() < (2e-5 if dtype == torch.float32 else 3e-2)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("cfg", [(3, 197, 8, 64, 0.125), (2, 99, 8, 32, 0.125), (28, 14, 8, 64, 0.125), (2, 17, 2, 128, 0.3),
+                                 (1, 1025, 8, 64, 0.125), (5, 1, 8, 32, 0.125)])
+def test_strip_attention(dtype, cfg):
+    n_strips, n, H, hd, scale = cfg
+    qkv = _mk((n_strips * n, 3 * H * hd), dtype, 4)
+    got = G.strip_attention(qkv, n_strips, n, H, hd, scale)
+    q, k, v = [t.reshape(n_strips, n, H, hd).transpose(1, 2).double() for t in qkv.chunk(3, dim=-1)]
+    want = (torch.softmax(q @ k.transpose(-1, -2) * scale, dim=-1) @ v).transpose(1, 2).reshape(n_strips * n, H * hd)
+    assert (got.double() - want).abs().max().item() < (2e-5 if dtype == torch.float32 else 1.5e-2)
+
+
+def test_strip_attention_softmax_over_queries():
+    n_strips, n, H, hd = 2, 17, 8, 32
+    qkv = _mk((n_strips * n, 3 * H * hd), torch.float32, 5)
+    got = G.strip_attention(qkv, n_strips, n, H, hd, 0.125, soq=1)
+    q, k, v = [t.reshape(n_strips, n, H, hd).transpose(1, 2).double() for t in qkv.chunk(3, dim=-1)]
+    want = (torch.softmax(q @ k.transpose(-1, -2) * 0.125, dim=-2) @ v).transpose(1, 2).reshape(n_strips * n, H * hd)
+    assert (got.double() - want).abs().max().item() < 2e-5
+
+
+def test_iou_kernels_bit_exact_against_reference_golden(golden):
+    g = golden("case_iou.pt")
+    p, q = g["pred"].to(DEV), g["gt"].to(DEV)
+    got = torch.stack(M.calculate_batch_iou(p, q)).cpu()
+    assert torch.equal(got, g["batch_iou"])                                  # bit-exact (contract: 1e-6)
+    assert torch.equal(torch.tensor(M.calculate_batch_max_iou(p, q)), g["max_iou"])
+    assert torch.equal(torch.tensor(M.calculate_batch_max_iou_torchvision(p, q)), g["max_iou_tv"])
+    assert torch.equal(M.giou_pairwise(p[2], q[2]).cpu(), g["giou_2"])
+    assert torch.equal(M.calculate_iou(p[2], q[2]).cpu(), g["calc_iou_2"])
+    assert torch.isnan(M.calculate_iou(p[3], q[4])).all()
+    assert abs(M.iou_loss(p[2], q[2]).item() - g["iou_loss_2"].item()) < 1e-6
+    loss, scores = M.giou_loss_with_scores(p, q)
+    assert abs(loss.item() - g["giou_loss"].item()) < 1e-6
+    assert len(scores) == len(g["giou_scores"])
+    for a, b in zip(scores, g["giou_scores"]):
+        assert a.shape == b.shape and (a.numel() == 0 or (a.cpu() - b).abs().max() < 1e-6)
+    assert abs(M.bbox_iou(torch.tensor([[0., 0, 10, 10]], device=DEV), torch.tensor([[5., 5, 15, 15]], device=DEV)).item() - 0.14285715) < 1e-7
+
+
+def test_iou_full_size_properties():
+    """BASELINE config 5 size (B=256, N<=19, M=5) and beyond: symmetry, self-IoU, range, oracle agreement."""
+    B, N, Mg = 4096, 19, 5
+    g = torch.Generator().manual_seed(3)
+    p = torch.rand(B, N, 4, generator=g) * 160; p[..., 2:] = p[..., :2] + 8 + torch.rand(B, N, 2, generator=g) * 56
+    q = torch.rand(B, Mg, 4, generator=g) * 160; q[..., 2:] = q[..., :2] + 8 + torch.rand(B, Mg, 2, generator=g) * 56
+    p[::7, 10:] = 0; q[::5, 3:] = 0
+    got = torch.stack(M.calculate_batch_iou(p.to(DEV), q.to(DEV))).cpu()
+    assert torch.equal(got, O.batch_iou(p, q))
+    rev = torch.stack(M.calculate_batch_iou(q.to(DEV), p.to(DEV))).cpu()
+    assert torch.equal(rev, got.transpose(1, 2))
+    assert got.min() >= 0 and got.max() <= 1
+    self_iou = torch.stack(M.calculate_batch_iou(q.to(DEV), q.to(DEV))).cpu()
+    d = torch.diagonal(self_iou, dim1=1, dim2=2)
+    assert torch.all((d > 0.999999) | (q.abs().sum(-1) == 0))
+    # empty batch edge cases
+    assert M.calculate_batch_max_iou(torch.zeros(2, 0, 4, device=DEV), torch.zeros(2, 3, 4, device=DEV)) == []
+
+
+def test_select_greedy_topk_topp_against_oracle():
+    torch.manual_seed(0)
+    logits = torch.randn(64, 305) * 3
+    logits[5, 17] = logits[5, 200] = logits[5].max() + 1          # tie -> first index
+    tok, conf = G.select(logits.to(DEV))
+    assert torch.equal(tok.cpu().long(), logits.argmax(-1))
+    assert tok[5].item() == 17
+    assert (conf.cpu() - torch.softmax(logits, -1).max(-1)[0]).abs().max() < 1e-6
+    u = torch.rand(64)
+    for k, p in [(5, 1.0), (0, 0.9), (7, 0.8), (1, 1.0), (305, 1.0)]:
+        filt = O.top_k_top_p_filtering(logits, top_k=k, top_p=p)
+        want = O.sample_from_uniform(filt, u)
+        tok, conf = G.select(logits.to(DEV), top_k=k, top_p=p, uniforms=u.to(DEV))
+        assert torch.equal(tok.cpu().long(), want), (k, p)
+        assert (conf.cpu() - torch.softmax(filt, -1).max(-1)[0]).abs().max() < 1e-6
+
+
+def test_preprocess_and_interp():
+    u8 = O.synth_gray_u8(3, hw=200, seed=9)
+    out = torch.empty((3, 3, 224, 224), dtype=torch.float32, device=DEV)
+    g = u8.to(DEV)
+    L.check(L.lib().mdc_preprocess_gray(L.ctx(DEV), L.ptr(g), 3, 200, 200, L.ptr(out), 224, L.stream_ptr()))
+    assert (out.cpu() - O.preprocess_gray(u8)).abs().max().item() < 1e-5
+    pos = torch.randn(1, 99, 256)
+    for n in (5, 13, 150, 257):
+        got = torch.empty((n, 256), dtype=torch.float32, device=DEV)
+        src = pos[0].to(DEV).contiguous()
+        L.check(L.lib().mdc_interp_rows(L.ctx(DEV), L.ptr(src), 99, L.ptr(got), n, 256, L.stream_ptr()))
+        assert (got.cpu() - O.interp_pos_embed(pos, n)[0]).abs().max().item() < 1e-6
+
+
+def test_bad_arguments_fail_loudly():
+    A = torch.zeros((4, 6), device=DEV)
+    with pytest.raises(L.MdcError):
+        G.gemm(A, A, torch.float32, L.EPI_BIAS)          # K % 4 != 0
+    with pytest.raises(L.MdcError):
+        G.strip_attention(torch.zeros((4, 3 * 8 * 24), device=DEV), 1, 4, 8, 24, 1.0)   # head_dim unsupported
