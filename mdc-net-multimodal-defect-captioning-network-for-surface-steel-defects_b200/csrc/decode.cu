@@ -17,7 +17,11 @@
 // next residual), so no projection needs a full-row epilogue and all of them spread over the SMs.
 // The head kernel fuses LN3 + vocab projection + greedy / top-k / top-p select + max-prob.
 #include "common.cuh"
+#include "select.cuh"
 #include <float.h>
+
+int decode_cluster_supported(const mdc_model* m, const mdc_decode_state* st, int t_end);
+int decode_cluster_launch(mdc_model* m, const mdc_decode_state* st, int t_begin, int t_end, void* logits_scratch, cudaStream_t s);
 
 namespace {
 
@@ -68,42 +72,168 @@ __device__ __forceinline__ void load_x_tile(const XSrc& xs, float* Xs, int b0, i
   }
 }
 
-// Y[B,N] = act(Xeff[B,K] . W[N,K]^T + bias).  grid = (N / (LIN_WARPS*RW), ceil(B/BT)).
-// A warp owns RW output columns; lanes split K in 8-element (128-bit) slices.
-template <typename TW, int RW, bool RELU>
+// Compile-time-K operand tile: every global load of the tile is in flight before the first use.
+//   PLAIN : cp.async 16-byte chunks straight into shared memory
+//   LN    : a warp owns rows (warp, warp+8); both rows' residual+delta slices are loaded as float4 first
+//   EMBED : token ids first (one round trip), then both embedding rows + the positional row
+__device__ __forceinline__ void cp_async16(float* smem_dst, const float* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory"); }
+
+template <int K>
+__device__ __forceinline__ void load_x_tile_fast(const XSrc& xs, float* Xs, int b0, int B, bool publish) {
+  static_assert(K % 128 == 0, "K must be a multiple of 128");
+  constexpr int V4 = K / 128;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (xs.mode == XMODE_PLAIN) {
+    constexpr int CH = K / 4;   // 16-byte chunks per row
+#pragma unroll 8
+    for (int i = threadIdx.x; i < BT * CH; i += LIN_THREADS) {
+      const int r = i / CH, c4 = i - r * CH, b = b0 + r;
+      if (b < B) cp_async16(Xs + (size_t)r * K + c4 * 4, xs.x + (int64_t)b * xs.ldx + c4 * 4);
+      else *reinterpret_cast<float4*>(Xs + (size_t)r * K + c4 * 4) = make_float4(0, 0, 0, 0);
+    }
+    cp_async_wait_all();
+    if (publish && xs.xn_out) {
+      __syncthreads();
+      for (int i = threadIdx.x; i < BT * CH; i += LIN_THREADS) {
+        const int r = i / CH, c4 = i - r * CH, b = b0 + r;
+        if (b < B) *reinterpret_cast<float4*>(xs.xn_out + (int64_t)b * K + c4 * 4) = *reinterpret_cast<const float4*>(Xs + (size_t)r * K + c4 * 4);
+      }
+    }
+    return;
+  }
+  if constexpr (K > 1024) { return; } else {   // LN / EMBED rows are model-width (<= 1024); wider K is only ever a PLAIN operand
+  float4 v[2][V4];
+  if (xs.mode == XMODE_EMBED) {
+    int tok[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) { const int b = b0 + warp + 8 * h; tok[h] = (b < B) ? xs.tokens[(int64_t)b * xs.tokens_ld + xs.t] : 0; }
+    float4 pz[V4];
+#pragma unroll
+    for (int i = 0; i < V4; ++i) pz[i] = __ldg(reinterpret_cast<const float4*>(xs.pos + (int64_t)xs.t * K + (i * 32 + lane) * 4));
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+#pragma unroll
+      for (int i = 0; i < V4; ++i) v[h][i] = __ldg(reinterpret_cast<const float4*>(xs.emb + (int64_t)tok[h] * K + (i * 32 + lane) * 4));
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+#pragma unroll
+      for (int i = 0; i < V4; ++i) { v[h][i].x += pz[i].x; v[h][i].y += pz[i].y; v[h][i].z += pz[i].z; v[h][i].w += pz[i].w; }
+  } else {  // XMODE_LN
+    float4 dl[2][V4];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int b = min(b0 + warp + 8 * h, B - 1);
+#pragma unroll
+      for (int i = 0; i < V4; ++i) {
+        v[h][i] = *reinterpret_cast<const float4*>(xs.resid + (int64_t)b * K + (i * 32 + lane) * 4);
+        dl[h][i] = *reinterpret_cast<const float4*>(xs.delta + (int64_t)b * K + (i * 32 + lane) * 4);
+      }
+    }
+    float4 g[V4], be[V4];
+#pragma unroll
+    for (int i = 0; i < V4; ++i) {
+      g[i] = __ldg(reinterpret_cast<const float4*>(xs.ln_w + (i * 32 + lane) * 4));
+      be[i] = __ldg(reinterpret_cast<const float4*>(xs.ln_b + (i * 32 + lane) * 4));
+    }
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      float sum = 0.f;
+#pragma unroll
+      for (int i = 0; i < V4; ++i) {
+        v[h][i].x += dl[h][i].x; v[h][i].y += dl[h][i].y; v[h][i].z += dl[h][i].z; v[h][i].w += dl[h][i].w;
+        sum += (v[h][i].x + v[h][i].y) + (v[h][i].z + v[h][i].w);
+      }
+      const float mean = warp_sum(sum) / (float)K;
+      float q = 0.f;
+#pragma unroll
+      for (int i = 0; i < V4; ++i) {
+        float a0 = v[h][i].x - mean, a1 = v[h][i].y - mean, a2 = v[h][i].z - mean, a3 = v[h][i].w - mean;
+        q += (a0 * a0 + a1 * a1) + (a2 * a2 + a3 * a3);
+      }
+      const float rstd = 1.0f / sqrtf(warp_sum(q) / (float)K + xs.eps);
+#pragma unroll
+      for (int i = 0; i < V4; ++i) {
+        v[h][i].x = (v[h][i].x - mean) * rstd * g[i].x + be[i].x; v[h][i].y = (v[h][i].y - mean) * rstd * g[i].y + be[i].y;
+        v[h][i].z = (v[h][i].z - mean) * rstd * g[i].z + be[i].z; v[h][i].w = (v[h][i].w - mean) * rstd * g[i].w + be[i].w;
+      }
+    }
+  }
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int r = warp + 8 * h, b = b0 + r;
+#pragma unroll
+    for (int i = 0; i < V4; ++i) {
+      *reinterpret_cast<float4*>(Xs + (size_t)r * K + (i * 32 + lane) * 4) = (b < B) ? v[h][i] : make_float4(0, 0, 0, 0);
+      if (publish && xs.xn_out && b < B) *reinterpret_cast<float4*>(xs.xn_out + (int64_t)b * K + (i * 32 + lane) * 4) = v[h][i];
+    }
+  }
+  }
+}
+
+// raw 8-element weight slice held in registers until the operand tile is ready
+template <typename T> struct Raw8;
+template <> struct Raw8<bf16> {
+  uint4 v;
+  __device__ __forceinline__ void load(const bf16* p) { v = __ldg(reinterpret_cast<const uint4*>(p)); }
+  __device__ __forceinline__ void zero() { v = make_uint4(0, 0, 0, 0); }
+  __device__ __forceinline__ void unpack(float* f) const {
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { float2 t = __bfloat1622float2(h[i]); f[2 * i] = t.x; f[2 * i + 1] = t.y; }
+  }
+};
+template <> struct Raw8<float> {
+  float4 a, b;
+  __device__ __forceinline__ void load(const float* p) { a = __ldg(reinterpret_cast<const float4*>(p)); b = __ldg(reinterpret_cast<const float4*>(p + 4)); }
+  __device__ __forceinline__ void zero() { a = make_float4(0, 0, 0, 0); b = a; }
+  __device__ __forceinline__ void unpack(float* f) const { f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w; }
+};
+
+// Y[B,N] = act(Xeff[B,K] . W[N,K]^T + bias), K = KCH*256.  grid = (N / (LIN_WARPS*RW), ceil(B/BT)).
+// A warp owns RW output columns; lanes split K in 8-element (128-bit) slices.  ALL of the warp's weight
+// slices are requested before the operand tile is built, so the weight fetch, the operand fetch and the
+// LayerNorm-on-load overlap instead of forming a chain of dependent round trips.
+template <typename TW, int RW, int KCH, bool RELU>
 __global__ void __launch_bounds__(LIN_THREADS) dec_linear_kernel(XSrc xs, const TW* __restrict__ W, const float* __restrict__ bias,
-                                                                  float* __restrict__ Y, int64_t ldy, int B, int N, int K) {
+                                                                  float* __restrict__ Y, int64_t ldy, int B, int N) {
+  constexpr int K = KCH * 256;
   extern __shared__ __align__(16) float Xs[];
   const int b0 = blockIdx.y * BT;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n0 = (blockIdx.x * LIN_WARPS + warp) * RW;
-  // issue the weight loads for the first K slice before the operand tile is built (overlaps latency)
-  load_x_tile(xs, Xs, b0, B, K, blockIdx.x == 0);
+  Raw8<TW> w[RW][KCH];
+#pragma unroll
+  for (int c = 0; c < RW; ++c)
+#pragma unroll
+    for (int kc = 0; kc < KCH; ++kc) {
+      if (n0 + c < N) w[c][kc].load(W + (int64_t)(n0 + c) * K + kc * 256 + lane * 8);
+      else w[c][kc].zero();
+    }
+  load_x_tile_fast<K>(xs, Xs, b0, B, blockIdx.x == 0);
   __syncthreads();
   float acc[RW][BT];
 #pragma unroll
   for (int c = 0; c < RW; ++c)
 #pragma unroll
     for (int r = 0; r < BT; ++r) acc[c][r] = 0.f;
-  for (int k0 = lane * 8; k0 < K; k0 += 256) {
-    float w[RW][8];
 #pragma unroll
-    for (int c = 0; c < RW; ++c) {
-      if (n0 + c < N) load8(W + (int64_t)(n0 + c) * K + k0, w[c]);
-      else {
+  for (int kc = 0; kc < KCH; ++kc) {
+    float wf[RW][8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) w[c][j] = 0.f;
-      }
-    }
+    for (int c = 0; c < RW; ++c) w[c][kc].unpack(wf[c]);
+    const float* xp = Xs + kc * 256 + lane * 8;
 #pragma unroll
     for (int r = 0; r < BT; ++r) {
-      float4 xa = *reinterpret_cast<const float4*>(Xs + (size_t)r * K + k0);
-      float4 xb = *reinterpret_cast<const float4*>(Xs + (size_t)r * K + k0 + 4);
+      float4 xa = *reinterpret_cast<const float4*>(xp + (size_t)r * K);
+      float4 xb = *reinterpret_cast<const float4*>(xp + (size_t)r * K + 4);
 #pragma unroll
       for (int c = 0; c < RW; ++c) {
         float a = acc[c][r];
-        a = fmaf(w[c][0], xa.x, a); a = fmaf(w[c][1], xa.y, a); a = fmaf(w[c][2], xa.z, a); a = fmaf(w[c][3], xa.w, a);
-        a = fmaf(w[c][4], xb.x, a); a = fmaf(w[c][5], xb.y, a); a = fmaf(w[c][6], xb.z, a); a = fmaf(w[c][7], xb.w, a);
+        a = fmaf(wf[c][0], xa.x, a); a = fmaf(wf[c][1], xa.y, a); a = fmaf(wf[c][2], xa.z, a); a = fmaf(wf[c][3], xa.w, a);
+        a = fmaf(wf[c][4], xb.x, a); a = fmaf(wf[c][5], xb.y, a); a = fmaf(wf[c][6], xb.z, a); a = fmaf(wf[c][7], xb.w, a);
         acc[c][r] = a;
       }
     }
@@ -115,7 +245,7 @@ __global__ void __launch_bounds__(LIN_THREADS) dec_linear_kernel(XSrc xs, const 
 #pragma unroll
     for (int r = 0; r < BT; ++r) {
       float v = warp_sum(acc[c][r]);
-      if (lane == (r & 31) && n < N && b0 + r < B) {
+      if (lane == r && n < N && b0 + r < B) {
         v += bv;
         if (RELU) v = fmaxf(v, 0.f);
         Y[(int64_t)(b0 + r) * ldy + n] = v;
@@ -124,64 +254,133 @@ __global__ void __launch_bounds__(LIN_THREADS) dec_linear_kernel(XSrc xs, const 
   }
 }
 
-// ---- attention of ONE query per (image, head) over a key/value set ---------------------------------
-// warp == head.  Scores go to shared memory; softmax max/sum are warp shuffles; P.V splits the warp
-// into (key subgroup, 8-channel chunk) so every V access is a 128-bit load.
-template <typename TKV, typename KeyPtr, typename Bias>
-__device__ __forceinline__ void attend_one(const float* q /*smem, hd, pre-scaled*/, float* sc /*smem, nkeys*/, int nkeys, int hd,
-                                           KeyPtr kv_ptr, Bias bias, float* out /*global or smem, hd*/) {
-  const int lane = threadIdx.x & 31;
-  float mx = -INFINITY;
-  for (int u = lane; u < nkeys; u += 32) {
-    const TKV* kp = kv_ptr(u, 0);
-    float s = 0.f;
-    for (int c = 0; c < hd; c += 8) {
-      float kv[8]; load8(kp + c, kv);
+// generic-K variant (K % 8 == 0 only; e.g. the 64-wide tiny configuration)
+template <typename TW, bool RELU>
+__global__ void __launch_bounds__(LIN_THREADS) dec_linear_generic_kernel(XSrc xs, const TW* __restrict__ W, const float* __restrict__ bias,
+                                                                          float* __restrict__ Y, int64_t ldy, int B, int N, int K) {
+  extern __shared__ __align__(16) float Xs[];
+  const int b0 = blockIdx.y * BT;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n = blockIdx.x * LIN_WARPS + warp;
+  load_x_tile(xs, Xs, b0, B, K, blockIdx.x == 0);
+  __syncthreads();
+  float acc[BT];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) s = fmaf(q[c + j], kv[j], s);
+  for (int r = 0; r < BT; ++r) acc[r] = 0.f;
+  for (int k0 = lane * 8; k0 < K; k0 += 256) {
+    float w[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (n < N) load8(W + (int64_t)n * K + k0, w);
+#pragma unroll
+    for (int r = 0; r < BT; ++r) {
+      float4 xa = *reinterpret_cast<const float4*>(Xs + (size_t)r * K + k0);
+      float4 xb = *reinterpret_cast<const float4*>(Xs + (size_t)r * K + k0 + 4);
+      float a = acc[r];
+      a = fmaf(w[0], xa.x, a); a = fmaf(w[1], xa.y, a); a = fmaf(w[2], xa.z, a); a = fmaf(w[3], xa.w, a);
+      a = fmaf(w[4], xb.x, a); a = fmaf(w[5], xb.y, a); a = fmaf(w[6], xb.z, a); a = fmaf(w[7], xb.w, a);
+      acc[r] = a;
     }
-    s += bias(u);
-    sc[u] = s; mx = fmaxf(mx, s);
+  }
+  const float bv = (n < N && bias) ? bias[n] : 0.f;
+#pragma unroll
+  for (int r = 0; r < BT; ++r) {
+    float v = warp_sum(acc[r]);
+    if (lane == r && n < N && b0 + r < B) {
+      v += bv;
+      if (RELU) v = fmaxf(v, 0.f);
+      Y[(int64_t)(b0 + r) * ldy + n] = v;
+    }
+  }
+}
+
+// ---- attention of ONE query per (image, head) over a key/value set ---------------------------------
+// warp == head.  A key's HD channels are split over LPK = HD/8 lanes (one 128-bit load each), so a warp
+// covers 32/LPK keys per pass with fully-used sectors; passes are unrolled x4 with the loads issued first
+// (memory-level parallelism instead of a chain of dependent round trips).  Softmax max/sum are warp
+// shuffles; P.V uses the same (key slot, 8-channel chunk) lane mapping.
+template <typename TKV, int HD, typename KeyPtr, typename Bias>
+__device__ __forceinline__ void attend_one(const float* q /*smem, HD, pre-scaled*/, float* sc /*smem, nkeys*/, int nkeys,
+                                           KeyPtr kv_ptr, Bias bias, float* out /*HD*/) {
+  constexpr int LPK = HD / 8, KPI = 32 / LPK, UN = 4;
+  const int lane = threadIdx.x & 31, sub = lane % LPK, kslot = lane / LPK;
+  float qv[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) qv[j] = q[sub * 8 + j];
+  float mx = -INFINITY;
+  for (int u0 = 0; u0 < nkeys; u0 += KPI * UN) {
+    Raw8<TKV> r[UN];
+#pragma unroll
+    for (int i = 0; i < UN; ++i) {
+      const int u = u0 + i * KPI + kslot;
+      if (u < nkeys) r[i].load(kv_ptr(u, 0) + sub * 8); else r[i].zero();
+    }
+#pragma unroll
+    for (int i = 0; i < UN; ++i) {
+      const int u = u0 + i * KPI + kslot;
+      float kf[8]; r[i].unpack(kf);
+      float sdot = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) sdot = fmaf(qv[j], kf[j], sdot);
+#pragma unroll
+      for (int o = 1; o < LPK; o <<= 1) sdot += __shfl_xor_sync(0xffffffffu, sdot, o);
+      if (u < nkeys) {
+        sdot += bias(u);
+        if (sub == 0) sc[u] = sdot;
+        mx = fmaxf(mx, sdot);
+      }
+    }
   }
   mx = warp_max(mx);
+  __syncwarp();
   float sum = 0.f;
   for (int u = lane; u < nkeys; u += 32) { float e = expf(sc[u] - mx); sc[u] = e; sum += e; }
   sum = warp_sum(sum);
   __syncwarp();
-  const int DC = hd / 8, KS = 32 / DC;       // hd in {32,64,128} -> DC in {4,8,16}
-  const int dc = lane % DC, ks = lane / DC;
   float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  for (int u = ks; u < nkeys; u += KS) {
-    float p = sc[u];
-    float vv[8]; load8(kv_ptr(u, 1) + dc * 8, vv);
+  for (int u0 = 0; u0 < nkeys; u0 += KPI * UN) {
+    Raw8<TKV> r[UN];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = fmaf(p, vv[j], acc[j]);
+    for (int i = 0; i < UN; ++i) {
+      const int u = u0 + i * KPI + kslot;
+      if (u < nkeys) r[i].load(kv_ptr(u, 1) + sub * 8); else r[i].zero();
+    }
+#pragma unroll
+    for (int i = 0; i < UN; ++i) {
+      const int u = u0 + i * KPI + kslot;
+      const float p = (u < nkeys) ? sc[u] : 0.f;
+      float vf[8]; r[i].unpack(vf);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = fmaf(p, vf[j], acc[j]);
+    }
   }
-  for (int o = DC; o < 32; o <<= 1) {
+#pragma unroll
+  for (int o = LPK; o < 32; o <<= 1) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], o);
   }
-  if (ks == 0) {
-    float inv = 1.0f / sum;
+  if (kslot == 0) {
+    const float inv = 1.0f / sum;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) out[dc * 8 + j] = acc[j] * inv;
+    for (int j = 0; j < 8; ++j) out[sub * 8 + j] = acc[j] * inv;
   }
   __syncwarp();
 }
 
 // self-attention: appends this step's k,v to the paged cache, then attends over slots 0..t.
 // pool layout: [page][layer][k|v][page_tokens][d]
-template <typename TKV>
+template <typename TKV, int HD>
 __global__ void dec_self_attn_kernel(const float* __restrict__ qkv /*[B,3d]*/, TKV* __restrict__ pool,
                                      const int32_t* __restrict__ page_table, int pages_per_seq, int PT, int n_layers, int layer,
-                                     const int32_t* __restrict__ tokens, int tokens_ld, int pad_idx, int t, int d, int hd,
+                                     const int32_t* __restrict__ tokens, int tokens_ld, int pad_idx, int t, int d,
                                      float scale, float* __restrict__ o /*[B,d]*/) {
+  constexpr int hd = HD;
   extern __shared__ float sm[];
   const int b = blockIdx.x, head = threadIdx.x >> 5, lane = threadIdx.x & 31, heads = blockDim.x >> 5;
   float* q = sm + head * hd;
   float* sc = sm + heads * hd + head * (t + 1);
+  int* pt = reinterpret_cast<int*>(sm + heads * (hd + t + 1)) + head * pages_per_seq;   // per-warp copy of the page ids: one round trip
   const float* row = qkv + (int64_t)b * 3 * d;
-  const int32_t* pt = page_table + (int64_t)b * pages_per_seq;
+  for (int j = lane; j <= t / PT; j += 32) pt[j] = page_table[(int64_t)b * pages_per_seq + j];
+  __syncwarp();
   const int64_t plane = (int64_t)PT * d;                    // one k or v plane of a page/layer
   {  // append k_t, v_t (this head's channels) and stage q
     TKV* kdst = pool + (((int64_t)pt[t / PT] * n_layers + layer) * 2) * plane + (int64_t)(t % PT) * d + head * hd;
@@ -196,13 +395,14 @@ __global__ void dec_self_attn_kernel(const float* __restrict__ qkv /*[B,3d]*/, T
     return pool + (((int64_t)pt[u / PT] * n_layers + layer) * 2 + which) * plane + (int64_t)(u % PT) * d + head * hd;
   };
   auto bias = [&](int u) -> float { return tokens[(int64_t)b * tokens_ld + u] == pad_idx ? 1.0f : 0.0f; };
-  attend_one<TKV>(q, sc, t + 1, hd, kv_ptr, bias, o + (int64_t)b * d + head * hd);
+  attend_one<TKV, HD>(q, sc, t + 1, kv_ptr, bias, o + (int64_t)b * d + head * hd);
 }
 
 // cross-attention over the S memory keys of image b; cross_kv layer plane: [B*S][2d] (K | V)
-template <typename TKV>
+template <typename TKV, int HD>
 __global__ void dec_cross_attn_kernel(const float* __restrict__ qc /*[B,d]*/, const TKV* __restrict__ ckv_layer, int S, int d,
-                                      int hd, float scale, float* __restrict__ o) {
+                                      float scale, float* __restrict__ o) {
+  constexpr int hd = HD;
   extern __shared__ float sm[];
   const int b = blockIdx.x, head = threadIdx.x >> 5, lane = threadIdx.x & 31, heads = blockDim.x >> 5;
   float* q = sm + head * hd;
@@ -212,170 +412,27 @@ __global__ void dec_cross_attn_kernel(const float* __restrict__ qc /*[B,d]*/, co
   const TKV* base = ckv_layer + (int64_t)b * S * 2 * d + head * hd;
   auto kv_ptr = [&](int u, int which) -> const TKV* { return base + (int64_t)u * 2 * d + which * d; };
   auto bias = [&](int) -> float { return 0.f; };
-  attend_one<TKV>(q, sc, S, hd, kv_ptr, bias, o + (int64_t)b * d + head * hd);
+  attend_one<TKV, HD>(q, sc, S, kv_ptr, bias, o + (int64_t)b * d + head * hd);
 }
 
-// ---- select -------------------------------------------------------------------------------------
-constexpr int SEL_THREADS = 256;
+using namespace mdcsel;
 
-__device__ __forceinline__ void block_argmax(float v, int idx, float* s_val, int* s_idx, float& out_v, int& out_i) {
-  // max value, lowest index on ties (torch.argmax returns the first maximal index)
-  for (int o = 16; o > 0; o >>= 1) {
-    float ov = __shfl_xor_sync(0xffffffffu, v, o); int oi = __shfl_xor_sync(0xffffffffu, idx, o);
-    if (ov > v || (ov == v && oi < idx)) { v = ov; idx = oi; }
-  }
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (lane == 0) { s_val[warp] = v; s_idx[warp] = idx; }
-  __syncthreads();
-  if (warp == 0) {
-    v = lane < (SEL_THREADS / 32) ? s_val[lane] : -INFINITY; idx = lane < (SEL_THREADS / 32) ? s_idx[lane] : 0x7fffffff;
-    for (int o = 16; o > 0; o >>= 1) {
-      float ov = __shfl_xor_sync(0xffffffffu, v, o); int oi = __shfl_xor_sync(0xffffffffu, idx, o);
-      if (ov > v || (ov == v && oi < idx)) { v = ov; idx = oi; }
-    }
-    if (lane == 0) { s_val[0] = v; s_idx[0] = idx; }
-  }
-  __syncthreads();
-  out_v = s_val[0]; out_i = s_idx[0];
-  __syncthreads();
-}
 
-__device__ __forceinline__ double block_sum_d(double v, double* s_d) {
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (lane == 0) s_d[warp] = v;
-  __syncthreads();
-  double tot = 0.0;
-  for (int i = 0; i < SEL_THREADS / 32; ++i) tot += s_d[i];
-  __syncthreads();
-  return tot;
-}
-
-// lg: V logits in shared memory (may be overwritten with the filtered logits); srt: scratch of
-// next_pow2(V) floats.  Returns (token, conf) in thread 0.
-// Semantics: transformers top_k_top_p_filtering (inference_p.py:83) -> conf = max softmax prob of the
-// filtered logits (inference_p.py:84-86) -> greedy argmax (inference_p.py:77) or inverse-CDF draw with u.
-__device__ void select_from_logits(float* lg, float* srt, int V, int Vp2, int top_k, float top_p, bool sample, float u,
-                                   int& token, float& conf) {
-  __shared__ float s_val[SEL_THREADS / 32]; __shared__ int s_idx[SEL_THREADS / 32];
-  __shared__ double s_d[SEL_THREADS / 32]; __shared__ double s_scan[SEL_THREADS]; __shared__ int s_first;
-  const int tid = threadIdx.x;
-  if (top_k > 0 || top_p < 1.0f) {
-    for (int i = tid; i < Vp2; i += SEL_THREADS) srt[i] = i < V ? lg[i] : -INFINITY;
-    __syncthreads();
-    for (int k = 2; k <= Vp2; k <<= 1)            // bitonic sort, descending
-      for (int j = k >> 1; j > 0; j >>= 1) {
-        for (int i = tid; i < Vp2; i += SEL_THREADS) {
-          int ixj = i ^ j;
-          if (ixj > i) {
-            float a = srt[i], b = srt[ixj];
-            bool desc = (i & k) == 0;
-            if (desc ? (a < b) : (a > b)) { srt[i] = b; srt[ixj] = a; }
-          }
-        }
-        __syncthreads();
-      }
-    float cut = -INFINITY;
-    int kept = V;
-    if (top_k > 0) { int k = min(max(top_k, 1), V); cut = srt[k - 1]; }
-    if (top_k > 0) {  // entries strictly below the k-th largest are removed (ties at the k-th kept)
-      int cnt = 0;
-      for (int i = tid; i < V; i += SEL_THREADS) cnt += (srt[i] >= cut);
-      double c = block_sum_d((double)cnt, s_d);
-      kept = (int)c;
-    }
-    if (top_p < 1.0f) {
-      // ascending cumulative softmax over the kept entries = suffix sums of the descending array
-      float mx = srt[0];
-      double part = 0.0;
-      for (int i = tid; i < kept; i += SEL_THREADS) part += (double)expf(srt[i] - mx);
-      double total = block_sum_d(part, s_d);
-      // thread 0 walks from the smallest kept entry upwards (V <= 4096; kept is small after top-k)
-      if (tid == 0) {
-        float cum = 0.f; int removed = 0;
-        for (int i = kept - 1; i >= 1; --i) {      // never remove the largest (min_tokens_to_keep = 1)
-          cum += (float)((double)expf(srt[i] - mx) / total);
-          if (cum <= 1.0f - top_p) removed++; else break;
-        }
-        s_first = kept - removed;                  // number of entries kept from the top
-      }
-      __syncthreads();
-      int nk = s_first;
-      cut = fmaxf(cut, srt[nk - 1]);
-      __syncthreads();
-    }
-    for (int i = tid; i < V; i += SEL_THREADS) if (lg[i] < cut) lg[i] = -INFINITY;
-    __syncthreads();
-  }
-  float bv = -INFINITY; int bi = 0x7fffffff;
-  for (int i = tid; i < V; i += SEL_THREADS) { float v = lg[i]; if (v > bv) { bv = v; bi = i; } }
-  float mx; int amax;
-  block_argmax(bv, bi, s_val, s_idx, mx, amax);
-  // softmax denominator in fp32 (conf) and, for sampling, probabilities in double (matches the oracle's draw)
-  const int EPT = (V + SEL_THREADS - 1) / SEL_THREADS;
-  double local = 0.0; float localf = 0.f;
-  for (int j = 0; j < EPT; ++j) {
-    int i = tid * EPT + j;
-    if (i < V) { float e = expf(lg[i] - mx); localf += e; if (sample) local += exp((double)lg[i] - (double)mx); }
-  }
-  double totf = block_sum_d((double)localf, s_d);
-  float cf = 1.0f / (float)totf;
-  int tok = amax;
-  if (sample) {
-    s_scan[tid] = local;
-    __syncthreads();
-    if (tid == 0) { double run = 0.0; for (int i = 0; i < SEL_THREADS; ++i) { double v = s_scan[i]; s_scan[i] = run; run += v; } s_d[0] = run; s_first = V - 1; }
-    __syncthreads();
-    double total = s_d[0], thr = (double)u * total, run = s_scan[tid];
-    int mine = 0x7fffffff;
-    for (int j = 0; j < EPT; ++j) {
-      int i = tid * EPT + j;
-      if (i < V) { run += exp((double)lg[i] - (double)mx); if (run > thr && mine == 0x7fffffff) mine = i; }
-    }
-    if (mine != 0x7fffffff) atomicMin(&s_first, mine);
-    __syncthreads();
-    tok = s_first;
-    __syncthreads();
-  }
-  token = tok; conf = cf;
-}
-
-// head: logits = LN3(xc + y3) . Wout^T + bout, then select.  One CTA per image.
-template <typename TW>
-__global__ void __launch_bounds__(SEL_THREADS) dec_head_select_kernel(XSrc xs, const TW* __restrict__ Wout, const float* __restrict__ bout,
-                                                                       int V, int Vp2, int K, int t, float* __restrict__ logits_out,
-                                                                       int64_t logits_img_stride, int logits_row, int32_t* __restrict__ tokens,
-                                                                       int tokens_ld, int forced, float* __restrict__ confs, int confs_ld,
-                                                                       const float* __restrict__ uniforms, int uniforms_ld, int top_k, float top_p) {
+// select for the decode loop: reads the step's logits [B,V] (written by the head linear), optionally copies them
+// to the caller's logits tensor, then greedy / top-k / top-p select + max-prob.  One CTA per image.
+__global__ void __launch_bounds__(SEL_THREADS) dec_select_kernel(const float* __restrict__ step_logits, int V, int Vp2, int t,
+                                                                  float* __restrict__ logits_out, int64_t logits_img_stride, int logits_row,
+                                                                  int32_t* __restrict__ tokens, int tokens_ld, int forced,
+                                                                  float* __restrict__ confs, int confs_ld, const float* __restrict__ uniforms,
+                                                                  int uniforms_ld, int top_k, float top_p) {
   extern __shared__ __align__(16) float sm[];
-  float* x = sm;              // K
-  float* lg = sm + K;         // V
+  float* lg = sm;             // V
   float* srt = lg + V;        // Vp2
-  const int b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (warp == 0) {
-    const float* a = xs.resid + (int64_t)b * K; const float* d = xs.delta + (int64_t)b * K;
-    float s = 0.f;
-    for (int c = lane; c < K; c += 32) { float v = a[c] + d[c]; x[c] = v; s += v; }
-    float mean = warp_sum(s) / (float)K;
-    float q = 0.f;
-    for (int c = lane; c < K; c += 32) { float v = x[c] - mean; q += v * v; }
-    float rstd = 1.0f / sqrtf(warp_sum(q) / (float)K + xs.eps);
-    for (int c = lane; c < K; c += 32) x[c] = (x[c] - mean) * rstd * xs.ln_w[c] + xs.ln_b[c];
-  }
-  __syncthreads();
-  for (int n = warp; n < V; n += SEL_THREADS / 32) {
-    float acc = 0.f;
-    for (int k0 = lane * 8; k0 < K; k0 += 256) {
-      float w[8]; load8(Wout + (int64_t)n * K + k0, w);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) acc = fmaf(w[j], x[k0 + j], acc);
-    }
-    acc = warp_sum(acc);
-    if (lane == 0) {
-      float v = acc + bout[n];
-      lg[n] = v;
-      if (logits_out) logits_out[(int64_t)b * logits_img_stride + (int64_t)logits_row * V + n] = v;
-    }
+  const int b = blockIdx.x;
+  for (int i = threadIdx.x; i < V; i += SEL_THREADS) {
+    float v = step_logits[(int64_t)b * V + i];
+    lg[i] = v;
+    if (logits_out) logits_out[(int64_t)b * logits_img_stride + (int64_t)logits_row * V + i] = v;
   }
   __syncthreads();
   if (forced && !(confs && (t % 4 == 0))) return;
@@ -409,31 +466,50 @@ template <typename TW>
 int launch_linear(mdc_ctx* ctx, const XSrc& xs, const void* W, const float* bias, float* Y, int64_t ldy, int B, int N, int K,
                   bool relu, cudaStream_t s) {
   MDC_CHECK_ARG(K % 8 == 0);
-  size_t smem = (size_t)BT * K * sizeof(float);
-  int rw = N >= 1536 ? 4 : (N >= 512 ? 2 : 1);
-  dim3 grid((N + LIN_WARPS * rw - 1) / (LIN_WARPS * rw), (B + BT - 1) / BT), block(LIN_THREADS);
-#define MDC_LIN(RW_, RELU_)                                                                                                  \
-  {                                                                                                                          \
-    MDC_ENSURE_SMEM((dec_linear_kernel<TW, RW_, RELU_>), smem);                                                              \
-    dec_linear_kernel<TW, RW_, RELU_><<<grid, block, smem, s>>>(xs, (const TW*)W, bias, Y, ldy, B, N, K);                       \
+  const size_t smem = (size_t)BT * K * sizeof(float);
+  dim3 block(LIN_THREADS);
+  const int gy = (B + BT - 1) / BT;
+#define MDC_LIN(RW_, KCH_)                                                                                            \
+  {                                                                                                                   \
+    dim3 grid((N + LIN_WARPS * RW_ - 1) / (LIN_WARPS * RW_), gy);                                                     \
+    if (relu) {                                                                                                       \
+      MDC_ENSURE_SMEM((dec_linear_kernel<TW, RW_, KCH_, true>), smem);                                                \
+      dec_linear_kernel<TW, RW_, KCH_, true><<<grid, block, smem, s>>>(xs, (const TW*)W, bias, Y, ldy, B, N);          \
+    } else {                                                                                                          \
+      MDC_ENSURE_SMEM((dec_linear_kernel<TW, RW_, KCH_, false>), smem);                                               \
+      dec_linear_kernel<TW, RW_, KCH_, false><<<grid, block, smem, s>>>(xs, (const TW*)W, bias, Y, ldy, B, N);         \
+    }                                                                                                                 \
   }
-  if (rw == 4) { if (relu) MDC_LIN(4, true) else MDC_LIN(4, false) }
-  else if (rw == 2) { if (relu) MDC_LIN(2, true) else MDC_LIN(2, false) }
-  else { if (relu) MDC_LIN(1, true) else MDC_LIN(1, false) }
+  const int kch = (K % 256 == 0) ? K / 256 : 0;
+  // columns per warp: enough CTAs to cover the SMs, bounded register footprint (RW * KCH <= 8 weight slices)
+  if (kch == 1) { if (N >= 1536) MDC_LIN(4, 1) else if (N >= 512) MDC_LIN(2, 1) else MDC_LIN(1, 1) }
+  else if (kch == 2) { if (N >= 1536) MDC_LIN(4, 2) else if (N >= 512) MDC_LIN(2, 2) else MDC_LIN(1, 2) }
+  else if (kch == 4) { if (N >= 1536) MDC_LIN(2, 4) else MDC_LIN(1, 4) }
+  else if (kch == 8) { MDC_LIN(1, 8) }
+  else {
+    dim3 grid((N + LIN_WARPS - 1) / LIN_WARPS, gy);
+    if (relu) {
+      MDC_ENSURE_SMEM((dec_linear_generic_kernel<TW, true>), smem);
+      dec_linear_generic_kernel<TW, true><<<grid, block, smem, s>>>(xs, (const TW*)W, bias, Y, ldy, B, N, K);
+    } else {
+      MDC_ENSURE_SMEM((dec_linear_generic_kernel<TW, false>), smem);
+      dec_linear_generic_kernel<TW, false><<<grid, block, smem, s>>>(xs, (const TW*)W, bias, Y, ldy, B, N, K);
+    }
+  }
 #undef MDC_LIN
   MDC_LAUNCH_CHECK(ctx); return 0;
 }
 
-struct Scratch { float *xa, *xb, *xc, *y1, *y2, *y3, *qkv, *qc, *o, *oc, *f1; };
+struct Scratch { float *xa, *xb, *xc, *y1, *y2, *y3, *qkv, *qc, *o, *oc, *f1, *lg; };
 
 size_t scratch_floats(const mdc_dims& d, int B) {
-  return (size_t)B * ((size_t)d.dim * 9 + (size_t)d.dim * 3 + d.dec_ffn);
+  return (size_t)B * ((size_t)d.dim * 9 + (size_t)d.dim * 3 + d.dec_ffn + d.vocab);
 }
 
 Scratch carve(const mdc_dims& d, int B, void* p) {
   float* f = (float*)p; Scratch s; size_t bd = (size_t)B * d.dim;
   s.xa = f; f += bd; s.xb = f; f += bd; s.xc = f; f += bd; s.y1 = f; f += bd; s.y2 = f; f += bd; s.y3 = f; f += bd;
-  s.qc = f; f += bd; s.o = f; f += bd; s.oc = f; f += bd; s.qkv = f; f += 3 * bd; s.f1 = f;
+  s.qc = f; f += bd; s.o = f; f += bd; s.oc = f; f += bd; s.qkv = f; f += 3 * bd; s.f1 = f; f += (size_t)B * d.dec_ffn; s.lg = f;
   return s;
 }
 
@@ -457,10 +533,16 @@ int decode_step_typed(mdc_model* m, const mdc_decode_state* st, int t, cudaStrea
     XSrc x1 = prev; x1.xn_out = sc.xa;
     MDC_TRY(launch_linear<T>(ctx, x1, lw[MDC_SA_IN_W], (const float*)lw[MDC_SA_IN_B], sc.qkv, 3 * dim, B, 3 * dim, dim, false, s));
     {
-      size_t smem = (size_t)d.dec_heads * (hd + t + 1) * sizeof(float);
-      MDC_ENSURE_SMEM(dec_self_attn_kernel<T>, smem);
-      dec_self_attn_kernel<T><<<B, d.dec_heads * 32, smem, s>>>(sc.qkv, (T*)st->kv_pool, st->page_table, st->pages_per_seq, d.page_tokens,
-                                                               d.dec_layers, l, st->tokens, st->tokens_ld, d.pad_idx, t, dim, hd, scale, sc.o);
+      size_t smem = (size_t)d.dec_heads * (hd + t + 1 + st->pages_per_seq) * sizeof(float);
+#define MDC_SA(HD_)                                                                                                      \
+  {                                                                                                                      \
+    MDC_ENSURE_SMEM((dec_self_attn_kernel<T, HD_>), smem);                                                               \
+    dec_self_attn_kernel<T, HD_><<<B, d.dec_heads * 32, smem, s>>>(sc.qkv, (T*)st->kv_pool, st->page_table, st->pages_per_seq, \
+        d.page_tokens, d.dec_layers, l, st->tokens, st->tokens_ld, d.pad_idx, t, dim, scale, sc.o);                      \
+  }
+      if (hd == 32) MDC_SA(32) else if (hd == 64) MDC_SA(64) else if (hd == 128) MDC_SA(128)
+      else MDC_FAIL(-2, "decode: head width %d not in {32,64,128}", hd);
+#undef MDC_SA
       MDC_LAUNCH_CHECK(ctx);
     }
     XSrc xo{}; xo.mode = XMODE_PLAIN; xo.x = sc.o; xo.ldx = dim;
@@ -472,8 +554,13 @@ int decode_step_typed(mdc_model* m, const mdc_decode_state* st, int t, cudaStrea
     {
       size_t smem = (size_t)d.dec_heads * (hd + d.n_patches) * sizeof(float);
       const T* ckv = (const T*)st->cross_kv + (int64_t)l * B * d.n_patches * 2 * dim;
-      MDC_ENSURE_SMEM(dec_cross_attn_kernel<T>, smem);
-      dec_cross_attn_kernel<T><<<B, d.dec_heads * 32, smem, s>>>(sc.qc, ckv, d.n_patches, dim, hd, scale, sc.oc);
+#define MDC_CA(HD_)                                                                                         \
+  {                                                                                                         \
+    MDC_ENSURE_SMEM((dec_cross_attn_kernel<T, HD_>), smem);                                                 \
+    dec_cross_attn_kernel<T, HD_><<<B, d.dec_heads * 32, smem, s>>>(sc.qc, ckv, d.n_patches, dim, scale, sc.oc); \
+  }
+      if (hd == 32) MDC_CA(32) else if (hd == 64) MDC_CA(64) else MDC_CA(128)
+#undef MDC_CA
       MDC_LAUNCH_CHECK(ctx);
     }
     XSrc xco{}; xco.mode = XMODE_PLAIN; xco.x = sc.oc; xco.ldx = dim;
@@ -489,12 +576,12 @@ int decode_step_typed(mdc_model* m, const mdc_decode_state* st, int t, cudaStrea
   }
   {
     const int V = d.vocab, Vp2 = next_pow2(V);
-    size_t smem = (size_t)(dim + V + Vp2) * sizeof(float);
-    MDC_ENSURE_SMEM(dec_head_select_kernel<T>, smem);
-    dec_head_select_kernel<T><<<B, SEL_THREADS, smem, s>>>(prev, (const T*)gw[MDC_OUT_W], (const float*)gw[MDC_OUT_B], V, Vp2, dim, t,
-                                                          st->logits, (int64_t)st->logits_ld * V, t + st->logits_row_offset, st->tokens,
-                                                          st->tokens_ld, st->forced, st->confs, st->confs_ld, st->uniforms, st->uniforms_ld,
-                                                          st->top_k, st->top_p);
+    MDC_TRY(launch_linear<T>(ctx, prev, gw[MDC_OUT_W], (const float*)gw[MDC_OUT_B], sc.lg, V, B, V, dim, false, s));
+    size_t smem = (size_t)(V + Vp2) * sizeof(float);
+    MDC_ENSURE_SMEM(dec_select_kernel, smem);
+    dec_select_kernel<<<B, SEL_THREADS, smem, s>>>(sc.lg, V, Vp2, t, st->logits, (int64_t)st->logits_ld * V, t + st->logits_row_offset,
+                                                  st->tokens, st->tokens_ld, st->forced, st->confs, st->confs_ld, st->uniforms,
+                                                  st->uniforms_ld, st->top_k, st->top_p);
     MDC_LAUNCH_CHECK(ctx);
   }
   return 0;
@@ -523,6 +610,10 @@ extern "C" int mdc_decode_steps(mdc_model* m, const mdc_decode_state* st, int t_
   if (st->confs) MDC_CHECK_ARG((t_end + 3) / 4 <= st->confs_ld);
   if ((st->top_k != 0 || st->top_p != 1.0f) && !st->forced) MDC_CHECK_ARG(st->uniforms && t_end <= st->uniforms_ld);
   cudaStream_t s = (cudaStream_t)stream;
+  if (t_end > t_begin && decode_cluster_supported(m, st, t_end)) {
+    Scratch sc = carve(m->d, st->B, st->scratch);      // the cluster kernel only needs the step-logits area
+    return decode_cluster_launch(m, st, t_begin, t_end, sc.lg, s);
+  }
   for (int t = t_begin; t < t_end; ++t) {
     if (m->d.precision == MDC_F32) MDC_TRY(decode_step_typed<float>(m, st, t, s));
     else MDC_TRY(decode_step_typed<bf16>(m, st, t, s));

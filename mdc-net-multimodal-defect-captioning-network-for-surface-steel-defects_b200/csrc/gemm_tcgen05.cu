@@ -3,7 +3,9 @@
 //   * persistent: one CTA per SM walks output tiles (n fastest so neighbouring CTAs share the A panel in L2)
 //   * warp-specialised: warp 0 = TMA producer (cp.async.bulk.tensor, SWIZZLE_128B, OOB rows/cols zero-filled),
 //     warp 1 = MMA issuer (one elected lane issues tcgen05.mma.cta_group::1.kind::f16, 128 x BN x 16),
-//     warps 2..5 = epilogue (tcgen05.ld 32x32b from TMEM -> bias / GELU / ReLU / LayerScale+residual / patch+pos)
+//     warps 2..9 = epilogue (tcgen05.ld 32x32b from TMEM -> bias / GELU / ReLU / LayerScale+residual / patch+pos);
+//     two warps per TMEM lane quadrant split the tile's columns, bias/gamma are staged in shared memory per tile
+//     and residual reads are issued before the TMEM read so no global-load latency sits on the critical path
 //   * three mbarrier pipelines: smem full/empty (kStages deep), TMEM full/empty (2 accumulator stages, so the
 //     epilogue of tile i overlaps the main loop of tile i+1)
 //   * accumulators live in TMEM (2 x BN fp32 columns), never in registers.
@@ -21,8 +23,8 @@ namespace {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;           // 64 bf16 = 128 B = one SWIZZLE_128B atom
 constexpr int UMMA_K = 16;
-constexpr int NUM_THREADS = 192;      // warp0 TMA, warp1 MMA, warps 2-5 epilogue
-constexpr int EPI_THREADS = 128;
+constexpr int NUM_THREADS = 320;      // warp0 TMA, warp1 MMA, warps 2-9 epilogue
+constexpr int EPI_THREADS = 256;
 
 template <int BN> struct Cfg {
   static constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
@@ -30,7 +32,7 @@ template <int BN> struct Cfg {
   static constexpr int kBBytes = BN * BLOCK_K * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kTmemCols = (2 * BN <= 32) ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + 4 * BN * 4 /*bias+gamma x2 stages*/;
 };
 
 // ---- PTX wrappers --------------------------------------------------------------------------------
@@ -108,7 +110,17 @@ struct EpiArgs {
   void* D; int64_t ldd; const float* bias; const float* aux0; int period; int epilogue;
 };
 
-template <int BN>
+// branch-free erf (Abramowitz-Stegun 7.1.26, |err| <= 1.5e-7 -- far below bf16 output rounding)
+__device__ __forceinline__ float gelu_fast(float x) {
+  const float z = fabsf(x) * 0.70710678118654752440f;
+  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f); p = fmaf(p, t, -0.284496736f); p = fmaf(p, t, 0.254829592f);
+  const float e = 1.0f - p * t * __expf(-z * z);          // erf(|x|/sqrt2)
+  return 0.5f * x * (1.0f + copysignf(e, x));
+}
+
+template <int BN, int EPI>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, EpiArgs ep, int M, int N, int K) {
   using C = Cfg<BN>;
@@ -122,6 +134,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   uint64_t* tmem_full = bars + 2 * C::kStages;   // [2]
   uint64_t* tmem_empty = tmem_full + 2;          // [2]
   uint32_t* tmem_ptr_smem = (uint32_t*)(tmem_empty + 2);
+  float* s_bias = (float*)(smem + C::kStages * C::kStageBytes + 256);   // [2][BN]
+  float* s_gamma = s_bias + 2 * BN;                                      // [2][BN]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tiles_n = (N + BN - 1) / BN, tiles_m = (M + BLOCK_M - 1) / BLOCK_M;
@@ -185,50 +199,66 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       }
     }
   } else {
-    // ===== epilogue: warp w may only touch TMEM lanes [32*(w%4), +32) =====
-    const int quad = warp & 3;
+    // ===== epilogue: warp w may only touch TMEM lanes [32*(w%4), +32); warps w and w+4 split the columns =====
+    const int quad = warp & 3, half = (warp - 2) >> 2, et = threadIdx.x - 64;
+    constexpr int HALF_COLS = BN / 2;
     int iter = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++iter) {
       const int as = iter & 1; const uint32_t aphase = (iter >> 1) & 1;
       const int m0 = (tile / tiles_n) * BLOCK_M, n0 = (tile % tiles_n) * BN;
+      // stage this tile's bias (and LayerScale gamma) once; overlaps the wait for the accumulator
+      for (int i = et; i < BN; i += EPI_THREADS) {
+        const bool ok = n0 + i < N;
+        s_bias[as * BN + i] = (ok && ep.bias) ? __ldg(ep.bias + n0 + i) : 0.f;
+        if (EPI == MDC_EPI_LS_RESIDUAL) s_gamma[as * BN + i] = ok ? __ldg(ep.aux0 + n0 + i) : 0.f;
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
       mbar_wait(smem_u32(&tmem_full[as]), aphase);
       tcgen05_fence_after();
       const int row = m0 + quad * 32 + lane;
-      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + as * BN;
+      const bool row_ok = row < M;
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + as * BN + half * HALF_COLS;
       int64_t orow = row; const float* posrow = nullptr;
-      if (ep.epilogue == MDC_EPI_PATCH) { int img = row / ep.period; orow = row + img + 1; posrow = ep.aux0 + (int64_t)(row - img * ep.period) * ep.ldd; }
+      if (EPI == MDC_EPI_PATCH) { int img = row / ep.period; orow = row + img + 1; posrow = ep.aux0 + (int64_t)(row - img * ep.period) * ep.ldd; }
+      const float* sb = s_bias + as * BN + half * HALF_COLS;
+      const float* sg = s_gamma + as * BN + half * HALF_COLS;
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
+      for (int c0 = 0; c0 < HALF_COLS; c0 += 32) {
+        const int col0 = n0 + half * HALF_COLS + c0;
+        const bool any = row_ok && col0 < N;
+        const bool full32 = (col0 + 32 <= N);
+        float4 rz[8];
+        if (EPI == MDC_EPI_LS_RESIDUAL || EPI == MDC_EPI_PATCH) {   // issue the stream / pos reads BEFORE the TMEM read
+          const float* src = (EPI == MDC_EPI_LS_RESIDUAL) ? reinterpret_cast<const float*>(ep.D) + orow * ep.ldd + col0 : posrow + col0;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) rz[j] = (any && full32) ? *reinterpret_cast<const float4*>(src + 4 * j) : make_float4(0, 0, 0, 0);
+        }
         uint32_t v[32];
         tmem_ld32(taddr + c0, v);
         tmem_ld_wait();
-        const int col0 = n0 + c0;
-        if (row < M && col0 < N) {
-          const bool full32 = (col0 + 32 <= N);
-          if (ep.epilogue == MDC_EPI_LS_RESIDUAL || ep.epilogue == MDC_EPI_PATCH) {
+        if (any) {
+          if (EPI == MDC_EPI_LS_RESIDUAL || EPI == MDC_EPI_PATCH) {
             float* dst = reinterpret_cast<float*>(ep.D) + orow * ep.ldd + col0;
+            if (full32) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              if (full32 || col0 + j + 3 < N) {
-                float4 b4 = ep.bias ? *reinterpret_cast<const float4*>(ep.bias + col0 + j) : make_float4(0, 0, 0, 0);
+              for (int j = 0; j < 8; ++j) {
+                const float4 b4 = *reinterpret_cast<const float4*>(sb + c0 + 4 * j);
                 float4 o;
-                if (ep.epilogue == MDC_EPI_LS_RESIDUAL) {
-                  float4 g4 = *reinterpret_cast<const float4*>(ep.aux0 + col0 + j);
-                  float4 r4 = *reinterpret_cast<const float4*>(dst + j);
-                  o.x = r4.x + g4.x * (__uint_as_float(v[j]) + b4.x); o.y = r4.y + g4.y * (__uint_as_float(v[j + 1]) + b4.y);
-                  o.z = r4.z + g4.z * (__uint_as_float(v[j + 2]) + b4.z); o.w = r4.w + g4.w * (__uint_as_float(v[j + 3]) + b4.w);
+                if (EPI == MDC_EPI_LS_RESIDUAL) {
+                  const float4 g4 = *reinterpret_cast<const float4*>(sg + c0 + 4 * j);
+                  o.x = rz[j].x + g4.x * (__uint_as_float(v[4 * j]) + b4.x); o.y = rz[j].y + g4.y * (__uint_as_float(v[4 * j + 1]) + b4.y);
+                  o.z = rz[j].z + g4.z * (__uint_as_float(v[4 * j + 2]) + b4.z); o.w = rz[j].w + g4.w * (__uint_as_float(v[4 * j + 3]) + b4.w);
                 } else {
-                  float4 p4 = *reinterpret_cast<const float4*>(posrow + col0 + j);
-                  o.x = __uint_as_float(v[j]) + b4.x + p4.x; o.y = __uint_as_float(v[j + 1]) + b4.y + p4.y;
-                  o.z = __uint_as_float(v[j + 2]) + b4.z + p4.z; o.w = __uint_as_float(v[j + 3]) + b4.w + p4.w;
+                  o.x = __uint_as_float(v[4 * j]) + b4.x + rz[j].x; o.y = __uint_as_float(v[4 * j + 1]) + b4.y + rz[j].y;
+                  o.z = __uint_as_float(v[4 * j + 2]) + b4.z + rz[j].z; o.w = __uint_as_float(v[4 * j + 3]) + b4.w + rz[j].w;
                 }
-                *reinterpret_cast<float4*>(dst + j) = o;
-              } else {
-                for (int jj = j; jj < j + 4 && col0 + jj < N; ++jj) {
-                  float a = __uint_as_float(v[jj]) + (ep.bias ? ep.bias[col0 + jj] : 0.f);
-                  if (ep.epilogue == MDC_EPI_LS_RESIDUAL) dst[jj] = dst[jj] + ep.aux0[col0 + jj] * a;
-                  else dst[jj] = a + posrow[col0 + jj];
-                }
+                *reinterpret_cast<float4*>(dst + 4 * j) = o;
+              }
+            } else {
+              for (int jj = 0; jj < 32 && col0 + jj < N; ++jj) {
+                float a = __uint_as_float(v[jj]) + sb[c0 + jj];
+                if (EPI == MDC_EPI_LS_RESIDUAL) dst[jj] = dst[jj] + sg[c0 + jj] * a;
+                else dst[jj] = a + posrow[col0 + jj];
               }
             }
           } else {
@@ -236,12 +266,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll
             for (int j = 0; j < 32; j += 8) {
               float o[8];
+              const float4 b0 = *reinterpret_cast<const float4*>(sb + c0 + j), b1 = *reinterpret_cast<const float4*>(sb + c0 + j + 4);
+              const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
               for (int jj = 0; jj < 8; ++jj) {
-                float a = __uint_as_float(v[j + jj]);
-                if (ep.bias && col0 + j + jj < N) a += __ldg(ep.bias + col0 + j + jj);
-                if (ep.epilogue == MDC_EPI_BIAS_GELU) a = gelu_erf(a);
-                else if (ep.epilogue == MDC_EPI_BIAS_RELU) a = fmaxf(a, 0.f);
+                float a = __uint_as_float(v[j + jj]) + bb[jj];
+                if (EPI == MDC_EPI_BIAS_GELU) a = gelu_fast(a);
+                else if (EPI == MDC_EPI_BIAS_RELU) a = fmaxf(a, 0.f);
                 o[jj] = a;
               }
               if (full32 || col0 + j + 7 < N) store8(dst + j, o);
@@ -303,19 +334,31 @@ int get_tmap(mdc_ctx* ctx, const void* ptr, int64_t rows, int64_t cols, int64_t 
   *out = m; return 0;
 }
 
-template <int BN>
-int launch_bn(mdc_ctx* ctx, const CUtensorMap& ma, const CUtensorMap& mw, const EpiArgs& ep, int M, int N, int K, cudaStream_t s) {
+template <int BN, int EPI>
+int launch_bn_epi(mdc_ctx* ctx, const CUtensorMap& ma, const CUtensorMap& mw, const EpiArgs& ep, int M, int N, int K, cudaStream_t s) {
   using C = Cfg<BN>;
   static bool attr_set = false;
   if (!attr_set) {
-    MDC_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
+    MDC_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
     attr_set = true;
   }
   int tiles = ((M + BLOCK_M - 1) / BLOCK_M) * ((N + BN - 1) / BN);
   int grid = tiles < ctx->sm_count ? tiles : ctx->sm_count;
-  gemm_tc_kernel<BN><<<grid, NUM_THREADS, C::kSmemBytes, s>>>(ma, mw, ep, M, N, K);
+  gemm_tc_kernel<BN, EPI><<<grid, NUM_THREADS, C::kSmemBytes, s>>>(ma, mw, ep, M, N, K);
   MDC_LAUNCH_CHECK(ctx);
   return 0;
+}
+
+template <int BN>
+int launch_bn(mdc_ctx* ctx, const CUtensorMap& ma, const CUtensorMap& mw, const EpiArgs& ep, int M, int N, int K, cudaStream_t s) {
+  switch (ep.epilogue) {
+    case MDC_EPI_BIAS: return launch_bn_epi<BN, MDC_EPI_BIAS>(ctx, ma, mw, ep, M, N, K, s);
+    case MDC_EPI_BIAS_GELU: return launch_bn_epi<BN, MDC_EPI_BIAS_GELU>(ctx, ma, mw, ep, M, N, K, s);
+    case MDC_EPI_BIAS_RELU: return launch_bn_epi<BN, MDC_EPI_BIAS_RELU>(ctx, ma, mw, ep, M, N, K, s);
+    case MDC_EPI_LS_RESIDUAL: return launch_bn_epi<BN, MDC_EPI_LS_RESIDUAL>(ctx, ma, mw, ep, M, N, K, s);
+    case MDC_EPI_PATCH: return launch_bn_epi<BN, MDC_EPI_PATCH>(ctx, ma, mw, ep, M, N, K, s);
+  }
+  MDC_FAIL(-2, "gemm: unknown epilogue %d", ep.epilogue);
 }
 
 }  // namespace

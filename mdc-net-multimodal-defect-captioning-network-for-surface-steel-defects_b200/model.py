@@ -12,6 +12,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 
 import torch
 from torch import nn
@@ -446,29 +447,85 @@ class EncoderDecoder(nn.Module, _EngineOwner):
 
     # -- the fast path used by generate(): encode once, cross-K/V once, incremental decode ---------
     @torch.no_grad()
-    def generate_tokens(self, image, max_new_tokens, top_k=0, top_p=1.0, uniforms=None, return_logits=False, plan=None):
-        """Returns (tokens int32 (B,1+T) on device, confs f32 (B,ceil(T/4)) on device[, logits (B,T,V)])."""
+    def generate_tokens(self, image, max_new_tokens, top_k=0, top_p=1.0, uniforms=None, return_logits=False, use_graph=None):
+        """Returns (tokens int32 (B,1+T) on device, confs f32 (B,ceil(T/4)) on device[, logits (B,T,V)]).
+        The whole call (encoder, cross-K/V, T decode steps) is one CUDA graph replay per (B, T, sampler) shape."""
         eng = self._engine(image.device if image.is_cuda else None)
         d = eng.dims
         T = int(max_new_tokens)
         if T > d.max_pos:
             raise RuntimeError(f"max_len {T} exceeds CFG.max_len-1 = {d.max_pos}: the positional table has no more rows "
                                "(reference fails at model.py:93, Q6)")
-        image = image.to(eng.device)
-        B = image.shape[0]
-        _, memory = eng.encode(image, want_enc_out=False, want_memory=True)
-        ckv = eng.cross_kv(memory)
-        tokens = torch.full((B, T + 1), int(CFG.pad_idx), dtype=torch.int32, device=eng.device)
-        tokens[:, 0] = int(CFG.bos_idx)
-        confs = torch.zeros((B, (T + 3) // 4), dtype=torch.float32, device=eng.device)
-        logits = torch.empty((B, T, d.vocab), dtype=torch.float32, device=eng.device) if return_logits else None
         sampling = (top_k != 0 or top_p != 1)
+        if use_graph is None:
+            use_graph = os.environ.get("MDC_NO_GRAPH", "0") != "1"
+        key = (id(eng), image.shape[0], T, int(top_k), float(top_p), bool(return_logits), bool(use_graph))
+        plans = self.__dict__.setdefault("_plans", {})
+        if plans.get("eng") is not eng:
+            plans.clear(); plans["eng"] = eng
+        plan = plans.get(key)
+        if plan is None:
+            plan = GenerationPlan(eng, image.shape[0], T, top_k, top_p, sampling, return_logits, use_graph)
+            plans[key] = plan
         if sampling and uniforms is None:
-            uniforms = torch.rand((B, T), dtype=torch.float32, device=eng.device)
-        if uniforms is not None:
-            uniforms = uniforms.to(eng.device, torch.float32).contiguous()
-        eng.decode(ckv, tokens, 0, T, max_tokens=T, forced=False, logits=logits, logits_row_offset=0, confs=confs,
-                   uniforms=uniforms, top_k=top_k, top_p=top_p)
+            uniforms = torch.rand((image.shape[0], T), dtype=torch.float32, device=eng.device)
+        tokens, confs, logits = plan.run(image, uniforms)
         if return_logits:
-            return tokens, confs, logits
-        return tokens, confs
+            return tokens.clone(), confs.clone(), logits.clone()
+        return tokens.clone(), confs.clone()
+
+
+class GenerationPlan:
+    """Static buffers + (optionally) a captured CUDA graph for one (batch, new tokens, sampler) shape:
+    encoder -> memory -> cross-K/V -> T decode steps, no host synchronisation anywhere inside."""
+
+    def __init__(self, eng, B, T, top_k, top_p, sampling, want_logits, use_graph):
+        d = eng.dims
+        dev = eng.device
+        self.eng, self.B, self.T = eng, B, T
+        self.top_k, self.top_p = int(top_k), float(top_p)
+        self.x = torch.zeros((B, d.in_chans, d.img_size, d.img_size), dtype=torch.float32, device=dev)
+        self.ws_bytes = eng.lib.mdc_encode_workspace_bytes(eng.handle, B)
+        self.ws = torch.empty(self.ws_bytes, dtype=torch.uint8, device=dev)
+        self.memory = torch.empty((B, d.n_patches, d.dim), dtype=eng.dtype, device=dev)
+        self.ckv = torch.empty(eng.lib.mdc_cross_kv_bytes(eng.handle, B), dtype=torch.uint8, device=dev)
+        self.tokens = torch.empty((B, T + 1), dtype=torch.int32, device=dev)
+        self.confs = torch.zeros((B, (T + 3) // 4), dtype=torch.float32, device=dev)
+        self.logits = torch.empty((B, T, d.vocab), dtype=torch.float32, device=dev) if want_logits else None
+        self.uniforms = torch.zeros((B, T), dtype=torch.float32, device=dev) if sampling else None
+        self.kv = PagedKVCache(B, T, d.dec_layers, d.dim, d.page_tokens, eng.dtype, dev)
+        self.scratch = torch.empty(eng.lib.mdc_decode_workspace_bytes(eng.handle, B), dtype=torch.uint8, device=dev)
+        self.graph = None
+        if use_graph:
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                self._launch()                      # warm-up: tensor maps, smem attributes, lazy module load
+            torch.cuda.current_stream(dev).wait_stream(side)
+            torch.cuda.synchronize(dev)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._launch()
+            self.graph = g
+
+    def _launch(self):
+        eng = self.eng
+        L.check(eng.lib.mdc_encode(eng.handle, L.ptr(self.x), self.B, None, L.ptr(self.memory), L.ptr(self.ws), self.ws_bytes, L.stream_ptr()))
+        L.check(eng.lib.mdc_cross_kv_build(eng.handle, L.ptr(self.memory), self.B, L.ptr(self.ckv), L.stream_ptr()))
+        self.tokens.fill_(int(CFG.pad_idx))
+        self.tokens[:, 0].fill_(int(CFG.bos_idx))
+        eng.decode(self.ckv, self.tokens, 0, self.T, max_tokens=self.T, forced=False, logits=self.logits, logits_row_offset=0,
+                   confs=self.confs, uniforms=self.uniforms, top_k=self.top_k, top_p=self.top_p, kv=self.kv, scratch=self.scratch)
+
+    def run(self, image, uniforms=None):
+        d = self.eng.dims
+        if tuple(image.shape) != tuple(self.x.shape):
+            raise AssertionError("Input size doesn't match model")
+        self.x.copy_(image, non_blocking=True)               # H2D from (pinned) host memory or D2D
+        if self.uniforms is not None:
+            self.uniforms.copy_(uniforms.to(torch.float32), non_blocking=True)
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            self._launch()
+        return self.tokens, self.confs, self.logits
