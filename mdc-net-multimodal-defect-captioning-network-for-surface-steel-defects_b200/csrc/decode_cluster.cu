@@ -65,6 +65,7 @@ struct ClusterParams {
   float* confs; int confs_ld;
   const float* uniforms; int uniforms_ld; int top_k; float top_p; int forced;
   int t_begin, t_end, maxT;                // maxT: padded key capacity per image in a self-KV stage
+  int pt_shift;                            // log2(PT)
   int ips;                                 // images per self-KV stage
 };
 
@@ -135,61 +136,79 @@ enum { K_INA = 0, K_INB, K_SELFK, K_SELFV, K_SOUT, K_CQ, K_CROSSK, K_CROSSV, K_C
 
 struct StageId { int kind, sub, layer, t; };
 
-__device__ __forceinline__ StageId decode_stage(const ClusterParams& P, const Sched& sc, int64_t idx) {
-  const int sps = P.layers * sc.spl + 1;
-  StageId id; id.t = P.t_begin + (int)(idx / sps);
-  int j = (int)(idx % sps);
-  if (j == sps - 1) { id.kind = K_HEAD; id.sub = 0; id.layer = 0; return id; }
-  id.layer = j / sc.spl; j %= sc.spl;
-  if (j < 2) { id.kind = j == 0 ? K_INA : K_INB; id.sub = 0; return id; } j -= 2;
-  if (j < 2 * sc.nS) { id.kind = (j & 1) ? K_SELFV : K_SELFK; id.sub = j >> 1; return id; } j -= 2 * sc.nS;
-  if (j == 0) { id.kind = K_SOUT; id.sub = 0; return id; } j -= 1;
-  if (j == 0) { id.kind = K_CQ; id.sub = 0; return id; } j -= 1;
-  if (j < 2 * sc.nC) { id.kind = (j & 1) ? K_CROSSV : K_CROSSK; id.sub = j >> 1; return id; } j -= 2 * sc.nC;
-  if (j == 0) { id.kind = K_COUT; id.sub = 0; return id; } j -= 1;
-  if (j < 4) { id.kind = K_F1; id.sub = j; return id; } j -= 4;
-  id.kind = K_F2; id.sub = j; return id;
-}
-
-// copy `nrows` weight rows (256 bf16 each, source pitch `spitch` elements, first row `row0`, k offset `koff`) to stage rows [dst0, ...)
-__device__ __forceinline__ void issue_rows(uint8_t* stage, int dst0, const bf16* W, int row0, int nrows, int spitch, int koff) {
-  for (int c = threadIdx.x; c < nrows * 32; c += NT) {
-    const int r = c >> 5, ch = c & 31;
-    cp16(stage + (size_t)(dst0 + r) * PITCH * 2 + ch * 16, W + (int64_t)(row0 + r) * spitch + koff + ch * 8);
+// Incremental position of the PRODUCER in the static stage schedule (no div/mod on the hot path).
+struct Cursor {
+  int t, layer, j; bool head;
+  __device__ __forceinline__ void advance(const Sched& sc, int layers) {
+    if (head) { head = false; ++t; layer = 0; j = 0; }
+    else if (++j == sc.spl) { j = 0; if (++layer == layers) head = true; }
   }
+  __device__ __forceinline__ StageId id(const Sched& sc) const {
+    StageId r; r.t = t; r.layer = layer; r.sub = 0;
+    if (head) { r.kind = K_HEAD; return r; }
+    int q = j;
+    if (q < 2) { r.kind = q == 0 ? K_INA : K_INB; return r; } q -= 2;
+    if (q < 2 * sc.nS) { r.kind = (q & 1) ? K_SELFV : K_SELFK; r.sub = q >> 1; return r; } q -= 2 * sc.nS;
+    if (q == 0) { r.kind = K_SOUT; return r; } q -= 1;
+    if (q == 0) { r.kind = K_CQ; return r; } q -= 1;
+    if (q < 2 * sc.nC) { r.kind = (q & 1) ? K_CROSSV : K_CROSSK; r.sub = q >> 1; return r; } q -= 2 * sc.nC;
+    if (q == 0) { r.kind = K_COUT; return r; } q -= 1;
+    if (q < 4) { r.kind = K_F1; r.sub = q; return r; } q -= 4;
+    r.kind = K_F2; r.sub = q; return r;
+  }
+};
+
+// copy `nrows` weight rows (256 bf16 each, source pitch `spitch` elements) to stage rows [dst0, ...): 32 chunks of 16 B per row,
+// one warp-pass = one row
+__device__ __forceinline__ void issue_rows(uint8_t* stage, int dst0, const bf16* W, int nrows, int spitch) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bf16* src = W + (int64_t)warp * spitch + lane * 8;
+  uint8_t* dst = stage + (size_t)(dst0 + warp) * (PITCH * 2) + lane * 16;
+  for (int r = warp; r < nrows; r += 8) { cp16(dst, src); src += (int64_t)8 * spitch; dst += 8 * PITCH * 2; }
 }
 
-__device__ void issue_stage(const ClusterParams& P, const Sched& sc, const Smem& sm, int64_t idx, int64_t total, int rank, int img0, int G) {
-  if (idx < total) {
-    uint8_t* stage = sm.ring + (size_t)(idx % NS) * STAGE_BYTES;
-    const StageId id = decode_stage(P, sc, idx);
+// copy nk keys (64 B = 4 chunks each) of one K or V panel: 4 lanes per key, division-free
+__device__ __forceinline__ void issue_panel_contig(uint8_t* dst_panel, const bf16* src0, int64_t key_pitch, int nk) {
+  const int ch = threadIdx.x & 3;
+  for (int ku = threadIdx.x >> 2; ku < nk; ku += NT / 4)
+    cp16(dst_panel + ((size_t)ku * KVP + ch * 8) * 2, src0 + (int64_t)ku * key_pitch + ch * 8);
+}
+
+__device__ void issue_stage(const ClusterParams& P, const Sched& sc, const Smem& sm, Cursor& cur, int slot, int rank, int img0, int G) {
+  if (cur.t < P.t_end) {
+    uint8_t* stage = sm.ring + (size_t)slot * STAGE_BYTES;
+    const StageId id = cur.id(sc);
     const int l = id.layer;
     switch (id.kind) {
       case K_INA:
-        issue_rows(stage, 0, P.w_in[l], rank * HD, 32, DM, 0);                 // q rows of head `rank`
-        issue_rows(stage, 32, P.w_in[l], DM + rank * HD, 32, DM, 0);           // k rows
+        issue_rows(stage, 0, P.w_in[l] + (int64_t)(rank * HD) * DM, 32, DM);               // q rows of head `rank`
+        issue_rows(stage, 32, P.w_in[l] + (int64_t)(DM + rank * HD) * DM, 32, DM);          // k rows
         break;
-      case K_INB: issue_rows(stage, 0, P.w_in[l], 2 * DM + rank * HD, 32, DM, 0); break;   // v rows
-      case K_SOUT: issue_rows(stage, 0, P.w_so[l], rank * 32, 32, DM, 0); break;
-      case K_CQ: issue_rows(stage, 0, P.w_ca[l], rank * 32, 32, DM, 0); break;              // q part = first DM rows of in_proj
-      case K_COUT: issue_rows(stage, 0, P.w_co[l], rank * 32, 32, DM, 0); break;
-      case K_F1: issue_rows(stage, 0, P.w_f1[l], rank * FS + id.sub * 64, 64, DM, 0); break;
-      case K_F2: issue_rows(stage, 0, P.w_f2[l], id.sub * 64, 64, FFN, rank * FS); break;    // K-split: columns of own hidden slice
+      case K_INB: issue_rows(stage, 0, P.w_in[l] + (int64_t)(2 * DM + rank * HD) * DM, 32, DM); break;   // v rows
+      case K_SOUT: issue_rows(stage, 0, P.w_so[l] + (int64_t)(rank * 32) * DM, 32, DM); break;
+      case K_CQ: issue_rows(stage, 0, P.w_ca[l] + (int64_t)(rank * 32) * DM, 32, DM); break;             // q part = first DM rows of in_proj
+      case K_COUT: issue_rows(stage, 0, P.w_co[l] + (int64_t)(rank * 32) * DM, 32, DM); break;
+      case K_F1: issue_rows(stage, 0, P.w_f1[l] + (int64_t)(rank * FS + id.sub * 64) * DM, 64, DM); break;
+      case K_F2: issue_rows(stage, 0, P.w_f2[l] + (int64_t)(id.sub * 64) * FFN + rank * FS, 64, FFN); break;   // K-split: own hidden columns
       case K_HEAD: {
         const int r0 = rank * VSL, n = max(0, min(VSL, P.vocab - r0));
-        issue_rows(stage, 0, P.w_out, r0, n, DM, 0);
+        issue_rows(stage, 0, P.w_out + (int64_t)r0 * DM, n, DM);
         break;
       }
       case K_SELFK: case K_SELFV: {
-        // keys 0..t-1 of head `rank` for images [sub*ips, ...): 64 B per key -> 4 chunks, padded rows of KVP elements
-        const int which = id.kind == K_SELFV, nk = id.t;          // key t itself comes from shared memory
+        // keys 0..t-1 of head `rank` for images [sub*ips, ...); the step's own key t comes from shared memory
+        const int which = id.kind == K_SELFV, nk = id.t;
         const int g0 = id.sub * P.ips, gn = min(P.ips, G - g0);
         const int64_t plane = (int64_t)P.PT * DM;
-        for (int c = threadIdx.x; c < gn * nk * 4; c += NT) {
-          const int ch = c & 3, ku = (c >> 2) % nk, gi = (c >> 2) / nk;
-          const int page = sm.pages[(g0 + gi) * 32 + ku / P.PT];
-          const bf16* src = P.kv_pool + (((int64_t)page * P.layers + l) * 2 + which) * plane + (int64_t)(ku % P.PT) * DM + rank * HD + ch * 8;
-          cp16(stage + ((size_t)(gi * P.maxT + ku) * KVP + ch * 8) * 2, src);
+        const int ch = threadIdx.x & 3;
+        for (int gi = 0; gi < gn; ++gi) {
+          const int* pg = sm.pages + (g0 + gi) * 32;
+          uint8_t* dstp = stage + (size_t)gi * P.maxT * KVP * 2;
+          for (int ku = threadIdx.x >> 2; ku < nk; ku += NT / 4) {
+            const bf16* src = P.kv_pool + (((int64_t)pg[ku >> P.pt_shift] * P.layers + l) * 2 + which) * plane +
+                              (int64_t)(ku & (P.PT - 1)) * DM + rank * HD + ch * 8;
+            cp16(dstp + ((size_t)ku * KVP + ch * 8) * 2, src);
+          }
         }
         break;
       }
@@ -197,52 +216,79 @@ __device__ void issue_stage(const ClusterParams& P, const Sched& sc, const Smem&
         const int which = id.kind == K_CROSSV;
         const int g0 = id.sub * 2, gn = min(2, G - g0), S = P.S;
         const bf16* base = P.cross_kv + (int64_t)l * P.B * S * 2 * DM + which * DM + rank * HD;
-        for (int c = threadIdx.x; c < gn * S * 4; c += NT) {
-          const int ch = c & 3, ku = (c >> 2) % S, gi = (c >> 2) / S;
-          cp16(stage + ((size_t)(gi * S + ku) * KVP + ch * 8) * 2, base + ((int64_t)(img0 + g0 + gi) * S + ku) * 2 * DM + ch * 8);
-        }
+        for (int gi = 0; gi < gn; ++gi)
+          issue_panel_contig(stage + (size_t)gi * S * KVP * 2, base + (int64_t)(img0 + g0 + gi) * S * 2 * DM, 2 * DM, S);
         break;
       }
     }
+    cur.advance(sc, P.layers);
   }
   cp_commit();     // always commit (possibly empty) so that wait_group accounting stays uniform
 }
 
-// one ring stage of a projection: out[g][col0 + 8w + ..] (+)= A[g][:] . Wstage[8w + n][:]   (warp w = n-tile w)
+__device__ __forceinline__ void ldsm_x4(uint32_t* r, const bf16* p) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"((uint32_t)__cvta_generic_to_shared(p)));
+}
+__device__ __forceinline__ void ldsm_x2(uint32_t& r0, uint32_t& r1, const bf16* p) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0,%1}, [%2];" : "=r"(r0), "=r"(r1) : "r"((uint32_t)__cvta_generic_to_shared(p)));
+}
+
+// One 16x8 output tile of a projection: C[g][n] = sum_k (Ahi+Alo)[g][k] * W[tile rows n][k], k = 0..255.
+// Shared (NOT inlined) by every projection phase to keep the instruction footprint small.  Fragments come from
+// ldmatrix (conflict-free with the 528-byte row pitch); four independent accumulator chains (hi/lo x even/odd
+// k-step) hide the HMMA latency.
+__device__ __noinline__ float4 mma_tile(const bf16* Wtile /*8 rows of the stage*/, const bf16* Ahi, const bf16* Alo) {
+  const int lane = threadIdx.x & 31;
+  const bf16* wp = Wtile + (size_t)(lane & 7) * PITCH + ((lane >> 3) & 1) * 8;
+  const int arow = (lane & 7) + ((lane >> 3) & 1) * 8, akof = (lane >> 4) * 8;
+  const bf16* ah = Ahi + (size_t)arow * PITCH + akof;
+  const bf16* al = Alo + (size_t)arow * PITCH + akof;
+  float c0[4] = {0, 0, 0, 0}, c1[4] = {0, 0, 0, 0}, c2[4] = {0, 0, 0, 0}, c3[4] = {0, 0, 0, 0};
+#pragma unroll 2
+  for (int k0 = 0; k0 < DM; k0 += 32) {
+    uint32_t b0, b1, b2, b3, h0[4], l0[4], h1[4], l1[4];
+    ldsm_x2(b0, b1, wp + k0); ldsm_x2(b2, b3, wp + k0 + 16);
+    ldsm_x4(h0, ah + k0); ldsm_x4(l0, al + k0); ldsm_x4(h1, ah + k0 + 16); ldsm_x4(l1, al + k0 + 16);
+    mma16816(c0, h0, b0, b1); mma16816(c1, l0, b0, b1);
+    mma16816(c2, h1, b2, b3); mma16816(c3, l1, b2, b3);
+  }
+  return make_float4((c0[0] + c2[0]) + (c1[0] + c3[0]), (c0[1] + c2[1]) + (c1[1] + c3[1]),
+                     (c0[2] + c2[2]) + (c1[2] + c3[2]), (c0[3] + c2[3]) + (c1[3] + c3[3]));
+}
+
+// one ring stage of a projection: warp w computes n-tile w (8 output columns) and hands the 16x8 tile to `store(row, col, value)`
 template <typename Store>
 __device__ __forceinline__ void mma_stage(const uint8_t* stage, int n_tiles, const bf16* Ahi, const bf16* Alo, Store store) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp >= n_tiles) return;
-  const bf16* W = reinterpret_cast<const bf16*>(stage) + (size_t)(warp * 8 + (lane >> 2)) * PITCH + 2 * (lane & 3);
-  const bf16* Ah = Ahi + (size_t)(lane >> 2) * PITCH + 2 * (lane & 3);
-  const bf16* Al = Alo + (size_t)(lane >> 2) * PITCH + 2 * (lane & 3);
-  float c[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll 4
-  for (int k0 = 0; k0 < DM; k0 += 16) {
-    const uint32_t b0 = *reinterpret_cast<const uint32_t*>(W + k0), b1 = *reinterpret_cast<const uint32_t*>(W + k0 + 8);
-    uint32_t ah[4], al[4];
-    ah[0] = *reinterpret_cast<const uint32_t*>(Ah + k0); ah[1] = *reinterpret_cast<const uint32_t*>(Ah + 8 * PITCH + k0);
-    ah[2] = *reinterpret_cast<const uint32_t*>(Ah + k0 + 8); ah[3] = *reinterpret_cast<const uint32_t*>(Ah + 8 * PITCH + k0 + 8);
-    al[0] = *reinterpret_cast<const uint32_t*>(Al + k0); al[1] = *reinterpret_cast<const uint32_t*>(Al + 8 * PITCH + k0);
-    al[2] = *reinterpret_cast<const uint32_t*>(Al + k0 + 8); al[3] = *reinterpret_cast<const uint32_t*>(Al + 8 * PITCH + k0 + 8);
-    mma16816(c, ah, b0, b1);
-    mma16816(c, al, b0, b1);
-  }
+  const float4 c = mma_tile(reinterpret_cast<const bf16*>(stage) + (size_t)warp * 8 * PITCH, Ahi, Alo);
   const int r0 = lane >> 2, cc = warp * 8 + 2 * (lane & 3);
-  store(r0, cc, c[0]); store(r0, cc + 1, c[1]); store(r0 + 8, cc, c[2]); store(r0 + 8, cc + 1, c[3]);
+  store(r0, cc, c.x); store(r0, cc + 1, c.y); store(r0 + 8, cc, c.z); store(r0 + 8, cc + 1, c.w);
 }
 
-// attention of one query (image g, own head) against nk keys held in a stage panel (padded bf16 rows) [+ one extra key in regs]
-// scores -> sc[0..nk]; returns via out[32].  One warp.
-__device__ __forceinline__ void attend_panel(const float* q /*smem 32, pre-scaled*/, const bf16* Kp, int nk, const uint8_t* padf,
-                                             const float* k_extra, bool has_extra, float extra_bias, float* sc) {
+// ---- attention of one query against a key panel, split over several warps (flash-decoding style) ------------------
+// A warp owns keys [k_lo,k_hi) of one image (plus, for part 0 of self-attention, the step's own key held in shared
+// memory).  Pass 1 parks exp(s - m_local) in the warp's score row and returns (m_local, l_local); pass 2 (after the V
+// panel has landed) accumulates the un-normalised output for channel `lane`.  Partials are merged by attn_merge().
+struct AttnJob {
+  const float* q;            // smem, 32, pre-scaled
+  const bf16* panel;         // K or V panel of this image (rows of KVP bf16)
+  int k_lo, k_hi;
+  const uint8_t* padf;       // PAD flags per key (self) or null (cross)
+  const float* extra;        // own key / value (smem, 32 f32) or null
+  float extra_bias;
+  float* sc;                 // this warp's score row
+};
+
+__device__ __noinline__ float2 attn_scores(const AttnJob& j) {
   const int lane = threadIdx.x & 31;
   float qv[32];
 #pragma unroll
-  for (int j = 0; j < 32; ++j) qv[j] = q[j];
+  for (int i = 0; i < 32; ++i) qv[i] = j.q[i];
   float mx = -INFINITY;
-  for (int u = lane; u < nk; u += 32) {
-    const uint4* kr = reinterpret_cast<const uint4*>(Kp + (size_t)u * KVP);
+  for (int u = j.k_lo + lane; u < j.k_hi; u += 32) {
+    const uint4* kr = reinterpret_cast<const uint4*>(j.panel + (size_t)u * KVP);
     float s = 0.f;
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
@@ -251,42 +297,57 @@ __device__ __forceinline__ void attend_panel(const float* q /*smem 32, pre-scale
 #pragma unroll
       for (int i = 0; i < 4; ++i) { float2 f = __bfloat1622float2(h[i]); s = fmaf(qv[c * 8 + 2 * i], f.x, s); s = fmaf(qv[c * 8 + 2 * i + 1], f.y, s); }
     }
-    if (padf && padf[u]) s += 1.0f;
-    sc[u] = s; mx = fmaxf(mx, s);
+    if (j.padf && j.padf[u]) s += 1.0f;
+    j.sc[u - j.k_lo] = s; mx = fmaxf(mx, s);
   }
-  if (has_extra) {
+  const int n = j.k_hi - j.k_lo;
+  if (j.extra) {
     float s = 0.f;
 #pragma unroll
-    for (int j = 0; j < 32; ++j) s = fmaf(qv[j], k_extra[j], s);
-    s += extra_bias;
-    if (lane == 0) sc[nk] = s;
+    for (int i = 0; i < 32; ++i) s = fmaf(qv[i], j.extra[i], s);
+    s += j.extra_bias;
+    if (lane == 0) j.sc[n] = s;
     mx = fmaxf(mx, s);
   }
   mx = warp_max(mx);
   __syncwarp();
-  const int n = nk + (has_extra ? 1 : 0);
+  const int nn = n + (j.extra ? 1 : 0);
   float sum = 0.f;
-  for (int u = lane; u < n; u += 32) { float e = expf(sc[u] - mx); sc[u] = e; sum += e; }
+  for (int u = lane; u < nn; u += 32) { float e = expf(j.sc[u] - mx); j.sc[u] = e; sum += e; }
   sum = warp_sum(sum);
-  if (lane == 0) sc[n] = 1.0f / sum;     // normaliser parked behind the probabilities
   __syncwarp();
+  return make_float2(mx, sum);
 }
 
-__device__ __forceinline__ float pv_panel(const bf16* Vp, int nk, const float* sc, const float* v_extra, bool has_extra) {
+__device__ __noinline__ float attn_pv(const AttnJob& j) {
   const int lane = threadIdx.x & 31;
-  float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
+  const int n = j.k_hi - j.k_lo;
+  const bf16* vp = j.panel + (size_t)j.k_lo * KVP + lane;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
   int u = 0;
-  for (; u + 4 <= nk; u += 4) {
-    acc0 = fmaf(sc[u], __bfloat162float(Vp[(size_t)u * KVP + lane]), acc0);
-    acc1 = fmaf(sc[u + 1], __bfloat162float(Vp[(size_t)(u + 1) * KVP + lane]), acc1);
-    acc2 = fmaf(sc[u + 2], __bfloat162float(Vp[(size_t)(u + 2) * KVP + lane]), acc2);
-    acc3 = fmaf(sc[u + 3], __bfloat162float(Vp[(size_t)(u + 3) * KVP + lane]), acc3);
+  for (; u + 4 <= n; u += 4) {
+    a0 = fmaf(j.sc[u], __bfloat162float(vp[(size_t)u * KVP]), a0);
+    a1 = fmaf(j.sc[u + 1], __bfloat162float(vp[(size_t)(u + 1) * KVP]), a1);
+    a2 = fmaf(j.sc[u + 2], __bfloat162float(vp[(size_t)(u + 2) * KVP]), a2);
+    a3 = fmaf(j.sc[u + 3], __bfloat162float(vp[(size_t)(u + 3) * KVP]), a3);
   }
-  for (; u < nk; ++u) acc0 = fmaf(sc[u], __bfloat162float(Vp[(size_t)u * KVP + lane]), acc0);
-  float acc = (acc0 + acc1) + (acc2 + acc3);
-  const int n = nk + (has_extra ? 1 : 0);
-  if (has_extra) acc = fmaf(sc[nk], v_extra[lane], acc);
-  return acc * sc[n];
+  for (; u < n; ++u) a0 = fmaf(j.sc[u], __bfloat162float(vp[(size_t)u * KVP]), a0);
+  float acc = (a0 + a1) + (a2 + a3);
+  if (j.extra) acc = fmaf(j.sc[n], j.extra[lane], acc);
+  return acc;
+}
+
+// merge `parts` partial results of image g: part p at buf[(g*4+p)*36 + {0: m, 1: l, 2+c: o_c}]
+__device__ __forceinline__ float attn_merge(const float* buf, int g, int parts) {
+  const int lane = threadIdx.x & 31;
+  float M = -INFINITY;
+  for (int p = 0; p < parts; ++p) M = fmaxf(M, buf[(g * 4 + p) * 36]);
+  float L = 0.f, o = 0.f;
+  for (int p = 0; p < parts; ++p) {
+    const float* b = buf + (g * 4 + p) * 36;
+    if (b[1] > 0.f) { const float w = expf(b[0] - M); L = fmaf(w, b[1], L); o = fmaf(w, b[2 + lane], o); }
+  }
+  return o / L;
 }
 
 __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(NT, 1) decode_cluster_kernel(const ClusterParams P) {
@@ -299,8 +360,6 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(NT, 1) decode_clust
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   Smem sm = carve(smem_raw);
   const Sched sc(P.G, P.ips);
-  const int sps = P.layers * sc.spl + 1;
-  const int64_t total = (int64_t)(P.t_end - P.t_begin) * sps;
   const float scale = rsqrtf((float)HD);       // 1/sqrt(32)
 
   // one-time: zero the A operands (rows >= G stay zero), page ids, PAD flags of the already-known prefix
@@ -315,15 +374,16 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(NT, 1) decode_clust
   }
   __syncthreads();
 
-  int64_t cons = 0;                                     // next stage to consume
-  for (int i = 0; i < NS - 1; ++i) issue_stage(P, sc, sm, i, total, rank, img0, G);
+  int cons = 0;                                         // ring slot of the next stage to consume
+  Cursor cur; cur.t = P.t_begin; cur.layer = 0; cur.j = 0; cur.head = false;
+  for (int i = 0; i < NS - 1; ++i) issue_stage(P, sc, sm, cur, i, rank, img0, G);
   // acquire(): stage `cons` has landed for every thread and slot (cons-1)%NS is free -> refill it
   auto acquire = [&]() -> const uint8_t* {
     cp_wait<NS - 2>();
     __syncthreads();
-    issue_stage(P, sc, sm, cons + NS - 1, total, rank, img0, G);
-    const uint8_t* st = sm.ring + (size_t)(cons % NS) * STAGE_BYTES;
-    ++cons;
+    issue_stage(P, sc, sm, cur, (cons + NS - 1) & (NS - 1), rank, img0, G);
+    const uint8_t* st = sm.ring + (size_t)cons * STAGE_BYTES;
+    cons = (cons + 1) & (NS - 1);
     return st;
   };
   // rows g = warp, warp+8 of a [GM][..] activation are owned by `warp` in the gather / LayerNorm phases
@@ -399,21 +459,37 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(NT, 1) decode_clust
       {
         // q pre-scaled into sm.qc (reused as the query buffer)
         for (int i = tid; i < G * 32; i += NT) sm.qc[i] = sm.qkv[(i >> 5) * 96 + (i & 31)] * scale;
+        const int wpi = min(4, 8 / P.ips);          // warps per image inside a self-KV stage
         for (int s = 0; s < sc.nS; ++s) {
           const uint8_t* st = acquire();            // the barrier inside also publishes sm.qc / rounded k,v
-          const int g0 = s * P.ips, gn = min(P.ips, G - g0);       // ips <= 8: at most one image per warp and stage
-          if (warp < gn) {
-            const int g = g0 + warp;
-            attend_panel(sm.qc + g * 32, reinterpret_cast<const bf16*>(st) + (size_t)warp * P.maxT * KVP, t, sm.padflag + g * 256,
-                         sm.qkv + g * 96 + 32, true, sm.padflag[g * 256 + t] ? 1.0f : 0.0f, sm.scores + (size_t)warp * SCR);
+          const int g0 = s * P.ips, gn = min(P.ips, G - g0);
+          const int gi = warp / wpi, part = warp % wpi;
+          const bool active = gi < gn;
+          AttnJob job{};
+          float2 ml = make_float2(-INFINITY, 0.f);
+          if (active) {
+            const int g = g0 + gi, chunk = (t + wpi - 1) / wpi;
+            job.q = sm.qc + g * 32; job.panel = reinterpret_cast<const bf16*>(st) + (size_t)gi * P.maxT * KVP;
+            job.k_lo = min(t, part * chunk); job.k_hi = min(t, (part + 1) * chunk);
+            job.padf = sm.padflag + g * 256;
+            job.extra = (part == 0) ? sm.qkv + g * 96 + 32 : nullptr;
+            job.extra_bias = sm.padflag[g * 256 + t] ? 1.0f : 0.0f;
+            job.sc = sm.scores + (size_t)warp * SCR;
+            ml = attn_scores(job);
           }
           st = acquire();                           // the matching V panel; the probabilities stay in this warp's score row
-          if (warp < gn) {
-            const int g = g0 + warp;
-            sm.oslice[g * 32 + lane] = pv_panel(reinterpret_cast<const bf16*>(st) + (size_t)warp * P.maxT * KVP, t,
-                                                sm.scores + (size_t)warp * SCR, sm.qkv + g * 96 + 64, true);
+          if (active) {
+            const int g = g0 + gi;
+            job.panel = reinterpret_cast<const bf16*>(st) + (size_t)gi * P.maxT * KVP;
+            if (job.extra) job.extra = sm.qkv + g * 96 + 64;
+            const float o = attn_pv(job);
+            float* pb = sm.ypart + (g * 4 + part) * 36;        // ypart is idle between FFN reductions
+            if (lane == 0) { pb[0] = ml.x; pb[1] = ml.y; }
+            pb[2 + lane] = o;
           }
         }
+        __syncthreads();
+        for (int g = warp; g < G; g += 8) sm.oslice[g * 32 + lane] = attn_merge(sm.ypart, g, wpi);
       }
       cluster.sync();                                                            // #1: head outputs visible
       gather_o();
@@ -435,17 +511,29 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(NT, 1) decode_clust
       for (int s = 0; s < sc.nC; ++s) {
         const uint8_t* st = acquire();
         const int gn = min(2, G - 2 * s);
-        if (warp < gn) {
-          const int g = 2 * s + warp;
-          attend_panel(sm.qc + g * 32, reinterpret_cast<const bf16*>(st) + (size_t)warp * P.S * KVP, P.S, nullptr, nullptr, false, 0.f,
-                       sm.scores + (size_t)warp * SCR);
+        const int gi = warp >> 2, part = warp & 3;   // 4 warps per image, 2 images per stage
+        const bool active = gi < gn;
+        AttnJob job{};
+        float2 ml = make_float2(-INFINITY, 0.f);
+        if (active) {
+          const int g = 2 * s + gi, chunk = (P.S + 3) / 4;
+          job.q = sm.qc + g * 32; job.panel = reinterpret_cast<const bf16*>(st) + (size_t)gi * P.S * KVP;
+          job.k_lo = min(P.S, part * chunk); job.k_hi = min(P.S, (part + 1) * chunk);
+          job.sc = sm.scores + (size_t)warp * SCR;
+          ml = attn_scores(job);
         }
         st = acquire();
-        if (warp < gn) {
-          const int g = 2 * s + warp;
-          sm.oslice[g * 32 + lane] = pv_panel(reinterpret_cast<const bf16*>(st) + (size_t)warp * P.S * KVP, P.S, sm.scores + (size_t)warp * SCR, nullptr, false);
+        if (active) {
+          const int g = 2 * s + gi;
+          job.panel = reinterpret_cast<const bf16*>(st) + (size_t)gi * P.S * KVP;
+          const float o = attn_pv(job);
+          float* pb = sm.ypart + (g * 4 + part) * 36;
+          if (lane == 0) { pb[0] = ml.x; pb[1] = ml.y; }
+          pb[2 + lane] = o;
         }
       }
+      __syncthreads();
+      for (int g = warp; g < G; g += 8) sm.oslice[g * 32 + lane] = attn_merge(sm.ypart, g, 4);
       cluster.sync();                                                            // #3
       gather_o();
       {
@@ -525,7 +613,7 @@ int decode_cluster_supported(const mdc_model* m, const mdc_decode_state* st, int
   if (d.dec_layers < 1 || d.dec_layers > 8 || d.vocab > CS * VSL || d.n_patches + 2 > SCR) return 0;
   if (st->x_override || st->pos_override) return 0;
   if (d.n_patches * KVP * 2 * 2 > STAGE_BYTES) return 0;          // two images' cross panels per stage
-  if (t_end > 256 || st->pages_per_seq > 32) return 0;
+  if (t_end > 256 || st->pages_per_seq > 32 || (d.page_tokens & (d.page_tokens - 1)) != 0) return 0;
   if (getenv("MDC_DECODE_BACKEND") && !strcmp(getenv("MDC_DECODE_BACKEND"), "generic")) return 0;
   return 1;
 }
@@ -579,6 +667,7 @@ int decode_cluster_launch(mdc_model* m, const mdc_decode_state* st, int t_begin,
   if (G > GM) G = GM;
   if (G < 1) G = 1;
   P.G = G;
+  P.pt_shift = 0; while ((1 << P.pt_shift) < d.page_tokens) ++P.pt_shift;
   P.ips = STAGE_BYTES / (P.maxT * KVP * 2);
   if (P.ips > 8) P.ips = 8;
   if (P.ips < 1) MDC_FAIL(-2, "decode_cluster: key capacity %d does not fit a stage", P.maxT);
