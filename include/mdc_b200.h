@@ -165,7 +165,8 @@ int mdc_cross_kv_build(mdc_model* m, const void* memory, int B, void* cross_kv, 
 /* ---- (c,d) autoregressive decode ---------------------------------------------------------------
  * State of one batch being decoded.  All device buffers caller-owned.
  *   tokens   int32 [B, tokens_ld]   column 0..t are known when step t runs; step t writes column t+1
- *   kv_pool  `precision` [n_pages][dec_layers][2][page_tokens][dim]   paged self-attention cache
+ *   kv_pool  `precision` [n_pages][dec_layers][2][page_tokens][dim]   paged self-attention cache (n_pages: pool extent;
+ *            it bounds the TMA view the fused decode kernel builds over the pool)
  *   page_table int32 [B, pages_per_seq]  physical page of logical page j of image b
  *   logits   f32 [B, logits_ld, vocab] or NULL: row (t+1) receives the step-t logits
  *            (= predict(x, prefix)[:, t+1], the reference's shifted layout, model.py:116-123)
@@ -177,7 +178,7 @@ int mdc_cross_kv_build(mdc_model* m, const void* memory, int B, void* cross_kv, 
 typedef struct mdc_decode_state {
   int32_t B;
   int32_t* tokens; int32_t tokens_ld;
-  void* kv_pool; const int32_t* page_table; int32_t pages_per_seq;
+  void* kv_pool; const int32_t* page_table; int32_t pages_per_seq; int32_t n_pages;
   const void* cross_kv;
   float* logits; int32_t logits_ld;
   int32_t logits_row_offset;        /* step t writes logits row t + offset: 1 = predict's shifted layout, 0 = forward's */

@@ -39,7 +39,7 @@ class DecodeState(C.Structure):
     _fields_ = [
         ("B", C.c_int32),
         ("tokens", C.c_void_p), ("tokens_ld", C.c_int32),
-        ("kv_pool", C.c_void_p), ("page_table", C.c_void_p), ("pages_per_seq", C.c_int32),
+        ("kv_pool", C.c_void_p), ("page_table", C.c_void_p), ("pages_per_seq", C.c_int32), ("n_pages", C.c_int32),
         ("cross_kv", C.c_void_p),
         ("logits", C.c_void_p), ("logits_ld", C.c_int32), ("logits_row_offset", C.c_int32),
         ("confs", C.c_void_p), ("confs_ld", C.c_int32),

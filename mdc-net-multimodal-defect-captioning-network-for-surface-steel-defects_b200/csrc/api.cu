@@ -62,5 +62,6 @@ extern "C" int mdc_model_create(mdc_ctx* ctx, const mdc_dims* d, const void* con
 
 extern "C" int mdc_model_destroy(mdc_model* m) {
   if (!m) return 0;
+  decode_cluster_model_destroy(m);
   free(m->w); free(m); return 0;
 }

@@ -38,6 +38,7 @@ struct mdc_model {
   mdc_dims d;
   const void** w;     // weight table copy (host array of device pointers)
   int n_w;
+  void* fused_cache;  // opaque, owned by decode_cluster.cu (cached weight tensor maps)
 };
 
 // ---- typed load/store ----------------------------------------------------------------------
@@ -105,4 +106,5 @@ int gemm_tc_launch(mdc_ctx* ctx, int epilogue, const void* A, int64_t lda, const
                    cudaStream_t s);
 int gemm_tc_supported(int M, int N, int K, int64_t lda, int64_t ldw);
 void gemm_tc_ctx_destroy(mdc_ctx* ctx);
-int mdc_make_tmap_2d(mdc_ctx* ctx, const void* ptr, int64_t rows, int64_t cols, int64_t ld, int box_cols, int box_rows, int swizzle128, void* out_map);
+int mdc_make_tmap_2d(mdc_ctx* ctx, const void* ptr, int64_t rows, int64_t cols, int64_t ld, int box_cols, int box_rows, int swizzle_mode, void* out_map);
+void decode_cluster_model_destroy(mdc_model* m);

@@ -1,31 +1,35 @@
 // decode_cluster.cu -- the whole autoregressive decode loop as ONE persistent, cluster-cooperative kernel
-// (north_star (c)+(d): paged bf16 self-KV, HBM/L2-resident cross-K/V, LayerNorm + residual + token select fused;
+// (north_star (c)+(d): paged bf16 self-KV, L2/HBM-resident cross-K/V, LayerNorm + residual + token select fused;
 //  "no collective inside the decode loop" -- here not even a kernel boundary).
 //
 // Decomposition (model width 256, 8 heads x 32, FFN 2048 -- the configuration inference_p.py:126-129 builds):
-//   * a thread-block CLUSTER of 8 CTAs owns G images (G = ceil(B / #clusters) <= 16) for the entire loop;
-//     clusters never talk to each other, so there is no grid-wide synchronisation at all.
-//   * inside a cluster CTA r owns attention head r and 1/8 of every projection:
-//       in-proj rows of head r (q,k,v), out-proj / cross-q / cross-out rows [32r,32r+32), FFN1 hidden units
-//       [256r,256r+256), FFN2 as a K-split over the same hidden units, vocab rows [40r,40r+40).
-//     Activations (a few KB) are exchanged through DISTRIBUTED SHARED MEMORY with cluster barriers; weights, the
-//     paged self-KV cache and the resident cross-K/V STREAM through a 4-stage cp.async ring (one 33 KB stage =
-//     64 weight rows x 256 k, or one K / V panel), so HBM/L2 traffic stays in flight across phase boundaries.
-//   * projections run on the tensor cores: mma.sync m16n8k16 bf16 with the G <= 16 images as the M dimension.
-//     Activations are split hi+lo into two bf16 operands (x = hi + lo, two MMAs), so the bf16 WEIGHTS are the only
-//     rounding on the fast path -- the same numerics as the unfused fp32-activation kernels in decode.cu.
-//   * LayerNorm+residual are fused into the DSMEM gathers; the head's logits go to a small global buffer, CTA r
-//     runs the greedy / top-k / top-p select for images r, r+8 and publishes the token; one more cluster barrier
-//     and the next step's embedding gather starts.  Weight prefetch runs across steps.
-// The generic kernels in decode.cu remain the path for the fp32 token-exact mode, teacher forcing and other
-// geometries; mdc_decode_steps picks this kernel when the geometry matches.
+//   * a thread-block CLUSTER of 8 CTAs owns a group of G <= 8 images for the entire loop; clusters never talk to
+//     each other, so there is no grid-wide synchronisation at all.  Further groups are processed back to back.
+//   * inside a cluster CTA r owns attention head r and 1/8 of every projection: in-proj rows of head r (q,k,v),
+//     out-proj / cross-q / cross-out rows [32r,32r+32), FFN1 hidden units [256r,256r+256), FFN2 as a K-split over
+//     the same hidden units, vocabulary rows [40r,40r+40).
+//   * everything that is read from HBM/L2 -- weights, the paged self-KV cache, the resident cross-K/V -- is fetched
+//     by a dedicated PRODUCER WARP with TMA (cp.async.bulk.tensor, hardware 128B/64B swizzle) into a 4 x 32 KB
+//     shared-memory ring guarded by full/empty mbarriers; the producer walks the static stage schedule and runs
+//     ahead of the 8 consumer warps across phase, layer and step boundaries.
+//   * projections run on the tensor cores with the roles swapped: the WEIGHT rows are the MMA M dimension
+//     (mma.sync m16n8k16, A fragments by ldmatrix from the swizzled TMA tile), the G <= 8 images are the N = 8
+//     dimension, so no MMA lane is wasted on padding.  Activations are split hi+lo into two bf16 operands
+//     (x = hi + lo, two MMAs), so the bf16 WEIGHTS are the only rounding -- the numerics of the unfused kernels.
+//   * activations (a few KB) are exchanged through DISTRIBUTED SHARED MEMORY, push style: the producer of a slice
+//     writes it into every peer with st.async (...mbarrier::complete_tx), the consumer waits on a local mbarrier
+//     for the expected byte count.  No cluster-wide barrier inside the loop.
+//   * LayerNorm+residual are fused into the all-gathers; the head's logits go straight to the CTA that owns the
+//     image, which runs the greedy / top-k / top-p select and broadcasts the token.
+// The generic kernels in decode.cu remain the path for the fp32 token-exact mode and other geometries;
+// mdc_decode_steps picks this kernel when the geometry matches.
 #include "common.cuh"
-#include "select.cuh"
-#include <cooperative_groups.h>
+#include <cuda.h>
 #include <stdlib.h>
 #include <string.h>
 
-namespace cg = cooperative_groups;
+#define MDC_SEL_SYNC() asm volatile("bar.sync 1, 256;" ::: "memory")
+#include "select.cuh"
 using namespace mdcsel;
 
 namespace {
@@ -35,631 +39,779 @@ constexpr int DM = 256;            // model width
 constexpr int HD = 32;             // head width
 constexpr int FFN = 2048;
 constexpr int FS = FFN / CS;       // hidden units per CTA (256)
-constexpr int NT = 256;            // threads per CTA
-constexpr int GM = 16;             // max images per cluster (the MMA M dimension)
-constexpr int PITCH = DM + 8;      // bf16 elements per padded smem row (528 B: conflict-free fragment loads)
-constexpr int STAGE_ROWS = 64;
-constexpr int STAGE_BYTES = STAGE_ROWS * PITCH * 2;   // 33792
+constexpr int NCT = 256;           // consumer threads (8 warps)
+constexpr int NT = NCT + 32;       // + producer warp
+constexpr int GM = 8;              // max images per cluster pass (the MMA N dimension)
+constexpr int XP = DM + 8;         // bf16 elements per padded activation row (528 B: conflict-free ldmatrix)
+constexpr int STAGE_BYTES = 32768;
 constexpr int NS = 4;              // ring stages
-constexpr int KVP = 40;            // bf16 elements per padded K/V row in a stage (80 B)
-constexpr int VSL = 40;            // vocab rows per CTA (5 n-tiles); 8*40 = 320 >= V
-constexpr int SCR = 264;           // floats per warp score row: <= 256 keys + own key + normaliser
+constexpr int VSL = 40;            // vocab rows per CTA; 8*40 = 320 >= V
+constexpr int PSTR = 36;           // floats per attention partial: m, l, -, -, o[32] (o is 16-byte aligned)
+constexpr int NPART = 9;           // 8 key slices + the step's own key
 
-struct ClusterParams {
-  // weights (bf16 [N,K] row-major unless noted; f32 for biases / norms / tables)
-  const bf16* w_in[8]; const float* b_in[8]; const bf16* w_so[8]; const float* b_so[8];
-  const float* ln1w[8]; const float* ln1b[8];
-  const bf16* w_ca[8]; const float* b_ca[8]; const bf16* w_co[8]; const float* b_co[8];
-  const float* ln2w[8]; const float* ln2b[8];
-  const bf16* w_f1[8]; const float* b_f1[8]; const bf16* w_f2[8]; const float* b_f2[8];
-  const float* ln3w[8]; const float* ln3b[8];
-  const float* emb; const float* pos; const bf16* w_out; const float* b_out;
+// ---- shared memory map (bytes from the 1024-aligned base) ---------------------------------------------------
+constexpr int OFF_RING = 0;
+constexpr int ACT_BYTES = GM * XP * 2;                     // 4224
+constexpr int OFF_XH = OFF_RING + NS * STAGE_BYTES;        // LN output, hi / lo
+constexpr int OFF_XL = OFF_XH + ACT_BYTES;
+constexpr int OFF_OH = OFF_XL + ACT_BYTES;                 // gathered attention output (written by peers)
+constexpr int OFF_OL = OFF_OH + ACT_BYTES;
+constexpr int OFF_FH = OFF_OL + ACT_BYTES;                 // own FFN hidden slice
+constexpr int OFF_FL = OFF_FH + ACT_BYTES;
+constexpr int OFF_XRES = OFF_FL + ACT_BYTES;               // [GM][DM] f32 residual stream
+constexpr int OFF_YRECV = OFF_XRES + GM * DM * 4;          // [GM][DM] f32 all-gathered projection output (peers write)
+constexpr int OFF_F2RECV = OFF_YRECV + GM * DM * 4;        // [CS src][GM][32] f32 FFN2 partial sums (peers write)
+constexpr int OFF_QS = OFF_F2RECV + CS * GM * 32 * 4;      // [GM][32] f32 scaled query of the own head
+constexpr int OFF_KNEW = OFF_QS + GM * 32 * 4;             // [GM][32] f32 this step's key (bf16-rounded)
+constexpr int OFF_VNEW = OFF_KNEW + GM * 32 * 4;
+constexpr int OFF_YTMP = OFF_VNEW + GM * 32 * 4;           // [GM][32] f32 own slice of a projection before the push
+constexpr int OFF_SC = OFF_YTMP + GM * 32 * 4;             // [8 warps][GM][32] f32 scores / probabilities
+constexpr int OFF_PART = OFF_SC + 8 * GM * 32 * 4;         // [GM][NPART][PSTR] f32
+constexpr int OFF_LRECV = OFF_PART + GM * NPART * PSTR * 4;   // [CS src][VSL] f32 logits of the image this CTA selects for
+constexpr int OFF_SEL = OFF_LRECV + CS * VSL * 4;          // select scratch: 320 + 512 floats
+constexpr int OFF_TOK = OFF_SEL + (CS * VSL + 512) * 4;    // [2][GM] int32 (double buffered by step parity)
+constexpr int OFF_PAGES = OFF_TOK + 2 * GM * 4;            // [GM][32] int32
+constexpr int OFF_PADF = OFF_PAGES + GM * 32 * 4;          // [GM][256] u8
+constexpr int OFF_BARS = OFF_PADF + GM * 256;              // mbarriers
+constexpr int NBARS = 2 * NS + 5;
+constexpr int SMEM_USED = OFF_BARS + NBARS * 8;
+constexpr int SMEM_BYTES = SMEM_USED + 1024;               // + alignment slack
+static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
+static_assert(OFF_XH % 16 == 0 && OFF_XRES % 16 == 0 && OFF_BARS % 8 == 0, "alignment");
+
+enum { BAR_FULL = 0, BAR_EMPTY = NS, BAR_O = 2 * NS, BAR_Y, BAR_F2, BAR_LG, BAR_TOK };
+
+struct __align__(64) FusedParams {
+  CUtensorMap m_in[8], m_so[8], m_ca[8], m_co[8], m_f1[8], m_f2[8];
+  CUtensorMap m_head, m_ckv, m_pool;
+  const float* b_in[8]; const float* b_so[8]; const float* ln1w[8]; const float* ln1b[8];
+  const float* b_ca[8]; const float* b_co[8]; const float* ln2w[8]; const float* ln2b[8];
+  const float* b_f1[8]; const float* b_f2[8]; const float* ln3w[8]; const float* ln3b[8];
+  const float* emb; const float* pos; const float* b_out;
   int layers, vocab, S, pad_idx;
-  // batch state
-  int B, G;
+  int B, G, n_groups;
   int32_t* tokens; int tokens_ld;
   bf16* kv_pool; const int32_t* page_table; int pages_per_seq, PT;
-  const bf16* cross_kv;                    // [layer][B*S][2*DM]
-  float* step_logits;                      // [B][vocab] scratch (L2)
   float* logits_out; int64_t logits_img_stride; int logits_row_offset;
   float* confs; int confs_ld;
   const float* uniforms; int uniforms_ld; int top_k; float top_p; int forced;
-  int t_begin, t_end, maxT;                // maxT: padded key capacity per image in a self-KV stage
-  int pt_shift;                            // log2(PT)
+  int t_begin, t_end;
+  int np_max;                              // pages per image panel in a self-KV stage (capacity for t_end keys)
   int ips;                                 // images per self-KV stage
 };
 
-// ---- small helpers -------------------------------------------------------------------------------------
-__device__ __forceinline__ void cp16(void* sdst, const void* gsrc) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(sdst)), "l"(gsrc) : "memory");
+// ---- PTX helpers ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
-__device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N> __device__ __forceinline__ void cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// bounded wait: a protocol bug traps (reported as a launch failure) instead of hanging the GPU box
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0, spins = 0;
+  long long t0 = 0;
+  while (true) {
+    asm volatile("{\n\t.reg .pred P1;\n\tmbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\tselp.u32 %0, 1, 0, P1;\n\t}\n"
+                 : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    if (done) break;
+    if ((++spins & 255u) == 0) {
+      long long now = clock64();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 3000000000LL) __trap();   // ~1.5 s
+    }
+  }
+}
+__device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t rank) {
+  uint32_t r; asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank)); return r;
+}
+__device__ __forceinline__ void st_async_b32(uint32_t raddr, uint32_t v, uint32_t rbar) {
+  asm volatile("st.async.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(raddr), "r"(v), "r"(rbar) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void cbar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }   // the 8 consumer warps
+__device__ __forceinline__ void tma_2d(const CUtensorMap* map, uint32_t bar, uint32_t dst, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void ldsm_x4(uint32_t* r, uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
 __device__ __forceinline__ void mma16816(float* c, const uint32_t* a, uint32_t b0, uint32_t b1) {
   asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
-
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v; asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr)); return v;
+}
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b); return *reinterpret_cast<uint32_t*>(&h);
+}
 __device__ __forceinline__ void split_store(bf16* hi, bf16* lo, int idx, float x) {
   bf16 h = __float2bfloat16_rn(x);
   hi[idx] = h; lo[idx] = __float2bfloat16_rn(x - __bfloat162float(h));
 }
 
-struct Smem {
-  uint8_t* ring;        // NS * STAGE_BYTES
-  bf16 *a_hi, *a_lo;    // [GM][PITCH]  A operand of the width-256 projections
-  bf16 *f_hi, *f_lo;    // [GM][PITCH]  A operand of FFN2 (own hidden slice)
-  float* xres;          // [GM][DM]     residual stream
-  float* qkv;           // [GM][96]     own head's q|k|v
-  float* qc;            // [GM][32]
-  float* oslice;        // [GM][32]     DSMEM-exposed: own head's attention output
-  float* yslice;        // [GM][32]     DSMEM-exposed: own 32-column slice of a projection
-  float* ypart;         // [GM][DM]     DSMEM-exposed: FFN2 partial sums
-  float* scores;        // [8 warps][SCR]   (also the select scratch)
-  int* pages;           // [GM][32]
-  uint8_t* padflag;     // [GM][256]
-};
-
-__device__ __forceinline__ Smem carve(uint8_t* base) {
-  Smem s; uint8_t* p = base;
-  s.ring = p; p += NS * STAGE_BYTES;
-  s.a_hi = (bf16*)p; p += GM * PITCH * 2; s.a_lo = (bf16*)p; p += GM * PITCH * 2;
-  s.f_hi = (bf16*)p; p += GM * PITCH * 2; s.f_lo = (bf16*)p; p += GM * PITCH * 2;
-  s.xres = (float*)p; p += GM * DM * 4;
-  s.qkv = (float*)p; p += GM * 96 * 4;
-  s.qc = (float*)p; p += GM * 32 * 4;
-  s.oslice = (float*)p; p += GM * 32 * 4;
-  s.yslice = (float*)p; p += GM * 32 * 4;
-  s.ypart = (float*)p; p += GM * DM * 4;
-  s.scores = (float*)p; p += 8 * SCR * 4;
-  s.pages = (int*)p; p += GM * 32 * 4;
-  s.padflag = p; p += GM * 256;
-  return s;
-}
-constexpr int SMEM_BYTES = NS * STAGE_BYTES + 4 * GM * PITCH * 2 + GM * DM * 4 + GM * 96 * 4 + 3 * GM * 32 * 4 + GM * DM * 4 +
-                           8 * SCR * 4 + GM * 32 * 4 + GM * 256;
-
-// ---- the stage schedule -------------------------------------------------------------------------------
-// per layer: 0,1 in-proj (q+k rows | v rows); (selfK, selfV) x nS; 1 self-out; 1 cross-q; (crossK, crossV) x nC;
-//            1 cross-out; 4 FFN1; 4 FFN2.   After the last layer: 1 head stage.
-struct Sched {
-  int nS, nC, spl, sps;   // self stages, cross stages, stages per layer, stages per step
-  __device__ Sched(int G, int ips) {
-    nS = (G + ips - 1) / ips; nC = (G + 1) / 2;
-    spl = 2 + 2 * nS + 2 + 2 * nC + 1 + 8;
-    sps = 0;
-  }
-};
-
-enum { K_INA = 0, K_INB, K_SELFK, K_SELFV, K_SOUT, K_CQ, K_CROSSK, K_CROSSV, K_COUT, K_F1, K_F2, K_HEAD };
-
-struct StageId { int kind, sub, layer, t; };
-
-// Incremental position of the PRODUCER in the static stage schedule (no div/mod on the hot path).
-struct Cursor {
-  int t, layer, j; bool head;
-  __device__ __forceinline__ void advance(const Sched& sc, int layers) {
-    if (head) { head = false; ++t; layer = 0; j = 0; }
-    else if (++j == sc.spl) { j = 0; if (++layer == layers) head = true; }
-  }
-  __device__ __forceinline__ StageId id(const Sched& sc) const {
-    StageId r; r.t = t; r.layer = layer; r.sub = 0;
-    if (head) { r.kind = K_HEAD; return r; }
-    int q = j;
-    if (q < 2) { r.kind = q == 0 ? K_INA : K_INB; return r; } q -= 2;
-    if (q < 2 * sc.nS) { r.kind = (q & 1) ? K_SELFV : K_SELFK; r.sub = q >> 1; return r; } q -= 2 * sc.nS;
-    if (q == 0) { r.kind = K_SOUT; return r; } q -= 1;
-    if (q == 0) { r.kind = K_CQ; return r; } q -= 1;
-    if (q < 2 * sc.nC) { r.kind = (q & 1) ? K_CROSSV : K_CROSSK; r.sub = q >> 1; return r; } q -= 2 * sc.nC;
-    if (q == 0) { r.kind = K_COUT; return r; } q -= 1;
-    if (q < 4) { r.kind = K_F1; r.sub = q; return r; } q -= 4;
-    r.kind = K_F2; r.sub = q; return r;
-  }
-};
-
-// copy `nrows` weight rows (256 bf16 each, source pitch `spitch` elements) to stage rows [dst0, ...): 32 chunks of 16 B per row,
-// one warp-pass = one row
-__device__ __forceinline__ void issue_rows(uint8_t* stage, int dst0, const bf16* W, int nrows, int spitch) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const bf16* src = W + (int64_t)warp * spitch + lane * 8;
-  uint8_t* dst = stage + (size_t)(dst0 + warp) * (PITCH * 2) + lane * 16;
-  for (int r = warp; r < nrows; r += 8) { cp16(dst, src); src += (int64_t)8 * spitch; dst += 8 * PITCH * 2; }
-}
-
-// copy nk keys (64 B = 4 chunks each) of one K or V panel: 4 lanes per key, division-free
-__device__ __forceinline__ void issue_panel_contig(uint8_t* dst_panel, const bf16* src0, int64_t key_pitch, int nk) {
-  const int ch = threadIdx.x & 3;
-  for (int ku = threadIdx.x >> 2; ku < nk; ku += NT / 4)
-    cp16(dst_panel + ((size_t)ku * KVP + ch * 8) * 2, src0 + (int64_t)ku * key_pitch + ch * 8);
-}
-
-__device__ void issue_stage(const ClusterParams& P, const Sched& sc, const Smem& sm, Cursor& cur, int slot, int rank, int img0, int G) {
-  if (cur.t < P.t_end) {
-    uint8_t* stage = sm.ring + (size_t)slot * STAGE_BYTES;
-    const StageId id = cur.id(sc);
-    const int l = id.layer;
-    switch (id.kind) {
-      case K_INA:
-        issue_rows(stage, 0, P.w_in[l] + (int64_t)(rank * HD) * DM, 32, DM);               // q rows of head `rank`
-        issue_rows(stage, 32, P.w_in[l] + (int64_t)(DM + rank * HD) * DM, 32, DM);          // k rows
-        break;
-      case K_INB: issue_rows(stage, 0, P.w_in[l] + (int64_t)(2 * DM + rank * HD) * DM, 32, DM); break;   // v rows
-      case K_SOUT: issue_rows(stage, 0, P.w_so[l] + (int64_t)(rank * 32) * DM, 32, DM); break;
-      case K_CQ: issue_rows(stage, 0, P.w_ca[l] + (int64_t)(rank * 32) * DM, 32, DM); break;             // q part = first DM rows of in_proj
-      case K_COUT: issue_rows(stage, 0, P.w_co[l] + (int64_t)(rank * 32) * DM, 32, DM); break;
-      case K_F1: issue_rows(stage, 0, P.w_f1[l] + (int64_t)(rank * FS + id.sub * 64) * DM, 64, DM); break;
-      case K_F2: issue_rows(stage, 0, P.w_f2[l] + (int64_t)(id.sub * 64) * FFN + rank * FS, 64, FFN); break;   // K-split: own hidden columns
-      case K_HEAD: {
-        const int r0 = rank * VSL, n = max(0, min(VSL, P.vocab - r0));
-        issue_rows(stage, 0, P.w_out + (int64_t)r0 * DM, n, DM);
-        break;
-      }
-      case K_SELFK: case K_SELFV: {
-        // keys 0..t-1 of head `rank` for images [sub*ips, ...); the step's own key t comes from shared memory
-        const int which = id.kind == K_SELFV, nk = id.t;
-        const int g0 = id.sub * P.ips, gn = min(P.ips, G - g0);
-        const int64_t plane = (int64_t)P.PT * DM;
-        const int ch = threadIdx.x & 3;
-        for (int gi = 0; gi < gn; ++gi) {
-          const int* pg = sm.pages + (g0 + gi) * 32;
-          uint8_t* dstp = stage + (size_t)gi * P.maxT * KVP * 2;
-          for (int ku = threadIdx.x >> 2; ku < nk; ku += NT / 4) {
-            const bf16* src = P.kv_pool + (((int64_t)pg[ku >> P.pt_shift] * P.layers + l) * 2 + which) * plane +
-                              (int64_t)(ku & (P.PT - 1)) * DM + rank * HD + ch * 8;
-            cp16(dstp + ((size_t)ku * KVP + ch * 8) * 2, src);
-          }
-        }
-        break;
-      }
-      case K_CROSSK: case K_CROSSV: {
-        const int which = id.kind == K_CROSSV;
-        const int g0 = id.sub * 2, gn = min(2, G - g0), S = P.S;
-        const bf16* base = P.cross_kv + (int64_t)l * P.B * S * 2 * DM + which * DM + rank * HD;
-        for (int gi = 0; gi < gn; ++gi)
-          issue_panel_contig(stage + (size_t)gi * S * KVP * 2, base + (int64_t)(img0 + g0 + gi) * S * 2 * DM, 2 * DM, S);
-        break;
-      }
-    }
-    cur.advance(sc, P.layers);
-  }
-  cp_commit();     // always commit (possibly empty) so that wait_group accounting stays uniform
-}
-
-__device__ __forceinline__ void ldsm_x4(uint32_t* r, const bf16* p) {
-  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"((uint32_t)__cvta_generic_to_shared(p)));
-}
-__device__ __forceinline__ void ldsm_x2(uint32_t& r0, uint32_t& r1, const bf16* p) {
-  asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0,%1}, [%2];" : "=r"(r0), "=r"(r1) : "r"((uint32_t)__cvta_generic_to_shared(p)));
-}
-
-// One 16x8 output tile of a projection: C[g][n] = sum_k (Ahi+Alo)[g][k] * W[tile rows n][k], k = 0..255.
-// Shared (NOT inlined) by every projection phase to keep the instruction footprint small.  Fragments come from
-// ldmatrix (conflict-free with the 528-byte row pitch); four independent accumulator chains (hi/lo x even/odd
-// k-step) hide the HMMA latency.
-__device__ __noinline__ float4 mma_tile(const bf16* Wtile /*8 rows of the stage*/, const bf16* Ahi, const bf16* Alo) {
+// One 16-row tile of a projection with the weights as the M operand:
+//   acc[0..3] = D[m0+g][img 2q], D[m0+g][2q+1], D[m0+g+8][2q], D[m0+g+8][2q+1]   (g = lane/4, q = lane%4)
+// wblk: shared address of the TMA row block [4 k-blocks][R rows][128 B] (SWIZZLE_128B); bh/bl: hi/lo activations
+// [8 images][XP] bf16.  Four independent accumulator chains hide the HMMA latency.
+template <int R>
+__device__ __forceinline__ void mma_mtile(uint32_t wblk, int m0, uint32_t bh, uint32_t bl, float* acc) {
   const int lane = threadIdx.x & 31;
-  const bf16* wp = Wtile + (size_t)(lane & 7) * PITCH + ((lane >> 3) & 1) * 8;
-  const int arow = (lane & 7) + ((lane >> 3) & 1) * 8, akof = (lane >> 4) * 8;
-  const bf16* ah = Ahi + (size_t)arow * PITCH + akof;
-  const bf16* al = Alo + (size_t)arow * PITCH + akof;
+  const int row = m0 + (lane & 7) + ((lane >> 3) & 1) * 8, csel = lane >> 4, sw = lane & 7;
+  const uint32_t a_base = wblk + row * 128;
+  const uint32_t boff = (lane & 7) * (XP * 2) + (lane >> 3) * 16;
   float c0[4] = {0, 0, 0, 0}, c1[4] = {0, 0, 0, 0}, c2[4] = {0, 0, 0, 0}, c3[4] = {0, 0, 0, 0};
-#pragma unroll 2
-  for (int k0 = 0; k0 < DM; k0 += 32) {
-    uint32_t b0, b1, b2, b3, h0[4], l0[4], h1[4], l1[4];
-    ldsm_x2(b0, b1, wp + k0); ldsm_x2(b2, b3, wp + k0 + 16);
-    ldsm_x4(h0, ah + k0); ldsm_x4(l0, al + k0); ldsm_x4(h1, ah + k0 + 16); ldsm_x4(l1, al + k0 + 16);
-    mma16816(c0, h0, b0, b1); mma16816(c1, l0, b0, b1);
-    mma16816(c2, h1, b2, b3); mma16816(c3, l1, b2, b3);
-  }
-  return make_float4((c0[0] + c2[0]) + (c1[0] + c3[0]), (c0[1] + c2[1]) + (c1[1] + c3[1]),
-                     (c0[2] + c2[2]) + (c1[2] + c3[2]), (c0[3] + c2[3]) + (c1[3] + c3[3]));
-}
-
-// one ring stage of a projection: warp w computes n-tile w (8 output columns) and hands the 16x8 tile to `store(row, col, value)`
-template <typename Store>
-__device__ __forceinline__ void mma_stage(const uint8_t* stage, int n_tiles, const bf16* Ahi, const bf16* Alo, Store store) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (warp >= n_tiles) return;
-  const float4 c = mma_tile(reinterpret_cast<const bf16*>(stage) + (size_t)warp * 8 * PITCH, Ahi, Alo);
-  const int r0 = lane >> 2, cc = warp * 8 + 2 * (lane & 3);
-  store(r0, cc, c.x); store(r0, cc + 1, c.y); store(r0 + 8, cc, c.z); store(r0 + 8, cc + 1, c.w);
-}
-
-// ---- attention of one query against a key panel, split over several warps (flash-decoding style) ------------------
-// A warp owns keys [k_lo,k_hi) of one image (plus, for part 0 of self-attention, the step's own key held in shared
-// memory).  Pass 1 parks exp(s - m_local) in the warp's score row and returns (m_local, l_local); pass 2 (after the V
-// panel has landed) accumulates the un-normalised output for channel `lane`.  Partials are merged by attn_merge().
-struct AttnJob {
-  const float* q;            // smem, 32, pre-scaled
-  const bf16* panel;         // K or V panel of this image (rows of KVP bf16)
-  int k_lo, k_hi;
-  const uint8_t* padf;       // PAD flags per key (self) or null (cross)
-  const float* extra;        // own key / value (smem, 32 f32) or null
-  float extra_bias;
-  float* sc;                 // this warp's score row
-};
-
-__device__ __noinline__ float2 attn_scores(const AttnJob& j) {
-  const int lane = threadIdx.x & 31;
-  float qv[32];
 #pragma unroll
-  for (int i = 0; i < 32; ++i) qv[i] = j.q[i];
+  for (int i = 0; i < 8; ++i) {                 // two k-steps (32 k) per iteration
+    const int kb = i >> 1, ch = (i & 1) * 4;
+    uint32_t a0[4], a1[4], xh[4], xl[4];
+    ldsm_x4(a0, a_base + kb * (R * 128) + (((ch + csel) ^ sw) << 4));
+    ldsm_x4(a1, a_base + kb * (R * 128) + (((ch + 2 + csel) ^ sw) << 4));
+    ldsm_x4(xh, bh + boff + i * 64);
+    ldsm_x4(xl, bl + boff + i * 64);
+    mma16816(c0, a0, xh[0], xh[1]); mma16816(c1, a0, xl[0], xl[1]);
+    mma16816(c2, a1, xh[2], xh[3]); mma16816(c3, a1, xl[2], xl[3]);
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) acc[j] = (c0[j] + c2[j]) + (c1[j] + c3[j]);
+}
+
+// ---- attention of one query against a slice of a key / value panel ---------------------------------------------
+// panel: shared address, key u at u*64 bytes, 16-byte chunk c stored at c ^ ((u >> 1) & 3) (TMA SWIZZLE_64B).
+// 4 lanes per key (one chunk each), 8 keys per pass.  Scores / probabilities are parked in sc[0..hi-lo).
+__device__ __forceinline__ float2 attn_qk(uint32_t panel, const float* q, int lo, int hi, const uint8_t* padf, float* sc) {
+  const int lane = threadIdx.x & 31, kslot = lane >> 2, sub = lane & 3;
+  const float4 qa = *reinterpret_cast<const float4*>(q + sub * 8), qb = *reinterpret_cast<const float4*>(q + sub * 8 + 4);
   float mx = -INFINITY;
-  for (int u = j.k_lo + lane; u < j.k_hi; u += 32) {
-    const uint4* kr = reinterpret_cast<const uint4*>(j.panel + (size_t)u * KVP);
-    float s = 0.f;
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      uint4 raw = kr[c];
-      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) { float2 f = __bfloat1622float2(h[i]); s = fmaf(qv[c * 8 + 2 * i], f.x, s); s = fmaf(qv[c * 8 + 2 * i + 1], f.y, s); }
+  for (int u0 = lo; u0 < hi; u0 += 8) {
+    const int u = u0 + kslot; const bool ok = u < hi; const int uu = ok ? u : lo;
+    const uint4 raw = lds128(panel + uu * 64 + ((sub ^ ((uu >> 1) & 3)) << 4));
+    float s = qa.x * __uint_as_float(raw.x << 16);
+    s = fmaf(qa.y, __uint_as_float(raw.x & 0xffff0000u), s);
+    s = fmaf(qa.z, __uint_as_float(raw.y << 16), s); s = fmaf(qa.w, __uint_as_float(raw.y & 0xffff0000u), s);
+    s = fmaf(qb.x, __uint_as_float(raw.z << 16), s); s = fmaf(qb.y, __uint_as_float(raw.z & 0xffff0000u), s);
+    s = fmaf(qb.z, __uint_as_float(raw.w << 16), s); s = fmaf(qb.w, __uint_as_float(raw.w & 0xffff0000u), s);
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    if (ok) {
+      if (padf && padf[u]) s += 1.0f;
+      mx = fmaxf(mx, s);
+      if (sub == 0) sc[u - lo] = s;
     }
-    if (j.padf && j.padf[u]) s += 1.0f;
-    j.sc[u - j.k_lo] = s; mx = fmaxf(mx, s);
-  }
-  const int n = j.k_hi - j.k_lo;
-  if (j.extra) {
-    float s = 0.f;
-#pragma unroll
-    for (int i = 0; i < 32; ++i) s = fmaf(qv[i], j.extra[i], s);
-    s += j.extra_bias;
-    if (lane == 0) j.sc[n] = s;
-    mx = fmaxf(mx, s);
   }
   mx = warp_max(mx);
   __syncwarp();
-  const int nn = n + (j.extra ? 1 : 0);
-  float sum = 0.f;
-  for (int u = lane; u < nn; u += 32) { float e = expf(j.sc[u] - mx); j.sc[u] = e; sum += e; }
-  sum = warp_sum(sum);
+  const int n = hi - lo;
+  float e = 0.f;
+  if (lane < n) { e = expf(sc[lane] - mx); sc[lane] = e; }
+  const float sum = warp_sum(e);
   __syncwarp();
   return make_float2(mx, sum);
 }
 
-__device__ __noinline__ float attn_pv(const AttnJob& j) {
-  const int lane = threadIdx.x & 31;
-  const int n = j.k_hi - j.k_lo;
-  const bf16* vp = j.panel + (size_t)j.k_lo * KVP + lane;
-  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-  int u = 0;
-  for (; u + 4 <= n; u += 4) {
-    a0 = fmaf(j.sc[u], __bfloat162float(vp[(size_t)u * KVP]), a0);
-    a1 = fmaf(j.sc[u + 1], __bfloat162float(vp[(size_t)(u + 1) * KVP]), a1);
-    a2 = fmaf(j.sc[u + 2], __bfloat162float(vp[(size_t)(u + 2) * KVP]), a2);
-    a3 = fmaf(j.sc[u + 3], __bfloat162float(vp[(size_t)(u + 3) * KVP]), a3);
+__device__ __forceinline__ void attn_pv(uint32_t panel, int lo, int hi, const float* sc, float* out) {
+  const int lane = threadIdx.x & 31, kslot = lane >> 2, sub = lane & 3;
+  float a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (int u0 = lo; u0 < hi; u0 += 8) {
+    const int u = u0 + kslot; const bool ok = u < hi; const int uu = ok ? u : lo;
+    const float p = ok ? sc[u - lo] : 0.f;
+    const uint4 raw = lds128(panel + uu * 64 + ((sub ^ ((uu >> 1) & 3)) << 4));
+    a[0] = fmaf(p, __uint_as_float(raw.x << 16), a[0]); a[1] = fmaf(p, __uint_as_float(raw.x & 0xffff0000u), a[1]);
+    a[2] = fmaf(p, __uint_as_float(raw.y << 16), a[2]); a[3] = fmaf(p, __uint_as_float(raw.y & 0xffff0000u), a[3]);
+    a[4] = fmaf(p, __uint_as_float(raw.z << 16), a[4]); a[5] = fmaf(p, __uint_as_float(raw.z & 0xffff0000u), a[5]);
+    a[6] = fmaf(p, __uint_as_float(raw.w << 16), a[6]); a[7] = fmaf(p, __uint_as_float(raw.w & 0xffff0000u), a[7]);
   }
-  for (; u < n; ++u) a0 = fmaf(j.sc[u], __bfloat162float(vp[(size_t)u * KVP]), a0);
-  float acc = (a0 + a1) + (a2 + a3);
-  if (j.extra) acc = fmaf(j.sc[n], j.extra[lane], acc);
-  return acc;
+#pragma unroll
+  for (int o = 4; o < 32; o <<= 1) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a[j] += __shfl_xor_sync(0xffffffffu, a[j], o);
+  }
+  if (kslot == 0) {
+    *reinterpret_cast<float4*>(out + sub * 8) = make_float4(a[0], a[1], a[2], a[3]);
+    *reinterpret_cast<float4*>(out + sub * 8 + 4) = make_float4(a[4], a[5], a[6], a[7]);
+  }
 }
 
-// merge `parts` partial results of image g: part p at buf[(g*4+p)*36 + {0: m, 1: l, 2+c: o_c}]
-__device__ __forceinline__ float attn_merge(const float* buf, int g, int parts) {
+// merge the partial results of one image (lane = channel); parts with l == 0 are empty
+__device__ __forceinline__ float attn_merge(const float* parts, int nparts) {
   const int lane = threadIdx.x & 31;
   float M = -INFINITY;
-  for (int p = 0; p < parts; ++p) M = fmaxf(M, buf[(g * 4 + p) * 36]);
+  for (int p = 0; p < nparts; ++p) { const float* b = parts + p * PSTR; if (b[1] > 0.f) M = fmaxf(M, b[0]); }
   float L = 0.f, o = 0.f;
-  for (int p = 0; p < parts; ++p) {
-    const float* b = buf + (g * 4 + p) * 36;
-    if (b[1] > 0.f) { const float w = expf(b[0] - M); L = fmaf(w, b[1], L); o = fmaf(w, b[2 + lane], o); }
+  for (int p = 0; p < nparts; ++p) {
+    const float* b = parts + p * PSTR;
+    if (b[1] > 0.f) { const float w = expf(b[0] - M); L = fmaf(w, b[1], L); o = fmaf(w, b[4 + lane], o); }
   }
   return o / L;
 }
 
-__global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(NT, 1) decode_cluster_kernel(const ClusterParams P) {
-  extern __shared__ __align__(16) uint8_t smem_raw[];
-  cg::cluster_group cluster = cg::this_cluster();
-  const int rank = (int)cluster.block_rank();
-  const int cid = blockIdx.x / CS;
-  const int img0 = cid * P.G;
-  const int G = min(P.G, P.B - img0);          // images of this cluster (>= 1 by construction)
+__global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(NT, 1) decode_fused_kernel(const __grid_constant__ FusedParams P) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);      // pointer arithmetic keeps the shared address space
+  const uint32_t sbase = smem_u32(smem);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  Smem sm = carve(smem_raw);
-  const Sched sc(P.G, P.ips);
-  const float scale = rsqrtf((float)HD);       // 1/sqrt(32)
+  uint32_t rank; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+  const int cid = blockIdx.x / CS, n_clusters = gridDim.x / CS;
 
-  // one-time: zero the A operands (rows >= G stay zero), page ids, PAD flags of the already-known prefix
-  for (int i = tid; i < 4 * GM * PITCH; i += NT) sm.a_hi[i] = __float2bfloat16_rn(0.f);   // a_hi,a_lo,f_hi,f_lo are contiguous
-  for (int i = tid; i < GM * 32; i += NT) {
-    const int g = i >> 5, j = i & 31;
-    sm.pages[i] = (g < G && j < P.pages_per_seq) ? P.page_table[(int64_t)(img0 + g) * P.pages_per_seq + j] : 0;
+  bf16* xh = (bf16*)(smem + OFF_XH); bf16* xl = (bf16*)(smem + OFF_XL);
+  bf16* fh = (bf16*)(smem + OFF_FH); bf16* fl = (bf16*)(smem + OFF_FL);
+  float* xres = (float*)(smem + OFF_XRES); float* yrecv = (float*)(smem + OFF_YRECV); float* f2recv = (float*)(smem + OFF_F2RECV);
+  float* qs = (float*)(smem + OFF_QS); float* knew = (float*)(smem + OFF_KNEW); float* vnew = (float*)(smem + OFF_VNEW);
+  float* ytmp = (float*)(smem + OFF_YTMP); float* scb = (float*)(smem + OFF_SC); float* part = (float*)(smem + OFF_PART);
+  float* lrecv = (float*)(smem + OFF_LRECV); float* selbuf = (float*)(smem + OFF_SEL);
+  int* tokbuf = (int*)(smem + OFF_TOK); int* pages = (int*)(smem + OFF_PAGES); uint8_t* padflag = smem + OFF_PADF;
+  const uint32_t bars = sbase + OFF_BARS;
+  auto bar = [&](int i) -> uint32_t { return bars + i * 8; };
+
+  if (tid == 0) {
+    for (int i = 0; i < NS; ++i) { mbar_init(bar(BAR_FULL + i), 1); mbar_init(bar(BAR_EMPTY + i), 8); }
+    for (int i = BAR_O; i <= BAR_TOK; ++i) mbar_init(bar(i), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  for (int i = tid; i < GM * 256; i += NT) {
-    const int g = i >> 8, u = i & 255;
-    sm.padflag[i] = (g < G && u < P.t_begin) ? (P.tokens[(int64_t)(img0 + g) * P.tokens_ld + u] == P.pad_idx) : 0;
-  }
+  // zero the activation operands once (rows >= G must stay finite)
+  for (int i = tid; i < 6 * ACT_BYTES / 4; i += NT) reinterpret_cast<uint32_t*>(smem + OFF_XH)[i] = 0u;
   __syncthreads();
+  cluster_sync_all();
 
-  int cons = 0;                                         // ring slot of the next stage to consume
-  Cursor cur; cur.t = P.t_begin; cur.layer = 0; cur.j = 0; cur.head = false;
-  for (int i = 0; i < NS - 1; ++i) issue_stage(P, sc, sm, cur, i, rank, img0, G);
-  // acquire(): stage `cons` has landed for every thread and slot (cons-1)%NS is free -> refill it
-  auto acquire = [&]() -> const uint8_t* {
-    cp_wait<NS - 2>();
+  const float scale = rsqrtf((float)HD);
+  const int L = P.layers, S = P.S;
+  const int nC = (P.G + 1) / 2;                       // cross stages (2 images each), by the full group size
+  const int nS = (P.G + P.ips - 1) / P.ips;           // self stages
+  const uint32_t self_panel = (uint32_t)P.np_max * 1024u;
+  const uint32_t cross_panel = ((uint32_t)S * 64u + 1023u) & ~1023u;
+
+  // ring cursors (producer and consumers keep their own copies)
+  uint32_t slot = 0, phase = 0;
+  uint32_t ph_o = 0, ph_y = 0, ph_f2 = 0, ph_lg = 0, ph_tok = 0;
+
+  for (int grp = cid; grp < P.n_groups; grp += n_clusters) {
+    const int img0 = grp * P.G;
+    const int G = min(P.G, P.B - img0);
+    // ---- per-group init: page ids, PAD flags of the known prefix ---------------------------------------------
+    for (int i = tid; i < GM * 32; i += NT) {
+      const int g = i >> 5, j = i & 31;
+      pages[i] = (g < G && j < P.pages_per_seq) ? P.page_table[(int64_t)(img0 + g) * P.pages_per_seq + j] : 0;
+    }
+    for (int i = tid; i < GM * 256; i += NT) {
+      const int g = i >> 8, u = i & 255;
+      padflag[i] = (g < G && u < P.t_begin) ? (P.tokens[(int64_t)(img0 + g) * P.tokens_ld + u] == P.pad_idx) : 0;
+    }
     __syncthreads();
-    issue_stage(P, sc, sm, cur, (cons + NS - 1) & (NS - 1), rank, img0, G);
-    const uint8_t* st = sm.ring + (size_t)cons * STAGE_BYTES;
-    cons = (cons + 1) & (NS - 1);
-    return st;
-  };
-  // rows g = warp, warp+8 of a [GM][..] activation are owned by `warp` in the gather / LayerNorm phases
-  auto ln_gather = [&](const float* lnw, const float* lnb) {
-    // x = LN(xres + gathered yslice); writes xres and the hi/lo A operand.  lane l <-> column 32p + l of peer p
-    for (int g = warp; g < G; g += 8) {
-      float v[CS]; float s = 0.f;
-#pragma unroll
-      for (int p = 0; p < CS; ++p) {
-        const float* peer = cluster.map_shared_rank(sm.yslice, p);
-        v[p] = sm.xres[g * DM + 32 * p + lane] + peer[g * 32 + lane];
-        s += v[p];
-      }
-      const float mean = warp_sum(s) * (1.0f / DM);
-      float q = 0.f;
-#pragma unroll
-      for (int p = 0; p < CS; ++p) { const float d = v[p] - mean; q += d * d; }
-      const float rstd = 1.0f / sqrtf(warp_sum(q) * (1.0f / DM) + 1e-5f);
-#pragma unroll
-      for (int p = 0; p < CS; ++p) {
-        const int c = 32 * p + lane;
-        const float xn = (v[p] - mean) * rstd * __ldg(lnw + c) + __ldg(lnb + c);
-        sm.xres[g * DM + c] = xn;
-        split_store(sm.a_hi, sm.a_lo, g * PITCH + c, xn);
-      }
-    }
-  };
-  auto gather_o = [&]() {       // A operand <- concatenated head outputs
-    for (int g = warp; g < G; g += 8) {
-#pragma unroll
-      for (int p = 0; p < CS; ++p) {
-        const float* peer = cluster.map_shared_rank(sm.oslice, p);
-        split_store(sm.a_hi, sm.a_lo, g * PITCH + 32 * p + lane, peer[g * 32 + lane]);
-      }
-    }
-  };
+    cluster_sync_all();          // no peer may push into this CTA before its buffers are set up for the group
 
-  for (int t = P.t_begin; t < P.t_end; ++t) {
-    // ---- embedding + positional row (model.py:98-101); PAD flag of the token at position t --------------
-    for (int g = warp; g < G; g += 8) {
-      const int tok = __ldcg(P.tokens + (int64_t)(img0 + g) * P.tokens_ld + t);
-      if (lane == 0) sm.padflag[g * 256 + t] = (tok == P.pad_idx);
+    if (warp == 8) {
+      // =================================== PRODUCER WARP ===================================================
+      auto acquire = [&]() -> uint32_t {           // wait until the consumers released the slot
+        mbar_wait(bar(BAR_EMPTY + slot), phase ^ 1);
+        return sbase + OFF_RING + slot * STAGE_BYTES;
+      };
+      auto advance = [&]() { if (++slot == NS) { slot = 0; phase ^= 1; } };
+      // one weight row block: 4 k-blocks of [R rows x 64 k]
+      auto load_rows = [&](const CUtensorMap* m, uint32_t dst, uint32_t fb, int col0, int row0, int R) {
 #pragma unroll
-      for (int p = 0; p < CS; ++p) {
-        const int c = 32 * p + lane;
-        const float x = __ldg(P.emb + (int64_t)tok * DM + c) + __ldg(P.pos + (int64_t)t * DM + c);
-        sm.xres[g * DM + c] = x;
-        split_store(sm.a_hi, sm.a_lo, g * PITCH + c, x);
-      }
-    }
-    for (int l = 0; l < P.layers; ++l) {
-      // ---- self-attention in-proj: own head's q | k (stage A) and v (stage B) -----------------------------
-      {
-        const uint8_t* st = acquire();
-        const float* bi = P.b_in[l];
-        mma_stage(st, 8, sm.a_hi, sm.a_lo, [&](int r, int c, float v) {
-          const int grow = (c < 32) ? rank * HD + c : DM + rank * HD + (c - 32);
-          sm.qkv[r * 96 + c] = v + __ldg(bi + grow);
-        });
-        st = acquire();
-        mma_stage(st, 4, sm.a_hi, sm.a_lo, [&](int r, int c, float v) { sm.qkv[r * 96 + 64 + c] = v + __ldg(bi + 2 * DM + rank * HD + c); });
-      }
-      __syncthreads();
-      // append k_t, v_t (bf16) to the paged cache; keep the ROUNDED values for this step's own key
-      for (int i = tid; i < G * 64; i += NT) {
-        const int g = i >> 6, c = i & 63;           // c < 32: k, else v
-        const bf16 h = __float2bfloat16_rn(sm.qkv[g * 96 + 32 + c]);
-        sm.qkv[g * 96 + 32 + c] = __bfloat162float(h);
-        const int page = sm.pages[g * 32 + t / P.PT];
-        P.kv_pool[(((int64_t)page * P.layers + l) * 2 + (c >> 5)) * ((int64_t)P.PT * DM) + (int64_t)(t % P.PT) * DM + rank * HD + (c & 31)] = h;
-      }
-      // ---- self-attention, head `rank`: K panels then V panels (probabilities parked in sm.scores) --------
-      {
-        // q pre-scaled into sm.qc (reused as the query buffer)
-        for (int i = tid; i < G * 32; i += NT) sm.qc[i] = sm.qkv[(i >> 5) * 96 + (i & 31)] * scale;
-        const int wpi = min(4, 8 / P.ips);          // warps per image inside a self-KV stage
-        for (int s = 0; s < sc.nS; ++s) {
-          const uint8_t* st = acquire();            // the barrier inside also publishes sm.qc / rounded k,v
-          const int g0 = s * P.ips, gn = min(P.ips, G - g0);
-          const int gi = warp / wpi, part = warp % wpi;
-          const bool active = gi < gn;
-          AttnJob job{};
-          float2 ml = make_float2(-INFINITY, 0.f);
-          if (active) {
-            const int g = g0 + gi, chunk = (t + wpi - 1) / wpi;
-            job.q = sm.qc + g * 32; job.panel = reinterpret_cast<const bf16*>(st) + (size_t)gi * P.maxT * KVP;
-            job.k_lo = min(t, part * chunk); job.k_hi = min(t, (part + 1) * chunk);
-            job.padf = sm.padflag + g * 256;
-            job.extra = (part == 0) ? sm.qkv + g * 96 + 32 : nullptr;
-            job.extra_bias = sm.padflag[g * 256 + t] ? 1.0f : 0.0f;
-            job.sc = sm.scores + (size_t)warp * SCR;
-            ml = attn_scores(job);
+        for (int kb = 0; kb < 4; ++kb) tma_2d(m, fb, dst + kb * R * 128, col0 + kb * 64, row0);
+      };
+      for (int t = P.t_begin; t < P.t_end; ++t) {
+        const int npg = (t + P.PT - 1) / P.PT;     // pages holding keys 0..t-1
+        for (int l = 0; l < L; ++l) {
+          {  // in-proj: q rows + k rows | v rows
+            uint32_t st = acquire(); uint32_t fb = bar(BAR_FULL + slot);
+            if (lane == 0) {
+              mbar_expect_tx(fb, 2 * 32 * 512);
+              load_rows(&P.m_in[l], st, fb, 0, rank * HD, 32);
+              load_rows(&P.m_in[l], st + 16384, fb, 0, DM + rank * HD, 32);
+            }
+            advance();
+            st = acquire(); fb = bar(BAR_FULL + slot);
+            if (lane == 0) { mbar_expect_tx(fb, 32 * 512); load_rows(&P.m_in[l], st, fb, 0, 2 * DM + rank * HD, 32); }
+            advance();
           }
-          st = acquire();                           // the matching V panel; the probabilities stay in this warp's score row
-          if (active) {
-            const int g = g0 + gi;
-            job.panel = reinterpret_cast<const bf16*>(st) + (size_t)gi * P.maxT * KVP;
-            if (job.extra) job.extra = sm.qkv + g * 96 + 64;
-            const float o = attn_pv(job);
-            float* pb = sm.ypart + (g * 4 + part) * 36;        // ypart is idle between FFN reductions
-            if (lane == 0) { pb[0] = ml.x; pb[1] = ml.y; }
-            pb[2 + lane] = o;
+          for (int sg = 0; sg < nS; ++sg) {        // self-KV: K pages then V pages of images [sg*ips, ...)
+            const int g0 = sg * P.ips, gn = max(0, min(P.ips, G - g0));
+            const int ops = gn * npg;
+            for (int which = 0; which < 2; ++which) {
+              const uint32_t st = acquire(); const uint32_t fb = bar(BAR_FULL + slot);
+              if (lane == 0) mbar_expect_tx(fb, ops * P.PT * 64);
+              __syncwarp();
+              for (int op = lane; op < ops; op += 32) {
+                const int gi = op / npg, j = op - gi * npg;
+                const int page = pages[(g0 + gi) * 32 + j];
+                tma_2d(&P.m_pool, fb, st + gi * self_panel + j * (P.PT * 64), rank * HD, ((page * L + l) * 2 + which) * P.PT);
+              }
+              advance();
+            }
+          }
+          {  // self out-proj rows, cross-q rows
+            uint32_t st = acquire(); uint32_t fb = bar(BAR_FULL + slot);
+            if (lane == 0) { mbar_expect_tx(fb, 32 * 512); load_rows(&P.m_so[l], st, fb, 0, rank * 32, 32); }
+            advance();
+            st = acquire(); fb = bar(BAR_FULL + slot);
+            if (lane == 0) { mbar_expect_tx(fb, 32 * 512); load_rows(&P.m_ca[l], st, fb, 0, rank * 32, 32); }
+            advance();
+          }
+          for (int sg = 0; sg < nC; ++sg) {        // cross K / V panels, 2 images per stage
+            const int g0 = sg * 2, gn = max(0, min(2, G - g0));
+            for (int which = 0; which < 2; ++which) {
+              const uint32_t st = acquire(); const uint32_t fb = bar(BAR_FULL + slot);
+              if (lane == 0) {
+                mbar_expect_tx(fb, gn * S * 64);
+                for (int gi = 0; gi < gn; ++gi)
+                  tma_2d(&P.m_ckv, fb, st + gi * cross_panel, which * DM + rank * HD, (l * P.B + img0 + g0 + gi) * S);
+              }
+              advance();
+            }
+          }
+          {  // cross out-proj rows
+            const uint32_t st = acquire(); const uint32_t fb = bar(BAR_FULL + slot);
+            if (lane == 0) { mbar_expect_tx(fb, 32 * 512); load_rows(&P.m_co[l], st, fb, 0, rank * 32, 32); }
+            advance();
+          }
+          for (int s4 = 0; s4 < 4; ++s4) {         // FFN1: own hidden rows
+            const uint32_t st = acquire(); const uint32_t fb = bar(BAR_FULL + slot);
+            if (lane == 0) { mbar_expect_tx(fb, 64 * 512); load_rows(&P.m_f1[l], st, fb, 0, rank * FS + s4 * 64, 64); }
+            advance();
+          }
+          for (int s4 = 0; s4 < 4; ++s4) {         // FFN2: K-split over the own hidden columns
+            const uint32_t st = acquire(); const uint32_t fb = bar(BAR_FULL + slot);
+            if (lane == 0) { mbar_expect_tx(fb, 64 * 512); load_rows(&P.m_f2[l], st, fb, rank * FS, s4 * 64, 64); }
+            advance();
           }
         }
-        __syncthreads();
-        for (int g = warp; g < G; g += 8) sm.oslice[g * 32 + lane] = attn_merge(sm.ypart, g, wpi);
-      }
-      cluster.sync();                                                            // #1: head outputs visible
-      gather_o();
-      // ---- self out-proj slice -> yslice ---------------------------------------------------------------------
-      {
-        const uint8_t* st = acquire();
-        const float* bo = P.b_so[l];
-        mma_stage(st, 4, sm.a_hi, sm.a_lo, [&](int r, int c, float v) { sm.yslice[r * 32 + c] = v + __ldg(bo + rank * 32 + c); });
-      }
-      cluster.sync();                                                            // #2
-      ln_gather(P.ln1w[l], P.ln1b[l]);
-      // ---- cross-attention query slice -------------------------------------------------------------------------
-      {
-        const uint8_t* st = acquire();
-        const float* bc = P.b_ca[l];
-        mma_stage(st, 4, sm.a_hi, sm.a_lo, [&](int r, int c, float v) { sm.qc[r * 32 + c] = (v + __ldg(bc + rank * 32 + c)) * scale; });
-      }
-      // ---- cross-attention over the S memory keys (2 images per panel) ---------------------------------------
-      for (int s = 0; s < sc.nC; ++s) {
-        const uint8_t* st = acquire();
-        const int gn = min(2, G - 2 * s);
-        const int gi = warp >> 2, part = warp & 3;   // 4 warps per image, 2 images per stage
-        const bool active = gi < gn;
-        AttnJob job{};
-        float2 ml = make_float2(-INFINITY, 0.f);
-        if (active) {
-          const int g = 2 * s + gi, chunk = (P.S + 3) / 4;
-          job.q = sm.qc + g * 32; job.panel = reinterpret_cast<const bf16*>(st) + (size_t)gi * P.S * KVP;
-          job.k_lo = min(P.S, part * chunk); job.k_hi = min(P.S, (part + 1) * chunk);
-          job.sc = sm.scores + (size_t)warp * SCR;
-          ml = attn_scores(job);
-        }
-        st = acquire();
-        if (active) {
-          const int g = 2 * s + gi;
-          job.panel = reinterpret_cast<const bf16*>(st) + (size_t)gi * P.S * KVP;
-          const float o = attn_pv(job);
-          float* pb = sm.ypart + (g * 4 + part) * 36;
-          if (lane == 0) { pb[0] = ml.x; pb[1] = ml.y; }
-          pb[2 + lane] = o;
+        {  // vocabulary head rows
+          const uint32_t st = acquire(); const uint32_t fb = bar(BAR_FULL + slot);
+          if (lane == 0) { mbar_expect_tx(fb, VSL * 512); load_rows(&P.m_head, st, fb, 0, rank * VSL, VSL); }
+          advance();
         }
       }
-      __syncthreads();
-      for (int g = warp; g < G; g += 8) sm.oslice[g * 32 + lane] = attn_merge(sm.ypart, g, 4);
-      cluster.sync();                                                            // #3
-      gather_o();
-      {
-        const uint8_t* st = acquire();
-        const float* bo = P.b_co[l];
-        mma_stage(st, 4, sm.a_hi, sm.a_lo, [&](int r, int c, float v) { sm.yslice[r * 32 + c] = v + __ldg(bo + rank * 32 + c); });
-      }
-      cluster.sync();                                                            // #4
-      ln_gather(P.ln2w[l], P.ln2b[l]);
-      // ---- FFN1: own 256 hidden units, ReLU, kept local as the FFN2 operand -----------------------------------
-      for (int s = 0; s < 4; ++s) {
-        const uint8_t* st = acquire();
-        const float* b1 = P.b_f1[l];
-        mma_stage(st, 8, sm.a_hi, sm.a_lo, [&](int r, int c, float v) {
-          const int hcol = s * 64 + c;
-          split_store(sm.f_hi, sm.f_lo, r * PITCH + hcol, fmaxf(v + __ldg(b1 + rank * FS + hcol), 0.f));
-        });
-      }
-      // ---- FFN2 as a K-split: partial sums over the own hidden slice ------------------------------------------
-      for (int s = 0; s < 4; ++s) {
-        const uint8_t* st = acquire();
-        mma_stage(st, 8, sm.f_hi, sm.f_lo, [&](int r, int c, float v) { sm.ypart[r * DM + s * 64 + c] = v; });
-      }
-      cluster.sync();                                                            // #5: partials visible
-      for (int g = warp; g < G; g += 8) {                                       // reduce-scatter: own 32 columns
-        float a = __ldg(P.b_f2[l] + rank * 32 + lane);
+    } else {
+      // =================================== CONSUMER WARPS ==================================================
+      auto stage_wait = [&]() -> uint32_t {
+        mbar_wait(bar(BAR_FULL + slot), phase);
+        return sbase + OFF_RING + slot * STAGE_BYTES;
+      };
+      auto stage_release = [&]() {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar(BAR_EMPTY + slot));
+        if (++slot == NS) { slot = 0; phase ^= 1; }
+      };
+      const int fg = lane >> 2, fq = lane & 3;       // MMA fragment coordinates: row group, image pair
+      const int gi_t = tid >> 5, c_t = tid & 31;     // (image, channel) coordinates of the elementwise phases
+      // push this CTA's [G][32] slice in ytmp into every peer's yrecv columns [32*rank, +32)
+      auto push_y = [&](float v) {
+        if (gi_t < G) {
+          const uint32_t off = sbase + OFF_YRECV + (gi_t * DM + 32 * rank + c_t) * 4;
 #pragma unroll
-        for (int p = 0; p < CS; ++p) a += cluster.map_shared_rank(sm.ypart, p)[g * DM + rank * 32 + lane];
-        sm.yslice[g * 32 + lane] = a;
-      }
-      cluster.sync();                                                            // #6
-      ln_gather(P.ln3w[l], P.ln3b[l]);
-    }
-    // ---- vocabulary head: own 40 rows -> global step logits ------------------------------------------------------
-    {
-      const uint8_t* st = acquire();
-      const int r0 = rank * VSL, nrows = max(0, min(VSL, P.vocab - r0));
-      mma_stage(st, (nrows + 7) / 8, sm.a_hi, sm.a_lo, [&](int r, int c, float v) {
-        if (r < G && c < nrows) {
-          const float lg = v + __ldg(P.b_out + r0 + c);
-          P.step_logits[(int64_t)(img0 + r) * P.vocab + r0 + c] = lg;
-          if (P.logits_out) P.logits_out[(int64_t)(img0 + r) * P.logits_img_stride + (int64_t)(t + P.logits_row_offset) * P.vocab + r0 + c] = lg;
+          for (int p = 0; p < CS; ++p) st_async_b32(mapa(off, p), __float_as_uint(v), mapa(bar(BAR_Y), p));
         }
-      });
-    }
-    __threadfence();
-    cluster.sync();                                                              // #7: all logits in L2
-    // ---- select: CTA `rank` serves images rank, rank+8 (whole CTA, so the branch is uniform) ----------------
-    for (int g = rank; g < G && !(P.forced && !(P.confs && (t % 4 == 0))); g += CS) {
-      const int V = P.vocab;
-      int Vp2 = 1; while (Vp2 < V) Vp2 <<= 1;
-      float* lg = sm.scores; float* srt = sm.scores + V;       // V + Vp2 <= 8*SCR floats
-      for (int i = tid; i < V; i += NT) lg[i] = __ldcg(P.step_logits + (int64_t)(img0 + g) * V + i);
-      __syncthreads();
-      const bool sample = (P.top_k != 0 || P.top_p != 1.0f) && P.uniforms != nullptr;
-      const float u = sample ? P.uniforms[(int64_t)(img0 + g) * P.uniforms_ld + t] : 0.f;
-      int token; float conf;
-      select_from_logits(lg, srt, V, Vp2, P.top_k, P.top_p, sample, u, token, conf);
-      if (tid == 0) {
-        if (!P.forced) P.tokens[(int64_t)(img0 + g) * P.tokens_ld + t + 1] = token;
-        if (P.confs && (t % 4 == 0)) P.confs[(int64_t)(img0 + g) * P.confs_ld + t / 4] = conf;
+      };
+      auto wait_y = [&]() {
+        if (tid == 0) mbar_expect_tx(bar(BAR_Y), G * DM * 4);
+        mbar_wait(bar(BAR_Y), ph_y); ph_y ^= 1;
+      };
+      // x = LN(xres + yrecv): warp w owns image w; writes xres and the hi/lo operand
+      auto layer_norm = [&](const float* lnw, const float* lnb) {
+        float gw[8], gb[8];
+        if (warp < G) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { gw[j] = __ldg(lnw + lane + 32 * j); gb[j] = __ldg(lnb + lane + 32 * j); }
+        }
+        wait_y();
+        if (warp < G) {
+          float v[8]; float s = 0.f;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { v[j] = xres[warp * DM + lane + 32 * j] + yrecv[warp * DM + lane + 32 * j]; s += v[j]; }
+          const float mean = warp_sum(s) * (1.0f / DM);
+          float q = 0.f;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { const float d = v[j] - mean; q += d * d; }
+          const float rstd = 1.0f / sqrtf(warp_sum(q) * (1.0f / DM) + 1e-5f);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int c = lane + 32 * j;
+            const float xn = (v[j] - mean) * rstd * gw[j] + gb[j];
+            xres[warp * DM + c] = xn;
+            split_store(xh, xl, warp * XP + c, xn);
+          }
+        }
+        cbar();
+      };
+      // attention output of image `warp` (lane = channel) -> hi/lo pairs into every peer's oh/ol columns [32*rank, +32)
+      auto push_o = [&](float o) {
+        const int j = lane & 15;
+        const float v0 = __shfl_sync(0xffffffffu, o, 2 * j), v1 = __shfl_sync(0xffffffffu, o, 2 * j + 1);
+        if (warp < G) {
+          const bf16 h0 = __float2bfloat16_rn(v0), h1 = __float2bfloat16_rn(v1);
+          uint32_t val;
+          if (lane < 16) val = pack_bf16(v0, v1);
+          else val = pack_bf16(v0 - __bfloat162float(h0), v1 - __bfloat162float(h1));
+          const uint32_t off = sbase + (lane < 16 ? OFF_OH : OFF_OL) + (warp * XP + 32 * rank + 2 * j) * 2;
+#pragma unroll
+          for (int p = 0; p < CS; ++p) st_async_b32(mapa(off, p), val, mapa(bar(BAR_O), p));
+        }
+      };
+      auto wait_o = [&]() {
+        if (tid == 0) mbar_expect_tx(bar(BAR_O), G * DM * 4);     // hi + lo: G * 256 * (2 + 2) bytes
+        mbar_wait(bar(BAR_O), ph_o); ph_o ^= 1;
+      };
+      // a 32-row projection of the gathered operand (bh,bl) -> ytmp (+bias) -> pushed to all peers
+      auto proj32_push = [&](uint32_t bh, uint32_t bl, const float* bias) {
+        float b0 = 0.f, b1 = 0.f;
+        if (warp < 2) { b0 = __ldg(bias + rank * 32 + warp * 16 + fg); b1 = __ldg(bias + rank * 32 + warp * 16 + fg + 8); }
+        const uint32_t st = stage_wait();
+        if (warp < 2) {
+          float acc[4];
+          mma_mtile<32>(st, warp * 16, bh, bl, acc);
+          const int f = warp * 16 + fg;
+          ytmp[(2 * fq) * 32 + f] = acc[0] + b0; ytmp[(2 * fq + 1) * 32 + f] = acc[1] + b0;
+          ytmp[(2 * fq) * 32 + f + 8] = acc[2] + b1; ytmp[(2 * fq + 1) * 32 + f + 8] = acc[3] + b1;
+        }
+        stage_release();
+        cbar();
+        push_y(ytmp[gi_t * 32 + c_t]);
+      };
+
+      for (int t = P.t_begin; t < P.t_end; ++t) {
+        // ---- embedding + positional row (model.py:98-101); PAD flag of the token at position t --------------
+        if (warp < G) {
+          float pz[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) pz[j] = __ldg(P.pos + (int64_t)t * DM + lane + 32 * j);
+          const int tok = (P.forced || t == P.t_begin) ? __ldcg(P.tokens + (int64_t)(img0 + warp) * P.tokens_ld + t) : tokbuf[(t & 1) * GM + warp];
+          if (lane == 0) padflag[warp * 256 + t] = (tok == P.pad_idx);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int c = lane + 32 * j;
+            const float x = __ldg(P.emb + (int64_t)tok * DM + c) + pz[j];
+            xres[warp * DM + c] = x;
+            split_store(xh, xl, warp * XP + c, x);
+          }
+        }
+        cbar();
+        for (int l = 0; l < L; ++l) {
+          // ---- self-attention in-proj: own head's q | k (stage A) and v (stage B) ---------------------------
+          {
+            const float* bi = P.b_in[l];
+            float b0 = 0.f, b1 = 0.f;
+            if (warp < 4) { const int r0 = (warp >> 1) * DM + rank * HD + (warp & 1) * 16 + fg; b0 = __ldg(bi + r0); b1 = __ldg(bi + r0 + 8); }
+            else if (warp < 6) { const int r0 = 2 * DM + rank * HD + (warp & 1) * 16 + fg; b0 = __ldg(bi + r0); b1 = __ldg(bi + r0 + 8); }
+            uint32_t st = stage_wait();
+            if (warp < 4) {
+              float acc[4];
+              mma_mtile<32>(st + (warp >> 1) * 16384, (warp & 1) * 16, sbase + OFF_XH, sbase + OFF_XL, acc);
+              const int f = (warp & 1) * 16 + fg;
+              if (warp < 2) {      // q, pre-scaled
+                qs[(2 * fq) * 32 + f] = (acc[0] + b0) * scale; qs[(2 * fq + 1) * 32 + f] = (acc[1] + b0) * scale;
+                qs[(2 * fq) * 32 + f + 8] = (acc[2] + b1) * scale; qs[(2 * fq + 1) * 32 + f + 8] = (acc[3] + b1) * scale;
+              } else {             // k, rounded to the cache precision
+                knew[(2 * fq) * 32 + f] = __bfloat162float(__float2bfloat16_rn(acc[0] + b0));
+                knew[(2 * fq + 1) * 32 + f] = __bfloat162float(__float2bfloat16_rn(acc[1] + b0));
+                knew[(2 * fq) * 32 + f + 8] = __bfloat162float(__float2bfloat16_rn(acc[2] + b1));
+                knew[(2 * fq + 1) * 32 + f + 8] = __bfloat162float(__float2bfloat16_rn(acc[3] + b1));
+              }
+            }
+            stage_release();
+            st = stage_wait();
+            if (warp == 4 || warp == 5) {
+              float acc[4];
+              mma_mtile<32>(st, (warp & 1) * 16, sbase + OFF_XH, sbase + OFF_XL, acc);
+              const int f = (warp & 1) * 16 + fg;
+              vnew[(2 * fq) * 32 + f] = __bfloat162float(__float2bfloat16_rn(acc[0] + b0));
+              vnew[(2 * fq + 1) * 32 + f] = __bfloat162float(__float2bfloat16_rn(acc[1] + b0));
+              vnew[(2 * fq) * 32 + f + 8] = __bfloat162float(__float2bfloat16_rn(acc[2] + b1));
+              vnew[(2 * fq + 1) * 32 + f + 8] = __bfloat162float(__float2bfloat16_rn(acc[3] + b1));
+            }
+            stage_release();
+          }
+          cbar();
+          // append k_t, v_t (bf16) to the paged cache: 16-byte stores, 4 per (image, k|v)
+          if (tid < G * 8) {
+            const int g = tid >> 3, which = (tid >> 2) & 1, ch = tid & 3;
+            const float* src = (which ? vnew : knew) + g * 32 + ch * 8;
+            const float4 a = *reinterpret_cast<const float4*>(src), b = *reinterpret_cast<const float4*>(src + 4);
+            uint4 o; o.x = pack_bf16(a.x, a.y); o.y = pack_bf16(a.z, a.w); o.z = pack_bf16(b.x, b.y); o.w = pack_bf16(b.z, b.w);
+            const int page = pages[g * 32 + t / P.PT];
+            bf16* dst = P.kv_pool + (((int64_t)page * L + l) * 2 + which) * ((int64_t)P.PT * DM) + (int64_t)(t % P.PT) * DM + rank * HD + ch * 8;
+            *reinterpret_cast<uint4*>(dst) = o;
+            asm volatile("fence.proxy.async;" ::: "memory");       // later TMA reads of the page must see this store
+          }
+          // the step's own key as partial #8 of image `warp`
+          if (warp < G) {
+            float s = warp_sum(qs[warp * 32 + lane] * knew[warp * 32 + lane]);
+            if (padflag[warp * 256 + t]) s += 1.0f;
+            float* pb = part + (warp * NPART + 8) * PSTR;
+            if (lane == 0) { pb[0] = s; pb[1] = 1.0f; }
+            pb[4 + lane] = vnew[warp * 32 + lane];
+          }
+          // ---- self-attention over keys [0,t), head `rank`: each warp owns a key slice of every image -----------
+          {
+            const int sl = (t + 7) >> 3;
+            const int lo = min(t, warp * sl), hi = min(t, lo + sl);
+            for (int sg = 0; sg < nS; ++sg) {
+              const int g0 = sg * P.ips, gn = max(0, min(P.ips, G - g0));
+              uint32_t st = stage_wait();
+              for (int gi = 0; gi < gn; ++gi) {
+                const int g = g0 + gi;
+                const float2 ml = attn_qk(st + gi * self_panel, qs + g * 32, lo, hi, padflag + g * 256, scb + (warp * GM + g) * 32);
+                if (lane == 0) { float* pb = part + (g * NPART + warp) * PSTR; pb[0] = ml.x; pb[1] = ml.y; }
+              }
+              stage_release();
+              st = stage_wait();
+              for (int gi = 0; gi < gn; ++gi) {
+                const int g = g0 + gi;
+                attn_pv(st + gi * self_panel, lo, hi, scb + (warp * GM + g) * 32, part + (g * NPART + warp) * PSTR + 4);
+              }
+              stage_release();
+            }
+          }
+          cbar();
+          {
+            float o = 0.f;
+            if (warp < G) o = attn_merge(part + warp * NPART * PSTR, NPART);
+            push_o(o);
+          }
+          wait_o();
+          // ---- self out-proj slice -> all-gather -> LN1 ------------------------------------------------------------
+          proj32_push(sbase + OFF_OH, sbase + OFF_OL, P.b_so[l]);
+          layer_norm(P.ln1w[l], P.ln1b[l]);
+          // ---- cross-attention query slice -------------------------------------------------------------------------
+          {
+            const float* bc = P.b_ca[l];
+            float b0 = 0.f, b1 = 0.f;
+            if (warp < 2) { b0 = __ldg(bc + rank * 32 + warp * 16 + fg); b1 = __ldg(bc + rank * 32 + warp * 16 + fg + 8); }
+            const uint32_t st = stage_wait();
+            if (warp < 2) {
+              float acc[4];
+              mma_mtile<32>(st, warp * 16, sbase + OFF_XH, sbase + OFF_XL, acc);
+              const int f = warp * 16 + fg;
+              qs[(2 * fq) * 32 + f] = (acc[0] + b0) * scale; qs[(2 * fq + 1) * 32 + f] = (acc[1] + b0) * scale;
+              qs[(2 * fq) * 32 + f + 8] = (acc[2] + b1) * scale; qs[(2 * fq + 1) * 32 + f + 8] = (acc[3] + b1) * scale;
+            }
+            stage_release();
+          }
+          cbar();
+          // ---- cross-attention over the S memory keys (2 images per panel stage) ---------------------------------
+          {
+            const int sl = (S + 7) >> 3;
+            const int lo = min(S, warp * sl), hi = min(S, lo + sl);
+            for (int sg = 0; sg < nC; ++sg) {
+              const int g0 = sg * 2, gn = max(0, min(2, G - g0));
+              uint32_t st = stage_wait();
+              for (int gi = 0; gi < gn; ++gi) {
+                const int g = g0 + gi;
+                const float2 ml = attn_qk(st + gi * cross_panel, qs + g * 32, lo, hi, nullptr, scb + (warp * GM + g) * 32);
+                if (lane == 0) { float* pb = part + (g * NPART + warp) * PSTR; pb[0] = ml.x; pb[1] = ml.y; }
+              }
+              stage_release();
+              st = stage_wait();
+              for (int gi = 0; gi < gn; ++gi) {
+                const int g = g0 + gi;
+                attn_pv(st + gi * cross_panel, lo, hi, scb + (warp * GM + g) * 32, part + (g * NPART + warp) * PSTR + 4);
+              }
+              stage_release();
+            }
+          }
+          cbar();
+          {
+            float o = 0.f;
+            if (warp < G) o = attn_merge(part + warp * NPART * PSTR, 8);
+            push_o(o);
+          }
+          wait_o();
+          proj32_push(sbase + OFF_OH, sbase + OFF_OL, P.b_co[l]);
+          layer_norm(P.ln2w[l], P.ln2b[l]);
+          // ---- FFN1: own 256 hidden units, ReLU, kept local as the FFN2 operand -----------------------------------
+          for (int s4 = 0; s4 < 4; ++s4) {
+            const int mt = warp - (s4 & 1) * 4;          // stages 0,2 -> warps 0-3; stages 1,3 -> warps 4-7
+            const bool mine = mt >= 0 && mt < 4;
+            float b0 = 0.f, b1 = 0.f;
+            if (mine) { const int h0 = rank * FS + s4 * 64 + mt * 16 + fg; b0 = __ldg(P.b_f1[l] + h0); b1 = __ldg(P.b_f1[l] + h0 + 8); }
+            const uint32_t st = stage_wait();
+            if (mine) {
+              float acc[4];
+              mma_mtile<64>(st, mt * 16, sbase + OFF_XH, sbase + OFF_XL, acc);
+              const int h = s4 * 64 + mt * 16 + fg;
+              split_store(fh, fl, (2 * fq) * XP + h, fmaxf(acc[0] + b0, 0.f)); split_store(fh, fl, (2 * fq + 1) * XP + h, fmaxf(acc[1] + b0, 0.f));
+              split_store(fh, fl, (2 * fq) * XP + h + 8, fmaxf(acc[2] + b1, 0.f)); split_store(fh, fl, (2 * fq + 1) * XP + h + 8, fmaxf(acc[3] + b1, 0.f));
+            }
+            stage_release();
+          }
+          cbar();
+          // ---- FFN2 as a K-split: partial sums pushed straight to the CTA that owns the output columns -----------
+          for (int s4 = 0; s4 < 4; ++s4) {
+            const int mt = warp - (s4 & 1) * 4;
+            const bool mine = mt >= 0 && mt < 4;
+            const uint32_t st = stage_wait();
+            if (mine) {
+              float acc[4];
+              mma_mtile<64>(st, mt * 16, sbase + OFF_FH, sbase + OFF_FL, acc);
+              const int feat = s4 * 64 + mt * 16 + fg;                 // output feature of acc[0..1]; +8 for acc[2..3]
+              const uint32_t peer = feat >> 5;                          // the whole 16-row tile lies inside one 32-column slice
+              const uint32_t rb = mapa(bar(BAR_F2), peer);
+              const uint32_t base = mapa(sbase + OFF_F2RECV + (rank * GM * 32 + (feat & 31)) * 4, peer);
+              if (2 * fq < G) { st_async_b32(base + (2 * fq) * 128, __float_as_uint(acc[0]), rb); st_async_b32(base + (2 * fq) * 128 + 32, __float_as_uint(acc[2]), rb); }
+              if (2 * fq + 1 < G) { st_async_b32(base + (2 * fq + 1) * 128, __float_as_uint(acc[1]), rb); st_async_b32(base + (2 * fq + 1) * 128 + 32, __float_as_uint(acc[3]), rb); }
+            }
+            stage_release();
+          }
+          {  // reduce the 8 partial slices of the own 32 columns, add bias, all-gather, LN3
+            const float b2 = __ldg(P.b_f2[l] + rank * 32 + c_t);
+            if (tid == 0) mbar_expect_tx(bar(BAR_F2), G * DM * 4);
+            mbar_wait(bar(BAR_F2), ph_f2); ph_f2 ^= 1;
+            float a = b2;
+            if (gi_t < G) {
+#pragma unroll
+              for (int p = 0; p < CS; ++p) a += f2recv[(p * GM + gi_t) * 32 + c_t];
+            }
+            push_y(a);
+          }
+          layer_norm(P.ln3w[l], P.ln3b[l]);
+        }
+        // ---- vocabulary head: own 40 rows -> logits to the caller's tensor and to the CTA that selects for the image ---
+        const bool want_conf = P.confs && (t % 4 == 0);
+        const bool need_select = !P.forced || want_conf;
+        {
+          const int r0 = rank * VSL;
+          float b0 = 0.f, b1 = 0.f;
+          const int row_a = warp * 16 + fg, row_b = row_a + 8;
+          const bool va = warp < 3 && row_a < VSL && r0 + row_a < P.vocab, vb = warp < 3 && row_b < VSL && r0 + row_b < P.vocab;
+          if (va) b0 = __ldg(P.b_out + r0 + row_a);
+          if (vb) b1 = __ldg(P.b_out + r0 + row_b);
+          const uint32_t st = stage_wait();
+          if (warp < 3) {
+            float acc[4];
+            mma_mtile<VSL>(st, warp * 16, sbase + OFF_XH, sbase + OFF_XL, acc);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int img = 2 * fq + (e & 1); const bool hi8 = e >= 2;
+              const bool valid = (hi8 ? vb : va) && img < G;
+              if (valid) {
+                const int row = hi8 ? row_b : row_a;
+                const float lg = acc[e] + (hi8 ? b1 : b0);
+                if (P.logits_out) P.logits_out[(int64_t)(img0 + img) * P.logits_img_stride + (int64_t)(t + P.logits_row_offset) * P.vocab + r0 + row] = lg;
+                if (need_select) st_async_b32(mapa(sbase + OFF_LRECV + (rank * VSL + row) * 4, img), __float_as_uint(lg), mapa(bar(BAR_LG), img));
+              }
+            }
+          }
+          stage_release();
+        }
+        // ---- select: CTA `rank` owns image `rank` ------------------------------------------------------------------
+        if (need_select && (int)rank < G) {
+          const int V = P.vocab;
+          if (tid == 0) mbar_expect_tx(bar(BAR_LG), V * 4);
+          mbar_wait(bar(BAR_LG), ph_lg);
+          int Vp2 = 1; while (Vp2 < V) Vp2 <<= 1;
+          float* lg = selbuf; float* srt = selbuf + CS * VSL;
+          for (int i = tid; i < V; i += NCT) lg[i] = lrecv[i];          // [src][VSL] is vocabulary order
+          cbar();
+          const bool sample = (P.top_k != 0 || P.top_p != 1.0f) && P.uniforms != nullptr;
+          const float u = sample ? P.uniforms[(int64_t)(img0 + rank) * P.uniforms_ld + t] : 0.f;
+          int token; float conf;
+          select_from_logits(lg, srt, V, Vp2, P.top_k, P.top_p, sample, u, token, conf);
+          ph_lg ^= 1;
+          if (tid == 0) {
+            if (!P.forced) {
+              P.tokens[(int64_t)(img0 + rank) * P.tokens_ld + t + 1] = token;
+              const uint32_t off = sbase + OFF_TOK + ((((t + 1) & 1) * GM) + rank) * 4;
+#pragma unroll
+              for (int p = 0; p < CS; ++p) st_async_b32(mapa(off, p), (uint32_t)token, mapa(bar(BAR_TOK), p));
+            }
+            if (want_conf) P.confs[(int64_t)(img0 + rank) * P.confs_ld + t / 4] = conf;
+          }
+        }
+        if (!P.forced) {
+          if (tid == 0) mbar_expect_tx(bar(BAR_TOK), G * 4);
+          mbar_wait(bar(BAR_TOK), ph_tok); ph_tok ^= 1;
+        }
       }
-      __syncthreads();
     }
-    __threadfence();
-    cluster.sync();                                                              // #8: tokens published
   }
-  cp_wait<0>();
+  // no CTA may exit while a peer can still push into its shared memory
+  __syncthreads();
+  cluster_sync_all();
 }
+
+// ---- host side: cached weight tensor maps ---------------------------------------------------------------------
+struct FusedCache {
+  const void* key[8 * 6 + 1];
+  FusedParams P;
+  bool valid;
+};
 
 }  // namespace
 
-// ---- host side ------------------------------------------------------------------------------------------
 int decode_cluster_supported(const mdc_model* m, const mdc_decode_state* st, int t_end) {
   const mdc_dims& d = m->d;
   if (d.precision != MDC_BF16 || d.dim != DM || d.dec_heads != CS || d.dec_ffn != FFN) return 0;
-  if (d.dec_layers < 1 || d.dec_layers > 8 || d.vocab > CS * VSL || d.n_patches + 2 > SCR) return 0;
+  if (d.dec_layers < 1 || d.dec_layers > 8 || d.vocab > CS * VSL || d.vocab < 8) return 0;
   if (st->x_override || st->pos_override) return 0;
-  if (d.n_patches * KVP * 2 * 2 > STAGE_BYTES) return 0;          // two images' cross panels per stage
-  if (t_end > 256 || st->pages_per_seq > 32 || (d.page_tokens & (d.page_tokens - 1)) != 0) return 0;
+  if (d.n_patches > 256 || d.n_patches < 8) return 0;             // one TMA box (<= 256 rows) per image panel, 2 panels per stage
+  if (t_end > 256 || st->pages_per_seq > 32 || d.page_tokens != 16 || st->n_pages < 1) return 0;
   if (getenv("MDC_DECODE_BACKEND") && !strcmp(getenv("MDC_DECODE_BACKEND"), "generic")) return 0;
   return 1;
 }
 
-size_t decode_cluster_scratch_bytes(const mdc_model* m, int B) { return (size_t)B * m->d.vocab * sizeof(float); }
+size_t decode_cluster_scratch_bytes(const mdc_model*, int) { return 0; }
 
-int decode_cluster_launch(mdc_model* m, const mdc_decode_state* st, int t_begin, int t_end, void* logits_scratch, cudaStream_t s) {
+void decode_cluster_model_destroy(mdc_model* m) {
+  if (m && m->fused_cache) { delete (FusedCache*)m->fused_cache; m->fused_cache = nullptr; }
+}
+
+int decode_cluster_launch(mdc_model* m, const mdc_decode_state* st, int t_begin, int t_end, void* /*logits_scratch*/, cudaStream_t s) {
   mdc_ctx* ctx = m->ctx; const mdc_dims& d = m->d;
   const void** gw = m->w + MDC_ENC_GLOBAL_SLOTS + d.enc_depth * MDC_ENC_BLOCK_SLOTS;
   const void** lw0 = gw + MDC_DEC_GLOBAL_SLOTS;
-  ClusterParams P{};
-  for (int l = 0; l < d.dec_layers; ++l) {
-    const void** lw = lw0 + l * MDC_DEC_LAYER_SLOTS;
-    P.w_in[l] = (const bf16*)lw[MDC_SA_IN_W]; P.b_in[l] = (const float*)lw[MDC_SA_IN_B];
-    P.w_so[l] = (const bf16*)lw[MDC_SA_OUT_W]; P.b_so[l] = (const float*)lw[MDC_SA_OUT_B];
-    P.ln1w[l] = (const float*)lw[MDC_LN1_W]; P.ln1b[l] = (const float*)lw[MDC_LN1_B];
-    P.w_ca[l] = (const bf16*)lw[MDC_CA_IN_W]; P.b_ca[l] = (const float*)lw[MDC_CA_IN_B];
-    P.w_co[l] = (const bf16*)lw[MDC_CA_OUT_W]; P.b_co[l] = (const float*)lw[MDC_CA_OUT_B];
-    P.ln2w[l] = (const float*)lw[MDC_LN2_W]; P.ln2b[l] = (const float*)lw[MDC_LN2_B];
-    P.w_f1[l] = (const bf16*)lw[MDC_FF1_W]; P.b_f1[l] = (const float*)lw[MDC_FF1_B];
-    P.w_f2[l] = (const bf16*)lw[MDC_FF2_W]; P.b_f2[l] = (const float*)lw[MDC_FF2_B];
-    P.ln3w[l] = (const float*)lw[MDC_LN3_W]; P.ln3b[l] = (const float*)lw[MDC_LN3_B];
+  if (!m->fused_cache) { FusedCache* c = new FusedCache(); memset(c, 0, sizeof(FusedCache)); m->fused_cache = c; }
+  FusedCache* fc = (FusedCache*)m->fused_cache;
+  if (!fc->valid) {
+    FusedParams& P = fc->P;
+    for (int l = 0; l < d.dec_layers; ++l) {
+      const void** lw = lw0 + l * MDC_DEC_LAYER_SLOTS;
+      MDC_TRY(mdc_make_tmap_2d(ctx, lw[MDC_SA_IN_W], 3 * DM, DM, DM, 64, 32, 3, &P.m_in[l]));
+      MDC_TRY(mdc_make_tmap_2d(ctx, lw[MDC_SA_OUT_W], DM, DM, DM, 64, 32, 3, &P.m_so[l]));
+      MDC_TRY(mdc_make_tmap_2d(ctx, lw[MDC_CA_IN_W], 3 * DM, DM, DM, 64, 32, 3, &P.m_ca[l]));
+      MDC_TRY(mdc_make_tmap_2d(ctx, lw[MDC_CA_OUT_W], DM, DM, DM, 64, 32, 3, &P.m_co[l]));
+      MDC_TRY(mdc_make_tmap_2d(ctx, lw[MDC_FF1_W], FFN, DM, DM, 64, 64, 3, &P.m_f1[l]));
+      MDC_TRY(mdc_make_tmap_2d(ctx, lw[MDC_FF2_W], DM, FFN, FFN, 64, 64, 3, &P.m_f2[l]));
+      P.b_in[l] = (const float*)lw[MDC_SA_IN_B]; P.b_so[l] = (const float*)lw[MDC_SA_OUT_B];
+      P.ln1w[l] = (const float*)lw[MDC_LN1_W]; P.ln1b[l] = (const float*)lw[MDC_LN1_B];
+      P.b_ca[l] = (const float*)lw[MDC_CA_IN_B]; P.b_co[l] = (const float*)lw[MDC_CA_OUT_B];
+      P.ln2w[l] = (const float*)lw[MDC_LN2_W]; P.ln2b[l] = (const float*)lw[MDC_LN2_B];
+      P.b_f1[l] = (const float*)lw[MDC_FF1_B]; P.b_f2[l] = (const float*)lw[MDC_FF2_B];
+      P.ln3w[l] = (const float*)lw[MDC_LN3_W]; P.ln3b[l] = (const float*)lw[MDC_LN3_B];
+    }
+    MDC_TRY(mdc_make_tmap_2d(ctx, gw[MDC_OUT_W], d.vocab, DM, DM, 64, VSL, 3, &P.m_head));
+    P.emb = (const float*)gw[MDC_EMB]; P.pos = (const float*)gw[MDC_DEC_POS]; P.b_out = (const float*)gw[MDC_OUT_B];
+    P.layers = d.dec_layers; P.vocab = d.vocab; P.S = d.n_patches; P.pad_idx = d.pad_idx; P.PT = d.page_tokens;
+    fc->valid = true;
   }
-  P.emb = (const float*)gw[MDC_EMB]; P.pos = (const float*)gw[MDC_DEC_POS];
-  P.w_out = (const bf16*)gw[MDC_OUT_W]; P.b_out = (const float*)gw[MDC_OUT_B];
-  P.layers = d.dec_layers; P.vocab = d.vocab; P.S = d.n_patches; P.pad_idx = d.pad_idx;
+  FusedParams P = fc->P;
   P.B = st->B;
   P.tokens = st->tokens; P.tokens_ld = st->tokens_ld;
-  P.kv_pool = (bf16*)st->kv_pool; P.page_table = st->page_table; P.pages_per_seq = st->pages_per_seq; P.PT = d.page_tokens;
-  P.cross_kv = (const bf16*)st->cross_kv;
-  P.step_logits = (float*)logits_scratch;
+  P.kv_pool = (bf16*)st->kv_pool; P.page_table = st->page_table; P.pages_per_seq = st->pages_per_seq;
   P.logits_out = st->logits; P.logits_img_stride = (int64_t)st->logits_ld * d.vocab; P.logits_row_offset = st->logits_row_offset;
   P.confs = st->confs; P.confs_ld = st->confs_ld;
   P.uniforms = st->uniforms; P.uniforms_ld = st->uniforms_ld; P.top_k = st->top_k; P.top_p = st->top_p; P.forced = st->forced;
   P.t_begin = t_begin; P.t_end = t_end;
-  P.maxT = ((t_end + 7) / 8) * 8;
-  if (P.maxT < 8) P.maxT = 8;
-  // images per cluster: as many clusters as the device can keep resident, at most GM images each
+  // cross-K/V [layers*B*S rows][2*DM]: one (S rows x 32 channels) box per (image, head, k|v); paged pool: one page x head box
+  MDC_TRY(mdc_make_tmap_2d(ctx, st->cross_kv, (int64_t)d.dec_layers * st->B * d.n_patches, 2 * DM, 2 * DM, HD, d.n_patches, 2, &P.m_ckv));
+  MDC_TRY(mdc_make_tmap_2d(ctx, st->kv_pool, (int64_t)st->n_pages * d.dec_layers * 2 * d.page_tokens, DM, DM, HD, d.page_tokens, 2, &P.m_pool));
   static int max_clusters = 0;
   if (!max_clusters) {
-    MDC_CUDA(cudaFuncSetAttribute(decode_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    MDC_CUDA(cudaFuncSetAttribute(decode_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     cudaLaunchConfig_t q{}; q.gridDim = dim3(CS * 32); q.blockDim = dim3(NT); q.dynamicSmemBytes = SMEM_BYTES;
     cudaLaunchAttribute a[1]; a[0].id = cudaLaunchAttributeClusterDimension; a[0].val.clusterDim.x = CS; a[0].val.clusterDim.y = 1; a[0].val.clusterDim.z = 1;
     q.attrs = a; q.numAttrs = 1;
     int n = 0;
-    cudaError_t e = cudaOccupancyMaxActiveClusters(&n, decode_cluster_kernel, &q);
+    cudaError_t e = cudaOccupancyMaxActiveClusters(&n, decode_fused_kernel, &q);
     if (e != cudaSuccess || n < 1) { (void)cudaGetLastError(); n = ctx->sm_count / CS / 2; if (n < 1) n = 1; }
     max_clusters = n;
   }
@@ -667,12 +819,14 @@ int decode_cluster_launch(mdc_model* m, const mdc_decode_state* st, int t_begin,
   if (G > GM) G = GM;
   if (G < 1) G = 1;
   P.G = G;
-  P.pt_shift = 0; while ((1 << P.pt_shift) < d.page_tokens) ++P.pt_shift;
-  P.ips = STAGE_BYTES / (P.maxT * KVP * 2);
-  if (P.ips > 8) P.ips = 8;
-  if (P.ips < 1) MDC_FAIL(-2, "decode_cluster: key capacity %d does not fit a stage", P.maxT);
-  const int n_clusters = (P.B + G - 1) / G;
-  decode_cluster_kernel<<<n_clusters * CS, NT, SMEM_BYTES, s>>>(P);
+  P.n_groups = (P.B + G - 1) / G;
+  P.np_max = (t_end + d.page_tokens - 1) / d.page_tokens;
+  if (P.np_max < 1) P.np_max = 1;
+  P.ips = STAGE_BYTES / (P.np_max * 1024);
+  if (P.ips > GM) P.ips = GM;
+  if (P.ips < 1) MDC_FAIL(-2, "decode_cluster: key capacity %d does not fit a stage", t_end);
+  const int n_clusters = P.n_groups < max_clusters ? P.n_groups : max_clusters;
+  decode_fused_kernel<<<n_clusters * CS, NT, SMEM_BYTES, s>>>(P);
   MDC_LAUNCH_CHECK(ctx);
   return 0;
 }

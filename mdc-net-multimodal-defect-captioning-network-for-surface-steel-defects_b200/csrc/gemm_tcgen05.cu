@@ -387,8 +387,8 @@ int gemm_tc_launch(mdc_ctx* ctx, int epilogue, const void* A, int64_t lda, const
 }
 
 // Generic 2-D bf16 tensor map (used by the cluster decode kernel): tensor [rows, cols] with row pitch `ld` elements,
-// box [box_cols, box_rows]; swizzle128 != 0 selects SWIZZLE_128B (box_cols * 2 bytes must then be 128).
-int mdc_make_tmap_2d(mdc_ctx* ctx, const void* ptr, int64_t rows, int64_t cols, int64_t ld, int box_cols, int box_rows, int swizzle128, void* out_map) {
+// box [box_cols, box_rows]; swizzle_mode 0 = none, 1 = 32B, 2 = 64B, 3 = 128B (box_cols * 2 bytes must not exceed the swizzle span).
+int mdc_make_tmap_2d(mdc_ctx* ctx, const void* ptr, int64_t rows, int64_t cols, int64_t ld, int box_cols, int box_rows, int swizzle_mode, void* out_map) {
   if (!ctx->encode_fn) {
     void* fn = nullptr; cudaDriverEntryPointQueryResult qres;
     MDC_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
@@ -400,8 +400,10 @@ int mdc_make_tmap_2d(mdc_ctx* ctx, const void* ptr, int64_t rows, int64_t cols, 
   cuuint64_t gstride[1] = {(cuuint64_t)ld * 2};
   cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
+  const CUtensorMapSwizzle sw = swizzle_mode == 3 ? CU_TENSOR_MAP_SWIZZLE_128B : swizzle_mode == 2 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                : swizzle_mode == 1 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE;
   CUresult r = encode((CUtensorMap*)out_map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstride, box, estr,
-                      CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
                       CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) MDC_FAIL(-3, "cuTensorMapEncodeTiled failed (%d) ptr=%p rows=%lld cols=%lld ld=%lld box=%dx%d", (int)r, ptr,
                                   (long long)rows, (long long)cols, (long long)ld, box_cols, box_rows);

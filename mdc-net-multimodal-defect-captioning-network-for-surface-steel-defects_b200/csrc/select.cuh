@@ -3,6 +3,11 @@
 #include "common.cuh"
 #include <float.h>
 
+// block barrier used inside the select; a kernel whose select runs on a subset of its warps overrides it with a named barrier
+#ifndef MDC_SEL_SYNC
+#define MDC_SEL_SYNC() __syncthreads()
+#endif
+
 namespace mdcsel {
 
 constexpr int SEL_THREADS = 256;
@@ -15,7 +20,7 @@ __device__ __forceinline__ void block_argmax(float v, int idx, float* s_val, int
   }
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (lane == 0) { s_val[warp] = v; s_idx[warp] = idx; }
-  __syncthreads();
+  MDC_SEL_SYNC();
   if (warp == 0) {
     v = lane < (SEL_THREADS / 32) ? s_val[lane] : -INFINITY; idx = lane < (SEL_THREADS / 32) ? s_idx[lane] : 0x7fffffff;
     for (int o = 16; o > 0; o >>= 1) {
@@ -24,19 +29,19 @@ __device__ __forceinline__ void block_argmax(float v, int idx, float* s_val, int
     }
     if (lane == 0) { s_val[0] = v; s_idx[0] = idx; }
   }
-  __syncthreads();
+  MDC_SEL_SYNC();
   out_v = s_val[0]; out_i = s_idx[0];
-  __syncthreads();
+  MDC_SEL_SYNC();
 }
 
 __device__ __forceinline__ double block_sum_d(double v, double* s_d) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (lane == 0) s_d[warp] = v;
-  __syncthreads();
+  MDC_SEL_SYNC();
   double tot = 0.0;
   for (int i = 0; i < SEL_THREADS / 32; ++i) tot += s_d[i];
-  __syncthreads();
+  MDC_SEL_SYNC();
   return tot;
 }
 
@@ -51,7 +56,7 @@ __device__ inline void select_from_logits(float* lg, float* srt, int V, int Vp2,
   const int tid = threadIdx.x;
   if (top_k > 0 || top_p < 1.0f) {
     for (int i = tid; i < Vp2; i += SEL_THREADS) srt[i] = i < V ? lg[i] : -INFINITY;
-    __syncthreads();
+    MDC_SEL_SYNC();
     for (int k = 2; k <= Vp2; k <<= 1)            // bitonic sort, descending
       for (int j = k >> 1; j > 0; j >>= 1) {
         for (int i = tid; i < Vp2; i += SEL_THREADS) {
@@ -62,7 +67,7 @@ __device__ inline void select_from_logits(float* lg, float* srt, int V, int Vp2,
             if (desc ? (a < b) : (a > b)) { srt[i] = b; srt[ixj] = a; }
           }
         }
-        __syncthreads();
+        MDC_SEL_SYNC();
       }
     float cut = -INFINITY;
     int kept = V;
@@ -88,13 +93,13 @@ __device__ inline void select_from_logits(float* lg, float* srt, int V, int Vp2,
         }
         s_first = kept - removed;                  // number of entries kept from the top
       }
-      __syncthreads();
+      MDC_SEL_SYNC();
       int nk = s_first;
       cut = fmaxf(cut, srt[nk - 1]);
-      __syncthreads();
+      MDC_SEL_SYNC();
     }
     for (int i = tid; i < V; i += SEL_THREADS) if (lg[i] < cut) lg[i] = -INFINITY;
-    __syncthreads();
+    MDC_SEL_SYNC();
   }
   float bv = -INFINITY; int bi = 0x7fffffff;
   for (int i = tid; i < V; i += SEL_THREADS) { float v = lg[i]; if (v > bv) { bv = v; bi = i; } }
@@ -112,9 +117,9 @@ __device__ inline void select_from_logits(float* lg, float* srt, int V, int Vp2,
   int tok = amax;
   if (sample) {
     s_scan[tid] = local;
-    __syncthreads();
+    MDC_SEL_SYNC();
     if (tid == 0) { double run = 0.0; for (int i = 0; i < SEL_THREADS; ++i) { double v = s_scan[i]; s_scan[i] = run; run += v; } s_d[0] = run; s_first = V - 1; }
-    __syncthreads();
+    MDC_SEL_SYNC();
     double total = s_d[0], thr = (double)u * total, run = s_scan[tid];
     int mine = 0x7fffffff;
     for (int j = 0; j < EPT; ++j) {
@@ -122,9 +127,9 @@ __device__ inline void select_from_logits(float* lg, float* srt, int V, int Vp2,
       if (i < V) { run += exp((double)lg[i] - (double)mx); if (run > thr && mine == 0x7fffffff) mine = i; }
     }
     if (mine != 0x7fffffff) atomicMin(&s_first, mine);
-    __syncthreads();
+    MDC_SEL_SYNC();
     tok = s_first;
-    __syncthreads();
+    MDC_SEL_SYNC();
   }
   token = tok; conf = cf;
 }

@@ -252,6 +252,7 @@ class Engine:
         st.B = B
         st.tokens, st.tokens_ld = tokens.data_ptr(), tokens.shape[1]
         st.kv_pool, st.page_table, st.pages_per_seq = kv.pool.data_ptr(), kv.page_table.data_ptr(), kv.pages_per_seq
+        st.n_pages = kv.pool.shape[0]
         st.cross_kv = cross_kv.data_ptr()
         if logits is not None:
             assert logits.dtype == torch.float32 and logits.is_contiguous()
