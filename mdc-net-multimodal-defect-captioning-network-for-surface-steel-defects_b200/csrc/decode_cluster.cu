@@ -47,7 +47,7 @@ constexpr int STAGE_BYTES = 32768;
 constexpr int NS = 4;              // ring stages
 constexpr int VSL = 40;            // vocab rows per CTA; 8*40 = 320 >= V
 constexpr int PSTR = 36;           // floats per attention partial: m, l, -, -, o[32] (o is 16-byte aligned)
-constexpr int NPART = 9;           // 8 key slices + the step's own key
+constexpr int NPART = 9;           // attention partials per image: one per warp (interleaved key tiles) + the step's own key
 
 // ---- shared memory map (bytes from the 1024-aligned base) ---------------------------------------------------
 constexpr int OFF_RING = 0;
@@ -65,14 +65,16 @@ constexpr int OFF_QS = OFF_F2RECV + CS * GM * 32 * 4;      // [GM][32] f32 scale
 constexpr int OFF_KNEW = OFF_QS + GM * 32 * 4;             // [GM][32] f32 this step's key (bf16-rounded)
 constexpr int OFF_VNEW = OFF_KNEW + GM * 32 * 4;
 constexpr int OFF_YTMP = OFF_VNEW + GM * 32 * 4;           // [GM][32] f32 own slice of a projection before the push
-constexpr int OFF_SC = OFF_YTMP + GM * 32 * 4;             // [8 warps][GM][32] f32 scores / probabilities
-constexpr int OFF_PART = OFF_SC + 8 * GM * 32 * 4;         // [GM][NPART][PSTR] f32
+constexpr int OFF_QH = OFF_YTMP + GM * 32 * 4;             // [GM][32] bf16 hi part of the scaled query (MMA operand)
+constexpr int OFF_QL = OFF_QH + GM * 32 * 2;               // [GM][32] bf16 lo part
+constexpr int OFF_PART = OFF_QL + GM * 32 * 2;             // [GM][NPART][PSTR] f32 attention partials
 constexpr int OFF_LRECV = OFF_PART + GM * NPART * PSTR * 4;   // [CS src][VSL] f32 logits of the image this CTA selects for
 constexpr int OFF_SEL = OFF_LRECV + CS * VSL * 4;          // select scratch: 320 + 512 floats
 constexpr int OFF_TOK = OFF_SEL + (CS * VSL + 512) * 4;    // [2][GM] int32 (double buffered by step parity)
 constexpr int OFF_PAGES = OFF_TOK + 2 * GM * 4;            // [GM][32] int32
 constexpr int OFF_PADF = OFF_PAGES + GM * 32 * 4;          // [GM][256] u8
-constexpr int OFF_BARS = OFF_PADF + GM * 256;              // mbarriers
+constexpr int OFF_HASPAD = OFF_PADF + GM * 256;            // [GM] int32: any PAD token among the keys so far
+constexpr int OFF_BARS = OFF_HASPAD + GM * 4;              // mbarriers
 constexpr int NBARS = 2 * NS + 5;
 constexpr int SMEM_USED = OFF_BARS + NBARS * 8;
 constexpr int SMEM_BYTES = SMEM_USED + 1024;               // + alignment slack
@@ -98,6 +100,7 @@ struct __align__(64) FusedParams {
   int t_begin, t_end;
   int np_max;                              // pages per image panel in a self-KV stage (capacity for t_end keys)
   int ips;                                 // images per self-KV stage
+  long long* trace; int trace_t;           // developer aid: phase timestamps of CTA 0 at step trace_t (MDC_DECODE_TRACE_PTR)
 };
 
 // ---- PTX helpers ------------------------------------------------------------------------------------------
@@ -184,72 +187,123 @@ __device__ __forceinline__ void mma_mtile(uint32_t wblk, int m0, uint32_t bh, ui
   for (int j = 0; j < 4; ++j) acc[j] = (c0[j] + c2[j]) + (c1[j] + c3[j]);
 }
 
-// ---- attention of one query against a slice of a key / value panel ---------------------------------------------
-// panel: shared address, key u at u*64 bytes, 16-byte chunk c stored at c ^ ((u >> 1) & 3) (TMA SWIZZLE_64B).
-// 4 lanes per key (one chunk each), 8 keys per pass.  Scores / probabilities are parked in sc[0..hi-lo).
-__device__ __forceinline__ float2 attn_qk(uint32_t panel, const float* q, int lo, int hi, const uint8_t* padf, float* sc) {
-  const int lane = threadIdx.x & 31, kslot = lane >> 2, sub = lane & 3;
-  const float4 qa = *reinterpret_cast<const float4*>(q + sub * 8), qb = *reinterpret_cast<const float4*>(q + sub * 8 + 4);
-  float mx = -INFINITY;
-  for (int u0 = lo; u0 < hi; u0 += 8) {
-    const int u = u0 + kslot; const bool ok = u < hi; const int uu = ok ? u : lo;
-    const uint4 raw = lds128(panel + uu * 64 + ((sub ^ ((uu >> 1) & 3)) << 4));
-    float s = qa.x * __uint_as_float(raw.x << 16);
-    s = fmaf(qa.y, __uint_as_float(raw.x & 0xffff0000u), s);
-    s = fmaf(qa.z, __uint_as_float(raw.y << 16), s); s = fmaf(qa.w, __uint_as_float(raw.y & 0xffff0000u), s);
-    s = fmaf(qb.x, __uint_as_float(raw.z << 16), s); s = fmaf(qb.y, __uint_as_float(raw.z & 0xffff0000u), s);
-    s = fmaf(qb.z, __uint_as_float(raw.w << 16), s); s = fmaf(qb.w, __uint_as_float(raw.w & 0xffff0000u), s);
-    s += __shfl_xor_sync(0xffffffffu, s, 1);
-    s += __shfl_xor_sync(0xffffffffu, s, 2);
-    if (ok) {
-      if (padf && padf[u]) s += 1.0f;
-      mx = fmaxf(mx, s);
-      if (sub == 0) sc[u - lo] = s;
+// ---- attention of ONE query per image on the tensor cores ------------------------------------------------------
+// A key / value panel in shared memory holds key u at u*64 bytes, 16-byte chunk c stored at c ^ ((u >> 1) & 3)
+// (TMA SWIZZLE_64B).  The fp32 query is the M operand of S = q.K^T with row 0 = bf16 hi part and row 1 = lo part, so the
+// score of key 2q, 2q+1 of an 8-key tile lands in lanes (g = 0|1, q) -- exactly where the B fragment of P.V wants the
+// probabilities: the softmax runs in registers (group g = 0 keeps the hi part of p, g = 1 the lo part), nothing goes
+// through shared memory, and q.K / P.V are exact up to the bf16 K/V storage.  Scores are in log2 units (q is pre-scaled
+// by log2(e)/sqrt(hd)), so p = exp2(s - m).
+constexpr float LOG2E = 1.4426950408889634f;
+
+__device__ __forceinline__ void ldsm_x4_trans(uint32_t* r, uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+
+// A fragments of q from its pre-split bf16 hi / lo rows (32 dims): aq[ks][h] covers dims 16*ks + 8*h + {2q, 2q+1} of MMA row g
+// (row 0 = hi, row 1 = lo, other rows 0)
+__device__ __forceinline__ void build_q_frag(const bf16* qh, const bf16* ql, uint32_t (&aq)[2][2]) {
+  const int lane = threadIdx.x & 31, g = lane >> 2, q4 = lane & 3;
+  const bf16* src = (g == 0 ? qh : ql) + 2 * q4;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const uint32_t v = *reinterpret_cast<const uint32_t*>(src + (i >> 1) * 16 + (i & 1) * 8);
+    aq[i >> 1][i & 1] = g < 2 ? v : 0u;
+  }
+}
+
+__device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
+// Flash-decoding over key tiles t0, t0+tstep, ... < t1 (16 keys each) of one (K, V) panel pair, in chunks of MAXT tiles with
+// the usual running (max, sum, output) rescale.  On return m_run / l_run are warp-uniform; the un-normalised output of dims
+// mt*16 + {g, g+8} sits in lanes with q == 0 as o[mt][0]+o[mt][1] and o[mt][2]+o[mt][3].
+template <int MAXT>
+__device__ __forceinline__ void attn_tiles(uint32_t kp, uint32_t vp, const uint32_t (&aq)[2][2], int t0, int t1, int tstep, int nkeys,
+                                           const uint8_t* padf, float& m_run, float& l_run, float (&o)[2][4]) {
+  const int lane = threadIdx.x & 31, g = lane >> 2, q4 = lane & 3;
+  const uint32_t a_k0[4] = {aq[0][0], 0u, aq[0][1], 0u}, a_k1[4] = {aq[1][0], 0u, aq[1][1], 0u};
+  for (int c0 = t0; c0 < t1; c0 += MAXT * tstep) {
+    const int nt = min(MAXT, (t1 - c0 + tstep - 1) / tstep);
+    float sc[MAXT][4];
+#pragma unroll
+    for (int i = 0; i < MAXT; ++i) {
+      if (i < nt) {
+        const int k0 = (c0 + i * tstep) * 16;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {          // 8-key n-tile j: one ldmatrix.x4 = the four dim chunks of keys k0+8j .. +7
+          const int key = k0 + 8 * j + (lane & 7);
+          uint32_t kb[4];
+          ldsm_x4(kb, kp + key * 64 + (((lane >> 3) ^ ((key >> 1) & 3)) << 4));
+          float c[4] = {0.f, 0.f, 0.f, 0.f}, d[4] = {0.f, 0.f, 0.f, 0.f};
+          mma16816(c, a_k0, kb[0], kb[1]);
+          mma16816(d, a_k1, kb[2], kb[3]);
+          const float e0 = c[0] + d[0], e1 = c[1] + d[1];
+          sc[i][2 * j] = e0 + __shfl_xor_sync(0xffffffffu, e0, 4);       // hi row + lo row
+          sc[i][2 * j + 1] = e1 + __shfl_xor_sync(0xffffffffu, e1, 4);
+        }
+        if (padf != nullptr || k0 + 16 > nkeys) {                          // PAD-key bias / tail mask: rare, warp-uniform
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int key = k0 + (e >> 1) * 8 + 2 * q4 + (e & 1);
+            if (padf != nullptr && padf[key]) sc[i][e] += LOG2E;           // float PAD-key bias +1.0 (Q7), in log2 units
+            if (key >= nkeys) sc[i][e] = -INFINITY;
+          }
+        }
+      } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) sc[i][e] = -INFINITY;
+      }
     }
+    float mx = m_run;
+#pragma unroll
+    for (int i = 0; i < MAXT; ++i) mx = fmaxf(fmaxf(mx, fmaxf(sc[i][0], sc[i][1])), fmaxf(sc[i][2], sc[i][3]));
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+    mx = __shfl_sync(0xffffffffu, mx, 0);                                   // lanes of groups g >= 2 hold no scores
+    const float corr = ex2_approx(m_run - mx);                              // first chunk: exp2(-inf) = 0
+    l_run *= corr;
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) o[mt][e] *= corr;
+    m_run = mx;
+    float ls = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXT; ++i) {
+      if (i < nt) {
+        float p[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { p[e] = ex2_approx(sc[i][e] - mx); ls += p[e]; }
+        // hi part for MMA column 0 (group g = 0), lo part for column 1 (g = 1), zero elsewhere -- branch-free
+        const uint32_t h0 = pack_bf16(p[0], p[1]), h1 = pack_bf16(p[2], p[3]);
+        const uint32_t l0 = pack_bf16(p[0] - __uint_as_float(h0 << 16), p[1] - __uint_as_float(h0 & 0xffff0000u));
+        const uint32_t l1 = pack_bf16(p[2] - __uint_as_float(h1 << 16), p[3] - __uint_as_float(h1 & 0xffff0000u));
+        const uint32_t b0 = g == 0 ? h0 : (g == 1 ? l0 : 0u), b1 = g == 0 ? h1 : (g == 1 ? l1 : 0u);
+        const int key = (c0 + i * tstep) * 16 + ((lane >> 4) & 1) * 8 + (lane & 7), sw = (key >> 1) & 3, dsel = (lane >> 3) & 1;
+        const uint32_t rowaddr = vp + key * 64;
+        uint32_t a0[4], a1[4];
+        ldsm_x4_trans(a0, rowaddr + ((dsel ^ sw) << 4));
+        ldsm_x4_trans(a1, rowaddr + (((2 + dsel) ^ sw) << 4));
+        mma16816(o[0], a0, b0, b1);
+        mma16816(o[1], a1, b0, b1);
+      }
+    }
+    ls += __shfl_xor_sync(0xffffffffu, ls, 1);
+    ls += __shfl_xor_sync(0xffffffffu, ls, 2);
+    l_run += __shfl_sync(0xffffffffu, ls, 0);
   }
-  mx = warp_max(mx);
-  __syncwarp();
-  const int n = hi - lo;
-  float e = 0.f;
-  if (lane < n) { e = expf(sc[lane] - mx); sc[lane] = e; }
-  const float sum = warp_sum(e);
-  __syncwarp();
-  return make_float2(mx, sum);
 }
 
-__device__ __forceinline__ void attn_pv(uint32_t panel, int lo, int hi, const float* sc, float* out) {
-  const int lane = threadIdx.x & 31, kslot = lane >> 2, sub = lane & 3;
-  float a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  for (int u0 = lo; u0 < hi; u0 += 8) {
-    const int u = u0 + kslot; const bool ok = u < hi; const int uu = ok ? u : lo;
-    const float p = ok ? sc[u - lo] : 0.f;
-    const uint4 raw = lds128(panel + uu * 64 + ((sub ^ ((uu >> 1) & 3)) << 4));
-    a[0] = fmaf(p, __uint_as_float(raw.x << 16), a[0]); a[1] = fmaf(p, __uint_as_float(raw.x & 0xffff0000u), a[1]);
-    a[2] = fmaf(p, __uint_as_float(raw.y << 16), a[2]); a[3] = fmaf(p, __uint_as_float(raw.y & 0xffff0000u), a[3]);
-    a[4] = fmaf(p, __uint_as_float(raw.z << 16), a[4]); a[5] = fmaf(p, __uint_as_float(raw.z & 0xffff0000u), a[5]);
-    a[6] = fmaf(p, __uint_as_float(raw.w << 16), a[6]); a[7] = fmaf(p, __uint_as_float(raw.w & 0xffff0000u), a[7]);
-  }
-#pragma unroll
-  for (int o = 4; o < 32; o <<= 1) {
-#pragma unroll
-    for (int j = 0; j < 8; ++j) a[j] += __shfl_xor_sync(0xffffffffu, a[j], o);
-  }
-  if (kslot == 0) {
-    *reinterpret_cast<float4*>(out + sub * 8) = make_float4(a[0], a[1], a[2], a[3]);
-    *reinterpret_cast<float4*>(out + sub * 8 + 4) = make_float4(a[4], a[5], a[6], a[7]);
-  }
-}
-
-// merge the partial results of one image (lane = channel); parts with l == 0 are empty
+// merge the partial results (m, l, -, -, o[32]) of one image; lane = channel.  Parts with l == 0 are empty.
 __device__ __forceinline__ float attn_merge(const float* parts, int nparts) {
   const int lane = threadIdx.x & 31;
-  float M = -INFINITY;
-  for (int p = 0; p < nparts; ++p) { const float* b = parts + p * PSTR; if (b[1] > 0.f) M = fmaxf(M, b[0]); }
-  float L = 0.f, o = 0.f;
-  for (int p = 0; p < nparts; ++p) {
-    const float* b = parts + p * PSTR;
-    if (b[1] > 0.f) { const float w = expf(b[0] - M); L = fmaf(w, b[1], L); o = fmaf(w, b[4 + lane], o); }
-  }
+  float m = -INFINITY, l = 0.f;
+  if (lane < nparts) { m = parts[lane * PSTR]; l = parts[lane * PSTR + 1]; if (!(l > 0.f)) m = -INFINITY; }
+  const float M = warp_max(m);
+  const float w = (l > 0.f) ? exp2f(m - M) : 0.f;
+  const float L = warp_sum(w * l);
+  float o = 0.f;
+  for (int p = 0; p < nparts; ++p) o = fmaf(__shfl_sync(0xffffffffu, w, p), parts[p * PSTR + 4 + lane], o);
   return o / L;
 }
 
@@ -266,9 +320,11 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(NT, 1) decode_fused
   bf16* fh = (bf16*)(smem + OFF_FH); bf16* fl = (bf16*)(smem + OFF_FL);
   float* xres = (float*)(smem + OFF_XRES); float* yrecv = (float*)(smem + OFF_YRECV); float* f2recv = (float*)(smem + OFF_F2RECV);
   float* qs = (float*)(smem + OFF_QS); float* knew = (float*)(smem + OFF_KNEW); float* vnew = (float*)(smem + OFF_VNEW);
-  float* ytmp = (float*)(smem + OFF_YTMP); float* scb = (float*)(smem + OFF_SC); float* part = (float*)(smem + OFF_PART);
+  float* ytmp = (float*)(smem + OFF_YTMP); float* part = (float*)(smem + OFF_PART);
+  bf16* qh = (bf16*)(smem + OFF_QH); bf16* ql = (bf16*)(smem + OFF_QL);
   float* lrecv = (float*)(smem + OFF_LRECV); float* selbuf = (float*)(smem + OFF_SEL);
   int* tokbuf = (int*)(smem + OFF_TOK); int* pages = (int*)(smem + OFF_PAGES); uint8_t* padflag = smem + OFF_PADF;
+  int* haspad = (int*)(smem + OFF_HASPAD);
   const uint32_t bars = sbase + OFF_BARS;
   auto bar = [&](int i) -> uint32_t { return bars + i * 8; };
 
@@ -277,15 +333,16 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(NT, 1) decode_fused
     for (int i = BAR_O; i <= BAR_TOK; ++i) mbar_init(bar(i), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  // zero the activation operands once (rows >= G must stay finite)
-  for (int i = tid; i < 6 * ACT_BYTES / 4; i += NT) reinterpret_cast<uint32_t*>(smem + OFF_XH)[i] = 0u;
+  // zero the ring and the activation operands once: rows >= G of the operands and the rows behind a partial key tile
+  // of a K/V panel are multiplied by zeros and must be finite
+  for (int i = tid; i < (NS * STAGE_BYTES + 6 * ACT_BYTES) / 16; i += NT) reinterpret_cast<uint4*>(smem + OFF_RING)[i] = make_uint4(0u, 0u, 0u, 0u);
   __syncthreads();
   cluster_sync_all();
 
-  const float scale = rsqrtf((float)HD);
+  const float scale = rsqrtf((float)HD) * LOG2E;      // scores in log2 units: p = exp2(s - m)
   const int L = P.layers, S = P.S;
-  const int nC = (P.G + 1) / 2;                       // cross stages (2 images each), by the full group size
-  const int nS = (P.G + P.ips - 1) / P.ips;           // self stages
+  const int nC = P.G;                                 // cross stages: K and V panel of ONE image each (by the full group size)
+  const int nS = (P.G + P.ips - 1) / P.ips;           // self stages: K and V panels of `ips` images each
   const uint32_t self_panel = (uint32_t)P.np_max * 1024u;
   const uint32_t cross_panel = ((uint32_t)S * 64u + 1023u) & ~1023u;
 
@@ -301,17 +358,24 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(NT, 1) decode_fused
       const int g = i >> 5, j = i & 31;
       pages[i] = (g < G && j < P.pages_per_seq) ? P.page_table[(int64_t)(img0 + g) * P.pages_per_seq + j] : 0;
     }
+    if (tid < GM) haspad[tid] = 0;
+    __syncthreads();
     for (int i = tid; i < GM * 256; i += NT) {
       const int g = i >> 8, u = i & 255;
-      padflag[i] = (g < G && u < P.t_begin) ? (P.tokens[(int64_t)(img0 + g) * P.tokens_ld + u] == P.pad_idx) : 0;
+      const bool pd = (g < G && u < P.t_begin) ? (P.tokens[(int64_t)(img0 + g) * P.tokens_ld + u] == P.pad_idx) : false;
+      padflag[i] = pd;
+      if (pd) haspad[g] = 1;
     }
     __syncthreads();
     cluster_sync_all();          // no peer may push into this CTA before its buffers are set up for the group
 
     if (warp == 8) {
       // =================================== PRODUCER WARP ===================================================
+      long long prod_wait = 0;
       auto acquire = [&]() -> uint32_t {           // wait until the consumers released the slot
+        const long long c0 = P.trace ? clock64() : 0;
         mbar_wait(bar(BAR_EMPTY + slot), phase ^ 1);
+        if (P.trace) prod_wait += clock64() - c0;
         return sbase + OFF_RING + slot * STAGE_BYTES;
       };
       auto advance = [&]() { if (++slot == NS) { slot = 0; phase ^= 1; } };
@@ -335,20 +399,18 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(NT, 1) decode_fused
             if (lane == 0) { mbar_expect_tx(fb, 32 * 512); load_rows(&P.m_in[l], st, fb, 0, 2 * DM + rank * HD, 32); }
             advance();
           }
-          for (int sg = 0; sg < nS; ++sg) {        // self-KV: K pages then V pages of images [sg*ips, ...)
+          for (int sg = 0; sg < nS; ++sg) {        // self-KV: K and V pages of images [sg*ips, ...), panels [gi][k|v]
             const int g0 = sg * P.ips, gn = max(0, min(P.ips, G - g0));
-            const int ops = gn * npg;
-            for (int which = 0; which < 2; ++which) {
-              const uint32_t st = acquire(); const uint32_t fb = bar(BAR_FULL + slot);
-              if (lane == 0) mbar_expect_tx(fb, ops * P.PT * 64);
-              __syncwarp();
-              for (int op = lane; op < ops; op += 32) {
-                const int gi = op / npg, j = op - gi * npg;
-                const int page = pages[(g0 + gi) * 32 + j];
-                tma_2d(&P.m_pool, fb, st + gi * self_panel + j * (P.PT * 64), rank * HD, ((page * L + l) * 2 + which) * P.PT);
-              }
-              advance();
+            const int ops = gn * 2 * npg;
+            const uint32_t st = acquire(); const uint32_t fb = bar(BAR_FULL + slot);
+            if (lane == 0) mbar_expect_tx(fb, ops * P.PT * 64);
+            __syncwarp();
+            for (int op = lane; op < ops; op += 32) {
+              const int pn = op / npg, j = op - pn * npg;          // pn = gi*2 + which
+              const int page = pages[(g0 + (pn >> 1)) * 32 + j];
+              tma_2d(&P.m_pool, fb, st + pn * self_panel + j * (P.PT * 64), rank * HD, ((page * L + l) * 2 + (pn & 1)) * P.PT);
             }
+            advance();
           }
           {  // self out-proj rows, cross-q rows
             uint32_t st = acquire(); uint32_t fb = bar(BAR_FULL + slot);
@@ -358,17 +420,16 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(NT, 1) decode_fused
             if (lane == 0) { mbar_expect_tx(fb, 32 * 512); load_rows(&P.m_ca[l], st, fb, 0, rank * 32, 32); }
             advance();
           }
-          for (int sg = 0; sg < nC; ++sg) {        // cross K / V panels, 2 images per stage
-            const int g0 = sg * 2, gn = max(0, min(2, G - g0));
-            for (int which = 0; which < 2; ++which) {
-              const uint32_t st = acquire(); const uint32_t fb = bar(BAR_FULL + slot);
-              if (lane == 0) {
-                mbar_expect_tx(fb, gn * S * 64);
-                for (int gi = 0; gi < gn; ++gi)
-                  tma_2d(&P.m_ckv, fb, st + gi * cross_panel, which * DM + rank * HD, (l * P.B + img0 + g0 + gi) * S);
-              }
-              advance();
+          for (int g = 0; g < nC; ++g) {           // cross K and V panel of image g
+            const uint32_t st = acquire(); const uint32_t fb = bar(BAR_FULL + slot);
+            if (lane == 0) {
+              if (g < G) {
+                mbar_expect_tx(fb, 2 * S * 64);
+                tma_2d(&P.m_ckv, fb, st, rank * HD, (l * P.B + img0 + g) * S);
+                tma_2d(&P.m_ckv, fb, st + cross_panel, DM + rank * HD, (l * P.B + img0 + g) * S);
+              } else mbar_expect_tx(fb, 0);
             }
+            advance();
           }
           {  // cross out-proj rows
             const uint32_t st = acquire(); const uint32_t fb = bar(BAR_FULL + slot);
@@ -392,11 +453,20 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(NT, 1) decode_fused
           advance();
         }
       }
+      if (P.trace && lane == 0 && blockIdx.x == 0) P.trace[202] = prod_wait;
     } else {
       // =================================== CONSUMER WARPS ==================================================
+      long long cons_wait = 0, exch_wait = 0;
       auto stage_wait = [&]() -> uint32_t {
+        const long long c0 = P.trace ? clock64() : 0;
         mbar_wait(bar(BAR_FULL + slot), phase);
+        if (P.trace) cons_wait += clock64() - c0;
         return sbase + OFF_RING + slot * STAGE_BYTES;
+      };
+      auto xwait = [&](int which, uint32_t& ph) {    // wait for a push-style exchange
+        const long long c0 = P.trace ? clock64() : 0;
+        mbar_wait(bar(which), ph); ph ^= 1;
+        if (P.trace) exch_wait += clock64() - c0;
       };
       auto stage_release = [&]() {
         __syncwarp();
@@ -404,6 +474,8 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(NT, 1) decode_fused
         if (++slot == NS) { slot = 0; phase ^= 1; }
       };
       const int fg = lane >> 2, fq = lane & 3;       // MMA fragment coordinates: row group, image pair
+      int trace_n = 0;
+      auto TRACE = [&](int t_now) { if (P.trace && tid == 0 && blockIdx.x == 0 && t_now == P.trace_t) P.trace[trace_n++] = clock64(); };
       const int gi_t = tid >> 5, c_t = tid & 31;     // (image, channel) coordinates of the elementwise phases
       // push this CTA's [G][32] slice in ytmp into every peer's yrecv columns [32*rank, +32)
       auto push_y = [&](float v) {
@@ -415,7 +487,7 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(NT, 1) decode_fused
       };
       auto wait_y = [&]() {
         if (tid == 0) mbar_expect_tx(bar(BAR_Y), G * DM * 4);
-        mbar_wait(bar(BAR_Y), ph_y); ph_y ^= 1;
+        xwait(BAR_Y, ph_y);
       };
       // x = LN(xres + yrecv): warp w owns image w; writes xres and the hi/lo operand
       auto layer_norm = [&](const float* lnw, const float* lnb) {
@@ -460,7 +532,7 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(NT, 1) decode_fused
       };
       auto wait_o = [&]() {
         if (tid == 0) mbar_expect_tx(bar(BAR_O), G * DM * 4);     // hi + lo: G * 256 * (2 + 2) bytes
-        mbar_wait(bar(BAR_O), ph_o); ph_o ^= 1;
+        xwait(BAR_O, ph_o);
       };
       // a 32-row projection of the gathered operand (bh,bl) -> ytmp (+bias) -> pushed to all peers
       auto proj32_push = [&](uint32_t bh, uint32_t bl, const float* bias) {
@@ -486,7 +558,7 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(NT, 1) decode_fused
 #pragma unroll
           for (int j = 0; j < 8; ++j) pz[j] = __ldg(P.pos + (int64_t)t * DM + lane + 32 * j);
           const int tok = (P.forced || t == P.t_begin) ? __ldcg(P.tokens + (int64_t)(img0 + warp) * P.tokens_ld + t) : tokbuf[(t & 1) * GM + warp];
-          if (lane == 0) padflag[warp * 256 + t] = (tok == P.pad_idx);
+          if (lane == 0) { padflag[warp * 256 + t] = (tok == P.pad_idx); if (tok == P.pad_idx) haspad[warp] = 1; }
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const int c = lane + 32 * j;
@@ -497,6 +569,7 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(NT, 1) decode_fused
         }
         cbar();
         for (int l = 0; l < L; ++l) {
+          TRACE(t);   // 0: layer start
           // ---- self-attention in-proj: own head's q | k (stage A) and v (stage B) ---------------------------
           {
             const float* bi = P.b_in[l];
@@ -509,8 +582,10 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(NT, 1) decode_fused
               mma_mtile<32>(st + (warp >> 1) * 16384, (warp & 1) * 16, sbase + OFF_XH, sbase + OFF_XL, acc);
               const int f = (warp & 1) * 16 + fg;
               if (warp < 2) {      // q, pre-scaled
-                qs[(2 * fq) * 32 + f] = (acc[0] + b0) * scale; qs[(2 * fq + 1) * 32 + f] = (acc[1] + b0) * scale;
-                qs[(2 * fq) * 32 + f + 8] = (acc[2] + b1) * scale; qs[(2 * fq + 1) * 32 + f + 8] = (acc[3] + b1) * scale;
+                const float q0 = (acc[0] + b0) * scale, q1 = (acc[1] + b0) * scale, q2 = (acc[2] + b1) * scale, q3 = (acc[3] + b1) * scale;
+                qs[(2 * fq) * 32 + f] = q0; qs[(2 * fq + 1) * 32 + f] = q1; qs[(2 * fq) * 32 + f + 8] = q2; qs[(2 * fq + 1) * 32 + f + 8] = q3;
+                split_store(qh, ql, (2 * fq) * 32 + f, q0); split_store(qh, ql, (2 * fq + 1) * 32 + f, q1);
+                split_store(qh, ql, (2 * fq) * 32 + f + 8, q2); split_store(qh, ql, (2 * fq + 1) * 32 + f + 8, q3);
               } else {             // k, rounded to the cache precision
                 knew[(2 * fq) * 32 + f] = __bfloat162float(__float2bfloat16_rn(acc[0] + b0));
                 knew[(2 * fq + 1) * 32 + f] = __bfloat162float(__float2bfloat16_rn(acc[1] + b0));
@@ -532,8 +607,12 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(NT, 1) decode_fused
             stage_release();
           }
           cbar();
-          // append k_t, v_t (bf16) to the paged cache: 16-byte stores, 4 per (image, k|v)
+          TRACE(t);   // 1: in-proj done
+          // append k_t, v_t (bf16) to the paged cache: 16-byte stores, 4 per (image, k|v).  The proxy fence that orders them
+          // before the TMA reads of the page (one step later) is issued by the same threads one layer later, when the stores
+          // have long drained (a fence right behind the stores stalls ~1500 cycles).
           if (tid < G * 8) {
+            asm volatile("fence.proxy.async;" ::: "memory");     // the PREVIOUS layer's append -> visible to later TMA reads of the page
             const int g = tid >> 3, which = (tid >> 2) & 1, ch = tid & 3;
             const float* src = (which ? vnew : knew) + g * 32 + ch * 8;
             const float4 a = *reinterpret_cast<const float4*>(src), b = *reinterpret_cast<const float4*>(src + 4);
@@ -541,47 +620,54 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(NT, 1) decode_fused
             const int page = pages[g * 32 + t / P.PT];
             bf16* dst = P.kv_pool + (((int64_t)page * L + l) * 2 + which) * ((int64_t)P.PT * DM) + (int64_t)(t % P.PT) * DM + rank * HD + ch * 8;
             *reinterpret_cast<uint4*>(dst) = o;
-            asm volatile("fence.proxy.async;" ::: "memory");       // later TMA reads of the page must see this store
           }
-          // the step's own key as partial #8 of image `warp`
-          if (warp < G) {
-            float s = warp_sum(qs[warp * 32 + lane] * knew[warp * 32 + lane]);
-            if (padflag[warp * 256 + t]) s += 1.0f;
-            float* pb = part + (warp * NPART + 8) * PSTR;
-            if (lane == 0) { pb[0] = s; pb[1] = 1.0f; }
-            pb[4 + lane] = vnew[warp * 32 + lane];
-          }
-          // ---- self-attention over keys [0,t), head `rank`: each warp owns a key slice of every image -----------
+          TRACE(t);   // 2: append
+          // ---- self-attention, head `rank`: keys [0,t) from the paged cache, key tiles interleaved over the 8 warps;
+          //      the step's own key (still in shared memory) is partial #8 ---------------------------------------------
           {
-            const int sl = (t + 7) >> 3;
-            const int lo = min(t, warp * sl), hi = min(t, lo + sl);
+            const int ntile = (t + 15) >> 4;
+            if (warp < G) {
+              float s_own = warp_sum(qs[warp * 32 + lane] * knew[warp * 32 + lane]);
+              if (padflag[warp * 256 + t]) s_own += LOG2E;
+              float* pb = part + (warp * NPART + 8) * PSTR;
+              if (lane == 0) { pb[0] = s_own; pb[1] = 1.0f; }
+              pb[4 + lane] = vnew[warp * 32 + lane];
+            }
             for (int sg = 0; sg < nS; ++sg) {
               const int g0 = sg * P.ips, gn = max(0, min(P.ips, G - g0));
-              uint32_t st = stage_wait();
+              const uint32_t st = stage_wait();
               for (int gi = 0; gi < gn; ++gi) {
                 const int g = g0 + gi;
-                const float2 ml = attn_qk(st + gi * self_panel, qs + g * 32, lo, hi, padflag + g * 256, scb + (warp * GM + g) * 32);
-                if (lane == 0) { float* pb = part + (g * NPART + warp) * PSTR; pb[0] = ml.x; pb[1] = ml.y; }
-              }
-              stage_release();
-              st = stage_wait();
-              for (int gi = 0; gi < gn; ++gi) {
-                const int g = g0 + gi;
-                attn_pv(st + gi * self_panel, lo, hi, scb + (warp * GM + g) * 32, part + (g * NPART + warp) * PSTR + 4);
+                float* pb = part + (g * NPART + warp) * PSTR;
+                if (warp < ntile) {
+                  const uint32_t kp = st + gi * 2 * self_panel, vp = kp + self_panel;
+                  uint32_t aq[2][2];
+                  build_q_frag(qh + g * 32, ql + g * 32, aq);
+                  float m_run = -INFINITY, l_run = 0.f;
+                  float o[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+                  attn_tiles<2>(kp, vp, aq, warp, ntile, 8, t, haspad[g] ? padflag + g * 256 : nullptr, m_run, l_run, o);
+                  if (lane == 0) { pb[0] = m_run; pb[1] = l_run; }
+                  if ((lane & 3) == 0) {
+                    const int g8 = lane >> 2;
+                    pb[4 + g8] = o[0][0] + o[0][1]; pb[4 + g8 + 8] = o[0][2] + o[0][3];
+                    pb[4 + g8 + 16] = o[1][0] + o[1][1]; pb[4 + g8 + 24] = o[1][2] + o[1][3];
+                  }
+                } else if (lane == 0) pb[1] = 0.f;
               }
               stage_release();
             }
           }
           cbar();
-          {
-            float o = 0.f;
-            if (warp < G) o = attn_merge(part + warp * NPART * PSTR, NPART);
-            push_o(o);
-          }
+          TRACE(t);   // 3: self attention
+          push_o(warp < G ? attn_merge(part + warp * NPART * PSTR, NPART) : 0.f);
           wait_o();
+          TRACE(t);   // 4: o gathered
           // ---- self out-proj slice -> all-gather -> LN1 ------------------------------------------------------------
           proj32_push(sbase + OFF_OH, sbase + OFF_OL, P.b_so[l]);
+          TRACE(t);   // 5: out-proj pushed
           layer_norm(P.ln1w[l], P.ln1b[l]);
+          TRACE(t);   // 6: LN1
+
           // ---- cross-attention query slice -------------------------------------------------------------------------
           {
             const float* bc = P.b_ca[l];
@@ -592,42 +678,47 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(NT, 1) decode_fused
               float acc[4];
               mma_mtile<32>(st, warp * 16, sbase + OFF_XH, sbase + OFF_XL, acc);
               const int f = warp * 16 + fg;
-              qs[(2 * fq) * 32 + f] = (acc[0] + b0) * scale; qs[(2 * fq + 1) * 32 + f] = (acc[1] + b0) * scale;
-              qs[(2 * fq) * 32 + f + 8] = (acc[2] + b1) * scale; qs[(2 * fq + 1) * 32 + f + 8] = (acc[3] + b1) * scale;
+              split_store(qh, ql, (2 * fq) * 32 + f, (acc[0] + b0) * scale); split_store(qh, ql, (2 * fq + 1) * 32 + f, (acc[1] + b0) * scale);
+              split_store(qh, ql, (2 * fq) * 32 + f + 8, (acc[2] + b1) * scale); split_store(qh, ql, (2 * fq + 1) * 32 + f + 8, (acc[3] + b1) * scale);
             }
             stage_release();
           }
           cbar();
-          // ---- cross-attention over the S memory keys (2 images per panel stage) ---------------------------------
+          TRACE(t);   // 7: cross q
+          // ---- cross-attention over the S memory keys: one image per stage, key tiles interleaved over the 8 warps -------
           {
-            const int sl = (S + 7) >> 3;
-            const int lo = min(S, warp * sl), hi = min(S, lo + sl);
-            for (int sg = 0; sg < nC; ++sg) {
-              const int g0 = sg * 2, gn = max(0, min(2, G - g0));
-              uint32_t st = stage_wait();
-              for (int gi = 0; gi < gn; ++gi) {
-                const int g = g0 + gi;
-                const float2 ml = attn_qk(st + gi * cross_panel, qs + g * 32, lo, hi, nullptr, scb + (warp * GM + g) * 32);
-                if (lane == 0) { float* pb = part + (g * NPART + warp) * PSTR; pb[0] = ml.x; pb[1] = ml.y; }
-              }
-              stage_release();
-              st = stage_wait();
-              for (int gi = 0; gi < gn; ++gi) {
-                const int g = g0 + gi;
-                attn_pv(st + gi * cross_panel, lo, hi, scb + (warp * GM + g) * 32, part + (g * NPART + warp) * PSTR + 4);
+            const int ntile = (S + 15) >> 4;
+            for (int g = 0; g < nC; ++g) {
+              const uint32_t st = stage_wait();
+              if (g < G) {
+                float* pb = part + (g * NPART + warp) * PSTR;
+                if (warp < ntile) {
+                  uint32_t aq[2][2];
+                  build_q_frag(qh + g * 32, ql + g * 32, aq);
+                  float m_run = -INFINITY, l_run = 0.f;
+                  float o[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+                  attn_tiles<2>(st, st + cross_panel, aq, warp, ntile, 8, S, nullptr, m_run, l_run, o);
+                  if (lane == 0) { pb[0] = m_run; pb[1] = l_run; }
+                  if ((lane & 3) == 0) {
+                    const int g8 = lane >> 2;
+                    pb[4 + g8] = o[0][0] + o[0][1]; pb[4 + g8 + 8] = o[0][2] + o[0][3];
+                    pb[4 + g8 + 16] = o[1][0] + o[1][1]; pb[4 + g8 + 24] = o[1][2] + o[1][3];
+                  }
+                } else if (lane == 0) pb[1] = 0.f;
               }
               stage_release();
             }
           }
           cbar();
-          {
-            float o = 0.f;
-            if (warp < G) o = attn_merge(part + warp * NPART * PSTR, 8);
-            push_o(o);
-          }
+          TRACE(t);   // 8: cross attention partials
+          push_o(warp < G ? attn_merge(part + warp * NPART * PSTR, 8) : 0.f);
           wait_o();
+          TRACE(t);   // 9: o gathered
           proj32_push(sbase + OFF_OH, sbase + OFF_OL, P.b_co[l]);
+          TRACE(t);   // 10: cross out-proj pushed
           layer_norm(P.ln2w[l], P.ln2b[l]);
+          TRACE(t);   // 11: LN2
+
           // ---- FFN1: own 256 hidden units, ReLU, kept local as the FFN2 operand -----------------------------------
           for (int s4 = 0; s4 < 4; ++s4) {
             const int mt = warp - (s4 & 1) * 4;          // stages 0,2 -> warps 0-3; stages 1,3 -> warps 4-7
@@ -645,6 +736,7 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(NT, 1) decode_fused
             stage_release();
           }
           cbar();
+          TRACE(t);   // 12: FFN1
           // ---- FFN2 as a K-split: partial sums pushed straight to the CTA that owns the output columns -----------
           for (int s4 = 0; s4 < 4; ++s4) {
             const int mt = warp - (s4 & 1) * 4;
@@ -662,10 +754,11 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(NT, 1) decode_fused
             }
             stage_release();
           }
+          TRACE(t);   // 13: FFN2 issued
           {  // reduce the 8 partial slices of the own 32 columns, add bias, all-gather, LN3
             const float b2 = __ldg(P.b_f2[l] + rank * 32 + c_t);
             if (tid == 0) mbar_expect_tx(bar(BAR_F2), G * DM * 4);
-            mbar_wait(bar(BAR_F2), ph_f2); ph_f2 ^= 1;
+            xwait(BAR_F2, ph_f2);
             float a = b2;
             if (gi_t < G) {
 #pragma unroll
@@ -673,7 +766,10 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(NT, 1) decode_fused
             }
             push_y(a);
           }
+          TRACE(t);   // 14: FFN2 reduced + pushed
           layer_norm(P.ln3w[l], P.ln3b[l]);
+          TRACE(t);   // 15: LN3
+
         }
         // ---- vocabulary head: own 40 rows -> logits to the caller's tensor and to the CTA that selects for the image ---
         const bool want_conf = P.confs && (t % 4 == 0);
@@ -703,6 +799,7 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(NT, 1) decode_fused
           }
           stage_release();
         }
+        TRACE(t);     // head done
         // ---- select: CTA `rank` owns image `rank` ------------------------------------------------------------------
         if (need_select && (int)rank < G) {
           const int V = P.vocab;
@@ -729,9 +826,11 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(NT, 1) decode_fused
         }
         if (!P.forced) {
           if (tid == 0) mbar_expect_tx(bar(BAR_TOK), G * 4);
-          mbar_wait(bar(BAR_TOK), ph_tok); ph_tok ^= 1;
+          xwait(BAR_TOK, ph_tok);
         }
+        TRACE(t);     // tokens exchanged
       }
+      if (P.trace && tid == 0 && blockIdx.x == 0) { P.trace[200] = cons_wait; P.trace[201] = exch_wait; }
     }
   }
   // no CTA may exit while a peer can still push into its shared memory
@@ -801,6 +900,8 @@ int decode_cluster_launch(mdc_model* m, const mdc_decode_state* st, int t_begin,
   P.confs = st->confs; P.confs_ld = st->confs_ld;
   P.uniforms = st->uniforms; P.uniforms_ld = st->uniforms_ld; P.top_k = st->top_k; P.top_p = st->top_p; P.forced = st->forced;
   P.t_begin = t_begin; P.t_end = t_end;
+  P.trace = nullptr; P.trace_t = -1;
+  if (const char* tp = getenv("MDC_DECODE_TRACE_PTR")) { P.trace = (long long*)strtoull(tp, nullptr, 0); const char* tt = getenv("MDC_DECODE_TRACE_T"); P.trace_t = tt ? atoi(tt) : t_begin; }
   // cross-K/V [layers*B*S rows][2*DM]: one (S rows x 32 channels) box per (image, head, k|v); paged pool: one page x head box
   MDC_TRY(mdc_make_tmap_2d(ctx, st->cross_kv, (int64_t)d.dec_layers * st->B * d.n_patches, 2 * DM, 2 * DM, HD, d.n_patches, 2, &P.m_ckv));
   MDC_TRY(mdc_make_tmap_2d(ctx, st->kv_pool, (int64_t)st->n_pages * d.dec_layers * 2 * d.page_tokens, DM, DM, HD, d.page_tokens, 2, &P.m_pool));
@@ -822,7 +923,7 @@ int decode_cluster_launch(mdc_model* m, const mdc_decode_state* st, int t_begin,
   P.n_groups = (P.B + G - 1) / G;
   P.np_max = (t_end + d.page_tokens - 1) / d.page_tokens;
   if (P.np_max < 1) P.np_max = 1;
-  P.ips = STAGE_BYTES / (P.np_max * 1024);
+  P.ips = STAGE_BYTES / (2 * P.np_max * 1024);       // a stage holds the K and the V panel of `ips` images
   if (P.ips > GM) P.ips = GM;
   if (P.ips < 1) MDC_FAIL(-2, "decode_cluster: key capacity %d does not fit a stage", t_end);
   const int n_clusters = P.n_groups < max_clusters ? P.n_groups : max_clusters;
