@@ -29,10 +29,11 @@
 extern "C" {
 #endif
 
-#define MDC_ABI_VERSION 1
+#define MDC_ABI_VERSION 2
 
-/* element types of activations / weights */
-enum { MDC_F32 = 0, MDC_BF16 = 1 };
+/* element types of activations / weights.  MDC_F16 (IEEE half) is only ever the type of the decode-loop weights, see
+ * mdc_dims.dec_loop_dtype. */
+enum { MDC_F32 = 0, MDC_BF16 = 1, MDC_F16 = 2 };
 
 /* GEMM epilogues: D = epi(A[M,K] . W[N,K]^T) */
 enum {
@@ -118,11 +119,18 @@ typedef struct mdc_dims {
   int32_t pad_idx, bos_idx;
   int32_t has_axial;     /* axial_model.Decoder.axial_attention present */
   int32_t page_tokens;   /* self-attention KV page size in tokens (16) */
+  int32_t dec_loop_dtype;/* element type of the weights the autoregressive loop re-reads every step: MDC_SA_IN_W, MDC_SA_OUT_W,
+                            rows [0,dim) of MDC_CA_IN_W (the cross-attention query projection), MDC_CA_OUT_W, MDC_FF1_W, MDC_FF2_W
+                            and MDC_OUT_W.  MDC_F32 with precision MDC_F32; with precision MDC_BF16 either MDC_BF16 or MDC_F16.
+                            fp16 has the same footprint and tensor-core rate as bf16 but 3 more mantissa bits: rounding these
+                            weights to bf16 alone costs 1.4e-2 of the 2e-2 max-abs logit budget (tools/error_budget_cpu.py),
+                            to fp16 2e-3.  Rows [dim,3dim) of MDC_CA_IN_W (cross K/V in-projection, a tcgen05 GEMM against the
+                            bf16 memory) and every other GEMM weight stay `precision` typed; KV caches stay `precision` typed. */
 } mdc_dims;
 
 /* Weight table: device pointers in the order of enum mdc_weight_slot, per-layer slots repeated.
- * GEMM weights are `precision` typed [N,K]; everything else (biases, norms, gammas, positional
- * tables, embedding, cls token) is f32.  The library keeps the pointers, never copies. */
+ * GEMM weights are `precision` typed [N,K] (decode-loop weights: `dec_loop_dtype`, see mdc_dims); everything else
+ * (biases, norms, gammas, positional tables, embedding, cls token) is f32.  The library keeps the pointers, never copies. */
 enum mdc_enc_slot {  /* encoder globals */
   MDC_W_PATCH = 0, MDC_B_PATCH, MDC_CLS, MDC_POS, MDC_NORM_W, MDC_NORM_B, MDC_ENC_GLOBAL_SLOTS
 };

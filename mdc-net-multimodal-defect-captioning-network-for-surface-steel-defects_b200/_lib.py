@@ -14,7 +14,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmdc_b200.so")
 
-MDC_F32, MDC_BF16 = 0, 1
+MDC_F32, MDC_BF16, MDC_F16 = 0, 1, 2
 EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RELU, EPI_LS_RESIDUAL, EPI_PATCH = range(5)
 IOU_EPS, IOU_PLAIN, IOU_NAN0, IOU_GIOU = range(4)
 
@@ -32,7 +32,7 @@ class Dims(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
         "precision", "img_size", "patch", "in_chans", "enc_dim", "enc_depth", "enc_heads", "enc_mlp",
         "n_patches", "dim", "dec_heads", "dec_layers", "dec_ffn", "vocab", "max_pos", "pad_idx", "bos_idx",
-        "has_axial", "page_tokens")]
+        "has_axial", "page_tokens", "dec_loop_dtype")]
 
 
 class DecodeState(C.Structure):
@@ -133,8 +133,25 @@ def ctx(device=None):
     return _ctxs[idx]
 
 
+_replayed = {}
+
+
+def _dev_index(device=None):
+    idx = torch.cuda.current_device() if device is None else torch.device(device).index
+    return torch.cuda.current_device() if idx is None else idx
+
+
+def note_graph_replay(device, n_kernels):
+    """A CUDA-graph replay re-launches the `n_kernels` kernels counted while the graph was captured; the C side only
+    sees the capture, so replays are accounted here."""
+    i = _dev_index(device)
+    _replayed[i] = _replayed.get(i, 0) + int(n_kernels)
+
+
 def launch_count(device=None):
-    return int(lib().mdc_ctx_launch_count(ctx(device)))
+    """Kernels of libmdc_b200.so launched on `device` so far: direct launches (counted in C, mdc_ctx_launch_count)
+    plus the kernels inside replayed CUDA graphs."""
+    return int(lib().mdc_ctx_launch_count(ctx(device))) + _replayed.get(_dev_index(device), 0)
 
 
 def stream_ptr():

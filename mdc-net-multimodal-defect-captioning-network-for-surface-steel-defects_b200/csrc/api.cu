@@ -48,6 +48,7 @@ extern "C" int mdc_model_create(mdc_ctx* ctx, const mdc_dims* d, const void* con
   MDC_CHECK_ARG(ctx && d && weights && out);
   MDC_CHECK_ARG(d->precision == MDC_F32 || d->precision == MDC_BF16);
   MDC_CHECK_ARG(n_weights == mdc_model_num_weights(d));
+  MDC_CHECK_ARG(d->precision == MDC_F32 ? d->dec_loop_dtype == MDC_F32 : (d->dec_loop_dtype == MDC_BF16 || d->dec_loop_dtype == MDC_F16));
   MDC_CHECK_ARG(d->enc_dim % d->enc_heads == 0 && d->dim % d->dec_heads == 0);
   MDC_CHECK_ARG(d->enc_dim % 8 == 0 && d->dim % 32 == 0 && d->dec_ffn % 8 == 0);
   MDC_CHECK_ARG((d->dim / d->dec_heads) % 8 == 0 && (d->dim / d->dec_heads) <= 128);

@@ -18,6 +18,7 @@
 // The head kernel fuses LN3 + vocab projection + greedy / top-k / top-p select + max-prob.
 #include "common.cuh"
 #include "select.cuh"
+#include <cuda_fp16.h>
 #include <float.h>
 
 int decode_cluster_supported(const mdc_model* m, const mdc_decode_state* st, int t_end);
@@ -183,6 +184,16 @@ template <> struct Raw8<bf16> {
     const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
 #pragma unroll
     for (int i = 0; i < 4; ++i) { float2 t = __bfloat1622float2(h[i]); f[2 * i] = t.x; f[2 * i + 1] = t.y; }
+  }
+};
+template <> struct Raw8<__half> {      // decode-loop weights on the bf16 path (mdc_dims.dec_loop_dtype == MDC_F16)
+  uint4 v;
+  __device__ __forceinline__ void load(const __half* p) { v = __ldg(reinterpret_cast<const uint4*>(p)); }
+  __device__ __forceinline__ void zero() { v = make_uint4(0, 0, 0, 0); }
+  __device__ __forceinline__ void unpack(float* f) const {
+    const __half2* h = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { float2 t = __half22float2(h[i]); f[2 * i] = t.x; f[2 * i + 1] = t.y; }
   }
 };
 template <> struct Raw8<float> {
@@ -513,7 +524,8 @@ Scratch carve(const mdc_dims& d, int B, void* p) {
   return s;
 }
 
-template <typename T>
+// TW: element type of the decode-loop weights (mdc_dims.dec_loop_dtype), T: element type of the KV caches (`precision`)
+template <typename TW, typename T>
 int decode_step_typed(mdc_model* m, const mdc_decode_state* st, int t, cudaStream_t s) {
   mdc_ctx* ctx = m->ctx; const mdc_dims& d = m->d;
   const int B = st->B, dim = d.dim, hd = dim / d.dec_heads;
@@ -531,7 +543,7 @@ int decode_step_typed(mdc_model* m, const mdc_decode_state* st, int t, cudaStrea
     const void** lw = lw0 + l * MDC_DEC_LAYER_SLOTS;
     // qkv = LNload(prev) . Ws^T + bs; publishes xa
     XSrc x1 = prev; x1.xn_out = sc.xa;
-    MDC_TRY(launch_linear<T>(ctx, x1, lw[MDC_SA_IN_W], (const float*)lw[MDC_SA_IN_B], sc.qkv, 3 * dim, B, 3 * dim, dim, false, s));
+    MDC_TRY(launch_linear<TW>(ctx, x1, lw[MDC_SA_IN_W], (const float*)lw[MDC_SA_IN_B], sc.qkv, 3 * dim, B, 3 * dim, dim, false, s));
     {
       size_t smem = (size_t)d.dec_heads * (hd + t + 1 + st->pages_per_seq) * sizeof(float);
 #define MDC_SA(HD_)                                                                                                      \
@@ -546,11 +558,11 @@ int decode_step_typed(mdc_model* m, const mdc_decode_state* st, int t, cudaStrea
       MDC_LAUNCH_CHECK(ctx);
     }
     XSrc xo{}; xo.mode = XMODE_PLAIN; xo.x = sc.o; xo.ldx = dim;
-    MDC_TRY(launch_linear<T>(ctx, xo, lw[MDC_SA_OUT_W], (const float*)lw[MDC_SA_OUT_B], sc.y1, dim, B, dim, dim, false, s));
+    MDC_TRY(launch_linear<TW>(ctx, xo, lw[MDC_SA_OUT_W], (const float*)lw[MDC_SA_OUT_B], sc.y1, dim, B, dim, dim, false, s));
     // cross-attention query from LN1(xa + y1); publishes xb
     XSrc x2{}; x2.mode = XMODE_LN; x2.resid = sc.xa; x2.delta = sc.y1; x2.ln_w = (const float*)lw[MDC_LN1_W]; x2.ln_b = (const float*)lw[MDC_LN1_B];
     x2.eps = 1e-5f; x2.xn_out = sc.xb;
-    MDC_TRY(launch_linear<T>(ctx, x2, lw[MDC_CA_IN_W], (const float*)lw[MDC_CA_IN_B], sc.qc, dim, B, dim, dim, false, s));
+    MDC_TRY(launch_linear<TW>(ctx, x2, lw[MDC_CA_IN_W], (const float*)lw[MDC_CA_IN_B], sc.qc, dim, B, dim, dim, false, s));
     {
       size_t smem = (size_t)d.dec_heads * (hd + d.n_patches) * sizeof(float);
       const T* ckv = (const T*)st->cross_kv + (int64_t)l * B * d.n_patches * 2 * dim;
@@ -564,19 +576,19 @@ int decode_step_typed(mdc_model* m, const mdc_decode_state* st, int t, cudaStrea
       MDC_LAUNCH_CHECK(ctx);
     }
     XSrc xco{}; xco.mode = XMODE_PLAIN; xco.x = sc.oc; xco.ldx = dim;
-    MDC_TRY(launch_linear<T>(ctx, xco, lw[MDC_CA_OUT_W], (const float*)lw[MDC_CA_OUT_B], sc.y2, dim, B, dim, dim, false, s));
+    MDC_TRY(launch_linear<TW>(ctx, xco, lw[MDC_CA_OUT_W], (const float*)lw[MDC_CA_OUT_B], sc.y2, dim, B, dim, dim, false, s));
     // FFN
     XSrc x3{}; x3.mode = XMODE_LN; x3.resid = sc.xb; x3.delta = sc.y2; x3.ln_w = (const float*)lw[MDC_LN2_W]; x3.ln_b = (const float*)lw[MDC_LN2_B];
     x3.eps = 1e-5f; x3.xn_out = sc.xc;
-    MDC_TRY(launch_linear<T>(ctx, x3, lw[MDC_FF1_W], (const float*)lw[MDC_FF1_B], sc.f1, d.dec_ffn, B, d.dec_ffn, dim, true, s));
+    MDC_TRY(launch_linear<TW>(ctx, x3, lw[MDC_FF1_W], (const float*)lw[MDC_FF1_B], sc.f1, d.dec_ffn, B, d.dec_ffn, dim, true, s));
     XSrc xf{}; xf.mode = XMODE_PLAIN; xf.x = sc.f1; xf.ldx = d.dec_ffn;
-    MDC_TRY(launch_linear<T>(ctx, xf, lw[MDC_FF2_W], (const float*)lw[MDC_FF2_B], sc.y3, dim, B, dim, d.dec_ffn, false, s));
+    MDC_TRY(launch_linear<TW>(ctx, xf, lw[MDC_FF2_W], (const float*)lw[MDC_FF2_B], sc.y3, dim, B, dim, d.dec_ffn, false, s));
     prev = XSrc{}; prev.mode = XMODE_LN; prev.resid = sc.xc; prev.delta = sc.y3; prev.ln_w = (const float*)lw[MDC_LN3_W];
     prev.ln_b = (const float*)lw[MDC_LN3_B]; prev.eps = 1e-5f;
   }
   {
     const int V = d.vocab, Vp2 = next_pow2(V);
-    MDC_TRY(launch_linear<T>(ctx, prev, gw[MDC_OUT_W], (const float*)gw[MDC_OUT_B], sc.lg, V, B, V, dim, false, s));
+    MDC_TRY(launch_linear<TW>(ctx, prev, gw[MDC_OUT_W], (const float*)gw[MDC_OUT_B], sc.lg, V, B, V, dim, false, s));
     size_t smem = (size_t)(V + Vp2) * sizeof(float);
     MDC_ENSURE_SMEM(dec_select_kernel, smem);
     dec_select_kernel<<<B, SEL_THREADS, smem, s>>>(sc.lg, V, Vp2, t, st->logits, (int64_t)st->logits_ld * V, t + st->logits_row_offset,
@@ -615,8 +627,9 @@ extern "C" int mdc_decode_steps(mdc_model* m, const mdc_decode_state* st, int t_
     return decode_cluster_launch(m, st, t_begin, t_end, sc.lg, s);
   }
   for (int t = t_begin; t < t_end; ++t) {
-    if (m->d.precision == MDC_F32) MDC_TRY(decode_step_typed<float>(m, st, t, s));
-    else MDC_TRY(decode_step_typed<bf16>(m, st, t, s));
+    if (m->d.precision == MDC_F32) MDC_TRY((decode_step_typed<float, float>(m, st, t, s)));
+    else if (m->d.dec_loop_dtype == MDC_F16) MDC_TRY((decode_step_typed<__half, bf16>(m, st, t, s)));
+    else MDC_TRY((decode_step_typed<bf16, bf16>(m, st, t, s)));
   }
   return 0;
 }

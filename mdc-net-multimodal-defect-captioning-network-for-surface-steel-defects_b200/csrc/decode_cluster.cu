@@ -14,8 +14,10 @@
 //     ahead of the 8 consumer warps across phase, layer and step boundaries.
 //   * projections run on the tensor cores with the roles swapped: the WEIGHT rows are the MMA M dimension
 //     (mma.sync m16n8k16, A fragments by ldmatrix from the swizzled TMA tile), the G <= 8 images are the N = 8
-//     dimension, so no MMA lane is wasted on padding.  Activations are split hi+lo into two bf16 operands
-//     (x = hi + lo, two MMAs), so the bf16 WEIGHTS are the only rounding -- the numerics of the unfused kernels.
+//     dimension, so no MMA lane is wasted on padding.  The decode-loop weights are IEEE fp16 (mdc_dims.dec_loop_dtype: same
+//     bytes as bf16, 8x smaller rounding); activations are split hi+lo into two fp16 operands (x = hi + lo, two MMAs), so the
+//     16-bit WEIGHTS are the only rounding -- the numerics of the unfused kernels.  Attention keeps bf16 K/V (the caches) with
+//     bf16 hi+lo queries and probabilities.
 //   * activations (a few KB) are exchanged through DISTRIBUTED SHARED MEMORY, push style: the producer of a slice
 //     writes it into every peer with st.async (...mbarrier::complete_tx), the consumer waits on a local mbarrier
 //     for the expected byte count.  No cluster-wide barrier inside the loop.
@@ -25,6 +27,7 @@
 // mdc_decode_steps picks this kernel when the geometry matches.
 #include "common.cuh"
 #include <cuda.h>
+#include <cuda_fp16.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -150,21 +153,36 @@ __device__ __forceinline__ void mma16816(float* c, const uint32_t* a, uint32_t b
   asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
+// projections: fp16 weights (A) x fp16 hi/lo activations (B), fp32 accumulate
+__device__ __forceinline__ void mma16816_h(float* c, const uint32_t* a, uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
 __device__ __forceinline__ uint4 lds128(uint32_t addr) {
   uint4 v; asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr)); return v;
 }
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 h = __floats2bfloat162_rn(a, b); return *reinterpret_cast<uint32_t*>(&h);
 }
-__device__ __forceinline__ void split_store(bf16* hi, bf16* lo, int idx, float x) {
+__device__ __forceinline__ void split_store(bf16* hi, bf16* lo, int idx, float x) {      // attention queries: bf16 pair (K/V are bf16)
   bf16 h = __float2bfloat16_rn(x);
   hi[idx] = h; lo[idx] = __float2bfloat16_rn(x - __bfloat162float(h));
+}
+// projection operands: x = hi + lo as an fp16 pair (22 significant bits); |x| is clamped to the fp16 range first
+__device__ __forceinline__ float clamp_h(float x) { return fminf(fmaxf(x, -65504.f), 65504.f); }
+__device__ __forceinline__ void split_store(__half* hi, __half* lo, int idx, float x) {
+  x = clamp_h(x);
+  const __half h = __float2half_rn(x);
+  hi[idx] = h; lo[idx] = __float2half_rn(x - __half2float(h));
+}
+__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
+  __half2 h = __floats2half2_rn(a, b); return *reinterpret_cast<uint32_t*>(&h);
 }
 
 // One 16-row tile of a projection with the weights as the M operand:
 //   acc[0..3] = D[m0+g][img 2q], D[m0+g][2q+1], D[m0+g+8][2q], D[m0+g+8][2q+1]   (g = lane/4, q = lane%4)
-// wblk: shared address of the TMA row block [4 k-blocks][R rows][128 B] (SWIZZLE_128B); bh/bl: hi/lo activations
-// [8 images][XP] bf16.  Four independent accumulator chains hide the HMMA latency.
+// wblk: shared address of the TMA row block [4 k-blocks][R rows][128 B] (SWIZZLE_128B), fp16 weights; bh/bl: hi/lo activations
+// [8 images][XP] fp16.  Four independent accumulator chains hide the HMMA latency.
 template <int R>
 __device__ __forceinline__ void mma_mtile(uint32_t wblk, int m0, uint32_t bh, uint32_t bl, float* acc) {
   const int lane = threadIdx.x & 31;
@@ -180,8 +198,8 @@ __device__ __forceinline__ void mma_mtile(uint32_t wblk, int m0, uint32_t bh, ui
     ldsm_x4(a1, a_base + kb * (R * 128) + (((ch + 2 + csel) ^ sw) << 4));
     ldsm_x4(xh, bh + boff + i * 64);
     ldsm_x4(xl, bl + boff + i * 64);
-    mma16816(c0, a0, xh[0], xh[1]); mma16816(c1, a0, xl[0], xl[1]);
-    mma16816(c2, a1, xh[2], xh[3]); mma16816(c3, a1, xl[2], xl[3]);
+    mma16816_h(c0, a0, xh[0], xh[1]); mma16816_h(c1, a0, xl[0], xl[1]);
+    mma16816_h(c2, a1, xh[2], xh[3]); mma16816_h(c3, a1, xl[2], xl[3]);
   }
 #pragma unroll
   for (int j = 0; j < 4; ++j) acc[j] = (c0[j] + c2[j]) + (c1[j] + c3[j]);
@@ -316,8 +334,8 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(NT, 1) decode_fused
   uint32_t rank; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
   const int cid = blockIdx.x / CS, n_clusters = gridDim.x / CS;
 
-  bf16* xh = (bf16*)(smem + OFF_XH); bf16* xl = (bf16*)(smem + OFF_XL);
-  bf16* fh = (bf16*)(smem + OFF_FH); bf16* fl = (bf16*)(smem + OFF_FL);
+  __half* xh = (__half*)(smem + OFF_XH); __half* xl = (__half*)(smem + OFF_XL);      // projection operands: fp16 hi / lo
+  __half* fh = (__half*)(smem + OFF_FH); __half* fl = (__half*)(smem + OFF_FL);
   float* xres = (float*)(smem + OFF_XRES); float* yrecv = (float*)(smem + OFF_YRECV); float* f2recv = (float*)(smem + OFF_F2RECV);
   float* qs = (float*)(smem + OFF_QS); float* knew = (float*)(smem + OFF_KNEW); float* vnew = (float*)(smem + OFF_VNEW);
   float* ytmp = (float*)(smem + OFF_YTMP); float* part = (float*)(smem + OFF_PART);
@@ -521,10 +539,11 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(NT, 1) decode_fused
         const int j = lane & 15;
         const float v0 = __shfl_sync(0xffffffffu, o, 2 * j), v1 = __shfl_sync(0xffffffffu, o, 2 * j + 1);
         if (warp < G) {
-          const bf16 h0 = __float2bfloat16_rn(v0), h1 = __float2bfloat16_rn(v1);
+          const float w0 = clamp_h(v0), w1 = clamp_h(v1);
+          const __half h0 = __float2half_rn(w0), h1 = __float2half_rn(w1);
           uint32_t val;
-          if (lane < 16) val = pack_bf16(v0, v1);
-          else val = pack_bf16(v0 - __bfloat162float(h0), v1 - __bfloat162float(h1));
+          if (lane < 16) val = pack_h2(w0, w1);
+          else val = pack_h2(w0 - __half2float(h0), w1 - __half2float(h1));
           const uint32_t off = sbase + (lane < 16 ? OFF_OH : OFF_OL) + (warp * XP + 32 * rank + 2 * j) * 2;
 #pragma unroll
           for (int p = 0; p < CS; ++p) st_async_b32(mapa(off, p), val, mapa(bar(BAR_O), p));
@@ -849,7 +868,7 @@ struct FusedCache {
 
 int decode_cluster_supported(const mdc_model* m, const mdc_decode_state* st, int t_end) {
   const mdc_dims& d = m->d;
-  if (d.precision != MDC_BF16 || d.dim != DM || d.dec_heads != CS || d.dec_ffn != FFN) return 0;
+  if (d.precision != MDC_BF16 || d.dec_loop_dtype != MDC_F16 || d.dim != DM || d.dec_heads != CS || d.dec_ffn != FFN) return 0;
   if (d.dec_layers < 1 || d.dec_layers > 8 || d.vocab > CS * VSL || d.vocab < 8) return 0;
   if (st->x_override || st->pos_override) return 0;
   if (d.n_patches > 256 || d.n_patches < 8) return 0;             // one TMA box (<= 256 rows) per image panel, 2 panels per stage

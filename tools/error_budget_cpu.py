@@ -5,7 +5,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from oracle import cases, mdc_oracle as O
 
 bf = lambda t: t.to(torch.bfloat16).float()
-FLAGS = dict(sq=False, sk=False, sv=False, so=False, cq=False, co=False, f1=False, f2=False, w_dec=False, w_head=False, w_ckv=False, mem=False, ckv=False, skv=False, act=False, w_enc=False, hid=False, w_fp16=False)
+FLAGS = dict(sq=False, sk=False, sv=False, so=False, cq=False, co=False, f1=False, f2=False, w_dec=False, w_head=False, w_ckv=False, mem=False, ckv=False, skv=False, act=False, w_enc=False, hid=False, w_fp16=False, own_exact=False)
 
 def mha(xq, xkv, w, b, wo, bo, heads, bias=None, cross=False):
     d = xq.shape[-1]; hd = d // heads
@@ -24,12 +24,22 @@ def mha(xq, xkv, w, b, wo, bo, heads, bias=None, cross=False):
     a = bf if FLAGS["act"] else (lambda t: t)
     q = a(xq) @ wq.T + b[:d]
     k = a(xkv) @ wk.T + b[d:2*d]; v = a(xkv) @ wv.T + b[2*d:]
+    k_ex, v_ex = k, v
     if (cross and FLAGS["ckv"]) or (not cross and FLAGS["skv"]): k, v = bf(k), bf(v)
     B, Lq, _ = q.shape; Lk = k.shape[1]
     q = q.reshape(B, Lq, heads, hd).transpose(1, 2); k = k.reshape(B, Lk, heads, hd).transpose(1, 2); v = v.reshape(B, Lk, heads, hd).transpose(1, 2)
     s = (q @ k.transpose(-1, -2)) / math.sqrt(hd)
     if bias is not None: s = s + bias
-    o = torch.softmax(s, dim=-1) @ v
+    if FLAGS["own_exact"] and not cross:
+        ke = k_ex.reshape(B, Lk, heads, hd).transpose(1, 2); ve = v_ex.reshape(B, Lk, heads, hd).transpose(1, 2)
+        sd_ = (q * ke).sum(-1) / math.sqrt(hd)
+        idx = torch.arange(Lq)
+        s[:, :, idx, idx] = sd_ + (bias[:, :, idx, idx] if bias is not None else 0)
+        p = torch.softmax(s, dim=-1)
+        pd = p[:, :, idx, idx]
+        o = p @ v + pd[..., None] * (ve - v)
+    else:
+        o = torch.softmax(s, dim=-1) @ v
     return a(o.transpose(1, 2).reshape(B, Lq, d)) @ woo.T + bo
 
 def stack(sd, x, mem, tokens, cfg, prefix="decoder.decoder.layers.", eps=1e-5):
@@ -91,6 +101,13 @@ with torch.no_grad():
         print("  f1,f2,so,co,sv bf16 (q,k exact)     ", run(**base, f1=True, f2=True, so=True, co=True, sv=True))
         print("  f1,f2 bf16 only (+kv)               ", run(**base, f1=True, f2=True))
         print("  f1,f2,sq,sk,sv bf16 (outs exact)    ", run(**base, f1=True, f2=True, sq=True, sk=True, sv=True, cq=True))
+        full = dict(w_dec=True, w_head=True, w_ckv=True, ckv=True, skv=True, mem=True)
+        print("  FULL (gpu-like)                      ", run(**full))
+        print("  FULL, own k/v exact                  ", run(**full, own_exact=True))
+        print("  FULL, head exact                     ", run(**{**full, "w_head": False}))
+        print("  FULL, head exact + own exact         ", run(**{**full, "w_head": False}, own_exact=True))
+        print("  FULL, self kv exact                  ", run(**{**full, "skv": False}))
+        print("  FULL, head exact, self kv exact      ", run(**{**full, "skv": False, "w_head": False}))
         print("  all weights bf16        ", run(w_dec=True, w_head=True, w_ckv=True))
         print("  all weights + kv storage", run(w_dec=True, w_head=True, w_ckv=True, ckv=True, skv=True))
         print("  ... + mem bf16          ", run(w_dec=True, w_head=True, w_ckv=True, ckv=True, skv=True, mem=True))

@@ -9,7 +9,10 @@ reps = int(sys.argv[2]) if len(sys.argv) > 2 else 20
 shapes = [("qkv", B * 197, 1536, 512, L.EPI_BIAS), ("fc1", B * 197, 2048, 512, L.EPI_BIAS_GELU),
           ("proj", B * 197, 512, 512, L.EPI_LS_RESIDUAL), ("fc2", B * 197, 512, 2048, L.EPI_LS_RESIDUAL),
           ("patch", B * 196, 512, 768, L.EPI_PATCH), ("crosskv", B * 196, 512, 256, L.EPI_BIAS)]
+only = sys.argv[3].split(",") if len(sys.argv) > 3 else None
 for name, Mr, N, K, epi in shapes:
+    if only and name not in only:
+        continue
     A = (torch.randn(Mr, K, device=dev) * 0.5).to(torch.bfloat16)
     W = (torch.randn(N, K, device=dev) * 0.05).to(torch.bfloat16)
     bias = torch.zeros(N, device=dev); gamma = torch.ones(N, device=dev)
