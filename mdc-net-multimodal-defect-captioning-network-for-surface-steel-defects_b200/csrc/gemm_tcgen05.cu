@@ -27,12 +27,13 @@ constexpr int NUM_THREADS = 320;      // warp0 TMA, warp1 MMA, warps 2-9 epilogu
 constexpr int EPI_THREADS = 256;
 
 template <int BN> struct Cfg {
-  static constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int kStages = (BN == 256) ? 3 : (BN == 128 ? 4 : 6);
   static constexpr int kABytes = BLOCK_M * BLOCK_K * 2;
   static constexpr int kBBytes = BN * BLOCK_K * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kTmemCols = (2 * BN <= 32) ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + 4 * BN * 4 /*bias+gamma x2 stages*/;
+  static constexpr int kStageOutBytes = 8 * 2 * 4096;   // per epilogue warp: two 32-row x 128-byte staging tiles for the TMA stores
+  static constexpr int kSmemBytes = kStages * kStageBytes + kStageOutBytes + 1024 /*align slack*/ + 256 /*barriers*/ + 4 * BN * 4 /*bias+gamma x2 stages*/;
 };
 
 // ---- PTX wrappers --------------------------------------------------------------------------------
@@ -71,6 +72,20 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint32_t bar
   asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
 }
+// epilogue: shared -> global tile store / reduce-add through the TMA unit (coalesced, OOB rows and columns clipped)
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(src), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(src), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ uint32_t pack2_bf16(float a, float b) { __nv_bfloat162 h = __floats2bfloat162_rn(a, b); return *reinterpret_cast<uint32_t*>(&h); }
 __device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
@@ -110,31 +125,48 @@ struct EpiArgs {
   void* D; int64_t ldd; const float* bias; const float* aux0; int period; int epilogue;
 };
 
-// branch-free erf (Abramowitz-Stegun 7.1.26, |err| <= 1.5e-7 -- far below bf16 output rounding)
-__device__ __forceinline__ float gelu_fast(float x) {
-  const float z = fabsf(x) * 0.70710678118654752440f;
-  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
-  float p = fmaf(1.061405429f, t, -1.453152027f);
-  p = fmaf(p, t, 1.421413741f); p = fmaf(p, t, -0.284496736f); p = fmaf(p, t, 0.254829592f);
-  const float e = 1.0f - p * t * __expf(-z * z);          // erf(|x|/sqrt2)
-  return 0.5f * x * (1.0f + copysignf(e, x));
+// packed fp32 pairs (sm_100 FFMA2 / FMUL2 / FADD2): the epilogue polynomial runs on two columns per instruction
+__device__ __forceinline__ uint64_t pk2(float a, float b) { uint64_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ void upk2(uint64_t v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) { uint64_t d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) { uint64_t d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
+// exact-erf GELU of two values, branch-free: erf(z) = 1 - 1/(1 + a1 z + ... + a6 z^6)^16 for z >= 0 (Abramowitz-Stegun 7.1.28,
+// |err| <= 3e-7 -- four orders below the bf16 rounding of the output), odd extension by copysign.  One MUFU per value (the
+// epilogue of mlp.fc1 is MUFU/issue bound, not tensor bound, with the two-MUFU + IEEE-reciprocal form it replaces).
+__device__ __forceinline__ void gelu2(float x0, float x1, float& y0, float& y1) {
+  const uint64_t z = pk2(fabsf(x0) * 0.70710678118654752440f, fabsf(x1) * 0.70710678118654752440f);
+  uint64_t p = fma2(z, pk2(0.0000430638f, 0.0000430638f), pk2(0.0002765672f, 0.0002765672f));
+  p = fma2(p, z, pk2(0.0001520143f, 0.0001520143f));
+  p = fma2(p, z, pk2(0.0092705272f, 0.0092705272f));
+  p = fma2(p, z, pk2(0.0422820123f, 0.0422820123f));
+  p = fma2(p, z, pk2(0.0705230784f, 0.0705230784f));
+  p = fma2(p, z, pk2(1.0f, 1.0f));
+  p = mul2(p, p); p = mul2(p, p); p = mul2(p, p); p = mul2(p, p);          // ^16 (overflow -> inf -> 1/inf = 0 -> erf = 1)
+  float p0, p1; upk2(p, p0, p1);
+  const float e0 = copysignf(1.0f - rcp_approx(p0), x0), e1 = copysignf(1.0f - rcp_approx(p1), x1);
+  const float h0 = 0.5f * x0, h1 = 0.5f * x1;
+  y0 = fmaf(h0, e0, h0); y1 = fmaf(h1, e1, h1);
 }
 
 template <int BN, int EPI>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, EpiArgs ep, int M, int N, int K) {
+gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_d,
+               EpiArgs ep, int M, int N, int K) {
   using C = Cfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + C::kStages * C::kABytes;
-  uint64_t* bars = (uint64_t*)(smem + C::kStages * C::kStageBytes);
+  uint8_t* smem_out = smem + C::kStages * C::kStageBytes;                 // 1024-aligned (stage sizes are multiples of 1024)
+  uint64_t* bars = (uint64_t*)(smem_out + C::kStageOutBytes);
   uint64_t* full = bars;                         // [kStages]
   uint64_t* empty = bars + C::kStages;           // [kStages]
   uint64_t* tmem_full = bars + 2 * C::kStages;   // [2]
   uint64_t* tmem_empty = tmem_full + 2;          // [2]
   uint32_t* tmem_ptr_smem = (uint32_t*)(tmem_empty + 2);
-  float* s_bias = (float*)(smem + C::kStages * C::kStageBytes + 256);   // [2][BN]
+  float* s_bias = (float*)(smem_out + C::kStageOutBytes + 256);          // [2][BN]
   float* s_gamma = s_bias + 2 * BN;                                      // [2][BN]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -145,6 +177,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   if (warp == 0 && elect_one()) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
+    if (EPI != MDC_EPI_PATCH) asm volatile("prefetch.tensormap [%0];" ::"l"(&map_d) : "memory");
     for (int i = 0; i < C::kStages; ++i) { mbar_init(smem_u32(&full[i]), 1); mbar_init(smem_u32(&empty[i]), 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&tmem_full[i]), 1); mbar_init(smem_u32(&tmem_empty[i]), EPI_THREADS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -202,6 +235,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     // ===== epilogue: warp w may only touch TMEM lanes [32*(w%4), +32); warps w and w+4 split the columns =====
     const int quad = warp & 3, half = (warp - 2) >> 2, et = threadIdx.x - 64;
     constexpr int HALF_COLS = BN / 2;
+    constexpr bool OUT_F32 = (EPI == MDC_EPI_LS_RESIDUAL);
+    // columns per staged chunk: one 32-row x 128-byte tile when the tile half is wide enough, else 32 columns
+    constexpr int CH = OUT_F32 ? 32 : (HALF_COLS >= 64 ? 64 : 32);
+    constexpr int ROWB = CH * (OUT_F32 ? 4 : 2);                 // bytes per staged row: 128 (SWIZZLE_128B) or 64 (SWIZZLE_64B)
+    const uint32_t stage_out = smem_u32(smem_out) + (warp - 2) * 8192;
+    int obuf = 0;
     int iter = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++iter) {
       const int as = iter & 1; const uint32_t aphase = (iter >> 1) & 1;
@@ -215,75 +254,95 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       asm volatile("bar.sync 1, 256;" ::: "memory");
       mbar_wait(smem_u32(&tmem_full[as]), aphase);
       tcgen05_fence_after();
-      const int row = m0 + quad * 32 + lane;
-      const bool row_ok = row < M;
+      const int row0 = m0 + quad * 32, row = row0 + lane;
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + as * BN + half * HALF_COLS;
-      int64_t orow = row; const float* posrow = nullptr;
-      if (EPI == MDC_EPI_PATCH) { int img = row / ep.period; orow = row + img + 1; posrow = ep.aux0 + (int64_t)(row - img * ep.period) * ep.ldd; }
       const float* sb = s_bias + as * BN + half * HALF_COLS;
       const float* sg = s_gamma + as * BN + half * HALF_COLS;
+      if constexpr (EPI == MDC_EPI_PATCH) {
+        // rows are re-mapped past each image's cls slot, so a 32-row box is not contiguous in the output: direct stores
+        const bool row_ok = row < M;
+        const int img = row / ep.period;
+        const int64_t orow = row + img + 1;
+        const float* posrow = ep.aux0 + (int64_t)(row - img * ep.period) * ep.ldd;
 #pragma unroll 1
-      for (int c0 = 0; c0 < HALF_COLS; c0 += 32) {
-        const int col0 = n0 + half * HALF_COLS + c0;
-        const bool any = row_ok && col0 < N;
-        const bool full32 = (col0 + 32 <= N);
-        float4 rz[8];
-        if (EPI == MDC_EPI_LS_RESIDUAL || EPI == MDC_EPI_PATCH) {   // issue the stream / pos reads BEFORE the TMEM read
-          const float* src = (EPI == MDC_EPI_LS_RESIDUAL) ? reinterpret_cast<const float*>(ep.D) + orow * ep.ldd + col0 : posrow + col0;
+        for (int c0 = 0; c0 < HALF_COLS; c0 += 32) {
+          const int col0 = n0 + half * HALF_COLS + c0;
+          const bool any = row_ok && col0 < N;
+          const bool full32 = (col0 + 32 <= N);
+          float4 rz[8];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) rz[j] = (any && full32) ? *reinterpret_cast<const float4*>(src + 4 * j) : make_float4(0, 0, 0, 0);
-        }
-        uint32_t v[32];
-        tmem_ld32(taddr + c0, v);
-        tmem_ld_wait();
-        if (any) {
-          if (EPI == MDC_EPI_LS_RESIDUAL || EPI == MDC_EPI_PATCH) {
+          for (int j = 0; j < 8; ++j) rz[j] = (any && full32) ? *reinterpret_cast<const float4*>(posrow + col0 + 4 * j) : make_float4(0, 0, 0, 0);
+          uint32_t v[32];
+          tmem_ld32(taddr + c0, v);
+          tmem_ld_wait();
+          if (any) {
             float* dst = reinterpret_cast<float*>(ep.D) + orow * ep.ldd + col0;
             if (full32) {
 #pragma unroll
               for (int j = 0; j < 8; ++j) {
                 const float4 b4 = *reinterpret_cast<const float4*>(sb + c0 + 4 * j);
                 float4 o;
-                if (EPI == MDC_EPI_LS_RESIDUAL) {
-                  const float4 g4 = *reinterpret_cast<const float4*>(sg + c0 + 4 * j);
-                  o.x = rz[j].x + g4.x * (__uint_as_float(v[4 * j]) + b4.x); o.y = rz[j].y + g4.y * (__uint_as_float(v[4 * j + 1]) + b4.y);
-                  o.z = rz[j].z + g4.z * (__uint_as_float(v[4 * j + 2]) + b4.z); o.w = rz[j].w + g4.w * (__uint_as_float(v[4 * j + 3]) + b4.w);
-                } else {
-                  o.x = __uint_as_float(v[4 * j]) + b4.x + rz[j].x; o.y = __uint_as_float(v[4 * j + 1]) + b4.y + rz[j].y;
-                  o.z = __uint_as_float(v[4 * j + 2]) + b4.z + rz[j].z; o.w = __uint_as_float(v[4 * j + 3]) + b4.w + rz[j].w;
-                }
+                o.x = __uint_as_float(v[4 * j]) + b4.x + rz[j].x; o.y = __uint_as_float(v[4 * j + 1]) + b4.y + rz[j].y;
+                o.z = __uint_as_float(v[4 * j + 2]) + b4.z + rz[j].z; o.w = __uint_as_float(v[4 * j + 3]) + b4.w + rz[j].w;
                 *reinterpret_cast<float4*>(dst + 4 * j) = o;
               }
             } else {
-              for (int jj = 0; jj < 32 && col0 + jj < N; ++jj) {
-                float a = __uint_as_float(v[jj]) + sb[c0 + jj];
-                if (EPI == MDC_EPI_LS_RESIDUAL) dst[jj] = dst[jj] + sg[c0 + jj] * a;
-                else dst[jj] = a + posrow[col0 + jj];
-              }
-            }
-          } else {
-            bf16* dst = reinterpret_cast<bf16*>(ep.D) + orow * ep.ldd + col0;
-#pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              float o[8];
-              const float4 b0 = *reinterpret_cast<const float4*>(sb + c0 + j), b1 = *reinterpret_cast<const float4*>(sb + c0 + j + 4);
-              const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-#pragma unroll
-              for (int jj = 0; jj < 8; ++jj) {
-                float a = __uint_as_float(v[j + jj]) + bb[jj];
-                if (EPI == MDC_EPI_BIAS_GELU) a = gelu_fast(a);
-                else if (EPI == MDC_EPI_BIAS_RELU) a = fmaxf(a, 0.f);
-                o[jj] = a;
-              }
-              if (full32 || col0 + j + 7 < N) store8(dst + j, o);
-              else for (int jj = 0; jj < 8 && col0 + j + jj < N; ++jj) dst[j + jj] = __float2bfloat16_rn(o[jj]);
+              for (int jj = 0; jj < 32 && col0 + jj < N; ++jj) dst[jj] = __uint_as_float(v[jj]) + sb[c0 + jj] + posrow[col0 + jj];
             }
           }
+        }
+      } else {
+        // TMEM -> registers -> epilogue math -> swizzled staging tile in shared memory -> one TMA store (bf16 outputs) or TMA
+        // reduce-add into the fp32 residual stream (LayerScale + residual: R += gamma * (acc + bias), added exactly once per
+        // element, so the result equals the read-modify-write) per 32-row x CH-column chunk.  No per-thread global access.
+#pragma unroll 1
+        for (int c0 = 0; c0 < HALF_COLS; c0 += CH) {
+          const int col0 = n0 + half * HALF_COLS + c0;
+          uint32_t v[CH];
+          tmem_ld32(taddr + c0, v);
+          if constexpr (CH == 64) tmem_ld32(taddr + c0 + 32, v + 32);
+          if (lane == 0) bulk_wait_read<1>();            // the store issued from this staging buffer two chunks ago has read it
+          __syncwarp();
+          tmem_ld_wait();
+          const uint32_t tile_s = stage_out + obuf * 4096;
+          const uint32_t row_s = tile_s + lane * ROWB;
+#pragma unroll
+          for (int j = 0; j < CH; j += 8) {               // 8 columns -> one 16-byte chunk (bf16) or two (fp32)
+            float o[8];
+            const float4 b0 = *reinterpret_cast<const float4*>(sb + c0 + j), b1 = *reinterpret_cast<const float4*>(sb + c0 + j + 4);
+            const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+            for (int jj = 0; jj < 8; jj += 2) {
+              float a0 = __uint_as_float(v[j + jj]) + bb[jj], a1 = __uint_as_float(v[j + jj + 1]) + bb[jj + 1];
+              if (EPI == MDC_EPI_BIAS_GELU) gelu2(a0, a1, a0, a1);
+              else if (EPI == MDC_EPI_BIAS_RELU) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); }
+              o[jj] = a0; o[jj + 1] = a1;
+            }
+            if constexpr (OUT_F32) {
+              const float4 g0 = *reinterpret_cast<const float4*>(sg + c0 + j), g1 = *reinterpret_cast<const float4*>(sg + c0 + j + 4);
+              const int c = j >> 2;                        // 16-byte chunk index within the 128-byte row
+              sts128(row_s + (((c) ^ (lane & 7)) << 4), __float_as_uint(o[0] * g0.x), __float_as_uint(o[1] * g0.y), __float_as_uint(o[2] * g0.z), __float_as_uint(o[3] * g0.w));
+              sts128(row_s + (((c + 1) ^ (lane & 7)) << 4), __float_as_uint(o[4] * g1.x), __float_as_uint(o[5] * g1.y), __float_as_uint(o[6] * g1.z), __float_as_uint(o[7] * g1.w));
+            } else {
+              const int c = j >> 3;
+              const int sw = (ROWB == 128) ? (lane & 7) : ((lane >> 1) & 3);
+              sts128(row_s + ((c ^ sw) << 4), pack2_bf16(o[0], o[1]), pack2_bf16(o[2], o[3]), pack2_bf16(o[4], o[5]), pack2_bf16(o[6], o[7]));
+            }
+          }
+          fence_async_smem();
+          __syncwarp();
+          if (lane == 0 && row0 < M && col0 < N) {
+            if constexpr (OUT_F32) tma_reduce_add_2d(&map_d, tile_s, col0, row0);
+            else tma_store_2d(&map_d, tile_s, col0, row0);
+          }
+          if (lane == 0) bulk_commit();
+          obuf ^= 1;
         }
       }
       tcgen05_fence_before();
       mbar_arrive(smem_u32(&tmem_empty[as]));
     }
+    if (EPI != MDC_EPI_PATCH && lane == 0) bulk_wait_read<0>();   // staging tiles must outlive the last stores' reads
   }
   tcgen05_fence_before();
   __syncthreads();
@@ -334,6 +393,21 @@ int get_tmap(mdc_ctx* ctx, const void* ptr, int64_t rows, int64_t cols, int64_t 
   *out = m; return 0;
 }
 
+// tensor map of the output for the epilogue's TMA stores: box = 32 rows x `box_cols` columns (128 or 64 bytes per row)
+int make_out_tmap(mdc_ctx* ctx, const void* ptr, int64_t rows, int64_t cols, int64_t ld, bool f32, int box_cols, CUtensorMap* out) {
+  auto encode = (PFN_cuTensorMapEncodeTiled_v12000)ctx->encode_fn;
+  const int es = f32 ? 4 : 2;
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstride[1] = {(cuuint64_t)ld * es};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, 32u};
+  cuuint32_t estr[2] = {1, 1};
+  const CUtensorMapSwizzle sw = (box_cols * es == 128) ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+  CUresult r = encode(out, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstride, box, estr,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) MDC_FAIL(-3, "cuTensorMapEncodeTiled (output) failed (%d) ptr=%p rows=%lld cols=%lld ld=%lld", (int)r, ptr, (long long)rows, (long long)cols, (long long)ld);
+  return 0;
+}
+
 template <int BN, int EPI>
 int launch_bn_epi(mdc_ctx* ctx, const CUtensorMap& ma, const CUtensorMap& mw, const EpiArgs& ep, int M, int N, int K, cudaStream_t s) {
   using C = Cfg<BN>;
@@ -344,7 +418,14 @@ int launch_bn_epi(mdc_ctx* ctx, const CUtensorMap& ma, const CUtensorMap& mw, co
   }
   int tiles = ((M + BLOCK_M - 1) / BLOCK_M) * ((N + BN - 1) / BN);
   int grid = tiles < ctx->sm_count ? tiles : ctx->sm_count;
-  gemm_tc_kernel<BN, EPI><<<grid, NUM_THREADS, C::kSmemBytes, s>>>(ma, mw, ep, M, N, K);
+  CUtensorMap md;
+  memset(&md, 0, sizeof(md));
+  if (EPI != MDC_EPI_PATCH) {
+    const bool f32 = (EPI == MDC_EPI_LS_RESIDUAL);
+    const int box_cols = f32 ? 32 : (BN / 2 >= 64 ? 64 : 32);
+    MDC_TRY(make_out_tmap(ctx, ep.D, M, N, ep.ldd, f32, box_cols, &md));
+  }
+  gemm_tc_kernel<BN, EPI><<<grid, NUM_THREADS, C::kSmemBytes, s>>>(ma, mw, md, ep, M, N, K);
   MDC_LAUNCH_CHECK(ctx);
   return 0;
 }
