@@ -68,9 +68,8 @@ constexpr int OFF_QS = OFF_F2RECV + CS * GM * 32 * 4;      // [GM][32] f32 scale
 constexpr int OFF_KNEW = OFF_QS + GM * 32 * 4;             // [GM][32] f32 this step's key (bf16-rounded)
 constexpr int OFF_VNEW = OFF_KNEW + GM * 32 * 4;
 constexpr int OFF_YTMP = OFF_VNEW + GM * 32 * 4;           // [GM][32] f32 own slice of a projection before the push
-constexpr int OFF_QH = OFF_YTMP + GM * 32 * 4;             // [GM][32] bf16 hi part of the scaled query (MMA operand)
-constexpr int OFF_QL = OFF_QH + GM * 32 * 2;               // [GM][32] bf16 lo part
-constexpr int OFF_PART = OFF_QL + GM * 32 * 2;             // [GM][NPART][PSTR] f32 attention partials
+constexpr int OFF_QH = OFF_YTMP + GM * 32 * 4;             // [GM][32] bf16 scaled query (MMA operand)
+constexpr int OFF_PART = OFF_QH + GM * 32 * 2;             // [GM][NPART][PSTR] f32 attention partials
 constexpr int OFF_LRECV = OFF_PART + GM * NPART * PSTR * 4;   // [CS src][VSL] f32 logits of the image this CTA selects for
 constexpr int OFF_SEL = OFF_LRECV + CS * VSL * 4;          // select scratch: 320 + 512 floats
 constexpr int OFF_TOK = OFF_SEL + (CS * VSL + 512) * 4;    // [2][GM] int32 (double buffered by step parity)
@@ -116,6 +115,9 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 }
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_n(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
 // bounded wait: a protocol bug traps (reported as a launch failure) instead of hanging the GPU box
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
@@ -164,10 +166,6 @@ __device__ __forceinline__ uint4 lds128(uint32_t addr) {
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 h = __floats2bfloat162_rn(a, b); return *reinterpret_cast<uint32_t*>(&h);
 }
-__device__ __forceinline__ void split_store(bf16* hi, bf16* lo, int idx, float x) {      // attention queries: bf16 pair (K/V are bf16)
-  bf16 h = __float2bfloat16_rn(x);
-  hi[idx] = h; lo[idx] = __float2bfloat16_rn(x - __bfloat162float(h));
-}
 // projection operands: x = hi + lo as an fp16 pair (22 significant bits); |x| is clamped to the fp16 range first
 __device__ __forceinline__ float clamp_h(float x) { return fminf(fmaxf(x, -65504.f), 65504.f); }
 __device__ __forceinline__ void split_store(__half* hi, __half* lo, int idx, float x) {
@@ -207,26 +205,25 @@ __device__ __forceinline__ void mma_mtile(uint32_t wblk, int m0, uint32_t bh, ui
 
 // ---- attention of ONE query per image on the tensor cores ------------------------------------------------------
 // A key / value panel in shared memory holds key u at u*64 bytes, 16-byte chunk c stored at c ^ ((u >> 1) & 3)
-// (TMA SWIZZLE_64B).  The fp32 query is the M operand of S = q.K^T with row 0 = bf16 hi part and row 1 = lo part, so the
-// score of key 2q, 2q+1 of an 8-key tile lands in lanes (g = 0|1, q) -- exactly where the B fragment of P.V wants the
-// probabilities: the softmax runs in registers (group g = 0 keeps the hi part of p, g = 1 the lo part), nothing goes
-// through shared memory, and q.K / P.V are exact up to the bf16 K/V storage.  Scores are in log2 units (q is pre-scaled
-// by log2(e)/sqrt(hd)), so p = exp2(s - m).
+// (TMA SWIZZLE_64B).  The query (bf16, like the K/V it meets -- the precision of the caches; tools/error_budget_cpu.py: "q bf16",
+// "p bf16" move the logit error by < 5e-4) is row 0 of the M operand of S = q.K^T, so the score of keys 2q, 2q+1 of an 8-key
+// tile lands in lanes (g = 0, q) -- exactly where the B fragment of P.V wants column 0: the softmax runs in registers, nothing
+// goes through shared memory.  Lanes of the other row groups compute on zero rows; their values only reach output columns
+// that are never read.  Scores are in log2 units (q is pre-scaled by log2(e)/sqrt(hd)), so p = exp2(s - m).
 constexpr float LOG2E = 1.4426950408889634f;
 
 __device__ __forceinline__ void ldsm_x4_trans(uint32_t* r, uint32_t addr) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
 }
 
-// A fragments of q from its pre-split bf16 hi / lo rows (32 dims): aq[ks][h] covers dims 16*ks + 8*h + {2q, 2q+1} of MMA row g
-// (row 0 = hi, row 1 = lo, other rows 0)
-__device__ __forceinline__ void build_q_frag(const bf16* qh, const bf16* ql, uint32_t (&aq)[2][2]) {
+// A fragments of q from its bf16 row (32 dims): aq[ks][h] covers dims 16*ks + 8*h + {2q, 2q+1} of MMA row 0 (other rows 0)
+__device__ __forceinline__ void build_q_frag(const bf16* qh, uint32_t (&aq)[2][2]) {
   const int lane = threadIdx.x & 31, g = lane >> 2, q4 = lane & 3;
-  const bf16* src = (g == 0 ? qh : ql) + 2 * q4;
+  const bf16* src = qh + 2 * q4;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const uint32_t v = *reinterpret_cast<const uint32_t*>(src + (i >> 1) * 16 + (i & 1) * 8);
-    aq[i >> 1][i & 1] = g < 2 ? v : 0u;
+    aq[i >> 1][i & 1] = g == 0 ? v : 0u;
   }
 }
 
@@ -234,7 +231,7 @@ __device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.
 
 // Flash-decoding over key tiles t0, t0+tstep, ... < t1 (16 keys each) of one (K, V) panel pair, in chunks of MAXT tiles with
 // the usual running (max, sum, output) rescale.  On return m_run / l_run are warp-uniform; the un-normalised output of dims
-// mt*16 + {g, g+8} sits in lanes with q == 0 as o[mt][0]+o[mt][1] and o[mt][2]+o[mt][3].
+// mt*16 + {g, g+8} sits in lanes with q == 0 as o[mt][0] and o[mt][2].
 template <int MAXT>
 __device__ __forceinline__ void attn_tiles(uint32_t kp, uint32_t vp, const uint32_t (&aq)[2][2], int t0, int t1, int tstep, int nkeys,
                                            const uint8_t* padf, float& m_run, float& l_run, float (&o)[2][4]) {
@@ -255,9 +252,8 @@ __device__ __forceinline__ void attn_tiles(uint32_t kp, uint32_t vp, const uint3
           float c[4] = {0.f, 0.f, 0.f, 0.f}, d[4] = {0.f, 0.f, 0.f, 0.f};
           mma16816(c, a_k0, kb[0], kb[1]);
           mma16816(d, a_k1, kb[2], kb[3]);
-          const float e0 = c[0] + d[0], e1 = c[1] + d[1];
-          sc[i][2 * j] = e0 + __shfl_xor_sync(0xffffffffu, e0, 4);       // hi row + lo row
-          sc[i][2 * j + 1] = e1 + __shfl_xor_sync(0xffffffffu, e1, 4);
+          sc[i][2 * j] = c[0] + d[0];
+          sc[i][2 * j + 1] = c[1] + d[1];
         }
         if (padf != nullptr || k0 + 16 > nkeys) {                          // PAD-key bias / tail mask: rare, warp-uniform
 #pragma unroll
@@ -277,7 +273,7 @@ __device__ __forceinline__ void attn_tiles(uint32_t kp, uint32_t vp, const uint3
     for (int i = 0; i < MAXT; ++i) mx = fmaxf(fmaxf(mx, fmaxf(sc[i][0], sc[i][1])), fmaxf(sc[i][2], sc[i][3]));
     mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
     mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
-    mx = __shfl_sync(0xffffffffu, mx, 0);                                   // lanes of groups g >= 2 hold no scores
+    mx = __shfl_sync(0xffffffffu, mx, 0);                                   // only row group g = 0 holds scores
     const float corr = ex2_approx(m_run - mx);                              // first chunk: exp2(-inf) = 0
     l_run *= corr;
 #pragma unroll
@@ -292,11 +288,7 @@ __device__ __forceinline__ void attn_tiles(uint32_t kp, uint32_t vp, const uint3
         float p[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) { p[e] = ex2_approx(sc[i][e] - mx); ls += p[e]; }
-        // hi part for MMA column 0 (group g = 0), lo part for column 1 (g = 1), zero elsewhere -- branch-free
-        const uint32_t h0 = pack_bf16(p[0], p[1]), h1 = pack_bf16(p[2], p[3]);
-        const uint32_t l0 = pack_bf16(p[0] - __uint_as_float(h0 << 16), p[1] - __uint_as_float(h0 & 0xffff0000u));
-        const uint32_t l1 = pack_bf16(p[2] - __uint_as_float(h1 << 16), p[3] - __uint_as_float(h1 & 0xffff0000u));
-        const uint32_t b0 = g == 0 ? h0 : (g == 1 ? l0 : 0u), b1 = g == 0 ? h1 : (g == 1 ? l1 : 0u);
+        const uint32_t b0 = pack_bf16(p[0], p[1]), b1 = pack_bf16(p[2], p[3]);   // column 0 of the B operand lives in row group g = 0
         const int key = (c0 + i * tstep) * 16 + ((lane >> 4) & 1) * 8 + (lane & 7), sw = (key >> 1) & 3, dsel = (lane >> 3) & 1;
         const uint32_t rowaddr = vp + key * 64;
         uint32_t a0[4], a1[4];
@@ -325,6 +317,9 @@ __device__ __forceinline__ float attn_merge(const float* parts, int nparts) {
   return o / L;
 }
 
+// kTrace: developer build of the same kernel that stamps clock64() at phase boundaries (tools/decode_trace.py); the production
+// instantiation carries no trace instructions.
+template <bool kTrace>
 __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(NT, 1) decode_fused_kernel(const __grid_constant__ FusedParams P) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -339,7 +334,7 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(NT, 1) decode_fused
   float* xres = (float*)(smem + OFF_XRES); float* yrecv = (float*)(smem + OFF_YRECV); float* f2recv = (float*)(smem + OFF_F2RECV);
   float* qs = (float*)(smem + OFF_QS); float* knew = (float*)(smem + OFF_KNEW); float* vnew = (float*)(smem + OFF_VNEW);
   float* ytmp = (float*)(smem + OFF_YTMP); float* part = (float*)(smem + OFF_PART);
-  bf16* qh = (bf16*)(smem + OFF_QH); bf16* ql = (bf16*)(smem + OFF_QL);
+  bf16* qh = (bf16*)(smem + OFF_QH);
   float* lrecv = (float*)(smem + OFF_LRECV); float* selbuf = (float*)(smem + OFF_SEL);
   int* tokbuf = (int*)(smem + OFF_TOK); int* pages = (int*)(smem + OFF_PAGES); uint8_t* padflag = smem + OFF_PADF;
   int* haspad = (int*)(smem + OFF_HASPAD);
@@ -391,9 +386,9 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(NT, 1) decode_fused
       // =================================== PRODUCER WARP ===================================================
       long long prod_wait = 0;
       auto acquire = [&]() -> uint32_t {           // wait until the consumers released the slot
-        const long long c0 = P.trace ? clock64() : 0;
+        const long long c0 = kTrace ? clock64() : 0;
         mbar_wait(bar(BAR_EMPTY + slot), phase ^ 1);
-        if (P.trace) prod_wait += clock64() - c0;
+        if (kTrace) prod_wait += clock64() - c0;
         return sbase + OFF_RING + slot * STAGE_BYTES;
       };
       auto advance = [&]() { if (++slot == NS) { slot = 0; phase ^= 1; } };
@@ -471,29 +466,32 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(NT, 1) decode_fused
           advance();
         }
       }
-      if (P.trace && lane == 0 && blockIdx.x == 0) P.trace[202] = prod_wait;
+      if (kTrace && lane == 0 && blockIdx.x == 0) P.trace[202] = prod_wait;
     } else {
       // =================================== CONSUMER WARPS ==================================================
       long long cons_wait = 0, exch_wait = 0;
       auto stage_wait = [&]() -> uint32_t {
-        const long long c0 = P.trace ? clock64() : 0;
+        const long long c0 = kTrace ? clock64() : 0;
         mbar_wait(bar(BAR_FULL + slot), phase);
-        if (P.trace) cons_wait += clock64() - c0;
+        if (kTrace) cons_wait += clock64() - c0;
         return sbase + OFF_RING + slot * STAGE_BYTES;
       };
       auto xwait = [&](int which, uint32_t& ph) {    // wait for a push-style exchange
-        const long long c0 = P.trace ? clock64() : 0;
+        const long long c0 = kTrace ? clock64() : 0;
         mbar_wait(bar(which), ph); ph ^= 1;
-        if (P.trace) exch_wait += clock64() - c0;
+        if (kTrace) exch_wait += clock64() - c0;
       };
-      auto stage_release = [&]() {
+      // A stage is released by the warps that read it: the empty barrier counts 8 arrivals, a stage with k user warps gets
+      // 8/k from each of them (`weight`); the other warps neither wait for the stage nor arrive, they only advance the cursor.
+      auto stage_release = [&](uint32_t weight = 1) {
         __syncwarp();
-        if (lane == 0) mbar_arrive(bar(BAR_EMPTY + slot));
+        if (lane == 0) mbar_arrive_n(bar(BAR_EMPTY + slot), weight);
         if (++slot == NS) { slot = 0; phase ^= 1; }
       };
+      auto stage_skip = [&]() { if (++slot == NS) { slot = 0; phase ^= 1; } };
       const int fg = lane >> 2, fq = lane & 3;       // MMA fragment coordinates: row group, image pair
       int trace_n = 0;
-      auto TRACE = [&](int t_now) { if (P.trace && tid == 0 && blockIdx.x == 0 && t_now == P.trace_t) P.trace[trace_n++] = clock64(); };
+      auto TRACE = [&](int t_now) { if (kTrace && tid == 0 && blockIdx.x == 0 && t_now == P.trace_t) P.trace[trace_n++] = clock64(); };
       const int gi_t = tid >> 5, c_t = tid & 31;     // (image, channel) coordinates of the elementwise phases
       // push this CTA's [G][32] slice in ytmp into every peer's yrecv columns [32*rank, +32)
       auto push_y = [&](float v) {
@@ -557,15 +555,15 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(NT, 1) decode_fused
       auto proj32_push = [&](uint32_t bh, uint32_t bl, const float* bias) {
         float b0 = 0.f, b1 = 0.f;
         if (warp < 2) { b0 = __ldg(bias + rank * 32 + warp * 16 + fg); b1 = __ldg(bias + rank * 32 + warp * 16 + fg + 8); }
-        const uint32_t st = stage_wait();
         if (warp < 2) {
+          const uint32_t st = stage_wait();
           float acc[4];
           mma_mtile<32>(st, warp * 16, bh, bl, acc);
           const int f = warp * 16 + fg;
           ytmp[(2 * fq) * 32 + f] = acc[0] + b0; ytmp[(2 * fq + 1) * 32 + f] = acc[1] + b0;
           ytmp[(2 * fq) * 32 + f + 8] = acc[2] + b1; ytmp[(2 * fq + 1) * 32 + f + 8] = acc[3] + b1;
-        }
-        stage_release();
+          stage_release(4);
+        } else stage_skip();
         cbar();
         push_y(ytmp[gi_t * 32 + c_t]);
       };
@@ -595,26 +593,28 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(NT, 1) decode_fused
             float b0 = 0.f, b1 = 0.f;
             if (warp < 4) { const int r0 = (warp >> 1) * DM + rank * HD + (warp & 1) * 16 + fg; b0 = __ldg(bi + r0); b1 = __ldg(bi + r0 + 8); }
             else if (warp < 6) { const int r0 = 2 * DM + rank * HD + (warp & 1) * 16 + fg; b0 = __ldg(bi + r0); b1 = __ldg(bi + r0 + 8); }
-            uint32_t st = stage_wait();
             if (warp < 4) {
+              const uint32_t st = stage_wait();
               float acc[4];
               mma_mtile<32>(st + (warp >> 1) * 16384, (warp & 1) * 16, sbase + OFF_XH, sbase + OFF_XL, acc);
               const int f = (warp & 1) * 16 + fg;
               if (warp < 2) {      // q, pre-scaled
                 const float q0 = (acc[0] + b0) * scale, q1 = (acc[1] + b0) * scale, q2 = (acc[2] + b1) * scale, q3 = (acc[3] + b1) * scale;
-                qs[(2 * fq) * 32 + f] = q0; qs[(2 * fq + 1) * 32 + f] = q1; qs[(2 * fq) * 32 + f + 8] = q2; qs[(2 * fq + 1) * 32 + f + 8] = q3;
-                split_store(qh, ql, (2 * fq) * 32 + f, q0); split_store(qh, ql, (2 * fq + 1) * 32 + f, q1);
-                split_store(qh, ql, (2 * fq) * 32 + f + 8, q2); split_store(qh, ql, (2 * fq + 1) * 32 + f + 8, q3);
+                const bf16 r0 = __float2bfloat16_rn(q0), r1 = __float2bfloat16_rn(q1), r2 = __float2bfloat16_rn(q2), r3 = __float2bfloat16_rn(q3);
+                qh[(2 * fq) * 32 + f] = r0; qh[(2 * fq + 1) * 32 + f] = r1; qh[(2 * fq) * 32 + f + 8] = r2; qh[(2 * fq + 1) * 32 + f + 8] = r3;
+                // the step's own key meets the same bf16 query as the cached keys
+                qs[(2 * fq) * 32 + f] = __bfloat162float(r0); qs[(2 * fq + 1) * 32 + f] = __bfloat162float(r1);
+                qs[(2 * fq) * 32 + f + 8] = __bfloat162float(r2); qs[(2 * fq + 1) * 32 + f + 8] = __bfloat162float(r3);
               } else {             // k, rounded to the cache precision
                 knew[(2 * fq) * 32 + f] = __bfloat162float(__float2bfloat16_rn(acc[0] + b0));
                 knew[(2 * fq + 1) * 32 + f] = __bfloat162float(__float2bfloat16_rn(acc[1] + b0));
                 knew[(2 * fq) * 32 + f + 8] = __bfloat162float(__float2bfloat16_rn(acc[2] + b1));
                 knew[(2 * fq + 1) * 32 + f + 8] = __bfloat162float(__float2bfloat16_rn(acc[3] + b1));
               }
-            }
-            stage_release();
-            st = stage_wait();
+              stage_release(2);
+            } else stage_skip();
             if (warp == 4 || warp == 5) {
+              const uint32_t st = stage_wait();
               float acc[4];
               mma_mtile<32>(st, (warp & 1) * 16, sbase + OFF_XH, sbase + OFF_XL, acc);
               const int f = (warp & 1) * 16 + fg;
@@ -622,8 +622,8 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(NT, 1) decode_fused
               vnew[(2 * fq + 1) * 32 + f] = __bfloat162float(__float2bfloat16_rn(acc[1] + b0));
               vnew[(2 * fq) * 32 + f + 8] = __bfloat162float(__float2bfloat16_rn(acc[2] + b1));
               vnew[(2 * fq + 1) * 32 + f + 8] = __bfloat162float(__float2bfloat16_rn(acc[3] + b1));
-            }
-            stage_release();
+              stage_release(4);
+            } else stage_skip();
           }
           cbar();
           TRACE(t);   // 1: in-proj done
@@ -661,15 +661,15 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(NT, 1) decode_fused
                 if (warp < ntile) {
                   const uint32_t kp = st + gi * 2 * self_panel, vp = kp + self_panel;
                   uint32_t aq[2][2];
-                  build_q_frag(qh + g * 32, ql + g * 32, aq);
+                  build_q_frag(qh + g * 32, aq);
                   float m_run = -INFINITY, l_run = 0.f;
                   float o[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
                   attn_tiles<2>(kp, vp, aq, warp, ntile, 8, t, haspad[g] ? padflag + g * 256 : nullptr, m_run, l_run, o);
                   if (lane == 0) { pb[0] = m_run; pb[1] = l_run; }
                   if ((lane & 3) == 0) {
                     const int g8 = lane >> 2;
-                    pb[4 + g8] = o[0][0] + o[0][1]; pb[4 + g8 + 8] = o[0][2] + o[0][3];
-                    pb[4 + g8 + 16] = o[1][0] + o[1][1]; pb[4 + g8 + 24] = o[1][2] + o[1][3];
+                    pb[4 + g8] = o[0][0]; pb[4 + g8 + 8] = o[0][2];
+                    pb[4 + g8 + 16] = o[1][0]; pb[4 + g8 + 24] = o[1][2];
                   }
                 } else if (lane == 0) pb[1] = 0.f;
               }
@@ -692,15 +692,15 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(NT, 1) decode_fused
             const float* bc = P.b_ca[l];
             float b0 = 0.f, b1 = 0.f;
             if (warp < 2) { b0 = __ldg(bc + rank * 32 + warp * 16 + fg); b1 = __ldg(bc + rank * 32 + warp * 16 + fg + 8); }
-            const uint32_t st = stage_wait();
             if (warp < 2) {
+              const uint32_t st = stage_wait();
               float acc[4];
               mma_mtile<32>(st, warp * 16, sbase + OFF_XH, sbase + OFF_XL, acc);
               const int f = warp * 16 + fg;
-              split_store(qh, ql, (2 * fq) * 32 + f, (acc[0] + b0) * scale); split_store(qh, ql, (2 * fq + 1) * 32 + f, (acc[1] + b0) * scale);
-              split_store(qh, ql, (2 * fq) * 32 + f + 8, (acc[2] + b1) * scale); split_store(qh, ql, (2 * fq + 1) * 32 + f + 8, (acc[3] + b1) * scale);
-            }
-            stage_release();
+              qh[(2 * fq) * 32 + f] = __float2bfloat16_rn((acc[0] + b0) * scale); qh[(2 * fq + 1) * 32 + f] = __float2bfloat16_rn((acc[1] + b0) * scale);
+              qh[(2 * fq) * 32 + f + 8] = __float2bfloat16_rn((acc[2] + b1) * scale); qh[(2 * fq + 1) * 32 + f + 8] = __float2bfloat16_rn((acc[3] + b1) * scale);
+              stage_release(4);
+            } else stage_skip();
           }
           cbar();
           TRACE(t);   // 7: cross q
@@ -713,15 +713,15 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(NT, 1) decode_fused
                 float* pb = part + (g * NPART + warp) * PSTR;
                 if (warp < ntile) {
                   uint32_t aq[2][2];
-                  build_q_frag(qh + g * 32, ql + g * 32, aq);
+                  build_q_frag(qh + g * 32, aq);
                   float m_run = -INFINITY, l_run = 0.f;
                   float o[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
                   attn_tiles<2>(st, st + cross_panel, aq, warp, ntile, 8, S, nullptr, m_run, l_run, o);
                   if (lane == 0) { pb[0] = m_run; pb[1] = l_run; }
                   if ((lane & 3) == 0) {
                     const int g8 = lane >> 2;
-                    pb[4 + g8] = o[0][0] + o[0][1]; pb[4 + g8 + 8] = o[0][2] + o[0][3];
-                    pb[4 + g8 + 16] = o[1][0] + o[1][1]; pb[4 + g8 + 24] = o[1][2] + o[1][3];
+                    pb[4 + g8] = o[0][0]; pb[4 + g8 + 8] = o[0][2];
+                    pb[4 + g8 + 16] = o[1][0]; pb[4 + g8 + 24] = o[1][2];
                   }
                 } else if (lane == 0) pb[1] = 0.f;
               }
@@ -744,15 +744,15 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(NT, 1) decode_fused
             const bool mine = mt >= 0 && mt < 4;
             float b0 = 0.f, b1 = 0.f;
             if (mine) { const int h0 = rank * FS + s4 * 64 + mt * 16 + fg; b0 = __ldg(P.b_f1[l] + h0); b1 = __ldg(P.b_f1[l] + h0 + 8); }
-            const uint32_t st = stage_wait();
             if (mine) {
+              const uint32_t st = stage_wait();
               float acc[4];
               mma_mtile<64>(st, mt * 16, sbase + OFF_XH, sbase + OFF_XL, acc);
               const int h = s4 * 64 + mt * 16 + fg;
               split_store(fh, fl, (2 * fq) * XP + h, fmaxf(acc[0] + b0, 0.f)); split_store(fh, fl, (2 * fq + 1) * XP + h, fmaxf(acc[1] + b0, 0.f));
               split_store(fh, fl, (2 * fq) * XP + h + 8, fmaxf(acc[2] + b1, 0.f)); split_store(fh, fl, (2 * fq + 1) * XP + h + 8, fmaxf(acc[3] + b1, 0.f));
-            }
-            stage_release();
+              stage_release(2);
+            } else stage_skip();
           }
           cbar();
           TRACE(t);   // 12: FFN1
@@ -760,8 +760,8 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(NT, 1) decode_fused
           for (int s4 = 0; s4 < 4; ++s4) {
             const int mt = warp - (s4 & 1) * 4;
             const bool mine = mt >= 0 && mt < 4;
-            const uint32_t st = stage_wait();
             if (mine) {
+              const uint32_t st = stage_wait();
               float acc[4];
               mma_mtile<64>(st, mt * 16, sbase + OFF_FH, sbase + OFF_FL, acc);
               const int feat = s4 * 64 + mt * 16 + fg;                 // output feature of acc[0..1]; +8 for acc[2..3]
@@ -770,8 +770,8 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(NT, 1) decode_fused
               const uint32_t base = mapa(sbase + OFF_F2RECV + (rank * GM * 32 + (feat & 31)) * 4, peer);
               if (2 * fq < G) { st_async_b32(base + (2 * fq) * 128, __float_as_uint(acc[0]), rb); st_async_b32(base + (2 * fq) * 128 + 32, __float_as_uint(acc[2]), rb); }
               if (2 * fq + 1 < G) { st_async_b32(base + (2 * fq + 1) * 128, __float_as_uint(acc[1]), rb); st_async_b32(base + (2 * fq + 1) * 128 + 32, __float_as_uint(acc[3]), rb); }
-            }
-            stage_release();
+              stage_release(2);
+            } else stage_skip();
           }
           TRACE(t);   // 13: FFN2 issued
           {  // reduce the 8 partial slices of the own 32 columns, add bias, all-gather, LN3
@@ -800,8 +800,8 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(NT, 1) decode_fused
           const bool va = warp < 3 && row_a < VSL && r0 + row_a < P.vocab, vb = warp < 3 && row_b < VSL && r0 + row_b < P.vocab;
           if (va) b0 = __ldg(P.b_out + r0 + row_a);
           if (vb) b1 = __ldg(P.b_out + r0 + row_b);
-          const uint32_t st = stage_wait();
           if (warp < 3) {
+            const uint32_t st = stage_wait();
             float acc[4];
             mma_mtile<VSL>(st, warp * 16, sbase + OFF_XH, sbase + OFF_XL, acc);
 #pragma unroll
@@ -815,8 +815,8 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(NT, 1) decode_fused
                 if (need_select) st_async_b32(mapa(sbase + OFF_LRECV + (rank * VSL + row) * 4, img), __float_as_uint(lg), mapa(bar(BAR_LG), img));
               }
             }
-          }
-          stage_release();
+            stage_release(warp == 0 ? 4 : 2);
+          } else stage_skip();
         }
         TRACE(t);     // head done
         // ---- select: CTA `rank` owns image `rank` ------------------------------------------------------------------
@@ -849,7 +849,7 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(NT, 1) decode_fused
         }
         TRACE(t);     // tokens exchanged
       }
-      if (P.trace && tid == 0 && blockIdx.x == 0) { P.trace[200] = cons_wait; P.trace[201] = exch_wait; }
+      if (kTrace && tid == 0 && blockIdx.x == 0) { P.trace[200] = cons_wait; P.trace[201] = exch_wait; }
     }
   }
   // no CTA may exit while a peer can still push into its shared memory
@@ -926,12 +926,13 @@ int decode_cluster_launch(mdc_model* m, const mdc_decode_state* st, int t_begin,
   MDC_TRY(mdc_make_tmap_2d(ctx, st->kv_pool, (int64_t)st->n_pages * d.dec_layers * 2 * d.page_tokens, DM, DM, HD, d.page_tokens, 2, &P.m_pool));
   static int max_clusters = 0;
   if (!max_clusters) {
-    MDC_CUDA(cudaFuncSetAttribute(decode_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    MDC_CUDA(cudaFuncSetAttribute(decode_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    MDC_CUDA(cudaFuncSetAttribute(decode_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     cudaLaunchConfig_t q{}; q.gridDim = dim3(CS * 32); q.blockDim = dim3(NT); q.dynamicSmemBytes = SMEM_BYTES;
     cudaLaunchAttribute a[1]; a[0].id = cudaLaunchAttributeClusterDimension; a[0].val.clusterDim.x = CS; a[0].val.clusterDim.y = 1; a[0].val.clusterDim.z = 1;
     q.attrs = a; q.numAttrs = 1;
     int n = 0;
-    cudaError_t e = cudaOccupancyMaxActiveClusters(&n, decode_fused_kernel, &q);
+    cudaError_t e = cudaOccupancyMaxActiveClusters(&n, decode_fused_kernel<false>, &q);
     if (e != cudaSuccess || n < 1) { (void)cudaGetLastError(); n = ctx->sm_count / CS / 2; if (n < 1) n = 1; }
     max_clusters = n;
   }
@@ -946,7 +947,8 @@ int decode_cluster_launch(mdc_model* m, const mdc_decode_state* st, int t_begin,
   if (P.ips > GM) P.ips = GM;
   if (P.ips < 1) MDC_FAIL(-2, "decode_cluster: key capacity %d does not fit a stage", t_end);
   const int n_clusters = P.n_groups < max_clusters ? P.n_groups : max_clusters;
-  decode_fused_kernel<<<n_clusters * CS, NT, SMEM_BYTES, s>>>(P);
+  if (P.trace) decode_fused_kernel<true><<<n_clusters * CS, NT, SMEM_BYTES, s>>>(P);
+  else decode_fused_kernel<false><<<n_clusters * CS, NT, SMEM_BYTES, s>>>(P);
   MDC_LAUNCH_CHECK(ctx);
   return 0;
 }

@@ -5,7 +5,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from oracle import cases, mdc_oracle as O
 
 bf = lambda t: t.to(torch.bfloat16).float()
-FLAGS = dict(sq=False, sk=False, sv=False, so=False, cq=False, co=False, f1=False, f2=False, w_dec=False, w_head=False, w_ckv=False, mem=False, ckv=False, skv=False, act=False, w_enc=False, hid=False, w_fp16=False, own_exact=False)
+FLAGS = dict(sq=False, sk=False, sv=False, so=False, cq=False, co=False, f1=False, f2=False, w_dec=False, w_head=False, w_ckv=False, mem=False, ckv=False, skv=False, act=False, w_enc=False, hid=False, w_fp16=False, own_exact=False, q_bf=False, p_bf=False)
 
 def mha(xq, xkv, w, b, wo, bo, heads, bias=None, cross=False):
     d = xq.shape[-1]; hd = d // heads
@@ -28,6 +28,7 @@ def mha(xq, xkv, w, b, wo, bo, heads, bias=None, cross=False):
     if (cross and FLAGS["ckv"]) or (not cross and FLAGS["skv"]): k, v = bf(k), bf(v)
     B, Lq, _ = q.shape; Lk = k.shape[1]
     q = q.reshape(B, Lq, heads, hd).transpose(1, 2); k = k.reshape(B, Lk, heads, hd).transpose(1, 2); v = v.reshape(B, Lk, heads, hd).transpose(1, 2)
+    if FLAGS["q_bf"]: q = bf(q * (1.4426950408889634 / math.sqrt(hd))) / (1.4426950408889634 / math.sqrt(hd))
     s = (q @ k.transpose(-1, -2)) / math.sqrt(hd)
     if bias is not None: s = s + bias
     if FLAGS["own_exact"] and not cross:
@@ -38,6 +39,10 @@ def mha(xq, xkv, w, b, wo, bo, heads, bias=None, cross=False):
         p = torch.softmax(s, dim=-1)
         pd = p[:, :, idx, idx]
         o = p @ v + pd[..., None] * (ve - v)
+    elif FLAGS["p_bf"]:
+        m = s.max(-1, keepdim=True).values
+        p = torch.exp(s - m)
+        o = (bf(p) @ v) / p.sum(-1, keepdim=True)
     else:
         o = torch.softmax(s, dim=-1) @ v
     return a(o.transpose(1, 2).reshape(B, Lq, d)) @ woo.T + bo
@@ -108,6 +113,11 @@ with torch.no_grad():
         print("  FULL, head exact + own exact         ", run(**{**full, "w_head": False}, own_exact=True))
         print("  FULL, self kv exact                  ", run(**{**full, "skv": False}))
         print("  FULL, head exact, self kv exact      ", run(**{**full, "skv": False, "w_head": False}))
+        new = dict(w_dec=True, w_head=True, w_fp16=True, ckv=True, skv=True, mem=True)   # current GPU policy (w_ckv is bf16 but w_fp16 flips all: approx)
+        print("  NEW policy (fp16 loop weights)       ", run(**new))
+        print("  NEW + q bf16                         ", run(**new, q_bf=True))
+        print("  NEW + p bf16                         ", run(**new, p_bf=True))
+        print("  NEW + q bf16 + p bf16                ", run(**new, q_bf=True, p_bf=True))
         print("  all weights bf16        ", run(w_dec=True, w_head=True, w_ckv=True))
         print("  all weights + kv storage", run(w_dec=True, w_head=True, w_ckv=True, ckv=True, skv=True))
         print("  ... + mem bf16          ", run(w_dec=True, w_head=True, w_ckv=True, ckv=True, skv=True, mem=True))
