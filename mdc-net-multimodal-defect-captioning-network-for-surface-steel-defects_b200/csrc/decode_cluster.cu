@@ -15,9 +15,8 @@
 //   * projections run on the tensor cores with the roles swapped: the WEIGHT rows are the MMA M dimension
 //     (mma.sync m16n8k16, A fragments by ldmatrix from the swizzled TMA tile), the G <= 8 images are the N = 8
 //     dimension, so no MMA lane is wasted on padding.  The decode-loop weights are IEEE fp16 (mdc_dims.dec_loop_dtype: same
-//     bytes as bf16, 8x smaller rounding); activations are split hi+lo into two fp16 operands (x = hi + lo, two MMAs), so the
-//     16-bit WEIGHTS are the only rounding -- the numerics of the unfused kernels.  Attention keeps bf16 K/V (the caches) with
-//     bf16 hi+lo queries and probabilities.
+//     bytes as bf16, 8x smaller rounding) and so are the projection operands (activations rounded to fp16: 11 significant bits).
+//     Attention keeps bf16 K/V (the caches) with bf16 queries and probabilities.
 //   * activations (a few KB) are exchanged through DISTRIBUTED SHARED MEMORY, push style: the producer of a slice
 //     writes it into every peer with st.async (...mbarrier::complete_tx), the consumer waits on a local mbarrier
 //     for the expected byte count.  No cluster-wide barrier inside the loop.
@@ -55,13 +54,10 @@ constexpr int NPART = 9;           // attention partials per image: one per warp
 // ---- shared memory map (bytes from the 1024-aligned base) ---------------------------------------------------
 constexpr int OFF_RING = 0;
 constexpr int ACT_BYTES = GM * XP * 2;                     // 4224
-constexpr int OFF_XH = OFF_RING + NS * STAGE_BYTES;        // LN output, hi / lo
-constexpr int OFF_XL = OFF_XH + ACT_BYTES;
-constexpr int OFF_OH = OFF_XL + ACT_BYTES;                 // gathered attention output (written by peers)
-constexpr int OFF_OL = OFF_OH + ACT_BYTES;
-constexpr int OFF_FH = OFF_OL + ACT_BYTES;                 // own FFN hidden slice
-constexpr int OFF_FL = OFF_FH + ACT_BYTES;
-constexpr int OFF_XRES = OFF_FL + ACT_BYTES;               // [GM][DM] f32 residual stream
+constexpr int OFF_XH = OFF_RING + NS * STAGE_BYTES;        // LN output (fp16 projection operand)
+constexpr int OFF_OH = OFF_XH + ACT_BYTES;                 // gathered attention output (written by peers)
+constexpr int OFF_FH = OFF_OH + ACT_BYTES;                 // own FFN hidden slice
+constexpr int OFF_XRES = OFF_FH + ACT_BYTES;               // [GM][DM] f32 residual stream
 constexpr int OFF_YRECV = OFF_XRES + GM * DM * 4;          // [GM][DM] f32 all-gathered projection output (peers write)
 constexpr int OFF_F2RECV = OFF_YRECV + GM * DM * 4;        // [CS src][GM][32] f32 FFN2 partial sums (peers write)
 constexpr int OFF_QS = OFF_F2RECV + CS * GM * 32 * 4;      // [GM][32] f32 scaled query of the own head
@@ -166,41 +162,53 @@ __device__ __forceinline__ uint4 lds128(uint32_t addr) {
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 h = __floats2bfloat162_rn(a, b); return *reinterpret_cast<uint32_t*>(&h);
 }
-// projection operands: x = hi + lo as an fp16 pair (22 significant bits); |x| is clamped to the fp16 range first
+// projection operands are fp16 (11 significant bits, 8x finer than bf16: tools/error_budget_cpu.py "activations fp16" moves the
+// logit error by < 3e-4, where bf16 activations would cost 1.4e-2); |x| is clamped to the fp16 range first
 __device__ __forceinline__ float clamp_h(float x) { return fminf(fmaxf(x, -65504.f), 65504.f); }
-__device__ __forceinline__ void split_store(__half* hi, __half* lo, int idx, float x) {
-  x = clamp_h(x);
-  const __half h = __float2half_rn(x);
-  hi[idx] = h; lo[idx] = __float2half_rn(x - __half2float(h));
-}
+__device__ __forceinline__ void store_h(__half* dst, int idx, float x) { dst[idx] = __float2half_rn(clamp_h(x)); }
 __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
   __half2 h = __floats2half2_rn(a, b); return *reinterpret_cast<uint32_t*>(&h);
 }
 
 // One 16-row tile of a projection with the weights as the M operand:
 //   acc[0..3] = D[m0+g][img 2q], D[m0+g][2q+1], D[m0+g+8][2q], D[m0+g+8][2q+1]   (g = lane/4, q = lane%4)
-// wblk: shared address of the TMA row block [4 k-blocks][R rows][128 B] (SWIZZLE_128B), fp16 weights; bh/bl: hi/lo activations
-// [8 images][XP] fp16.  Four independent accumulator chains hide the HMMA latency.
+// wblk: shared address of the TMA row block [4 k-blocks][R rows][128 B] (SWIZZLE_128B), fp16 weights; bh: fp16 activations
+// [8 images][XP].  The fragment loads run two iterations ahead of the MMAs (the asm statements are volatile, so program order
+// IS issue order: without the explicit skew every iteration pays the full ldmatrix latency; the buffer of iteration i is
+// refilled for iteration i+2 as soon as its MMAs are issued); four accumulator chains.
 template <int R>
-__device__ __forceinline__ void mma_mtile(uint32_t wblk, int m0, uint32_t bh, uint32_t bl, float* acc) {
+__device__ __forceinline__ void mma_mtile(uint32_t wblk, int m0, uint32_t bh, float* acc) {
   const int lane = threadIdx.x & 31;
   const int row = m0 + (lane & 7) + ((lane >> 3) & 1) * 8, csel = lane >> 4, sw = lane & 7;
   const uint32_t a_base = wblk + row * 128;
-  const uint32_t boff = (lane & 7) * (XP * 2) + (lane >> 3) * 16;
-  float c0[4] = {0, 0, 0, 0}, c1[4] = {0, 0, 0, 0}, c2[4] = {0, 0, 0, 0}, c3[4] = {0, 0, 0, 0};
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {                 // two k-steps (32 k) per iteration
-    const int kb = i >> 1, ch = (i & 1) * 4;
-    uint32_t a0[4], a1[4], xh[4], xl[4];
-    ldsm_x4(a0, a_base + kb * (R * 128) + (((ch + csel) ^ sw) << 4));
-    ldsm_x4(a1, a_base + kb * (R * 128) + (((ch + 2 + csel) ^ sw) << 4));
-    ldsm_x4(xh, bh + boff + i * 64);
-    ldsm_x4(xl, bl + boff + i * 64);
-    mma16816_h(c0, a0, xh[0], xh[1]); mma16816_h(c1, a0, xl[0], xl[1]);
-    mma16816_h(c2, a1, xh[2], xh[3]); mma16816_h(c3, a1, xl[2], xl[3]);
+  const uint32_t b_base = bh + (lane & 7) * (XP * 2) + (lane >> 3) * 16;
+  float c[4][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}, {0, 0, 0, 0}, {0, 0, 0, 0}};
+  uint32_t a0[2][4], a1[2][4], xb[2][4];
+#define MDC_MTILE_LOAD(I)                                                                                      \
+  {                                                                                                            \
+    constexpr int i_ = (I), kb_ = i_ >> 1, ch_ = (i_ & 1) * 4, buf_ = i_ & 1;                                  \
+    ldsm_x4(a0[buf_], a_base + kb_ * (R * 128) + (((ch_ + csel) ^ sw) << 4));                                  \
+    ldsm_x4(a1[buf_], a_base + kb_ * (R * 128) + (((ch_ + 2 + csel) ^ sw) << 4));                              \
+    ldsm_x4(xb[buf_], b_base + i_ * 64);                                                                       \
   }
+#define MDC_MTILE_MMA(I)                                                                                       \
+  {                                                                                                            \
+    constexpr int i_ = (I), buf_ = i_ & 1, par_ = (i_ & 1) * 2;                                                \
+    mma16816_h(c[par_], a0[buf_], xb[buf_][0], xb[buf_][1]);                                                   \
+    mma16816_h(c[par_ + 1], a1[buf_], xb[buf_][2], xb[buf_][3]);                                               \
+  }
+  MDC_MTILE_LOAD(0) MDC_MTILE_LOAD(1)
+  MDC_MTILE_MMA(0) MDC_MTILE_LOAD(2)
+  MDC_MTILE_MMA(1) MDC_MTILE_LOAD(3)
+  MDC_MTILE_MMA(2) MDC_MTILE_LOAD(4)
+  MDC_MTILE_MMA(3) MDC_MTILE_LOAD(5)
+  MDC_MTILE_MMA(4) MDC_MTILE_LOAD(6)
+  MDC_MTILE_MMA(5) MDC_MTILE_LOAD(7)
+  MDC_MTILE_MMA(6) MDC_MTILE_MMA(7)
+#undef MDC_MTILE_LOAD
+#undef MDC_MTILE_MMA
 #pragma unroll
-  for (int j = 0; j < 4; ++j) acc[j] = (c0[j] + c2[j]) + (c1[j] + c3[j]);
+  for (int j = 0; j < 4; ++j) acc[j] = (c[0][j] + c[1][j]) + (c[2][j] + c[3][j]);
 }
 
 // ---- attention of ONE query per image on the tensor cores ------------------------------------------------------
@@ -329,8 +337,7 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(NT, 1) decode_fused
   uint32_t rank; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
   const int cid = blockIdx.x / CS, n_clusters = gridDim.x / CS;
 
-  __half* xh = (__half*)(smem + OFF_XH); __half* xl = (__half*)(smem + OFF_XL);      // projection operands: fp16 hi / lo
-  __half* fh = (__half*)(smem + OFF_FH); __half* fl = (__half*)(smem + OFF_FL);
+  __half* xh = (__half*)(smem + OFF_XH); __half* fh = (__half*)(smem + OFF_FH);      // projection operands (fp16)
   float* xres = (float*)(smem + OFF_XRES); float* yrecv = (float*)(smem + OFF_YRECV); float* f2recv = (float*)(smem + OFF_F2RECV);
   float* qs = (float*)(smem + OFF_QS); float* knew = (float*)(smem + OFF_KNEW); float* vnew = (float*)(smem + OFF_VNEW);
   float* ytmp = (float*)(smem + OFF_YTMP); float* part = (float*)(smem + OFF_PART);
@@ -348,7 +355,7 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(NT, 1) decode_fused
   }
   // zero the ring and the activation operands once: rows >= G of the operands and the rows behind a partial key tile
   // of a K/V panel are multiplied by zeros and must be finite
-  for (int i = tid; i < (NS * STAGE_BYTES + 6 * ACT_BYTES) / 16; i += NT) reinterpret_cast<uint4*>(smem + OFF_RING)[i] = make_uint4(0u, 0u, 0u, 0u);
+  for (int i = tid; i < (NS * STAGE_BYTES + 3 * ACT_BYTES) / 16; i += NT) reinterpret_cast<uint4*>(smem + OFF_RING)[i] = make_uint4(0u, 0u, 0u, 0u);
   __syncthreads();
   cluster_sync_all();
 
@@ -492,6 +499,9 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(NT, 1) decode_fused
       const int fg = lane >> 2, fq = lane & 3;       // MMA fragment coordinates: row group, image pair
       int trace_n = 0;
       auto TRACE = [&](int t_now) { if (kTrace && tid == 0 && blockIdx.x == 0 && t_now == P.trace_t) P.trace[trace_n++] = clock64(); };
+      auto FINE = [&](int l_now, int t_now, int idx) {   // trace build: fine stamps of layer 2 into trace[100 + idx] by lane 0 of the calling warp
+        if (kTrace && lane == 0 && blockIdx.x == 0 && t_now == P.trace_t && l_now == 2) P.trace[100 + idx] = clock64();
+      };
       const int gi_t = tid >> 5, c_t = tid & 31;     // (image, channel) coordinates of the elementwise phases
       // push this CTA's [G][32] slice in ytmp into every peer's yrecv columns [32*rank, +32)
       auto push_y = [&](float v) {
@@ -527,38 +537,36 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(NT, 1) decode_fused
             const int c = lane + 32 * j;
             const float xn = (v[j] - mean) * rstd * gw[j] + gb[j];
             xres[warp * DM + c] = xn;
-            split_store(xh, xl, warp * XP + c, xn);
+            store_h(xh, warp * XP + c, xn);
           }
         }
         cbar();
       };
-      // attention output of image `warp` (lane = channel) -> hi/lo pairs into every peer's oh/ol columns [32*rank, +32)
+      // attention output of image `warp` (lane = channel) -> fp16 pairs into every peer's oh columns [32*rank, +32); lane j < 16
+      // sends channels 2j, 2j+1 to peers 0..3, lane 16 + j the same pair to peers 4..7
       auto push_o = [&](float o) {
         const int j = lane & 15;
         const float v0 = __shfl_sync(0xffffffffu, o, 2 * j), v1 = __shfl_sync(0xffffffffu, o, 2 * j + 1);
         if (warp < G) {
-          const float w0 = clamp_h(v0), w1 = clamp_h(v1);
-          const __half h0 = __float2half_rn(w0), h1 = __float2half_rn(w1);
-          uint32_t val;
-          if (lane < 16) val = pack_h2(w0, w1);
-          else val = pack_h2(w0 - __half2float(h0), w1 - __half2float(h1));
-          const uint32_t off = sbase + (lane < 16 ? OFF_OH : OFF_OL) + (warp * XP + 32 * rank + 2 * j) * 2;
+          const uint32_t val = pack_h2(clamp_h(v0), clamp_h(v1));
+          const uint32_t off = sbase + OFF_OH + (warp * XP + 32 * rank + 2 * j) * 2;
+          const int p0 = (lane >> 4) * 4;
 #pragma unroll
-          for (int p = 0; p < CS; ++p) st_async_b32(mapa(off, p), val, mapa(bar(BAR_O), p));
+          for (int p = 0; p < 4; ++p) st_async_b32(mapa(off, p0 + p), val, mapa(bar(BAR_O), p0 + p));
         }
       };
       auto wait_o = [&]() {
-        if (tid == 0) mbar_expect_tx(bar(BAR_O), G * DM * 4);     // hi + lo: G * 256 * (2 + 2) bytes
+        if (tid == 0) mbar_expect_tx(bar(BAR_O), G * DM * 2);
         xwait(BAR_O, ph_o);
       };
-      // a 32-row projection of the gathered operand (bh,bl) -> ytmp (+bias) -> pushed to all peers
-      auto proj32_push = [&](uint32_t bh, uint32_t bl, const float* bias) {
+      // a 32-row projection of the gathered operand bh -> ytmp (+bias) -> pushed to all peers
+      auto proj32_push = [&](uint32_t bh, const float* bias) {
         float b0 = 0.f, b1 = 0.f;
         if (warp < 2) { b0 = __ldg(bias + rank * 32 + warp * 16 + fg); b1 = __ldg(bias + rank * 32 + warp * 16 + fg + 8); }
         if (warp < 2) {
           const uint32_t st = stage_wait();
           float acc[4];
-          mma_mtile<32>(st, warp * 16, bh, bl, acc);
+          mma_mtile<32>(st, warp * 16, bh, acc);
           const int f = warp * 16 + fg;
           ytmp[(2 * fq) * 32 + f] = acc[0] + b0; ytmp[(2 * fq + 1) * 32 + f] = acc[1] + b0;
           ytmp[(2 * fq) * 32 + f + 8] = acc[2] + b1; ytmp[(2 * fq + 1) * 32 + f + 8] = acc[3] + b1;
@@ -581,7 +589,7 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(NT, 1) decode_fused
             const int c = lane + 32 * j;
             const float x = __ldg(P.emb + (int64_t)tok * DM + c) + pz[j];
             xres[warp * DM + c] = x;
-            split_store(xh, xl, warp * XP + c, x);
+            store_h(xh, warp * XP + c, x);
           }
         }
         cbar();
@@ -596,7 +604,7 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(NT, 1) decode_fused
             if (warp < 4) {
               const uint32_t st = stage_wait();
               float acc[4];
-              mma_mtile<32>(st + (warp >> 1) * 16384, (warp & 1) * 16, sbase + OFF_XH, sbase + OFF_XL, acc);
+              mma_mtile<32>(st + (warp >> 1) * 16384, (warp & 1) * 16, sbase + OFF_XH, acc);
               const int f = (warp & 1) * 16 + fg;
               if (warp < 2) {      // q, pre-scaled
                 const float q0 = (acc[0] + b0) * scale, q1 = (acc[1] + b0) * scale, q2 = (acc[2] + b1) * scale, q3 = (acc[3] + b1) * scale;
@@ -616,7 +624,7 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(NT, 1) decode_fused
             if (warp == 4 || warp == 5) {
               const uint32_t st = stage_wait();
               float acc[4];
-              mma_mtile<32>(st, (warp & 1) * 16, sbase + OFF_XH, sbase + OFF_XL, acc);
+              mma_mtile<32>(st, (warp & 1) * 16, sbase + OFF_XH, acc);
               const int f = (warp & 1) * 16 + fg;
               vnew[(2 * fq) * 32 + f] = __bfloat162float(__float2bfloat16_rn(acc[0] + b0));
               vnew[(2 * fq + 1) * 32 + f] = __bfloat162float(__float2bfloat16_rn(acc[1] + b0));
@@ -682,7 +690,7 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(NT, 1) decode_fused
           wait_o();
           TRACE(t);   // 4: o gathered
           // ---- self out-proj slice -> all-gather -> LN1 ------------------------------------------------------------
-          proj32_push(sbase + OFF_OH, sbase + OFF_OL, P.b_so[l]);
+          proj32_push(sbase + OFF_OH, P.b_so[l]);
           TRACE(t);   // 5: out-proj pushed
           layer_norm(P.ln1w[l], P.ln1b[l]);
           TRACE(t);   // 6: LN1
@@ -695,7 +703,7 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(NT, 1) decode_fused
             if (warp < 2) {
               const uint32_t st = stage_wait();
               float acc[4];
-              mma_mtile<32>(st, warp * 16, sbase + OFF_XH, sbase + OFF_XL, acc);
+              mma_mtile<32>(st, warp * 16, sbase + OFF_XH, acc);
               const int f = warp * 16 + fg;
               qh[(2 * fq) * 32 + f] = __float2bfloat16_rn((acc[0] + b0) * scale); qh[(2 * fq + 1) * 32 + f] = __float2bfloat16_rn((acc[1] + b0) * scale);
               qh[(2 * fq) * 32 + f + 8] = __float2bfloat16_rn((acc[2] + b1) * scale); qh[(2 * fq + 1) * 32 + f + 8] = __float2bfloat16_rn((acc[3] + b1) * scale);
@@ -708,7 +716,9 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(NT, 1) decode_fused
           {
             const int ntile = (S + 15) >> 4;
             for (int g = 0; g < nC; ++g) {
+              if (warp == 0) FINE(l, t, 20 + g * 3);
               const uint32_t st = stage_wait();
+              if (warp == 0) FINE(l, t, 21 + g * 3);
               if (g < G) {
                 float* pb = part + (g * NPART + warp) * PSTR;
                 if (warp < ntile) {
@@ -726,6 +736,7 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(NT, 1) decode_fused
                 } else if (lane == 0) pb[1] = 0.f;
               }
               stage_release();
+              if (warp == 0) FINE(l, t, 22 + g * 3);
             }
           }
           cbar();
@@ -733,7 +744,7 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(NT, 1) decode_fused
           push_o(warp < G ? attn_merge(part + warp * NPART * PSTR, 8) : 0.f);
           wait_o();
           TRACE(t);   // 9: o gathered
-          proj32_push(sbase + OFF_OH, sbase + OFF_OL, P.b_co[l]);
+          proj32_push(sbase + OFF_OH, P.b_co[l]);
           TRACE(t);   // 10: cross out-proj pushed
           layer_norm(P.ln2w[l], P.ln2b[l]);
           TRACE(t);   // 11: LN2
@@ -745,13 +756,17 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(NT, 1) decode_fused
             float b0 = 0.f, b1 = 0.f;
             if (mine) { const int h0 = rank * FS + s4 * 64 + mt * 16 + fg; b0 = __ldg(P.b_f1[l] + h0); b1 = __ldg(P.b_f1[l] + h0 + 8); }
             if (mine) {
+              if (mt == 0) FINE(l, t, s4 * 4 + 0);
               const uint32_t st = stage_wait();
+              if (mt == 0) FINE(l, t, s4 * 4 + 1);
               float acc[4];
-              mma_mtile<64>(st, mt * 16, sbase + OFF_XH, sbase + OFF_XL, acc);
+              mma_mtile<64>(st, mt * 16, sbase + OFF_XH, acc);
+              if (mt == 0) FINE(l, t, s4 * 4 + 2);
               const int h = s4 * 64 + mt * 16 + fg;
-              split_store(fh, fl, (2 * fq) * XP + h, fmaxf(acc[0] + b0, 0.f)); split_store(fh, fl, (2 * fq + 1) * XP + h, fmaxf(acc[1] + b0, 0.f));
-              split_store(fh, fl, (2 * fq) * XP + h + 8, fmaxf(acc[2] + b1, 0.f)); split_store(fh, fl, (2 * fq + 1) * XP + h + 8, fmaxf(acc[3] + b1, 0.f));
+              store_h(fh, (2 * fq) * XP + h, fmaxf(acc[0] + b0, 0.f)); store_h(fh, (2 * fq + 1) * XP + h, fmaxf(acc[1] + b0, 0.f));
+              store_h(fh, (2 * fq) * XP + h + 8, fmaxf(acc[2] + b1, 0.f)); store_h(fh, (2 * fq + 1) * XP + h + 8, fmaxf(acc[3] + b1, 0.f));
               stage_release(2);
+              if (mt == 0) FINE(l, t, s4 * 4 + 3);
             } else stage_skip();
           }
           cbar();
@@ -763,7 +778,7 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(NT, 1) decode_fused
             if (mine) {
               const uint32_t st = stage_wait();
               float acc[4];
-              mma_mtile<64>(st, mt * 16, sbase + OFF_FH, sbase + OFF_FL, acc);
+              mma_mtile<64>(st, mt * 16, sbase + OFF_FH, acc);
               const int feat = s4 * 64 + mt * 16 + fg;                 // output feature of acc[0..1]; +8 for acc[2..3]
               const uint32_t peer = feat >> 5;                          // the whole 16-row tile lies inside one 32-column slice
               const uint32_t rb = mapa(bar(BAR_F2), peer);
@@ -803,7 +818,7 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(NT, 1) decode_fused
           if (warp < 3) {
             const uint32_t st = stage_wait();
             float acc[4];
-            mma_mtile<VSL>(st, warp * 16, sbase + OFF_XH, sbase + OFF_XL, acc);
+            mma_mtile<VSL>(st, warp * 16, sbase + OFF_XH, acc);
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               const int img = 2 * fq + (e & 1); const bool hi8 = e >= 2;
@@ -818,6 +833,8 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(NT, 1) decode_fused
             stage_release(warp == 0 ? 4 : 2);
           } else stage_skip();
         }
+        cbar();       // the next step's embedding overwrites the operand rows the head MMAs of warps 0-2 are reading (in teacher-forced
+                      // mode nothing else orders the two: no select, no token exchange)
         TRACE(t);     // head done
         // ---- select: CTA `rank` owns image `rank` ------------------------------------------------------------------
         if (need_select && (int)rank < G) {

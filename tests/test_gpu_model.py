@@ -184,27 +184,40 @@ def test_input_size_mismatch_raises_like_timm(model_p):
 @pytest.mark.parametrize("B,T", [(2, 24), (5, 40), (37, 30), (64, 99)])
 def test_cluster_decode_kernel_matches_generic_kernels(model_p, golden, B, T):
     """The persistent cluster-cooperative decode kernel (decode_cluster.cu) against the unfused kernels (decode.cu) on the
-    same bf16 weights: same tokens, logits equal up to summation order (both keep fp32 activations; bf16 weights/KV)."""
+    same weights and KV precision.  Teacher-forced along the generic kernels' own greedy trajectory, so that a near-tie
+    token flip cannot hide (or fake) a logit difference; then the free-running trajectories are compared."""
     import os
     model_p.set_precision("bf16")
     x = cases.images(B, seed=21).to(DEV)
     os.environ["MDC_DECODE_BACKEND"] = "generic"
     try:
-        tg, cg_, lg = model_p.generate_tokens(x, T, return_logits=True, use_graph=False)
+        tg, _ = model_p.generate_tokens(x, T, use_graph=False)
+        lg = model_p.predict(x, tg[:, :T].long())[:, 1:T + 1]
     finally:
         os.environ.pop("MDC_DECODE_BACKEND", None)
-    tc, cc, lc = model_p.generate_tokens(x, T, return_logits=True, use_graph=False)
-    # compare along the common trajectory: up to (and including) the first step where the tokens differ
-    same = (tg == tc).all(dim=0).cpu()
-    first_diff = int((~same).nonzero()[0]) if (~same).any() else T + 1
-    steps = min(T, first_diff)           # logits of step t depend on tokens 0..t
-    err = (lg[:, :steps] - lc[:, :steps]).abs().max().item()
-    print(f"cluster vs generic: B={B} T={T} first token difference at column {first_diff}, max|dlogit| over common prefix = {err:.2e}")
-    # both kernels carry the same bf16 weight / KV rounding but realise it in a different summation order; they sit equally
-    # far (~2e-2 worst case on this stress weight set) from the fp32 reference, and closer than that to each other
-    assert steps >= min(T, 5) and err < 1e-2
+    lc = model_p.predict(x, tg[:, :T].long())[:, 1:T + 1]
+    tc, _ = model_p.generate_tokens(x, T, use_graph=False)
+    err = (lg - lc).abs().max().item()
+    mean = (lg - lc).abs().mean().item()
     agree = (tg == tc).float().mean().item()
+    print(f"cluster vs generic: B={B} T={T} teacher-forced max|dlogit| = {err:.2e} mean = {mean:.2e}; free-running token agreement {agree:.3f}")
+    # the generic kernels keep fp32 activations / queries / probabilities, the fused kernel rounds projection operands to fp16 and
+    # attention queries / probabilities to bf16 (DESIGN.md 3.7): both sit ~1e-2 (worst case) from the fp32 reference
+    assert err < 1.5e-2 and mean < 1.5e-3
     assert agree > 0.5, agree
+
+
+def test_cluster_decode_is_run_to_run_deterministic(model_p):
+    """Race detector for the fused kernel: teacher-forced (no select / token exchange between steps -- the path where a missing
+    barrier between the head MMAs and the next step's operand write once showed up) and free-running, 6 runs each, bitwise."""
+    model_p.set_precision("bf16")
+    x = cases.images(64, seed=33).to(DEV)
+    toks, confs = model_p.generate_tokens(x, 99, use_graph=False)
+    ref = model_p.predict(x, toks[:, :99].long())
+    for _ in range(5):
+        assert torch.equal(model_p.predict(x, toks[:, :99].long()), ref)
+        t2, c2 = model_p.generate_tokens(x, 99, use_graph=False)
+        assert torch.equal(t2, toks) and torch.equal(c2, confs)
 
 
 def test_cluster_decode_topk_and_graph_replay(model_p):

@@ -16,7 +16,7 @@ torch.cuda.synchronize()
 tr = trace.cpu().tolist()
 names = ["in-proj", "append+own", "self-attn", "merge+gather o", "so proj+push", "LN1(wait y)", "cross q", "cross-attn", "merge+gather o", "co proj+push",
          "LN2(wait y)", "FFN1", "FFN2 issue", "f2 wait+reduce+push", "LN3(wait y)"]
-n = len([v for v in tr if v]); L = (n - 2) // 16
+n = len([v for v in tr[:100] if v]); L = (n - 2) // 16
 print(f"B={B} T={T} step={step}: {n} stamps, {L} layers")
 tot = [0] * 15
 for l in range(L):
@@ -30,6 +30,17 @@ for nm, v in zip(names, tot):
 print(f"  whole loop: consumer warp 0 blocked on ring stages {tr[200]} cyc, on exchanges {tr[201]} cyc; producer blocked on free slots {tr[202]} cyc")
 print(f"  layer total {sum(tot)/L:.0f} cyc; head {tr[L*16]-tr[L*16-1]} cyc; select+token exchange {tr[L*16+1]-tr[L*16]} cyc; step {tr[L*16+1]-tr[0]} cyc")
 
+f = tr[100:160]
+print("fine stamps, layer 2 (cycles relative to FFN1 stage-0 start of warp 0): per FFN1 stage [enter, data ready, mma done, released]")
+for s4 in range(4):
+    v = f[s4 * 4:s4 * 4 + 4]
+    if v[0]:
+        print(f"  FFN1 stage {s4} (warp {0 if s4 % 2 == 0 else 4}): enter +{v[0]-f[0]:6d}  wait {v[1]-v[0]:5d}  mma {v[2]-v[1]:5d}  epilogue+release {v[3]-v[2]:5d}")
+print("cross stages (warp 0): [enter, data ready, released]")
+for g in range(8):
+    v = f[20 + g * 3:23 + g * 3]
+    if v[0]:
+        print(f"  cross image {g}: enter +{v[0]-f[20]:6d}  wait {v[1]-v[0]:5d}  attend+release {v[2]-v[1]:5d}")
 import sys; sys.exit(0)
 for g in range(8):
     v = tr[100 + g * 8:100 + g * 8 + 6]

@@ -5,7 +5,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from oracle import cases, mdc_oracle as O
 
 bf = lambda t: t.to(torch.bfloat16).float()
-FLAGS = dict(sq=False, sk=False, sv=False, so=False, cq=False, co=False, f1=False, f2=False, w_dec=False, w_head=False, w_ckv=False, mem=False, ckv=False, skv=False, act=False, w_enc=False, hid=False, w_fp16=False, own_exact=False, q_bf=False, p_bf=False)
+FLAGS = dict(sq=False, sk=False, sv=False, so=False, cq=False, co=False, f1=False, f2=False, w_dec=False, w_head=False, w_ckv=False, mem=False, ckv=False, skv=False, act=False, w_enc=False, hid=False, w_fp16=False, own_exact=False, q_bf=False, p_bf=False, act16=False)
 
 def mha(xq, xkv, w, b, wo, bo, heads, bias=None, cross=False):
     d = xq.shape[-1]; hd = d // heads
@@ -21,7 +21,7 @@ def mha(xq, xkv, w, b, wo, bo, heads, bias=None, cross=False):
     else:
         if FLAGS["cq"]: wq = rw(wq)
         if FLAGS["co"]: woo = rw(woo)
-    a = bf if FLAGS["act"] else (lambda t: t)
+    a = bf if FLAGS["act"] else ((lambda t: t.half().float()) if FLAGS["act16"] else (lambda t: t))
     q = a(xq) @ wq.T + b[:d]
     k = a(xkv) @ wk.T + b[d:2*d]; v = a(xkv) @ wv.T + b[2*d:]
     k_ex, v_ex = k, v
@@ -52,7 +52,7 @@ def stack(sd, x, mem, tokens, cfg, prefix="decoder.decoder.layers.", eps=1e-5):
     causal = torch.full((L, L), float("-inf")).triu(1)
     bias = causal[None, None] + (tokens == cfg.pad_idx).float()[:, None, None, :]
     rw = (lambda t: t.half().float()) if FLAGS["w_fp16"] else bf
-    a = bf if FLAGS["act"] else (lambda t: t)
+    a = bf if FLAGS["act"] else ((lambda t: t.half().float()) if FLAGS["act16"] else (lambda t: t))
     if FLAGS["mem"]: mem = bf(mem)
     for i in range(O._num_dec_layers(sd, prefix)):
         g = lambda k: sd[f"{prefix}{i}.{k}"]
@@ -64,6 +64,7 @@ def stack(sd, x, mem, tokens, cfg, prefix="decoder.decoder.layers.", eps=1e-5):
         if FLAGS["f2"]: w2 = rw(w2)
         h = torch.relu(a(x) @ w1.T + g("linear1.bias"))
         if FLAGS["hid"] or FLAGS["act"]: h = bf(h)
+        if FLAGS["act16"]: h = h.half().float()
         x = O._ln(x + h @ w2.T + g("linear2.bias"), g("norm3.weight"), g("norm3.bias"), eps)
     return x
 
@@ -73,7 +74,7 @@ def logits_along(sd, enc_out, toks, cfg, n):
     y = stack(sd, x, mem, toks[:, :n], cfg)
     wo = sd["decoder.output.weight"]
     if FLAGS["w_head"]: wo = (wo.half().float() if FLAGS["w_fp16"] else bf(wo))
-    a = bf if FLAGS["act"] else (lambda t: t)
+    a = bf if FLAGS["act"] else ((lambda t: t.half().float()) if FLAGS["act16"] else (lambda t: t))
     return a(y) @ wo.T + sd["decoder.output.bias"]
 
 with torch.no_grad():
@@ -118,6 +119,7 @@ with torch.no_grad():
         print("  NEW + q bf16                         ", run(**new, q_bf=True))
         print("  NEW + p bf16                         ", run(**new, p_bf=True))
         print("  NEW + q bf16 + p bf16                ", run(**new, q_bf=True, p_bf=True))
+        print("  NEW + q,p bf16 + activations fp16    ", run(**new, q_bf=True, p_bf=True, act16=True))
         print("  all weights bf16        ", run(w_dec=True, w_head=True, w_ckv=True))
         print("  all weights + kv storage", run(w_dec=True, w_head=True, w_ckv=True, ckv=True, skv=True))
         print("  ... + mem bf16          ", run(w_dec=True, w_head=True, w_ckv=True, ckv=True, skv=True, mem=True))
