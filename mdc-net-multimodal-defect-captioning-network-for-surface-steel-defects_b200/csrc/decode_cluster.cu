@@ -312,16 +312,91 @@ __device__ __forceinline__ void attn_tiles(uint32_t kp, uint32_t vp, const uint3
   }
 }
 
-// merge the partial results (m, l, -, -, o[32]) of one image; lane = channel.  Parts with l == 0 are empty.
-__device__ __forceinline__ float attn_merge(const float* parts, int nparts) {
+// The same attention over key tiles tl, tl + tstep (at most two, 16 keys each) as ONE straight-line chunk: a tile past the end is
+// clamped onto tile `tl` and masked, so there is no control flow between the fragment loads and the MMAs and all four K fragments
+// and all four V fragments (which do not depend on the scores) are requested before the first MMA (volatile asm: program order
+// is issue order) -- the chunk pays the ldmatrix latency once.  Requires tl < ntile.  Outputs as attn_tiles.
+__device__ __forceinline__ void attn_chunk2(uint32_t kp, uint32_t vp, const uint32_t (&aq)[2][2], int tl, int tstep, int ntile, int nkeys,
+                                            const uint8_t* padf, float& m_out, float& l_out, float (&o)[2][4]) {
+  const int lane = threadIdx.x & 31, q4 = lane & 3;
+  const uint32_t a_k0[4] = {aq[0][0], 0u, aq[0][1], 0u}, a_k1[4] = {aq[1][0], 0u, aq[1][1], 0u};
+  const bool two = tl + tstep < ntile;
+  const int k0a = tl * 16, k0b = (two ? tl + tstep : tl) * 16;
+  uint32_t kb[2][2][4], va[2][2][4];
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int k0 = i ? k0b : k0a;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {              // 8-key n-tile j: one ldmatrix.x4 = the four dim chunks of keys k0+8j .. +7
+      const int key = k0 + 8 * j + (lane & 7);
+      ldsm_x4(kb[i][j], kp + key * 64 + (((lane >> 3) ^ ((key >> 1) & 3)) << 4));
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int key = (i ? k0b : k0a) + ((lane >> 4) & 1) * 8 + (lane & 7), sw = (key >> 1) & 3, dsel = (lane >> 3) & 1;
+    ldsm_x4_trans(va[i][0], vp + key * 64 + ((dsel ^ sw) << 4));
+    ldsm_x4_trans(va[i][1], vp + key * 64 + (((2 + dsel) ^ sw) << 4));
+  }
+  float sc[2][4];
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      float c[4] = {0.f, 0.f, 0.f, 0.f}, d[4] = {0.f, 0.f, 0.f, 0.f};
+      mma16816(c, a_k0, kb[i][j][0], kb[i][j][1]);
+      mma16816(d, a_k1, kb[i][j][2], kb[i][j][3]);
+      sc[i][2 * j] = c[0] + d[0];
+      sc[i][2 * j + 1] = c[1] + d[1];
+    }
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int key = (i ? k0b : k0a) + (e >> 1) * 8 + 2 * q4 + (e & 1);
+      if (padf != nullptr && padf[key]) sc[i][e] += LOG2E;               // float PAD-key bias +1.0 (Q7), in log2 units (padf: rare)
+      if (key >= nkeys || (i == 1 && !two)) sc[i][e] = -INFINITY;        // tail of the last tile / clamped duplicate tile
+    }
+  float mx = fmaxf(fmaxf(fmaxf(sc[0][0], sc[0][1]), fmaxf(sc[0][2], sc[0][3])), fmaxf(fmaxf(sc[1][0], sc[1][1]), fmaxf(sc[1][2], sc[1][3])));
+  mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+  mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+  mx = __shfl_sync(0xffffffffu, mx, 0);                                   // only row group g = 0 holds scores; key tl*16 is valid, so mx is finite
+  float ls = 0.f;
+  float o2[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};          // second tile: its own accumulator chain
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    float p[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { p[e] = ex2_approx(sc[i][e] - mx); ls += p[e]; }
+    const uint32_t b0 = pack_bf16(p[0], p[1]), b1 = pack_bf16(p[2], p[3]);   // column 0 of the B operand lives in row group g = 0
+    if (i == 0) { mma16816(o[0], va[0][0], b0, b1); mma16816(o[1], va[0][1], b0, b1); }
+    else { mma16816(o2[0], va[1][0], b0, b1); mma16816(o2[1], va[1][1], b0, b1); }
+  }
+  ls += __shfl_xor_sync(0xffffffffu, ls, 1);
+  ls += __shfl_xor_sync(0xffffffffu, ls, 2);
+  l_out = __shfl_sync(0xffffffffu, ls, 0);
+  m_out = mx;
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) o[mt][e] += o2[mt][e];
+}
+
+// merge the partial results (m, l, -, -, o[32]) of one image; lane = channel.  `mask`: bit p set for every slot p (< NPART)
+// written this phase; slots with l == 0 are empty.
+__device__ __forceinline__ float attn_merge(const float* parts, uint32_t mask) {
   const int lane = threadIdx.x & 31;
   float m = -INFINITY, l = 0.f;
-  if (lane < nparts) { m = parts[lane * PSTR]; l = parts[lane * PSTR + 1]; if (!(l > 0.f)) m = -INFINITY; }
+  if ((mask >> lane) & 1u) { m = parts[lane * PSTR]; l = parts[lane * PSTR + 1]; if (!(l > 0.f)) m = -INFINITY; }
   const float M = warp_max(m);
   const float w = (l > 0.f) ? exp2f(m - M) : 0.f;
   const float L = warp_sum(w * l);
   float o = 0.f;
-  for (int p = 0; p < nparts; ++p) o = fmaf(__shfl_sync(0xffffffffu, w, p), parts[p * PSTR + 4 + lane], o);
+#pragma unroll
+  for (int p = 0; p < NPART; ++p) {
+    const float wp = __shfl_sync(0xffffffffu, w, p);
+    if (wp != 0.f) o = fmaf(wp, parts[p * PSTR + 4 + lane], o);      // warp-uniform
+  }
   return o / L;
 }
 
@@ -649,8 +724,10 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(NT, 1) decode_fused
             *reinterpret_cast<uint4*>(dst) = o;
           }
           TRACE(t);   // 2: append
-          // ---- self-attention, head `rank`: keys [0,t) from the paged cache, key tiles interleaved over the 8 warps;
-          //      the step's own key (still in shared memory) is partial #8 ---------------------------------------------
+          // ---- self-attention, head `rank`: keys [0,t) from the paged cache.  A stage holds `ips` images; its 8 warps split evenly
+          //      over them (wpi = 8 / ips warps per image, a function of the key capacity only -- never of the batch), the warps of
+          //      an image interleave its key tiles (two per warp at most: wpi * 2 * 16 >= key capacity).  The step's own key (still
+          //      in shared memory) is partial #8 ------------------------------------------------------------------------------
           {
             const int ntile = (t + 15) >> 4;
             if (warp < G) {
@@ -660,19 +737,19 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(NT, 1) decode_fused
               if (lane == 0) { pb[0] = s_own; pb[1] = 1.0f; }
               pb[4 + lane] = vnew[warp * 32 + lane];
             }
+            const int wpi = 8 / P.ips, gi = warp / wpi, tl = warp - gi * wpi;
             for (int sg = 0; sg < nS; ++sg) {
-              const int g0 = sg * P.ips, gn = max(0, min(P.ips, G - g0));
+              const int g = sg * P.ips + gi;
               const uint32_t st = stage_wait();
-              for (int gi = 0; gi < gn; ++gi) {
-                const int g = g0 + gi;
-                float* pb = part + (g * NPART + warp) * PSTR;
-                if (warp < ntile) {
+              if (g < G) {
+                float* pb = part + (g * NPART + tl) * PSTR;
+                if (tl < ntile) {
                   const uint32_t kp = st + gi * 2 * self_panel, vp = kp + self_panel;
                   uint32_t aq[2][2];
                   build_q_frag(qh + g * 32, aq);
-                  float m_run = -INFINITY, l_run = 0.f;
+                  float m_run, l_run;
                   float o[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
-                  attn_tiles<2>(kp, vp, aq, warp, ntile, 8, t, haspad[g] ? padflag + g * 256 : nullptr, m_run, l_run, o);
+                  attn_chunk2(kp, vp, aq, tl, wpi, ntile, t, haspad[g] ? padflag + g * 256 : nullptr, m_run, l_run, o);
                   if (lane == 0) { pb[0] = m_run; pb[1] = l_run; }
                   if ((lane & 3) == 0) {
                     const int g8 = lane >> 2;
@@ -686,7 +763,7 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(NT, 1) decode_fused
           }
           cbar();
           TRACE(t);   // 3: self attention
-          push_o(warp < G ? attn_merge(part + warp * NPART * PSTR, NPART) : 0.f);
+          push_o(warp < G ? attn_merge(part + warp * NPART * PSTR, ((1u << (8 / P.ips)) - 1u) | (1u << 8)) : 0.f);
           wait_o();
           TRACE(t);   // 4: o gathered
           // ---- self out-proj slice -> all-gather -> LN1 ------------------------------------------------------------
@@ -724,9 +801,9 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(NT, 1) decode_fused
                 if (warp < ntile) {
                   uint32_t aq[2][2];
                   build_q_frag(qh + g * 32, aq);
-                  float m_run = -INFINITY, l_run = 0.f;
+                  float m_run, l_run;
                   float o[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
-                  attn_tiles<2>(st, st + cross_panel, aq, warp, ntile, 8, S, nullptr, m_run, l_run, o);
+                  attn_chunk2(st, st + cross_panel, aq, warp, 8, ntile, S, nullptr, m_run, l_run, o);
                   if (lane == 0) { pb[0] = m_run; pb[1] = l_run; }
                   if ((lane & 3) == 0) {
                     const int g8 = lane >> 2;
@@ -741,7 +818,7 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(NT, 1) decode_fused
           }
           cbar();
           TRACE(t);   // 8: cross attention partials
-          push_o(warp < G ? attn_merge(part + warp * NPART * PSTR, 8) : 0.f);
+          push_o(warp < G ? attn_merge(part + warp * NPART * PSTR, 0xffu) : 0.f);
           wait_o();
           TRACE(t);   // 9: o gathered
           proj32_push(sbase + OFF_OH, P.b_co[l]);
@@ -961,7 +1038,7 @@ int decode_cluster_launch(mdc_model* m, const mdc_decode_state* st, int t_begin,
   P.np_max = (t_end + d.page_tokens - 1) / d.page_tokens;
   if (P.np_max < 1) P.np_max = 1;
   P.ips = STAGE_BYTES / (2 * P.np_max * 1024);       // a stage holds the K and the V panel of `ips` images
-  if (P.ips > GM) P.ips = GM;
+  P.ips = P.ips >= 4 ? 4 : (P.ips >= 2 ? 2 : P.ips);    // {1, 2, 4}: 8 / ips warps per image, two key tiles per warp cover the capacity
   if (P.ips < 1) MDC_FAIL(-2, "decode_cluster: key capacity %d does not fit a stage", t_end);
   const int n_clusters = P.n_groups < max_clusters ? P.n_groups : max_clusters;
   if (P.trace) decode_fused_kernel<true><<<n_clusters * CS, NT, SMEM_BYTES, s>>>(P);
