@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define MDC_ABI_VERSION 2
+#define MDC_ABI_VERSION 3
 
 /* element types of activations / weights.  MDC_F16 (IEEE half) is only ever the type of the decode-loop weights, see
  * mdc_dims.dec_loop_dtype. */
@@ -233,6 +233,30 @@ int mdc_iou_batch(mdc_ctx* ctx, int mode, const float* pred, const float* gt, in
  * (NaN-free: entries of filtered rows/cols are written as 0 and flagged in valid u8 [B,N,M]). */
 int mdc_giou_loss(mdc_ctx* ctx, const float* pred, const float* gt, int B, int N, int M, float no_detection_penalty,
                   float* loss_per_image, float* giou_out, uint8_t* valid_out, void* stream);
+
+/* ---- token sequences -> labels / boxes / caption ids ---------------------------------------------------
+ * The reference's per-sequence Python scans (with .item() syncs) between generate() and the IoU functions, as one launch.
+ *   MDC_TOK_BBOXES  Tokenizer.decode_bboxes (data_processing.py:556-598): start after the first caption-end token (0 if none);
+ *                   at a label token read the next four as a box, keep it when all are in [0,coord_max] and x1>x0, y1>y0,
+ *                   advance 5 either way; stop at EOS; any other token advances 1; loop bound i < L-4.
+ *   MDC_TOK_DECODE  Tokenizer.decode (data_processing.py:317-391), batched: PADs removed, cut at the first EOS, needs both
+ *                   caption-start and caption-end; caption ids = the tokens between them; then fixed groups of five, kept when
+ *                   the label is in range and all four values are in [0,coord_max].
+ * De-quantisation: float32(v) / (num_bins-1) * width|height with the reference's two float32 roundings (:258-262, :551-553).
+ * tokens int32 [B, tokens_ld] (first L columns used).  Outputs (device, caller-owned): boxes f32 [B,max_boxes,4] xyxy, rows
+ * >= counts[b] zero (= pad_sequence's padding / the (1,4) zero box of an empty sequence); labels int32 [B,max_boxes] or NULL;
+ * counts int32 [B]; caption int32 [B,L] padded with `pad` and caption_len int32 [B] (MDC_TOK_DECODE; may be NULL;
+ * -1 = no caption-start/caption-end pair, for which the reference returns "" rather than a word list). */
+enum { MDC_TOK_BBOXES = 0, MDC_TOK_DECODE = 1 };
+typedef struct mdc_token_grammar {
+  int32_t pad, eos, caption_start, caption_end;   /* 302, 301, 303, 304 (data_processing.py:235-239) */
+  int32_t label_lo, label_hi;                     /* 258, 267 */
+  int32_t coord_max;                              /* 224: the reference's literal bound (bins are 0..223) */
+  int32_t num_bins, width, height;                /* 224, CFG.img_size, CFG.img_size */
+} mdc_token_grammar;
+int mdc_decode_tokens(mdc_ctx* ctx, int mode, const int32_t* tokens, int64_t tokens_ld, int B, int L,
+                      const mdc_token_grammar* grammar, int max_boxes, int32_t* labels_out, float* boxes_out,
+                      int32_t* counts_out, int32_t* caption_out, int32_t* caption_len_out, void* stream);
 
 #ifdef __cplusplus
 }

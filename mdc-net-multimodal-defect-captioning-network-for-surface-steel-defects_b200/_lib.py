@@ -35,6 +35,14 @@ class Dims(C.Structure):
         "has_axial", "page_tokens", "dec_loop_dtype")]
 
 
+class TokenGrammar(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("pad", "eos", "caption_start", "caption_end", "label_lo", "label_hi", "coord_max",
+                                         "num_bins", "width", "height")]
+
+
+TOK_BBOXES, TOK_DECODE = 0, 1
+
+
 class DecodeState(C.Structure):
     _fields_ = [
         ("B", C.c_int32),
@@ -84,6 +92,7 @@ SIGNATURES = {
     "mdc_axial_embed": (_I, [_P, _P, _I, _I, _I, _P, _I, _P, _P, _SZ, _P]),
     "mdc_iou_batch": (_I, [_P, _I, _P, _P, _I, _I, _I, _P, _P, _P]),
     "mdc_giou_loss": (_I, [_P, _P, _P, _I, _I, _I, _F, _P, _P, _P, _P]),
+    "mdc_decode_tokens": (_I, [_P, _I, _P, _L, _I, _I, C.POINTER(TokenGrammar), _I, _P, _P, _P, _P, _P, _P]),
 }
 
 _lib = None

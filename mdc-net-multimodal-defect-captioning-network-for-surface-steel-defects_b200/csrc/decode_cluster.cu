@@ -635,7 +635,7 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(NT, 1) decode_fused
         xwait(BAR_O, ph_o);
       };
       // a 32-row projection of the gathered operand bh -> ytmp (+bias) -> pushed to all peers
-      auto proj32_push = [&](uint32_t bh, const float* bias) {
+      auto proj32_push = [&](uint32_t bh, const float* bias, bool fence_appends) {
         float b0 = 0.f, b1 = 0.f;
         if (warp < 2) { b0 = __ldg(bias + rank * 32 + warp * 16 + fg); b1 = __ldg(bias + rank * 32 + warp * 16 + fg + 8); }
         if (warp < 2) {
@@ -646,7 +646,10 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(NT, 1) decode_fused
           ytmp[(2 * fq) * 32 + f] = acc[0] + b0; ytmp[(2 * fq + 1) * 32 + f] = acc[1] + b0;
           ytmp[(2 * fq) * 32 + f + 8] = acc[2] + b1; ytmp[(2 * fq + 1) * 32 + f + 8] = acc[3] + b1;
           stage_release(4);
-        } else stage_skip();
+        } else {
+          stage_skip();
+          if (fence_appends && tid >= 192 && tid - 192 < G * 8) asm volatile("fence.proxy.async;" ::: "memory");   // this layer's KV append
+        }
         cbar();
         push_y(ytmp[gi_t * 32 + c_t]);
       };
@@ -710,12 +713,12 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(NT, 1) decode_fused
           }
           cbar();
           TRACE(t);   // 1: in-proj done
-          // append k_t, v_t (bf16) to the paged cache: 16-byte stores, 4 per (image, k|v).  The proxy fence that orders them
-          // before the TMA reads of the page (one step later) is issued by the same threads one layer later, when the stores
-          // have long drained (a fence right behind the stores stalls ~1500 cycles).
-          if (tid < G * 8) {
-            asm volatile("fence.proxy.async;" ::: "memory");     // the PREVIOUS layer's append -> visible to later TMA reads of the page
-            const int g = tid >> 3, which = (tid >> 2) & 1, ch = tid & 3;
+          // append k_t, v_t (bf16) to the paged cache: 16-byte stores, 4 per (image, k|v), by warps 6-7.  The proxy fence that
+          // orders them before the TMA reads of the page (one step later) costs ~1200 cycles; the same threads issue it in the
+          // self out-proj phase below, where warps 2-7 have nothing else to do (proj32_push).
+          if (tid >= 192 && tid - 192 < G * 8) {
+            const int at = tid - 192;
+            const int g = at >> 3, which = (at >> 2) & 1, ch = at & 3;
             const float* src = (which ? vnew : knew) + g * 32 + ch * 8;
             const float4 a = *reinterpret_cast<const float4*>(src), b = *reinterpret_cast<const float4*>(src + 4);
             uint4 o; o.x = pack_bf16(a.x, a.y); o.y = pack_bf16(a.z, a.w); o.z = pack_bf16(b.x, b.y); o.w = pack_bf16(b.z, b.w);
@@ -767,7 +770,7 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(NT, 1) decode_fused
           wait_o();
           TRACE(t);   // 4: o gathered
           // ---- self out-proj slice -> all-gather -> LN1 ------------------------------------------------------------
-          proj32_push(sbase + OFF_OH, P.b_so[l]);
+          proj32_push(sbase + OFF_OH, P.b_so[l], true);
           TRACE(t);   // 5: out-proj pushed
           layer_norm(P.ln1w[l], P.ln1b[l]);
           TRACE(t);   // 6: LN1
@@ -821,7 +824,7 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(NT, 1) decode_fused
           push_o(warp < G ? attn_merge(part + warp * NPART * PSTR, 0xffu) : 0.f);
           wait_o();
           TRACE(t);   // 9: o gathered
-          proj32_push(sbase + OFF_OH, P.b_co[l]);
+          proj32_push(sbase + OFF_OH, P.b_co[l], false);
           TRACE(t);   // 10: cross out-proj pushed
           layer_norm(P.ln2w[l], P.ln2b[l]);
           TRACE(t);   // 11: LN2

@@ -38,17 +38,29 @@ def generate(model, x, tokenizer, max_len=50, top_k=0, top_p=1, uniforms=None):
 
 def postprocess(batch_preds, batch_confs, tokenizer):
     """inference_trail_after_good_map.py:50-76 (caption-aware twin of inference_p.py:93-115): first EOS,
-    the reference's `(EOS-1) % 5` sanity rule (Q12, kept verbatim), then tokenizer.decode per sample.
-    Host-side Python, as in the reference."""
+    the reference's `(EOS-1) % 5` sanity rule (Q12, kept verbatim), then Tokenizer.decode of every sample -- as one
+    batched GPU scan (csrc/tokens.cu) when the tokenizer is the B200 one."""
     EOS_idxs = (batch_preds == tokenizer.EOS_code).float().argmax(dim=-1)
     invalid_idxs = ((EOS_idxs - 1) % 5 != 0).nonzero().view(-1)
     EOS_idxs[invalid_idxs] = 0
     all_bboxes, all_labels, all_captions, all_confs = [], [], [], []
+    batched = None
+    if hasattr(tokenizer, "decode_batch"):
+        # ONE kernel launch + one device->host copy for the whole batch instead of a tokenizer.decode() call (with its own
+        # .item() reads) per sample: decode() drops PADs and cuts at the first EOS itself, so decoding the full row equals
+        # decoding batch_preds[i, :EOS_idx + 1]
+        labels_d, boxes_d, counts_d, cap_d, cap_len_d = tokenizer.decode_batch(batch_preds)
+        batched = (labels_d.cpu(), boxes_d.cpu(), counts_d.cpu().tolist(), cap_d.cpu(), cap_len_d.cpu().tolist())
     for i, EOS_idx in enumerate(EOS_idxs.tolist()):
         if EOS_idx == 0:
             all_bboxes.append(None); all_labels.append(None); all_captions.append(None); all_confs.append(None)
             continue
-        decoded = tokenizer.decode(batch_preds[i, :EOS_idx + 1])
+        if batched is not None:
+            lab, box, cnt, cap, cap_len = batched
+            n, c = cnt[i], cap_len[i]
+            decoded = (lab[i, :n].tolist(), box[i, :n].double().tolist(), "" if c < 0 else tokenizer.tokens_to_text(cap[i, :c].tolist()))
+        else:
+            decoded = tokenizer.decode(batch_preds[i, :EOS_idx + 1])
         if len(decoded) == 3:
             labels, bboxes, captions = decoded
         else:                                   # caption-less tokenizer API of inference_p.py:108

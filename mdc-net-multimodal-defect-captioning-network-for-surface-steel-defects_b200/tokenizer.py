@@ -28,48 +28,72 @@ class Tokenizer:
     def dequantize(self, x):
         return x.float() / (self.num_bins - 1)
 
-    def decode_bboxes(self, token_batch):
-        """data_processing.py:556-598 for a (B,L) batch: after the caption-end token, read groups of
-        label,x0,y0,x1,y1; keep groups with 0<=v<=num_bins, x1>x0, y1>y0; de-quantise v/(num_bins-1)*W;
-        zero-row pad to the longest.  Returns f32 (B,Nmax,4) (Nmax >= 1)."""
-        out = []
-        for seq in token_batch.tolist():
-            boxes = []
-            try:
-                i = seq.index(self.CAPTION_END) + 1
-            except ValueError:
-                i = 1
-            while i + 4 < len(seq):
-                lab, x0, y0, x1, y1 = seq[i:i + 5]
-                if lab in (self.EOS_code, self.PAD_code):
-                    break
-                if all(0 <= v <= self.num_bins for v in (x0, y0, x1, y1)) and x1 > x0 and y1 > y0:
-                    s = 1.0 / (self.num_bins - 1)
-                    boxes.append([x0 * s * self.width, y0 * s * self.height, x1 * s * self.width, y1 * s * self.height])
-                i += 5
-            out.append(boxes)
-        n = max(1, max(len(b) for b in out))
-        t = torch.zeros((len(out), n, 4), dtype=torch.float32)
-        for b, boxes in enumerate(out):
-            if boxes:
-                t[b, :len(boxes)] = torch.tensor(boxes, dtype=torch.float32)
-        return t
+    # -- decode side: one kernel launch per batch (csrc/tokens.cu), no per-token host synchronisation ------------------
+    def _grammar(self):
+        from . import _lib as L
+        g = L.TokenGrammar()
+        g.pad, g.eos, g.caption_start, g.caption_end = self.PAD_code, self.EOS_code, self.CAPTION_START, self.CAPTION_END
+        g.label_lo, g.label_hi = self.LABEL_BASE, self.LABEL_BASE + 9            # the reference's literal 258..267
+        g.coord_max = 224                                                         # data_processing.py:583 literal bound
+        g.num_bins, g.width, g.height = int(self.num_bins), int(self.width), int(self.height)
+        return g
+
+    def _run(self, mode, tokens, want_caption):
+        """tokens: int (B,L) tensor (moved to CFG.device when it lives on the host).  Returns device tensors
+        (boxes f32 (B,N,4), labels int32 (B,N), counts int32 (B,), caption int32 (B,L) | None, caption_len int32 (B,) | None)
+        with N = (L+4)//5 rows (an upper bound of what either grammar can emit), rows >= counts zero."""
+        import ctypes as C
+        from . import _lib as L
+        from .config import CFG
+        if tokens.dim() == 1:
+            tokens = tokens.unsqueeze(0)
+        dev = tokens.device if tokens.is_cuda else torch.device(CFG.device)
+        if dev.type != "cuda":
+            raise L.MdcError("token decoding runs on the GPU (csrc/tokens.cu); there is no CPU fallback")
+        t = tokens.to(dev, torch.int32).contiguous()
+        B, Ln = t.shape
+        N = max(1, (Ln + 4) // 5)
+        boxes = torch.empty((B, N, 4), dtype=torch.float32, device=dev)
+        labels = torch.empty((B, N), dtype=torch.int32, device=dev)
+        counts = torch.empty((B,), dtype=torch.int32, device=dev)
+        cap = torch.empty((B, Ln), dtype=torch.int32, device=dev) if want_caption else None
+        cap_len = torch.empty((B,), dtype=torch.int32, device=dev) if want_caption else None
+        g = self._grammar()
+        with torch.cuda.device(dev):
+            L.check(L.lib().mdc_decode_tokens(L.ctx(dev), mode, L.ptr(t), t.stride(0), B, Ln, C.byref(g), N, L.ptr(labels), L.ptr(boxes),
+                                              L.ptr(counts), L.ptr(cap), L.ptr(cap_len), L.stream_ptr()))
+        return boxes, labels, counts, cap, cap_len
+
+    def decode_bboxes(self, pred_seq):
+        """data_processing.py:556-598: (B,L) tokens -> f32 (B, Nmax, 4) on the device, zero-row padded to the longest
+        sequence of the batch (Nmax >= 1: an empty sequence is one zero box).  ONE launch + one scalar read (Nmax)."""
+        from . import _lib as L
+        boxes, _, counts, _, _ = self._run(L.TOK_BBOXES, torch.as_tensor(pred_seq), False)
+        n = max(1, int(counts.max().item()))
+        return boxes[:, :n].contiguous()
+
+    def decode_bboxes_padded(self, pred_seq):
+        """Sync-free form for pipelines (bench / parallel.pack_results): (boxes (B,N,4) with N = (L+4)//5, counts (B,))."""
+        from . import _lib as L
+        boxes, _, counts, _, _ = self._run(L.TOK_BBOXES, torch.as_tensor(pred_seq), False)
+        return boxes, counts
+
+    def decode_batch(self, tokens):
+        """Batched Tokenizer.decode (data_processing.py:317-391): device tensors (labels (B,N), boxes (B,N,4), counts (B,),
+        caption ids (B,L) PAD-padded, caption lengths (B,), -1 = no caption markers)."""
+        from . import _lib as L
+        boxes, labels, counts, cap, cap_len = self._run(L.TOK_DECODE, torch.as_tensor(tokens), True)
+        return labels, boxes, counts, cap, cap_len
+
+    def tokens_to_text(self, ids):
+        """data_processing.py:760-770 as `decode` uses it (a flat id list becomes one entry per token): list of words;
+        `vocab` = {id: word} or an object with .itos."""
+        table = getattr(self.vocab, "itos", self.vocab) or {}
+        return [table.get(int(t), "<UNK>") for t in ids]
 
     def decode(self, tokens):
-        """(labels, bboxes, caption words) of ONE sequence, data_processing.py:317-391 shape."""
-        seq = tokens.tolist()
-        caption = []
-        if self.CAPTION_START in seq and self.CAPTION_END in seq:
-            a, b = seq.index(self.CAPTION_START), seq.index(self.CAPTION_END)
-            ids = seq[a + 1:b]
-            caption = [self.vocab.get(t, "<unk>") if self.vocab else str(t) for t in ids]
-        boxes = self.decode_bboxes(torch.tensor([seq]))[0]
-        keep = boxes.abs().sum(-1) != 0
-        labels = []
-        try:
-            i = seq.index(self.CAPTION_END) + 1
-        except ValueError:
-            i = 1
-        while i + 4 < len(seq) and seq[i] not in (self.EOS_code, self.PAD_code):
-            labels.append(seq[i]); i += 5
-        return labels[:int(keep.sum())], boxes[keep], caption
+        """data_processing.py:317-391 for ONE sequence: (labels list, boxes list of [x0,y0,x1,y1], caption text)."""
+        labels, boxes, counts, cap, cap_len = self.decode_batch(torch.as_tensor(tokens).reshape(1, -1))
+        n, c = int(counts[0].item()), int(cap_len[0].item())
+        text = "" if c < 0 else self.tokens_to_text(cap[0, :c].tolist())
+        return labels[0, :n].tolist(), boxes[0, :n].double().tolist(), text

@@ -87,3 +87,42 @@ def iou_boxes(B=6, N=7, M=5, seed=11):
 def quiet():
     with contextlib.redirect_stdout(io.StringIO()):
         yield
+
+
+def token_sequences(seed=11):
+    """Token batches for the decode-side codec (Tokenizer.decode_bboxes / decode): well-formed sequences in the layout of
+    data_processing.py:264-290, damaged ones (missing markers, early EOS, PAD inside, invalid or truncated groups, the literal
+    bound 224, x1 <= x0), and pure noise as a random-init model emits it.  int64 (B, 100)."""
+    g = torch.Generator().manual_seed(seed)
+    L, rows = 100, []
+
+    def ri(lo, hi, n=None):
+        return torch.randint(lo, hi, (n,) if n else (), generator=g).tolist()
+
+    def pad(seq):
+        seq = seq[:L]
+        return seq + [302] * (L - len(seq))
+
+    for k in range(24):                                   # well-formed, 1..6 boxes, 0..14 caption words
+        seq = [300, 303] + [270 + w for w in ri(0, 13, int(ri(0, 15)))] + [304]
+        for _ in range(int(ri(1, 7))):
+            x0, y0 = ri(0, 200), ri(0, 200)
+            seq += [258 + ri(0, 10), x0, y0, x0 + ri(1, 24), y0 + ri(1, 24)]
+        rows.append(pad(seq + [301]))
+    rows.append(pad([300, 258, 10, 20, 30, 40, 301]))                         # no caption markers at all
+    rows.append(pad([300, 303, 270, 258, 10, 20, 30, 40, 301]))               # caption start without end
+    rows.append(pad([300, 304, 303, 258, 10, 20, 30, 40, 259, 1, 2, 3, 4, 301]))   # end before start
+    rows.append(pad([300, 303, 271, 304, 258, 10, 20, 10, 40, 259, 5, 6, 7, 8, 301]))       # x1 == x0 (bboxes drops, decode keeps)
+    rows.append(pad([300, 303, 271, 304, 258, 0, 0, 224, 224, 260, 1, 1, 225, 9, 301]))     # literal bound 224 / out of range 225
+    rows.append(pad([300, 303, 271, 304, 258, 10, 20, 30, 301, 259, 1, 2, 3, 4]))           # EOS inside a group
+    rows.append(pad([300, 303, 271, 304, 302, 258, 10, 20, 30, 40, 302, 259, 1, 2, 3, 4, 301]))   # PADs between groups
+    rows.append(pad([300, 303, 271, 304, 7, 8, 258, 10, 20, 30, 40, 301]))                  # stray tokens before the label
+    rows.append(pad([300, 303, 271, 304, 299, 10, 20, 30, 40, 258, 1, 2, 3, 4, 301]))       # non-label where a label belongs
+    rows.append([300, 303, 271, 304] + [258, 1, 2, 3, 4] * 19 + [258])                      # full length, truncated last group
+    rows.append([300, 303] + [270] * 10 + [304] + [259, 5, 6, 50, 60] * 17 + [301, 302])    # EOS near the end
+    rows.append(pad([301]))                                                                 # EOS first
+    rows.append([302] * L)                                                                   # all PAD
+    noise = torch.randint(0, 305, (19, L), generator=g)
+    noise[:, 0] = 300
+    noise[::2, 7] = 304; noise[::3, 3] = 303
+    return torch.cat([torch.tensor(rows, dtype=torch.int64), noise], dim=0)

@@ -1,5 +1,5 @@
 """TEST INFRASTRUCTURE ONLY -- generates tests/golden/*.pt by running the UNMODIFIED reference files
-(/root/reference/model.py, axial_model.py, iou_calcualtions.py, iou_bbox.py through oracle/shims) on the
+(/root/reference/model.py, axial_model.py, iou_calcualtions.py, iou_bbox.py, data_processing.py through oracle/shims) on the
 seeded cases of oracle/cases.py, and asserts on the way that the restatement oracle/mdc_oracle.py agrees.
 
 Run in the build container only (needs /root/reference):   python oracle/make_golden.py
@@ -53,11 +53,44 @@ def close(a, b, what, tol=TOL):
     assert d <= tol, what
 
 
+class _Vocab:
+    """Stand-in for data_processing.Vocabulary (needs spaCy): id -> word table only, which is all Tokenizer.decode reads."""
+    def __init__(self):
+        self.itos = {i: f"w{i}" for i in range(270, 299)}
+
+
+def tokens_case(R):
+    """The UNMODIFIED data_processing.Tokenizer (imported through the spacy / albumentations shims) on oracle/cases.token_sequences."""
+    import importlib
+    print("case tokens")
+    dp = importlib.import_module("data_processing")
+    tok = dp.Tokenizer(vocab=_Vocab(), num_classes=10, num_bins=224, width=224, height=224, max_len=100)
+    seqs = cases.token_sequences()
+    with cases.quiet():
+        bb = tok.decode_bboxes(seqs)
+        dec = [tok.decode(s) for s in seqs]
+    ob = O.decode_bboxes(seqs)
+    assert bb.shape == ob.shape and torch.equal(bb, ob), "decode_bboxes restatement"
+    labels, boxes, caps = [], [], []
+    for (lab, bx, cap), s in zip(dec, seqs):
+        olab, obx, ocap = O.decode_sequence(s)
+        rb = torch.tensor(bx, dtype=torch.float64).reshape(-1, 4)
+        assert lab == olab and torch.equal(rb.float(), obx) and torch.equal(rb, rb.float().double()), "decode restatement"
+        want_cap = "" if ocap is None else [f"w{t}" if 270 <= t < 299 else "<UNK>" for t in ocap]
+        assert cap == want_cap, (cap, want_cap)
+        labels.append(lab); boxes.append(rb.float()); caps.append(cap)
+    print(f"  {len(seqs)} sequences, {int((bb.abs().sum(-1) != 0).sum())} boxes from decode_bboxes, {sum(len(l) for l in labels)} from decode")
+    torch.save({"tokens": seqs, "decode_bboxes": bb, "decode_labels": labels, "decode_boxes": boxes, "decode_captions": caps},
+               os.path.join(OUT, "case_tokens.pt"))
+
+
 def main():
     assert ref_loader.available(), "needs /root/reference"
     os.makedirs(OUT, exist_ok=True)
     R = ref_loader.load()
     torch.set_num_threads(8)
+    if "--only-tokens" in sys.argv:
+        return tokens_case(R)
 
     # ---- config P, LayerScale gamma ~ U(0.5,1.5) ------------------------------------------------
     print("case P (gamma U(0.5,1.5))")
@@ -146,6 +179,7 @@ def main():
     assert torch.equal(gold["giou_2"], O.giou_pairwise(p[2], q[2]))
     assert abs(gl.item() - O.giou_loss_with_scores(p, q)[0].item()) < 1e-6
     torch.save(gold, os.path.join(OUT, "case_iou.pt"))
+    tokens_case(R)
     for f in sorted(os.listdir(OUT)):
         print(f"  {f}: {os.path.getsize(os.path.join(OUT, f)) / 1024:.0f} KiB")
 

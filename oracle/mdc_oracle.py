@@ -298,6 +298,80 @@ def generate(sd, image, cfg: OracleCfg, max_len=50, top_k=0, top_p=1.0, uniforms
 
 
 # ----------------------------------------------------------------------------------------
+# A.4b token codec, decode side    data_processing.py:317-391 (decode), :547-598 (decode_bboxes)
+# ----------------------------------------------------------------------------------------
+TOK_EOS, TOK_PAD, TOK_SOC, TOK_EOC, LABEL_LO, LABEL_HI = 301, 302, 303, 304, 258, 267
+
+
+def _dequant(v, num_bins, extent):
+    """data_processing.py:258-262 + :551-553: float32(v) / (num_bins-1) * extent, both steps in float32 (numpy weak scalars)."""
+    import numpy as np
+    return (np.asarray(v).astype("float32") / (num_bins - 1)) * extent
+
+
+def decode_bboxes(tokens, num_bins=224, width=224, height=224):
+    """data_processing.py:556-598 for an int (B,L) batch -> f32 (B, Nmax, 4), zero-row padded, Nmax >= 1.
+    Per sequence: start after the first caption-end token (0 if there is none); at a label token (258..267) read the next four
+    tokens as a box, keep it when all are in [0,224] and x1 > x0, y1 > y0, advance by 5 either way; stop at EOS; any other token
+    advances by 1.  The loop bound `i < len-4` is the reference's."""
+    import numpy as np
+    out = []
+    for seq in tokens.tolist():
+        n = len(seq)
+        start = seq.index(TOK_EOC) + 1 if TOK_EOC in seq else 0
+        boxes, i = [], start
+        while i < n - 4:
+            tok = seq[i]
+            if LABEL_LO <= tok <= LABEL_HI:
+                b = seq[i + 1:i + 5]
+                if all(0 <= v <= 224 for v in b) and b[2] > b[0] and b[3] > b[1]:
+                    boxes.append(b)
+                i += 5
+            elif tok == TOK_EOS:
+                break
+            else:
+                i += 1
+        if boxes:
+            a = np.asarray(boxes)
+            f = _dequant(a, num_bins, 1.0).astype("float32")
+            f[:, [0, 2]] = f[:, [0, 2]] * width
+            f[:, [1, 3]] = f[:, [1, 3]] * height
+            out.append(torch.tensor(f).float())
+        else:
+            out.append(torch.zeros(1, 4))
+    return torch.nn.utils.rnn.pad_sequence(out, batch_first=True, padding_value=0)
+
+
+def decode_sequence(tokens, num_bins=224, width=224, height=224):
+    """data_processing.py:317-391 for ONE int sequence -> (labels, boxes f32 (n,4), caption token ids).  PAD tokens are removed
+    first, then everything from the first EOS on; a caption needs both 303 and 304; boxes are read in fixed groups of five after
+    the caption-end token and kept when the label is 258..267 and all four values are in [0,224] (no ordering test here)."""
+    import numpy as np
+    seq = [t for t in tokens.tolist() if t != TOK_PAD]
+    if TOK_EOS in seq:
+        seq = seq[:seq.index(TOK_EOS)]
+    labels, boxes, caption = [], [], None          # caption None: no 303/304 pair (the reference returns "" then)
+    if TOK_SOC in seq and TOK_EOC in seq:
+        soc, eoc = seq.index(TOK_SOC), seq.index(TOK_EOC)
+        caption = seq[soc + 1:eoc]
+        rest = seq[eoc + 1:]
+        for i in range(0, len(rest), 5):
+            if i + 4 < len(rest):
+                lab, b = rest[i], rest[i + 1:i + 5]
+                if LABEL_LO <= lab <= LABEL_HI and all(0 <= v <= 224 for v in b):
+                    labels.append(lab); boxes.append(b)
+    if boxes:
+        a = np.asarray(boxes)
+        f = np.empty(a.shape, dtype="float32")
+        f[:, [0, 2]] = _dequant(a[:, [0, 2]], num_bins, width)
+        f[:, [1, 3]] = _dequant(a[:, [1, 3]], num_bins, height)
+        bx = torch.tensor(f)
+    else:
+        bx = torch.zeros(0, 4)
+    return labels, bx, caption
+
+
+# ----------------------------------------------------------------------------------------
 # A.5 box scores
 # ----------------------------------------------------------------------------------------
 def _pair(b1, b2):

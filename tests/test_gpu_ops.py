@@ -177,3 +177,60 @@ def test_bad_arguments_fail_loudly():
         G.gemm(A, A, torch.float32, L.EPI_BIAS)          # K % 4 != 0
     with pytest.raises(L.MdcError):
         G.strip_attention(torch.zeros((4, 3 * 8 * 24), device=DEV), 1, 4, 8, 24, 1.0)   # head_dim unsupported
+
+
+def test_token_decode_kernel_bit_exact_against_reference_golden(golden):
+    """csrc/tokens.cu through the host mirror against the unmodified reference Tokenizer's outputs (tests/golden/case_tokens.pt)."""
+    g = golden("case_tokens.pt")
+    tk = M.Tokenizer(num_bins=224, width=224, height=224, vocab={i: f"w{i}" for i in range(270, 299)})
+    toks = g["tokens"].to(DEV)
+    bb = tk.decode_bboxes(toks)
+    assert bb.is_cuda and bb.shape == g["decode_bboxes"].shape and torch.equal(bb.cpu(), g["decode_bboxes"])
+    labels, boxes, counts, cap, cap_len = tk.decode_batch(toks)
+    for i in range(toks.shape[0]):
+        n = int(counts[i])
+        assert labels[i, :n].tolist() == g["decode_labels"][i]
+        assert torch.equal(boxes[i, :n].cpu(), g["decode_boxes"][i])
+        assert boxes[i, n:].abs().sum() == 0
+        lab1, bx1, cap1 = tk.decode(toks[i])                     # the single-sequence entry point of the reference
+        assert lab1 == g["decode_labels"][i] and cap1 == g["decode_captions"][i]
+        assert torch.equal(torch.tensor(bx1).reshape(-1, 4).float(), g["decode_boxes"][i])
+
+
+def test_token_decode_kernel_full_size_against_oracle():
+    """Config 5 shape: B=256 sequences of 257 tokens (random grammar soup), both modes, bit-exact against the CPU oracle."""
+    gen = torch.Generator().manual_seed(5)
+    B, Ln = 256, 257
+    toks = torch.randint(0, 305, (B, Ln), generator=gen)
+    # make labels / markers frequent enough that boxes actually appear
+    pick = torch.rand((B, Ln), generator=gen)
+    toks = torch.where(pick < 0.15, torch.randint(258, 268, (B, Ln), generator=gen), toks)
+    toks = torch.where((pick >= 0.15) & (pick < 0.6), torch.randint(0, 226, (B, Ln), generator=gen), toks)
+    toks[:, 0] = 300; toks[::2, 5] = 303; toks[::2, 9] = 304; toks[::5, 200] = 301
+    tk = M.Tokenizer(num_bins=224, width=224, height=224)
+    bb = tk.decode_bboxes(toks.to(DEV)).cpu()
+    want = O.decode_bboxes(toks)
+    assert bb.shape == want.shape and torch.equal(bb, want)
+    labels, boxes, counts, cap, cap_len = tk.decode_batch(toks.to(DEV))
+    for i in range(0, B, 7):
+        olab, obx, ocap = O.decode_sequence(toks[i])
+        n = int(counts[i])
+        assert labels[i, :n].tolist() == olab and torch.equal(boxes[i, :n].cpu(), obx)
+        assert (int(cap_len[i]) == -1) if ocap is None else (cap[i, :int(cap_len[i])].tolist() == ocap)
+
+
+def test_postprocess_batched_equals_per_sample_decode(golden):
+    g = golden("case_tokens.pt")
+    tk = M.Tokenizer(num_bins=224, width=224, height=224, vocab={i: f"w{i}" for i in range(270, 299)})
+    toks = g["tokens"]
+    confs = [torch.full((toks.shape[0],), 0.5 + 0.01 * j) for j in range(25)]
+    bboxes, labels, caps, cf = M.postprocess(toks, confs, tk)
+    eos = (toks == 301).float().argmax(-1)
+    for i in range(toks.shape[0]):
+        e = int(eos[i])
+        if e == 0 or (e - 1) % 5 != 0:
+            assert bboxes[i] is None and labels[i] is None
+            continue
+        assert labels[i] == g["decode_labels"][i] and caps[i] == g["decode_captions"][i]
+        assert torch.equal(torch.tensor(bboxes[i]).reshape(-1, 4).float(), g["decode_boxes"][i])
+        assert len(cf[i]) == len(bboxes[i])

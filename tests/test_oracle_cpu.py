@@ -61,6 +61,17 @@ def test_iou_matches_reference_golden(golden):
     assert abs(g["kat_iou"].item() - 0.14285715) < 1e-7 and abs(g["kat_giou"].item() + 0.07936507) < 1e-7
 
 
+def test_token_decode_matches_reference_golden(golden):
+    """Tokenizer.decode_bboxes / decode restatements against the outputs of the unmodified data_processing.Tokenizer
+    (oracle/make_golden.py tokens_case): bit-exact boxes, same labels, same caption ids."""
+    g = golden("case_tokens.pt")
+    assert torch.equal(O.decode_bboxes(g["tokens"]), g["decode_bboxes"])
+    for s, lab, bx, cap in zip(g["tokens"], g["decode_labels"], g["decode_boxes"], g["decode_captions"]):
+        olab, obx, ocap = O.decode_sequence(s)
+        assert olab == lab and torch.equal(obx, bx)
+        assert cap == ("" if ocap is None else [f"w{t}" if 270 <= t < 299 else "<UNK>" for t in ocap])
+
+
 def test_axial_matches_reference_golden(golden):
     g = golden("case_axial.pt")
     pa = cases.build_product_model("P", seed=2, gamma_seed=7, axial=True)
