@@ -30,7 +30,16 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
 // byte offset of 16-byte chunk `c` (0..7) of row `r` in a swizzled [rows][64 bf16] panel
 __device__ __forceinline__ uint32_t swz(int r, int c) { return (uint32_t)(r * 128 + ((c ^ (r & 7)) << 4)); }
 
-__global__ void attn_tc_kernel(const bf16* __restrict__ qkv, int64_t ld, bf16* __restrict__ out, int64_t ldo, int S, int H, float scale_log2e) {
+__device__ __forceinline__ void cp_async16(uint32_t smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_dst), "l"(gsrc) : "memory");
+}
+
+// MAXT = 416 (197-token strips: 13 warps) is compiled for TWO CTAs per SM (<= 72 registers), so one CTA's K/V fetch overlaps the
+// other's MMAs -- at 80 registers a 416-thread CTA is 512 registers over half the file and the SM runs the two phases strictly
+// back to back.  MAXT = 1024 serves strips of up to 512 tokens.
+template <int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB)
+attn_tc_kernel(const bf16* __restrict__ qkv, int64_t ld, bf16* __restrict__ out, int64_t ldo, int S, int H, float scale_log2e) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int rows = ((S + 15) / 16) * 16;
   uint8_t* Ks = smem; uint8_t* Vs = smem + (size_t)rows * 128;
@@ -38,16 +47,20 @@ __global__ void attn_tc_kernel(const bf16* __restrict__ qkv, int64_t ld, bf16* _
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const bf16* base = qkv + (int64_t)strip * S * ld + head * HD;
   const int D = H * HD;
+  // K / V panels: 16-byte asynchronous copies straight into the swizzled rows (no register staging: every copy of the CTA is in
+  // flight at once, and the Q fragment loads below join them)
+  const uint32_t ks_u32 = (uint32_t)__cvta_generic_to_shared(Ks), vs_u32 = (uint32_t)__cvta_generic_to_shared(Vs);
   for (int i = tid; i < rows * 8; i += blockDim.x) {
     const int r = i >> 3, c = i & 7;
-    uint4 k = make_uint4(0, 0, 0, 0), v = k;
     if (r < S) {
-      k = *reinterpret_cast<const uint4*>(base + (int64_t)r * ld + D + c * 8);
-      v = *reinterpret_cast<const uint4*>(base + (int64_t)r * ld + 2 * D + c * 8);
+      cp_async16(ks_u32 + swz(r, c), base + (int64_t)r * ld + D + c * 8);
+      cp_async16(vs_u32 + swz(r, c), base + (int64_t)r * ld + 2 * D + c * 8);
+    } else {
+      *reinterpret_cast<uint4*>(Ks + swz(r, c)) = make_uint4(0, 0, 0, 0);
+      *reinterpret_cast<uint4*>(Vs + swz(r, c)) = make_uint4(0, 0, 0, 0);
     }
-    *reinterpret_cast<uint4*>(Ks + swz(r, c)) = k;
-    *reinterpret_cast<uint4*>(Vs + swz(r, c)) = v;
   }
+  asm volatile("cp.async.commit_group;" ::: "memory");
   // Q fragments straight from global memory (A operand layout of m16n8k16)
   const int q0 = warp * 16, r0 = q0 + (lane >> 2), r1 = r0 + 8;
   uint32_t qa[4][4];
@@ -59,9 +72,10 @@ __global__ void attn_tc_kernel(const bf16* __restrict__ qkv, int64_t ld, bf16* _
     qa[ks][2] = r0 < S ? *reinterpret_cast<const uint32_t*>(base + (int64_t)r0 * ld + k + 8) : 0u;
     qa[ks][3] = r1 < S ? *reinterpret_cast<const uint32_t*>(base + (int64_t)r1 * ld + k + 8) : 0u;
   }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncthreads();
   if (q0 >= S) return;
-  const uint32_t ks_base = (uint32_t)__cvta_generic_to_shared(Ks), vs_base = (uint32_t)__cvta_generic_to_shared(Vs);
+  const uint32_t ks_base = ks_u32, vs_base = vs_u32;
   float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
   float o[8][4];
 #pragma unroll
@@ -143,9 +157,14 @@ int attn_tc_launch(mdc_ctx* ctx, const void* qkv, int64_t ld, void* out, int64_t
   MDC_CHECK_ARG(((uintptr_t)qkv & 15) == 0 && ((uintptr_t)out & 3) == 0);
   const int rows = ((strip_len + 15) / 16) * 16;
   const size_t smem = (size_t)rows * 128 * 2;
-  MDC_ENSURE_SMEM(attn_tc_kernel, smem);
   dim3 grid(heads, n_strips), block(32 * (rows / 16));
-  attn_tc_kernel<<<grid, block, smem, s>>>((const bf16*)qkv, ld, (bf16*)out, ldo, strip_len, heads, scale * 1.4426950408889634f);
+  if (block.x <= 416) {
+    MDC_ENSURE_SMEM((attn_tc_kernel<416, 2>), smem);
+    attn_tc_kernel<416, 2><<<grid, block, smem, s>>>((const bf16*)qkv, ld, (bf16*)out, ldo, strip_len, heads, scale * 1.4426950408889634f);
+  } else {
+    MDC_ENSURE_SMEM((attn_tc_kernel<1024, 1>), smem);
+    attn_tc_kernel<1024, 1><<<grid, block, smem, s>>>((const bf16*)qkv, ld, (bf16*)out, ldo, strip_len, heads, scale * 1.4426950408889634f);
+  }
   MDC_LAUNCH_CHECK(ctx);
   return 0;
 }

@@ -60,6 +60,45 @@ __global__ void layernorm_kernel(const float* __restrict__ x, int64_t ldx, const
   }
 }
 
+// Fast path for cols = NV * 128 <= 1024: the row lives in registers (one global read), statistics in the same two-pass order
+// (mean, then centred variance), 8-byte packed stores for bf16 output.
+template <typename TO, int NV>
+__global__ void __launch_bounds__(256) layernorm_rows_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict__ w,
+                                                              const float* __restrict__ b, float eps, TO* __restrict__ out, int64_t ldo, int rows) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= rows) return;
+  const float* xr = x + (int64_t)warp * ldx;
+  float4 v[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) v[i] = *reinterpret_cast<const float4*>(xr + i * 128 + lane * 4);
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  const float mean = warp_sum(s) / (float)(NV * 128);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const float a0 = v[i].x - mean, a1 = v[i].y - mean, a2 = v[i].z - mean, a3 = v[i].w - mean;
+    q += (a0 * a0 + a1 * a1) + (a2 * a2 + a3 * a3);
+  }
+  const float rstd = 1.0f / sqrtf(warp_sum(q) / (float)(NV * 128) + eps);
+  TO* orow = out + (int64_t)warp * ldo;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = i * 128 + lane * 4;
+    const float4 g = __ldg(reinterpret_cast<const float4*>(w + c)), bb = __ldg(reinterpret_cast<const float4*>(b + c));
+    const float o0 = (v[i].x - mean) * rstd * g.x + bb.x, o1 = (v[i].y - mean) * rstd * g.y + bb.y;
+    const float o2 = (v[i].z - mean) * rstd * g.z + bb.z, o3 = (v[i].w - mean) * rstd * g.w + bb.w;
+    if constexpr (sizeof(TO) == 2) {
+      __nv_bfloat162 lo = __floats2bfloat162_rn(o0, o1), hi = __floats2bfloat162_rn(o2, o3);
+      uint2 pk; pk.x = *reinterpret_cast<uint32_t*>(&lo); pk.y = *reinterpret_cast<uint32_t*>(&hi);
+      *reinterpret_cast<uint2*>(orow + c) = pk;
+    } else {
+      *reinterpret_cast<float4*>(orow + c) = make_float4(o0, o1, o2, o3);
+    }
+  }
+}
+
 // ---- encoder tail: final LN (eps 1e-6), drop cls (model.py:23 features[:,1:]), AdaptiveAvgPool1d over
 // channels (model.py:19), + encoder_pos_embed (model.py:103-105).  Warp per patch token.
 template <typename TO>
@@ -183,6 +222,16 @@ extern "C" int mdc_layernorm(mdc_ctx* ctx, const float* x, int64_t ldx, const fl
   if (rows == 0) return 0;
   cudaStream_t s = (cudaStream_t)stream;
   int grid = (rows + 7) / 8;
+  const bool vec_ok = ldo % 4 == 0 && ((uintptr_t)out & 15) == 0 && ((uintptr_t)x & 15) == 0 && ((uintptr_t)w & 15) == 0 && ((uintptr_t)b & 15) == 0;
+#define MDC_LN_FAST(NV_)                                                                                                        \
+  if (vec_ok && cols == NV_ * 128) {                                                                                            \
+    if (out_dtype == MDC_F32) layernorm_rows_kernel<float, NV_><<<grid, 256, 0, s>>>(x, ldx, w, b, eps, (float*)out, ldo, rows);  \
+    else if (out_dtype == MDC_BF16) layernorm_rows_kernel<bf16, NV_><<<grid, 256, 0, s>>>(x, ldx, w, b, eps, (bf16*)out, ldo, rows); \
+    else MDC_FAIL(-2, "layernorm: bad out_dtype %d", out_dtype);                                                                \
+    MDC_LAUNCH_CHECK(ctx); return 0;                                                                                            \
+  }
+  MDC_LN_FAST(3) MDC_LN_FAST(4) MDC_LN_FAST(6) MDC_LN_FAST(8)      // deit3 small / medium / base / large widths
+#undef MDC_LN_FAST
   if (out_dtype == MDC_F32) layernorm_kernel<float><<<grid, 256, 0, s>>>(x, ldx, w, b, eps, (float*)out, ldo, rows, cols);
   else if (out_dtype == MDC_BF16) layernorm_kernel<bf16><<<grid, 256, 0, s>>>(x, ldx, w, b, eps, (bf16*)out, ldo, rows, cols);
   else MDC_FAIL(-2, "layernorm: bad out_dtype %d", out_dtype);
