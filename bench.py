@@ -119,7 +119,9 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     cfg = {"workload": f"MDC-Net config P (deit3_medium 224 + 6-layer dim-256 decoder, V=305), batch {B_PER_GPU}/GPU, "
                        f"{T_NEW} greedy tokens, synthetic 200x200 gray -> 3x224x224", "global_batch": B_PER_GPU * world,
-           "new_tokens": T_NEW, "parallelism": f"dp{world}", "l2": "256 MiB L2 flush between timed steps (untimed)"}
+           "new_tokens": T_NEW, "parallelism": f"dp{world}",
+           "pipeline": "batch pipeline depth 2: encoder of step i+1 overlaps the decode loop of step i (GenerationPipeline / generate_stream)",
+           "l2": "no flush inside the pipelined region: 4 rotating input batches (154 MB) and a per-step working set of ~330 MB both exceed the 126 MB L2"}
 
     if args.impl == "reference":
         if rank != 0:
@@ -144,8 +146,10 @@ def main():
     model = cases.build_product_model("P", seed=0, gamma_seed=5).to(dev).set_precision("bf16")
     tok = M.Tokenizer()
     B = B_PER_GPU
-    x_host = cases.images(B, seed=1234 + rank).pin_memory()
-    x_dev = x_host.to(dev)
+    NROT = 4                                         # rotating input batches: 4 x 38.5 MB > the 126 MB L2
+    xs_host = [cases.images(B, seed=1234 + 17 * rank + i).pin_memory() for i in range(NROT)]
+    xs_dev = [x.to(dev) for x in xs_host]
+    x_host, x_dev = xs_host[0], xs_dev[0]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     T1, C = T_NEW + 1, (T_NEW + 3) // 4
 
@@ -158,6 +162,26 @@ def main():
         bp, cf = M.generate(model, x_host, tok, max_len=T_NEW)       # H2D of x inside, D2H of tokens+confs inside
         return bp
 
+    pipe = M.GenerationPipeline(model, B, T_NEW, depth=2)
+
+    def steps_pipelined(k):
+        """k steps through the batch pipeline (encoder of step i+1 overlaps the decode loop of step i); every step ends with the
+        all-gather of its packed results, stream-ordered behind its decode."""
+        outs = []
+        for i in range(k):
+            t = pipe.submit(xs_dev[i % NROT])
+            with torch.cuda.stream(t.stream):
+                outs.append(M.parallel.all_gather_results(M.parallel.pack_results(t.tokens, t.confs), B * world))
+        pipe.join()
+        return outs
+
+    def steps_e2e_pipelined(k):
+        """the public streaming API with HOST buffers: H2D of every batch and D2H of its tokens + confs inside"""
+        n = 0
+        for bp, cf in M.generate_stream(model, (xs_host[i % NROT] for i in range(k)), tok, max_len=T_NEW):
+            n += bp.shape[0]
+        return n
+
     if args.profile:
         step_device(); torch.cuda.synchronize()
         n0 = M._lib.launch_count(dev)
@@ -165,9 +189,10 @@ def main():
         print(json.dumps({"profile_step_launches": int(M._lib.launch_count(dev) - n0)}))
         return
 
-    # warm-up (also builds the engine / tensor maps)
+    # warm-up (also builds the engine / tensor maps / graphs of both the serial plan and the pipeline)
     for _ in range(max(3, args.warmup)):
         out = step_device()
+    steps_pipelined(max(3, args.warmup))
     torch.cuda.synchronize()
 
     sampler = ClockSampler(local)
@@ -187,12 +212,38 @@ def main():
     if world > 1:
         dist.barrier()
     clocks = sampler.stop()
-    total_ms = sum(a.elapsed_time(b) for a, b in ev)
+    serial_ms = sum(a.elapsed_time(b) for a, b in ev)
+    t = torch.tensor([serial_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    serial_ms = t.item()
+    value_serial = B * world * args.steps / (serial_ms / 1e3)
+
+    # ---- headline: the same K steps through the batch pipeline (device-resident inputs, CUDA events, max over ranks) ----
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler2 = ClockSampler(local)
+    sampler2.start()
+    n2 = M._lib.launch_count(dev)
+    pa, pb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    pa.record()
+    out = steps_pipelined(args.steps)
+    pb.record()
+    torch.cuda.synchronize()
+    n3 = M._lib.launch_count(dev)
+    if world > 1:
+        dist.barrier()
+    clocks2 = sampler2.stop()
+    if clocks2.get("sm_mhz"):
+        clocks = clocks2
+    total_ms = pa.elapsed_time(pb)
     t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms = t.item()
     value = B * world * args.steps / (total_ms / 1e3)
+    n0, n1 = n2, n3
 
     # end-to-end through the public API with host buffers
     for _ in range(2):
@@ -206,6 +257,18 @@ def main():
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_serial = B * world * args.steps / t.item()
+    # end-to-end through the public streaming API (generate_stream), host buffers
+    steps_e2e_pipelined(3)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    steps_e2e_pipelined(args.steps)
+    torch.cuda.synchronize()
+    t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_val = B * world * args.steps / t.item()
@@ -224,7 +287,9 @@ def main():
            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
            "data": "synthetic", "config": cfg, "clocks": clocks,
            "e2e": {"value": e2e_val, "unit": "images/s", "h2d_bytes_per_step": x_host.numel() * 4, "d2h_bytes_per_step": B * (T1 * 4 + C * 4)},
-           "gpu_launches": int(n1 - n0), "ms_per_decode_token": dec_ms / T_NEW, "roofline": roof, "roofline_gemm": roof_gemm}
+           "gpu_launches": int(n1 - n0), "ms_per_decode_token": dec_ms / T_NEW, "roofline": roof, "roofline_gemm": roof_gemm,
+           "serial": {"value": value_serial, "ms_per_step": serial_ms / args.steps, "e2e": e2e_serial,
+                      "note": "one batch at a time (generate_tokens / generate), 256 MiB L2 flush between steps (untimed)"}}
     if not args.no_cpu_baseline:
         out["cpu_baseline"], _ = cpu_reference_arm(1, 1)
     print(json.dumps(out))

@@ -497,7 +497,7 @@ class GenerationPlan:
     """Static buffers + (optionally) a captured CUDA graph for one (batch, new tokens, sampler) shape:
     encoder -> memory -> cross-K/V -> T decode steps, no host synchronisation anywhere inside."""
 
-    def __init__(self, eng, B, T, top_k, top_p, sampling, want_logits, use_graph):
+    def __init__(self, eng, B, T, top_k, top_p, sampling, want_logits, use_graph, split=False):
         d = eng.dims
         dev = eng.device
         self.eng, self.B, self.T = eng, B, T
@@ -514,6 +514,27 @@ class GenerationPlan:
         self.kv = PagedKVCache(B, T, d.dec_layers, d.dim, d.page_tokens, eng.dtype, dev)
         self.scratch = torch.empty(eng.lib.mdc_decode_workspace_bytes(eng.handle, B), dtype=torch.uint8, device=dev)
         self.graph = None
+        self.split = bool(split)
+        if split:
+            # two graphs (encoder + cross-K/V | decode loop) so that a GenerationPipeline can run them on different streams
+            assert use_graph, "split plans are graph plans"
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                self._launch_encode(); self._launch_decode()
+            torch.cuda.current_stream(dev).wait_stream(side)
+            torch.cuda.synchronize(dev)
+            self.enc_graph, self.dec_graph = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+            n0 = L.launch_count(dev)
+            with torch.cuda.graph(self.enc_graph):
+                self._launch_encode()
+            n1 = L.launch_count(dev)
+            with torch.cuda.graph(self.dec_graph):
+                self._launch_decode()
+            self.enc_kernels, self.dec_kernels = n1 - n0, L.launch_count(dev) - n1
+            self.enc_done, self.dec_done = torch.cuda.Event(), torch.cuda.Event()
+            self.busy = False
+            return
         if use_graph:
             side = torch.cuda.Stream(device=dev)
             side.wait_stream(torch.cuda.current_stream(dev))
@@ -529,9 +550,16 @@ class GenerationPlan:
             self.graph = g
 
     def _launch(self):
+        self._launch_encode()
+        self._launch_decode()
+
+    def _launch_encode(self):
         eng = self.eng
         L.check(eng.lib.mdc_encode(eng.handle, L.ptr(self.x), self.B, None, L.ptr(self.memory), L.ptr(self.ws), self.ws_bytes, L.stream_ptr()))
         L.check(eng.lib.mdc_cross_kv_build(eng.handle, L.ptr(self.memory), self.B, L.ptr(self.ckv), L.stream_ptr()))
+
+    def _launch_decode(self):
+        eng = self.eng
         self.tokens.fill_(int(CFG.pad_idx))
         self.tokens[:, 0].fill_(int(CFG.bos_idx))
         eng.decode(self.ckv, self.tokens, 0, self.T, max_tokens=self.T, forced=False, logits=self.logits, logits_row_offset=0,

@@ -1,0 +1,123 @@
+"""Batch pipelining of the inference loop `for x in test_loader: generate(model, x, ...)` (inference_p.py:216-224).
+
+One batch is two dependent phases with very different shapes on a B200:
+  * encoder + cross-K/V build : ~90 short, wide kernels (tcgen05 GEMMs, strip attention) that fill all 148 SMs for ~2 ms
+  * decode loop               : ONE persistent cluster kernel that owns 13-15 clusters x 8 SMs for ~8 ms and leaves ~40 SMs idle
+Batches are independent, so the encoder phase of batch i+1 runs on a low-priority stream WHILE the decode kernel
+of batch i runs on a high-priority stream: its CTAs land on the SMs the clusters leave idle, and the host->device copy of
+batch i+1's images overlaps too.  `depth` plans (static buffers + two CUDA graphs each) are used round-robin; events order
+encoder(i) -> decode(i) -> encoder(i + depth).  Results are bit-identical to the serial `generate()`.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib as L
+from .config import CFG
+
+
+class Ticket:
+    """Result handle of one submitted batch.  `tokens` / `confs` are device tensors valid in the order of `stream`;
+    `result()` blocks the host until this batch (only) is done and returns the host copies."""
+
+    def __init__(self, tokens, confs, host_tokens, host_confs, done, stream):
+        self.tokens, self.confs = tokens, confs
+        self._ht, self._hc, self._done, self.stream = host_tokens, host_confs, done, stream
+
+    def result(self):
+        self._done.synchronize()
+        if self._ht is None:
+            return self.tokens, self.confs
+        return self._ht, self._hc
+
+
+class GenerationPipeline:
+    def __init__(self, model, batch, max_new_tokens, top_k=0, top_p=1.0, depth=2, to_host=False, device=None):
+        from .model import GenerationPlan
+        if not hasattr(model, "_engine"):
+            raise TypeError("GenerationPipeline needs the B200 EncoderDecoder; there is no PyTorch fallback path")
+        eng = model._engine(device)
+        d = eng.dims
+        T = int(max_new_tokens)
+        if T > d.max_pos:
+            raise RuntimeError(f"max_len {T} exceeds CFG.max_len-1 = {d.max_pos} (model.py:93, Q6)")
+        self.eng, self.B, self.T, self.depth, self.to_host = eng, int(batch), T, int(depth), bool(to_host)
+        self.sampling = (top_k != 0 or top_p != 1)
+        dev = eng.device
+        with torch.cuda.device(dev):
+            self.plans = [GenerationPlan(eng, self.B, T, top_k, top_p, self.sampling, False, True, split=True) for _ in range(self.depth)]
+            self.s_enc = torch.cuda.Stream(device=dev, priority=0)      # encoder / cross-K/V / H2D: fills whatever the decode leaves idle
+            self.s_dec = torch.cuda.Stream(device=dev, priority=-1)     # decode clusters are scheduled first
+        self.n = 0
+
+    def submit(self, image, uniforms=None):
+        """image: f32 (B,3,H,W) on the device or in (pinned) host memory.  Returns a Ticket."""
+        p = self.plans[self.n % self.depth]
+        self.n += 1
+        dev = self.eng.device
+        if tuple(image.shape) != tuple(p.x.shape):
+            raise AssertionError("Input size doesn't match model")
+        cur = torch.cuda.current_stream(dev)
+        self.s_enc.wait_stream(cur)                                     # the caller's prior work on `image`
+        with torch.cuda.stream(self.s_enc):
+            if p.busy:
+                self.s_enc.wait_event(p.dec_done)                       # plan buffers are free again
+            p.x.copy_(image, non_blocking=True)
+            if p.uniforms is not None:
+                if uniforms is None:
+                    uniforms = torch.rand((self.B, self.T), dtype=torch.float32, device=dev)
+                p.uniforms.copy_(uniforms.to(torch.float32), non_blocking=True)
+            p.enc_graph.replay()
+            L.note_graph_replay(dev, p.enc_kernels)
+            p.enc_done.record(self.s_enc)
+        with torch.cuda.stream(self.s_dec):
+            self.s_dec.wait_event(p.enc_done)
+            p.dec_graph.replay()
+            L.note_graph_replay(dev, p.dec_kernels)
+            tokens, confs = p.tokens.clone(), p.confs.clone()
+            ht = hc = None
+            if self.to_host:
+                ht = torch.empty(tokens.shape, dtype=torch.int32, pin_memory=True)
+                hc = torch.empty(confs.shape, dtype=torch.float32, pin_memory=True)
+                ht.copy_(tokens, non_blocking=True); hc.copy_(confs, non_blocking=True)
+            p.dec_done.record(self.s_dec)
+            p.busy = True
+            done = torch.cuda.Event()
+            done.record(self.s_dec)
+        return Ticket(tokens, confs, ht, hc, done, self.s_dec)
+
+    def join(self):
+        """Makes the caller's current stream wait for everything submitted so far (no host synchronisation)."""
+        cur = torch.cuda.current_stream(self.eng.device)
+        cur.wait_stream(self.s_dec); cur.wait_stream(self.s_enc)
+
+
+@torch.no_grad()
+def generate_stream(model, batches, tokenizer, max_len=50, top_k=0, top_p=1, depth=2):
+    """The reference's inference loop as ONE pipelined call: yields, per batch and in order, what `generate(model, x, tokenizer,
+    max_len, top_k, top_p)` returns -- (LongTensor (B,1+max_len) on CPU, list of ceil(max_len/4) float tensors (B,) on CPU).
+    `batches` is any iterable of f32 (B,3,H,W) tensors (host, ideally pinned, or device) of one shape."""
+    bos = int(getattr(tokenizer, "BOS_code", CFG.bos_idx))
+    if bos != int(CFG.bos_idx):
+        raise ValueError("tokenizer.BOS_code must equal CFG.bos_idx (model.py:117 reads the global)")
+    pipes, pipe, pending = model.__dict__.setdefault("_stream_pipes", {}), None, []     # plans + graphs are reused across calls
+    n_conf = (max_len + 3) // 4
+
+    def finish(t):
+        host, host_c = t.result()
+        return host.long(), [host_c[:, i].clone() for i in range(n_conf)]
+
+    for x in batches:
+        dev = x.device if x.is_cuda else None
+        key = (tuple(x.shape), int(max_len), int(top_k), float(top_p), int(depth), str(dev))
+        if key not in pipes or pipes[key].eng is not model._engine(dev):      # new shape (e.g. the ragged last batch) / new weights
+            pipes[key] = GenerationPipeline(model, x.shape[0], max_len, top_k=top_k, top_p=top_p, depth=depth, to_host=True, device=dev)
+        if pipes[key] is not pipe:
+            while pending:                       # different plans share no events: drain before switching
+                yield finish(pending.pop(0))
+            pipe = pipes[key]
+        pending.append(pipe.submit(x))
+        if len(pending) > depth:                 # keep `depth` batches in flight, hand out the oldest
+            yield finish(pending.pop(0))
+    while pending:
+        yield finish(pending.pop(0))

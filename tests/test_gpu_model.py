@@ -230,3 +230,26 @@ def test_cluster_decode_topk_and_graph_replay(model_p):
     assert torch.equal(a, b) and torch.equal(a, c)
     g, _ = model_p.generate_tokens(x, 20)
     assert not torch.equal(a, g)
+
+
+def test_batch_pipeline_equals_serial_generate(model_p):
+    """GenerationPipeline / generate_stream (encoder of batch i+1 overlapping the decode loop of batch i on a second stream)
+    must return exactly what the serial generate() returns, batch by batch, including a ragged last batch and sampling."""
+    model_p.set_precision("bf16")
+    tok = M.Tokenizer()
+    xs = [cases.images(16, seed=200 + i) for i in range(5)] + [cases.images(5, seed=300)]
+    want = [M.generate(model_p, x.to(DEV), tok, max_len=40) for x in xs]
+    got = list(M.generate_stream(model_p, (x.pin_memory() for x in xs), tok, max_len=40))
+    assert len(got) == len(want)
+    for (gt, gc), (wt, wc) in zip(got, want):
+        assert torch.equal(gt, wt) and len(gc) == len(wc) and all(torch.equal(a, b) for a, b in zip(gc, wc))
+    # second call reuses the cached plans; device inputs; explicit pipeline with top-k sampling and shared uniforms
+    got2 = list(M.generate_stream(model_p, (x.to(DEV) for x in xs), tok, max_len=40))
+    assert all(torch.equal(a[0], b[0]) for a, b in zip(got2, want))
+    pipe = M.GenerationPipeline(model_p, 16, 24, top_k=5, depth=3)
+    us = [torch.rand(16, 24, generator=torch.Generator().manual_seed(i)).to(DEV) for i in range(4)]
+    tickets = [pipe.submit(xs[i].to(DEV), uniforms=us[i]) for i in range(4)]
+    pipe.join()
+    for i, t in enumerate(tickets):
+        ref, _ = model_p.generate_tokens(xs[i].to(DEV), 24, top_k=5, uniforms=us[i])
+        assert torch.equal(t.result()[0], ref)
