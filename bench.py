@@ -323,11 +323,23 @@ def decode_algorithmic_bytes(B, T=T_NEW, S=196, dim=256, layers=6, ffn=2048, voc
     return T * per_step_fixed + self_kv
 
 
+def ncu_traffic(name):
+    """DRAM bytes per launch of `name` from the newest committed ncu --set full capture (profiles/*_traffic.json), or None."""
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_traffic.json")))
+    if not files:
+        return None
+    try:
+        return json.load(open(files[-1])).get(name, {}).get("dram_bytes_per_launch")
+    except Exception:
+        return None
+
+
 def decode_roofline(dec_ms, peaks, B):
     nbytes = decode_algorithmic_bytes(B)
     ach = nbytes / (dec_ms / 1e3) / 1e9
     return {"kernel": f"decode_fused_kernel (one launch = {T_NEW} decode steps x 6 layers, B={B})", "bound": "hbm", "achieved": ach,
-            "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"], "traffic": None,
+            "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"], "traffic": ncu_traffic("decode"),
             "algorithmic_bytes_per_launch": nbytes, "ms_per_launch": dec_ms,
             "peak_src": peaks["src"] + " HBM copy bandwidth (kernel timed alone, CUDA events)"}
 
@@ -358,7 +370,7 @@ def roofline_probe(M, dev, peaks, B):
     flops = 2.0 * Mr * N * K
     ach = flops / (ms / 1e3) / 1e12
     return {"kernel": "gemm_tc_kernel (mlp.fc1 shape, bias+GELU)", "bound": "tensor", "achieved": ach, "peak": peaks["bf16_tflops"],
-            "unit": "TFLOP/s", "frac": ach / peaks["bf16_tflops"], "traffic": None, "peak_src": peaks["src"] + " burst (kernel timed alone)",
+            "unit": "TFLOP/s", "frac": ach / peaks["bf16_tflops"], "traffic": ncu_traffic("gemm_fc1"), "peak_src": peaks["src"] + " burst (kernel timed alone)",
             "ms_per_launch": ms}
 
 

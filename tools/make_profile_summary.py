@@ -32,6 +32,7 @@ WANT = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "la
         "sm__pipe_tensor_subpipe_hmma_cycles_active.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_tensor_subpipe_hmma.avg.pct_of_peak_sustained_active",
         "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__warps_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum", "sm__cycles_elapsed.max",
         "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "smsp__pcsamp_sample_count"]
+traffic = {}
 for name in ["gemm_fc1", "attn", "decode", "ln"]:
     rep = f"{G}/{tag}_{name}.ncu-rep"
     if not os.path.exists(rep):
@@ -41,6 +42,11 @@ for name in ["gemm_fc1", "attn", "decode", "ln"]:
     hdr, units, vals = rr[0], rr[1], rr[2]
     d = dict(zip(hdr, zip(vals, units)))
     out.append(f"## `{d['Kernel Name'][0][:110]}`  (ncu --set full --clock-control none; `{rep}`)\n")
+    def _bytes(key):
+        v, u = d.get(key, ("0", "byte"))
+        return float(v) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}.get(u, 1)
+    traffic[name] = {"kernel": d["Kernel Name"][0][:80], "dram_bytes_per_launch": _bytes("dram__bytes_read.sum") + _bytes("dram__bytes_write.sum"),
+                     "duration_us_under_ncu": float(d["gpu__time_duration.sum"][0]) * {"us": 1, "ms": 1e3, "ns": 1e-3, "s": 1e6}.get(d["gpu__time_duration.sum"][1], 1)}
     out.append("| metric | value |\n|---|---|")
     for k in WANT:
         if k in d:
@@ -56,4 +62,5 @@ for f in ["bench.log", "gemm.log", "trace.log"]:
     if os.path.exists(pth):
         out.append(f"## {f}\n\n```\n" + open(pth).read().strip() + "\n```\n")
 open(f"{P}/{rnd}_summary.md", "w").write("\n".join(out))
+json.dump(traffic, open(f"{P}/{rnd}_traffic.json", "w"), indent=1)
 print("wrote", f"{P}/{rnd}_summary.md", f"{P}/{rnd}_launches.csv")
