@@ -57,6 +57,7 @@ class DecodeState(C.Structure):
         ("pos_override", C.c_void_p),
         ("x_override", C.c_void_p), ("x_override_ld", C.c_int32),
         ("scratch", C.c_void_p), ("scratch_bytes", C.c_size_t),
+        ("images_per_cluster", C.c_int32),
     ]
 
 

@@ -256,7 +256,8 @@ class Engine:
         return ckv
 
     def decode(self, cross_kv, tokens, t_begin, t_end, *, max_tokens, forced, logits=None, logits_row_offset=0,
-               confs=None, uniforms=None, top_k=0, top_p=1.0, pos_override=None, x_override=None, kv=None, scratch=None):
+               confs=None, uniforms=None, top_k=0, top_p=1.0, pos_override=None, x_override=None, kv=None, scratch=None,
+               images_per_cluster=0):
         """Runs decode steps [t_begin, t_end) back to back on the current stream (no host sync)."""
         d = self.dims
         B = tokens.shape[0]
@@ -286,6 +287,7 @@ class Engine:
         if x_override is not None:
             st.x_override, st.x_override_ld = x_override.data_ptr(), x_override.shape[1]
         st.scratch, st.scratch_bytes = scratch.data_ptr(), scratch.numel()
+        st.images_per_cluster = int(images_per_cluster)
         L.check(self.lib.mdc_decode_steps(self.handle, C.byref(st), t_begin, t_end, L.stream_ptr()))
         return kv, scratch
 
@@ -497,11 +499,12 @@ class GenerationPlan:
     """Static buffers + (optionally) a captured CUDA graph for one (batch, new tokens, sampler) shape:
     encoder -> memory -> cross-K/V -> T decode steps, no host synchronisation anywhere inside."""
 
-    def __init__(self, eng, B, T, top_k, top_p, sampling, want_logits, use_graph, split=False):
+    def __init__(self, eng, B, T, top_k, top_p, sampling, want_logits, use_graph, split=False, images_per_cluster=0):
         d = eng.dims
         dev = eng.device
         self.eng, self.B, self.T = eng, B, T
         self.top_k, self.top_p = int(top_k), float(top_p)
+        self.images_per_cluster = int(images_per_cluster)
         self.x = torch.zeros((B, d.in_chans, d.img_size, d.img_size), dtype=torch.float32, device=dev)
         self.ws_bytes = eng.lib.mdc_encode_workspace_bytes(eng.handle, B)
         self.ws = torch.empty(self.ws_bytes, dtype=torch.uint8, device=dev)
@@ -563,7 +566,8 @@ class GenerationPlan:
         self.tokens.fill_(int(CFG.pad_idx))
         self.tokens[:, 0].fill_(int(CFG.bos_idx))
         eng.decode(self.ckv, self.tokens, 0, self.T, max_tokens=self.T, forced=False, logits=self.logits, logits_row_offset=0,
-                   confs=self.confs, uniforms=self.uniforms, top_k=self.top_k, top_p=self.top_p, kv=self.kv, scratch=self.scratch)
+                   confs=self.confs, uniforms=self.uniforms, top_k=self.top_k, top_p=self.top_p, kv=self.kv, scratch=self.scratch,
+                   images_per_cluster=self.images_per_cluster)
 
     def run(self, image, uniforms=None):
         d = self.eng.dims

@@ -2,11 +2,15 @@
 
 One batch is two dependent phases with very different shapes on a B200:
   * encoder + cross-K/V build : ~90 short, wide kernels (tcgen05 GEMMs, strip attention) that fill all 148 SMs for ~2 ms
-  * decode loop               : ONE persistent cluster kernel that owns 13-15 clusters x 8 SMs for ~8 ms and leaves ~40 SMs idle
-Batches are independent, so the encoder phase of batch i+1 runs on a low-priority stream WHILE the decode kernel
-of batch i runs on a high-priority stream: its CTAs land on the SMs the clusters leave idle, and the host->device copy of
-batch i+1's images overlaps too.  `depth` plans (static buffers + two CUDA graphs each) are used round-robin; events order
-encoder(i) -> decode(i) -> encoder(i + depth).  Results are bit-identical to the serial `generate()`.
+  * decode loop               : ONE persistent cluster kernel, latency-bound (a chain of dependent phases per layer), ~8-10 ms
+Batches are independent, so several are kept in flight: the encoder phase (and the host->device copy) of batch
+i+1 runs on a low-priority stream WHILE the decode kernels of earlier batches run on high-priority streams.  For a single
+batch the decode kernel spreads over as many 8-SM clusters as fit (13-15 x 5 images: lowest latency); in the pipeline it is
+asked for 8 images per cluster instead (8 clusters = 64 SMs for B = 64: ~25 % longer, but 23 % less SM-time per batch), so that
+two to three decode kernels and an encoder share the 148 SMs.  Measured on B200 (tools/pipeline_probe.py, B=64, T=99):
+serial 10.3 ms/batch, 1 decode stream 8.7, 2 streams 7.6, 3 streams 7.2 (saturated: more streams / depth change nothing).
+`depth` plans (static buffers + two CUDA graphs each) are used round-robin; events order encoder(i) -> decode(i) ->
+encoder(i + depth).  Results are bit-identical to the serial `generate()`.
 """
 from __future__ import annotations
 
@@ -32,7 +36,8 @@ class Ticket:
 
 
 class GenerationPipeline:
-    def __init__(self, model, batch, max_new_tokens, top_k=0, top_p=1.0, depth=2, to_host=False, device=None):
+    def __init__(self, model, batch, max_new_tokens, top_k=0, top_p=1.0, depth=4, decode_streams=3, images_per_cluster=8,
+                 to_host=False, device=None):
         from .model import GenerationPlan
         if not hasattr(model, "_engine"):
             raise TypeError("GenerationPipeline needs the B200 EncoderDecoder; there is no PyTorch fallback path")
@@ -45,14 +50,16 @@ class GenerationPipeline:
         self.sampling = (top_k != 0 or top_p != 1)
         dev = eng.device
         with torch.cuda.device(dev):
-            self.plans = [GenerationPlan(eng, self.B, T, top_k, top_p, self.sampling, False, True, split=True) for _ in range(self.depth)]
-            self.s_enc = torch.cuda.Stream(device=dev, priority=0)      # encoder / cross-K/V / H2D: fills whatever the decode leaves idle
-            self.s_dec = torch.cuda.Stream(device=dev, priority=-1)     # decode clusters are scheduled first
+            self.plans = [GenerationPlan(eng, self.B, T, top_k, top_p, self.sampling, False, True, split=True,
+                                         images_per_cluster=images_per_cluster) for _ in range(self.depth)]
+            self.s_enc = torch.cuda.Stream(device=dev, priority=0)      # encoder / cross-K/V / H2D: fills whatever the decodes leave idle
+            self.s_decs = [torch.cuda.Stream(device=dev, priority=-1) for _ in range(max(1, int(decode_streams)))]   # clusters first
         self.n = 0
 
     def submit(self, image, uniforms=None):
         """image: f32 (B,3,H,W) on the device or in (pinned) host memory.  Returns a Ticket."""
         p = self.plans[self.n % self.depth]
+        s_dec = self.s_decs[self.n % len(self.s_decs)]
         self.n += 1
         dev = self.eng.device
         if tuple(image.shape) != tuple(p.x.shape):
@@ -70,8 +77,8 @@ class GenerationPipeline:
             p.enc_graph.replay()
             L.note_graph_replay(dev, p.enc_kernels)
             p.enc_done.record(self.s_enc)
-        with torch.cuda.stream(self.s_dec):
-            self.s_dec.wait_event(p.enc_done)
+        with torch.cuda.stream(s_dec):
+            s_dec.wait_event(p.enc_done)
             p.dec_graph.replay()
             L.note_graph_replay(dev, p.dec_kernels)
             tokens, confs = p.tokens.clone(), p.confs.clone()
@@ -80,20 +87,22 @@ class GenerationPipeline:
                 ht = torch.empty(tokens.shape, dtype=torch.int32, pin_memory=True)
                 hc = torch.empty(confs.shape, dtype=torch.float32, pin_memory=True)
                 ht.copy_(tokens, non_blocking=True); hc.copy_(confs, non_blocking=True)
-            p.dec_done.record(self.s_dec)
+            p.dec_done.record(s_dec)
             p.busy = True
             done = torch.cuda.Event()
-            done.record(self.s_dec)
-        return Ticket(tokens, confs, ht, hc, done, self.s_dec)
+            done.record(s_dec)
+        return Ticket(tokens, confs, ht, hc, done, s_dec)
 
     def join(self):
         """Makes the caller's current stream wait for everything submitted so far (no host synchronisation)."""
         cur = torch.cuda.current_stream(self.eng.device)
-        cur.wait_stream(self.s_dec); cur.wait_stream(self.s_enc)
+        for sd in self.s_decs:
+            cur.wait_stream(sd)
+        cur.wait_stream(self.s_enc)
 
 
 @torch.no_grad()
-def generate_stream(model, batches, tokenizer, max_len=50, top_k=0, top_p=1, depth=2):
+def generate_stream(model, batches, tokenizer, max_len=50, top_k=0, top_p=1, depth=4):
     """The reference's inference loop as ONE pipelined call: yields, per batch and in order, what `generate(model, x, tokenizer,
     max_len, top_k, top_p)` returns -- (LongTensor (B,1+max_len) on CPU, list of ceil(max_len/4) float tensors (B,) on CPU).
     `batches` is any iterable of f32 (B,3,H,W) tensors (host, ideally pinned, or device) of one shape."""

@@ -246,7 +246,7 @@ def test_batch_pipeline_equals_serial_generate(model_p):
     # second call reuses the cached plans; device inputs; explicit pipeline with top-k sampling and shared uniforms
     got2 = list(M.generate_stream(model_p, (x.to(DEV) for x in xs), tok, max_len=40))
     assert all(torch.equal(a[0], b[0]) for a, b in zip(got2, want))
-    pipe = M.GenerationPipeline(model_p, 16, 24, top_k=5, depth=3)
+    pipe = M.GenerationPipeline(model_p, 16, 24, top_k=5, depth=3, decode_streams=2)
     us = [torch.rand(16, 24, generator=torch.Generator().manual_seed(i)).to(DEV) for i in range(4)]
     tickets = [pipe.submit(xs[i].to(DEV), uniforms=us[i]) for i in range(4)]
     pipe.join()
