@@ -12,7 +12,7 @@ import threading
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmdc_b200.so")
+LIB_PATH = os.environ.get("MDC_LIB_PATH") or os.path.join(_HERE, "libmdc_b200.so")     # env override: A/B runs of two builds (tools/)
 
 MDC_F32, MDC_BF16, MDC_F16 = 0, 1, 2
 EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RELU, EPI_LS_RESIDUAL, EPI_PATCH = range(5)

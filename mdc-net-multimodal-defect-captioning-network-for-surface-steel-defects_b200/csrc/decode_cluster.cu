@@ -1034,7 +1034,9 @@ int decode_cluster_launch(mdc_model* m, const mdc_decode_state* st, int t_begin,
     max_clusters = n;
   }
   int G = (P.B + max_clusters - 1) / max_clusters;
-  if (st->images_per_cluster > 0 && st->images_per_cluster > G) G = st->images_per_cluster;   // fewer, fuller clusters (batch pipelining)
+  int ipc = st->images_per_cluster;
+  if (const char* e = getenv("MDC_DECODE_IPC")) ipc = atoi(e);                                  // developer override (tools/decode_trace.py)
+  if (ipc > 0 && ipc > G) G = ipc;                                                              // fewer, fuller clusters (batch pipelining)
   if (G > GM) G = GM;
   if (G < 1) G = 1;
   P.G = G;
