@@ -272,6 +272,23 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_val = B * world * args.steps / t.item()
+    # the same with raw 200x200 u8 grayscale host batches (40 KB / image over PCIe, fused preprocessing kernel on the device)
+    from oracle import mdc_oracle as _O         # synthetic-image generator only
+    gs_host = [_O.synth_gray_u8(B, seed=4321 + 17 * rank + i).pin_memory() for i in range(NROT)]
+    def steps_e2e_gray(k):
+        for bp, cf in M.generate_stream(model, (gs_host[i % NROT] for i in range(k)), tok, max_len=T_NEW):
+            pass
+    steps_e2e_gray(8)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    steps_e2e_gray(args.steps)
+    torch.cuda.synchronize()
+    t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_gray = B * world * args.steps / t.item()
 
     if rank != 0:
         if world > 1:
@@ -288,6 +305,8 @@ def main():
            "data": "synthetic", "config": cfg, "clocks": clocks,
            "e2e": {"value": e2e_val, "unit": "images/s", "h2d_bytes_per_step": x_host.numel() * 4, "d2h_bytes_per_step": B * (T1 * 4 + C * 4)},
            "gpu_launches": int(n1 - n0), "ms_per_decode_token": dec_ms / T_NEW, "roofline": roof, "roofline_gemm": roof_gemm,
+           "e2e_gray_u8": {"value": e2e_gray, "unit": "images/s", "h2d_bytes_per_step": B * 200 * 200, "d2h_bytes_per_step": B * (T1 * 4 + C * 4),
+                           "note": "generate_stream over raw u8 200x200 host images; normalisation by mdc_preprocess_gray on the device"},
            "serial": {"value": value_serial, "ms_per_step": serial_ms / args.steps, "e2e": e2e_serial,
                       "note": "one batch at a time (generate_tokens / generate), 256 MiB L2 flush between steps (untimed)"}}
     if not args.no_cpu_baseline:

@@ -9,7 +9,7 @@ from .tokenizer import Tokenizer
 from .model import Encoder, Decoder, EncoderDecoder, Engine
 from .axial_model import AxialAttention
 from . import axial_model
-from .inference import generate, postprocess
+from .inference import generate, postprocess, preprocess_gray
 from .pipeline import GenerationPipeline, generate_stream
 from .iou import (bbox_iou, calculate_batch_iou, calculate_batch_max_iou, calculate_batch_max_iou_torchvision,
                   calculate_batch_max_iou_masked, giou_pairwise, giou_loss_with_scores, calculate_iou, iou_loss)
@@ -18,6 +18,6 @@ from . import parallel
 from . import _lib
 
 __all__ = ["CFG", "Tokenizer", "Encoder", "Decoder", "EncoderDecoder", "Engine", "AxialAttention", "axial_model",
-           "generate", "postprocess", "GenerationPipeline", "generate_stream", "bbox_iou", "calculate_batch_iou", "calculate_batch_max_iou",
+           "generate", "postprocess", "preprocess_gray", "GenerationPipeline", "generate_stream", "bbox_iou", "calculate_batch_iou", "calculate_batch_max_iou",
            "calculate_batch_max_iou_torchvision", "calculate_batch_max_iou_masked", "giou_pairwise",
            "giou_loss_with_scores", "calculate_iou", "iou_loss", "PagedKVCache", "PageAllocator", "parallel"]

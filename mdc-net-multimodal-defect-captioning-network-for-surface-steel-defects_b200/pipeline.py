@@ -57,19 +57,29 @@ class GenerationPipeline:
         self.n = 0
 
     def submit(self, image, uniforms=None):
-        """image: f32 (B,3,H,W) on the device or in (pinned) host memory.  Returns a Ticket."""
+        """image: f32 (B,3,H,W) on the device or in (pinned) host memory -- or raw grayscale u8 (B,h,w), which is normalised
+        on the device by the fused preprocessing kernel (inference.preprocess_gray) straight into the plan's input buffer.
+        Returns a Ticket."""
         p = self.plans[self.n % self.depth]
         s_dec = self.s_decs[self.n % len(self.s_decs)]
         self.n += 1
         dev = self.eng.device
-        if tuple(image.shape) != tuple(p.x.shape):
+        gray = image.dtype == torch.uint8
+        if gray:
+            if image.dim() != 3 or image.shape[0] != self.B:
+                raise AssertionError("gray input must be uint8 (B,h,w)")
+        elif tuple(image.shape) != tuple(p.x.shape):
             raise AssertionError("Input size doesn't match model")
         cur = torch.cuda.current_stream(dev)
         self.s_enc.wait_stream(cur)                                     # the caller's prior work on `image`
         with torch.cuda.stream(self.s_enc):
             if p.busy:
                 self.s_enc.wait_event(p.dec_done)                       # plan buffers are free again
-            p.x.copy_(image, non_blocking=True)
+            if gray:
+                from .inference import preprocess_gray
+                preprocess_gray(image, size=p.x.shape[-1], out=p.x)
+            else:
+                p.x.copy_(image, non_blocking=True)
             if p.uniforms is not None:
                 if uniforms is None:
                     uniforms = torch.rand((self.B, self.T), dtype=torch.float32, device=dev)
@@ -105,7 +115,8 @@ class GenerationPipeline:
 def generate_stream(model, batches, tokenizer, max_len=50, top_k=0, top_p=1, depth=4):
     """The reference's inference loop as ONE pipelined call: yields, per batch and in order, what `generate(model, x, tokenizer,
     max_len, top_k, top_p)` returns -- (LongTensor (B,1+max_len) on CPU, list of ceil(max_len/4) float tensors (B,) on CPU).
-    `batches` is any iterable of f32 (B,3,H,W) tensors (host, ideally pinned, or device) of one shape."""
+    `batches` is any iterable of f32 (B,3,H,W) tensors (host, ideally pinned, or device) -- or of raw grayscale u8 (B,h,w)
+    tensors, normalised on the device (preprocess_gray)."""
     bos = int(getattr(tokenizer, "BOS_code", CFG.bos_idx))
     if bos != int(CFG.bos_idx):
         raise ValueError("tokenizer.BOS_code must equal CFG.bos_idx (model.py:117 reads the global)")
@@ -118,7 +129,7 @@ def generate_stream(model, batches, tokenizer, max_len=50, top_k=0, top_p=1, dep
 
     for x in batches:
         dev = x.device if x.is_cuda else None
-        key = (tuple(x.shape), int(max_len), int(top_k), float(top_p), int(depth), str(dev))
+        key = ((x.shape[0], str(x.dtype)) if x.dtype == torch.uint8 else tuple(x.shape), int(max_len), int(top_k), float(top_p), int(depth), str(dev))
         if key not in pipes or pipes[key].eng is not model._engine(dev):      # new shape (e.g. the ragged last batch) / new weights
             pipes[key] = GenerationPipeline(model, x.shape[0], max_len, top_k=top_k, top_p=top_p, depth=depth, to_host=True, device=dev)
         if pipes[key] is not pipe:

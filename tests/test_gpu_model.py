@@ -253,3 +253,17 @@ def test_batch_pipeline_equals_serial_generate(model_p):
     for i, t in enumerate(tickets):
         ref, _ = model_p.generate_tokens(xs[i].to(DEV), 24, top_k=5, uniforms=us[i])
         assert torch.equal(t.result()[0], ref)
+
+
+def test_gray_u8_inputs_through_the_fused_preprocessing(model_p):
+    """raw 200x200 grayscale u8 images -> preprocess_gray kernel -> the same tokens as feeding the float tensor
+    the oracle's restatement of the reference transform produces (inference_p.py:148-158 semantics)."""
+    model_p.set_precision("bf16")
+    tok = M.Tokenizer()
+    u8 = O.synth_gray_u8(16, seed=77)
+    x = O.preprocess_gray(u8)
+    xg = M.preprocess_gray(u8.to(DEV))
+    assert xg.shape == (16, 3, 224, 224) and (xg.cpu() - x).abs().max().item() < 1e-5
+    want, _ = M.generate(model_p, xg, tok, max_len=30)
+    got = list(M.generate_stream(model_p, [u8.pin_memory(), u8.to(DEV)], tok, max_len=30))
+    assert torch.equal(got[0][0], want) and torch.equal(got[1][0], want)
