@@ -27,6 +27,7 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
 }
+__device__ __forceinline__ float ex2_fast(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }   // exp2f() adds denormal range handling the softmax does not need
 // byte offset of 16-byte chunk `c` (0..7) of row `r` in a swizzled [rows][64 bf16] panel
 __device__ __forceinline__ uint32_t swz(int r, int c) { return (uint32_t)(r * 128 + ((c ^ (r & 7)) << 4)); }
 
@@ -109,19 +110,21 @@ attn_tc_kernel(const bf16* __restrict__ qkv, int64_t ld, bf16* __restrict__ out,
     mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
     mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
     const float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);          // finite: key 0 of the first block is always valid
-    const float c0 = exp2f((m0 - mn0) * scale_log2e), c1 = exp2f((m1 - mn1) * scale_log2e);
+    const float c0 = ex2_fast((m0 - mn0) * scale_log2e), c1 = ex2_fast((m1 - mn1) * scale_log2e);
     m0 = mn0; m1 = mn1;
     const float ms0 = mn0 * scale_log2e, ms1 = mn1 * scale_log2e;
     float p[2][4];
 #pragma unroll
     for (int nt = 0; nt < 2; ++nt) {
-      p[nt][0] = exp2f(fmaf(s[nt][0], scale_log2e, -ms0)); p[nt][1] = exp2f(fmaf(s[nt][1], scale_log2e, -ms0));
-      p[nt][2] = exp2f(fmaf(s[nt][2], scale_log2e, -ms1)); p[nt][3] = exp2f(fmaf(s[nt][3], scale_log2e, -ms1));
+      p[nt][0] = ex2_fast(fmaf(s[nt][0], scale_log2e, -ms0)); p[nt][1] = ex2_fast(fmaf(s[nt][1], scale_log2e, -ms0));
+      p[nt][2] = ex2_fast(fmaf(s[nt][2], scale_log2e, -ms1)); p[nt][3] = ex2_fast(fmaf(s[nt][3], scale_log2e, -ms1));
     }
     l0 = l0 * c0 + (p[0][0] + p[0][1]) + (p[1][0] + p[1][1]);
     l1 = l1 * c1 + (p[0][2] + p[0][3]) + (p[1][2] + p[1][3]);
+    if (__any_sync(0xffffffffu, c0 != 1.0f || c1 != 1.0f)) {       // a running maximum moved: rescale (rare after the first key blocks)
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { o[i][0] *= c0; o[i][1] *= c0; o[i][2] *= c1; o[i][3] *= c1; }
+      for (int i = 0; i < 8; ++i) { o[i][0] *= c0; o[i][1] *= c0; o[i][2] *= c1; o[i][3] *= c1; }
+    }
     // ---- O += P V : P is the A operand (rows = queries, k = these 16 keys) -----------------------------------------
     uint32_t pa[4];
     pa[0] = pack_bf16(p[0][0], p[0][1]); pa[1] = pack_bf16(p[0][2], p[0][3]);
