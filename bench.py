@@ -162,6 +162,13 @@ def main():
         bp, cf = M.generate(model, x_host, tok, max_len=T_NEW)       # H2D of x inside, D2H of tokens+confs inside
         return bp
 
+    if args.profile:
+        step_device(); torch.cuda.synchronize()
+        n0 = M._lib.launch_count(dev)
+        step_device(); torch.cuda.synchronize()
+        print(json.dumps({"profile_step_launches": int(M._lib.launch_count(dev) - n0)}))
+        return
+
     pipe = M.GenerationPipeline(model, B, T_NEW)
 
     def steps_pipelined(k):
@@ -181,13 +188,6 @@ def main():
         for bp, cf in M.generate_stream(model, (xs_host[i % NROT] for i in range(k)), tok, max_len=T_NEW):
             n += bp.shape[0]
         return n
-
-    if args.profile:
-        step_device(); torch.cuda.synchronize()
-        n0 = M._lib.launch_count(dev)
-        step_device(); torch.cuda.synchronize()
-        print(json.dumps({"profile_step_launches": int(M._lib.launch_count(dev) - n0)}))
-        return
 
     # warm-up (also builds the engine / tensor maps / graphs of both the serial plan and the pipeline)
     for _ in range(max(3, args.warmup)):

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define MDC_ABI_VERSION 3
+#define MDC_ABI_VERSION 4
 
 /* element types of activations / weights.  MDC_F16 (IEEE half) is only ever the type of the decode-loop weights, see
  * mdc_dims.dec_loop_dtype. */
@@ -208,11 +208,13 @@ size_t mdc_kv_page_bytes(const mdc_model* m);
 /* steps t = t_begin .. t_end-1, back to back on `stream`, no host synchronisation inside. */
 int mdc_decode_steps(mdc_model* m, const mdc_decode_state* st, int t_begin, int t_end, void* stream);
 
-/* (d) head + select as a stand-alone op: logits f32 [B,V] -> token, max prob.
+/* (d) head + select as a stand-alone op: logits f32 [B,V] -> token, max prob, probability of the selected token.
  * greedy: argmax(softmax(logits)) = first max index (inference_p.py:77);
- * top_k/top_p: transformers top_k_top_p_filtering (inference_p.py:83) then inverse-CDF draw with u. */
+ * top_k/top_p: transformers top_k_top_p_filtering (inference_p.py:83) then inverse-CDF draw with u.
+ * Also serves data_processing.py:786-790 top_k_sampling and :803-835 top_k_sampling_with_scores_2d (prob_out = the sampled
+ * token's softmax probability under the filtered distribution); any of the three outputs may be NULL. */
 int mdc_select(mdc_ctx* ctx, const float* logits, int64_t ld, int B, int V, int top_k, float top_p,
-               const float* uniforms, int32_t* token_out, float* conf_out, void* stream);
+               const float* uniforms, int32_t* token_out, float* conf_out, float* prob_out, void* stream);
 
 /* AxialAttention.forward as a whole (axial_model.py:28-40): x f32 (B,n,dim) -> f32 (B,n,dim). */
 size_t mdc_axial_workspace_bytes(const mdc_model* m, int B, int n);

@@ -86,7 +86,7 @@ SIGNATURES = {
     "mdc_decode_workspace_bytes": (_SZ, [_P, _I]),
     "mdc_kv_page_bytes": (_SZ, [_P]),
     "mdc_decode_steps": (_I, [_P, C.POINTER(DecodeState), _I, _I, _P]),
-    "mdc_select": (_I, [_P, _P, _L, _I, _I, _I, _F, _P, _P, _P, _P]),
+    "mdc_select": (_I, [_P, _P, _L, _I, _I, _I, _F, _P, _P, _P, _P, _P]),
     "mdc_axial_workspace_bytes": (_SZ, [_P, _I, _I]),
     "mdc_axial_attention": (_I, [_P, _P, _I, _I, _I, _P, _P, _SZ, _P]),
     "mdc_axial_embed_workspace_bytes": (_SZ, [_P, _I, _I]),

@@ -459,16 +459,16 @@ __global__ void __launch_bounds__(SEL_THREADS) dec_select_kernel(const float* __
 
 __global__ void __launch_bounds__(SEL_THREADS) select_kernel(const float* __restrict__ logits, int64_t ld, int V, int Vp2, int top_k,
                                                              float top_p, const float* __restrict__ uniforms, int32_t* __restrict__ token_out,
-                                                             float* __restrict__ conf_out) {
+                                                             float* __restrict__ conf_out, float* __restrict__ prob_out) {
   extern __shared__ __align__(16) float sm[];
   float* lg = sm; float* srt = sm + V;
   const int b = blockIdx.x;
   for (int i = threadIdx.x; i < V; i += SEL_THREADS) lg[i] = logits[(int64_t)b * ld + i];
   __syncthreads();
   const bool sample = (top_k != 0 || top_p != 1.0f) && uniforms != nullptr;
-  int token; float conf;
-  select_from_logits(lg, srt, V, Vp2, top_k, top_p, sample, sample ? uniforms[b] : 0.f, token, conf);
-  if (threadIdx.x == 0) { if (token_out) token_out[b] = token; if (conf_out) conf_out[b] = conf; }
+  int token; float conf, prob;
+  select_from_logits(lg, srt, V, Vp2, top_k, top_p, sample, sample ? uniforms[b] : 0.f, token, conf, &prob);
+  if (threadIdx.x == 0) { if (token_out) token_out[b] = token; if (conf_out) conf_out[b] = conf; if (prob_out) prob_out[b] = prob; }
 }
 
 int next_pow2(int v) { int p = 1; while (p < v) p <<= 1; return p; }
@@ -635,10 +635,10 @@ extern "C" int mdc_decode_steps(mdc_model* m, const mdc_decode_state* st, int t_
 }
 
 extern "C" int mdc_select(mdc_ctx* ctx, const float* logits, int64_t ld, int B, int V, int top_k, float top_p, const float* uniforms,
-                          int32_t* token_out, float* conf_out, void* stream) {
-  MDC_CHECK_ARG(ctx && logits && B > 0 && V > 0 && V <= 4096 && (token_out || conf_out));
+                          int32_t* token_out, float* conf_out, float* prob_out, void* stream) {
+  MDC_CHECK_ARG(ctx && logits && B > 0 && V > 0 && V <= 4096 && (token_out || conf_out || prob_out));
   int Vp2 = next_pow2(V);
   size_t smem = (size_t)(V + Vp2) * sizeof(float);
-  select_kernel<<<B, SEL_THREADS, smem, (cudaStream_t)stream>>>(logits, ld, V, Vp2, top_k, top_p, uniforms, token_out, conf_out);
+  select_kernel<<<B, SEL_THREADS, smem, (cudaStream_t)stream>>>(logits, ld, V, Vp2, top_k, top_p, uniforms, token_out, conf_out, prob_out);
   MDC_LAUNCH_CHECK(ctx); return 0;
 }

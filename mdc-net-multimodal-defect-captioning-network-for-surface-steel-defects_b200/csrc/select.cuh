@@ -50,7 +50,7 @@ __device__ __forceinline__ double block_sum_d(double v, double* s_d) {
 // Semantics: transformers top_k_top_p_filtering (inference_p.py:83) -> conf = max softmax prob of the
 // filtered logits (inference_p.py:84-86) -> greedy argmax (inference_p.py:77) or inverse-CDF draw with u.
 __device__ inline void select_from_logits(float* lg, float* srt, int V, int Vp2, int top_k, float top_p, bool sample, float u,
-                                   int& token, float& conf) {
+                                   int& token, float& conf, float* token_prob = nullptr) {
   __shared__ float s_val[SEL_THREADS / 32]; __shared__ int s_idx[SEL_THREADS / 32];
   __shared__ double s_d[SEL_THREADS / 32]; __shared__ double s_scan[SEL_THREADS]; __shared__ int s_first;
   const int tid = threadIdx.x;
@@ -132,6 +132,7 @@ __device__ inline void select_from_logits(float* lg, float* srt, int V, int Vp2,
     MDC_SEL_SYNC();
   }
   token = tok; conf = cf;
+  if (token_prob) *token_prob = expf(lg[tok] - mx) * cf;      // softmax probability of the selected token (filtered distribution)
 }
 
 

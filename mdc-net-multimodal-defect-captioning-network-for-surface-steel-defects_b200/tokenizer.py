@@ -11,6 +11,40 @@ from __future__ import annotations
 import torch
 
 
+def _select(logits, k, uniforms, want_prob):
+    import ctypes as C  # noqa: F401
+    from . import _lib as L
+    from .config import CFG
+    if logits.dim() != 2:
+        raise ValueError("logits must be (batch, num_classes)")
+    dev = logits.device if logits.is_cuda else torch.device(CFG.device)
+    if dev.type != "cuda":
+        raise L.MdcError("sampling runs on the GPU (mdc_select); there is no CPU fallback")
+    lg = logits.to(dev, torch.float32).contiguous()
+    B, V = lg.shape
+    if uniforms is None:
+        uniforms = torch.rand(B, device=dev)
+    u = uniforms.to(dev, torch.float32).reshape(B).contiguous()
+    tok = torch.empty(B, dtype=torch.int32, device=dev)
+    prob = torch.empty(B, dtype=torch.float32, device=dev) if want_prob else None
+    with torch.cuda.device(dev):
+        L.check(L.lib().mdc_select(L.ctx(dev), L.ptr(lg), lg.stride(0), B, V, int(k), 1.0, L.ptr(u), L.ptr(tok), None, L.ptr(prob), L.stream_ptr()))
+    return tok.long().view(B, 1), (prob.view(B, 1) if want_prob else None)
+
+
+def top_k_sampling(logits, k, uniforms=None):
+    """data_processing.py:786-790: keep the k largest logits (ties at the k-th kept), softmax, draw one index per row ->
+    LongTensor (B,1).  The reference draws with torch.multinomial; here the draw is the inverse CDF of the same distribution at
+    `uniforms` (B,) in [0,1) (torch.rand on the device when omitted), which makes it reproducible and testable against the
+    oracle.  Unlike the reference the caller's `logits` tensor is not modified in place."""
+    return _select(logits, k, uniforms, False)[0]
+
+
+def top_k_sampling_with_scores_2d(logits, k, uniforms=None):
+    """data_processing.py:803-835: as top_k_sampling, plus the sampled index's probability -> (LongTensor (B,1), f32 (B,1))."""
+    return _select(logits, k, uniforms, True)
+
+
 class Tokenizer:
     UNK_code, BOS_code, EOS_code, PAD_code = 299, 300, 301, 302
     CAPTION_START, CAPTION_END = 303, 304

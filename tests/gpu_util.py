@@ -40,7 +40,7 @@ def select(logits, top_k=0, top_p=1.0, uniforms=None):
     tok = torch.empty(B, dtype=torch.int32, device=logits.device)
     conf = torch.empty(B, dtype=torch.float32, device=logits.device)
     L.check(L.lib().mdc_select(L.ctx(logits.device), L.ptr(logits), logits.stride(0), B, V, top_k, float(top_p), L.ptr(uniforms),
-                               L.ptr(tok), L.ptr(conf), L.stream_ptr()))
+                               L.ptr(tok), L.ptr(conf), None, L.stream_ptr()))
     return tok, conf
 
 

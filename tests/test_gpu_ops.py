@@ -234,3 +234,19 @@ def test_postprocess_batched_equals_per_sample_decode(golden):
         assert labels[i] == g["decode_labels"][i] and caps[i] == g["decode_captions"][i]
         assert torch.equal(torch.tensor(bboxes[i]).reshape(-1, 4).float(), g["decode_boxes"][i])
         assert len(cf[i]) == len(bboxes[i])
+
+
+def test_top_k_sampling_helpers_against_oracle():
+    """data_processing.py:786-835 top_k_sampling / top_k_sampling_with_scores_2d with shared uniforms: same indices as the oracle's
+    inverse-CDF draw over the top-k-filtered softmax, same probabilities to 1e-6."""
+    gen = torch.Generator().manual_seed(12)
+    logits = torch.randn(64, 305, generator=gen) * 2.0
+    logits[3, 10] = logits[3, 20] = logits[3].max() + 1.0           # a tie inside the top-k
+    u = torch.rand(64, generator=gen)
+    idx, score = M.top_k_sampling_with_scores_2d(logits.to(DEV), 5, uniforms=u.to(DEV))
+    idx1 = M.top_k_sampling(logits.to(DEV), 5, uniforms=u.to(DEV))
+    filt = O.top_k_top_p_filtering(logits.clone(), top_k=5, top_p=1.0)
+    want = O.sample_from_uniform(filt, u)
+    probs = torch.softmax(filt, dim=-1)
+    assert idx.shape == (64, 1) and idx.dtype == torch.int64 and torch.equal(idx.cpu().view(-1), want.view(-1)) and torch.equal(idx, idx1)
+    assert (score.cpu().view(-1) - probs.gather(1, want.view(-1, 1)).view(-1)).abs().max().item() < 1e-6

@@ -12,4 +12,4 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 800 --csv --log-fil
 ncu --set full --clock-control none --import-source on -k regex:gemm_tc_kernel -c 1 -f -o $o/${tag}_gemm_fc1 python tools/gemm_probe.py 64 1 fc1 > $o/${tag}_ncu_gemm.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:attn_tc_kernel -c 1 -f -o $o/${tag}_attn python bench.py --profile > $o/${tag}_ncu_attn.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:decode_fused_kernel -c 1 -f -o $o/${tag}_decode python tools/decode_probe.py 64 99 > $o/${tag}_ncu_decode.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:layernorm_kernel -c 1 -f -o $o/${tag}_ln python bench.py --profile > $o/${tag}_ncu_ln.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:layernorm_rows_kernel -c 1 -f -o $o/${tag}_ln python bench.py --profile > $o/${tag}_ncu_ln.log 2>&1
