@@ -237,85 +237,11 @@ __device__ __forceinline__ void build_q_frag(const bf16* qh, uint32_t (&aq)[2][2
 
 __device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 
-// Flash-decoding over key tiles t0, t0+tstep, ... < t1 (16 keys each) of one (K, V) panel pair, in chunks of MAXT tiles with
-// the usual running (max, sum, output) rescale.  On return m_run / l_run are warp-uniform; the un-normalised output of dims
-// mt*16 + {g, g+8} sits in lanes with q == 0 as o[mt][0] and o[mt][2].
-template <int MAXT>
-__device__ __forceinline__ void attn_tiles(uint32_t kp, uint32_t vp, const uint32_t (&aq)[2][2], int t0, int t1, int tstep, int nkeys,
-                                           const uint8_t* padf, float& m_run, float& l_run, float (&o)[2][4]) {
-  const int lane = threadIdx.x & 31, g = lane >> 2, q4 = lane & 3;
-  const uint32_t a_k0[4] = {aq[0][0], 0u, aq[0][1], 0u}, a_k1[4] = {aq[1][0], 0u, aq[1][1], 0u};
-  for (int c0 = t0; c0 < t1; c0 += MAXT * tstep) {
-    const int nt = min(MAXT, (t1 - c0 + tstep - 1) / tstep);
-    float sc[MAXT][4];
-#pragma unroll
-    for (int i = 0; i < MAXT; ++i) {
-      if (i < nt) {
-        const int k0 = (c0 + i * tstep) * 16;
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {          // 8-key n-tile j: one ldmatrix.x4 = the four dim chunks of keys k0+8j .. +7
-          const int key = k0 + 8 * j + (lane & 7);
-          uint32_t kb[4];
-          ldsm_x4(kb, kp + key * 64 + (((lane >> 3) ^ ((key >> 1) & 3)) << 4));
-          float c[4] = {0.f, 0.f, 0.f, 0.f}, d[4] = {0.f, 0.f, 0.f, 0.f};
-          mma16816(c, a_k0, kb[0], kb[1]);
-          mma16816(d, a_k1, kb[2], kb[3]);
-          sc[i][2 * j] = c[0] + d[0];
-          sc[i][2 * j + 1] = c[1] + d[1];
-        }
-        if (padf != nullptr || k0 + 16 > nkeys) {                          // PAD-key bias / tail mask: rare, warp-uniform
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const int key = k0 + (e >> 1) * 8 + 2 * q4 + (e & 1);
-            if (padf != nullptr && padf[key]) sc[i][e] += LOG2E;           // float PAD-key bias +1.0 (Q7), in log2 units
-            if (key >= nkeys) sc[i][e] = -INFINITY;
-          }
-        }
-      } else {
-#pragma unroll
-        for (int e = 0; e < 4; ++e) sc[i][e] = -INFINITY;
-      }
-    }
-    float mx = m_run;
-#pragma unroll
-    for (int i = 0; i < MAXT; ++i) mx = fmaxf(fmaxf(mx, fmaxf(sc[i][0], sc[i][1])), fmaxf(sc[i][2], sc[i][3]));
-    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
-    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
-    mx = __shfl_sync(0xffffffffu, mx, 0);                                   // only row group g = 0 holds scores
-    const float corr = ex2_approx(m_run - mx);                              // first chunk: exp2(-inf) = 0
-    l_run *= corr;
-#pragma unroll
-    for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-      for (int e = 0; e < 4; ++e) o[mt][e] *= corr;
-    m_run = mx;
-    float ls = 0.f;
-#pragma unroll
-    for (int i = 0; i < MAXT; ++i) {
-      if (i < nt) {
-        float p[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) { p[e] = ex2_approx(sc[i][e] - mx); ls += p[e]; }
-        const uint32_t b0 = pack_bf16(p[0], p[1]), b1 = pack_bf16(p[2], p[3]);   // column 0 of the B operand lives in row group g = 0
-        const int key = (c0 + i * tstep) * 16 + ((lane >> 4) & 1) * 8 + (lane & 7), sw = (key >> 1) & 3, dsel = (lane >> 3) & 1;
-        const uint32_t rowaddr = vp + key * 64;
-        uint32_t a0[4], a1[4];
-        ldsm_x4_trans(a0, rowaddr + ((dsel ^ sw) << 4));
-        ldsm_x4_trans(a1, rowaddr + (((2 + dsel) ^ sw) << 4));
-        mma16816(o[0], a0, b0, b1);
-        mma16816(o[1], a1, b0, b1);
-      }
-    }
-    ls += __shfl_xor_sync(0xffffffffu, ls, 1);
-    ls += __shfl_xor_sync(0xffffffffu, ls, 2);
-    l_run += __shfl_sync(0xffffffffu, ls, 0);
-  }
-}
-
-// The same attention over key tiles tl, tl + tstep (at most two, 16 keys each) as ONE straight-line chunk: a tile past the end is
-// clamped onto tile `tl` and masked, so there is no control flow between the fragment loads and the MMAs and all four K fragments
-// and all four V fragments (which do not depend on the scores) are requested before the first MMA (volatile asm: program order
-// is issue order) -- the chunk pays the ldmatrix latency once.  Requires tl < ntile.  Outputs as attn_tiles.
+// One query against key tiles tl, tl + tstep (at most two, 16 keys each) of one (K, V) panel pair as ONE straight-line chunk: a
+// tile past the end is clamped onto tile `tl` and masked, so there is no control flow between the fragment loads and the MMAs and
+// all four K fragments and all four V fragments (which do not depend on the scores) are requested before the first MMA (volatile
+// asm: program order is issue order) -- the chunk pays the ldmatrix latency once.  Requires tl < ntile.  On return m_out / l_out
+// are warp-uniform; the un-normalised output of dims mt*16 + {g, g+8} sits in lanes with q == 0 as o[mt][0] and o[mt][2].
 __device__ __forceinline__ void attn_chunk2(uint32_t kp, uint32_t vp, const uint32_t (&aq)[2][2], int tl, int tstep, int ntile, int nkeys,
                                             const uint8_t* padf, float& m_out, float& l_out, float (&o)[2][4]) {
   const int lane = threadIdx.x & 31, q4 = lane & 3;
