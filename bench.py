@@ -8,11 +8,16 @@ through encoder -> cross-K/V -> 99 greedy decode steps (BASELINE.json configs[1]
 N>1 (torchrun): every rank owns its own 64 images (weak scaling; configs[2] at 8 ranks = B 512) and the
 step ends with ONE all-gather of the packed results.  Prints ONE JSON line on rank 0.
 
-  value  : device-resident inputs, CUDA-event time of the step (max over ranks)
-  e2e    : the public API generate(model, x_host_pinned, tokenizer, max_len) incl. H2D of x and D2H of results
-  roofline: the dominant kernel timed alone with CUDA events (algorithmic bytes or flops / time)
+  value  : K steps through the batch pipeline (mdcnet_b200.GenerationPipeline: the encoder of step i+1 overlaps the decode loops
+           of earlier steps on other streams), device-resident inputs, CUDA events around the K steps, max over ranks
+  e2e    : the public streaming API generate_stream(model, pinned host batches, tokenizer, max_len): H2D of every batch and D2H
+           of its results inside; e2e_gray_u8: the same from raw 200x200 u8 images (fused preprocessing kernel)
+  serial : the same numbers one batch at a time (generate_tokens / generate), 256 MiB L2 flush between steps
+  roofline: the dominant kernel (fused decode loop) timed alone with CUDA events, algorithmic bytes / time against the measured
+           HBM peak, `traffic` = DRAM bytes per launch from the newest committed ncu capture; roofline_gemm: mlp.fc1 against the
+           measured bf16 tensor peak
   cpu_baseline: the oracle port of the reference's own loop (encoder recomputed every step, model.py:177-181)
-              on the host cores, bounded sample.   --impl reference prints only that arm.
+              on the host cores, bounded sample (N = 1 only).   --impl reference prints only that arm.
 """
 import argparse
 import json
@@ -309,7 +314,7 @@ def main():
                            "note": "generate_stream over raw u8 200x200 host images; normalisation by mdc_preprocess_gray on the device"},
            "serial": {"value": value_serial, "ms_per_step": serial_ms / args.steps, "e2e": e2e_serial,
                       "note": "one batch at a time (generate_tokens / generate), 256 MiB L2 flush between steps (untimed)"}}
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:          # reported on rank 0 at N = 1 only; `--impl reference` is the arm for every N
         out["cpu_baseline"], _ = cpu_reference_arm(1, 1)
     print(json.dumps(out))
     if world > 1:
