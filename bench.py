@@ -48,40 +48,62 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    """SM clock + throttle reasons DURING the timed region (B200_PROFILING.md recipe), sampled every 10 ms through NVML in a
+    background thread (nvidia-smi -lms needs ~0.5 s to start, longer than a short timed region); nvidia-smi is the fallback."""
+
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.samples, self.run, self.t, self.h, self.mx = index, [], False, None, None, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[index]) if vis and all(v.strip().isdigit() for v in vis.split(",")) else index
+            self.nv, self.h = pynvml, pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.h = None
+
+    def _loop(self):
+        nv = self.nv
+        while self.run:
+            try:
+                self.samples.append((float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)), int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))))
+            except Exception:
+                pass
+            time.sleep(0.01)
 
     def start(self):
-        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
-            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
+        self.samples = []
+        if self.h is not None:
+            self.run = True
+            self.t = threading.Thread(target=self._loop, daemon=True)
             self.t.start()
-        except Exception:
-            self.proc = None
-
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
+        if self.h is None:
+            return self._smi_once()
+        self.run = False
+        self.t.join(timeout=1.0)
+        sm = [c for c, _ in self.samples]
+        mask = 0
+        for _, r in self.samples:
+            mask |= r
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": self.mx, "reasons": [n for b, n in self.REASONS.items() if mask & b],
+                "samples": len(sm), "source": "nvml, 10 ms period"}
+
+    def _smi_once(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         try:
-            self.proc.wait(timeout=3)
+            r = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=10)
+            c = [x.strip() for x in r.stdout.strip().split(",")]
+            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+            return {"sm_mhz": float(c[0]), "sm_max_mhz": float(c[1]), "reasons": [n for i, n in enumerate(names) if c[2 + i].lower().startswith("active")],
+                    "samples": 1, "source": "nvidia-smi, one sample right after the timed region (NVML unavailable)"}
         except Exception:
-            self.proc.kill()
-        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(len(r) >= 7 and r[3 + i].lower().startswith("active") for r in self.rows)]
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
-                "samples": len(sm)}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"], "samples": 0}
 
 
 def cpu_reference_arm(steps, warmup, sample_steps=6):
@@ -240,8 +262,9 @@ def main():
     if world > 1:
         dist.barrier()
     clocks2 = sampler2.stop()
+    clocks_serial = clocks
     if clocks2.get("sm_mhz"):
-        clocks = clocks2
+        clocks = clocks2                      # the headline (pipelined) region
     total_ms = pa.elapsed_time(pb)
     t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -312,7 +335,7 @@ def main():
            "gpu_launches": int(n1 - n0), "ms_per_decode_token": dec_ms / T_NEW, "roofline": roof, "roofline_gemm": roof_gemm,
            "e2e_gray_u8": {"value": e2e_gray, "unit": "images/s", "h2d_bytes_per_step": B * 200 * 200, "d2h_bytes_per_step": B * (T1 * 4 + C * 4),
                            "note": "generate_stream over raw u8 200x200 host images; normalisation by mdc_preprocess_gray on the device"},
-           "serial": {"value": value_serial, "ms_per_step": serial_ms / args.steps, "e2e": e2e_serial,
+           "serial": {"value": value_serial, "ms_per_step": serial_ms / args.steps, "e2e": e2e_serial, "clocks": clocks_serial,
                       "note": "one batch at a time (generate_tokens / generate), 256 MiB L2 flush between steps (untimed)"}}
     if not args.no_cpu_baseline and world == 1:          # reported on rank 0 at N = 1 only; `--impl reference` is the arm for every N
         out["cpu_baseline"], _ = cpu_reference_arm(1, 1)
