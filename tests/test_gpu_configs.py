@@ -111,3 +111,32 @@ def test_config5_long_decode_topk_paged_kv_and_iou(restore_cfg):
     gt[torch.rand(B, 5, generator=gg) < 0.3] = 0                      # pad_sequence-style zero rows
     got = torch.tensor(M.calculate_batch_max_iou(boxes, gt.to(DEV)))
     assert torch.equal(got, O.batch_max_iou(want_boxes, gt).flatten())
+
+
+def test_config_T_trained_geometry_runs_on_the_generic_kernels():
+    """The geometry the reference was actually trained with (trail_01.py:158-160 / inference_code_craeted_me_gpt.py:128-130: dim 1024,
+    8 heads x 128, 8 layers, vocab 332) is outside the fused cluster kernel's shape (dim 256); it must run -- and match -- on the
+    generic decode kernels: fp32 tokens exact, bf16 logits within the contract."""
+    cases.product_cfg(100)
+    torch.manual_seed(4)
+    enc = M.Encoder(model_name=cases.VIT, pretrained=False, out_dim=1024)
+    dec = M.Decoder(332, 196, 1024, 8, 8)
+    model = M.EncoderDecoder(enc, dec).eval()
+    g = torch.Generator().manual_seed(9)
+    with torch.no_grad():
+        for k, p in model.named_parameters():
+            if k.endswith("gamma"):
+                p.copy_(torch.rand(p.shape, generator=g) + 0.5)
+    sd = cases.state_dict_of(model)
+    cfg = O.OracleCfg(max_len=100, dec_heads=8, out_dim=1024)
+    x = cases.images(2, seed=61)
+    want_toks, _, want_logits = O.generate(sd, x, cfg, max_len=10, return_logits=True)
+    model.to(DEV).set_precision("fp32")
+    toks, _, logits = model.generate_tokens(x.to(DEV), 10, return_logits=True)
+    e32 = (logits.cpu() - want_logits).abs().max().item()
+    assert torch.equal(toks.cpu().long(), want_toks) and e32 < 5e-4, e32
+    model.set_precision("bf16")
+    _, _, logits_b = model.generate_tokens(x.to(DEV), 10, return_logits=True)
+    eb = (logits_b.cpu() - want_logits).abs().max().item()
+    print(f"config T: fp32 logits max|d| = {e32:.2e}; bf16 max|d| = {eb:.2e}, cosine = {G.cos(logits_b.cpu(), want_logits):.6f}")
+    assert eb <= 2e-2 and G.cos(logits_b.cpu(), want_logits) >= 0.999
