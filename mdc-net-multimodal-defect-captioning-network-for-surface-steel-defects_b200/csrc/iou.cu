@@ -25,7 +25,8 @@ __device__ __forceinline__ Pair pair_terms(float4 p, float4 g) {
   return r;
 }
 
-__device__ __forceinline__ float score(int mode, float4 p, float4 g) {
+template <int mode>
+__device__ __forceinline__ float score(float4 p, float4 g) {
   Pair t = pair_terms(p, g);
   if (mode == MDC_IOU_EPS) return __fdiv_rn(t.inter, __fadd_rn(t.uni, 1e-6f));
   float iou = __fdiv_rn(t.inter, t.uni);
@@ -40,32 +41,46 @@ __device__ __forceinline__ float score(int mode, float4 p, float4 g) {
 
 constexpr int IOU_THREADS = 256;
 
-__global__ void __launch_bounds__(IOU_THREADS) iou_batch_kernel(int mode, const float4* __restrict__ pred,
+// I = index type: 32-bit when B*N*M < 2^31 (the kernel is issue-bound, and three 64-bit integer divisions per thread were a third
+// of its instructions), 64-bit otherwise
+template <int MODE, typename I>
+__global__ void __launch_bounds__(IOU_THREADS) iou_batch_kernel(const float4* __restrict__ pred,
                                                                 const float4* __restrict__ gt, int B, int N, int M,
-                                                                float* __restrict__ iou_out, float* __restrict__ max_out) {
-  extern __shared__ float4 sgt[];   // GT boxes of the images this block touches
-  const int64_t total = (int64_t)B * N;
-  const int64_t first = (int64_t)blockIdx.x * IOU_THREADS;
+                                                                float* __restrict__ iou_out, float* __restrict__ max_out, int n_gt_cap) {
+  extern __shared__ float4 sgt[];   // GT boxes of the images this block touches, then the block's 256 x M outputs
+  float* sout = reinterpret_cast<float*>(sgt + n_gt_cap);
+  const I total = (I)B * N;
+  const I first = (I)blockIdx.x * IOU_THREADS;
   const int img0 = (int)(first / N);
-  const int64_t last = min(first + IOU_THREADS, total) - 1;
+  const I last = min(first + (I)IOU_THREADS, total) - 1;
   const int img1 = (int)(last / N);
   const int n_gt = (img1 - img0 + 1) * M;
-  for (int i = threadIdx.x; i < n_gt; i += IOU_THREADS) sgt[i] = __ldg(gt + (int64_t)img0 * M + i);
+  for (int i = threadIdx.x; i < n_gt; i += IOU_THREADS) sgt[i] = __ldg(gt + (I)img0 * M + i);
   __syncthreads();
-  int64_t idx = first + threadIdx.x;
-  if (idx >= total) return;
-  const int img = (int)(idx / N);
-  const float4 p = __ldg(pred + idx);
-  const float4* g = sgt + (img - img0) * M;
-  float best = -INFINITY;
-  bool any_nan = false;
-  for (int j = 0; j < M; ++j) {
-    float v = score(mode, p, g[j]);
-    if (iou_out) iou_out[idx * M + j] = v;
-    any_nan |= isnan(v);
-    best = fmaxf(best, v);
+  I idx = first + threadIdx.x;
+  if (idx < total) {
+    const int img = (int)(idx / N);
+    const float4 p = __ldg(pred + idx);
+    const float4* g = sgt + (img - img0) * M;
+    float best = -INFINITY;
+    bool any_nan = false;
+#pragma unroll 4
+    for (int j = 0; j < M; ++j) {
+      const float v = score<MODE>(p, g[j]);
+      sout[threadIdx.x * M + j] = v;
+      any_nan |= isnan(v);
+      best = fmaxf(best, v);
+    }
+    if (max_out) max_out[idx] = any_nan ? NAN : best;   // torch.max propagates NaN
   }
-  if (max_out) max_out[idx] = any_nan ? NAN : best;   // torch.max propagates NaN
+  if (iou_out) {
+    // the block's outputs are one contiguous range of the (B,N,M) tensor: written back with consecutive lanes on consecutive floats
+    // (M-strided 4-byte stores cost 17 L2 sectors per warp store)
+    __syncthreads();
+    const int n_out = (int)(min(first + (I)IOU_THREADS, total) - first) * M;
+    float* dst = iou_out + first * M;
+    for (int i = threadIdx.x; i < n_out; i += IOU_THREADS) dst[i] = sout[i];
+  }
 }
 
 // giou_loss_with_scores: one warp per image
@@ -85,7 +100,7 @@ __global__ void giou_loss_kernel(const float4* __restrict__ pred, const float4* 
     int i = e / M, j = e % M;
     float4 a = p[i], b = g[j];
     bool ok = ((((a.x + a.y) + a.z) + a.w) != 0.f) && ((((b.x + b.y) + b.z) + b.w) != 0.f);
-    float v = ok ? score(MDC_IOU_GIOU, a, b) : 0.f;
+    float v = ok ? score<MDC_IOU_GIOU>(a, b) : 0.f;
     if (giou_out) giou_out[(int64_t)img * N * M + e] = v;
     if (valid_out) valid_out[(int64_t)img * N * M + e] = ok ? 1 : 0;
     sum += v;
@@ -120,10 +135,25 @@ extern "C" int mdc_iou_batch(mdc_ctx* ctx, int mode, const float* pred, const fl
   int64_t total = (int64_t)B * N;
   int grid = (int)((total + IOU_THREADS - 1) / IOU_THREADS);
   int imgs_per_block = IOU_THREADS / (N > 0 ? N : 1) + 2;
-  size_t smem = (size_t)imgs_per_block * M * sizeof(float4);
+  const int n_gt_cap = imgs_per_block * M;
+  size_t smem = (size_t)n_gt_cap * sizeof(float4) + (size_t)IOU_THREADS * M * sizeof(float);
   MDC_CHECK_ARG(smem <= 200 * 1024);
-  MDC_ENSURE_SMEM(iou_batch_kernel, smem);
-  iou_batch_kernel<<<grid, IOU_THREADS, smem, (cudaStream_t)stream>>>(mode, (const float4*)pred, (const float4*)gt, B, N, M, iou_out, max_out);
+  const bool small = total * M < ((int64_t)1 << 31) - IOU_THREADS * (int64_t)M;
+#define MDC_IOU_LAUNCH(MODE_)                                                                                                                        \
+  if (small) {                                                                                                                                       \
+    MDC_ENSURE_SMEM((iou_batch_kernel<MODE_, int>), smem);                                                                                           \
+    iou_batch_kernel<MODE_, int><<<grid, IOU_THREADS, smem, (cudaStream_t)stream>>>((const float4*)pred, (const float4*)gt, B, N, M, iou_out, max_out, n_gt_cap); \
+  } else {                                                                                                                                           \
+    MDC_ENSURE_SMEM((iou_batch_kernel<MODE_, int64_t>), smem);                                                                                       \
+    iou_batch_kernel<MODE_, int64_t><<<grid, IOU_THREADS, smem, (cudaStream_t)stream>>>((const float4*)pred, (const float4*)gt, B, N, M, iou_out, max_out, n_gt_cap); \
+  }
+  switch (mode) {
+    case MDC_IOU_EPS: MDC_IOU_LAUNCH(MDC_IOU_EPS) break;
+    case MDC_IOU_PLAIN: MDC_IOU_LAUNCH(MDC_IOU_PLAIN) break;
+    case MDC_IOU_NAN0: MDC_IOU_LAUNCH(MDC_IOU_NAN0) break;
+    default: MDC_IOU_LAUNCH(MDC_IOU_GIOU) break;
+  }
+#undef MDC_IOU_LAUNCH
   MDC_LAUNCH_CHECK(ctx); return 0;
 }
 

@@ -13,3 +13,5 @@ ncu --set full --clock-control none --import-source on -k regex:gemm_tc_kernel -
 ncu --set full --clock-control none --import-source on -k regex:attn_tc_kernel -c 1 -f -o $o/${tag}_attn python bench.py --profile > $o/${tag}_ncu_attn.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:decode_fused_kernel -c 1 -f -o $o/${tag}_decode python tools/decode_probe.py 64 99 > $o/${tag}_ncu_decode.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:layernorm_rows_kernel -c 1 -f -o $o/${tag}_ln python bench.py --profile > $o/${tag}_ncu_ln.log 2>&1
+python tools/iou_probe.py > $o/${tag}_iou.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:iou_batch_kernel -c 1 -f -o $o/${tag}_iou python tools/iou_probe.py 262144 1 > $o/${tag}_ncu_iou.log 2>&1
