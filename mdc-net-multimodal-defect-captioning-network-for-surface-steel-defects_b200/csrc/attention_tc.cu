@@ -35,35 +35,24 @@ __device__ __forceinline__ void cp_async16(uint32_t smem_dst, const void* gsrc) 
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_dst), "l"(gsrc) : "memory");
 }
 
-// MAXT = 416 (197-token strips: 13 warps) is compiled for TWO CTAs per SM (<= 72 registers), so one CTA's K/V fetch overlaps the
-// other's MMAs -- at 80 registers a 416-thread CTA is 512 registers over half the file and the SM runs the two phases strictly
-// back to back.  MAXT = 1024 serves strips of up to 512 tokens.
-template <int MAXT, int MINB>
-__global__ void __launch_bounds__(MAXT, MINB)
-attn_tc_kernel(const bf16* __restrict__ qkv, int64_t ld, bf16* __restrict__ out, int64_t ldo, int S, int H, float scale_log2e) {
+// One CTA = one (strip, head, chunk of up to 208 queries): 13 warps x 16 queries, compiled for TWO CTAs per SM (<= 72 registers), so
+// one CTA's K/V fetch overlaps the other's MMAs.  Keys are consumed in chunks of up to 208 staged in shared memory (a 197-token
+// ViT strip is one chunk and one query chunk -- the common case; a 1025-token strip of a 512x512 input is 5 x 5), the online
+// softmax state lives in registers across the chunks.
+constexpr int QCHUNK = 208;
+template <bool MULTI>      // MULTI = false: the strip is one key chunk and one query chunk (compile-time single trip)
+__global__ void __launch_bounds__(416, 2)
+attn_tc_kernel(const bf16* __restrict__ qkv, int64_t ld, bf16* __restrict__ out, int64_t ldo, int S, int H, float scale_log2e, int KC) {
   extern __shared__ __align__(128) uint8_t smem[];
-  const int rows = ((S + 15) / 16) * 16;
-  uint8_t* Ks = smem; uint8_t* Vs = smem + (size_t)rows * 128;
+  uint8_t* Ks = smem; uint8_t* Vs = smem + (size_t)KC * 128;
   const int strip = blockIdx.y, head = blockIdx.x;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const bf16* base = qkv + (int64_t)strip * S * ld + head * HD;
   const int D = H * HD;
-  // K / V panels: 16-byte asynchronous copies straight into the swizzled rows (no register staging: every copy of the CTA is in
-  // flight at once, and the Q fragment loads below join them)
   const uint32_t ks_u32 = (uint32_t)__cvta_generic_to_shared(Ks), vs_u32 = (uint32_t)__cvta_generic_to_shared(Vs);
-  for (int i = tid; i < rows * 8; i += blockDim.x) {
-    const int r = i >> 3, c = i & 7;
-    if (r < S) {
-      cp_async16(ks_u32 + swz(r, c), base + (int64_t)r * ld + D + c * 8);
-      cp_async16(vs_u32 + swz(r, c), base + (int64_t)r * ld + 2 * D + c * 8);
-    } else {
-      *reinterpret_cast<uint4*>(Ks + swz(r, c)) = make_uint4(0, 0, 0, 0);
-      *reinterpret_cast<uint4*>(Vs + swz(r, c)) = make_uint4(0, 0, 0, 0);
-    }
-  }
-  asm volatile("cp.async.commit_group;" ::: "memory");
   // Q fragments straight from global memory (A operand layout of m16n8k16)
-  const int q0 = warp * 16, r0 = q0 + (lane >> 2), r1 = r0 + 8;
+  const int q0 = blockIdx.z * QCHUNK + warp * 16, r0 = q0 + (lane >> 2), r1 = r0 + 8;
+  const bool active = q0 < S;           // warps past the strip's end only help staging
   uint32_t qa[4][4];
 #pragma unroll
   for (int ks = 0; ks < 4; ++ks) {
@@ -73,17 +62,30 @@ attn_tc_kernel(const bf16* __restrict__ qkv, int64_t ld, bf16* __restrict__ out,
     qa[ks][2] = r0 < S ? *reinterpret_cast<const uint32_t*>(base + (int64_t)r0 * ld + k + 8) : 0u;
     qa[ks][3] = r1 < S ? *reinterpret_cast<const uint32_t*>(base + (int64_t)r1 * ld + k + 8) : 0u;
   }
-  asm volatile("cp.async.wait_group 0;" ::: "memory");
-  __syncthreads();
-  if (q0 >= S) return;
   const uint32_t ks_base = ks_u32, vs_base = vs_u32;
   float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
   float o[8][4];
 #pragma unroll
   for (int i = 0; i < 8; ++i) { o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f; }
-  const int nblk = rows / 16;
+  for (int kc0 = 0; kc0 < (MULTI ? S : 1); kc0 += KC) {
+  // K / V chunk: 16-byte asynchronous copies straight into the swizzled rows (no register staging: every copy of the CTA is in
+  // flight at once); rows past the strip's end are zero (they meet p = 0, so they must be finite)
+  if (kc0 > 0) __syncthreads();                // every warp is done with the previous chunk
+  for (int i = tid; i < KC * 8; i += blockDim.x) {
+    const int r = i >> 3, c = i & 7, gr = kc0 + r;
+    if (gr < S) {
+      cp_async16(ks_u32 + swz(r, c), base + (int64_t)gr * ld + D + c * 8);
+      cp_async16(vs_u32 + swz(r, c), base + (int64_t)gr * ld + 2 * D + c * 8);
+    } else {
+      *reinterpret_cast<uint4*>(Ks + swz(r, c)) = make_uint4(0, 0, 0, 0);
+      *reinterpret_cast<uint4*>(Vs + swz(r, c)) = make_uint4(0, 0, 0, 0);
+    }
+  }
+  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+  const int nblk = active ? (min(KC, S - kc0) + 15) / 16 : 0;
   for (int kb = 0; kb < nblk; ++kb) {
-    const int key0 = kb * 16;
+    const int lk0 = kb * 16, key0 = kc0 + lk0;
     // ---- S = Q K^T for 16 keys: two n-tiles (keys key0..+7, key0+8..+15) ------------------------------------
     float s[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
 #pragma unroll
@@ -91,7 +93,7 @@ attn_tc_kernel(const bf16* __restrict__ qkv, int64_t ld, bf16* __restrict__ out,
 #pragma unroll
       for (int kp = 0; kp < 2; ++kp) {        // two k-steps (32 dims) per ldmatrix.x4
         // matrices: (dims 32kp..+7), (+8..15), (+16..23), (+24..31) of keys key0+8nt+0..7
-        const int krow = key0 + nt * 8 + (lane & 7), chunk = kp * 4 + (lane >> 3);
+        const int krow = lk0 + nt * 8 + (lane & 7), chunk = kp * 4 + (lane >> 3);
         uint32_t b0, b1, b2, b3;
         ldsm_x4(b0, b1, b2, b3, ks_base + swz(krow, chunk));
         mma16816(s[nt], qa[2 * kp], b0, b1);
@@ -132,13 +134,15 @@ attn_tc_kernel(const bf16* __restrict__ qkv, int64_t ld, bf16* __restrict__ out,
 #pragma unroll
     for (int dp = 0; dp < 4; ++dp) {           // two 8-wide dim tiles per ldmatrix.x4.trans
       // matrices: (keys key0..+7, dims 16dp..+7), (keys +8..15, same dims), (keys key0..+7, dims 16dp+8..), (keys +8..15, dims 16dp+8..)
-      const int vrow = key0 + (lane & 7) + ((lane >> 3) & 1) * 8, chunk = dp * 2 + (lane >> 4);
+      const int vrow = lk0 + (lane & 7) + ((lane >> 3) & 1) * 8, chunk = dp * 2 + (lane >> 4);
       uint32_t b0, b1, b2, b3;
       ldsm_x4_trans(b0, b1, b2, b3, vs_base + swz(vrow, chunk));
       mma16816(o[2 * dp], pa, b0, b1);
       mma16816(o[2 * dp + 1], pa, b2, b3);
     }
   }
+  }
+  if (!active) return;
   l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
   l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
   const float i0 = 1.0f / l0, i1 = 1.0f / l1;
@@ -152,21 +156,23 @@ attn_tc_kernel(const bf16* __restrict__ qkv, int64_t ld, bf16* __restrict__ out,
 
 }  // namespace
 
-int attn_tc_supported(int strip_len, int head_dim) { return head_dim == HD && strip_len >= 1 && strip_len <= 512; }
+int attn_tc_supported(int strip_len, int head_dim) { return head_dim == HD && strip_len >= 1; }
 
 int attn_tc_launch(mdc_ctx* ctx, const void* qkv, int64_t ld, void* out, int64_t ldo, int n_strips, int strip_len, int heads,
                    int head_dim, float scale, cudaStream_t s) {
   MDC_CHECK_ARG(head_dim == HD && ld % 8 == 0 && ldo % 2 == 0);
   MDC_CHECK_ARG(((uintptr_t)qkv & 15) == 0 && ((uintptr_t)out & 3) == 0);
   const int rows = ((strip_len + 15) / 16) * 16;
-  const size_t smem = (size_t)rows * 128 * 2;
-  dim3 grid(heads, n_strips), block(32 * (rows / 16));
-  if (block.x <= 416) {
-    MDC_ENSURE_SMEM((attn_tc_kernel<416, 2>), smem);
-    attn_tc_kernel<416, 2><<<grid, block, smem, s>>>((const bf16*)qkv, ld, (bf16*)out, ldo, strip_len, heads, scale * 1.4426950408889634f);
+  const int KC = rows < QCHUNK ? rows : QCHUNK;                 // keys staged per chunk
+  const int q_chunks = (strip_len + QCHUNK - 1) / QCHUNK;
+  const size_t smem = (size_t)KC * 128 * 2;
+  dim3 grid(heads, n_strips, q_chunks), block(32 * (KC / 16));
+  if (q_chunks == 1) {
+    MDC_ENSURE_SMEM(attn_tc_kernel<false>, smem);
+    attn_tc_kernel<false><<<grid, block, smem, s>>>((const bf16*)qkv, ld, (bf16*)out, ldo, strip_len, heads, scale * 1.4426950408889634f, KC);
   } else {
-    MDC_ENSURE_SMEM((attn_tc_kernel<1024, 1>), smem);
-    attn_tc_kernel<1024, 1><<<grid, block, smem, s>>>((const bf16*)qkv, ld, (bf16*)out, ldo, strip_len, heads, scale * 1.4426950408889634f);
+    MDC_ENSURE_SMEM(attn_tc_kernel<true>, smem);
+    attn_tc_kernel<true><<<grid, block, smem, s>>>((const bf16*)qkv, ld, (bf16*)out, ldo, strip_len, heads, scale * 1.4426950408889634f, KC);
   }
   MDC_LAUNCH_CHECK(ctx);
   return 0;

@@ -83,7 +83,7 @@ def test_layernorm(dtype):
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("cfg", [(3, 197, 8, 64, 0.125), (2, 99, 8, 32, 0.125), (28, 14, 8, 64, 0.125), (2, 17, 2, 128, 0.3),
-                                 (1, 1025, 8, 64, 0.125), (5, 1, 8, 32, 0.125)])
+                                 (1, 1025, 8, 64, 0.125), (2, 300, 8, 64, 0.125), (2, 208, 8, 64, 0.125), (2, 209, 8, 64, 0.125), (5, 1, 8, 32, 0.125)])
 def test_strip_attention(dtype, cfg):
     n_strips, n, H, hd, scale = cfg
     qkv = _mk((n_strips * n, 3 * H * hd), dtype, 4)
