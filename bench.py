@@ -147,7 +147,7 @@ def main():
     cfg = {"workload": f"MDC-Net config P (deit3_medium 224 + 6-layer dim-256 decoder, V=305), batch {B_PER_GPU}/GPU, "
                        f"{T_NEW} greedy tokens, synthetic 200x200 gray -> 3x224x224", "global_batch": B_PER_GPU * world,
            "new_tokens": T_NEW, "parallelism": f"dp{world}",
-           "pipeline": "batch pipeline (GenerationPipeline / generate_stream): 4 plans, 3 decode streams at 8 images per 8-SM cluster + 1 encoder stream; steps overlap, every step does all of its work inside the timed region",
+           "pipeline": "batch pipeline (GenerationPipeline / generate_stream): 6 plans, 4 decode streams at 16 images per 8-SM cluster + 1 encoder stream; steps overlap, every step does all of its work inside the timed region",
            "l2": "no flush inside the pipelined region: 4 rotating input batches (154 MB) and a per-step working set of ~330 MB both exceed the 126 MB L2"}
 
     if args.impl == "reference":

@@ -198,9 +198,10 @@ typedef struct mdc_decode_state {
   const float* x_override;          /* optional (B, n, dim) pre-computed input embeddings incl. pos (axial path) */
   int32_t x_override_ld;            /* n */
   void* scratch; size_t scratch_bytes;
-  int32_t images_per_cluster;       /* 0 = spread the batch over as many 8-SM clusters as fit (lowest latency of ONE batch); 1..8 =
+  int32_t images_per_cluster;       /* 0 = spread the batch over as many 8-SM clusters as fit (lowest latency of ONE batch); 1..16 =
                                        at least that many images per cluster, i.e. fewer SMs per batch, so that several batches in
-                                       flight (pipeline.py) share the GPU.  Does not change results. */
+                                       flight (pipeline.py) share the GPU; more than 8 selects the kernel instantiation with two
+                                       8-image column blocks per cluster pass.  Does not change results (bitwise). */
 } mdc_decode_state;
 
 size_t mdc_decode_workspace_bytes(const mdc_model* m, int B);

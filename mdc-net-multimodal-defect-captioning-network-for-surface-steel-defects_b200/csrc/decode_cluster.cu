@@ -3,18 +3,19 @@
 //  "no collective inside the decode loop" -- here not even a kernel boundary).
 //
 // Decomposition (model width 256, 8 heads x 32, FFN 2048 -- the configuration inference_p.py:126-129 builds):
-//   * a thread-block CLUSTER of 8 CTAs owns a group of G <= 8 images for the entire loop; clusters never talk to
-//     each other, so there is no grid-wide synchronisation at all.  Further groups are processed back to back.
+//   * a thread-block CLUSTER of 8 CTAs owns a group of G <= 8 images (G <= 16 in the two-column-block instantiation the
+//     batch pipeline uses) for the entire loop; clusters never talk to each other, so there is no grid-wide
+//     synchronisation at all.  Further groups are processed back to back.
 //   * inside a cluster CTA r owns attention head r and 1/8 of every projection: in-proj rows of head r (q,k,v),
 //     out-proj / cross-q / cross-out rows [32r,32r+32), FFN1 hidden units [256r,256r+256), FFN2 as a K-split over
 //     the same hidden units, vocabulary rows [40r,40r+40).
 //   * everything that is read from HBM/L2 -- weights, the paged self-KV cache, the resident cross-K/V -- is fetched
-//     by a dedicated PRODUCER WARP with TMA (cp.async.bulk.tensor, hardware 128B/64B swizzle) into a 4 x 32 KB
-//     shared-memory ring guarded by full/empty mbarriers; the producer walks the static stage schedule and runs
+//     by a dedicated PRODUCER WARP with TMA (cp.async.bulk.tensor, hardware 128B/64B swizzle) into a 5 x 32 KB (4 x 32 KB
+//     with 16 images) shared-memory ring guarded by full/empty mbarriers; the producer walks the static stage schedule and runs
 //     ahead of the 8 consumer warps across phase, layer and step boundaries.
 //   * projections run on the tensor cores with the roles swapped: the WEIGHT rows are the MMA M dimension
-//     (mma.sync m16n8k16, A fragments by ldmatrix from the swizzled TMA tile), the G <= 8 images are the N = 8
-//     dimension, so no MMA lane is wasted on padding.  The decode-loop weights are IEEE fp16 (mdc_dims.dec_loop_dtype: same
+//     (mma.sync m16n8k16, A fragments by ldmatrix from the swizzled TMA tile), the images are the N = 8
+//     dimension (one or two column blocks per weight fragment), so no MMA lane is wasted on padding.  The decode-loop weights are IEEE fp16 (mdc_dims.dec_loop_dtype: same
 //     bytes as bf16, 8x smaller rounding) and so are the projection operands (activations rounded to fp16: 11 significant bits).
 //     Attention keeps bf16 K/V (the caches) with bf16 queries and probabilities.
 //   * activations (a few KB) are exchanged through DISTRIBUTED SHARED MEMORY, push style: the producer of a slice
@@ -43,43 +44,56 @@ constexpr int FFN = 2048;
 constexpr int FS = FFN / CS;       // hidden units per CTA (256)
 constexpr int NCT = 256;           // consumer threads (8 warps)
 constexpr int NT = NCT + 32;       // + producer warp
-constexpr int GM = 8;              // max images per cluster pass (the MMA N dimension)
-constexpr int XP = DM + 8;         // bf16 elements per padded activation row (528 B: conflict-free ldmatrix)
+constexpr int XP = DM + 8;         // fp16 elements per padded activation row (528 B: conflict-free ldmatrix)
 constexpr int STAGE_BYTES = 32768;
-constexpr int NS = 5;              // ring stages (160 KB in flight: +1.2 % over 4, same-box A/B)
 constexpr int VSL = 40;            // vocab rows per CTA; 8*40 = 320 >= V
 constexpr int PSTR = 36;           // floats per attention partial: m, l, -, -, o[32] (o is 16-byte aligned)
 constexpr int NPART = 9;           // attention partials per image: one per warp (interleaved key tiles) + the step's own key
+constexpr int NS_MAX = 5;
 
-// ---- shared memory map (bytes from the 1024-aligned base) ---------------------------------------------------
-constexpr int OFF_RING = 0;
-constexpr int ACT_BYTES = GM * XP * 2;                     // 4224
-constexpr int OFF_XH = OFF_RING + NS * STAGE_BYTES;        // LN output (fp16 projection operand)
-constexpr int OFF_OH = OFF_XH + ACT_BYTES;                 // gathered attention output (written by peers)
-constexpr int OFF_FH = OFF_OH + ACT_BYTES;                 // own FFN hidden slice
-constexpr int OFF_XRES = OFF_FH + ACT_BYTES;               // [GM][DM] f32 residual stream
-constexpr int OFF_YRECV = OFF_XRES + GM * DM * 4;          // [GM][DM] f32 all-gathered projection output (peers write)
-constexpr int OFF_F2RECV = OFF_YRECV + GM * DM * 4;        // [CS src][GM][32] f32 FFN2 partial sums (peers write)
-constexpr int OFF_QS = OFF_F2RECV + CS * GM * 32 * 4;      // [GM][32] f32 scaled query of the own head
-constexpr int OFF_KNEW = OFF_QS + GM * 32 * 4;             // [GM][32] f32 this step's key (bf16-rounded)
-constexpr int OFF_VNEW = OFF_KNEW + GM * 32 * 4;
-constexpr int OFF_YTMP = OFF_VNEW + GM * 32 * 4;           // [GM][32] f32 own slice of a projection before the push
-constexpr int OFF_QH = OFF_YTMP + GM * 32 * 4;             // [GM][32] bf16 scaled query (MMA operand)
-constexpr int OFF_PART = OFF_QH + GM * 32 * 2;             // [GM][NPART][PSTR] f32 attention partials
-constexpr int OFF_LRECV = OFF_PART + GM * NPART * PSTR * 4;   // [CS src][VSL] f32 logits of the image this CTA selects for
-constexpr int OFF_SEL = OFF_LRECV + CS * VSL * 4;          // select scratch: 320 + 512 floats
-constexpr int OFF_TOK = OFF_SEL + (CS * VSL + 512) * 4;    // [2][GM] int32 (double buffered by step parity)
-constexpr int OFF_PAGES = OFF_TOK + 2 * GM * 4;            // [GM][32] int32
-constexpr int OFF_PADF = OFF_PAGES + GM * 32 * 4;          // [GM][256] u8
-constexpr int OFF_HASPAD = OFF_PADF + GM * 256;            // [GM] int32: any PAD token among the keys so far
-constexpr int OFF_BARS = OFF_HASPAD + GM * 4;              // mbarriers
-constexpr int NBARS = 2 * NS + 5;
-constexpr int SMEM_USED = OFF_BARS + NBARS * 8;
-constexpr int SMEM_BYTES = SMEM_USED + 1024;               // + alignment slack
-static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
-static_assert(OFF_XH % 16 == 0 && OFF_XRES % 16 == 0 && OFF_BARS % 8 == 0, "alignment");
+// ---- shared memory map (bytes from the 1024-aligned base), per instantiation -------------------------------------
+// NB = 8-image column blocks per cluster pass: NB = 1 (up to 8 images per cluster: lowest latency, the serial path) or NB = 2
+// (up to 16 images: every weight fragment a warp loads feeds two MMA column blocks and every exchange carries twice the
+// images -- less SM-time per image, used by the batch pipeline).  With 16 images the per-group buffers double, so the ring
+// has 4 stages instead of 5, the FFN2 receive buffer shares its bytes with the attention partials and the select scratch
+// with the q/k staging (disjoint phases, see the ordering notes at the uses).
+template <int NB>
+struct Lay {
+  static constexpr int GMX = 8 * NB;                             // max images per cluster pass
+  static constexpr int NS = NB == 1 ? 5 : 4;                     // ring stages (160 KB in flight at NB = 1: +1.2 % over 4, same-box A/B)
+  static constexpr int ACT_BYTES = GMX * XP * 2;
+  static constexpr int OFF_RING = 0;
+  static constexpr int OFF_XH = OFF_RING + NS * STAGE_BYTES;      // LN output (fp16 projection operand)
+  static constexpr int OFF_OH = OFF_XH + ACT_BYTES;               // gathered attention output (written by peers)
+  static constexpr int OFF_FH = OFF_OH + ACT_BYTES;               // own FFN hidden slice
+  static constexpr int OFF_XRES = OFF_FH + ACT_BYTES;             // [GMX][DM] f32 residual stream
+  static constexpr int OFF_YRECV = OFF_XRES + GMX * DM * 4;       // [GMX][DM] f32 all-gathered projection output (peers write)
+  static constexpr int OFF_PART = OFF_YRECV + GMX * DM * 4;       // [GMX][NPART][PSTR] f32 attention partials
+  static constexpr int PART_BYTES = GMX * NPART * PSTR * 4;
+  static constexpr int F2_BYTES = CS * GMX * 32 * 4;              // [CS src][GMX][32] f32 FFN2 partial sums (peers write)
+  static constexpr int OFF_F2RECV = NB == 1 ? OFF_PART + PART_BYTES : OFF_PART;
+  static constexpr int OFF_QS = NB == 1 ? OFF_F2RECV + F2_BYTES : OFF_PART + (PART_BYTES > F2_BYTES ? PART_BYTES : F2_BYTES);   // [GMX][32] f32 scaled query of the own head
+  static constexpr int OFF_KNEW = OFF_QS + GMX * 32 * 4;          // [GMX][32] f32 this step's key (bf16-rounded)
+  static constexpr int OFF_VNEW = OFF_KNEW + GMX * 32 * 4;
+  static constexpr int OFF_YTMP = OFF_VNEW + GMX * 32 * 4;        // [GMX][32] f32 own slice of a projection before the push
+  static constexpr int OFF_QH = OFF_YTMP + GMX * 32 * 4;          // [GMX][32] bf16 scaled query (MMA A operand)
+  static constexpr int OFF_LRECV = OFF_QH + GMX * 32 * 2;         // [NB][CS src][VSL] f32 logits of the images this CTA selects for
+  static constexpr int SEL_BYTES = (CS * VSL + 512) * 4;          // select scratch: 320 + 512 floats
+  static constexpr int OFF_SEL = NB == 1 ? OFF_LRECV + NB * CS * VSL * 4 : OFF_QS;
+  static constexpr int OFF_TOK = NB == 1 ? OFF_SEL + SEL_BYTES : OFF_LRECV + NB * CS * VSL * 4;    // [2][GMX] int32 (double buffered by step parity)
+  static constexpr int OFF_PAGES = OFF_TOK + 2 * GMX * 4;         // [GMX][32] int32
+  static constexpr int OFF_PADF = OFF_PAGES + GMX * 32 * 4;       // [GMX][256] u8
+  static constexpr int OFF_HASPAD = OFF_PADF + GMX * 256;         // [GMX] int32: any PAD token among the keys so far
+  static constexpr int OFF_BARS = OFF_HASPAD + GMX * 4;           // mbarriers
+  static constexpr int NBARS = 2 * NS_MAX + 5;
+  static constexpr int SMEM_USED = OFF_BARS + NBARS * 8;
+  static constexpr int SMEM_BYTES = SMEM_USED + 1024;             // + alignment slack
+  static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
+  static_assert(OFF_XH % 16 == 0 && OFF_XRES % 16 == 0 && OFF_PART % 16 == 0 && OFF_QS % 16 == 0 && OFF_BARS % 8 == 0, "alignment");
+  static_assert(3 * GMX * 32 * 4 >= SEL_BYTES || NB == 1, "select scratch must fit the q/k/v staging it shares");
+};
 
-enum { BAR_FULL = 0, BAR_EMPTY = NS, BAR_O = 2 * NS, BAR_Y, BAR_F2, BAR_LG, BAR_TOK };
+enum { BAR_FULL = 0, BAR_EMPTY = NS_MAX, BAR_O = 2 * NS_MAX, BAR_Y, BAR_F2, BAR_LG, BAR_TOK, BAR_COUNT };
 
 struct __align__(64) FusedParams {
   CUtensorMap m_in[8], m_so[8], m_ca[8], m_co[8], m_f1[8], m_f2[8];
@@ -171,31 +185,37 @@ __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
 }
 
 // One 16-row tile of a projection with the weights as the M operand:
-//   acc[0..3] = D[m0+g][img 2q], D[m0+g][2q+1], D[m0+g+8][2q], D[m0+g+8][2q+1]   (g = lane/4, q = lane%4)
+//   acc[nb][0..3] = D[m0+g][img], D[m0+g][img+1], D[m0+g+8][img], D[m0+g+8][img+1], img = 8nb + 2q   (g = lane/4, q = lane%4)
 // wblk: shared address of the TMA row block [4 k-blocks][R rows][128 B] (SWIZZLE_128B), fp16 weights; bh: fp16 activations
 // [8 images][XP].  The fragment loads run two iterations ahead of the MMAs (the asm statements are volatile, so program order
 // IS issue order: without the explicit skew every iteration pays the full ldmatrix latency; the buffer of iteration i is
 // refilled for iteration i+2 as soon as its MMAs are issued); four accumulator chains.
-template <int R>
-__device__ __forceinline__ void mma_mtile(uint32_t wblk, int m0, uint32_t bh, float* acc) {
+template <int R, int NB>
+__device__ __forceinline__ void mma_mtile(uint32_t wblk, int m0, uint32_t bh, float (&acc)[NB][4]) {
   const int lane = threadIdx.x & 31;
   const int row = m0 + (lane & 7) + ((lane >> 3) & 1) * 8, csel = lane >> 4, sw = lane & 7;
   const uint32_t a_base = wblk + row * 128;
   const uint32_t b_base = bh + (lane & 7) * (XP * 2) + (lane >> 3) * 16;
-  float c[4][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}, {0, 0, 0, 0}, {0, 0, 0, 0}};
-  uint32_t a0[2][4], a1[2][4], xb[2][4];
+  float c[NB][4][4];
+#pragma unroll
+  for (int nb = 0; nb < NB; ++nb)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { c[nb][j][0] = c[nb][j][1] = c[nb][j][2] = c[nb][j][3] = 0.f; }
+  uint32_t a0[2][4], a1[2][4], xb[2][NB][4];
 #define MDC_MTILE_LOAD(I)                                                                                      \
   {                                                                                                            \
     constexpr int i_ = (I), kb_ = i_ >> 1, ch_ = (i_ & 1) * 4, buf_ = i_ & 1;                                  \
     ldsm_x4(a0[buf_], a_base + kb_ * (R * 128) + (((ch_ + csel) ^ sw) << 4));                                  \
     ldsm_x4(a1[buf_], a_base + kb_ * (R * 128) + (((ch_ + 2 + csel) ^ sw) << 4));                              \
-    ldsm_x4(xb[buf_], b_base + i_ * 64);                                                                       \
+    _Pragma("unroll") for (int nb_ = 0; nb_ < NB; ++nb_) ldsm_x4(xb[buf_][nb_], b_base + nb_ * (8 * XP * 2) + i_ * 64); \
   }
 #define MDC_MTILE_MMA(I)                                                                                       \
   {                                                                                                            \
     constexpr int i_ = (I), buf_ = i_ & 1, par_ = (i_ & 1) * 2;                                                \
-    mma16816_h(c[par_], a0[buf_], xb[buf_][0], xb[buf_][1]);                                                   \
-    mma16816_h(c[par_ + 1], a1[buf_], xb[buf_][2], xb[buf_][3]);                                               \
+    _Pragma("unroll") for (int nb_ = 0; nb_ < NB; ++nb_) {                                                     \
+      mma16816_h(c[nb_][par_], a0[buf_], xb[buf_][nb_][0], xb[buf_][nb_][1]);                                  \
+      mma16816_h(c[nb_][par_ + 1], a1[buf_], xb[buf_][nb_][2], xb[buf_][nb_][3]);                              \
+    }                                                                                                          \
   }
   MDC_MTILE_LOAD(0) MDC_MTILE_LOAD(1)
   MDC_MTILE_MMA(0) MDC_MTILE_LOAD(2)
@@ -208,7 +228,9 @@ __device__ __forceinline__ void mma_mtile(uint32_t wblk, int m0, uint32_t bh, fl
 #undef MDC_MTILE_LOAD
 #undef MDC_MTILE_MMA
 #pragma unroll
-  for (int j = 0; j < 4; ++j) acc[j] = (c[0][j] + c[1][j]) + (c[2][j] + c[3][j]);
+  for (int nb = 0; nb < NB; ++nb)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[nb][j] = (c[nb][0][j] + c[nb][1][j]) + (c[nb][2][j] + c[nb][3][j]);
 }
 
 // ---- attention of ONE query per image on the tensor cores ------------------------------------------------------
@@ -328,8 +350,10 @@ __device__ __forceinline__ float attn_merge(const float* parts, uint32_t mask) {
 
 // kTrace: developer build of the same kernel that stamps clock64() at phase boundaries (tools/decode_trace.py); the production
 // instantiation carries no trace instructions.
-template <bool kTrace>
+template <bool kTrace, int NB>
 __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(NT, 1) decode_fused_kernel(const __grid_constant__ FusedParams P) {
+  using Y = Lay<NB>;
+  constexpr int GMX = Y::GMX, NS = Y::NS;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);      // pointer arithmetic keeps the shared address space
@@ -338,15 +362,15 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(NT, 1) decode_fused
   uint32_t rank; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
   const int cid = blockIdx.x / CS, n_clusters = gridDim.x / CS;
 
-  __half* xh = (__half*)(smem + OFF_XH); __half* fh = (__half*)(smem + OFF_FH);      // projection operands (fp16)
-  float* xres = (float*)(smem + OFF_XRES); float* yrecv = (float*)(smem + OFF_YRECV); float* f2recv = (float*)(smem + OFF_F2RECV);
-  float* qs = (float*)(smem + OFF_QS); float* knew = (float*)(smem + OFF_KNEW); float* vnew = (float*)(smem + OFF_VNEW);
-  float* ytmp = (float*)(smem + OFF_YTMP); float* part = (float*)(smem + OFF_PART);
-  bf16* qh = (bf16*)(smem + OFF_QH);
-  float* lrecv = (float*)(smem + OFF_LRECV); float* selbuf = (float*)(smem + OFF_SEL);
-  int* tokbuf = (int*)(smem + OFF_TOK); int* pages = (int*)(smem + OFF_PAGES); uint8_t* padflag = smem + OFF_PADF;
-  int* haspad = (int*)(smem + OFF_HASPAD);
-  const uint32_t bars = sbase + OFF_BARS;
+  __half* xh = (__half*)(smem + Y::OFF_XH); __half* fh = (__half*)(smem + Y::OFF_FH);      // projection operands (fp16)
+  float* xres = (float*)(smem + Y::OFF_XRES); float* yrecv = (float*)(smem + Y::OFF_YRECV); float* f2recv = (float*)(smem + Y::OFF_F2RECV);
+  float* qs = (float*)(smem + Y::OFF_QS); float* knew = (float*)(smem + Y::OFF_KNEW); float* vnew = (float*)(smem + Y::OFF_VNEW);
+  float* ytmp = (float*)(smem + Y::OFF_YTMP); float* part = (float*)(smem + Y::OFF_PART);
+  bf16* qh = (bf16*)(smem + Y::OFF_QH);
+  float* lrecv = (float*)(smem + Y::OFF_LRECV); float* selbuf = (float*)(smem + Y::OFF_SEL);
+  int* tokbuf = (int*)(smem + Y::OFF_TOK); int* pages = (int*)(smem + Y::OFF_PAGES); uint8_t* padflag = smem + Y::OFF_PADF;
+  int* haspad = (int*)(smem + Y::OFF_HASPAD);
+  const uint32_t bars = sbase + Y::OFF_BARS;
   auto bar = [&](int i) -> uint32_t { return bars + i * 8; };
 
   if (tid == 0) {
@@ -356,7 +380,7 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(NT, 1) decode_fused
   }
   // zero the ring and the activation operands once: rows >= G of the operands and the rows behind a partial key tile
   // of a K/V panel are multiplied by zeros and must be finite
-  for (int i = tid; i < (NS * STAGE_BYTES + 3 * ACT_BYTES) / 16; i += NT) reinterpret_cast<uint4*>(smem + OFF_RING)[i] = make_uint4(0u, 0u, 0u, 0u);
+  for (int i = tid; i < (NS * STAGE_BYTES + 3 * Y::ACT_BYTES) / 16; i += NT) reinterpret_cast<uint4*>(smem + Y::OFF_RING)[i] = make_uint4(0u, 0u, 0u, 0u);
   __syncthreads();
   cluster_sync_all();
 
@@ -375,13 +399,13 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(NT, 1) decode_fused
     const int img0 = grp * P.G;
     const int G = min(P.G, P.B - img0);
     // ---- per-group init: page ids, PAD flags of the known prefix ---------------------------------------------
-    for (int i = tid; i < GM * 32; i += NT) {
+    for (int i = tid; i < GMX * 32; i += NT) {
       const int g = i >> 5, j = i & 31;
       pages[i] = (g < G && j < P.pages_per_seq) ? P.page_table[(int64_t)(img0 + g) * P.pages_per_seq + j] : 0;
     }
-    if (tid < GM) haspad[tid] = 0;
+    if (tid < GMX) haspad[tid] = 0;
     __syncthreads();
-    for (int i = tid; i < GM * 256; i += NT) {
+    for (int i = tid; i < GMX * 256; i += NT) {
       const int g = i >> 8, u = i & 255;
       const bool pd = (g < G && u < P.t_begin) ? (P.tokens[(int64_t)(img0 + g) * P.tokens_ld + u] == P.pad_idx) : false;
       padflag[i] = pd;
@@ -397,7 +421,7 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(NT, 1) decode_fused
         const long long c0 = kTrace ? clock64() : 0;
         mbar_wait(bar(BAR_EMPTY + slot), phase ^ 1);
         if (kTrace) prod_wait += clock64() - c0;
-        return sbase + OFF_RING + slot * STAGE_BYTES;
+        return sbase + Y::OFF_RING + slot * STAGE_BYTES;
       };
       auto advance = [&]() { if (++slot == NS) { slot = 0; phase ^= 1; } };
       // one weight row block: 4 k-blocks of [R rows x 64 k]
@@ -482,7 +506,7 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(NT, 1) decode_fused
         const long long c0 = kTrace ? clock64() : 0;
         mbar_wait(bar(BAR_FULL + slot), phase);
         if (kTrace) cons_wait += clock64() - c0;
-        return sbase + OFF_RING + slot * STAGE_BYTES;
+        return sbase + Y::OFF_RING + slot * STAGE_BYTES;
       };
       auto xwait = [&](int which, uint32_t& ph) {    // wait for a push-style exchange
         const long long c0 = kTrace ? clock64() : 0;
@@ -503,11 +527,12 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(NT, 1) decode_fused
       auto FINE = [&](int l_now, int t_now, int idx) {   // trace build: fine stamps of layer 2 into trace[100 + idx] by lane 0 of the calling warp
         if (kTrace && lane == 0 && blockIdx.x == 0 && t_now == P.trace_t && l_now == 2) P.trace[100 + idx] = clock64();
       };
-      const int gi_t = tid >> 5, c_t = tid & 31;     // (image, channel) coordinates of the elementwise phases
+      const int gi_t = tid >> 5, c_t = tid & 31;     // (image [+ 8], channel) coordinates of the elementwise phases
+      constexpr int APP0 = NCT - GMX * 8;           // first thread of the KV-append crew (the last GMX * 8 consumer threads)
       // push this CTA's [G][32] slice in ytmp into every peer's yrecv columns [32*rank, +32)
-      auto push_y = [&](float v) {
-        if (gi_t < G) {
-          const uint32_t off = sbase + OFF_YRECV + (gi_t * DM + 32 * rank + c_t) * 4;
+      auto push_y = [&](int img, float v) {
+        if (img < G) {
+          const uint32_t off = sbase + Y::OFF_YRECV + (img * DM + 32 * rank + c_t) * 4;
 #pragma unroll
           for (int p = 0; p < CS; ++p) st_async_b32(mapa(off, p), __float_as_uint(v), mapa(bar(BAR_Y), p));
         }
@@ -516,7 +541,7 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(NT, 1) decode_fused
         if (tid == 0) mbar_expect_tx(bar(BAR_Y), G * DM * 4);
         xwait(BAR_Y, ph_y);
       };
-      // x = LN(xres + yrecv): warp w owns image w; writes xres and the hi/lo operand
+      // x = LN(xres + yrecv): warp w owns images w (and w + 8); writes xres and the fp16 operand
       auto layer_norm = [&](const float* lnw, const float* lnb) {
         float gw[8], gb[8];
         if (warp < G) {
@@ -524,33 +549,37 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(NT, 1) decode_fused
           for (int j = 0; j < 8; ++j) { gw[j] = __ldg(lnw + lane + 32 * j); gb[j] = __ldg(lnb + lane + 32 * j); }
         }
         wait_y();
-        if (warp < G) {
-          float v[8]; float s = 0.f;
 #pragma unroll
-          for (int j = 0; j < 8; ++j) { v[j] = xres[warp * DM + lane + 32 * j] + yrecv[warp * DM + lane + 32 * j]; s += v[j]; }
-          const float mean = warp_sum(s) * (1.0f / DM);
-          float q = 0.f;
+        for (int nb = 0; nb < NB; ++nb) {
+          const int img = warp + 8 * nb;
+          if (img < G) {
+            float v[8]; float s = 0.f;
 #pragma unroll
-          for (int j = 0; j < 8; ++j) { const float d = v[j] - mean; q += d * d; }
-          const float rstd = 1.0f / sqrtf(warp_sum(q) * (1.0f / DM) + 1e-5f);
+            for (int j = 0; j < 8; ++j) { v[j] = xres[img * DM + lane + 32 * j] + yrecv[img * DM + lane + 32 * j]; s += v[j]; }
+            const float mean = warp_sum(s) * (1.0f / DM);
+            float q = 0.f;
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const int c = lane + 32 * j;
-            const float xn = (v[j] - mean) * rstd * gw[j] + gb[j];
-            xres[warp * DM + c] = xn;
-            store_h(xh, warp * XP + c, xn);
+            for (int j = 0; j < 8; ++j) { const float d = v[j] - mean; q += d * d; }
+            const float rstd = 1.0f / sqrtf(warp_sum(q) * (1.0f / DM) + 1e-5f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const int c = lane + 32 * j;
+              const float xn = (v[j] - mean) * rstd * gw[j] + gb[j];
+              xres[img * DM + c] = xn;
+              store_h(xh, img * XP + c, xn);
+            }
           }
         }
         cbar();
       };
-      // attention output of image `warp` (lane = channel) -> fp16 pairs into every peer's oh columns [32*rank, +32); lane j < 16
+      // attention output of image `img` (lane = channel) -> fp16 pairs into every peer's oh columns [32*rank, +32); lane j < 16
       // sends channels 2j, 2j+1 to peers 0..3, lane 16 + j the same pair to peers 4..7
-      auto push_o = [&](float o) {
+      auto push_o = [&](int img, float o) {
         const int j = lane & 15;
         const float v0 = __shfl_sync(0xffffffffu, o, 2 * j), v1 = __shfl_sync(0xffffffffu, o, 2 * j + 1);
-        if (warp < G) {
+        if (img < G) {
           const uint32_t val = pack_h2(clamp_h(v0), clamp_h(v1));
-          const uint32_t off = sbase + OFF_OH + (warp * XP + 32 * rank + 2 * j) * 2;
+          const uint32_t off = sbase + Y::OFF_OH + (img * XP + 32 * rank + 2 * j) * 2;
           const int p0 = (lane >> 4) * 4;
 #pragma unroll
           for (int p = 0; p < 4; ++p) st_async_b32(mapa(off, p0 + p), val, mapa(bar(BAR_O), p0 + p));
@@ -566,18 +595,22 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(NT, 1) decode_fused
         if (warp < 2) { b0 = __ldg(bias + rank * 32 + warp * 16 + fg); b1 = __ldg(bias + rank * 32 + warp * 16 + fg + 8); }
         if (warp < 2) {
           const uint32_t st = stage_wait();
-          float acc[4];
-          mma_mtile<32>(st, warp * 16, bh, acc);
+          float acc[NB][4];
+          mma_mtile<32, NB>(st, warp * 16, bh, acc);
           const int f = warp * 16 + fg;
-          ytmp[(2 * fq) * 32 + f] = acc[0] + b0; ytmp[(2 * fq + 1) * 32 + f] = acc[1] + b0;
-          ytmp[(2 * fq) * 32 + f + 8] = acc[2] + b1; ytmp[(2 * fq + 1) * 32 + f + 8] = acc[3] + b1;
+#pragma unroll
+          for (int nb = 0; nb < NB; ++nb) {
+            float* y = ytmp + (8 * nb + 2 * fq) * 32 + f;
+            y[0] = acc[nb][0] + b0; y[32] = acc[nb][1] + b0; y[8] = acc[nb][2] + b1; y[40] = acc[nb][3] + b1;
+          }
           stage_release(4);
         } else {
           stage_skip();
-          if (fence_appends && tid >= 192 && tid - 192 < G * 8) asm volatile("fence.proxy.async;" ::: "memory");   // this layer's KV append
+          if (fence_appends && tid >= APP0 && tid - APP0 < G * 8) asm volatile("fence.proxy.async;" ::: "memory");   // this layer's KV append
         }
         cbar();
-        push_y(ytmp[gi_t * 32 + c_t]);
+#pragma unroll
+        for (int nb = 0; nb < NB; ++nb) push_y(gi_t + 8 * nb, ytmp[(gi_t + 8 * nb) * 32 + c_t]);
       };
 
       for (int t = P.t_begin; t < P.t_end; ++t) {
@@ -586,14 +619,20 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(NT, 1) decode_fused
           float pz[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) pz[j] = __ldg(P.pos + (int64_t)t * DM + lane + 32 * j);
-          const int tok = (P.forced || t == P.t_begin) ? __ldcg(P.tokens + (int64_t)(img0 + warp) * P.tokens_ld + t) : tokbuf[(t & 1) * GM + warp];
-          if (lane == 0) { padflag[warp * 256 + t] = (tok == P.pad_idx); if (tok == P.pad_idx) haspad[warp] = 1; }
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const int c = lane + 32 * j;
-            const float x = __ldg(P.emb + (int64_t)tok * DM + c) + pz[j];
-            xres[warp * DM + c] = x;
-            store_h(xh, warp * XP + c, x);
+          for (int nb = 0; nb < NB; ++nb) {
+            const int img = warp + 8 * nb;
+            if (img < G) {
+              const int tok = (P.forced || t == P.t_begin) ? __ldcg(P.tokens + (int64_t)(img0 + img) * P.tokens_ld + t) : tokbuf[(t & 1) * GMX + img];
+              if (lane == 0) { padflag[img * 256 + t] = (tok == P.pad_idx); if (tok == P.pad_idx) haspad[img] = 1; }
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const int c = lane + 32 * j;
+                const float x = __ldg(P.emb + (int64_t)tok * DM + c) + pz[j];
+                xres[img * DM + c] = x;
+                store_h(xh, img * XP + c, x);
+              }
+            }
           }
         }
         cbar();
@@ -607,43 +646,50 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(NT, 1) decode_fused
             else if (warp < 6) { const int r0 = 2 * DM + rank * HD + (warp & 1) * 16 + fg; b0 = __ldg(bi + r0); b1 = __ldg(bi + r0 + 8); }
             if (warp < 4) {
               const uint32_t st = stage_wait();
-              float acc[4];
-              mma_mtile<32>(st + (warp >> 1) * 16384, (warp & 1) * 16, sbase + OFF_XH, acc);
+              float acc[NB][4];
+              mma_mtile<32, NB>(st + (warp >> 1) * 16384, (warp & 1) * 16, sbase + Y::OFF_XH, acc);
               const int f = (warp & 1) * 16 + fg;
-              if (warp < 2) {      // q, pre-scaled
-                const float q0 = (acc[0] + b0) * scale, q1 = (acc[1] + b0) * scale, q2 = (acc[2] + b1) * scale, q3 = (acc[3] + b1) * scale;
-                const bf16 r0 = __float2bfloat16_rn(q0), r1 = __float2bfloat16_rn(q1), r2 = __float2bfloat16_rn(q2), r3 = __float2bfloat16_rn(q3);
-                qh[(2 * fq) * 32 + f] = r0; qh[(2 * fq + 1) * 32 + f] = r1; qh[(2 * fq) * 32 + f + 8] = r2; qh[(2 * fq + 1) * 32 + f + 8] = r3;
-                // the step's own key meets the same bf16 query as the cached keys
-                qs[(2 * fq) * 32 + f] = __bfloat162float(r0); qs[(2 * fq + 1) * 32 + f] = __bfloat162float(r1);
-                qs[(2 * fq) * 32 + f + 8] = __bfloat162float(r2); qs[(2 * fq + 1) * 32 + f + 8] = __bfloat162float(r3);
-              } else {             // k, rounded to the cache precision
-                knew[(2 * fq) * 32 + f] = __bfloat162float(__float2bfloat16_rn(acc[0] + b0));
-                knew[(2 * fq + 1) * 32 + f] = __bfloat162float(__float2bfloat16_rn(acc[1] + b0));
-                knew[(2 * fq) * 32 + f + 8] = __bfloat162float(__float2bfloat16_rn(acc[2] + b1));
-                knew[(2 * fq + 1) * 32 + f + 8] = __bfloat162float(__float2bfloat16_rn(acc[3] + b1));
+#pragma unroll
+              for (int nb = 0; nb < NB; ++nb) {
+                const int o = (8 * nb + 2 * fq) * 32 + f;
+                if (warp < 2) {      // q, pre-scaled
+                  const float q0 = (acc[nb][0] + b0) * scale, q1 = (acc[nb][1] + b0) * scale, q2 = (acc[nb][2] + b1) * scale, q3 = (acc[nb][3] + b1) * scale;
+                  const bf16 r0 = __float2bfloat16_rn(q0), r1 = __float2bfloat16_rn(q1), r2 = __float2bfloat16_rn(q2), r3 = __float2bfloat16_rn(q3);
+                  qh[o] = r0; qh[o + 32] = r1; qh[o + 8] = r2; qh[o + 40] = r3;
+                  // the step's own key meets the same bf16 query as the cached keys
+                  qs[o] = __bfloat162float(r0); qs[o + 32] = __bfloat162float(r1); qs[o + 8] = __bfloat162float(r2); qs[o + 40] = __bfloat162float(r3);
+                } else {             // k, rounded to the cache precision
+                  knew[o] = __bfloat162float(__float2bfloat16_rn(acc[nb][0] + b0));
+                  knew[o + 32] = __bfloat162float(__float2bfloat16_rn(acc[nb][1] + b0));
+                  knew[o + 8] = __bfloat162float(__float2bfloat16_rn(acc[nb][2] + b1));
+                  knew[o + 40] = __bfloat162float(__float2bfloat16_rn(acc[nb][3] + b1));
+                }
               }
               stage_release(2);
             } else stage_skip();
             if (warp == 4 || warp == 5) {
               const uint32_t st = stage_wait();
-              float acc[4];
-              mma_mtile<32>(st, (warp & 1) * 16, sbase + OFF_XH, acc);
+              float acc[NB][4];
+              mma_mtile<32, NB>(st, (warp & 1) * 16, sbase + Y::OFF_XH, acc);
               const int f = (warp & 1) * 16 + fg;
-              vnew[(2 * fq) * 32 + f] = __bfloat162float(__float2bfloat16_rn(acc[0] + b0));
-              vnew[(2 * fq + 1) * 32 + f] = __bfloat162float(__float2bfloat16_rn(acc[1] + b0));
-              vnew[(2 * fq) * 32 + f + 8] = __bfloat162float(__float2bfloat16_rn(acc[2] + b1));
-              vnew[(2 * fq + 1) * 32 + f + 8] = __bfloat162float(__float2bfloat16_rn(acc[3] + b1));
+#pragma unroll
+              for (int nb = 0; nb < NB; ++nb) {
+                const int o = (8 * nb + 2 * fq) * 32 + f;
+                vnew[o] = __bfloat162float(__float2bfloat16_rn(acc[nb][0] + b0));
+                vnew[o + 32] = __bfloat162float(__float2bfloat16_rn(acc[nb][1] + b0));
+                vnew[o + 8] = __bfloat162float(__float2bfloat16_rn(acc[nb][2] + b1));
+                vnew[o + 40] = __bfloat162float(__float2bfloat16_rn(acc[nb][3] + b1));
+              }
               stage_release(4);
             } else stage_skip();
           }
           cbar();
           TRACE(t);   // 1: in-proj done
-          // append k_t, v_t (bf16) to the paged cache: 16-byte stores, 4 per (image, k|v), by warps 6-7.  The proxy fence that
+          // append k_t, v_t (bf16) to the paged cache: 16-byte stores, 4 per (image, k|v), by the last warps.  The proxy fence that
           // orders them before the TMA reads of the page (one step later) costs ~1200 cycles; the same threads issue it in the
           // self out-proj phase below, where warps 2-7 have nothing else to do (proj32_push).
-          if (tid >= 192 && tid - 192 < G * 8) {
-            const int at = tid - 192;
+          if (tid >= APP0 && tid - APP0 < G * 8) {
+            const int at = tid - APP0;
             const int g = at >> 3, which = (at >> 2) & 1, ch = at & 3;
             const float* src = (which ? vnew : knew) + g * 32 + ch * 8;
             const float4 a = *reinterpret_cast<const float4*>(src), b = *reinterpret_cast<const float4*>(src + 4);
@@ -659,12 +705,16 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(NT, 1) decode_fused
           //      in shared memory) is partial #8 ------------------------------------------------------------------------------
           {
             const int ntile = (t + 15) >> 4;
-            if (warp < G) {
-              float s_own = warp_sum(qs[warp * 32 + lane] * knew[warp * 32 + lane]);
-              if (padflag[warp * 256 + t]) s_own += LOG2E;
-              float* pb = part + (warp * NPART + 8) * PSTR;
-              if (lane == 0) { pb[0] = s_own; pb[1] = 1.0f; }
-              pb[4 + lane] = vnew[warp * 32 + lane];
+#pragma unroll
+            for (int nb = 0; nb < NB; ++nb) {
+              const int img = warp + 8 * nb;
+              if (img < G) {
+                float s_own = warp_sum(qs[img * 32 + lane] * knew[img * 32 + lane]);
+                if (padflag[img * 256 + t]) s_own += LOG2E;
+                float* pb = part + (img * NPART + 8) * PSTR;
+                if (lane == 0) { pb[0] = s_own; pb[1] = 1.0f; }
+                pb[4 + lane] = vnew[img * 32 + lane];
+              }
             }
             const int wpi = 8 / P.ips, gi = warp / wpi, tl = warp - gi * wpi;
             for (int sg = 0; sg < nS; ++sg) {
@@ -692,11 +742,15 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(NT, 1) decode_fused
           }
           cbar();
           TRACE(t);   // 3: self attention
-          push_o(warp < G ? attn_merge(part + warp * NPART * PSTR, ((1u << (8 / P.ips)) - 1u) | (1u << 8)) : 0.f);
+#pragma unroll
+          for (int nb = 0; nb < NB; ++nb) {
+            const int img = warp + 8 * nb;
+            push_o(img, img < G ? attn_merge(part + img * NPART * PSTR, ((1u << (8 / P.ips)) - 1u) | (1u << 8)) : 0.f);
+          }
           wait_o();
           TRACE(t);   // 4: o gathered
           // ---- self out-proj slice -> all-gather -> LN1 ------------------------------------------------------------
-          proj32_push(sbase + OFF_OH, P.b_so[l], true);
+          proj32_push(sbase + Y::OFF_OH, P.b_so[l], true);
           TRACE(t);   // 5: out-proj pushed
           layer_norm(P.ln1w[l], P.ln1b[l]);
           TRACE(t);   // 6: LN1
@@ -708,11 +762,15 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(NT, 1) decode_fused
             if (warp < 2) { b0 = __ldg(bc + rank * 32 + warp * 16 + fg); b1 = __ldg(bc + rank * 32 + warp * 16 + fg + 8); }
             if (warp < 2) {
               const uint32_t st = stage_wait();
-              float acc[4];
-              mma_mtile<32>(st, warp * 16, sbase + OFF_XH, acc);
+              float acc[NB][4];
+              mma_mtile<32, NB>(st, warp * 16, sbase + Y::OFF_XH, acc);
               const int f = warp * 16 + fg;
-              qh[(2 * fq) * 32 + f] = __float2bfloat16_rn((acc[0] + b0) * scale); qh[(2 * fq + 1) * 32 + f] = __float2bfloat16_rn((acc[1] + b0) * scale);
-              qh[(2 * fq) * 32 + f + 8] = __float2bfloat16_rn((acc[2] + b1) * scale); qh[(2 * fq + 1) * 32 + f + 8] = __float2bfloat16_rn((acc[3] + b1) * scale);
+#pragma unroll
+              for (int nb = 0; nb < NB; ++nb) {
+                bf16* q = qh + (8 * nb + 2 * fq) * 32 + f;
+                q[0] = __float2bfloat16_rn((acc[nb][0] + b0) * scale); q[32] = __float2bfloat16_rn((acc[nb][1] + b0) * scale);
+                q[8] = __float2bfloat16_rn((acc[nb][2] + b1) * scale); q[40] = __float2bfloat16_rn((acc[nb][3] + b1) * scale);
+              }
               stage_release(4);
             } else stage_skip();
           }
@@ -747,10 +805,14 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(NT, 1) decode_fused
           }
           cbar();
           TRACE(t);   // 8: cross attention partials
-          push_o(warp < G ? attn_merge(part + warp * NPART * PSTR, 0xffu) : 0.f);
+#pragma unroll
+          for (int nb = 0; nb < NB; ++nb) {
+            const int img = warp + 8 * nb;
+            push_o(img, img < G ? attn_merge(part + img * NPART * PSTR, 0xffu) : 0.f);
+          }
           wait_o();
           TRACE(t);   // 9: o gathered
-          proj32_push(sbase + OFF_OH, P.b_co[l], false);
+          proj32_push(sbase + Y::OFF_OH, P.b_co[l], false);
           TRACE(t);   // 10: cross out-proj pushed
           layer_norm(P.ln2w[l], P.ln2b[l]);
           TRACE(t);   // 11: LN2
@@ -765,12 +827,16 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(NT, 1) decode_fused
               if (mt == 0) FINE(l, t, s4 * 4 + 0);
               const uint32_t st = stage_wait();
               if (mt == 0) FINE(l, t, s4 * 4 + 1);
-              float acc[4];
-              mma_mtile<64>(st, mt * 16, sbase + OFF_XH, acc);
+              float acc[NB][4];
+              mma_mtile<64, NB>(st, mt * 16, sbase + Y::OFF_XH, acc);
               if (mt == 0) FINE(l, t, s4 * 4 + 2);
               const int h = s4 * 64 + mt * 16 + fg;
-              store_h(fh, (2 * fq) * XP + h, fmaxf(acc[0] + b0, 0.f)); store_h(fh, (2 * fq + 1) * XP + h, fmaxf(acc[1] + b0, 0.f));
-              store_h(fh, (2 * fq) * XP + h + 8, fmaxf(acc[2] + b1, 0.f)); store_h(fh, (2 * fq + 1) * XP + h + 8, fmaxf(acc[3] + b1, 0.f));
+#pragma unroll
+              for (int nb = 0; nb < NB; ++nb) {
+                const int r = 8 * nb + 2 * fq;
+                store_h(fh, r * XP + h, fmaxf(acc[nb][0] + b0, 0.f)); store_h(fh, (r + 1) * XP + h, fmaxf(acc[nb][1] + b0, 0.f));
+                store_h(fh, r * XP + h + 8, fmaxf(acc[nb][2] + b1, 0.f)); store_h(fh, (r + 1) * XP + h + 8, fmaxf(acc[nb][3] + b1, 0.f));
+              }
               stage_release(2);
               if (mt == 0) FINE(l, t, s4 * 4 + 3);
             } else stage_skip();
@@ -783,14 +849,18 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(NT, 1) decode_fused
             const bool mine = mt >= 0 && mt < 4;
             if (mine) {
               const uint32_t st = stage_wait();
-              float acc[4];
-              mma_mtile<64>(st, mt * 16, sbase + OFF_FH, acc);
-              const int feat = s4 * 64 + mt * 16 + fg;                 // output feature of acc[0..1]; +8 for acc[2..3]
+              float acc[NB][4];
+              mma_mtile<64, NB>(st, mt * 16, sbase + Y::OFF_FH, acc);
+              const int feat = s4 * 64 + mt * 16 + fg;                 // output feature of acc[.][0..1]; +8 for acc[.][2..3]
               const uint32_t peer = feat >> 5;                          // the whole 16-row tile lies inside one 32-column slice
               const uint32_t rb = mapa(bar(BAR_F2), peer);
-              const uint32_t base = mapa(sbase + OFF_F2RECV + (rank * GM * 32 + (feat & 31)) * 4, peer);
-              if (2 * fq < G) { st_async_b32(base + (2 * fq) * 128, __float_as_uint(acc[0]), rb); st_async_b32(base + (2 * fq) * 128 + 32, __float_as_uint(acc[2]), rb); }
-              if (2 * fq + 1 < G) { st_async_b32(base + (2 * fq + 1) * 128, __float_as_uint(acc[1]), rb); st_async_b32(base + (2 * fq + 1) * 128 + 32, __float_as_uint(acc[3]), rb); }
+              const uint32_t base = mapa(sbase + Y::OFF_F2RECV + (rank * GMX * 32 + (feat & 31)) * 4, peer);
+#pragma unroll
+              for (int nb = 0; nb < NB; ++nb) {
+                const int i0 = 8 * nb + 2 * fq;
+                if (i0 < G) { st_async_b32(base + i0 * 128, __float_as_uint(acc[nb][0]), rb); st_async_b32(base + i0 * 128 + 32, __float_as_uint(acc[nb][2]), rb); }
+                if (i0 + 1 < G) { st_async_b32(base + (i0 + 1) * 128, __float_as_uint(acc[nb][1]), rb); st_async_b32(base + (i0 + 1) * 128 + 32, __float_as_uint(acc[nb][3]), rb); }
+              }
               stage_release(2);
             } else stage_skip();
           }
@@ -799,12 +869,16 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(NT, 1) decode_fused
             const float b2 = __ldg(P.b_f2[l] + rank * 32 + c_t);
             if (tid == 0) mbar_expect_tx(bar(BAR_F2), G * DM * 4);
             xwait(BAR_F2, ph_f2);
-            float a = b2;
-            if (gi_t < G) {
 #pragma unroll
-              for (int p = 0; p < CS; ++p) a += f2recv[(p * GM + gi_t) * 32 + c_t];
+            for (int nb = 0; nb < NB; ++nb) {
+              const int img = gi_t + 8 * nb;
+              float a = b2;
+              if (img < G) {
+#pragma unroll
+                for (int p = 0; p < CS; ++p) a += f2recv[(p * GMX + img) * 32 + c_t];
+              }
+              push_y(img, a);
             }
-            push_y(a);
           }
           TRACE(t);   // 14: FFN2 reduced + pushed
           layer_norm(P.ln3w[l], P.ln3b[l]);
@@ -823,47 +897,55 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(NT, 1) decode_fused
           if (vb) b1 = __ldg(P.b_out + r0 + row_b);
           if (warp < 3) {
             const uint32_t st = stage_wait();
-            float acc[4];
-            mma_mtile<VSL>(st, warp * 16, sbase + OFF_XH, acc);
+            float acc[NB][4];
+            mma_mtile<VSL, NB>(st, warp * 16, sbase + Y::OFF_XH, acc);
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const int img = 2 * fq + (e & 1); const bool hi8 = e >= 2;
-              const bool valid = (hi8 ? vb : va) && img < G;
-              if (valid) {
-                const int row = hi8 ? row_b : row_a;
-                const float lg = acc[e] + (hi8 ? b1 : b0);
-                if (P.logits_out) P.logits_out[(int64_t)(img0 + img) * P.logits_img_stride + (int64_t)(t + P.logits_row_offset) * P.vocab + r0 + row] = lg;
-                if (need_select) st_async_b32(mapa(sbase + OFF_LRECV + (rank * VSL + row) * 4, img), __float_as_uint(lg), mapa(bar(BAR_LG), img));
+            for (int nb = 0; nb < NB; ++nb)
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const int img = 8 * nb + 2 * fq + (e & 1); const bool hi8 = e >= 2;
+                const bool valid = (hi8 ? vb : va) && img < G;
+                if (valid) {
+                  const int row = hi8 ? row_b : row_a;
+                  const float lg = acc[nb][e] + (hi8 ? b1 : b0);
+                  if (P.logits_out) P.logits_out[(int64_t)(img0 + img) * P.logits_img_stride + (int64_t)(t + P.logits_row_offset) * P.vocab + r0 + row] = lg;
+                  // the CTA that selects for image img is img % 8; it keeps one [CS][VSL] receive block per owned image
+                  if (need_select) st_async_b32(mapa(sbase + Y::OFF_LRECV + ((nb * CS + rank) * VSL + row) * 4, img & 7), __float_as_uint(lg), mapa(bar(BAR_LG), img & 7));
+                }
               }
-            }
             stage_release(warp == 0 ? 4 : 2);
           } else stage_skip();
         }
         cbar();       // the next step's embedding overwrites the operand rows the head MMAs of warps 0-2 are reading (in teacher-forced
                       // mode nothing else orders the two: no select, no token exchange)
         TRACE(t);     // head done
-        // ---- select: CTA `rank` owns image `rank` ------------------------------------------------------------------
+        // ---- select: CTA `rank` owns images `rank` (and `rank + 8`) ---------------------------------------------------
         if (need_select && (int)rank < G) {
           const int V = P.vocab;
-          if (tid == 0) mbar_expect_tx(bar(BAR_LG), V * 4);
+          const int n_own = ((int)rank + 8 < G && NB > 1) ? 2 : 1;
+          if (tid == 0) mbar_expect_tx(bar(BAR_LG), n_own * V * 4);
           mbar_wait(bar(BAR_LG), ph_lg);
+          ph_lg ^= 1;
           int Vp2 = 1; while (Vp2 < V) Vp2 <<= 1;
           float* lg = selbuf; float* srt = selbuf + CS * VSL;
-          for (int i = tid; i < V; i += NCT) lg[i] = lrecv[i];          // [src][VSL] is vocabulary order
-          cbar();
           const bool sample = (P.top_k != 0 || P.top_p != 1.0f) && P.uniforms != nullptr;
-          const float u = sample ? P.uniforms[(int64_t)(img0 + rank) * P.uniforms_ld + t] : 0.f;
-          int token; float conf;
-          select_from_logits(lg, srt, V, Vp2, P.top_k, P.top_p, sample, u, token, conf);
-          ph_lg ^= 1;
-          if (tid == 0) {
-            if (!P.forced) {
-              P.tokens[(int64_t)(img0 + rank) * P.tokens_ld + t + 1] = token;
-              const uint32_t off = sbase + OFF_TOK + ((((t + 1) & 1) * GM) + rank) * 4;
+          for (int nb = 0; nb < n_own; ++nb) {
+            const int img = rank + 8 * nb;
+            for (int i = tid; i < V; i += NCT) lg[i] = lrecv[nb * CS * VSL + i];          // [src][VSL] is vocabulary order
+            cbar();
+            const float u = sample ? P.uniforms[(int64_t)(img0 + img) * P.uniforms_ld + t] : 0.f;
+            int token; float conf;
+            select_from_logits(lg, srt, V, Vp2, P.top_k, P.top_p, sample, u, token, conf);
+            if (tid == 0) {
+              if (!P.forced) {
+                P.tokens[(int64_t)(img0 + img) * P.tokens_ld + t + 1] = token;
+                const uint32_t off = sbase + Y::OFF_TOK + ((((t + 1) & 1) * GMX) + img) * 4;
 #pragma unroll
-              for (int p = 0; p < CS; ++p) st_async_b32(mapa(off, p), (uint32_t)token, mapa(bar(BAR_TOK), p));
+                for (int p = 0; p < CS; ++p) st_async_b32(mapa(off, p), (uint32_t)token, mapa(bar(BAR_TOK), p));
+              }
+              if (want_conf) P.confs[(int64_t)(img0 + img) * P.confs_ld + t / 4] = conf;
             }
-            if (want_conf) P.confs[(int64_t)(img0 + rank) * P.confs_ld + t / 4] = conf;
+            if (nb + 1 < n_own) cbar();      // the scratch is reused by the second image
           }
         }
         if (!P.forced) {
@@ -947,23 +1029,30 @@ int decode_cluster_launch(mdc_model* m, const mdc_decode_state* st, int t_begin,
   // cross-K/V [layers*B*S rows][2*DM]: one (S rows x 32 channels) box per (image, head, k|v); paged pool: one page x head box
   MDC_TRY(mdc_make_tmap_2d(ctx, st->cross_kv, (int64_t)d.dec_layers * st->B * d.n_patches, 2 * DM, 2 * DM, HD, d.n_patches, 2, &P.m_ckv));
   MDC_TRY(mdc_make_tmap_2d(ctx, st->kv_pool, (int64_t)st->n_pages * d.dec_layers * 2 * d.page_tokens, DM, DM, HD, d.page_tokens, 2, &P.m_pool));
-  static int max_clusters = 0;
-  if (!max_clusters) {
-    MDC_CUDA(cudaFuncSetAttribute(decode_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    MDC_CUDA(cudaFuncSetAttribute(decode_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    cudaLaunchConfig_t q{}; q.gridDim = dim3(CS * 32); q.blockDim = dim3(NT); q.dynamicSmemBytes = SMEM_BYTES;
+  // NB = 1: up to 8 images per cluster (13-15 clusters: lowest latency); NB = 2: up to 16 images per cluster, asked for by the
+  // batch pipeline through images_per_cluster > 8 (less SM-time per image, twice the latency)
+  int ipc = st->images_per_cluster;
+  if (const char* e = getenv("MDC_DECODE_IPC")) ipc = atoi(e);                                  // developer override (tools/decode_trace.py)
+  const int nb = ipc > 8 ? 2 : 1;
+  static int max_clusters_nb[2] = {0, 0};
+  if (!max_clusters_nb[nb - 1]) {
+    const int smem = nb == 1 ? Lay<1>::SMEM_BYTES : Lay<2>::SMEM_BYTES;
+    const void* fn = nb == 1 ? (const void*)decode_fused_kernel<false, 1> : (const void*)decode_fused_kernel<false, 2>;
+    const void* fn_t = nb == 1 ? (const void*)decode_fused_kernel<true, 1> : (const void*)decode_fused_kernel<true, 2>;
+    MDC_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    MDC_CUDA(cudaFuncSetAttribute(fn_t, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    cudaLaunchConfig_t q{}; q.gridDim = dim3(CS * 32); q.blockDim = dim3(NT); q.dynamicSmemBytes = smem;
     cudaLaunchAttribute a[1]; a[0].id = cudaLaunchAttributeClusterDimension; a[0].val.clusterDim.x = CS; a[0].val.clusterDim.y = 1; a[0].val.clusterDim.z = 1;
     q.attrs = a; q.numAttrs = 1;
     int n = 0;
-    cudaError_t e = cudaOccupancyMaxActiveClusters(&n, decode_fused_kernel<false>, &q);
+    cudaError_t e = cudaOccupancyMaxActiveClusters(&n, fn, &q);
     if (e != cudaSuccess || n < 1) { (void)cudaGetLastError(); n = ctx->sm_count / CS / 2; if (n < 1) n = 1; }
-    max_clusters = n;
+    max_clusters_nb[nb - 1] = n;
   }
+  const int max_clusters = max_clusters_nb[nb - 1];
   int G = (P.B + max_clusters - 1) / max_clusters;
-  int ipc = st->images_per_cluster;
-  if (const char* e = getenv("MDC_DECODE_IPC")) ipc = atoi(e);                                  // developer override (tools/decode_trace.py)
   if (ipc > 0 && ipc > G) G = ipc;                                                              // fewer, fuller clusters (batch pipelining)
-  if (G > GM) G = GM;
+  if (G > 8 * nb) G = 8 * nb;
   if (G < 1) G = 1;
   P.G = G;
   P.n_groups = (P.B + G - 1) / G;
@@ -973,8 +1062,13 @@ int decode_cluster_launch(mdc_model* m, const mdc_decode_state* st, int t_begin,
   P.ips = P.ips >= 4 ? 4 : (P.ips >= 2 ? 2 : P.ips);    // {1, 2, 4}: 8 / ips warps per image, two key tiles per warp cover the capacity
   if (P.ips < 1) MDC_FAIL(-2, "decode_cluster: key capacity %d does not fit a stage", t_end);
   const int n_clusters = P.n_groups < max_clusters ? P.n_groups : max_clusters;
-  if (P.trace) decode_fused_kernel<true><<<n_clusters * CS, NT, SMEM_BYTES, s>>>(P);
-  else decode_fused_kernel<false><<<n_clusters * CS, NT, SMEM_BYTES, s>>>(P);
+  if (nb == 1) {
+    if (P.trace) decode_fused_kernel<true, 1><<<n_clusters * CS, NT, Lay<1>::SMEM_BYTES, s>>>(P);
+    else decode_fused_kernel<false, 1><<<n_clusters * CS, NT, Lay<1>::SMEM_BYTES, s>>>(P);
+  } else {
+    if (P.trace) decode_fused_kernel<true, 2><<<n_clusters * CS, NT, Lay<2>::SMEM_BYTES, s>>>(P);
+    else decode_fused_kernel<false, 2><<<n_clusters * CS, NT, Lay<2>::SMEM_BYTES, s>>>(P);
+  }
   MDC_LAUNCH_CHECK(ctx);
   return 0;
 }

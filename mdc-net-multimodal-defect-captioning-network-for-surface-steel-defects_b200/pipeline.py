@@ -6,9 +6,10 @@ One batch is two dependent phases with very different shapes on a B200:
 Batches are independent, so several are kept in flight: the encoder phase (and the host->device copy) of batch
 i+1 runs on a low-priority stream WHILE the decode kernels of earlier batches run on high-priority streams.  For a single
 batch the decode kernel spreads over as many 8-SM clusters as fit (13-15 x 5 images: lowest latency); in the pipeline it is
-asked for 8 images per cluster instead (8 clusters = 64 SMs for B = 64: ~25 % longer, but 23 % less SM-time per batch), so that
-two to three decode kernels and an encoder share the 148 SMs.  Measured on B200 (tools/pipeline_probe.py, B=64, T=99):
-serial 10.3 ms/batch, 1 decode stream 8.7, 2 streams 7.6, 3 streams 7.2 (saturated: more streams / depth change nothing).
+asked for 16 images per cluster instead (the kernel's two-column-block instantiation; 4 clusters = 32 SMs for B = 64: twice the
+latency, but ~35 % less SM-time per batch), so that four decode kernels and an encoder share the 148 SMs.  Measured on B200
+(tools/pipeline_probe.py, B=64, T=99, same box): serial 10.1 ms/batch; 8 images/cluster, 3 decode streams, 4 plans 6.91;
+16 images/cluster with 3 streams / 6 plans 6.45, 4 / 6 6.11, 5 / 8 6.11 (saturated).
 `depth` plans (static buffers + two CUDA graphs each) are used round-robin; events order encoder(i) -> decode(i) ->
 encoder(i + depth).  Results are bit-identical to the serial `generate()`.
 """
@@ -36,7 +37,7 @@ class Ticket:
 
 
 class GenerationPipeline:
-    def __init__(self, model, batch, max_new_tokens, top_k=0, top_p=1.0, depth=4, decode_streams=3, images_per_cluster=8,
+    def __init__(self, model, batch, max_new_tokens, top_k=0, top_p=1.0, depth=6, decode_streams=4, images_per_cluster=16,
                  to_host=False, device=None):
         from .model import GenerationPlan
         if not hasattr(model, "_engine"):
@@ -112,7 +113,7 @@ class GenerationPipeline:
 
 
 @torch.no_grad()
-def generate_stream(model, batches, tokenizer, max_len=50, top_k=0, top_p=1, depth=4):
+def generate_stream(model, batches, tokenizer, max_len=50, top_k=0, top_p=1, depth=6):
     """The reference's inference loop as ONE pipelined call: yields, per batch and in order, what `generate(model, x, tokenizer,
     max_len, top_k, top_p)` returns -- (LongTensor (B,1+max_len) on CPU, list of ceil(max_len/4) float tensors (B,) on CPU).
     `batches` is any iterable of f32 (B,3,H,W) tensors (host, ideally pinned, or device) -- or of raw grayscale u8 (B,h,w)

@@ -207,6 +207,29 @@ def test_cluster_decode_kernel_matches_generic_kernels(model_p, golden, B, T):
     assert agree > 0.5, agree
 
 
+@pytest.mark.parametrize("B,T", [(13, 30), (37, 40), (64, 99)])
+def test_cluster_decode_16_images_per_cluster_is_bitwise_the_8_image_kernel(model_p, B, T):
+    """The two-column-block instantiation of the fused kernel (up to 16 images per cluster pass: what the batch pipeline asks
+    for) against the one-block instantiation (up to 8): every image's arithmetic is the same sequence of operations, so logits,
+    tokens and confidences must be bitwise equal -- teacher-forced, free-running greedy and top-k sampling."""
+    import os
+    model_p.set_precision("bf16")
+    x = cases.images(B, seed=77).to(DEV)
+    u = torch.rand(B, T, generator=torch.Generator().manual_seed(5)).to(DEV)
+    def run():
+        t, c = model_p.generate_tokens(x, T, use_graph=False)
+        ts, cs = model_p.generate_tokens(x, T, top_k=5, uniforms=u, use_graph=False)
+        return t, c, ts, cs, model_p.predict(x, t[:, :T].long())
+    want = run()
+    os.environ["MDC_DECODE_IPC"] = "16"
+    try:
+        got = run()
+    finally:
+        os.environ.pop("MDC_DECODE_IPC", None)
+    for a, b in zip(got, want):
+        assert torch.equal(a, b)
+
+
 def test_cluster_decode_is_run_to_run_deterministic(model_p):
     """Race detector for the fused kernel: teacher-forced (no select / token exchange between steps -- the path where a missing
     barrier between the head MMAs and the next step's operand write once showed up) and free-running, 6 runs each, bitwise."""

@@ -15,7 +15,8 @@ a.record()
 outs = [m.generate_tokens(xs[i % 4], T)[0] for i in range(K)]
 b.record(); torch.cuda.synchronize()
 print(f"serial                                  : {B * K / (a.elapsed_time(b) / 1e3):9.1f} img/s  ({a.elapsed_time(b) / K:.3f} ms/batch)")
-for ipc, ndec, depth in [(8, 3, 4), (8, 3, 4)]:
+cfgs = [tuple(int(v) for v in c.split(',')) for c in sys.argv[2:]] or [(8, 3, 4), (16, 4, 6), (16, 5, 8), (16, 6, 8), (16, 3, 6)]
+for ipc, ndec, depth in cfgs:
     plans = [GenerationPlan(eng, B, T, 0, 1.0, False, False, True, split=True, images_per_cluster=ipc) for _ in range(depth)]
     s_enc = torch.cuda.Stream(priority=0)
     s_decs = [torch.cuda.Stream(priority=-1) for _ in range(ndec)]
