@@ -33,7 +33,7 @@ WANT = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "la
         "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__warps_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum", "sm__cycles_elapsed.max",
         "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "smsp__pcsamp_sample_count"]
 traffic = {}
-for name in ["gemm_fc1", "attn", "decode", "ln", "iou"]:
+for name in ["gemm_fc1", "attn", "decode", "decode16", "ln", "iou"]:
     rep = f"{G}/{tag}_{name}.ncu-rep"
     if not os.path.exists(rep):
         continue
@@ -57,7 +57,7 @@ for name in ["gemm_fc1", "attn", "decode", "ln", "iou"]:
     out.append("")
     lines = subprocess.run([sys.executable, "tools/ncu_lines.py", rep, "14"], capture_output=True, text=True).stdout
     out.append("Hottest source lines (stall samples, instructions executed):\n\n```\n" + lines + "```\n")
-for f in ["bench.log", "gemm.log", "iou.log", "trace.log"]:
+for f in ["bench.log", "gemm.log", "cublas.log", "iou.log", "trace.log", "trace16.log", "pipeline.log"]:
     pth = f"{G}/{tag}_{f}"
     if os.path.exists(pth):
         out.append(f"## {f}\n\n```\n" + open(pth).read().strip() + "\n```\n")
