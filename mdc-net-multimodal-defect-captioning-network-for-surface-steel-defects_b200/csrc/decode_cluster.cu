@@ -261,7 +261,7 @@ __device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.
 // tile past the end is clamped onto tile `tl` and masked, so there is no control flow between the fragment loads and the MMAs and
 // all four K fragments and all four V fragments (which do not depend on the scores) are requested before the first MMA (volatile
 // asm: program order is issue order) -- the chunk pays the ldmatrix latency once.  Requires tl < ntile.  On return m_out / l_out
-// are warp-uniform; the un-normalised output of dims mt*16 + {g, g+8} sits in lanes with q == 0 as o[mt][0] and o[mt][2].
+// are valid in lanes 0-3; the un-normalised output of dims mt*16 + {g, g+8} sits in lanes with q == 0 as o[mt][0] and o[mt][2].
 __device__ __forceinline__ void attn_chunk2(uint32_t kp, uint32_t vp, const uint32_t (&aq)[2][2], int tl, int tstep, int ntile, int nkeys,
                                             const uint8_t* padf, float& m_out, float& l_out, float (&o)[2][4]) {
   const int lane = threadIdx.x & 31, q4 = lane & 3;
@@ -306,7 +306,8 @@ __device__ __forceinline__ void attn_chunk2(uint32_t kp, uint32_t vp, const uint
   float mx = fmaxf(fmaxf(fmaxf(sc[0][0], sc[0][1]), fmaxf(sc[0][2], sc[0][3])), fmaxf(fmaxf(sc[1][0], sc[1][1]), fmaxf(sc[1][2], sc[1][3])));
   mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
   mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
-  mx = __shfl_sync(0xffffffffu, mx, 0);                                   // only row group g = 0 holds scores; key tl*16 is valid, so mx is finite
+  // only row group g = 0 (lanes 0-3) holds scores -- key tl*16 is valid, so their mx is finite; the other lanes work on the all-zero
+  // rows of the M operand (scores 0, own mx 0, p = 1: finite) and feed output columns that are never read, so no broadcast is needed
   float ls = 0.f;
   float o2[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};          // second tile: its own accumulator chain
 #pragma unroll
@@ -320,7 +321,7 @@ __device__ __forceinline__ void attn_chunk2(uint32_t kp, uint32_t vp, const uint
   }
   ls += __shfl_xor_sync(0xffffffffu, ls, 1);
   ls += __shfl_xor_sync(0xffffffffu, ls, 2);
-  l_out = __shfl_sync(0xffffffffu, ls, 0);
+  l_out = ls;          // valid in lanes 0-3 (lane 0 stores the partial)
   m_out = mx;
 #pragma unroll
   for (int mt = 0; mt < 2; ++mt)
