@@ -347,6 +347,22 @@ __device__ __forceinline__ float attn_merge(const float* parts, uint32_t mask) {
   return o / L;
 }
 
+// Greedy select of one image by ONE warp, no block barrier: argmax (lowest index on ties, like torch.argmax) and the maximal
+// softmax probability 1 / sum exp(l - max) (inference_p.py:77, 84-86 with top_k = 0, top_p = 1: the filter is the identity).
+__device__ __forceinline__ void warp_greedy_select(const float* lg, int V, int& token, float& conf) {
+  const int lane = threadIdx.x & 31;
+  float bv = -INFINITY; int bi = 0x7fffffff;
+  for (int i = lane; i < V; i += 32) { const float v = lg[i]; if (v > bv) { bv = v; bi = i; } }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, bv, o); const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+  }
+  float sum = 0.f;
+  for (int i = lane; i < V; i += 32) sum += expf(lg[i] - bv);
+  token = bi; conf = 1.0f / warp_sum(sum);
+}
+
 // kTrace: developer build of the same kernel that stamps clock64() at phase boundaries (tools/decode_trace.py); the production
 // instantiation carries no trace instructions.
 template <bool kTrace, int NB>
@@ -931,26 +947,36 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(NT, 1) decode_fused
           if (tid == 0) mbar_expect_tx(bar(BAR_LG), n_own * V * 4);
           mbar_wait(bar(BAR_LG), ph_lg);
           ph_lg ^= 1;
-          int Vp2 = 1; while (Vp2 < V) Vp2 <<= 1;
-          float* lg = selbuf; float* srt = selbuf + CS * VSL;
-          const bool sample = (P.top_k != 0 || P.top_p != 1.0f) && P.uniforms != nullptr;
-          for (int nb = 0; nb < n_own; ++nb) {
-            const int img = rank + 8 * nb;
-            for (int i = tid; i < V; i += NCT) lg[i] = lrecv[nb * CS * VSL + i];          // [src][VSL] is vocabulary order
-            cbar();
-            const float u = sample ? P.uniforms[(int64_t)(img0 + img) * P.uniforms_ld + t] : 0.f;
-            int token; float conf;
-            select_from_logits(lg, srt, V, Vp2, P.top_k, P.top_p, sample, u, token, conf);
-            if (tid == 0) {
-              if (!P.forced) {
-                P.tokens[(int64_t)(img0 + img) * P.tokens_ld + t + 1] = token;
-                const uint32_t off = sbase + Y::OFF_TOK + ((((t + 1) & 1) * GMX) + img) * 4;
+          auto publish = [&](int img, int token, float conf) {     // one thread: token to the caller's buffer and to every peer
+            if (!P.forced) {
+              P.tokens[(int64_t)(img0 + img) * P.tokens_ld + t + 1] = token;
+              const uint32_t off = sbase + Y::OFF_TOK + ((((t + 1) & 1) * GMX) + img) * 4;
 #pragma unroll
-                for (int p = 0; p < CS; ++p) st_async_b32(mapa(off, p), (uint32_t)token, mapa(bar(BAR_TOK), p));
-              }
-              if (want_conf) P.confs[(int64_t)(img0 + img) * P.confs_ld + t / 4] = conf;
+              for (int p = 0; p < CS; ++p) st_async_b32(mapa(off, p), (uint32_t)token, mapa(bar(BAR_TOK), p));
             }
-            if (nb + 1 < n_own) cbar();      // the scratch is reused by the second image
+            if (want_conf) P.confs[(int64_t)(img0 + img) * P.confs_ld + t / 4] = conf;
+          };
+          if (P.top_k == 0 && P.top_p == 1.0f) {
+            // greedy: one warp per owned image straight from the receive buffer ([src][VSL] is vocabulary order), no block barrier
+            if (warp < n_own) {
+              int token; float conf;
+              warp_greedy_select(lrecv + warp * CS * VSL, V, token, conf);
+              if (lane == 0) publish(rank + 8 * warp, token, conf);
+            }
+          } else {
+            int Vp2 = 1; while (Vp2 < V) Vp2 <<= 1;
+            float* lg = selbuf; float* srt = selbuf + CS * VSL;
+            const bool sample = P.uniforms != nullptr;
+            for (int nb = 0; nb < n_own; ++nb) {
+              const int img = rank + 8 * nb;
+              for (int i = tid; i < V; i += NCT) lg[i] = lrecv[nb * CS * VSL + i];
+              cbar();
+              const float u = sample ? P.uniforms[(int64_t)(img0 + img) * P.uniforms_ld + t] : 0.f;
+              int token; float conf;
+              select_from_logits(lg, srt, V, Vp2, P.top_k, P.top_p, sample, u, token, conf);
+              if (tid == 0) publish(img, token, conf);
+              if (nb + 1 < n_own) cbar();      // the scratch is reused by the second image
+            }
           }
         }
         if (!P.forced) {
