@@ -561,7 +561,9 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(NT, 1) decode_fused
         xwait(BAR_Y, ph_y);
       };
       // x = LN(xres + yrecv): warp w owns images w (and w + 8); writes xres and the fp16 operand
-      auto layer_norm = [&](const float* lnw, const float* lnb) {
+      auto layer_norm = [&](const float* lnw, const float* lnb, bool fence_appends = false) {
+        // this layer's KV append: the generic->async proxy fence (~1200 cycles) of the appending threads overlaps the exchange latency
+        if (fence_appends && tid >= APP0 && tid - APP0 < G * 8) asm volatile("fence.proxy.async;" ::: "memory");
         float gw[8], gb[8];
         if (warp < G) {
 #pragma unroll
@@ -609,7 +611,7 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(NT, 1) decode_fused
         xwait(BAR_O, ph_o);
       };
       // a 32-row projection of the gathered operand bh -> ytmp (+bias) -> pushed to all peers
-      auto proj32_push = [&](uint32_t bh, const float* bias, bool fence_appends) {
+      auto proj32_push = [&](uint32_t bh, const float* bias) {
         float b0 = 0.f, b1 = 0.f;
         if (warp < 2) { b0 = __ldg(bias + rank * 32 + warp * 16 + fg); b1 = __ldg(bias + rank * 32 + warp * 16 + fg + 8); }
         if (warp < 2) {
@@ -625,7 +627,6 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(NT, 1) decode_fused
           stage_release(4);
         } else {
           stage_skip();
-          if (fence_appends && tid >= APP0 && tid - APP0 < G * 8) asm volatile("fence.proxy.async;" ::: "memory");   // this layer's KV append
         }
         cbar();
 #pragma unroll
@@ -707,8 +708,8 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(NT, 1) decode_fused
           cbar();
           TRACE(t);   // 1: in-proj done
           // append k_t, v_t (bf16) to the paged cache: 16-byte stores, 4 per (image, k|v), by the last warps.  The proxy fence that
-          // orders them before the TMA reads of the page (one step later) costs ~1200 cycles; the same threads issue it in the
-          // self out-proj phase below, where warps 2-7 have nothing else to do (proj32_push).
+          // orders them before the TMA reads of the page (one step later) costs ~1200 cycles; the same threads issue it while they
+          // wait for the out-projection exchange (layer_norm), where its latency hides behind the exchange's.
           if (tid >= APP0 && tid - APP0 < G * 8) {
             const int at = tid - APP0;
             const int g = at >> 3, which = (at >> 2) & 1, ch = at & 3;
@@ -771,9 +772,9 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(NT, 1) decode_fused
           wait_o();
           TRACE(t);   // 4: o gathered
           // ---- self out-proj slice -> all-gather -> LN1 ------------------------------------------------------------
-          proj32_push(sbase + Y::OFF_OH, P.b_so[l], true);
+          proj32_push(sbase + Y::OFF_OH, P.b_so[l]);
           TRACE(t);   // 5: out-proj pushed
-          layer_norm(P.ln1w[l], P.ln1b[l]);
+          layer_norm(P.ln1w[l], P.ln1b[l], true);
           TRACE(t);   // 6: LN1
 
           // ---- cross-attention query slice -------------------------------------------------------------------------
@@ -833,7 +834,7 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(NT, 1) decode_fused
           }
           wait_o();
           TRACE(t);   // 9: o gathered
-          proj32_push(sbase + Y::OFF_OH, P.b_co[l], false);
+          proj32_push(sbase + Y::OFF_OH, P.b_co[l]);
           TRACE(t);   // 10: cross out-proj pushed
           layer_norm(P.ln2w[l], P.ln2b[l]);
           TRACE(t);   // 11: LN2
