@@ -230,6 +230,33 @@ def test_cluster_decode_16_images_per_cluster_is_bitwise_the_8_image_kernel(mode
         assert torch.equal(a, b)
 
 
+def test_greedy_select_breaks_ties_like_torch_argmax():
+    """Three vocabulary rows (in three different CTAs of the cluster) carry identical weights and a large bias, so their logits
+    tie exactly at every step: the greedy select must return the lowest index (torch.argmax, inference_p.py:77) and the max-prob
+    must equal the reference formula on the kernel's own logits -- fused kernel (one image per cluster slot and sixteen) and the
+    generic select kernel alike."""
+    import os
+    m = cases.build_product_model("P", seed=0, gamma_seed=5)
+    with torch.no_grad():
+        w, b = m.decoder.output.weight, m.decoder.output.bias
+        for j in (150, 290):
+            w[j].copy_(w[7]); b[j].copy_(b[7])
+        b[[7, 150, 290]] += 8.0
+    m = m.to(DEV).set_precision("bf16")
+    x = cases.images(19, seed=12).to(DEV)
+    for env in ({}, {"MDC_DECODE_IPC": "16"}, {"MDC_DECODE_BACKEND": "generic"}):
+        os.environ.update(env)
+        try:
+            toks, confs, logits = m.generate_tokens(x, 12, return_logits=True, use_graph=False)
+        finally:
+            for k in env:
+                os.environ.pop(k, None)
+        assert torch.equal(logits[..., 7], logits[..., 150]) and torch.equal(logits[..., 7], logits[..., 290])
+        assert (toks[:, 1:] == 7).all(), (env, toks[0])
+        want = torch.softmax(logits.float(), -1).max(-1)[0][:, ::4]
+        assert (confs[:, :want.shape[1]] - want).abs().max().item() < 1e-6, env
+
+
 def test_cluster_decode_is_run_to_run_deterministic(model_p):
     """Race detector for the fused kernel: teacher-forced (no select / token exchange between steps -- the path where a missing
     barrier between the head MMAs and the next step's operand write once showed up) and free-running, 6 runs each, bitwise."""
