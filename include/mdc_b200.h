@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define MDC_ABI_VERSION 4
+#define MDC_ABI_VERSION 5
 
 /* element types of activations / weights.  MDC_F16 (IEEE half) is only ever the type of the decode-loop weights, see
  * mdc_dims.dec_loop_dtype. */
@@ -202,6 +202,13 @@ typedef struct mdc_decode_state {
                                        at least that many images per cluster, i.e. fewer SMs per batch, so that several batches in
                                        flight (pipeline.py) share the GPU; more than 8 selects the kernel instantiation with two
                                        8-image column blocks per cluster pass.  Does not change results (bitwise). */
+  int32_t ctas_per_sm;              /* 0 / 1 = one decode CTA per SM (deep TMA ring); 2 (with images_per_cluster <= 8) = the compact
+                                       shared-memory layout that lets two clusters -- two independent image groups -- share each
+                                       SM, so that one group's dependent phase chain fills the other's stalls.  Bitwise the same
+                                       results. */
+  int32_t per_op_kernels;           /* 1 = run every step as per-operation kernels (decode.cu: the path of the fp32 token-exact
+                                       mode and of geometries the fused cluster kernel does not cover) even where the fused kernel
+                                       applies -- the parity tests compare the two implementations on the same inputs. */
 } mdc_decode_state;
 
 size_t mdc_decode_workspace_bytes(const mdc_model* m, int B);

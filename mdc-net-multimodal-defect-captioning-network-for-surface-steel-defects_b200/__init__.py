@@ -6,7 +6,7 @@ attention, fused decode step, batched IoU); there is NO CPU or PyTorch fallback.
 """
 from .config import CFG
 from .tokenizer import Tokenizer, top_k_sampling, top_k_sampling_with_scores_2d
-from .model import Encoder, Decoder, EncoderDecoder, Engine
+from .model import Encoder, Decoder, EncoderDecoder, Engine, decode_options
 from .axial_model import AxialAttention
 from . import axial_model
 from .inference import generate, postprocess, preprocess_gray
@@ -17,7 +17,7 @@ from .kvcache import PagedKVCache, PageAllocator
 from . import parallel
 from . import _lib
 
-__all__ = ["CFG", "Tokenizer", "top_k_sampling", "top_k_sampling_with_scores_2d", "Encoder", "Decoder", "EncoderDecoder", "Engine", "AxialAttention", "axial_model",
+__all__ = ["CFG", "Tokenizer", "top_k_sampling", "top_k_sampling_with_scores_2d", "Encoder", "Decoder", "EncoderDecoder", "Engine", "decode_options", "AxialAttention", "axial_model",
            "generate", "postprocess", "preprocess_gray", "GenerationPipeline", "generate_stream", "bbox_iou", "calculate_batch_iou", "calculate_batch_max_iou",
            "calculate_batch_max_iou_torchvision", "calculate_batch_max_iou_masked", "giou_pairwise",
            "giou_loss_with_scores", "calculate_iou", "iou_loss", "PagedKVCache", "PageAllocator", "parallel"]

@@ -58,6 +58,8 @@ class DecodeState(C.Structure):
         ("x_override", C.c_void_p), ("x_override_ld", C.c_int32),
         ("scratch", C.c_void_p), ("scratch_bytes", C.c_size_t),
         ("images_per_cluster", C.c_int32),
+        ("ctas_per_sm", C.c_int32),
+        ("per_op_kernels", C.c_int32),
     ]
 
 
@@ -164,8 +166,9 @@ def launch_count(device=None):
     return int(lib().mdc_ctx_launch_count(ctx(device))) + _replayed.get(_dev_index(device), 0)
 
 
-def stream_ptr():
-    return _P(torch.cuda.current_stream().cuda_stream)
+def stream_ptr(device=None):
+    """The current torch stream of `device` (default: the current device)."""
+    return _P(torch.cuda.current_stream(device).cuda_stream)
 
 
 def ptr(t):

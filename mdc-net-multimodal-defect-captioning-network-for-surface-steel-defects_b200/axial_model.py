@@ -47,7 +47,8 @@ class AxialAttention(nn.Module, _EngineOwner):
         out = torch.empty_like(x)
         wsb = eng.lib.mdc_axial_workspace_bytes(eng.handle, B, n)
         ws = torch.empty(wsb, dtype=torch.uint8, device=eng.device)
-        L.check(eng.lib.mdc_axial_attention(eng.handle, L.ptr(x), B, n, soq, L.ptr(out), L.ptr(ws), wsb, L.stream_ptr()))
+        with torch.cuda.device(eng.device):
+            L.check(eng.lib.mdc_axial_attention(eng.handle, L.ptr(x), B, n, soq, L.ptr(out), L.ptr(ws), wsb, L.stream_ptr(eng.device)))
         return out
 
 
@@ -86,7 +87,8 @@ class Decoder(_BaseDecoder):
         x = torch.empty((B, n, self.dim), dtype=torch.float32, device=eng.device)
         wsb = eng.lib.mdc_axial_embed_workspace_bytes(eng.handle, B, n)
         ws = torch.empty(wsb, dtype=torch.uint8, device=eng.device)
-        L.check(eng.lib.mdc_axial_embed(eng.handle, L.ptr(tokens), n, B, n, L.ptr(pos), 0, L.ptr(x), L.ptr(ws), wsb, L.stream_ptr()))
+        with torch.cuda.device(eng.device):
+            L.check(eng.lib.mdc_axial_embed(eng.handle, L.ptr(tokens), n, B, n, L.ptr(pos), 0, L.ptr(x), L.ptr(ws), wsb, L.stream_ptr(eng.device)))
         return self._run_forced(eng, memory, tokens, n, n, 0, x_override=x)
 
 

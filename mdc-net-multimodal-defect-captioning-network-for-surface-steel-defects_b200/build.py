@@ -9,6 +9,11 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libmdc_b200.so")
+# developer build (-DMDC_DEVTOOLS): the same sources plus the decode kernel's phase-trace instantiations and the environment
+# switches tools/*.py use for A/B runs (MDC_DECODE_TRACE_PTR, MDC_DECODE_IPC, MDC_DECODE_CPS, MDC_GEMM_BACKEND, MDC_ATTN_BACKEND).
+# Never loaded by the package unless MDC_LIB_PATH points at it.
+OBJ_DEV = os.path.join(HERE, "build_dev")
+LIB_DEV = os.path.join(HERE, "libmdc_b200_dev.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "--std=c++17",
          "-Xcompiler", "-fPIC", "-Xptxas", "-v", "--expt-relaxed-constexpr"]
@@ -24,7 +29,19 @@ def _deps_mtime():
     return max(os.path.getmtime(h) for h in hdrs)
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, devtools=False):
+    global OBJ, LIB
+    if devtools:
+        saved = (OBJ, LIB)
+        OBJ, LIB = OBJ_DEV, LIB_DEV
+        try:
+            return _build(force, verbose, ["-DMDC_DEVTOOLS"])
+        finally:
+            OBJ, LIB = saved
+    return _build(force, verbose, [])
+
+
+def _build(force, verbose, extra):
     os.makedirs(OBJ, exist_ok=True)
     hdr_m = _deps_mtime()
     jobs = []
@@ -36,7 +53,7 @@ def build(force=False, verbose=False):
 
     def cc(job):
         s, o = job
-        r = subprocess.run([NVCC, *FLAGS, "-c", s, "-o", o], capture_output=True, text=True)
+        r = subprocess.run([NVCC, *FLAGS, *extra, "-c", s, "-o", o], capture_output=True, text=True)
         return s, r
 
     with ThreadPoolExecutor(max_workers=min(8, max(1, len(jobs)))) as ex:
@@ -56,4 +73,4 @@ def build(force=False, verbose=False):
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, devtools="--devtools" in sys.argv))

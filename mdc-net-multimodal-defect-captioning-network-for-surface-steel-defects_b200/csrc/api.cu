@@ -24,16 +24,19 @@ extern "C" int mdc_ctx_create(int device, mdc_ctx** out) {
     MDC_FAIL(-1, "mdc_ctx_create: device %d is sm_%d%d; this library is built for sm_100a (B200) only", device, p.major, p.minor);
   mdc_ctx* c = (mdc_ctx*)calloc(1, sizeof(mdc_ctx));
   c->device = device; c->sm_count = p.multiProcessorCount;
+#ifdef MDC_DEVTOOLS   // developer build only: kernel A/B switches (the product library has one path per operation)
   const char* gb = getenv("MDC_GEMM_BACKEND");
   c->gemm_backend_simt = (gb && !strcmp(gb, "simt"));
   const char* ab = getenv("MDC_ATTN_BACKEND");
   c->attn_backend_simt = (ab && !strcmp(ab, "simt"));
+#endif
   *out = c; return 0;
 }
 
 extern "C" int mdc_ctx_destroy(mdc_ctx* ctx) {
   if (!ctx) return 0;
   gemm_tc_ctx_destroy(ctx);
+  decode_cluster_ctx_destroy(ctx);
   free(ctx); return 0;
 }
 

@@ -195,6 +195,7 @@ extern "C" int mdc_strip_attention(mdc_ctx* ctx, int dtype, const void* qkv, int
                                    int n_strips, int strip_len, int heads, int head_dim, float scale,
                                    int softmax_over_queries, void* stream) {
   MDC_CHECK_ARG(ctx && qkv && out);
+  MDC_CHECK_DEVICE(ctx);
   MDC_CHECK_ARG(dtype == MDC_F32 || dtype == MDC_BF16);
   MDC_CHECK_ARG(n_strips >= 0 && strip_len > 0 && heads > 0 && heads <= 65535 && n_strips <= 65535 * 32);
   MDC_CHECK_ARG(ld_qkv % 8 == 0 && head_dim % 8 == 0);

@@ -28,11 +28,17 @@ struct mdc_ctx {
   int device;
   int sm_count;
   int64_t launches;
-  int gemm_backend_simt;      // MDC_GEMM_BACKEND=simt forces the FFMA kernel for bf16 too (debug aid)
+  int gemm_backend_simt;      // developer builds (-DMDC_DEVTOOLS) only: MDC_GEMM_BACKEND=simt forces the FFMA kernel for bf16 too
   int attn_backend_simt;
   void* tmap_cache;           // opaque, owned by gemm_tcgen05.cu
   void* encode_fn;            // cuTensorMapEncodeTiled entry point
+  void* decode_state;         // opaque, owned by decode_cluster.cu (per-device occupancy / smem opt-in state)
 };
+
+#define MDC_MAX_DEVICES 32
+// every entry point runs on the device its context was created for (cudaFuncSetAttribute, streams and tensor maps are per device)
+#define MDC_CHECK_DEVICE(ctx) do { int dev__ = -1; MDC_CUDA(cudaGetDevice(&dev__)); if (dev__ != (ctx)->device) \
+    MDC_FAIL(-5, "%s:%d: current CUDA device %d is not the context's device %d (wrap the call in a device guard)", __FILE__, __LINE__, dev__, (ctx)->device); } while (0)
 
 struct mdc_model {
   mdc_ctx* ctx;
@@ -92,12 +98,15 @@ __device__ __forceinline__ void store8(bf16* p, const float* v) {
 }
 
 // raise a kernel's dynamic-smem limit only when a launch needs more than any launch before it (one driver call, not one per launch)
+// (the attribute is per device: the high-water mark is kept per device index)
 #define MDC_ENSURE_SMEM(kernel, bytes)                                                                          \
   do {                                                                                                          \
-    static int cur__ = 48 * 1024;                                                                               \
-    if ((int)(bytes) > cur__) {                                                                                 \
+    static int cur__[MDC_MAX_DEVICES];                                                                          \
+    int dev__ = 0; MDC_CUDA(cudaGetDevice(&dev__));                                                             \
+    if (dev__ < 0 || dev__ >= MDC_MAX_DEVICES) MDC_FAIL(-2, "device index %d out of range", dev__);             \
+    if ((int)(bytes) > 48 * 1024 && (int)(bytes) > cur__[dev__]) {                                              \
       MDC_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes)));        \
-      cur__ = (int)(bytes);                                                                                     \
+      cur__[dev__] = (int)(bytes);                                                                              \
     }                                                                                                           \
   } while (0)
 
@@ -115,3 +124,4 @@ int gemm_tc_supported(int M, int N, int K, int64_t lda, int64_t ldw);
 void gemm_tc_ctx_destroy(mdc_ctx* ctx);
 int mdc_make_tmap_2d(mdc_ctx* ctx, const void* ptr, int64_t rows, int64_t cols, int64_t ld, int box_cols, int box_rows, int swizzle_mode, void* out_map);
 void decode_cluster_model_destroy(mdc_model* m);
+void decode_cluster_ctx_destroy(mdc_ctx* ctx);

@@ -613,6 +613,7 @@ extern "C" size_t mdc_kv_page_bytes(const mdc_model* m) {
 
 extern "C" int mdc_decode_steps(mdc_model* m, const mdc_decode_state* st, int t_begin, int t_end, void* stream) {
   MDC_CHECK_ARG(m && st && st->B > 0 && st->tokens && st->kv_pool && st->page_table && st->cross_kv && st->scratch);
+  MDC_CHECK_DEVICE(m->ctx);
   MDC_CHECK_ARG(t_begin >= 0 && t_end >= t_begin);
   MDC_CHECK_ARG(st->x_override || st->pos_override || t_end <= m->d.max_pos);   // Q6: the pos table has max_len-1 rows
   MDC_CHECK_ARG(t_end <= st->pages_per_seq * m->d.page_tokens);
@@ -637,6 +638,7 @@ extern "C" int mdc_decode_steps(mdc_model* m, const mdc_decode_state* st, int t_
 extern "C" int mdc_select(mdc_ctx* ctx, const float* logits, int64_t ld, int B, int V, int top_k, float top_p, const float* uniforms,
                           int32_t* token_out, float* conf_out, float* prob_out, void* stream) {
   MDC_CHECK_ARG(ctx && logits && B > 0 && V > 0 && V <= 4096 && (token_out || conf_out || prob_out));
+  MDC_CHECK_DEVICE(ctx);
   int Vp2 = next_pow2(V);
   size_t smem = (size_t)(V + Vp2) * sizeof(float);
   select_kernel<<<B, SEL_THREADS, smem, (cudaStream_t)stream>>>(logits, ld, V, Vp2, top_k, top_p, uniforms, token_out, conf_out, prob_out);

@@ -45,11 +45,11 @@ constexpr int FS = FFN / CS;       // hidden units per CTA (256)
 constexpr int NCT = 256;           // consumer threads (8 warps)
 constexpr int NT = NCT + 32;       // + producer warp
 constexpr int XP = DM + 8;         // fp16 elements per padded activation row (528 B: conflict-free ldmatrix)
-constexpr int STAGE_BYTES = 32768;
+constexpr int STAGE_BYTES = 16384;   // one ring stage: a 32-row weight block (32 x 512 B), the K or V panel of one image (S <= 256 keys x 64 B) or packed self-KV pages
 constexpr int VSL = 40;            // vocab rows per CTA; 8*40 = 320 >= V
 constexpr int PSTR = 36;           // floats per attention partial: m, l, -, -, o[32] (o is 16-byte aligned)
 constexpr int NPART = 9;           // attention partials per image: one per warp (interleaved key tiles) + the step's own key
-constexpr int NS_MAX = 5;
+constexpr int NS_MAX = 10;
 
 // ---- shared memory map (bytes from the 1024-aligned base), per instantiation -------------------------------------
 // NB = 8-image column blocks per cluster pass: NB = 1 (up to 8 images per cluster: lowest latency, the serial path) or NB = 2
@@ -57,10 +57,11 @@ constexpr int NS_MAX = 5;
 // images -- less SM-time per image, used by the batch pipeline).  With 16 images the per-group buffers double, so the ring
 // has 4 stages instead of 5, the FFN2 receive buffer shares its bytes with the attention partials and the select scratch
 // with the q/k staging (disjoint phases, see the ordering notes at the uses).
-template <int NB>
+// OVL: the overlays described above (always on with NB = 2; with NB = 1 they make the two-CTAs-per-SM layout fit).
+template <int NB, int NSTG, bool OVL>
 struct Lay {
   static constexpr int GMX = 8 * NB;                             // max images per cluster pass
-  static constexpr int NS = NB == 1 ? 5 : 4;                     // ring stages (160 KB in flight at NB = 1: +1.2 % over 4, same-box A/B)
+  static constexpr int NS = NSTG;                                // ring stages (160 KB in flight at NB = 1: +1.2 % over 4, same-box A/B)
   static constexpr int ACT_BYTES = GMX * XP * 2;
   static constexpr int OFF_RING = 0;
   static constexpr int OFF_XH = OFF_RING + NS * STAGE_BYTES;      // LN output (fp16 projection operand)
@@ -71,33 +72,33 @@ struct Lay {
   static constexpr int OFF_PART = OFF_YRECV + GMX * DM * 4;       // [GMX][NPART][PSTR] f32 attention partials
   static constexpr int PART_BYTES = GMX * NPART * PSTR * 4;
   static constexpr int F2_BYTES = CS * GMX * 32 * 4;              // [CS src][GMX][32] f32 FFN2 partial sums (peers write)
-  static constexpr int OFF_F2RECV = NB == 1 ? OFF_PART + PART_BYTES : OFF_PART;
-  static constexpr int OFF_QS = NB == 1 ? OFF_F2RECV + F2_BYTES : OFF_PART + (PART_BYTES > F2_BYTES ? PART_BYTES : F2_BYTES);   // [GMX][32] f32 scaled query of the own head
+  static constexpr int OFF_F2RECV = !OVL ? OFF_PART + PART_BYTES : OFF_PART;
+  static constexpr int OFF_QS = !OVL ? OFF_F2RECV + F2_BYTES : OFF_PART + (PART_BYTES > F2_BYTES ? PART_BYTES : F2_BYTES);   // [GMX][32] f32 scaled query of the own head
   static constexpr int OFF_KNEW = OFF_QS + GMX * 32 * 4;          // [GMX][32] f32 this step's key (bf16-rounded)
   static constexpr int OFF_VNEW = OFF_KNEW + GMX * 32 * 4;
   static constexpr int OFF_YTMP = OFF_VNEW + GMX * 32 * 4;        // [GMX][32] f32 own slice of a projection before the push
   static constexpr int OFF_QH = OFF_YTMP + GMX * 32 * 4;          // [GMX][32] bf16 scaled query (MMA A operand)
   static constexpr int OFF_LRECV = OFF_QH + GMX * 32 * 2;         // [NB][CS src][VSL] f32 logits of the images this CTA selects for
   static constexpr int SEL_BYTES = (CS * VSL + 512) * 4;          // select scratch: 320 + 512 floats
-  static constexpr int OFF_SEL = NB == 1 ? OFF_LRECV + NB * CS * VSL * 4 : OFF_QS;
-  static constexpr int OFF_TOK = NB == 1 ? OFF_SEL + SEL_BYTES : OFF_LRECV + NB * CS * VSL * 4;    // [2][GMX] int32 (double buffered by step parity)
+  static constexpr int OFF_SEL = !OVL ? OFF_LRECV + NB * CS * VSL * 4 : OFF_QS;
+  static constexpr int OFF_TOK = !OVL ? OFF_SEL + SEL_BYTES : OFF_LRECV + NB * CS * VSL * 4;    // [2][GMX] int32 (double buffered by step parity)
   static constexpr int OFF_PAGES = OFF_TOK + 2 * GMX * 4;         // [GMX][32] int32
-  static constexpr int OFF_PADF = OFF_PAGES + GMX * 32 * 4;       // [GMX][256] u8
-  static constexpr int OFF_HASPAD = OFF_PADF + GMX * 256;         // [GMX] int32: any PAD token among the keys so far
+  static constexpr int OFF_PADF = OFF_PAGES + GMX * 32 * 4;       // [GMX][8] u32: bit u of an image's 256-bit row = token u is PAD
+  static constexpr int OFF_HASPAD = OFF_PADF + GMX * 32;          // [GMX] int32: any PAD token among the keys so far
   static constexpr int OFF_BARS = OFF_HASPAD + GMX * 4;           // mbarriers
   static constexpr int NBARS = 2 * NS_MAX + 5;
   static constexpr int SMEM_USED = OFF_BARS + NBARS * 8;
   static constexpr int SMEM_BYTES = SMEM_USED + 1024;             // + alignment slack
   static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
   static_assert(OFF_XH % 16 == 0 && OFF_XRES % 16 == 0 && OFF_PART % 16 == 0 && OFF_QS % 16 == 0 && OFF_BARS % 8 == 0, "alignment");
-  static_assert(3 * GMX * 32 * 4 >= SEL_BYTES || NB == 1, "select scratch must fit the q/k/v staging it shares");
+  static_assert(!OVL || 4 * GMX * 32 * 4 >= SEL_BYTES, "select scratch must fit the q/k/v/y staging it shares");
 };
 
 enum { BAR_FULL = 0, BAR_EMPTY = NS_MAX, BAR_O = 2 * NS_MAX, BAR_Y, BAR_F2, BAR_LG, BAR_TOK, BAR_COUNT };
 
 struct __align__(64) FusedParams {
   CUtensorMap m_in[8], m_so[8], m_ca[8], m_co[8], m_f1[8], m_f2[8];
-  CUtensorMap m_head, m_ckv, m_pool;
+  CUtensorMap m_head, m_head8, m_ckv, m_pool;
   const float* b_in[8]; const float* b_so[8]; const float* ln1w[8]; const float* ln1b[8];
   const float* b_ca[8]; const float* b_co[8]; const float* ln2w[8]; const float* ln2b[8];
   const float* b_f1[8]; const float* b_f2[8]; const float* ln3w[8]; const float* ln3b[8];
@@ -127,19 +128,18 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 __device__ __forceinline__ void mbar_arrive_n(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
-// bounded wait: a protocol bug traps (reported as a launch failure) instead of hanging the GPU box
+// bounded wait: a protocol bug traps (reported as a launch failure) instead of hanging the GPU box.  try_wait carries a suspend-time
+// hint: the waiting warp SLEEPS in hardware until the phase completes (or the hint expires) instead of spinning -- a spinning
+// waiter (without the hint try_wait returns after a few hundred cycles: 1.2 G of the 6.5 G instructions of a 256-image launch were
+// this loop, profiles/r2b) takes issue slots from the warps of the same SM sub-partition that have work, in particular from
+// the second CTA that shares the SM in the two-CTAs-per-SM variant.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t done = 0, spins = 0;
-  long long t0 = 0;
   while (true) {
-    asm volatile("{\n\t.reg .pred P1;\n\tmbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\tselp.u32 %0, 1, 0, P1;\n\t}\n"
-                 : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    asm volatile("{\n\t.reg .pred P1;\n\tmbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, P1;\n\t}\n"
+                 : "=r"(done) : "r"(bar), "r"(parity), "r"(1000000u) : "memory");      // hint: 1 ms
     if (done) break;
-    if ((++spins & 255u) == 0) {
-      long long now = clock64();
-      if (t0 == 0) t0 = now;
-      else if (now - t0 > 3000000000LL) __trap();   // ~1.5 s
-    }
+    if (++spins > 2000u) __trap();          // ~2 s
   }
 }
 __device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t rank) {
@@ -263,7 +263,7 @@ __device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.
 // asm: program order is issue order) -- the chunk pays the ldmatrix latency once.  Requires tl < ntile.  On return m_out / l_out
 // are valid in lanes 0-3; the un-normalised output of dims mt*16 + {g, g+8} sits in lanes with q == 0 as o[mt][0] and o[mt][2].
 __device__ __forceinline__ void attn_chunk2(uint32_t kp, uint32_t vp, const uint32_t (&aq)[2][2], int tl, int tstep, int ntile, int nkeys,
-                                            const uint8_t* padf, float& m_out, float& l_out, float (&o)[2][4]) {
+                                            const uint32_t* padf, float& m_out, float& l_out, float (&o)[2][4]) {
   const int lane = threadIdx.x & 31, q4 = lane & 3;
   const uint32_t a_k0[4] = {aq[0][0], 0u, aq[0][1], 0u}, a_k1[4] = {aq[1][0], 0u, aq[1][1], 0u};
   const bool two = tl + tstep < ntile;
@@ -300,7 +300,7 @@ __device__ __forceinline__ void attn_chunk2(uint32_t kp, uint32_t vp, const uint
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       const int key = (i ? k0b : k0a) + (e >> 1) * 8 + 2 * q4 + (e & 1);
-      if (padf != nullptr && padf[key]) sc[i][e] += LOG2E;               // float PAD-key bias +1.0 (Q7), in log2 units (padf: rare)
+      if (padf != nullptr && ((padf[key >> 5] >> (key & 31)) & 1u)) sc[i][e] += LOG2E;   // float PAD-key bias +1.0 (Q7), in log2 units (padf: rare)
       if (key >= nkeys || (i == 1 && !two)) sc[i][e] = -INFINITY;        // tail of the last tile / clamped duplicate tile
     }
   float mx = fmaxf(fmaxf(fmaxf(sc[0][0], sc[0][1]), fmaxf(sc[0][2], sc[0][3])), fmaxf(fmaxf(sc[1][0], sc[1][1]), fmaxf(sc[1][2], sc[1][3])));
@@ -365,9 +365,11 @@ __device__ __forceinline__ void warp_greedy_select(const float* lg, int V, int& 
 
 // kTrace: developer build of the same kernel that stamps clock64() at phase boundaries (tools/decode_trace.py); the production
 // instantiation carries no trace instructions.
-template <bool kTrace, int NB>
-__global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(NT, 1) decode_fused_kernel(const __grid_constant__ FusedParams P) {
-  using Y = Lay<NB>;
+// NSTG ring stages; MINB = 2: compact shared-memory layout and a register budget that let two CTAs (of two different clusters,
+// i.e. two independent image groups) share an SM, so that one group's dependent phase chain fills the other's stalls.
+template <bool kTrace, int NB, int NSTG, int MINB>
+__global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(NT, MINB) decode_fused_kernel(const __grid_constant__ FusedParams P) {
+  using Y = Lay<NB, NSTG, NB == 2 || MINB == 2>;
   constexpr int GMX = Y::GMX, NS = Y::NS;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -383,7 +385,7 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(NT, 1) decode_fused
   float* ytmp = (float*)(smem + Y::OFF_YTMP); float* part = (float*)(smem + Y::OFF_PART);
   bf16* qh = (bf16*)(smem + Y::OFF_QH);
   float* lrecv = (float*)(smem + Y::OFF_LRECV); float* selbuf = (float*)(smem + Y::OFF_SEL);
-  int* tokbuf = (int*)(smem + Y::OFF_TOK); int* pages = (int*)(smem + Y::OFF_PAGES); uint8_t* padflag = smem + Y::OFF_PADF;
+  int* tokbuf = (int*)(smem + Y::OFF_TOK); int* pages = (int*)(smem + Y::OFF_PAGES); uint32_t* padbits = (uint32_t*)(smem + Y::OFF_PADF);
   int* haspad = (int*)(smem + Y::OFF_HASPAD);
   const uint32_t bars = sbase + Y::OFF_BARS;
   auto bar = [&](int i) -> uint32_t { return bars + i * 8; };
@@ -406,7 +408,6 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(NT, 1) decode_fused
   // (2 * wpi >= npg) and a 32 KB stage holds the K and V panels (wpi * 2 KB each) of ips = 8 / wpi images -- early steps pack 8 or 4
   // images into a stage.  A function of the step only (never of the batch: results stay batch-invariant).
   auto self_wpi = [](int npg) { return npg <= 2 ? 1 : (npg <= 4 ? 2 : (npg <= 8 ? 4 : 8)); };
-  const uint32_t cross_panel = ((uint32_t)S * 64u + 1023u) & ~1023u;
 
   // ring cursors (producer and consumers keep their own copies)
   uint32_t slot = 0, phase = 0;
@@ -420,13 +421,19 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(NT, 1) decode_fused
       const int g = i >> 5, j = i & 31;
       pages[i] = (g < G && j < P.pages_per_seq) ? P.page_table[(int64_t)(img0 + g) * P.pages_per_seq + j] : 0;
     }
-    if (tid < GMX) haspad[tid] = 0;
+    for (int i = tid; i < GMX * 8; i += NT) {      // PAD bits of the known prefix (tokens [0, t_begin))
+      const int g = i >> 3, w = i & 7;
+      uint32_t bits = 0;
+      if (g < G)
+        for (int b = 0; b < 32 && w * 32 + b < P.t_begin; ++b)
+          if (P.tokens[(int64_t)(img0 + g) * P.tokens_ld + w * 32 + b] == P.pad_idx) bits |= 1u << b;
+      padbits[i] = bits;
+    }
     __syncthreads();
-    for (int i = tid; i < GMX * 256; i += NT) {
-      const int g = i >> 8, u = i & 255;
-      const bool pd = (g < G && u < P.t_begin) ? (P.tokens[(int64_t)(img0 + g) * P.tokens_ld + u] == P.pad_idx) : false;
-      padflag[i] = pd;
-      if (pd) haspad[g] = 1;
+    if (tid < GMX) {
+      uint32_t any = 0;
+      for (int w = 0; w < 8; ++w) any |= padbits[tid * 8 + w];
+      haspad[tid] = any != 0u;
     }
     __syncthreads();
     cluster_sync_all();          // no peer may push into this CTA before its buffers are set up for the group
@@ -448,33 +455,43 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(NT, 1) decode_fused
       };
       for (int t = P.t_begin; t < P.t_end; ++t) {
         const int npg = (t + P.PT - 1) / P.PT;     // pages holding keys 0..t-1
-        const int wpi_t = self_wpi(npg), ips_t = 8 / wpi_t, nS = (P.G + ips_t - 1) / ips_t;
+        const int wpi_t = self_wpi(npg);
+        const bool split_kv = wpi_t == 8;          // K panel and V panel of ONE image fill a stage each
+        const int ips_t = split_kv ? 1 : 4 / wpi_t, nS = split_kv ? 2 * P.G : (P.G + ips_t - 1) / ips_t;
         const uint32_t self_panel = (uint32_t)wpi_t * 2048u;
         for (int l = 0; l < L; ++l) {
-          {  // in-proj: q rows + k rows | v rows
-            uint32_t st = acquire(); uint32_t fb = bar(BAR_FULL + slot);
-            if (lane == 0) {
-              mbar_expect_tx(fb, 2 * 32 * 512);
-              load_rows(&P.m_in[l], st, fb, 0, rank * HD, 32);
-              load_rows(&P.m_in[l], st + 16384, fb, 0, DM + rank * HD, 32);
-            }
-            advance();
-            st = acquire(); fb = bar(BAR_FULL + slot);
-            if (lane == 0) { mbar_expect_tx(fb, 32 * 512); load_rows(&P.m_in[l], st, fb, 0, 2 * DM + rank * HD, 32); }
+          for (int part = 0; part < 3; ++part) {   // in-proj: own head's q rows, k rows, v rows
+            const uint32_t st = acquire(); const uint32_t fb = bar(BAR_FULL + slot);
+            if (lane == 0) { mbar_expect_tx(fb, 32 * 512); load_rows(&P.m_in[l], st, fb, 0, part * DM + rank * HD, 32); }
             advance();
           }
-          for (int sg = 0; sg < nS; ++sg) {        // self-KV: K and V pages of images [sg*ips, ...), panels [gi][k|v]
-            const int g0 = sg * ips_t, gn = max(0, min(ips_t, G - g0));
-            const int ops = gn * 2 * npg;
-            const uint32_t st = acquire(); const uint32_t fb = bar(BAR_FULL + slot);
-            if (lane == 0) mbar_expect_tx(fb, ops * P.PT * 64);
-            __syncwarp();
-            for (int op = lane; op < ops; op += 32) {
-              const int pn = op / npg, j = op - pn * npg;          // pn = gi*2 + which
-              const int page = pages[(g0 + (pn >> 1)) * 32 + j];
-              tma_2d(&P.m_pool, fb, st + pn * self_panel + j * (P.PT * 64), rank * HD, ((page * L + l) * 2 + (pn & 1)) * P.PT);
+          if (!split_kv) {
+            for (int sg = 0; sg < nS; ++sg) {      // self-KV: K and V pages of images [sg*ips, ...), panels [gi][k|v]
+              const int g0 = sg * ips_t, gn = max(0, min(ips_t, G - g0));
+              const int ops = gn * 2 * npg;
+              const uint32_t st = acquire(); const uint32_t fb = bar(BAR_FULL + slot);
+              if (lane == 0) mbar_expect_tx(fb, ops * P.PT * 64);
+              __syncwarp();
+              for (int op = lane; op < ops; op += 32) {
+                const int pn = op / npg, j = op - pn * npg;          // pn = gi*2 + which
+                const int page = pages[(g0 + (pn >> 1)) * 32 + j];
+                tma_2d(&P.m_pool, fb, st + pn * self_panel + j * (P.PT * 64), rank * HD, ((page * L + l) * 2 + (pn & 1)) * P.PT);
+              }
+              advance();
             }
-            advance();
+          } else {
+            for (int sg = 0; sg < nS; ++sg) {      // more than 8 pages of keys: the K pages of image sg/2 in one stage, its V pages in the next
+              const int g = sg >> 1, which = sg & 1;
+              const int ops = g < G ? npg : 0;
+              const uint32_t st = acquire(); const uint32_t fb = bar(BAR_FULL + slot);
+              if (lane == 0) mbar_expect_tx(fb, ops * P.PT * 64);
+              __syncwarp();
+              if (lane < ops) {
+                const int page = pages[g * 32 + lane];
+                tma_2d(&P.m_pool, fb, st + lane * (P.PT * 64), rank * HD, ((page * L + l) * 2 + which) * P.PT);
+              }
+              advance();
+            }
           }
           {  // self out-proj rows, cross-q rows
             uint32_t st = acquire(); uint32_t fb = bar(BAR_FULL + slot);
@@ -484,13 +501,13 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(NT, 1) decode_fused
             if (lane == 0) { mbar_expect_tx(fb, 32 * 512); load_rows(&P.m_ca[l], st, fb, 0, rank * 32, 32); }
             advance();
           }
-          for (int g = 0; g < nC; ++g) {           // cross K and V panel of image g
+          for (int sg = 0; sg < 2 * nC; ++sg) {    // cross K panel of image sg/2 in one stage, its V panel in the next
+            const int g = sg >> 1, which = sg & 1;
             const uint32_t st = acquire(); const uint32_t fb = bar(BAR_FULL + slot);
             if (lane == 0) {
               if (g < G) {
-                mbar_expect_tx(fb, 2 * S * 64);
-                tma_2d(&P.m_ckv, fb, st, rank * HD, (l * P.B + img0 + g) * S);
-                tma_2d(&P.m_ckv, fb, st + cross_panel, DM + rank * HD, (l * P.B + img0 + g) * S);
+                mbar_expect_tx(fb, S * 64);
+                tma_2d(&P.m_ckv, fb, st, which * DM + rank * HD, (l * P.B + img0 + g) * S);
               } else mbar_expect_tx(fb, 0);
             }
             advance();
@@ -500,20 +517,27 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(NT, 1) decode_fused
             if (lane == 0) { mbar_expect_tx(fb, 32 * 512); load_rows(&P.m_co[l], st, fb, 0, rank * 32, 32); }
             advance();
           }
-          for (int s4 = 0; s4 < 4; ++s4) {         // FFN1: own hidden rows
+          for (int s8 = 0; s8 < 8; ++s8) {         // FFN1: own hidden rows, 32 per stage
             const uint32_t st = acquire(); const uint32_t fb = bar(BAR_FULL + slot);
-            if (lane == 0) { mbar_expect_tx(fb, 64 * 512); load_rows(&P.m_f1[l], st, fb, 0, rank * FS + s4 * 64, 64); }
+            if (lane == 0) { mbar_expect_tx(fb, 32 * 512); load_rows(&P.m_f1[l], st, fb, 0, rank * FS + s8 * 32, 32); }
             advance();
           }
-          for (int s4 = 0; s4 < 4; ++s4) {         // FFN2: K-split over the own hidden columns
+          for (int s8 = 0; s8 < 8; ++s8) {         // FFN2: K-split over the own hidden columns, 32 output features per stage
             const uint32_t st = acquire(); const uint32_t fb = bar(BAR_FULL + slot);
-            if (lane == 0) { mbar_expect_tx(fb, 64 * 512); load_rows(&P.m_f2[l], st, fb, rank * FS, s4 * 64, 64); }
+            if (lane == 0) { mbar_expect_tx(fb, 32 * 512); load_rows(&P.m_f2[l], st, fb, rank * FS, s8 * 32, 32); }
             advance();
           }
         }
-        {  // vocabulary head rows
-          const uint32_t st = acquire(); const uint32_t fb = bar(BAR_FULL + slot);
-          if (lane == 0) { mbar_expect_tx(fb, VSL * 512); load_rows(&P.m_head, st, fb, 0, rank * VSL, VSL); }
+        {  // vocabulary head rows: [0,32) of the own 40 in one stage, [32,40) in the next
+          uint32_t st = acquire(); uint32_t fb = bar(BAR_FULL + slot);
+          if (lane == 0) { mbar_expect_tx(fb, 32 * 512); load_rows(&P.m_head, st, fb, 0, rank * VSL, 32); }
+          advance();
+          st = acquire(); fb = bar(BAR_FULL + slot);
+          if (lane == 0) {
+            mbar_expect_tx(fb, 8 * 512);
+#pragma unroll
+            for (int kb = 0; kb < 4; ++kb) tma_2d(&P.m_head8, fb, st + kb * 8 * 128, kb * 64, rank * VSL + 32);
+          }
           advance();
         }
       }
@@ -526,6 +550,13 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(NT, 1) decode_fused
         mbar_wait(bar(BAR_FULL + slot), phase);
         if (kTrace) cons_wait += clock64() - c0;
         return sbase + Y::OFF_RING + slot * STAGE_BYTES;
+      };
+      auto stage_wait_next = [&]() -> uint32_t {     // the stage after the cursor (two-stage jobs: K panel, then V panel)
+        const uint32_t s1 = slot + 1 == NS ? 0u : slot + 1, p1 = slot + 1 == NS ? phase ^ 1u : phase;
+        const long long c0 = kTrace ? clock64() : 0;
+        mbar_wait(bar(BAR_FULL + s1), p1);
+        if (kTrace) cons_wait += clock64() - c0;
+        return sbase + Y::OFF_RING + s1 * STAGE_BYTES;
       };
       auto xwait = [&](int which, uint32_t& ph) {    // wait for a push-style exchange
         const long long c0 = kTrace ? clock64() : 0;
@@ -633,8 +664,28 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(NT, 1) decode_fused
         for (int nb = 0; nb < NB; ++nb) push_y(gi_t + 8 * nb, ytmp[(gi_t + 8 * nb) * 32 + c_t]);
       };
 
+      // one warp's share of one (image, head) attention job: key tiles tl, tl + tstep of the panels kp / vp -> partial slot `pslot`
+      auto attend = [&](uint32_t kp, uint32_t vp, int g, int pslot, int tl, int tstep, int ntile, int nkeys, const uint32_t* padw) {
+        float* pb = part + (g * NPART + pslot) * PSTR;
+        if (tl < ntile) {
+          uint32_t aq[2][2];
+          build_q_frag(qh + g * 32, aq);
+          float m_run, l_run;
+          float o[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+          attn_chunk2(kp, vp, aq, tl, tstep, ntile, nkeys, padw, m_run, l_run, o);
+          if (lane == 0) { pb[0] = m_run; pb[1] = l_run; }
+          if ((lane & 3) == 0) {
+            const int g8 = lane >> 2;
+            pb[4 + g8] = o[0][0]; pb[4 + g8 + 8] = o[0][2];
+            pb[4 + g8 + 16] = o[1][0]; pb[4 + g8 + 24] = o[1][2];
+          }
+        } else if (lane == 0) pb[1] = 0.f;
+      };
+
       for (int t = P.t_begin; t < P.t_end; ++t) {
-        const int wpi_t = self_wpi((t + P.PT - 1) / P.PT), ips_t = 8 / wpi_t, nS = (P.G + ips_t - 1) / ips_t;
+        const int wpi_t = self_wpi((t + P.PT - 1) / P.PT);
+        const bool split_kv = wpi_t == 8;
+        const int ips_t = split_kv ? 1 : 4 / wpi_t, nS = split_kv ? 2 * P.G : (P.G + ips_t - 1) / ips_t;
         const uint32_t self_panel = (uint32_t)wpi_t * 2048u;
         // ---- embedding + positional row (model.py:98-101); PAD flag of the token at position t --------------
         if (warp < G) {
@@ -646,7 +697,7 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(NT, 1) decode_fused
             const int img = warp + 8 * nb;
             if (img < G) {
               const int tok = (P.forced || t == P.t_begin) ? __ldcg(P.tokens + (int64_t)(img0 + img) * P.tokens_ld + t) : tokbuf[(t & 1) * GMX + img];
-              if (lane == 0) { padflag[img * 256 + t] = (tok == P.pad_idx); if (tok == P.pad_idx) haspad[img] = 1; }
+              if (lane == 0 && tok == P.pad_idx) { padbits[img * 8 + (t >> 5)] |= 1u << (t & 31); haspad[img] = 1; }
 #pragma unroll
               for (int j = 0; j < 8; ++j) {
                 const int c = lane + 32 * j;
@@ -660,50 +711,39 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(NT, 1) decode_fused
         cbar();
         for (int l = 0; l < L; ++l) {
           TRACE(t);   // 0: layer start
-          // ---- self-attention in-proj: own head's q | k (stage A) and v (stage B) ---------------------------
+          // ---- self-attention in-proj: own head's q (warps 0-1), k (warps 2-3), v (warps 4-5), one 32-row stage each ------
           {
             const float* bi = P.b_in[l];
+            const int part = warp >> 1;                  // 0 q, 1 k, 2 v (3: no projection work)
             float b0 = 0.f, b1 = 0.f;
-            if (warp < 4) { const int r0 = (warp >> 1) * DM + rank * HD + (warp & 1) * 16 + fg; b0 = __ldg(bi + r0); b1 = __ldg(bi + r0 + 8); }
-            else if (warp < 6) { const int r0 = 2 * DM + rank * HD + (warp & 1) * 16 + fg; b0 = __ldg(bi + r0); b1 = __ldg(bi + r0 + 8); }
-            if (warp < 4) {
-              const uint32_t st = stage_wait();
-              float acc[NB][4];
-              mma_mtile<32, NB>(st + (warp >> 1) * 16384, (warp & 1) * 16, sbase + Y::OFF_XH, acc);
-              const int f = (warp & 1) * 16 + fg;
+            if (part < 3) { const int r0 = part * DM + rank * HD + (warp & 1) * 16 + fg; b0 = __ldg(bi + r0); b1 = __ldg(bi + r0 + 8); }
 #pragma unroll
-              for (int nb = 0; nb < NB; ++nb) {
-                const int o = (8 * nb + 2 * fq) * 32 + f;
-                if (warp < 2) {      // q, pre-scaled
-                  const float q0 = (acc[nb][0] + b0) * scale, q1 = (acc[nb][1] + b0) * scale, q2 = (acc[nb][2] + b1) * scale, q3 = (acc[nb][3] + b1) * scale;
-                  const bf16 r0 = __float2bfloat16_rn(q0), r1 = __float2bfloat16_rn(q1), r2 = __float2bfloat16_rn(q2), r3 = __float2bfloat16_rn(q3);
-                  qh[o] = r0; qh[o + 32] = r1; qh[o + 8] = r2; qh[o + 40] = r3;
-                  // the step's own key meets the same bf16 query as the cached keys
-                  qs[o] = __bfloat162float(r0); qs[o + 32] = __bfloat162float(r1); qs[o + 8] = __bfloat162float(r2); qs[o + 40] = __bfloat162float(r3);
-                } else {             // k, rounded to the cache precision
-                  knew[o] = __bfloat162float(__float2bfloat16_rn(acc[nb][0] + b0));
-                  knew[o + 32] = __bfloat162float(__float2bfloat16_rn(acc[nb][1] + b0));
-                  knew[o + 8] = __bfloat162float(__float2bfloat16_rn(acc[nb][2] + b1));
-                  knew[o + 40] = __bfloat162float(__float2bfloat16_rn(acc[nb][3] + b1));
+            for (int pt = 0; pt < 3; ++pt) {
+              if (part == pt) {
+                const uint32_t st = stage_wait();
+                float acc[NB][4];
+                mma_mtile<32, NB>(st, (warp & 1) * 16, sbase + Y::OFF_XH, acc);
+                const int f = (warp & 1) * 16 + fg;
+#pragma unroll
+                for (int nb = 0; nb < NB; ++nb) {
+                  const int o = (8 * nb + 2 * fq) * 32 + f;
+                  if (pt == 0) {       // q, pre-scaled
+                    const float q0 = (acc[nb][0] + b0) * scale, q1 = (acc[nb][1] + b0) * scale, q2 = (acc[nb][2] + b1) * scale, q3 = (acc[nb][3] + b1) * scale;
+                    const bf16 r0 = __float2bfloat16_rn(q0), r1 = __float2bfloat16_rn(q1), r2 = __float2bfloat16_rn(q2), r3 = __float2bfloat16_rn(q3);
+                    qh[o] = r0; qh[o + 32] = r1; qh[o + 8] = r2; qh[o + 40] = r3;
+                    // the step's own key meets the same bf16 query as the cached keys
+                    qs[o] = __bfloat162float(r0); qs[o + 32] = __bfloat162float(r1); qs[o + 8] = __bfloat162float(r2); qs[o + 40] = __bfloat162float(r3);
+                  } else {             // k / v, rounded to the cache precision
+                    float* dst = pt == 1 ? knew : vnew;
+                    dst[o] = __bfloat162float(__float2bfloat16_rn(acc[nb][0] + b0));
+                    dst[o + 32] = __bfloat162float(__float2bfloat16_rn(acc[nb][1] + b0));
+                    dst[o + 8] = __bfloat162float(__float2bfloat16_rn(acc[nb][2] + b1));
+                    dst[o + 40] = __bfloat162float(__float2bfloat16_rn(acc[nb][3] + b1));
+                  }
                 }
-              }
-              stage_release(2);
-            } else stage_skip();
-            if (warp == 4 || warp == 5) {
-              const uint32_t st = stage_wait();
-              float acc[NB][4];
-              mma_mtile<32, NB>(st, (warp & 1) * 16, sbase + Y::OFF_XH, acc);
-              const int f = (warp & 1) * 16 + fg;
-#pragma unroll
-              for (int nb = 0; nb < NB; ++nb) {
-                const int o = (8 * nb + 2 * fq) * 32 + f;
-                vnew[o] = __bfloat162float(__float2bfloat16_rn(acc[nb][0] + b0));
-                vnew[o + 32] = __bfloat162float(__float2bfloat16_rn(acc[nb][1] + b0));
-                vnew[o + 8] = __bfloat162float(__float2bfloat16_rn(acc[nb][2] + b1));
-                vnew[o + 40] = __bfloat162float(__float2bfloat16_rn(acc[nb][3] + b1));
-              }
-              stage_release(4);
-            } else stage_skip();
+                stage_release(4);
+              } else stage_skip();
+            }
           }
           cbar();
           TRACE(t);   // 1: in-proj done
@@ -721,10 +761,11 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(NT, 1) decode_fused
             *reinterpret_cast<uint4*>(dst) = o;
           }
           TRACE(t);   // 2: append
-          // ---- self-attention, head `rank`: keys [0,t) from the paged cache.  A stage holds ips_t images; its 8 warps split evenly
-          //      over them (wpi_t = 8 / ips_t warps per image, a function of the step only -- never of the batch), the warps of
-          //      an image interleave its key tiles (two per warp at most: wpi_t * 2 * 16 >= t).  The step's own key (still
-          //      in shared memory) is partial #8 ------------------------------------------------------------------------------
+          // ---- self-attention, head `rank`: keys [0,t) from the paged cache.  An image's key tiles are interleaved over wpi_t warps (two
+          //      tiles per warp at most: wpi_t * 2 * 16 >= t; a function of the step only -- never of the batch).  Up to 8 pages of keys:
+          //      a 16 KB stage holds the K and V panels of 4 / wpi_t images and belongs to one half of the warps (even stages: warps
+          //      0-3, odd stages: warps 4-7 -- two stages are worked on at a time); beyond that all 8 warps share one image, its K
+          //      panel in one stage and its V panel in the next.  The step's own key (still in shared memory) is partial #8 --------
           {
             const int ntile = (t + 15) >> 4;
 #pragma unroll
@@ -732,34 +773,30 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(NT, 1) decode_fused
               const int img = warp + 8 * nb;
               if (img < G) {
                 float s_own = warp_sum(qs[img * 32 + lane] * knew[img * 32 + lane]);
-                if (padflag[img * 256 + t]) s_own += LOG2E;
+                if ((padbits[img * 8 + (t >> 5)] >> (t & 31)) & 1u) s_own += LOG2E;
                 float* pb = part + (img * NPART + 8) * PSTR;
                 if (lane == 0) { pb[0] = s_own; pb[1] = 1.0f; }
                 pb[4 + lane] = vnew[img * 32 + lane];
               }
             }
-            const int wpi = wpi_t, gi = warp / wpi, tl = warp - gi * wpi;
-            for (int sg = 0; sg < nS; ++sg) {
-              const int g = sg * ips_t + gi;
-              const uint32_t st = stage_wait();
-              if (g < G) {
-                float* pb = part + (g * NPART + tl) * PSTR;
-                if (tl < ntile) {
-                  const uint32_t kp = st + gi * 2 * self_panel, vp = kp + self_panel;
-                  uint32_t aq[2][2];
-                  build_q_frag(qh + g * 32, aq);
-                  float m_run, l_run;
-                  float o[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
-                  attn_chunk2(kp, vp, aq, tl, wpi, ntile, t, haspad[g] ? padflag + g * 256 : nullptr, m_run, l_run, o);
-                  if (lane == 0) { pb[0] = m_run; pb[1] = l_run; }
-                  if ((lane & 3) == 0) {
-                    const int g8 = lane >> 2;
-                    pb[4 + g8] = o[0][0]; pb[4 + g8 + 8] = o[0][2];
-                    pb[4 + g8 + 16] = o[1][0]; pb[4 + g8 + 24] = o[1][2];
-                  }
-                } else if (lane == 0) pb[1] = 0.f;
+            if (!split_kv) {
+              const int wpi = wpi_t, half = warp >> 2, w4 = warp & 3, gi = w4 / wpi, tl = w4 - gi * wpi;
+              for (int sg = 0; sg < nS; ++sg) {
+                if ((sg & 1) != half) { stage_skip(); continue; }
+                const int g = sg * ips_t + gi;
+                const uint32_t st = stage_wait();
+                if (g < G) {
+                  const uint32_t kp = st + gi * 2 * self_panel;
+                  attend(kp, kp + self_panel, g, tl, tl, wpi, ntile, t, haspad[g] ? padbits + g * 8 : nullptr);
+                }
+                stage_release(2);
               }
-              stage_release();
+            } else {
+              for (int g = 0; g < P.G; ++g) {
+                const uint32_t kp = stage_wait(), vp = stage_wait_next();
+                if (g < G) attend(kp, vp, g, warp, warp, 8, ntile, t, haspad[g] ? padbits + g * 8 : nullptr);
+                stage_release(); stage_release();
+              }
             }
           }
           cbar();
@@ -798,30 +835,16 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(NT, 1) decode_fused
           }
           cbar();
           TRACE(t);   // 7: cross q
-          // ---- cross-attention over the S memory keys: one image per stage, key tiles interleaved over the 8 warps -------
+          // ---- cross-attention over the S memory keys: per image its K panel in one stage and its V panel in the next, key tiles
+          //      interleaved over the 8 warps ------------------------------------------------------------------------------------
           {
             const int ntile = (S + 15) >> 4;
             for (int g = 0; g < nC; ++g) {
               if (warp == 0) FINE(l, t, 20 + g * 3);
-              const uint32_t st = stage_wait();
+              const uint32_t kp = stage_wait(), vp = stage_wait_next();
               if (warp == 0) FINE(l, t, 21 + g * 3);
-              if (g < G) {
-                float* pb = part + (g * NPART + warp) * PSTR;
-                if (warp < ntile) {
-                  uint32_t aq[2][2];
-                  build_q_frag(qh + g * 32, aq);
-                  float m_run, l_run;
-                  float o[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
-                  attn_chunk2(st, st + cross_panel, aq, warp, 8, ntile, S, nullptr, m_run, l_run, o);
-                  if (lane == 0) { pb[0] = m_run; pb[1] = l_run; }
-                  if ((lane & 3) == 0) {
-                    const int g8 = lane >> 2;
-                    pb[4 + g8] = o[0][0]; pb[4 + g8 + 8] = o[0][2];
-                    pb[4 + g8 + 16] = o[1][0]; pb[4 + g8 + 24] = o[1][2];
-                  }
-                } else if (lane == 0) pb[1] = 0.f;
-              }
-              stage_release();
+              if (g < G) attend(kp, vp, g, warp, warp, 8, ntile, S, nullptr);
+              stage_release(); stage_release();
               if (warp == 0) FINE(l, t, 22 + g * 3);
             }
           }
@@ -839,42 +862,43 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(NT, 1) decode_fused
           layer_norm(P.ln2w[l], P.ln2b[l]);
           TRACE(t);   // 11: LN2
 
-          // ---- FFN1: own 256 hidden units, ReLU, kept local as the FFN2 operand -----------------------------------
-          for (int s4 = 0; s4 < 4; ++s4) {
-            const int mt = warp - (s4 & 1) * 4;          // stages 0,2 -> warps 0-3; stages 1,3 -> warps 4-7
-            const bool mine = mt >= 0 && mt < 4;
-            float b0 = 0.f, b1 = 0.f;
-            if (mine) { const int h0 = rank * FS + s4 * 64 + mt * 16 + fg; b0 = __ldg(P.b_f1[l] + h0); b1 = __ldg(P.b_f1[l] + h0 + 8); }
+          // ---- FFN1: own 256 hidden units in 8 stages of 32 rows (stage s -> warps 2(s%4), 2(s%4)+1: four stages are worked on at a
+          //      time), ReLU, kept local as the FFN2 operand -------------------------------------------------------------------
+          for (int s8 = 0; s8 < 8; ++s8) {
+            const bool mine = (warp >> 1) == (s8 & 3);
+            const int mt = warp & 1;
             if (mine) {
-              if (mt == 0) FINE(l, t, s4 * 4 + 0);
+              const int h0 = rank * FS + s8 * 32 + mt * 16 + fg;
+              const float b0 = __ldg(P.b_f1[l] + h0), b1 = __ldg(P.b_f1[l] + h0 + 8);
+              if (warp == 0) FINE(l, t, (s8 >> 2) * 4 + 0);
               const uint32_t st = stage_wait();
-              if (mt == 0) FINE(l, t, s4 * 4 + 1);
+              if (warp == 0) FINE(l, t, (s8 >> 2) * 4 + 1);
               float acc[NB][4];
-              mma_mtile<64, NB>(st, mt * 16, sbase + Y::OFF_XH, acc);
-              if (mt == 0) FINE(l, t, s4 * 4 + 2);
-              const int h = s4 * 64 + mt * 16 + fg;
+              mma_mtile<32, NB>(st, mt * 16, sbase + Y::OFF_XH, acc);
+              if (warp == 0) FINE(l, t, (s8 >> 2) * 4 + 2);
+              const int h = s8 * 32 + mt * 16 + fg;
 #pragma unroll
               for (int nb = 0; nb < NB; ++nb) {
                 const int r = 8 * nb + 2 * fq;
                 store_h(fh, r * XP + h, fmaxf(acc[nb][0] + b0, 0.f)); store_h(fh, (r + 1) * XP + h, fmaxf(acc[nb][1] + b0, 0.f));
                 store_h(fh, r * XP + h + 8, fmaxf(acc[nb][2] + b1, 0.f)); store_h(fh, (r + 1) * XP + h + 8, fmaxf(acc[nb][3] + b1, 0.f));
               }
-              stage_release(2);
-              if (mt == 0) FINE(l, t, s4 * 4 + 3);
+              stage_release(4);
+              if (warp == 0) FINE(l, t, (s8 >> 2) * 4 + 3);
             } else stage_skip();
           }
           cbar();
           TRACE(t);   // 12: FFN1
-          // ---- FFN2 as a K-split: partial sums pushed straight to the CTA that owns the output columns -----------
-          for (int s4 = 0; s4 < 4; ++s4) {
-            const int mt = warp - (s4 & 1) * 4;
-            const bool mine = mt >= 0 && mt < 4;
+          // ---- FFN2 as a K-split, 32 output features per stage: partial sums pushed straight to the CTA that owns the columns ----
+          for (int s8 = 0; s8 < 8; ++s8) {
+            const bool mine = (warp >> 1) == (s8 & 3);
+            const int mt = warp & 1;
             if (mine) {
               const uint32_t st = stage_wait();
               float acc[NB][4];
-              mma_mtile<64, NB>(st, mt * 16, sbase + Y::OFF_FH, acc);
-              const int feat = s4 * 64 + mt * 16 + fg;                 // output feature of acc[.][0..1]; +8 for acc[.][2..3]
-              const uint32_t peer = feat >> 5;                          // the whole 16-row tile lies inside one 32-column slice
+              mma_mtile<32, NB>(st, mt * 16, sbase + Y::OFF_FH, acc);
+              const int feat = s8 * 32 + mt * 16 + fg;                 // output feature of acc[.][0..1]; +8 for acc[.][2..3]
+              const uint32_t peer = (uint32_t)s8;                       // stage s8 = the 32-column slice of CTA s8
               const uint32_t rb = mapa(bar(BAR_F2), peer);
               const uint32_t base = mapa(sbase + Y::OFF_F2RECV + (rank * GMX * 32 + (feat & 31)) * 4, peer);
 #pragma unroll
@@ -883,7 +907,7 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(NT, 1) decode_fused
                 if (i0 < G) { st_async_b32(base + i0 * 128, __float_as_uint(acc[nb][0]), rb); st_async_b32(base + i0 * 128 + 32, __float_as_uint(acc[nb][2]), rb); }
                 if (i0 + 1 < G) { st_async_b32(base + (i0 + 1) * 128, __float_as_uint(acc[nb][1]), rb); st_async_b32(base + (i0 + 1) * 128 + 32, __float_as_uint(acc[nb][3]), rb); }
               }
-              stage_release(2);
+              stage_release(4);
             } else stage_skip();
           }
           TRACE(t);   // 13: FFN2 issued
@@ -917,10 +941,9 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(NT, 1) decode_fused
           const bool va = warp < 3 && row_a < VSL && r0 + row_a < P.vocab, vb = warp < 3 && row_b < VSL && r0 + row_b < P.vocab;
           if (va) b0 = __ldg(P.b_out + r0 + row_a);
           if (vb) b1 = __ldg(P.b_out + r0 + row_b);
-          if (warp < 3) {
-            const uint32_t st = stage_wait();
-            float acc[NB][4];
-            mma_mtile<VSL, NB>(st, warp * 16, sbase + Y::OFF_XH, acc);
+          // rows [0,32) of the own 40 sit in one stage (warps 0-1), rows [32,40) in the next (warp 2: an 8-row block, the upper half
+          // of its 16-row MMA tile reads the neighbouring k-block -- finite weights feeding accumulator rows that are never used)
+          auto head_out = [&](float (&acc)[NB][4]) {
 #pragma unroll
             for (int nb = 0; nb < NB; ++nb)
 #pragma unroll
@@ -935,7 +958,20 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(NT, 1) decode_fused
                   if (need_select) st_async_b32(mapa(sbase + Y::OFF_LRECV + ((nb * CS + rank) * VSL + row) * 4, img & 7), __float_as_uint(lg), mapa(bar(BAR_LG), img & 7));
                 }
               }
-            stage_release(warp == 0 ? 4 : 2);
+          };
+          if (warp < 2) {
+            const uint32_t st = stage_wait();
+            float acc[NB][4];
+            mma_mtile<32, NB>(st, warp * 16, sbase + Y::OFF_XH, acc);
+            head_out(acc);
+            stage_release(4);
+          } else stage_skip();
+          if (warp == 2) {
+            const uint32_t st = stage_wait();
+            float acc[NB][4];
+            mma_mtile<8, NB>(st, 0, sbase + Y::OFF_XH, acc);
+            head_out(acc);
+            stage_release(8);
           } else stage_skip();
         }
         cbar();       // the next step's embedding overwrites the operand rows the head MMAs of warps 0-2 are reading (in teacher-forced
@@ -1001,16 +1037,34 @@ struct FusedCache {
   bool valid;
 };
 
+// ---- kernel variants --------------------------------------------------------------------------------------------------
+// 0: NB = 1, 10-stage ring (160 KB), one CTA per SM   (<= 8 images per cluster; lowest latency of one batch)
+// 1: NB = 2, 8-stage ring (128 KB), one CTA per SM    (<= 16 images per cluster)
+// 2: NB = 1, 4-stage ring (64 KB), compact layout, two CTAs per SM (<= 8 images per cluster; two clusters interleave on the same SMs)
+constexpr int N_VARIANTS = 3;
+template <bool kTrace> struct Variants {
+  static const void* fn(int v) {
+    switch (v) {
+      case 0: return (const void*)decode_fused_kernel<kTrace, 1, 10, 1>;
+      case 1: return (const void*)decode_fused_kernel<kTrace, 2, 8, 1>;
+      default: return (const void*)decode_fused_kernel<kTrace, 1, 4, 2>;
+    }
+  }
+};
+int variant_smem(int v) { return v == 0 ? Lay<1, 10, false>::SMEM_BYTES : (v == 1 ? Lay<2, 8, true>::SMEM_BYTES : Lay<1, 4, true>::SMEM_BYTES); }
+
+// per-context (= per-device) launch state: the dynamic-smem opt-in and the occupancy query are device properties
+struct ClusterCtxState { int max_clusters[N_VARIANTS]; };
+
 }  // namespace
 
 int decode_cluster_supported(const mdc_model* m, const mdc_decode_state* st, int t_end) {
   const mdc_dims& d = m->d;
   if (d.precision != MDC_BF16 || d.dec_loop_dtype != MDC_F16 || d.dim != DM || d.dec_heads != CS || d.dec_ffn != FFN) return 0;
   if (d.dec_layers < 1 || d.dec_layers > 8 || d.vocab > CS * VSL || d.vocab < 8) return 0;
-  if (st->x_override || st->pos_override) return 0;
+  if (st->x_override || st->pos_override || st->per_op_kernels) return 0;
   if (d.n_patches > 256 || d.n_patches < 8) return 0;             // one TMA box (<= 256 rows) per image panel, 2 panels per stage
   if (t_end > 256 || st->pages_per_seq > 32 || d.page_tokens != 16 || st->n_pages < 1) return 0;
-  if (getenv("MDC_DECODE_BACKEND") && !strcmp(getenv("MDC_DECODE_BACKEND"), "generic")) return 0;
   return 1;
 }
 
@@ -1018,6 +1072,10 @@ size_t decode_cluster_scratch_bytes(const mdc_model*, int) { return 0; }
 
 void decode_cluster_model_destroy(mdc_model* m) {
   if (m && m->fused_cache) { delete (FusedCache*)m->fused_cache; m->fused_cache = nullptr; }
+}
+
+void decode_cluster_ctx_destroy(mdc_ctx* ctx) {
+  if (ctx && ctx->decode_state) { delete (ClusterCtxState*)ctx->decode_state; ctx->decode_state = nullptr; }
 }
 
 int decode_cluster_launch(mdc_model* m, const mdc_decode_state* st, int t_begin, int t_end, void* /*logits_scratch*/, cudaStream_t s) {
@@ -1034,8 +1092,8 @@ int decode_cluster_launch(mdc_model* m, const mdc_decode_state* st, int t_begin,
       MDC_TRY(mdc_make_tmap_2d(ctx, lw[MDC_SA_OUT_W], DM, DM, DM, 64, 32, 3, &P.m_so[l]));
       MDC_TRY(mdc_make_tmap_2d(ctx, lw[MDC_CA_IN_W], 3 * DM, DM, DM, 64, 32, 3, &P.m_ca[l]));
       MDC_TRY(mdc_make_tmap_2d(ctx, lw[MDC_CA_OUT_W], DM, DM, DM, 64, 32, 3, &P.m_co[l]));
-      MDC_TRY(mdc_make_tmap_2d(ctx, lw[MDC_FF1_W], FFN, DM, DM, 64, 64, 3, &P.m_f1[l]));
-      MDC_TRY(mdc_make_tmap_2d(ctx, lw[MDC_FF2_W], DM, FFN, FFN, 64, 64, 3, &P.m_f2[l]));
+      MDC_TRY(mdc_make_tmap_2d(ctx, lw[MDC_FF1_W], FFN, DM, DM, 64, 32, 3, &P.m_f1[l]));
+      MDC_TRY(mdc_make_tmap_2d(ctx, lw[MDC_FF2_W], DM, FFN, FFN, 64, 32, 3, &P.m_f2[l]));
       P.b_in[l] = (const float*)lw[MDC_SA_IN_B]; P.b_so[l] = (const float*)lw[MDC_SA_OUT_B];
       P.ln1w[l] = (const float*)lw[MDC_LN1_W]; P.ln1b[l] = (const float*)lw[MDC_LN1_B];
       P.b_ca[l] = (const float*)lw[MDC_CA_IN_B]; P.b_co[l] = (const float*)lw[MDC_CA_OUT_B];
@@ -1043,7 +1101,8 @@ int decode_cluster_launch(mdc_model* m, const mdc_decode_state* st, int t_begin,
       P.b_f1[l] = (const float*)lw[MDC_FF1_B]; P.b_f2[l] = (const float*)lw[MDC_FF2_B];
       P.ln3w[l] = (const float*)lw[MDC_LN3_W]; P.ln3b[l] = (const float*)lw[MDC_LN3_B];
     }
-    MDC_TRY(mdc_make_tmap_2d(ctx, gw[MDC_OUT_W], d.vocab, DM, DM, 64, VSL, 3, &P.m_head));
+    MDC_TRY(mdc_make_tmap_2d(ctx, gw[MDC_OUT_W], d.vocab, DM, DM, 64, 32, 3, &P.m_head));
+    MDC_TRY(mdc_make_tmap_2d(ctx, gw[MDC_OUT_W], d.vocab, DM, DM, 64, 8, 3, &P.m_head8));
     P.emb = (const float*)gw[MDC_EMB]; P.pos = (const float*)gw[MDC_DEC_POS]; P.b_out = (const float*)gw[MDC_OUT_B];
     P.layers = d.dec_layers; P.vocab = d.vocab; P.S = d.n_patches; P.pad_idx = d.pad_idx; P.PT = d.page_tokens;
     fc->valid = true;
@@ -1057,45 +1116,49 @@ int decode_cluster_launch(mdc_model* m, const mdc_decode_state* st, int t_begin,
   P.uniforms = st->uniforms; P.uniforms_ld = st->uniforms_ld; P.top_k = st->top_k; P.top_p = st->top_p; P.forced = st->forced;
   P.t_begin = t_begin; P.t_end = t_end;
   P.trace = nullptr; P.trace_t = -1;
+  int ipc = st->images_per_cluster, cps = st->ctas_per_sm;
+#ifdef MDC_DEVTOOLS   // developer build only (tools/decode_trace.py): phase-trace buffer and variant overrides from the environment
   if (const char* tp = getenv("MDC_DECODE_TRACE_PTR")) { P.trace = (long long*)strtoull(tp, nullptr, 0); const char* tt = getenv("MDC_DECODE_TRACE_T"); P.trace_t = tt ? atoi(tt) : t_begin; }
+  if (const char* e = getenv("MDC_DECODE_IPC")) ipc = atoi(e);
+  if (const char* e = getenv("MDC_DECODE_CPS")) cps = atoi(e);
+#endif
   // cross-K/V [layers*B*S rows][2*DM]: one (S rows x 32 channels) box per (image, head, k|v); paged pool: one page x head box
   MDC_TRY(mdc_make_tmap_2d(ctx, st->cross_kv, (int64_t)d.dec_layers * st->B * d.n_patches, 2 * DM, 2 * DM, HD, d.n_patches, 2, &P.m_ckv));
   MDC_TRY(mdc_make_tmap_2d(ctx, st->kv_pool, (int64_t)st->n_pages * d.dec_layers * 2 * d.page_tokens, DM, DM, HD, d.page_tokens, 2, &P.m_pool));
-  // NB = 1: up to 8 images per cluster (13-15 clusters: lowest latency); NB = 2: up to 16 images per cluster, asked for by the
-  // batch pipeline through images_per_cluster > 8 (less SM-time per image, twice the latency)
-  int ipc = st->images_per_cluster;
-  if (const char* e = getenv("MDC_DECODE_IPC")) ipc = atoi(e);                                  // developer override (tools/decode_trace.py)
-  const int nb = ipc > 8 ? 2 : 1;
-  static int max_clusters_nb[2] = {0, 0};
-  if (!max_clusters_nb[nb - 1]) {
-    const int smem = nb == 1 ? Lay<1>::SMEM_BYTES : Lay<2>::SMEM_BYTES;
-    const void* fn = nb == 1 ? (const void*)decode_fused_kernel<false, 1> : (const void*)decode_fused_kernel<false, 2>;
-    const void* fn_t = nb == 1 ? (const void*)decode_fused_kernel<true, 1> : (const void*)decode_fused_kernel<true, 2>;
+  // variant: more than 8 images per cluster -> the two-column-block instantiation; otherwise ctas_per_sm == 2 -> the compact one
+  const int variant = ipc > 8 ? 1 : (cps == 2 ? 2 : 0);
+  const int gmx = variant == 1 ? 16 : 8;
+  if (!ctx->decode_state) { ClusterCtxState* cs = new ClusterCtxState(); memset(cs, 0, sizeof(*cs)); ctx->decode_state = cs; }
+  ClusterCtxState* cs = (ClusterCtxState*)ctx->decode_state;
+  const int smem = variant_smem(variant);
+  if (!cs->max_clusters[variant]) {
+    const void* fn = Variants<false>::fn(variant);
     MDC_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    MDC_CUDA(cudaFuncSetAttribute(fn_t, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    cudaLaunchConfig_t q{}; q.gridDim = dim3(CS * 32); q.blockDim = dim3(NT); q.dynamicSmemBytes = smem;
+#ifdef MDC_DEVTOOLS
+    MDC_CUDA(cudaFuncSetAttribute(Variants<true>::fn(variant), cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+#endif
+    cudaLaunchConfig_t q{}; q.gridDim = dim3(CS * 64); q.blockDim = dim3(NT); q.dynamicSmemBytes = smem;
     cudaLaunchAttribute a[1]; a[0].id = cudaLaunchAttributeClusterDimension; a[0].val.clusterDim.x = CS; a[0].val.clusterDim.y = 1; a[0].val.clusterDim.z = 1;
     q.attrs = a; q.numAttrs = 1;
     int n = 0;
     cudaError_t e = cudaOccupancyMaxActiveClusters(&n, fn, &q);
     if (e != cudaSuccess || n < 1) { (void)cudaGetLastError(); n = ctx->sm_count / CS / 2; if (n < 1) n = 1; }
-    max_clusters_nb[nb - 1] = n;
+    cs->max_clusters[variant] = n;
   }
-  const int max_clusters = max_clusters_nb[nb - 1];
+  const int max_clusters = cs->max_clusters[variant];
   int G = (P.B + max_clusters - 1) / max_clusters;
   if (ipc > 0 && ipc > G) G = ipc;                                                              // fewer, fuller clusters (batch pipelining)
-  if (G > 8 * nb) G = 8 * nb;
+  if (G > gmx) G = gmx;
   if (G < 1) G = 1;
   P.G = G;
   P.n_groups = (P.B + G - 1) / G;
   const int n_clusters = P.n_groups < max_clusters ? P.n_groups : max_clusters;
-  if (nb == 1) {
-    if (P.trace) decode_fused_kernel<true, 1><<<n_clusters * CS, NT, Lay<1>::SMEM_BYTES, s>>>(P);
-    else decode_fused_kernel<false, 1><<<n_clusters * CS, NT, Lay<1>::SMEM_BYTES, s>>>(P);
-  } else {
-    if (P.trace) decode_fused_kernel<true, 2><<<n_clusters * CS, NT, Lay<2>::SMEM_BYTES, s>>>(P);
-    else decode_fused_kernel<false, 2><<<n_clusters * CS, NT, Lay<2>::SMEM_BYTES, s>>>(P);
-  }
+  void* args[1] = {(void*)&P};
+  const void* fn = Variants<false>::fn(variant);
+#ifdef MDC_DEVTOOLS
+  if (P.trace) fn = Variants<true>::fn(variant);
+#endif
+  MDC_CUDA(cudaLaunchKernel(fn, dim3(n_clusters * CS), dim3(NT), args, (size_t)smem, s));
   MDC_LAUNCH_CHECK(ctx);
   return 0;
 }

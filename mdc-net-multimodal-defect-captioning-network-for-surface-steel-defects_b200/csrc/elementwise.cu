@@ -218,6 +218,7 @@ int k_add_pos(mdc_ctx* ctx, int dtype, const float* enc_out, const float* pos, v
 extern "C" int mdc_layernorm(mdc_ctx* ctx, const float* x, int64_t ldx, const float* w, const float* b, float eps,
                              void* out, int64_t ldo, int out_dtype, int rows, int cols, void* stream) {
   MDC_CHECK_ARG(ctx && x && w && b && out);
+  MDC_CHECK_DEVICE(ctx);
   MDC_CHECK_ARG(cols % 4 == 0 && ldx % 4 == 0 && rows >= 0);
   if (rows == 0) return 0;
   cudaStream_t s = (cudaStream_t)stream;
@@ -240,6 +241,7 @@ extern "C" int mdc_layernorm(mdc_ctx* ctx, const float* x, int64_t ldx, const fl
 
 extern "C" int mdc_preprocess_gray(mdc_ctx* ctx, const uint8_t* gray, int B, int h, int w, float* out, int size, void* stream) {
   MDC_CHECK_ARG(ctx && gray && out && B >= 0 && h > 0 && w > 0 && size > 0);
+  MDC_CHECK_DEVICE(ctx);
   if (B == 0) return 0;
   int grid = blocks_for((int64_t)B * size * size, 256, ctx->sm_count);
   preprocess_gray_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(gray, B, h, w, out, size);
@@ -248,6 +250,7 @@ extern "C" int mdc_preprocess_gray(mdc_ctx* ctx, const uint8_t* gray, int B, int
 
 extern "C" int mdc_interp_rows(mdc_ctx* ctx, const float* in, int n_in, float* out, int n_out, int dim, void* stream) {
   MDC_CHECK_ARG(ctx && in && out && n_in > 0 && n_out > 0 && dim > 0);
+  MDC_CHECK_DEVICE(ctx);
   int grid = blocks_for((int64_t)n_out * dim, 256, ctx->sm_count);
   interp_rows_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(in, n_in, out, n_out, dim);
   MDC_LAUNCH_CHECK(ctx); return 0;

@@ -132,6 +132,7 @@ extern "C" int mdc_gemm(mdc_ctx* ctx, int dtype, int epilogue, const void* A, in
                         void* D, int64_t ldd, const float* bias, const float* aux0, int period, int M, int N, int K,
                         void* stream) {
   MDC_CHECK_ARG(ctx && A && W && D);
+  MDC_CHECK_DEVICE(ctx);
   MDC_CHECK_ARG(dtype == MDC_F32 || dtype == MDC_BF16);
   MDC_CHECK_ARG(M >= 0 && N > 0 && K > 0);
   if (epilogue == MDC_EPI_LS_RESIDUAL) MDC_CHECK_ARG(aux0 != nullptr);

@@ -419,10 +419,11 @@ template <int BN, int EPI>
 int launch_bn_epi(mdc_ctx* ctx, const CUtensorMap& ma, const CUtensorMap& mw, const EpiArgs& ep, int M, int N, int K, cudaStream_t s) {
   constexpr int EW = (BN == 256 && EPI == MDC_EPI_BIAS_GELU) ? 16 : 8;     // A/B on one box: fc1 34.0 -> 31.6 us; bias-only epilogues lose 3 %
   using C = Cfg<BN, EW>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[MDC_MAX_DEVICES];      // the dynamic-smem opt-in is a per-device attribute of this instantiation
+  if (ctx->device < 0 || ctx->device >= MDC_MAX_DEVICES) MDC_FAIL(-2, "device index %d out of range", ctx->device);
+  if (!attr_set[ctx->device]) {
     MDC_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
-    attr_set = true;
+    attr_set[ctx->device] = true;
   }
   int tiles = ((M + BLOCK_M - 1) / BLOCK_M) * ((N + BN - 1) / BN);
   int grid = tiles < ctx->sm_count ? tiles : ctx->sm_count;

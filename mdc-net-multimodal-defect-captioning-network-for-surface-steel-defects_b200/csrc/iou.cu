@@ -127,6 +127,7 @@ __global__ void mean_kernel(const float* __restrict__ v, int n, float* __restric
 extern "C" int mdc_iou_batch(mdc_ctx* ctx, int mode, const float* pred, const float* gt, int B, int N, int M,
                              float* iou_out, float* max_out, void* stream) {
   MDC_CHECK_ARG(ctx && pred && gt && (iou_out || max_out));
+  MDC_CHECK_DEVICE(ctx);
   MDC_CHECK_ARG(mode >= MDC_IOU_EPS && mode <= MDC_IOU_GIOU);
   MDC_CHECK_ARG(B >= 0 && N >= 0 && M >= 0);
   MDC_CHECK_ARG(((uintptr_t)pred & 15) == 0 && ((uintptr_t)gt & 15) == 0);
@@ -160,6 +161,7 @@ extern "C" int mdc_iou_batch(mdc_ctx* ctx, int mode, const float* pred, const fl
 extern "C" int mdc_giou_loss(mdc_ctx* ctx, const float* pred, const float* gt, int B, int N, int M, float no_detection_penalty,
                              float* loss_per_image, float* giou_out, uint8_t* valid_out, void* stream) {
   MDC_CHECK_ARG(ctx && pred && gt && loss_per_image && B > 0 && N >= 0 && M >= 0);
+  MDC_CHECK_DEVICE(ctx);
   cudaStream_t s = (cudaStream_t)stream;
   giou_loss_kernel<<<(B + 7) / 8, 256, 0, s>>>((const float4*)pred, (const float4*)gt, B, N, M, no_detection_penalty,
                                                loss_per_image, giou_out, valid_out);

@@ -36,6 +36,7 @@ extern "C" size_t mdc_encode_workspace_bytes(const mdc_model* m, int B) {
 extern "C" int mdc_encode(mdc_model* m, const float* image, int B, float* enc_out, void* memory, void* workspace,
                           size_t workspace_bytes, void* stream) {
   MDC_CHECK_ARG(m && image && workspace && B > 0 && (enc_out || memory));
+  MDC_CHECK_DEVICE(m->ctx);
   MDC_CHECK_ARG(workspace_bytes >= enc_ws_bytes(m->d, B));
   mdc_ctx* ctx = m->ctx; const mdc_dims& d = m->d; cudaStream_t s = (cudaStream_t)stream;
   const int dt = d.precision, D = d.enc_dim, n = d.n_patches, M = B * (n + 1), Kp = d.in_chans * d.patch * d.patch;
@@ -69,6 +70,7 @@ extern "C" int mdc_encode(mdc_model* m, const float* image, int B, float* enc_ou
 
 extern "C" int mdc_memory_from_encoder_out(mdc_model* m, const float* enc_out, int B, void* memory, void* stream) {
   MDC_CHECK_ARG(m && enc_out && memory && B > 0);
+  MDC_CHECK_DEVICE(m->ctx);
   const mdc_dims& d = m->d;
   const void** dg = m->w + MDC_ENC_GLOBAL_SLOTS + d.enc_depth * MDC_ENC_BLOCK_SLOTS;
   int64_t per = (int64_t)d.n_patches * d.dim;
@@ -82,6 +84,7 @@ extern "C" size_t mdc_cross_kv_bytes(const mdc_model* m, int B) {
 
 extern "C" int mdc_cross_kv_build(mdc_model* m, const void* memory, int B, void* cross_kv, void* stream) {
   MDC_CHECK_ARG(m && memory && cross_kv && B > 0);
+  MDC_CHECK_DEVICE(m->ctx);
   const mdc_dims& d = m->d; const int dim = d.dim, S = d.n_patches;
   const void** lw0 = m->w + MDC_ENC_GLOBAL_SLOTS + d.enc_depth * MDC_ENC_BLOCK_SLOTS + MDC_DEC_GLOBAL_SLOTS;
   const size_t es = esize(d.precision);
@@ -113,6 +116,7 @@ __global__ void uncast_rows_kernel(const bf16* __restrict__ in, float* __restric
 extern "C" int mdc_axial_attention(mdc_model* m, const float* x, int B, int n, int softmax_over_queries, float* out, void* workspace,
                                    size_t workspace_bytes, void* stream) {
   MDC_CHECK_ARG(m && x && out && workspace && B > 0 && n > 0 && m->d.has_axial);
+  MDC_CHECK_DEVICE(m->ctx);
   MDC_CHECK_ARG(workspace_bytes >= mdc_axial_workspace_bytes(m, B, n));
   mdc_ctx* ctx = m->ctx; const mdc_dims& d = m->d; cudaStream_t s = (cudaStream_t)stream;
   const int dim = d.dim, heads = 8, dt = d.precision; const size_t es = esize(dt);   // axial_model.py:20 heads=8
@@ -161,6 +165,7 @@ extern "C" size_t mdc_axial_embed_workspace_bytes(const mdc_model* m, int B, int
 extern "C" int mdc_axial_embed(mdc_model* m, const int32_t* tokens, int tokens_ld, int B, int n, const float* pos,
                                int softmax_over_queries, float* out, void* workspace, size_t workspace_bytes, void* stream) {
   MDC_CHECK_ARG(m && tokens && out && workspace && B > 0 && n > 0 && tokens_ld >= n);
+  MDC_CHECK_DEVICE(m->ctx);
   MDC_CHECK_ARG(workspace_bytes >= mdc_axial_embed_workspace_bytes(m, B, n));
   mdc_ctx* ctx = m->ctx; const mdc_dims& d = m->d; cudaStream_t s = (cudaStream_t)stream;
   const void** dg = m->w + MDC_ENC_GLOBAL_SLOTS + d.enc_depth * MDC_ENC_BLOCK_SLOTS;

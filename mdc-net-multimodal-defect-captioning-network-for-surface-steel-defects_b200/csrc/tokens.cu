@@ -92,6 +92,7 @@ extern "C" int mdc_decode_tokens(mdc_ctx* ctx, int mode, const int32_t* tokens, 
                                  int max_boxes, int32_t* labels_out, float* boxes_out, int32_t* counts_out, int32_t* caption_out,
                                  int32_t* caption_len_out, void* stream) {
   MDC_CHECK_ARG(ctx && tokens && grammar && boxes_out && counts_out && B > 0 && L > 0 && L <= 4096 && tokens_ld >= L && max_boxes > 0);
+  MDC_CHECK_DEVICE(ctx);
   MDC_CHECK_ARG(mode == MDC_TOK_BBOXES || mode == MDC_TOK_DECODE);
   MDC_CHECK_ARG(grammar->num_bins > 1);
   const size_t smem = (size_t)TOK_WARPS * L * sizeof(int32_t);

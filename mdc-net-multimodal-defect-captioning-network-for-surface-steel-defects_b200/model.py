@@ -97,6 +97,35 @@ class VisionTransformerParams(_Holder):
                 nn.init.zeros_(m.bias)
 
 
+# Decode-kernel launch options (mdc_decode_state.images_per_cluster / ctas_per_sm / per_op_kernels).  None of them changes a
+# result bit (tests/test_gpu_model.py); they trade latency of one batch against SM-time per batch, and `per_op_kernels` lets the
+# parity tests run the per-operation kernels where the fused cluster kernel would be picked.
+_DECODE_OPTIONS = {"images_per_cluster": 0, "ctas_per_sm": 0, "per_op_kernels": False}
+
+
+class decode_options:
+    """`with decode_options(images_per_cluster=16): ...` -- scoped override of the decode launch options."""
+
+    def __init__(self, **kw):
+        bad = set(kw) - set(_DECODE_OPTIONS)
+        if bad:
+            raise TypeError(f"unknown decode option(s) {sorted(bad)}")
+        self.kw, self.saved = kw, None
+
+    def __enter__(self):
+        self.saved = dict(_DECODE_OPTIONS)
+        _DECODE_OPTIONS.update(self.kw)
+        return self
+
+    def __exit__(self, *exc):
+        _DECODE_OPTIONS.clear(); _DECODE_OPTIONS.update(self.saved)
+        return False
+
+
+def _decode_options_key():
+    return tuple(sorted((k, int(v)) for k, v in _DECODE_OPTIONS.items()))
+
+
 def _precision_dtype(precision):
     if precision in ("bf16", torch.bfloat16):
         return torch.bfloat16
@@ -235,7 +264,8 @@ class Engine:
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=self.device)
         enc_out = torch.empty((B, d.n_patches, d.dim), dtype=torch.float32, device=self.device) if want_enc_out else None
         memory = torch.empty((B, d.n_patches, d.dim), dtype=self.dtype, device=self.device) if want_memory else None
-        L.check(self.lib.mdc_encode(self.handle, L.ptr(image), B, L.ptr(enc_out), L.ptr(memory), L.ptr(ws), ws_bytes, L.stream_ptr()))
+        with torch.cuda.device(self.device):      # the C side checks that the current device is the context's
+            L.check(self.lib.mdc_encode(self.handle, L.ptr(image), B, L.ptr(enc_out), L.ptr(memory), L.ptr(ws), ws_bytes, L.stream_ptr(self.device)))
         return enc_out, memory
 
     def memory_from(self, encoder_out):
@@ -245,19 +275,21 @@ class Engine:
         if tuple(encoder_out.shape[1:]) != (d.n_patches, d.dim):
             raise ValueError(f"encoder_out must be (B,{d.n_patches},{d.dim})")
         memory = torch.empty((B, d.n_patches, d.dim), dtype=self.dtype, device=self.device)
-        L.check(self.lib.mdc_memory_from_encoder_out(self.handle, L.ptr(encoder_out), B, L.ptr(memory), L.stream_ptr()))
+        with torch.cuda.device(self.device):
+            L.check(self.lib.mdc_memory_from_encoder_out(self.handle, L.ptr(encoder_out), B, L.ptr(memory), L.stream_ptr(self.device)))
         return memory
 
     def cross_kv(self, memory):
         B = memory.shape[0]
         nbytes = self.lib.mdc_cross_kv_bytes(self.handle, B)
         ckv = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
-        L.check(self.lib.mdc_cross_kv_build(self.handle, L.ptr(memory), B, L.ptr(ckv), L.stream_ptr()))
+        with torch.cuda.device(self.device):
+            L.check(self.lib.mdc_cross_kv_build(self.handle, L.ptr(memory), B, L.ptr(ckv), L.stream_ptr(self.device)))
         return ckv
 
     def decode(self, cross_kv, tokens, t_begin, t_end, *, max_tokens, forced, logits=None, logits_row_offset=0,
                confs=None, uniforms=None, top_k=0, top_p=1.0, pos_override=None, x_override=None, kv=None, scratch=None,
-               images_per_cluster=0):
+               images_per_cluster=None, ctas_per_sm=None, per_op_kernels=None):
         """Runs decode steps [t_begin, t_end) back to back on the current stream (no host sync)."""
         d = self.dims
         B = tokens.shape[0]
@@ -287,8 +319,12 @@ class Engine:
         if x_override is not None:
             st.x_override, st.x_override_ld = x_override.data_ptr(), x_override.shape[1]
         st.scratch, st.scratch_bytes = scratch.data_ptr(), scratch.numel()
-        st.images_per_cluster = int(images_per_cluster)
-        L.check(self.lib.mdc_decode_steps(self.handle, C.byref(st), t_begin, t_end, L.stream_ptr()))
+        opt = _DECODE_OPTIONS
+        st.images_per_cluster = int(opt["images_per_cluster"] if images_per_cluster is None else images_per_cluster)
+        st.ctas_per_sm = int(opt["ctas_per_sm"] if ctas_per_sm is None else ctas_per_sm)
+        st.per_op_kernels = int(opt["per_op_kernels"] if per_op_kernels is None else per_op_kernels)
+        with torch.cuda.device(self.device):
+            L.check(self.lib.mdc_decode_steps(self.handle, C.byref(st), t_begin, t_end, L.stream_ptr(self.device)))
         return kv, scratch
 
     def interp_pos(self, pos, length):
@@ -298,7 +334,8 @@ class Engine:
         if length == n:
             return src
         out = torch.empty((length, dim), dtype=torch.float32, device=self.device)
-        L.check(self.lib.mdc_interp_rows(self.ctx, L.ptr(src), n, L.ptr(out), length, dim, L.stream_ptr()))
+        with torch.cuda.device(self.device):
+            L.check(self.lib.mdc_interp_rows(self.ctx, L.ptr(src), n, L.ptr(out), length, dim, L.stream_ptr(self.device)))
         return out
 
 
@@ -479,7 +516,7 @@ class EncoderDecoder(nn.Module, _EngineOwner):
         sampling = (top_k != 0 or top_p != 1)
         if use_graph is None:
             use_graph = os.environ.get("MDC_NO_GRAPH", "0") != "1"
-        key = (id(eng), image.shape[0], T, int(top_k), float(top_p), bool(return_logits), bool(use_graph))
+        key = (id(eng), image.shape[0], T, int(top_k), float(top_p), bool(return_logits), bool(use_graph), _decode_options_key())
         plans = self.__dict__.setdefault("_plans", {})
         if plans.get("eng") is not eng:
             plans.clear(); plans["eng"] = eng
@@ -499,12 +536,14 @@ class GenerationPlan:
     """Static buffers + (optionally) a captured CUDA graph for one (batch, new tokens, sampler) shape:
     encoder -> memory -> cross-K/V -> T decode steps, no host synchronisation anywhere inside."""
 
-    def __init__(self, eng, B, T, top_k, top_p, sampling, want_logits, use_graph, split=False, images_per_cluster=0):
+    def __init__(self, eng, B, T, top_k, top_p, sampling, want_logits, use_graph, split=False, images_per_cluster=None, ctas_per_sm=None):
         d = eng.dims
         dev = eng.device
         self.eng, self.B, self.T = eng, B, T
         self.top_k, self.top_p = int(top_k), float(top_p)
-        self.images_per_cluster = int(images_per_cluster)
+        self.images_per_cluster = _DECODE_OPTIONS["images_per_cluster"] if images_per_cluster is None else int(images_per_cluster)
+        self.ctas_per_sm = _DECODE_OPTIONS["ctas_per_sm"] if ctas_per_sm is None else int(ctas_per_sm)
+        self.per_op_kernels = bool(_DECODE_OPTIONS["per_op_kernels"])
         self.x = torch.zeros((B, d.in_chans, d.img_size, d.img_size), dtype=torch.float32, device=dev)
         self.ws_bytes = eng.lib.mdc_encode_workspace_bytes(eng.handle, B)
         self.ws = torch.empty(self.ws_bytes, dtype=torch.uint8, device=dev)
@@ -558,8 +597,9 @@ class GenerationPlan:
 
     def _launch_encode(self):
         eng = self.eng
-        L.check(eng.lib.mdc_encode(eng.handle, L.ptr(self.x), self.B, None, L.ptr(self.memory), L.ptr(self.ws), self.ws_bytes, L.stream_ptr()))
-        L.check(eng.lib.mdc_cross_kv_build(eng.handle, L.ptr(self.memory), self.B, L.ptr(self.ckv), L.stream_ptr()))
+        with torch.cuda.device(eng.device):
+            L.check(eng.lib.mdc_encode(eng.handle, L.ptr(self.x), self.B, None, L.ptr(self.memory), L.ptr(self.ws), self.ws_bytes, L.stream_ptr(eng.device)))
+            L.check(eng.lib.mdc_cross_kv_build(eng.handle, L.ptr(self.memory), self.B, L.ptr(self.ckv), L.stream_ptr(eng.device)))
 
     def _launch_decode(self):
         eng = self.eng
@@ -567,7 +607,7 @@ class GenerationPlan:
         self.tokens[:, 0].fill_(int(CFG.bos_idx))
         eng.decode(self.ckv, self.tokens, 0, self.T, max_tokens=self.T, forced=False, logits=self.logits, logits_row_offset=0,
                    confs=self.confs, uniforms=self.uniforms, top_k=self.top_k, top_p=self.top_p, kv=self.kv, scratch=self.scratch,
-                   images_per_cluster=self.images_per_cluster)
+                   images_per_cluster=self.images_per_cluster, ctas_per_sm=self.ctas_per_sm, per_op_kernels=self.per_op_kernels)
 
     def run(self, image, uniforms=None):
         d = self.eng.dims

@@ -38,7 +38,7 @@ class Ticket:
 
 class GenerationPipeline:
     def __init__(self, model, batch, max_new_tokens, top_k=0, top_p=1.0, depth=6, decode_streams=4, images_per_cluster=16,
-                 to_host=False, device=None):
+                 ctas_per_sm=0, to_host=False, device=None):
         from .model import GenerationPlan
         if not hasattr(model, "_engine"):
             raise TypeError("GenerationPipeline needs the B200 EncoderDecoder; there is no PyTorch fallback path")
@@ -52,7 +52,7 @@ class GenerationPipeline:
         dev = eng.device
         with torch.cuda.device(dev):
             self.plans = [GenerationPlan(eng, self.B, T, top_k, top_p, self.sampling, False, True, split=True,
-                                         images_per_cluster=images_per_cluster) for _ in range(self.depth)]
+                                         images_per_cluster=images_per_cluster, ctas_per_sm=ctas_per_sm) for _ in range(self.depth)]
             self.s_enc = torch.cuda.Stream(device=dev, priority=0)      # encoder / cross-K/V / H2D: fills whatever the decodes leave idle
             self.s_decs = [torch.cuda.Stream(device=dev, priority=-1) for _ in range(max(1, int(decode_streams)))]   # clusters first
         self.n = 0

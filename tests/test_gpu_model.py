@@ -96,12 +96,8 @@ def test_bf16_logits_within_contract(model_p, x2, golden):
     print(f"bf16 path: encoder max|d| = {e_err:.3e}; logits max|d| = {err:.3e}, cosine = {c:.6f}")
     assert err <= BF16_MAXABS and c >= BF16_COS
     # same contract on the generic (unfused) decode kernels
-    import os
-    os.environ["MDC_DECODE_BACKEND"] = "generic"
-    try:
+    with M.decode_options(per_op_kernels=True):
         pred_g = model_p.predict(x2, g["prefix"].to(DEV))
-    finally:
-        os.environ.pop("MDC_DECODE_BACKEND", None)
     assert (pred_g.cpu()[:, 1:] - g["predict"][:, 1:]).abs().max().item() <= BF16_MAXABS
     # teacher-forced per-step logits along the reference's own greedy trajectory
     toks = g["tokens"].to(DEV)
@@ -189,12 +185,9 @@ def test_cluster_decode_kernel_matches_generic_kernels(model_p, golden, B, T):
     import os
     model_p.set_precision("bf16")
     x = cases.images(B, seed=21).to(DEV)
-    os.environ["MDC_DECODE_BACKEND"] = "generic"
-    try:
+    with M.decode_options(per_op_kernels=True):
         tg, _ = model_p.generate_tokens(x, T, use_graph=False)
         lg = model_p.predict(x, tg[:, :T].long())[:, 1:T + 1]
-    finally:
-        os.environ.pop("MDC_DECODE_BACKEND", None)
     lc = model_p.predict(x, tg[:, :T].long())[:, 1:T + 1]
     tc, _ = model_p.generate_tokens(x, T, use_graph=False)
     err = (lg - lc).abs().max().item()
@@ -221,13 +214,11 @@ def test_cluster_decode_16_images_per_cluster_is_bitwise_the_8_image_kernel(mode
         ts, cs = model_p.generate_tokens(x, T, top_k=5, uniforms=u, use_graph=False)
         return t, c, ts, cs, model_p.predict(x, t[:, :T].long())
     want = run()
-    os.environ["MDC_DECODE_IPC"] = "16"
-    try:
-        got = run()
-    finally:
-        os.environ.pop("MDC_DECODE_IPC", None)
-    for a, b in zip(got, want):
-        assert torch.equal(a, b)
+    for opts in ({"images_per_cluster": 16}, {"images_per_cluster": 8, "ctas_per_sm": 2}):
+        with M.decode_options(**opts):
+            got = run()
+        for a, b in zip(got, want):
+            assert torch.equal(a, b), opts
 
 
 def test_greedy_select_breaks_ties_like_torch_argmax():
@@ -244,13 +235,9 @@ def test_greedy_select_breaks_ties_like_torch_argmax():
         b[[7, 150, 290]] += 8.0
     m = m.to(DEV).set_precision("bf16")
     x = cases.images(19, seed=12).to(DEV)
-    for env in ({}, {"MDC_DECODE_IPC": "16"}, {"MDC_DECODE_BACKEND": "generic"}):
-        os.environ.update(env)
-        try:
+    for env in ({}, {"images_per_cluster": 16}, {"ctas_per_sm": 2}, {"per_op_kernels": True}):
+        with M.decode_options(**env):
             toks, confs, logits = m.generate_tokens(x, 12, return_logits=True, use_graph=False)
-        finally:
-            for k in env:
-                os.environ.pop(k, None)
         assert torch.equal(logits[..., 7], logits[..., 150]) and torch.equal(logits[..., 7], logits[..., 290])
         assert (toks[:, 1:] == 7).all(), (env, toks[0])
         want = torch.softmax(logits.float(), -1).max(-1)[0][:, ::4]

@@ -1,6 +1,9 @@
 """Developer aid: phase timestamps (clock64) of CTA 0 of the fused decode kernel at one step.  python tools/decode_trace.py [B] [T] [step]"""
 import os, sys, torch
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+# the trace instantiations and the MDC_DECODE_* switches only exist in the developer build (build.py --devtools)
+os.environ.setdefault("MDC_LIB_PATH", os.path.join(ROOT, "mdc-net-multimodal-defect-captioning-network-for-surface-steel-defects_b200", "libmdc_b200_dev.so"))
 from oracle import cases
 import mdcnet_b200 as M
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 64
@@ -32,10 +35,10 @@ print(f"  layer total {sum(tot)/L:.0f} cyc; head {tr[L*16]-tr[L*16-1]} cyc; sele
 
 f = tr[100:160]
 print("fine stamps, layer 2 (cycles relative to FFN1 stage-0 start of warp 0): per FFN1 stage [enter, data ready, mma done, released]")
-for s4 in range(4):
+for s4 in range(2):
     v = f[s4 * 4:s4 * 4 + 4]
     if v[0]:
-        print(f"  FFN1 stage {s4} (warp {0 if s4 % 2 == 0 else 4}): enter +{v[0]-f[0]:6d}  wait {v[1]-v[0]:5d}  mma {v[2]-v[1]:5d}  epilogue+release {v[3]-v[2]:5d}")
+        print(f"  FFN1 stage {s4 * 4} (warp 0): enter +{v[0]-f[0]:6d}  wait {v[1]-v[0]:5d}  mma {v[2]-v[1]:5d}  epilogue+release {v[3]-v[2]:5d}")
 print("cross stages (warp 0): [enter, data ready, released]")
 for g in range(8):
     v = f[20 + g * 3:23 + g * 3]
