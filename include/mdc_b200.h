@@ -166,15 +166,18 @@ int mdc_memory_from_encoder_out(mdc_model* m, const float* enc_out, int B, void*
 
 /* ---- (c) cross-attention K/V, once per image, HBM resident -----------------------------------
  * cross_kv[l][b*S+s][0:dim]=K, [dim:2dim]=V  (`precision`), from rows [dim:3dim] of
- * multihead_attn.in_proj_weight (torch functional.py in-proj packing q|k|v). */
+ * multihead_attn.in_proj_weight (torch functional.py in-proj packing q|k|v).  Where the fused decode kernel covers the
+ * geometry the buffer also carries, behind that tensor, the same values re-arranged per (layer, image, head, 16-key chunk)
+ * into contiguous 2 KB cells that the kernel fetches with one bulk copy each; mdc_cross_kv_bytes() covers both parts. */
 size_t mdc_cross_kv_bytes(const mdc_model* m, int B);
 int mdc_cross_kv_build(mdc_model* m, const void* memory, int B, void* cross_kv, void* stream);
 
 /* ---- (c,d) autoregressive decode ---------------------------------------------------------------
  * State of one batch being decoded.  All device buffers caller-owned.
  *   tokens   int32 [B, tokens_ld]   column 0..t are known when step t runs; step t writes column t+1
- *   kv_pool  `precision` [n_pages][dec_layers][2][page_tokens][dim]   paged self-attention cache (n_pages: pool extent;
- *            it bounds the TMA view the fused decode kernel builds over the pool)
+ *   kv_pool  `precision` [n_pages][dec_layers][heads][2][page_tokens][head_dim]   paged self-attention cache, zero-initialised by
+ *            the caller (n_pages: pool extent).  The K and V rows of one (page, layer, head) are contiguous; with 64-byte rows the
+ *            16-byte chunk c of token r sits at chunk c ^ ((r >> 1) & 3).  Opaque to callers: only the library reads or writes it.
  *   page_table int32 [B, pages_per_seq]  physical page of logical page j of image b
  *   logits   f32 [B, logits_ld, vocab] or NULL: row (t+1) receives the step-t logits
  *            (= predict(x, prefix)[:, t+1], the reference's shifted layout, model.py:116-123)
@@ -212,6 +215,14 @@ typedef struct mdc_decode_state {
 } mdc_decode_state;
 
 size_t mdc_decode_workspace_bytes(const mdc_model* m, int B);
+/* Decode-loop weights (mdc_dims.dec_loop_dtype slots) pre-arranged for the fused decode kernel: per (layer, cluster rank) the
+ * 32-row blocks the kernel consumes, in consumption order, each stored as the exact shared-memory image its tensor-core
+ * fragment loads expect -- one contiguous bulk copy per pipeline stage instead of per-row tensor-map traffic.
+ * mdc_decode_pack_bytes() is 0 when the fused kernel does not cover the model's geometry (the per-operation kernels then
+ * serve mdc_decode_steps).  `packed` is a caller-owned device buffer that must outlive the model; call once after
+ * mdc_model_create (and again if the weight buffers are rewritten in place). */
+size_t mdc_decode_pack_bytes(const mdc_model* m);
+int mdc_decode_pack(mdc_model* m, void* packed, void* stream);
 size_t mdc_kv_page_bytes(const mdc_model* m);
 /* steps t = t_begin .. t_end-1, back to back on `stream`, no host synchronisation inside. */
 int mdc_decode_steps(mdc_model* m, const mdc_decode_state* st, int t_begin, int t_end, void* stream);

@@ -86,6 +86,8 @@ SIGNATURES = {
     "mdc_cross_kv_bytes": (_SZ, [_P, _I]),
     "mdc_cross_kv_build": (_I, [_P, _P, _I, _P, _P]),
     "mdc_decode_workspace_bytes": (_SZ, [_P, _I]),
+    "mdc_decode_pack_bytes": (_SZ, [_P]),
+    "mdc_decode_pack": (_I, [_P, _P, _P]),
     "mdc_kv_page_bytes": (_SZ, [_P]),
     "mdc_decode_steps": (_I, [_P, C.POINTER(DecodeState), _I, _I, _P]),
     "mdc_select": (_I, [_P, _P, _L, _I, _I, _I, _F, _P, _P, _P, _P, _P]),

@@ -45,7 +45,8 @@ struct mdc_model {
   mdc_dims d;
   const void** w;     // weight table copy (host array of device pointers)
   int n_w;
-  void* fused_cache;  // opaque, owned by decode_cluster.cu (cached weight tensor maps)
+  void* fused_cache;  // opaque, owned by decode_cluster.cu (cached kernel parameters)
+  const void* dec_pack;  // decode-loop weights packed for the fused kernel (mdc_decode_pack), caller-owned
 };
 
 // ---- typed load/store ----------------------------------------------------------------------
@@ -125,3 +126,7 @@ void gemm_tc_ctx_destroy(mdc_ctx* ctx);
 int mdc_make_tmap_2d(mdc_ctx* ctx, const void* ptr, int64_t rows, int64_t cols, int64_t ld, int box_cols, int box_rows, int swizzle_mode, void* out_map);
 void decode_cluster_model_destroy(mdc_model* m);
 void decode_cluster_ctx_destroy(mdc_ctx* ctx);
+size_t decode_cluster_pack_bytes(const mdc_model* m);
+int decode_cluster_pack(mdc_model* m, void* out, cudaStream_t s);
+size_t decode_cluster_ckv_pack_bytes(const mdc_model* m, int B);
+int decode_cluster_ckv_pack(mdc_model* m, const void* ckv_plain, int B, void* out, cudaStream_t s);

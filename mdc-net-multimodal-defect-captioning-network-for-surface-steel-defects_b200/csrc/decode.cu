@@ -322,7 +322,7 @@ __device__ __forceinline__ void attend_one(const float* q /*smem, HD, pre-scaled
 #pragma unroll
     for (int i = 0; i < UN; ++i) {
       const int u = u0 + i * KPI + kslot;
-      if (u < nkeys) r[i].load(kv_ptr(u, 0) + sub * 8); else r[i].zero();
+      if (u < nkeys) r[i].load(kv_ptr(u, 0, sub)); else r[i].zero();
     }
 #pragma unroll
     for (int i = 0; i < UN; ++i) {
@@ -352,7 +352,7 @@ __device__ __forceinline__ void attend_one(const float* q /*smem, HD, pre-scaled
 #pragma unroll
     for (int i = 0; i < UN; ++i) {
       const int u = u0 + i * KPI + kslot;
-      if (u < nkeys) r[i].load(kv_ptr(u, 1) + sub * 8); else r[i].zero();
+      if (u < nkeys) r[i].load(kv_ptr(u, 1, sub)); else r[i].zero();
     }
 #pragma unroll
     for (int i = 0; i < UN; ++i) {
@@ -377,7 +377,13 @@ __device__ __forceinline__ void attend_one(const float* q /*smem, HD, pre-scaled
 }
 
 // self-attention: appends this step's k,v to the paged cache, then attends over slots 0..t.
-// pool layout: [page][layer][k|v][page_tokens][d]
+// pool layout: [page][layer][head][k|v][page_tokens][hd] -- the K and V rows of one (page, layer, head) are one contiguous
+// 2 * page_tokens * hd block (the fused decode kernel fetches it with ONE bulk copy).  When a row is 64 bytes (hd = 32, 16-bit
+// cache) the 16-byte chunk c of token r is stored at chunk c ^ ((r >> 1) & 3): the bank-conflict-free pattern of the fused kernel's
+// ldmatrix reads (what TMA SWIZZLE_64B would produce), shared by both implementations.
+template <typename TKV, int HD>
+__device__ __forceinline__ int kv_chunk(int r, int c) { return (HD * (int)sizeof(TKV) == 64) ? (c ^ ((r >> 1) & 3)) : c; }
+
 template <typename TKV, int HD>
 __global__ void dec_self_attn_kernel(const float* __restrict__ qkv /*[B,3d]*/, TKV* __restrict__ pool,
                                      const int32_t* __restrict__ page_table, int pages_per_seq, int PT, int n_layers, int layer,
@@ -392,19 +398,22 @@ __global__ void dec_self_attn_kernel(const float* __restrict__ qkv /*[B,3d]*/, T
   const float* row = qkv + (int64_t)b * 3 * d;
   for (int j = lane; j <= t / PT; j += 32) pt[j] = page_table[(int64_t)b * pages_per_seq + j];
   __syncwarp();
-  const int64_t plane = (int64_t)PT * d;                    // one k or v plane of a page/layer
+  const int64_t plane = (int64_t)PT * hd;                   // the k or v rows of one (page, layer, head)
+  auto kv_base = [&](int u, int which) -> TKV* {
+    return pool + ((((int64_t)pt[u / PT] * n_layers + layer) * heads + head) * 2 + which) * plane + (int64_t)(u % PT) * hd;
+  };
   {  // append k_t, v_t (this head's channels) and stage q
-    TKV* kdst = pool + (((int64_t)pt[t / PT] * n_layers + layer) * 2) * plane + (int64_t)(t % PT) * d + head * hd;
+    TKV* kdst = kv_base(t, 0); TKV* vdst = kv_base(t, 1);
+    const int r = t % PT;
     for (int c = lane; c < hd; c += 32) {
       q[c] = row[head * hd + c] * scale;
-      kdst[c] = from_f<TKV>(row[d + head * hd + c]);
-      kdst[plane + c] = from_f<TKV>(row[2 * d + head * hd + c]);
+      const int pc = kv_chunk<TKV, HD>(r, c >> 3) * 8 + (c & 7);
+      kdst[pc] = from_f<TKV>(row[d + head * hd + c]);
+      vdst[pc] = from_f<TKV>(row[2 * d + head * hd + c]);
     }
   }
   __syncwarp();
-  auto kv_ptr = [&](int u, int which) -> const TKV* {
-    return pool + (((int64_t)pt[u / PT] * n_layers + layer) * 2 + which) * plane + (int64_t)(u % PT) * d + head * hd;
-  };
+  auto kv_ptr = [&](int u, int which, int sub) -> const TKV* { return kv_base(u, which) + kv_chunk<TKV, HD>(u % PT, sub) * 8; };
   auto bias = [&](int u) -> float { return tokens[(int64_t)b * tokens_ld + u] == pad_idx ? 1.0f : 0.0f; };
   attend_one<TKV, HD>(q, sc, t + 1, kv_ptr, bias, o + (int64_t)b * d + head * hd);
 }
@@ -421,7 +430,7 @@ __global__ void dec_cross_attn_kernel(const float* __restrict__ qc /*[B,d]*/, co
   for (int c = lane; c < hd; c += 32) q[c] = qc[(int64_t)b * d + head * hd + c] * scale;
   __syncwarp();
   const TKV* base = ckv_layer + (int64_t)b * S * 2 * d + head * hd;
-  auto kv_ptr = [&](int u, int which) -> const TKV* { return base + (int64_t)u * 2 * d + which * d; };
+  auto kv_ptr = [&](int u, int which, int sub) -> const TKV* { return base + (int64_t)u * 2 * d + which * d + sub * 8; };
   auto bias = [&](int) -> float { return 0.f; };
   attend_one<TKV, HD>(q, sc, S, kv_ptr, bias, o + (int64_t)b * d + head * hd);
 }

@@ -26,7 +26,6 @@
 // The generic kernels in decode.cu remain the path for the fp32 token-exact mode and other geometries;
 // mdc_decode_steps picks this kernel when the geometry matches.
 #include "common.cuh"
-#include <cuda.h>
 #include <cuda_fp16.h>
 #include <stdlib.h>
 #include <string.h>
@@ -45,39 +44,38 @@ constexpr int FS = FFN / CS;       // hidden units per CTA (256)
 constexpr int NCT = 256;           // consumer threads (8 warps)
 constexpr int NT = NCT + 32;       // + producer warp
 constexpr int XP = DM + 8;         // fp16 elements per padded activation row (528 B: conflict-free ldmatrix)
-constexpr int STAGE_BYTES = 16384;   // one ring stage: a 32-row weight block (32 x 512 B), the K or V panel of one image (S <= 256 keys x 64 B) or packed self-KV pages
+constexpr int BLK_BYTES = 16384;     // one 32-row weight block (32 rows x 512 B); a ring stage holds NB of them, or one 16-key chunk of every image's K and V
 constexpr int VSL = 40;            // vocab rows per CTA; 8*40 = 320 >= V
-constexpr int PSTR = 36;           // floats per attention partial: m, l, -, -, o[32] (o is 16-byte aligned)
-constexpr int NPART = 9;           // attention partials per image: one per warp (interleaved key tiles) + the step's own key
+constexpr int OSTR = 36;           // floats per image in the attention output staging: o[32], running max, softmax denominator, -, -
 constexpr int NS_MAX = 10;
 
 // ---- shared memory map (bytes from the 1024-aligned base), per instantiation -------------------------------------
 // NB = 8-image column blocks per cluster pass: NB = 1 (up to 8 images per cluster: lowest latency, the serial path) or NB = 2
-// (up to 16 images: every weight fragment a warp loads feeds two MMA column blocks and every exchange carries twice the
-// images -- less SM-time per image, used by the batch pipeline).  With 16 images the per-group buffers double, so the ring
-// has 4 stages instead of 5, the FFN2 receive buffer shares its bytes with the attention partials and the select scratch
-// with the q/k staging (disjoint phases, see the ordering notes at the uses).
-// OVL: the overlays described above (always on with NB = 2; with NB = 1 they make the two-CTAs-per-SM layout fit).
+// (up to 16 images: every weight fragment a warp loads feeds two MMA column blocks, every exchange carries twice the images and
+// every warp attends for two images at a time -- less SM-time per image, used by the batch pipeline).  A ring stage is
+// NB x 16 KB: NB weight blocks of 32 rows, or one 16-key chunk of the K and V head slices of all 8 NB images.
+// OVL: the select scratch shares its bytes with the q/k/v/y staging (disjoint phases); always on with NB = 2, with NB = 1 it
+// makes the two-CTAs-per-SM layout fit.
 template <int NB, int NSTG, bool OVL>
 struct Lay {
   static constexpr int GMX = 8 * NB;                             // max images per cluster pass
-  static constexpr int NS = NSTG;                                // ring stages (160 KB in flight at NB = 1: +1.2 % over 4, same-box A/B)
+  static constexpr int NS = NSTG;                                // ring stages
+  static constexpr int STAGE = NB * BLK_BYTES;
   static constexpr int ACT_BYTES = GMX * XP * 2;
   static constexpr int OFF_RING = 0;
-  static constexpr int OFF_XH = OFF_RING + NS * STAGE_BYTES;      // LN output (fp16 projection operand)
+  static constexpr int OFF_XH = OFF_RING + NS * STAGE;            // LN output (fp16 projection operand)
   static constexpr int OFF_OH = OFF_XH + ACT_BYTES;               // gathered attention output (written by peers)
   static constexpr int OFF_FH = OFF_OH + ACT_BYTES;               // own FFN hidden slice
   static constexpr int OFF_XRES = OFF_FH + ACT_BYTES;             // [GMX][DM] f32 residual stream
   static constexpr int OFF_YRECV = OFF_XRES + GMX * DM * 4;       // [GMX][DM] f32 all-gathered projection output (peers write)
-  static constexpr int OFF_PART = OFF_YRECV + GMX * DM * 4;       // [GMX][NPART][PSTR] f32 attention partials
-  static constexpr int PART_BYTES = GMX * NPART * PSTR * 4;
   static constexpr int F2_BYTES = CS * GMX * 32 * 4;              // [CS src][GMX][32] f32 FFN2 partial sums (peers write)
-  static constexpr int OFF_F2RECV = !OVL ? OFF_PART + PART_BYTES : OFF_PART;
-  static constexpr int OFF_QS = !OVL ? OFF_F2RECV + F2_BYTES : OFF_PART + (PART_BYTES > F2_BYTES ? PART_BYTES : F2_BYTES);   // [GMX][32] f32 scaled query of the own head
+  static constexpr int OFF_F2RECV = OFF_YRECV + GMX * DM * 4;
+  static constexpr int OFF_QS = OFF_F2RECV + F2_BYTES;            // [GMX][32] f32 scaled query of the own head
   static constexpr int OFF_KNEW = OFF_QS + GMX * 32 * 4;          // [GMX][32] f32 this step's key (bf16-rounded)
   static constexpr int OFF_VNEW = OFF_KNEW + GMX * 32 * 4;
   static constexpr int OFF_YTMP = OFF_VNEW + GMX * 32 * 4;        // [GMX][32] f32 own slice of a projection before the push
-  static constexpr int OFF_QH = OFF_YTMP + GMX * 32 * 4;          // [GMX][32] bf16 scaled query (MMA A operand)
+  static constexpr int OFF_OST = OFF_YTMP + GMX * 32 * 4;         // [GMX][OSTR] f32 attention output staging (fragment -> channel order)
+  static constexpr int OFF_QH = OFF_OST + GMX * OSTR * 4;         // [GMX][32] bf16 scaled query (MMA A operand)
   static constexpr int OFF_LRECV = OFF_QH + GMX * 32 * 2;         // [NB][CS src][VSL] f32 logits of the images this CTA selects for
   static constexpr int SEL_BYTES = (CS * VSL + 512) * 4;          // select scratch: 320 + 512 floats
   static constexpr int OFF_SEL = !OVL ? OFF_LRECV + NB * CS * VSL * 4 : OFF_QS;
@@ -90,15 +88,19 @@ struct Lay {
   static constexpr int SMEM_USED = OFF_BARS + NBARS * 8;
   static constexpr int SMEM_BYTES = SMEM_USED + 1024;             // + alignment slack
   static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
-  static_assert(OFF_XH % 16 == 0 && OFF_XRES % 16 == 0 && OFF_PART % 16 == 0 && OFF_QS % 16 == 0 && OFF_BARS % 8 == 0, "alignment");
+  static_assert(OFF_XH % 16 == 0 && OFF_XRES % 16 == 0 && OFF_F2RECV % 16 == 0 && OFF_QS % 16 == 0 && OFF_OST % 16 == 0 && OFF_BARS % 8 == 0, "alignment");
   static_assert(!OVL || 4 * GMX * 32 * 4 >= SEL_BYTES, "select scratch must fit the q/k/v/y staging it shares");
+  static_assert(GMX * 2048 == STAGE, "a 16-key chunk of all images' K and V head slices fills a stage");
 };
 
 enum { BAR_FULL = 0, BAR_EMPTY = NS_MAX, BAR_O = 2 * NS_MAX, BAR_Y, BAR_F2, BAR_LG, BAR_TOK, BAR_COUNT };
 
+constexpr int BLOCKS_PER_LAYER = 22;   // packed weight blocks per (layer, CTA rank): in-proj q,k,v | self out | cross q | cross out | FFN1 x8 | FFN2 x8
+constexpr int HEAD_PACK_BYTES = BLK_BYTES + 8 * 512;    // per rank: vocabulary rows [0,32) as a 32-row block + rows [32,40) as an 8-row block
+
 struct __align__(64) FusedParams {
-  CUtensorMap m_in[8], m_so[8], m_ca[8], m_co[8], m_f1[8], m_f2[8];
-  CUtensorMap m_head, m_head8, m_ckv, m_pool;
+  const uint8_t* wpack;          // packed decode-loop weights (mdc_decode_pack): ready-to-use shared-memory images, one bulk copy per stage
+  const uint8_t* ckv_pack;       // packed cross-K/V (mdc_cross_kv_build): [layer][image][head][16-key chunk] x 2 KB
   const float* b_in[8]; const float* b_so[8]; const float* ln1w[8]; const float* ln1b[8];
   const float* b_ca[8]; const float* b_co[8]; const float* ln2w[8]; const float* ln2b[8];
   const float* b_f1[8]; const float* b_f2[8]; const float* ln3w[8]; const float* ln3b[8];
@@ -152,9 +154,13 @@ __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 __device__ __forceinline__ void cbar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }   // the 8 consumer warps
-__device__ __forceinline__ void tma_2d(const CUtensorMap* map, uint32_t bar, uint32_t dst, int c0, int c1) {
-  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-               ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+// TMA bulk copy (non-tensor): `bytes` contiguous bytes global -> shared, completion counted on an mbarrier.  The kernel moves
+// EVERYTHING it streams this way (16-32 KB weight stages, 2 KB key/value chunks): tensor-map boxes cost the TMA unit ~4.5 cycles per
+// box ROW whatever its width (64-byte head slices: 14 B/clk/SM, 128-byte weight rows: 28 B/clk/SM -- profiles/r2d), which bounded the
+// previous version of this kernel; contiguous copies of pre-arranged shared-memory images do not pay per row.
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
 __device__ __forceinline__ void ldsm_x4(uint32_t* r, uint32_t addr) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
@@ -244,107 +250,91 @@ __device__ __forceinline__ void ldsm_x4_trans(uint32_t* r, uint32_t addr) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
 }
 
-// A fragments of q from its bf16 row (32 dims): aq[ks][h] covers dims 16*ks + 8*h + {2q, 2q+1} of MMA row 0 (other rows 0)
+// A fragments of q from its bf16 row (32 dims): aq[ks][h] covers dims 16*ks + 8*h + {2q, 2q+1}.  The query fills ALL eight row groups
+// of the M operand (rows 8-15 stay zero): every row group then computes the same scores, so the running maximum, the rescale factor
+// and the probabilities are identical in all lanes of a quad column and every column of P.V carries the output -- no broadcast.
 __device__ __forceinline__ void build_q_frag(const bf16* qh, uint32_t (&aq)[2][2]) {
-  const int lane = threadIdx.x & 31, g = lane >> 2, q4 = lane & 3;
+  const int q4 = threadIdx.x & 3;
   const bf16* src = qh + 2 * q4;
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const uint32_t v = *reinterpret_cast<const uint32_t*>(src + (i >> 1) * 16 + (i & 1) * 8);
-    aq[i >> 1][i & 1] = g == 0 ? v : 0u;
-  }
+  for (int i = 0; i < 4; ++i) aq[i >> 1][i & 1] = *reinterpret_cast<const uint32_t*>(src + (i >> 1) * 16 + (i & 1) * 8);
 }
 
 __device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 
-// One query against key tiles tl, tl + tstep (at most two, 16 keys each) of one (K, V) panel pair as ONE straight-line chunk: a
-// tile past the end is clamped onto tile `tl` and masked, so there is no control flow between the fragment loads and the MMAs and
-// all four K fragments and all four V fragments (which do not depend on the scores) are requested before the first MMA (volatile
-// asm: program order is issue order) -- the chunk pays the ldmatrix latency once.  Requires tl < ntile.  On return m_out / l_out
-// are valid in lanes 0-3; the un-normalised output of dims mt*16 + {g, g+8} sits in lanes with q == 0 as o[mt][0] and o[mt][2].
-__device__ __forceinline__ void attn_chunk2(uint32_t kp, uint32_t vp, const uint32_t (&aq)[2][2], int tl, int tstep, int ntile, int nkeys,
-                                            const uint32_t* padf, float& m_out, float& l_out, float (&o)[2][4]) {
+// running state of one (image, head) attention job, owned by ONE warp for the whole key range (flash-style online softmax):
+// m: running maximum (log2 units), ls: this lane's share of the softmax denominator (lanes of a quad hold different keys),
+// o: un-normalised output, dims mt*16 + {g, g+8} as o[mt][0] / o[mt][2] (every lane of the row group holds a copy).
+struct AttnState { float m, ls; float o[2][4]; };
+
+// One 16-key tile (a [16 keys][64 B] K panel and V panel, TMA SWIZZLE_64B: 16-byte chunk c of key r at c ^ ((r >> 1) & 3)) for N
+// images at once, written phase by phase across the images (the asm statements are volatile: program order is issue order), so
+// that the two images of a warp overlap their ldmatrix / MMA / shuffle latencies.  key0: index of the tile's first key; keys
+// >= nkeys are masked; padw: PAD bit rows (or null).
+template <int N>
+__device__ __forceinline__ void attn_tile(const uint32_t (&kp)[N], const uint32_t (&vp)[N], const uint32_t (&aq)[N][2][2], int key0, int nkeys,
+                                          const uint32_t* const (&padw)[N], AttnState (&st)[N]) {
   const int lane = threadIdx.x & 31, q4 = lane & 3;
-  const uint32_t a_k0[4] = {aq[0][0], 0u, aq[0][1], 0u}, a_k1[4] = {aq[1][0], 0u, aq[1][1], 0u};
-  const bool two = tl + tstep < ntile;
-  const int k0a = tl * 16, k0b = (two ? tl + tstep : tl) * 16;
-  uint32_t kb[2][2][4], va[2][2][4];
+  uint32_t kb[N][2][4], va[N][2][4];
 #pragma unroll
-  for (int i = 0; i < 2; ++i) {
-    const int k0 = i ? k0b : k0a;
+  for (int n = 0; n < N; ++n)
 #pragma unroll
-    for (int j = 0; j < 2; ++j) {              // 8-key n-tile j: one ldmatrix.x4 = the four dim chunks of keys k0+8j .. +7
-      const int key = k0 + 8 * j + (lane & 7);
-      ldsm_x4(kb[i][j], kp + key * 64 + (((lane >> 3) ^ ((key >> 1) & 3)) << 4));
+    for (int j = 0; j < 2; ++j) {              // 8-key n-tile j: one ldmatrix.x4 = the four dim chunks of keys 8j .. 8j+7
+      const int r = 8 * j + (lane & 7);
+      ldsm_x4(kb[n][j], kp[n] + r * 64 + (((lane >> 3) ^ ((r >> 1) & 3)) << 4));
     }
-  }
 #pragma unroll
-  for (int i = 0; i < 2; ++i) {
-    const int key = (i ? k0b : k0a) + ((lane >> 4) & 1) * 8 + (lane & 7), sw = (key >> 1) & 3, dsel = (lane >> 3) & 1;
-    ldsm_x4_trans(va[i][0], vp + key * 64 + ((dsel ^ sw) << 4));
-    ldsm_x4_trans(va[i][1], vp + key * 64 + (((2 + dsel) ^ sw) << 4));
+  for (int n = 0; n < N; ++n) {
+    const int r = ((lane >> 4) & 1) * 8 + (lane & 7), sw = (r >> 1) & 3, dsel = (lane >> 3) & 1;
+    ldsm_x4_trans(va[n][0], vp[n] + r * 64 + ((dsel ^ sw) << 4));
+    ldsm_x4_trans(va[n][1], vp[n] + r * 64 + (((2 + dsel) ^ sw) << 4));
   }
-  float sc[2][4];
+  float sc[N][4];
 #pragma unroll
-  for (int i = 0; i < 2; ++i)
+  for (int n = 0; n < N; ++n) {
+    const uint32_t a_k0[4] = {aq[n][0][0], 0u, aq[n][0][1], 0u}, a_k1[4] = {aq[n][1][0], 0u, aq[n][1][1], 0u};
 #pragma unroll
     for (int j = 0; j < 2; ++j) {
       float c[4] = {0.f, 0.f, 0.f, 0.f}, d[4] = {0.f, 0.f, 0.f, 0.f};
-      mma16816(c, a_k0, kb[i][j][0], kb[i][j][1]);
-      mma16816(d, a_k1, kb[i][j][2], kb[i][j][3]);
-      sc[i][2 * j] = c[0] + d[0];
-      sc[i][2 * j + 1] = c[1] + d[1];
+      mma16816(c, a_k0, kb[n][j][0], kb[n][j][1]);
+      mma16816(d, a_k1, kb[n][j][2], kb[n][j][3]);
+      sc[n][2 * j] = c[0] + d[0];
+      sc[n][2 * j + 1] = c[1] + d[1];
     }
+  }
+  float mx[N];
 #pragma unroll
-  for (int i = 0; i < 2; ++i)
+  for (int n = 0; n < N; ++n) {
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-      const int key = (i ? k0b : k0a) + (e >> 1) * 8 + 2 * q4 + (e & 1);
-      if (padf != nullptr && ((padf[key >> 5] >> (key & 31)) & 1u)) sc[i][e] += LOG2E;   // float PAD-key bias +1.0 (Q7), in log2 units (padf: rare)
-      if (key >= nkeys || (i == 1 && !two)) sc[i][e] = -INFINITY;        // tail of the last tile / clamped duplicate tile
+      const int key = key0 + (e >> 1) * 8 + 2 * q4 + (e & 1);
+      if (padw[n] != nullptr && ((padw[n][key >> 5] >> (key & 31)) & 1u)) sc[n][e] += LOG2E;   // float PAD-key bias +1.0 (Q7), in log2 units
+      if (key >= nkeys) sc[n][e] = -INFINITY;                                                  // tail of the last tile
     }
-  float mx = fmaxf(fmaxf(fmaxf(sc[0][0], sc[0][1]), fmaxf(sc[0][2], sc[0][3])), fmaxf(fmaxf(sc[1][0], sc[1][1]), fmaxf(sc[1][2], sc[1][3])));
-  mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
-  mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
-  // only row group g = 0 (lanes 0-3) holds scores -- key tl*16 is valid, so their mx is finite; the other lanes work on the all-zero
-  // rows of the M operand (scores 0, own mx 0, p = 1: finite) and feed output columns that are never read, so no broadcast is needed
-  float ls = 0.f;
-  float o2[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};          // second tile: its own accumulator chain
+    mx[n] = fmaxf(fmaxf(sc[n][0], sc[n][1]), fmaxf(sc[n][2], sc[n][3]));
+  }
 #pragma unroll
-  for (int i = 0; i < 2; ++i) {
+  for (int n = 0; n < N; ++n) mx[n] = fmaxf(mx[n], __shfl_xor_sync(0xffffffffu, mx[n], 1));
+#pragma unroll
+  for (int n = 0; n < N; ++n) mx[n] = fmaxf(mx[n], __shfl_xor_sync(0xffffffffu, mx[n], 2));
+#pragma unroll
+  for (int n = 0; n < N; ++n) {
+    // key0 < nkeys: the tile holds a valid key, so the quad maximum is finite; the first tile meets m = -inf: factor 0 on a zero state
+    const float m_new = fmaxf(st[n].m, mx[n]);
+    const float sf = ex2_approx(st[n].m - m_new);
+    st[n].m = m_new;
     float p[4];
 #pragma unroll
-    for (int e = 0; e < 4; ++e) { p[e] = ex2_approx(sc[i][e] - mx); ls += p[e]; }
-    const uint32_t b0 = pack_bf16(p[0], p[1]), b1 = pack_bf16(p[2], p[3]);   // column 0 of the B operand lives in row group g = 0
-    if (i == 0) { mma16816(o[0], va[0][0], b0, b1); mma16816(o[1], va[0][1], b0, b1); }
-    else { mma16816(o2[0], va[1][0], b0, b1); mma16816(o2[1], va[1][1], b0, b1); }
+    for (int e = 0; e < 4; ++e) p[e] = ex2_approx(sc[n][e] - m_new);
+    st[n].ls = fmaf(st[n].ls, sf, (p[0] + p[1]) + (p[2] + p[3]));
+    const uint32_t b0 = pack_bf16(p[0], p[1]), b1 = pack_bf16(p[2], p[3]);
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) st[n].o[mt][e] *= sf;
+    mma16816(st[n].o[0], va[n][0], b0, b1);
+    mma16816(st[n].o[1], va[n][1], b0, b1);
   }
-  ls += __shfl_xor_sync(0xffffffffu, ls, 1);
-  ls += __shfl_xor_sync(0xffffffffu, ls, 2);
-  l_out = ls;          // valid in lanes 0-3 (lane 0 stores the partial)
-  m_out = mx;
-#pragma unroll
-  for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-    for (int e = 0; e < 4; ++e) o[mt][e] += o2[mt][e];
-}
-
-// merge the partial results (m, l, -, -, o[32]) of one image; lane = channel.  `mask`: bit p set for every slot p (< NPART)
-// written this phase; slots with l == 0 are empty.
-__device__ __forceinline__ float attn_merge(const float* parts, uint32_t mask) {
-  const int lane = threadIdx.x & 31;
-  float m = -INFINITY, l = 0.f;
-  if ((mask >> lane) & 1u) { m = parts[lane * PSTR]; l = parts[lane * PSTR + 1]; if (!(l > 0.f)) m = -INFINITY; }
-  const float M = warp_max(m);
-  const float w = (l > 0.f) ? exp2f(m - M) : 0.f;
-  const float L = warp_sum(w * l);
-  float o = 0.f;
-#pragma unroll
-  for (int p = 0; p < NPART; ++p) {
-    const float wp = __shfl_sync(0xffffffffu, w, p);
-    if (wp != 0.f) o = fmaf(wp, parts[p * PSTR + 4 + lane], o);      // warp-uniform
-  }
-  return o / L;
 }
 
 // Greedy select of one image by ONE warp, no block barrier: argmax (lowest index on ties, like torch.argmax) and the maximal
@@ -370,7 +360,7 @@ __device__ __forceinline__ void warp_greedy_select(const float* lg, int V, int& 
 template <bool kTrace, int NB, int NSTG, int MINB>
 __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(NT, MINB) decode_fused_kernel(const __grid_constant__ FusedParams P) {
   using Y = Lay<NB, NSTG, NB == 2 || MINB == 2>;
-  constexpr int GMX = Y::GMX, NS = Y::NS;
+  constexpr int GMX = Y::GMX, NS = Y::NS, STAGE = Y::STAGE;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);      // pointer arithmetic keeps the shared address space
@@ -382,7 +372,7 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(NT, MINB) decode_fu
   __half* xh = (__half*)(smem + Y::OFF_XH); __half* fh = (__half*)(smem + Y::OFF_FH);      // projection operands (fp16)
   float* xres = (float*)(smem + Y::OFF_XRES); float* yrecv = (float*)(smem + Y::OFF_YRECV); float* f2recv = (float*)(smem + Y::OFF_F2RECV);
   float* qs = (float*)(smem + Y::OFF_QS); float* knew = (float*)(smem + Y::OFF_KNEW); float* vnew = (float*)(smem + Y::OFF_VNEW);
-  float* ytmp = (float*)(smem + Y::OFF_YTMP); float* part = (float*)(smem + Y::OFF_PART);
+  float* ytmp = (float*)(smem + Y::OFF_YTMP); float* ost = (float*)(smem + Y::OFF_OST);
   bf16* qh = (bf16*)(smem + Y::OFF_QH);
   float* lrecv = (float*)(smem + Y::OFF_LRECV); float* selbuf = (float*)(smem + Y::OFF_SEL);
   int* tokbuf = (int*)(smem + Y::OFF_TOK); int* pages = (int*)(smem + Y::OFF_PAGES); uint32_t* padbits = (uint32_t*)(smem + Y::OFF_PADF);
@@ -395,19 +385,15 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(NT, MINB) decode_fu
     for (int i = BAR_O; i <= BAR_TOK; ++i) mbar_init(bar(i), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  // zero the ring and the activation operands once: rows >= G of the operands and the rows behind a partial key tile
-  // of a K/V panel are multiplied by zeros and must be finite
-  for (int i = tid; i < (NS * STAGE_BYTES + 3 * Y::ACT_BYTES) / 16; i += NT) reinterpret_cast<uint4*>(smem + Y::OFF_RING)[i] = make_uint4(0u, 0u, 0u, 0u);
+  // zero the ring and the activation operands once: rows >= G of the operands are multiplied by weights and must be finite
+  // (ring bytes that a stage does not fill are only ever stale finite fp16 / bf16 data of earlier stages)
+  for (int i = tid; i < (NS * STAGE + 3 * Y::ACT_BYTES) / 16; i += NT) reinterpret_cast<uint4*>(smem + Y::OFF_RING)[i] = make_uint4(0u, 0u, 0u, 0u);
   __syncthreads();
   cluster_sync_all();
 
   const float scale = rsqrtf((float)HD) * LOG2E;      // scores in log2 units: p = exp2(s - m)
   const int L = P.layers, S = P.S;
-  const int nC = P.G;                                 // cross stages: K and V panel of ONE image each (by the full group size)
-  // Self-KV stages are sized per step: with npg pages of keys an image is split into wpi = 1 / 2 / 4 / 8 chunks of two key tiles
-  // (2 * wpi >= npg) and a 32 KB stage holds the K and V panels (wpi * 2 KB each) of ips = 8 / wpi images -- early steps pack 8 or 4
-  // images into a stage.  A function of the step only (never of the batch: results stay batch-invariant).
-  auto self_wpi = [](int npg) { return npg <= 2 ? 1 : (npg <= 4 ? 2 : (npg <= 8 ? 4 : 8)); };
+  const int nck = (S + 15) >> 4;                      // cross-attention key chunks (16 keys each)
 
   // ring cursors (producer and consumers keep their own copies)
   uint32_t slot = 0, phase = 0;
@@ -445,98 +431,58 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(NT, MINB) decode_fu
         const long long c0 = kTrace ? clock64() : 0;
         mbar_wait(bar(BAR_EMPTY + slot), phase ^ 1);
         if (kTrace) prod_wait += clock64() - c0;
-        return sbase + Y::OFF_RING + slot * STAGE_BYTES;
+        return sbase + Y::OFF_RING + slot * STAGE;
       };
       auto advance = [&]() { if (++slot == NS) { slot = 0; phase ^= 1; } };
-      // one weight row block: 4 k-blocks of [R rows x 64 k]
-      auto load_rows = [&](const CUtensorMap* m, uint32_t dst, uint32_t fb, int col0, int row0, int R) {
-#pragma unroll
-        for (int kb = 0; kb < 4; ++kb) tma_2d(m, fb, dst + kb * R * 128, col0 + kb * 64, row0);
+      // packed weights of (layer l, this CTA): BLOCKS_PER_LAYER consecutive 16 KB blocks in consumption order; a projection of
+      // nblk blocks starting at block `first` takes ceil(nblk / NB) stages, each ONE bulk copy of up to NB blocks
+      const uint8_t* wl = nullptr;
+      auto emit_proj = [&](int first, int nblk) {
+        for (int s = 0; s * NB < nblk; ++s) {
+          const int here = min(NB, nblk - s * NB);
+          const uint32_t st = acquire(); const uint32_t fb = bar(BAR_FULL + slot);
+          if (lane == 0) {
+            mbar_expect_tx(fb, here * BLK_BYTES);
+            bulk_g2s(st, wl + (size_t)(first + s * NB) * BLK_BYTES, here * BLK_BYTES, fb);
+          }
+          advance();
+        }
+      };
+      // chunk c (16 keys) of the K and V head slices of all images of the group: [image][k|v][16 keys][64 B], one 2 KB copy per image
+      auto emit_kv = [&](bool cross, int l, int c) {
+        const uint32_t st = acquire(); const uint32_t fb = bar(BAR_FULL + slot);
+        if (lane == 0) mbar_expect_tx(fb, G * 2048);
+        __syncwarp();
+        if (lane < G) {
+          const uint8_t* src = cross ? P.ckv_pack + ((((size_t)l * P.B + img0 + lane) * CS + rank) * nck + c) * 2048
+                                     : (const uint8_t*)P.kv_pool + (((size_t)pages[lane * 32 + c] * L + l) * CS + rank) * 2048;
+          bulk_g2s(st + lane * 2048, src, 2048, fb);
+        }
+        advance();
       };
       for (int t = P.t_begin; t < P.t_end; ++t) {
-        const int npg = (t + P.PT - 1) / P.PT;     // pages holding keys 0..t-1
-        const int wpi_t = self_wpi(npg);
-        const bool split_kv = wpi_t == 8;          // K panel and V panel of ONE image fill a stage each
-        const int ips_t = split_kv ? 1 : 4 / wpi_t, nS = split_kv ? 2 * P.G : (P.G + ips_t - 1) / ips_t;
-        const uint32_t self_panel = (uint32_t)wpi_t * 2048u;
+        const int npg = (t + P.PT - 1) / P.PT;     // pages (= 16-key chunks) holding keys 0..t-1
         for (int l = 0; l < L; ++l) {
-          for (int part = 0; part < 3; ++part) {   // in-proj: own head's q rows, k rows, v rows
-            const uint32_t st = acquire(); const uint32_t fb = bar(BAR_FULL + slot);
-            if (lane == 0) { mbar_expect_tx(fb, 32 * 512); load_rows(&P.m_in[l], st, fb, 0, part * DM + rank * HD, 32); }
-            advance();
-          }
-          if (!split_kv) {
-            for (int sg = 0; sg < nS; ++sg) {      // self-KV: K and V pages of images [sg*ips, ...), panels [gi][k|v]
-              const int g0 = sg * ips_t, gn = max(0, min(ips_t, G - g0));
-              const int ops = gn * 2 * npg;
-              const uint32_t st = acquire(); const uint32_t fb = bar(BAR_FULL + slot);
-              if (lane == 0) mbar_expect_tx(fb, ops * P.PT * 64);
-              __syncwarp();
-              for (int op = lane; op < ops; op += 32) {
-                const int pn = op / npg, j = op - pn * npg;          // pn = gi*2 + which
-                const int page = pages[(g0 + (pn >> 1)) * 32 + j];
-                tma_2d(&P.m_pool, fb, st + pn * self_panel + j * (P.PT * 64), rank * HD, ((page * L + l) * 2 + (pn & 1)) * P.PT);
-              }
-              advance();
-            }
-          } else {
-            for (int sg = 0; sg < nS; ++sg) {      // more than 8 pages of keys: the K pages of image sg/2 in one stage, its V pages in the next
-              const int g = sg >> 1, which = sg & 1;
-              const int ops = g < G ? npg : 0;
-              const uint32_t st = acquire(); const uint32_t fb = bar(BAR_FULL + slot);
-              if (lane == 0) mbar_expect_tx(fb, ops * P.PT * 64);
-              __syncwarp();
-              if (lane < ops) {
-                const int page = pages[g * 32 + lane];
-                tma_2d(&P.m_pool, fb, st + lane * (P.PT * 64), rank * HD, ((page * L + l) * 2 + which) * P.PT);
-              }
-              advance();
-            }
-          }
-          {  // self out-proj rows, cross-q rows
-            uint32_t st = acquire(); uint32_t fb = bar(BAR_FULL + slot);
-            if (lane == 0) { mbar_expect_tx(fb, 32 * 512); load_rows(&P.m_so[l], st, fb, 0, rank * 32, 32); }
-            advance();
-            st = acquire(); fb = bar(BAR_FULL + slot);
-            if (lane == 0) { mbar_expect_tx(fb, 32 * 512); load_rows(&P.m_ca[l], st, fb, 0, rank * 32, 32); }
-            advance();
-          }
-          for (int sg = 0; sg < 2 * nC; ++sg) {    // cross K panel of image sg/2 in one stage, its V panel in the next
-            const int g = sg >> 1, which = sg & 1;
-            const uint32_t st = acquire(); const uint32_t fb = bar(BAR_FULL + slot);
-            if (lane == 0) {
-              if (g < G) {
-                mbar_expect_tx(fb, S * 64);
-                tma_2d(&P.m_ckv, fb, st, which * DM + rank * HD, (l * P.B + img0 + g) * S);
-              } else mbar_expect_tx(fb, 0);
-            }
-            advance();
-          }
-          {  // cross out-proj rows
-            const uint32_t st = acquire(); const uint32_t fb = bar(BAR_FULL + slot);
-            if (lane == 0) { mbar_expect_tx(fb, 32 * 512); load_rows(&P.m_co[l], st, fb, 0, rank * 32, 32); }
-            advance();
-          }
-          for (int s8 = 0; s8 < 8; ++s8) {         // FFN1: own hidden rows, 32 per stage
-            const uint32_t st = acquire(); const uint32_t fb = bar(BAR_FULL + slot);
-            if (lane == 0) { mbar_expect_tx(fb, 32 * 512); load_rows(&P.m_f1[l], st, fb, 0, rank * FS + s8 * 32, 32); }
-            advance();
-          }
-          for (int s8 = 0; s8 < 8; ++s8) {         // FFN2: K-split over the own hidden columns, 32 output features per stage
-            const uint32_t st = acquire(); const uint32_t fb = bar(BAR_FULL + slot);
-            if (lane == 0) { mbar_expect_tx(fb, 32 * 512); load_rows(&P.m_f2[l], st, fb, rank * FS, s8 * 32, 32); }
-            advance();
-          }
+          wl = P.wpack + ((size_t)l * CS + rank) * BLOCKS_PER_LAYER * BLK_BYTES;
+          emit_proj(0, 3);                                            // in-proj: own head's q rows, k rows, v rows
+          for (int c = 0; c < npg; ++c) emit_kv(false, l, c);        // self-KV pages
+          emit_proj(3, 1);                                            // self out-proj rows
+          emit_proj(4, 1);                                            // cross-q rows
+          for (int c = 0; c < nck; ++c) emit_kv(true, l, c);         // cross K/V chunks
+          emit_proj(5, 1);                                            // cross out-proj rows
+          emit_proj(6, 8);                                            // FFN1: own hidden rows
+          emit_proj(14, 8);                                           // FFN2: K-split over the own hidden columns
         }
-        {  // vocabulary head rows: [0,32) of the own 40 in one stage, [32,40) in the next
+        // vocabulary head rows: [0,32) of the own 40 as one block, [32,40) as an 8-row block (same stage with NB = 2, the next otherwise)
+        {
+          const uint8_t* hp = P.wpack + (size_t)L * CS * BLOCKS_PER_LAYER * BLK_BYTES + (size_t)rank * HEAD_PACK_BYTES;
           uint32_t st = acquire(); uint32_t fb = bar(BAR_FULL + slot);
-          if (lane == 0) { mbar_expect_tx(fb, 32 * 512); load_rows(&P.m_head, st, fb, 0, rank * VSL, 32); }
-          advance();
-          st = acquire(); fb = bar(BAR_FULL + slot);
-          if (lane == 0) {
-            mbar_expect_tx(fb, 8 * 512);
-#pragma unroll
-            for (int kb = 0; kb < 4; ++kb) tma_2d(&P.m_head8, fb, st + kb * 8 * 128, kb * 64, rank * VSL + 32);
+          if (NB == 2) {
+            if (lane == 0) { mbar_expect_tx(fb, HEAD_PACK_BYTES); bulk_g2s(st, hp, HEAD_PACK_BYTES, fb); }
+          } else {
+            if (lane == 0) { mbar_expect_tx(fb, BLK_BYTES); bulk_g2s(st, hp, BLK_BYTES, fb); }
+            advance(); st = acquire(); fb = bar(BAR_FULL + slot);
+            if (lane == 0) { mbar_expect_tx(fb, 8 * 512); bulk_g2s(st, hp + BLK_BYTES, 8 * 512, fb); }
           }
           advance();
         }
@@ -549,14 +495,7 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(NT, MINB) decode_fu
         const long long c0 = kTrace ? clock64() : 0;
         mbar_wait(bar(BAR_FULL + slot), phase);
         if (kTrace) cons_wait += clock64() - c0;
-        return sbase + Y::OFF_RING + slot * STAGE_BYTES;
-      };
-      auto stage_wait_next = [&]() -> uint32_t {     // the stage after the cursor (two-stage jobs: K panel, then V panel)
-        const uint32_t s1 = slot + 1 == NS ? 0u : slot + 1, p1 = slot + 1 == NS ? phase ^ 1u : phase;
-        const long long c0 = kTrace ? clock64() : 0;
-        mbar_wait(bar(BAR_FULL + s1), p1);
-        if (kTrace) cons_wait += clock64() - c0;
-        return sbase + Y::OFF_RING + s1 * STAGE_BYTES;
+        return sbase + Y::OFF_RING + slot * STAGE;
       };
       auto xwait = [&](int which, uint32_t& ph) {    // wait for a push-style exchange
         const long long c0 = kTrace ? clock64() : 0;
@@ -579,6 +518,20 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(NT, MINB) decode_fu
       };
       const int gi_t = tid >> 5, c_t = tid & 31;     // (image [+ 8], channel) coordinates of the elementwise phases
       constexpr int APP0 = NCT - GMX * 8;           // first thread of the KV-append crew (the last GMX * 8 consumer threads)
+      // A projection of nblk 32-row weight blocks, NB blocks per stage: block b belongs to warp pair b % 4 (16 rows per warp).
+      // body(b, block address, m-tile 0 / 1) runs in the two warps of the pair; every other warp only advances its ring cursor.
+      auto proj_blocks = [&](int nblk, auto&& body) {
+        const int pr = warp >> 1;
+        for (int s = 0; s * NB < nblk; ++s) {
+          const int j = (pr - s * NB) & 3, b = s * NB + j;
+          if (j < NB && b < nblk) {
+            const uint32_t users = 2u * (uint32_t)min(NB, nblk - s * NB);
+            const uint32_t st = stage_wait();
+            body(b, st + j * BLK_BYTES, warp & 1);
+            stage_release(8u / users);
+          } else stage_skip();
+        }
+      };
       // push this CTA's [G][32] slice in ytmp into every peer's yrecv columns [32*rank, +32)
       auto push_y = [&](int img, float v) {
         if (img < G) {
@@ -645,48 +598,84 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(NT, MINB) decode_fu
       auto proj32_push = [&](uint32_t bh, const float* bias) {
         float b0 = 0.f, b1 = 0.f;
         if (warp < 2) { b0 = __ldg(bias + rank * 32 + warp * 16 + fg); b1 = __ldg(bias + rank * 32 + warp * 16 + fg + 8); }
-        if (warp < 2) {
-          const uint32_t st = stage_wait();
+        proj_blocks(1, [&](int, uint32_t blk, int mt) {
           float acc[NB][4];
-          mma_mtile<32, NB>(st, warp * 16, bh, acc);
-          const int f = warp * 16 + fg;
+          mma_mtile<32, NB>(blk, mt * 16, bh, acc);
+          const int f = mt * 16 + fg;
 #pragma unroll
           for (int nb = 0; nb < NB; ++nb) {
             float* y = ytmp + (8 * nb + 2 * fq) * 32 + f;
             y[0] = acc[nb][0] + b0; y[32] = acc[nb][1] + b0; y[8] = acc[nb][2] + b1; y[40] = acc[nb][3] + b1;
           }
-          stage_release(4);
-        } else {
-          stage_skip();
-        }
+        });
         cbar();
 #pragma unroll
         for (int nb = 0; nb < NB; ++nb) push_y(gi_t + 8 * nb, ytmp[(gi_t + 8 * nb) * 32 + c_t]);
       };
-
-      // one warp's share of one (image, head) attention job: key tiles tl, tl + tstep of the panels kp / vp -> partial slot `pslot`
-      auto attend = [&](uint32_t kp, uint32_t vp, int g, int pslot, int tl, int tstep, int ntile, int nkeys, const uint32_t* padw) {
-        float* pb = part + (g * NPART + pslot) * PSTR;
-        if (tl < ntile) {
-          uint32_t aq[2][2];
-          build_q_frag(qh + g * 32, aq);
-          float m_run, l_run;
-          float o[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
-          attn_chunk2(kp, vp, aq, tl, tstep, ntile, nkeys, padw, m_run, l_run, o);
-          if (lane == 0) { pb[0] = m_run; pb[1] = l_run; }
-          if ((lane & 3) == 0) {
-            const int g8 = lane >> 2;
-            pb[4 + g8] = o[0][0]; pb[4 + g8 + 8] = o[0][2];
-            pb[4 + g8 + 16] = o[1][0]; pb[4 + g8 + 24] = o[1][2];
+      // Attention of head `rank` for the images of this warp (image `warp`, and `warp + 8` with NB = 2) over nchunk 16-key chunks:
+      // the warp keeps the running softmax state of its images in registers across the chunks (every warp reads every chunk stage:
+      // its own images' panels), then stages the un-normalised output, running maximum and denominator in `ost` (fragment order ->
+      // channel order).  One image = one warp = one fixed operation sequence: results do not depend on the batch or the variant.
+      auto attention = [&](int nchunk, int nkeys, bool use_pad, int l_now, int t_now) {
+        AttnState as[NB];
+        uint32_t aq[NB][2][2];
+        const uint32_t* padw[NB];
+#pragma unroll
+        for (int nb = 0; nb < NB; ++nb) {
+          const int img = warp + 8 * nb;
+          as[nb].m = -INFINITY; as[nb].ls = 0.f;
+#pragma unroll
+          for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) as[nb].o[mt][e] = 0.f;
+          padw[nb] = (use_pad && img < G && haspad[img]) ? padbits + img * 8 : nullptr;
+          if (img < G) build_q_frag(qh + img * 32, aq[nb]);
+          else { aq[nb][0][0] = aq[nb][0][1] = aq[nb][1][0] = aq[nb][1][1] = 0u; }
+        }
+        const bool two = NB == 2 && warp + 8 < G;
+        for (int c = 0; c < nchunk; ++c) {
+          if (warp == 0 && c < 8) FINE(l_now, t_now, 20 + c * 3);
+          const uint32_t st = stage_wait();
+          if (warp == 0 && c < 8) FINE(l_now, t_now, 21 + c * 3);
+          if (warp < G) {
+            bool done = false;
+            if constexpr (NB == 2) {
+              if (two) {
+                const uint32_t kp[2] = {st + warp * 2048u, st + (warp + 8) * 2048u};
+                const uint32_t vp[2] = {kp[0] + 1024u, kp[1] + 1024u};
+                attn_tile<2>(kp, vp, aq, c * 16, nkeys, padw, as);
+                done = true;
+              }
+            }
+            if (!done) {
+              const uint32_t kp[1] = {st + warp * 2048u}, vp[1] = {kp[0] + 1024u};
+              const uint32_t aq1[1][2][2] = {{{aq[0][0][0], aq[0][0][1]}, {aq[0][1][0], aq[0][1][1]}}};
+              const uint32_t* pw1[1] = {padw[0]};
+              AttnState a1[1] = {as[0]};
+              attn_tile<1>(kp, vp, aq1, c * 16, nkeys, pw1, a1);
+              as[0] = a1[0];
+            }
           }
-        } else if (lane == 0) pb[1] = 0.f;
+          stage_release();
+          if (warp == 0 && c < 8) FINE(l_now, t_now, 22 + c * 3);
+        }
+#pragma unroll
+        for (int nb = 0; nb < NB; ++nb) {
+          const int img = warp + 8 * nb;
+          if (img < G) {
+            float lt = as[nb].ls;
+            lt += __shfl_xor_sync(0xffffffffu, lt, 1);
+            lt += __shfl_xor_sync(0xffffffffu, lt, 2);
+            float* ob = ost + img * OSTR;
+            if (fq == 0) { ob[fg] = as[nb].o[0][0]; ob[fg + 8] = as[nb].o[0][2]; ob[fg + 16] = as[nb].o[1][0]; ob[fg + 24] = as[nb].o[1][2]; }
+            if (lane == 0) { ob[32] = as[nb].m; ob[33] = lt; }
+          }
+        }
+        __syncwarp();
       };
 
       for (int t = P.t_begin; t < P.t_end; ++t) {
-        const int wpi_t = self_wpi((t + P.PT - 1) / P.PT);
-        const bool split_kv = wpi_t == 8;
-        const int ips_t = split_kv ? 1 : 4 / wpi_t, nS = split_kv ? 2 * P.G : (P.G + ips_t - 1) / ips_t;
-        const uint32_t self_panel = (uint32_t)wpi_t * 2048u;
+        const int npg = (t + P.PT - 1) / P.PT;
         // ---- embedding + positional row (model.py:98-101); PAD flag of the token at position t --------------
         if (warp < G) {
           float pz[8];
@@ -711,39 +700,34 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(NT, MINB) decode_fu
         cbar();
         for (int l = 0; l < L; ++l) {
           TRACE(t);   // 0: layer start
-          // ---- self-attention in-proj: own head's q (warps 0-1), k (warps 2-3), v (warps 4-5), one 32-row stage each ------
+          // ---- self-attention in-proj: own head's q (warps 0-1), k (warps 2-3), v (warps 4-5), one 32-row block each ------
           {
             const float* bi = P.b_in[l];
             const int part = warp >> 1;                  // 0 q, 1 k, 2 v (3: no projection work)
             float b0 = 0.f, b1 = 0.f;
             if (part < 3) { const int r0 = part * DM + rank * HD + (warp & 1) * 16 + fg; b0 = __ldg(bi + r0); b1 = __ldg(bi + r0 + 8); }
+            proj_blocks(3, [&](int pt, uint32_t blk, int mt) {
+              float acc[NB][4];
+              mma_mtile<32, NB>(blk, mt * 16, sbase + Y::OFF_XH, acc);
+              const int f = mt * 16 + fg;
 #pragma unroll
-            for (int pt = 0; pt < 3; ++pt) {
-              if (part == pt) {
-                const uint32_t st = stage_wait();
-                float acc[NB][4];
-                mma_mtile<32, NB>(st, (warp & 1) * 16, sbase + Y::OFF_XH, acc);
-                const int f = (warp & 1) * 16 + fg;
-#pragma unroll
-                for (int nb = 0; nb < NB; ++nb) {
-                  const int o = (8 * nb + 2 * fq) * 32 + f;
-                  if (pt == 0) {       // q, pre-scaled
-                    const float q0 = (acc[nb][0] + b0) * scale, q1 = (acc[nb][1] + b0) * scale, q2 = (acc[nb][2] + b1) * scale, q3 = (acc[nb][3] + b1) * scale;
-                    const bf16 r0 = __float2bfloat16_rn(q0), r1 = __float2bfloat16_rn(q1), r2 = __float2bfloat16_rn(q2), r3 = __float2bfloat16_rn(q3);
-                    qh[o] = r0; qh[o + 32] = r1; qh[o + 8] = r2; qh[o + 40] = r3;
-                    // the step's own key meets the same bf16 query as the cached keys
-                    qs[o] = __bfloat162float(r0); qs[o + 32] = __bfloat162float(r1); qs[o + 8] = __bfloat162float(r2); qs[o + 40] = __bfloat162float(r3);
-                  } else {             // k / v, rounded to the cache precision
-                    float* dst = pt == 1 ? knew : vnew;
-                    dst[o] = __bfloat162float(__float2bfloat16_rn(acc[nb][0] + b0));
-                    dst[o + 32] = __bfloat162float(__float2bfloat16_rn(acc[nb][1] + b0));
-                    dst[o + 8] = __bfloat162float(__float2bfloat16_rn(acc[nb][2] + b1));
-                    dst[o + 40] = __bfloat162float(__float2bfloat16_rn(acc[nb][3] + b1));
-                  }
+              for (int nb = 0; nb < NB; ++nb) {
+                const int o = (8 * nb + 2 * fq) * 32 + f;
+                if (pt == 0) {       // q, pre-scaled
+                  const float q0 = (acc[nb][0] + b0) * scale, q1 = (acc[nb][1] + b0) * scale, q2 = (acc[nb][2] + b1) * scale, q3 = (acc[nb][3] + b1) * scale;
+                  const bf16 r0 = __float2bfloat16_rn(q0), r1 = __float2bfloat16_rn(q1), r2 = __float2bfloat16_rn(q2), r3 = __float2bfloat16_rn(q3);
+                  qh[o] = r0; qh[o + 32] = r1; qh[o + 8] = r2; qh[o + 40] = r3;
+                  // the step's own key meets the same bf16 query as the cached keys
+                  qs[o] = __bfloat162float(r0); qs[o + 32] = __bfloat162float(r1); qs[o + 8] = __bfloat162float(r2); qs[o + 40] = __bfloat162float(r3);
+                } else {             // k / v, rounded to the cache precision
+                  float* dst = pt == 1 ? knew : vnew;
+                  dst[o] = __bfloat162float(__float2bfloat16_rn(acc[nb][0] + b0));
+                  dst[o + 32] = __bfloat162float(__float2bfloat16_rn(acc[nb][1] + b0));
+                  dst[o + 8] = __bfloat162float(__float2bfloat16_rn(acc[nb][2] + b1));
+                  dst[o + 40] = __bfloat162float(__float2bfloat16_rn(acc[nb][3] + b1));
                 }
-                stage_release(4);
-              } else stage_skip();
-            }
+              }
+            });
           }
           cbar();
           TRACE(t);   // 1: in-proj done
@@ -757,54 +741,33 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(NT, MINB) decode_fu
             const float4 a = *reinterpret_cast<const float4*>(src), b = *reinterpret_cast<const float4*>(src + 4);
             uint4 o; o.x = pack_bf16(a.x, a.y); o.y = pack_bf16(a.z, a.w); o.z = pack_bf16(b.x, b.y); o.w = pack_bf16(b.z, b.w);
             const int page = pages[g * 32 + t / P.PT];
-            bf16* dst = P.kv_pool + (((int64_t)page * L + l) * 2 + which) * ((int64_t)P.PT * DM) + (int64_t)(t % P.PT) * DM + rank * HD + ch * 8;
+            const int r = t % P.PT;      // pool: [page][layer][head][k|v][16 tokens][32]; chunk ch of token r at ch ^ ((r >> 1) & 3) (decode.cu kv_chunk)
+            bf16* dst = P.kv_pool + ((((int64_t)page * L + l) * CS + rank) * 2 + which) * (int64_t)(P.PT * HD) + r * HD + ((ch ^ ((r >> 1) & 3)) << 3);
             *reinterpret_cast<uint4*>(dst) = o;
           }
           TRACE(t);   // 2: append
-          // ---- self-attention, head `rank`: keys [0,t) from the paged cache.  An image's key tiles are interleaved over wpi_t warps (two
-          //      tiles per warp at most: wpi_t * 2 * 16 >= t; a function of the step only -- never of the batch).  Up to 8 pages of keys:
-          //      a 16 KB stage holds the K and V panels of 4 / wpi_t images and belongs to one half of the warps (even stages: warps
-          //      0-3, odd stages: warps 4-7 -- two stages are worked on at a time); beyond that all 8 warps share one image, its K
-          //      panel in one stage and its V panel in the next.  The step's own key (still in shared memory) is partial #8 --------
-          {
-            const int ntile = (t + 15) >> 4;
-#pragma unroll
-            for (int nb = 0; nb < NB; ++nb) {
-              const int img = warp + 8 * nb;
-              if (img < G) {
-                float s_own = warp_sum(qs[img * 32 + lane] * knew[img * 32 + lane]);
-                if ((padbits[img * 8 + (t >> 5)] >> (t & 31)) & 1u) s_own += LOG2E;
-                float* pb = part + (img * NPART + 8) * PSTR;
-                if (lane == 0) { pb[0] = s_own; pb[1] = 1.0f; }
-                pb[4 + lane] = vnew[img * 32 + lane];
-              }
-            }
-            if (!split_kv) {
-              const int wpi = wpi_t, half = warp >> 2, w4 = warp & 3, gi = w4 / wpi, tl = w4 - gi * wpi;
-              for (int sg = 0; sg < nS; ++sg) {
-                if ((sg & 1) != half) { stage_skip(); continue; }
-                const int g = sg * ips_t + gi;
-                const uint32_t st = stage_wait();
-                if (g < G) {
-                  const uint32_t kp = st + gi * 2 * self_panel;
-                  attend(kp, kp + self_panel, g, tl, tl, wpi, ntile, t, haspad[g] ? padbits + g * 8 : nullptr);
-                }
-                stage_release(2);
-              }
-            } else {
-              for (int g = 0; g < P.G; ++g) {
-                const uint32_t kp = stage_wait(), vp = stage_wait_next();
-                if (g < G) attend(kp, vp, g, warp, warp, 8, ntile, t, haspad[g] ? padbits + g * 8 : nullptr);
-                stage_release(); stage_release();
-              }
-            }
-          }
-          cbar();
+          // ---- self-attention, head `rank`: keys [0,t) from the paged cache in chunks of one page, then the step's own key (still in
+          //      shared memory) joins as one more online-softmax term ---------------------------------------------------------------
+          attention(npg, t, true, -1, t);
           TRACE(t);   // 3: self attention
 #pragma unroll
           for (int nb = 0; nb < NB; ++nb) {
             const int img = warp + 8 * nb;
-            push_o(img, img < G ? attn_merge(part + img * NPART * PSTR, ((1u << wpi_t) - 1u) | (1u << 8)) : 0.f);
+            float out = 0.f;
+            if (img < G) {
+              float s_own = warp_sum(qs[img * 32 + lane] * knew[img * 32 + lane]);
+              if ((padbits[img * 8 + (t >> 5)] >> (t & 31)) & 1u) s_own += LOG2E;
+              const float v_own = vnew[img * 32 + lane];
+              if (npg == 0) out = v_own;                     // t = 0: the own key is the only key
+              else {
+                const float* ob = ost + img * OSTR;
+                const float m_run = ob[32], l_run = ob[33];
+                const float mf = fmaxf(m_run, s_own);
+                const float wr = exp2f(m_run - mf), wo = exp2f(s_own - mf);
+                out = fmaf(ob[lane], wr, v_own * wo) / fmaf(l_run, wr, wo);
+              }
+            }
+            push_o(img, out);
           }
           wait_o();
           TRACE(t);   // 4: o gathered
@@ -819,41 +782,29 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(NT, MINB) decode_fu
             const float* bc = P.b_ca[l];
             float b0 = 0.f, b1 = 0.f;
             if (warp < 2) { b0 = __ldg(bc + rank * 32 + warp * 16 + fg); b1 = __ldg(bc + rank * 32 + warp * 16 + fg + 8); }
-            if (warp < 2) {
-              const uint32_t st = stage_wait();
+            proj_blocks(1, [&](int, uint32_t blk, int mt) {
               float acc[NB][4];
-              mma_mtile<32, NB>(st, warp * 16, sbase + Y::OFF_XH, acc);
-              const int f = warp * 16 + fg;
+              mma_mtile<32, NB>(blk, mt * 16, sbase + Y::OFF_XH, acc);
+              const int f = mt * 16 + fg;
 #pragma unroll
               for (int nb = 0; nb < NB; ++nb) {
                 bf16* q = qh + (8 * nb + 2 * fq) * 32 + f;
                 q[0] = __float2bfloat16_rn((acc[nb][0] + b0) * scale); q[32] = __float2bfloat16_rn((acc[nb][1] + b0) * scale);
                 q[8] = __float2bfloat16_rn((acc[nb][2] + b1) * scale); q[40] = __float2bfloat16_rn((acc[nb][3] + b1) * scale);
               }
-              stage_release(4);
-            } else stage_skip();
+            });
           }
           cbar();
           TRACE(t);   // 7: cross q
-          // ---- cross-attention over the S memory keys: per image its K panel in one stage and its V panel in the next, key tiles
-          //      interleaved over the 8 warps ------------------------------------------------------------------------------------
-          {
-            const int ntile = (S + 15) >> 4;
-            for (int g = 0; g < nC; ++g) {
-              if (warp == 0) FINE(l, t, 20 + g * 3);
-              const uint32_t kp = stage_wait(), vp = stage_wait_next();
-              if (warp == 0) FINE(l, t, 21 + g * 3);
-              if (g < G) attend(kp, vp, g, warp, warp, 8, ntile, S, nullptr);
-              stage_release(); stage_release();
-              if (warp == 0) FINE(l, t, 22 + g * 3);
-            }
-          }
-          cbar();
-          TRACE(t);   // 8: cross attention partials
+          // ---- cross-attention over the S memory keys (HBM/L2-resident cross-K/V), 16-key chunks ------------------------------
+          attention(nck, S, false, l, t);
+          TRACE(t);   // 8: cross attention
 #pragma unroll
           for (int nb = 0; nb < NB; ++nb) {
             const int img = warp + 8 * nb;
-            push_o(img, img < G ? attn_merge(part + img * NPART * PSTR, 0xffu) : 0.f);
+            float out = 0.f;
+            if (img < G) { const float* ob = ost + img * OSTR; out = ob[lane] / ob[33]; }
+            push_o(img, out);
           }
           wait_o();
           TRACE(t);   // 9: o gathered
@@ -862,54 +813,41 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(NT, MINB) decode_fu
           layer_norm(P.ln2w[l], P.ln2b[l]);
           TRACE(t);   // 11: LN2
 
-          // ---- FFN1: own 256 hidden units in 8 stages of 32 rows (stage s -> warps 2(s%4), 2(s%4)+1: four stages are worked on at a
-          //      time), ReLU, kept local as the FFN2 operand -------------------------------------------------------------------
-          for (int s8 = 0; s8 < 8; ++s8) {
-            const bool mine = (warp >> 1) == (s8 & 3);
-            const int mt = warp & 1;
-            if (mine) {
-              const int h0 = rank * FS + s8 * 32 + mt * 16 + fg;
-              const float b0 = __ldg(P.b_f1[l] + h0), b1 = __ldg(P.b_f1[l] + h0 + 8);
-              if (warp == 0) FINE(l, t, (s8 >> 2) * 4 + 0);
-              const uint32_t st = stage_wait();
-              if (warp == 0) FINE(l, t, (s8 >> 2) * 4 + 1);
+          // ---- FFN1: own 256 hidden units as 8 blocks of 32 rows (block b -> warp pair b % 4), ReLU, kept local as the FFN2 operand ----
+          {
+            const float* bf = P.b_f1[l] + rank * FS + (warp & 1) * 16 + fg;
+            const int pr = warp >> 1;
+            const float ba0 = __ldg(bf + pr * 32), ba1 = __ldg(bf + pr * 32 + 8), bb0 = __ldg(bf + (pr + 4) * 32), bb1 = __ldg(bf + (pr + 4) * 32 + 8);
+            proj_blocks(8, [&](int b, uint32_t blk, int mt) {
+              const float b0 = b < 4 ? ba0 : bb0, b1 = b < 4 ? ba1 : bb1;
               float acc[NB][4];
-              mma_mtile<32, NB>(st, mt * 16, sbase + Y::OFF_XH, acc);
-              if (warp == 0) FINE(l, t, (s8 >> 2) * 4 + 2);
-              const int h = s8 * 32 + mt * 16 + fg;
+              mma_mtile<32, NB>(blk, mt * 16, sbase + Y::OFF_XH, acc);
+              const int h = b * 32 + mt * 16 + fg;
 #pragma unroll
               for (int nb = 0; nb < NB; ++nb) {
                 const int r = 8 * nb + 2 * fq;
                 store_h(fh, r * XP + h, fmaxf(acc[nb][0] + b0, 0.f)); store_h(fh, (r + 1) * XP + h, fmaxf(acc[nb][1] + b0, 0.f));
                 store_h(fh, r * XP + h + 8, fmaxf(acc[nb][2] + b1, 0.f)); store_h(fh, (r + 1) * XP + h + 8, fmaxf(acc[nb][3] + b1, 0.f));
               }
-              stage_release(4);
-              if (warp == 0) FINE(l, t, (s8 >> 2) * 4 + 3);
-            } else stage_skip();
+            });
           }
           cbar();
           TRACE(t);   // 12: FFN1
-          // ---- FFN2 as a K-split, 32 output features per stage: partial sums pushed straight to the CTA that owns the columns ----
-          for (int s8 = 0; s8 < 8; ++s8) {
-            const bool mine = (warp >> 1) == (s8 & 3);
-            const int mt = warp & 1;
-            if (mine) {
-              const uint32_t st = stage_wait();
-              float acc[NB][4];
-              mma_mtile<32, NB>(st, mt * 16, sbase + Y::OFF_FH, acc);
-              const int feat = s8 * 32 + mt * 16 + fg;                 // output feature of acc[.][0..1]; +8 for acc[.][2..3]
-              const uint32_t peer = (uint32_t)s8;                       // stage s8 = the 32-column slice of CTA s8
-              const uint32_t rb = mapa(bar(BAR_F2), peer);
-              const uint32_t base = mapa(sbase + Y::OFF_F2RECV + (rank * GMX * 32 + (feat & 31)) * 4, peer);
+          // ---- FFN2 as a K-split, 32 output features per block: partial sums pushed straight to the CTA that owns the columns ----
+          proj_blocks(8, [&](int b, uint32_t blk, int mt) {
+            float acc[NB][4];
+            mma_mtile<32, NB>(blk, mt * 16, sbase + Y::OFF_FH, acc);
+            const int f = mt * 16 + fg;                                // feature within the block of acc[.][0..1]; +8 for acc[.][2..3]
+            const uint32_t peer = (uint32_t)b;                         // block b = the 32-column slice of CTA b
+            const uint32_t rb = mapa(bar(BAR_F2), peer);
+            const uint32_t base = mapa(sbase + Y::OFF_F2RECV + (rank * GMX * 32 + f) * 4, peer);
 #pragma unroll
-              for (int nb = 0; nb < NB; ++nb) {
-                const int i0 = 8 * nb + 2 * fq;
-                if (i0 < G) { st_async_b32(base + i0 * 128, __float_as_uint(acc[nb][0]), rb); st_async_b32(base + i0 * 128 + 32, __float_as_uint(acc[nb][2]), rb); }
-                if (i0 + 1 < G) { st_async_b32(base + (i0 + 1) * 128, __float_as_uint(acc[nb][1]), rb); st_async_b32(base + (i0 + 1) * 128 + 32, __float_as_uint(acc[nb][3]), rb); }
-              }
-              stage_release(4);
-            } else stage_skip();
-          }
+            for (int nb = 0; nb < NB; ++nb) {
+              const int i0 = 8 * nb + 2 * fq;
+              if (i0 < G) { st_async_b32(base + i0 * 128, __float_as_uint(acc[nb][0]), rb); st_async_b32(base + i0 * 128 + 32, __float_as_uint(acc[nb][2]), rb); }
+              if (i0 + 1 < G) { st_async_b32(base + (i0 + 1) * 128, __float_as_uint(acc[nb][1]), rb); st_async_b32(base + (i0 + 1) * 128 + 32, __float_as_uint(acc[nb][3]), rb); }
+            }
+          });
           TRACE(t);   // 13: FFN2 issued
           {  // reduce the 8 partial slices of the own 32 columns, add bias, all-gather, LN3
             const float b2 = __ldg(P.b_f2[l] + rank * 32 + c_t);
@@ -941,8 +879,8 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(NT, MINB) decode_fu
           const bool va = warp < 3 && row_a < VSL && r0 + row_a < P.vocab, vb = warp < 3 && row_b < VSL && r0 + row_b < P.vocab;
           if (va) b0 = __ldg(P.b_out + r0 + row_a);
           if (vb) b1 = __ldg(P.b_out + r0 + row_b);
-          // rows [0,32) of the own 40 sit in one stage (warps 0-1), rows [32,40) in the next (warp 2: an 8-row block, the upper half
-          // of its 16-row MMA tile reads the neighbouring k-block -- finite weights feeding accumulator rows that are never used)
+          // rows [0,32) of the own 40 are one block (warps 0-1), rows [32,40) an 8-row block (warp 2: the upper half of its 16-row
+          // MMA tile reads the neighbouring k-block -- finite weights feeding accumulator rows that are never used)
           auto head_out = [&](float (&acc)[NB][4]) {
 #pragma unroll
             for (int nb = 0; nb < NB; ++nb)
@@ -959,20 +897,31 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(NT, MINB) decode_fu
                 }
               }
           };
-          if (warp < 2) {
-            const uint32_t st = stage_wait();
-            float acc[NB][4];
-            mma_mtile<32, NB>(st, warp * 16, sbase + Y::OFF_XH, acc);
-            head_out(acc);
-            stage_release(4);
-          } else stage_skip();
-          if (warp == 2) {
-            const uint32_t st = stage_wait();
-            float acc[NB][4];
-            mma_mtile<8, NB>(st, 0, sbase + Y::OFF_XH, acc);
-            head_out(acc);
-            stage_release(8);
-          } else stage_skip();
+          if (NB == 2) {            // both blocks in one stage: users warps 0, 1 (weight 3 each) and 2 (weight 2)
+            if (warp < 3) {
+              const uint32_t st = stage_wait();
+              float acc[NB][4];
+              if (warp < 2) mma_mtile<32, NB>(st, warp * 16, sbase + Y::OFF_XH, acc);
+              else mma_mtile<8, NB>(st + BLK_BYTES, 0, sbase + Y::OFF_XH, acc);
+              head_out(acc);
+              stage_release(warp < 2 ? 3 : 2);
+            } else stage_skip();
+          } else {
+            if (warp < 2) {
+              const uint32_t st = stage_wait();
+              float acc[NB][4];
+              mma_mtile<32, NB>(st, warp * 16, sbase + Y::OFF_XH, acc);
+              head_out(acc);
+              stage_release(4);
+            } else stage_skip();
+            if (warp == 2) {
+              const uint32_t st = stage_wait();
+              float acc[NB][4];
+              mma_mtile<8, NB>(st, 0, sbase + Y::OFF_XH, acc);
+              head_out(acc);
+              stage_release(8);
+            } else stage_skip();
+          }
         }
         cbar();       // the next step's embedding overwrites the operand rows the head MMAs of warps 0-2 are reading (in teacher-forced
                       // mode nothing else orders the two: no select, no token exchange)
@@ -1030,28 +979,86 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(NT, MINB) decode_fu
   cluster_sync_all();
 }
 
-// ---- host side: cached weight tensor maps ---------------------------------------------------------------------
+// ---- pack kernels: global-memory images of what the kernel wants in shared memory -----------------------------------
+// Weight block (R rows x 256 k, fp16): [4 k-blocks][R rows][128 B], the 16-byte chunk c of row i stored at chunk c ^ (i & 7)
+// (the layout a SWIZZLE_128B tensor-map load would produce, which mma_mtile's ldmatrix addressing expects).
+struct PackArgs {
+  const __half* w[8][6];     // per layer: self in-proj [3*DM][DM], self out [DM][DM], cross in-proj [3*DM][DM] (rows [0,DM) = q), cross out, FFN1 [FFN][DM], FFN2 [DM][FFN]
+  const __half* head;        // [vocab][DM]
+  int layers, vocab;
+};
+
+__global__ void pack_weights_kernel(PackArgs a, uint4* __restrict__ out, size_t n_chunks) {
+  const size_t layer_bytes = (size_t)a.layers * CS * BLOCKS_PER_LAYER * BLK_BYTES;
+  for (size_t id = (size_t)blockIdx.x * blockDim.x + threadIdx.x; id < n_chunks; id += (size_t)gridDim.x * blockDim.x) {
+    const size_t off = id * 16;
+    const __half* src = nullptr;
+    if (off < layer_bytes) {
+      const int blk = (int)(off / BLK_BYTES), within = (int)(off % BLK_BYTES);
+      const int l = blk / (CS * BLOCKS_PER_LAYER), r = (blk / BLOCKS_PER_LAYER) % CS, b = blk % BLOCKS_PER_LAYER;
+      const int kb = within / 4096, i = (within % 4096) / 128, pc = (within % 128) / 16;
+      const int k0 = kb * 64 + ((pc ^ (i & 7)) << 3);
+      if (b < 3) src = a.w[l][0] + (size_t)(b * DM + r * HD + i) * DM + k0;
+      else if (b == 3) src = a.w[l][1] + (size_t)(r * 32 + i) * DM + k0;
+      else if (b == 4) src = a.w[l][2] + (size_t)(r * 32 + i) * DM + k0;
+      else if (b == 5) src = a.w[l][3] + (size_t)(r * 32 + i) * DM + k0;
+      else if (b < 14) src = a.w[l][4] + (size_t)(r * FS + (b - 6) * 32 + i) * DM + k0;
+      else src = a.w[l][5] + (size_t)((b - 14) * 32 + i) * FFN + r * FS + k0;
+    } else {
+      const size_t hoff = off - layer_bytes;
+      const int r = (int)(hoff / HEAD_PACK_BYTES), within = (int)(hoff % HEAD_PACK_BYTES);
+      int kb, i, row;
+      if (within < BLK_BYTES) { kb = within / 4096; i = (within % 4096) / 128; row = r * VSL + i; }
+      else { const int w2 = within - BLK_BYTES; kb = w2 / 1024; i = (w2 % 1024) / 128; row = r * VSL + 32 + i; }
+      const int pc = (within % 128) / 16;
+      const int k0 = kb * 64 + ((pc ^ (i & 7)) << 3);
+      if (row < a.vocab) src = a.head + (size_t)row * DM + k0;
+    }
+    out[id] = src ? *reinterpret_cast<const uint4*>(src) : make_uint4(0u, 0u, 0u, 0u);
+  }
+}
+
+// cross-K/V [layer][B*S][K(DM) | V(DM)] -> [layer][image][head][16-key chunk][k|v][16 keys][32 channels], 16-byte chunk c of key r
+// at chunk c ^ ((r >> 1) & 3); keys >= S are zero rows (masked by the kernel)
+__global__ void pack_cross_kv_kernel(const uint4* __restrict__ ckv, uint4* __restrict__ out, int B, int S, int nck, size_t n_chunks) {
+  for (size_t id = (size_t)blockIdx.x * blockDim.x + threadIdx.x; id < n_chunks; id += (size_t)gridDim.x * blockDim.x) {
+    const size_t cell = id / 128; const int within = (int)(id % 128);        // 128 chunks of 16 bytes per 2 KB cell
+    const int c = (int)(cell % nck), h = (int)((cell / nck) % CS); const size_t lb = cell / ((size_t)nck * CS);     // lb = layer * B + image
+    const int which = within / 64, r = (within % 64) / 4, pc = within % 4;
+    const int key = c * 16 + r;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (key < S) v = ckv[((lb * S + key) * (2 * DM) + which * DM + h * HD) / 8 + (pc ^ ((r >> 1) & 3))];
+    out[id] = v;
+  }
+}
+
 struct FusedCache {
-  const void* key[8 * 6 + 1];
   FusedParams P;
   bool valid;
 };
 
+bool geometry_ok(const mdc_dims& d) {
+  if (d.precision != MDC_BF16 || d.dec_loop_dtype != MDC_F16 || d.dim != DM || d.dec_heads != CS || d.dec_ffn != FFN) return false;
+  if (d.dec_layers < 1 || d.dec_layers > 8 || d.vocab > CS * VSL || d.vocab < 8) return false;
+  if (d.n_patches < 1 || d.page_tokens != 16) return false;
+  return true;
+}
+
 // ---- kernel variants --------------------------------------------------------------------------------------------------
 // 0: NB = 1, 10-stage ring (160 KB), one CTA per SM   (<= 8 images per cluster; lowest latency of one batch)
-// 1: NB = 2, 8-stage ring (128 KB), one CTA per SM    (<= 16 images per cluster)
+// 1: NB = 2, 4-stage ring of 32 KB stages (128 KB), one CTA per SM    (<= 16 images per cluster)
 // 2: NB = 1, 4-stage ring (64 KB), compact layout, two CTAs per SM (<= 8 images per cluster; two clusters interleave on the same SMs)
 constexpr int N_VARIANTS = 3;
 template <bool kTrace> struct Variants {
   static const void* fn(int v) {
     switch (v) {
       case 0: return (const void*)decode_fused_kernel<kTrace, 1, 10, 1>;
-      case 1: return (const void*)decode_fused_kernel<kTrace, 2, 8, 1>;
+      case 1: return (const void*)decode_fused_kernel<kTrace, 2, 4, 1>;
       default: return (const void*)decode_fused_kernel<kTrace, 1, 4, 2>;
     }
   }
 };
-int variant_smem(int v) { return v == 0 ? Lay<1, 10, false>::SMEM_BYTES : (v == 1 ? Lay<2, 8, true>::SMEM_BYTES : Lay<1, 4, true>::SMEM_BYTES); }
+int variant_smem(int v) { return v == 0 ? Lay<1, 10, false>::SMEM_BYTES : (v == 1 ? Lay<2, 4, true>::SMEM_BYTES : Lay<1, 4, true>::SMEM_BYTES); }
 
 // per-context (= per-device) launch state: the dynamic-smem opt-in and the occupancy query are device properties
 struct ClusterCtxState { int max_clusters[N_VARIANTS]; };
@@ -1059,13 +1066,49 @@ struct ClusterCtxState { int max_clusters[N_VARIANTS]; };
 }  // namespace
 
 int decode_cluster_supported(const mdc_model* m, const mdc_decode_state* st, int t_end) {
-  const mdc_dims& d = m->d;
-  if (d.precision != MDC_BF16 || d.dec_loop_dtype != MDC_F16 || d.dim != DM || d.dec_heads != CS || d.dec_ffn != FFN) return 0;
-  if (d.dec_layers < 1 || d.dec_layers > 8 || d.vocab > CS * VSL || d.vocab < 8) return 0;
+  if (!geometry_ok(m->d) || !m->dec_pack) return 0;                // the packed weights are attached by mdc_decode_pack
   if (st->x_override || st->pos_override || st->per_op_kernels) return 0;
-  if (d.n_patches > 256 || d.n_patches < 8) return 0;             // one TMA box (<= 256 rows) per image panel, 2 panels per stage
-  if (t_end > 256 || st->pages_per_seq > 32 || d.page_tokens != 16 || st->n_pages < 1) return 0;
+  if (t_end > 256 || st->pages_per_seq > 32 || st->n_pages < 1) return 0;
   return 1;
+}
+
+size_t decode_cluster_pack_bytes(const mdc_model* m) {
+  if (!geometry_ok(m->d)) return 0;
+  return (size_t)m->d.dec_layers * CS * BLOCKS_PER_LAYER * BLK_BYTES + (size_t)CS * HEAD_PACK_BYTES;
+}
+
+int decode_cluster_pack(mdc_model* m, void* out, cudaStream_t s) {
+  const mdc_dims& d = m->d;
+  const void** gw = m->w + MDC_ENC_GLOBAL_SLOTS + d.enc_depth * MDC_ENC_BLOCK_SLOTS;
+  const void** lw0 = gw + MDC_DEC_GLOBAL_SLOTS;
+  PackArgs a; memset(&a, 0, sizeof(a));
+  for (int l = 0; l < d.dec_layers; ++l) {
+    const void** lw = lw0 + l * MDC_DEC_LAYER_SLOTS;
+    a.w[l][0] = (const __half*)lw[MDC_SA_IN_W]; a.w[l][1] = (const __half*)lw[MDC_SA_OUT_W]; a.w[l][2] = (const __half*)lw[MDC_CA_IN_W];
+    a.w[l][3] = (const __half*)lw[MDC_CA_OUT_W]; a.w[l][4] = (const __half*)lw[MDC_FF1_W]; a.w[l][5] = (const __half*)lw[MDC_FF2_W];
+  }
+  a.head = (const __half*)gw[MDC_OUT_W]; a.layers = d.dec_layers; a.vocab = d.vocab;
+  const size_t n = decode_cluster_pack_bytes(m) / 16;
+  pack_weights_kernel<<<m->ctx->sm_count * 4, 256, 0, s>>>(a, (uint4*)out, n);
+  MDC_LAUNCH_CHECK(m->ctx);
+  m->dec_pack = out;
+  if (m->fused_cache) ((FusedCache*)m->fused_cache)->valid = false;
+  return 0;
+}
+
+// packed cross-K/V behind the plain [layer][B*S][2*DM] tensor in the caller's cross_kv buffer (mdc_cross_kv_bytes covers both)
+size_t decode_cluster_ckv_pack_bytes(const mdc_model* m, int B) {
+  if (!geometry_ok(m->d)) return 0;
+  const int nck = (m->d.n_patches + 15) / 16;
+  return (size_t)m->d.dec_layers * B * CS * nck * 2048;
+}
+
+int decode_cluster_ckv_pack(mdc_model* m, const void* ckv_plain, int B, void* out, cudaStream_t s) {
+  const int S = m->d.n_patches, nck = (S + 15) / 16;
+  const size_t n = decode_cluster_ckv_pack_bytes(m, B) / 16;
+  pack_cross_kv_kernel<<<m->ctx->sm_count * 8, 256, 0, s>>>((const uint4*)ckv_plain, (uint4*)out, B, S, nck, n);
+  MDC_LAUNCH_CHECK(m->ctx);
+  return 0;
 }
 
 size_t decode_cluster_scratch_bytes(const mdc_model*, int) { return 0; }
@@ -1088,12 +1131,6 @@ int decode_cluster_launch(mdc_model* m, const mdc_decode_state* st, int t_begin,
     FusedParams& P = fc->P;
     for (int l = 0; l < d.dec_layers; ++l) {
       const void** lw = lw0 + l * MDC_DEC_LAYER_SLOTS;
-      MDC_TRY(mdc_make_tmap_2d(ctx, lw[MDC_SA_IN_W], 3 * DM, DM, DM, 64, 32, 3, &P.m_in[l]));
-      MDC_TRY(mdc_make_tmap_2d(ctx, lw[MDC_SA_OUT_W], DM, DM, DM, 64, 32, 3, &P.m_so[l]));
-      MDC_TRY(mdc_make_tmap_2d(ctx, lw[MDC_CA_IN_W], 3 * DM, DM, DM, 64, 32, 3, &P.m_ca[l]));
-      MDC_TRY(mdc_make_tmap_2d(ctx, lw[MDC_CA_OUT_W], DM, DM, DM, 64, 32, 3, &P.m_co[l]));
-      MDC_TRY(mdc_make_tmap_2d(ctx, lw[MDC_FF1_W], FFN, DM, DM, 64, 32, 3, &P.m_f1[l]));
-      MDC_TRY(mdc_make_tmap_2d(ctx, lw[MDC_FF2_W], DM, FFN, FFN, 64, 32, 3, &P.m_f2[l]));
       P.b_in[l] = (const float*)lw[MDC_SA_IN_B]; P.b_so[l] = (const float*)lw[MDC_SA_OUT_B];
       P.ln1w[l] = (const float*)lw[MDC_LN1_W]; P.ln1b[l] = (const float*)lw[MDC_LN1_B];
       P.b_ca[l] = (const float*)lw[MDC_CA_IN_B]; P.b_co[l] = (const float*)lw[MDC_CA_OUT_B];
@@ -1101,8 +1138,7 @@ int decode_cluster_launch(mdc_model* m, const mdc_decode_state* st, int t_begin,
       P.b_f1[l] = (const float*)lw[MDC_FF1_B]; P.b_f2[l] = (const float*)lw[MDC_FF2_B];
       P.ln3w[l] = (const float*)lw[MDC_LN3_W]; P.ln3b[l] = (const float*)lw[MDC_LN3_B];
     }
-    MDC_TRY(mdc_make_tmap_2d(ctx, gw[MDC_OUT_W], d.vocab, DM, DM, 64, 32, 3, &P.m_head));
-    MDC_TRY(mdc_make_tmap_2d(ctx, gw[MDC_OUT_W], d.vocab, DM, DM, 64, 8, 3, &P.m_head8));
+    P.wpack = (const uint8_t*)m->dec_pack;
     P.emb = (const float*)gw[MDC_EMB]; P.pos = (const float*)gw[MDC_DEC_POS]; P.b_out = (const float*)gw[MDC_OUT_B];
     P.layers = d.dec_layers; P.vocab = d.vocab; P.S = d.n_patches; P.pad_idx = d.pad_idx; P.PT = d.page_tokens;
     fc->valid = true;
@@ -1122,9 +1158,7 @@ int decode_cluster_launch(mdc_model* m, const mdc_decode_state* st, int t_begin,
   if (const char* e = getenv("MDC_DECODE_IPC")) ipc = atoi(e);
   if (const char* e = getenv("MDC_DECODE_CPS")) cps = atoi(e);
 #endif
-  // cross-K/V [layers*B*S rows][2*DM]: one (S rows x 32 channels) box per (image, head, k|v); paged pool: one page x head box
-  MDC_TRY(mdc_make_tmap_2d(ctx, st->cross_kv, (int64_t)d.dec_layers * st->B * d.n_patches, 2 * DM, 2 * DM, HD, d.n_patches, 2, &P.m_ckv));
-  MDC_TRY(mdc_make_tmap_2d(ctx, st->kv_pool, (int64_t)st->n_pages * d.dec_layers * 2 * d.page_tokens, DM, DM, HD, d.page_tokens, 2, &P.m_pool));
+  P.ckv_pack = (const uint8_t*)st->cross_kv + align_up((size_t)d.dec_layers * st->B * d.n_patches * 2 * DM * 2, 256);
   // variant: more than 8 images per cluster -> the two-column-block instantiation; otherwise ctas_per_sm == 2 -> the compact one
   const int variant = ipc > 8 ? 1 : (cps == 2 ? 2 : 0);
   const int gmx = variant == 1 ? 16 : 8;

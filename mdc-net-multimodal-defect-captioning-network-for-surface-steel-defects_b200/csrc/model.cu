@@ -77,9 +77,16 @@ extern "C" int mdc_memory_from_encoder_out(mdc_model* m, const float* enc_out, i
   return k_add_pos(m->ctx, d.precision, enc_out, (const float*)dg[MDC_ENC_POS], memory, per * B, per, (cudaStream_t)stream);
 }
 
+// cross_kv buffer: the plain tensor [layer][B*S][K(dim) | V(dim)] (what the per-operation decode kernels read), followed -- when the
+// fused decode kernel covers the geometry -- by the same values re-arranged per (layer, image, head, 16-key chunk) into 2 KB cells
+// that the fused kernel fetches with one bulk copy each (decode_cluster.cu).
+static size_t ckv_plain_bytes(const mdc_model* m, int B) {
+  return align_up((size_t)m->d.dec_layers * B * m->d.n_patches * 2 * m->d.dim * esize(m->d.precision), 256);
+}
+
 extern "C" size_t mdc_cross_kv_bytes(const mdc_model* m, int B) {
   if (!m || B <= 0) return 0;
-  return (size_t)m->d.dec_layers * B * m->d.n_patches * 2 * m->d.dim * esize(m->d.precision);
+  return ckv_plain_bytes(m, B) + decode_cluster_ckv_pack_bytes(m, B);
 }
 
 extern "C" int mdc_cross_kv_build(mdc_model* m, const void* memory, int B, void* cross_kv, void* stream) {
@@ -95,7 +102,18 @@ extern "C" int mdc_cross_kv_build(mdc_model* m, const void* memory, int B, void*
     char* out = (char*)cross_kv + (size_t)l * B * S * 2 * dim * es;
     MDC_TRY(mdc_gemm(m->ctx, d.precision, MDC_EPI_BIAS, memory, dim, Wkv, dim, out, 2 * dim, bkv, nullptr, 0, B * S, 2 * dim, dim, stream));
   }
+  if (decode_cluster_ckv_pack_bytes(m, B))
+    MDC_TRY(decode_cluster_ckv_pack(m, cross_kv, B, (char*)cross_kv + ckv_plain_bytes(m, B), (cudaStream_t)stream));
   return 0;
+}
+
+// decode-loop weights pre-arranged for the fused decode kernel (decode_cluster.cu): 0 bytes when it does not cover the geometry
+extern "C" size_t mdc_decode_pack_bytes(const mdc_model* m) { return m ? decode_cluster_pack_bytes(m) : 0; }
+
+extern "C" int mdc_decode_pack(mdc_model* m, void* packed, void* stream) {
+  MDC_CHECK_ARG(m && packed && decode_cluster_pack_bytes(m) > 0);
+  MDC_CHECK_DEVICE(m->ctx);
+  return decode_cluster_pack(m, packed, (cudaStream_t)stream);
 }
 
 // AxialAttention.forward (axial_model.py:28-40): qkv = x . Wqkv^T (no bias) -> strip attention with

@@ -1,8 +1,8 @@
 """Paged KV cache for decoder self-attention (north_star (c)); host-side page bookkeeping.
 
-Pool layout (device, `dtype`): [n_pages][dec_layers][k|v][page_tokens][dim] -- one page holds
-`page_tokens` consecutive positions of ONE image for ALL layers, so a single page table serves
-every layer.  The page table is int32 [B, pages_per_seq] of physical page ids.  Pages are handed
+Pool layout (device, `dtype`): [n_pages][dec_layers][heads][k|v][page_tokens][head_dim] (opaque to
+the host: include/mdc_b200.h) -- one page holds `page_tokens` consecutive positions of ONE image
+for ALL layers, so a single page table serves every layer.  The page table is int32 [B, pages_per_seq] of physical page ids.  Pages are handed
 out from a free list; `interleave=True` deals them round-robin across sequences so that a
 sequence's pages are deliberately NOT contiguous (exercises the indirection).
 """

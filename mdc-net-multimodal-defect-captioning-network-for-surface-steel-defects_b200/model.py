@@ -244,6 +244,13 @@ class Engine:
         h = C.c_void_p()
         L.check(self.lib.mdc_model_create(self.ctx, C.byref(d), arr, n, C.byref(h)))
         self.handle = h
+        # decode-loop weights pre-arranged for the fused decode kernel (one bulk copy per pipeline stage); 0 bytes = other geometry
+        nb = self.lib.mdc_decode_pack_bytes(h)
+        self.dec_pack = None
+        if nb:
+            self.dec_pack = torch.empty(nb, dtype=torch.uint8, device=self.device)
+            with torch.cuda.device(self.device):
+                L.check(self.lib.mdc_decode_pack(h, L.ptr(self.dec_pack), L.stream_ptr(self.device)))
 
     def __del__(self):
         try:

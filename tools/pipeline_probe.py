@@ -15,9 +15,10 @@ a.record()
 outs = [m.generate_tokens(xs[i % 4], T)[0] for i in range(K)]
 b.record(); torch.cuda.synchronize()
 print(f"serial                                  : {B * K / (a.elapsed_time(b) / 1e3):9.1f} img/s  ({a.elapsed_time(b) / K:.3f} ms/batch)")
-cfgs = [tuple(int(v) for v in c.split(',')) for c in sys.argv[2:]] or [(8, 3, 4), (16, 4, 6), (16, 5, 8), (16, 6, 8), (16, 3, 6)]
-for ipc, ndec, depth in cfgs:
-    plans = [GenerationPlan(eng, B, T, 0, 1.0, False, False, True, split=True, images_per_cluster=ipc) for _ in range(depth)]
+cfgs = [tuple(int(v) for v in c.split(',')) for c in sys.argv[2:]] or [(16, 4, 6, 0), (8, 4, 6, 2), (8, 5, 8, 2), (8, 6, 8, 2)]
+for cfg in cfgs:
+    ipc, ndec, depth = cfg[:3]; cps = cfg[3] if len(cfg) > 3 else 0
+    plans = [GenerationPlan(eng, B, T, 0, 1.0, False, False, True, split=True, images_per_cluster=ipc, ctas_per_sm=cps) for _ in range(depth)]
     s_enc = torch.cuda.Stream(priority=0)
     s_decs = [torch.cuda.Stream(priority=-1) for _ in range(ndec)]
     def run(K):
@@ -46,5 +47,5 @@ for ipc, ndec, depth in cfgs:
     cur.wait_stream(s_enc)
     b.record(); torch.cuda.synchronize()
     ok = all(torch.equal(r, o) for r, o in zip(res, outs))
-    print(f"images/cluster {ipc} decode streams {ndec} depth {depth}: {B * K / (a.elapsed_time(b) / 1e3):9.1f} img/s  ({a.elapsed_time(b) / K:.3f} ms/batch)  equal: {ok}")
+    print(f"images/cluster {ipc} ctas/SM {cps} decode streams {ndec} depth {depth}: {B * K / (a.elapsed_time(b) / 1e3):9.1f} img/s  ({a.elapsed_time(b) / K:.3f} ms/batch)  equal: {ok}")
     del plans
