@@ -97,9 +97,16 @@ int mdc_strip_attention(mdc_ctx* ctx, int dtype, const void* qkv, int64_t ld_qkv
 int mdc_layernorm(mdc_ctx* ctx, const float* x, int64_t ldx, const float* w, const float* b, float eps,
                   void* out, int64_t ldo, int out_dtype, int rows, int cols, void* stream);
 
-/* u8 grayscale (B,h,w) -> 3 equal channels -> bilinear (half-pixel) resize -> /255 -> ImageNet
- * normalise -> f32 NCHW (B,3,size,size).  inference_p.py:148-158 / dataset.py:109-113 semantics. */
+/* The reference's image transform (inference_p.py:148-158 VOCDatasetTest, dataset.py:109-113) as one kernel:
+ *   cv2.imread(...)[..., ::-1] -> A.Resize(size, size) -> A.Normalize() -> FloatTensor.permute(2, 0, 1)
+ * A.Resize on a uint8 image is cv2.resize(INTER_LINEAR): fixed-point bilinear interpolation whose result is ROUNDED TO uint8
+ * before A.Normalize turns it into float32 -- reproduced bit for bit (pinned against cv2 outputs); A.Normalize is
+ * (v - mean*255) * (1/(std*255)) in float32 with the ImageNet mean / std.
+ *   mdc_preprocess_gray: u8 (B,h,w) single-channel images (cv2.imread of a gray file yields three equal channels)
+ *   mdc_preprocess_bgr : u8 (B,h,w,3) interleaved B,G,R as cv2.imread returns them; output channel order R,G,B
+ * out: f32 NCHW (B,3,size,size). */
 int mdc_preprocess_gray(mdc_ctx* ctx, const uint8_t* gray, int B, int h, int w, float* out, int size, void* stream);
+int mdc_preprocess_bgr(mdc_ctx* ctx, const uint8_t* bgr, int B, int h, int w, float* out, int size, void* stream);
 
 /* F.interpolate(mode='linear', align_corners=False) of a (n_in, dim) table to (n_out, dim): model.py:64-68 */
 int mdc_interp_rows(mdc_ctx* ctx, const float* in, int n_in, float* out, int n_out, int dim, void* stream);

@@ -76,6 +76,7 @@ SIGNATURES = {
     "mdc_strip_attention": (_I, [_P, _I, _P, _L, _P, _L, _I, _I, _I, _I, _F, _I, _P]),
     "mdc_layernorm": (_I, [_P, _P, _L, _P, _P, _F, _P, _L, _I, _I, _I, _P]),
     "mdc_preprocess_gray": (_I, [_P, _P, _I, _I, _I, _P, _I, _P]),
+    "mdc_preprocess_bgr": (_I, [_P, _P, _I, _I, _I, _P, _I, _P]),
     "mdc_interp_rows": (_I, [_P, _P, _I, _P, _I, _I, _P]),
     "mdc_model_create": (_I, [_P, C.POINTER(Dims), C.POINTER(_P), _I, C.POINTER(_P)]),
     "mdc_model_destroy": (_I, [_P]),

@@ -143,23 +143,58 @@ __global__ void add_pos_kernel(const float* __restrict__ enc_out, const float* _
     mem[i] = from_f<TO>(enc_out[i] + pos[i % per_img]);
 }
 
-// ---- u8 gray -> normalised 3-channel f32 at model size (bilinear, half-pixel centres)
-__global__ void preprocess_gray_kernel(const uint8_t* __restrict__ g, int B, int h, int w, float* __restrict__ out, int size) {
-  const float sy = (float)h / (float)size, sx = (float)w / (float)size;
-  int64_t total = (int64_t)B * size * size;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    int x = (int)(i % size), y = (int)((i / size) % size), b = (int)(i / ((int64_t)size * size));
-    float fy = fmaxf(sy * ((float)y + 0.5f) - 0.5f, 0.f), fx = fmaxf(sx * ((float)x + 0.5f) - 0.5f, 0.f);
-    int y0 = (int)fy, x0 = (int)fx;
-    int y1 = y0 + (y0 < h - 1 ? 1 : 0), x1 = x0 + (x0 < w - 1 ? 1 : 0);
-    float ly = fy - (float)y0, lx = fx - (float)x0;
-    const uint8_t* im = g + (int64_t)b * h * w;
-    float v00 = im[y0 * w + x0], v01 = im[y0 * w + x1], v10 = im[y1 * w + x0], v11 = im[y1 * w + x1];
-    float v = (1.f - ly) * ((1.f - lx) * v00 + lx * v01) + ly * ((1.f - lx) * v10 + lx * v11);
-    v = v / 255.0f;
-    const float mean[3] = {0.485f, 0.456f, 0.406f}, sd[3] = {0.229f, 0.224f, 0.225f};
+// ---- u8 image -> model tensor exactly as the reference's transform does it (inference_p.py:148-158, dataset.py:109-113):
+//   cv2.imread(...)[..., ::-1]          BGR -> RGB (a gray image has three equal channels)
+//   A.Resize(size, size)                cv2.resize(uint8, INTER_LINEAR): FIXED-POINT bilinear, result rounded to uint8
+//   A.Normalize()                       float32: (v - mean*255) * (1 / (std*255)), two roundings
+// The resize is integer work and is reproduced bit for bit (OpenCV imgproc/resize.cpp, 8-bit linear path): per destination
+// coordinate f = (float)((d + 0.5) * scale - 0.5) with scale = 1 / (dst / src) in double, s = floor(f), coefficients
+// saturate_cast<short>((1 - f) * 2048), ((f) * 2048) rounded half-to-even; in x a source index outside the row gets coefficient
+// (2048, 0) on the clamped pixel, in y the two ROWS are clamped and keep their coefficients; horizontal pass in int32, vertical pass
+// ((b0 * (S0 >> 4)) >> 16) + ((b1 * (S1 >> 4)) >> 16) + 2) >> 2.  Pinned against cv2 4.13 outputs (tests/golden/case_preprocess.pt).
+struct ResizeCoef { int s; int a0, a1; };
+
+__device__ __forceinline__ ResizeCoef resize_coef(int d, int src, int dst, bool zero_outside) {
+  const double scale = __ddiv_rn(1.0, __ddiv_rn((double)dst, (double)src));
+  float f = __double2float_rn(__dadd_rn(__dmul_rn((double)d + 0.5, scale), -0.5));     // no fused multiply-add: OpenCV's baseline build has none
+  int s = (int)floorf(f);
+  f = __fsub_rn(f, (float)s);
+  if (zero_outside) {
+    if (s < 0) { f = 0.f; s = 0; }
+    if (s >= src - 1) { f = 0.f; s = src - 1; }
+  }
+  ResizeCoef c;
+  c.s = s;
+  c.a0 = max(-32768, min(32767, __float2int_rn(__fmul_rn(__fsub_rn(1.0f, f), 2048.0f))));
+  c.a1 = max(-32768, min(32767, __float2int_rn(__fmul_rn(f, 2048.0f))));
+  return c;
+}
+
+// one block per (output row, image), one thread per output column; CH = 1 (gray, (B,h,w)) or 3 (BGR interleaved, (B,h,w,3))
+template <int CH>
+__global__ void preprocess_u8_kernel(const uint8_t* __restrict__ src, int h, int w, float* __restrict__ out, int size,
+                                     float m0, float m1, float m2, float d0, float d1, float d2) {
+  const int y = blockIdx.x, b = blockIdx.y;
+  const ResizeCoef cy = resize_coef(y, h, size, false);
+  const int y0 = min(max(cy.s, 0), h - 1), y1 = min(max(cy.s + 1, 0), h - 1);
+  const uint8_t* im = src + (int64_t)b * h * w * CH;
+  const float mean[3] = {m0, m1, m2}, den[3] = {d0, d1, d2};
+  for (int x = threadIdx.x; x < size; x += blockDim.x) {
+    const ResizeCoef cx = resize_coef(x, w, size, true);
+    const int x0 = cx.s, x1 = min(cx.s + 1, w - 1);
+    int v[CH];
 #pragma unroll
-    for (int c = 0; c < 3; ++c) out[(((int64_t)b * 3 + c) * size + y) * size + x] = (v - mean[c]) / sd[c];
+    for (int c = 0; c < CH; ++c) {
+      const int S0 = (int)im[((int64_t)y0 * w + x0) * CH + c] * cx.a0 + (int)im[((int64_t)y0 * w + x1) * CH + c] * cx.a1;
+      const int S1 = (int)im[((int64_t)y1 * w + x0) * CH + c] * cx.a0 + (int)im[((int64_t)y1 * w + x1) * CH + c] * cx.a1;
+      const int r = (((cy.a0 * (S0 >> 4)) >> 16) + ((cy.a1 * (S1 >> 4)) >> 16) + 2) >> 2;
+      v[c] = min(255, max(0, r));
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {           // output channel c = R,G,B; BGR input: source channel 2 - c
+      const int vv = CH == 1 ? v[0] : v[CH == 1 ? 0 : 2 - c];
+      out[(((int64_t)b * 3 + c) * size + y) * size + x] = __fmul_rn(__fsub_rn((float)vv, mean[c]), den[c]);
+    }
   }
 }
 
@@ -239,13 +274,29 @@ extern "C" int mdc_layernorm(mdc_ctx* ctx, const float* x, int64_t ldx, const fl
   MDC_LAUNCH_CHECK(ctx); return 0;
 }
 
-extern "C" int mdc_preprocess_gray(mdc_ctx* ctx, const uint8_t* gray, int B, int h, int w, float* out, int size, void* stream) {
-  MDC_CHECK_ARG(ctx && gray && out && B >= 0 && h > 0 && w > 0 && size > 0);
+// A.Normalize() constants as albumentations computes them (functional.normalize): float32 mean * 255, reciprocal of float32 std * 255
+static void normalize_constants(float (&m)[3], float (&d)[3]) {
+  const float mean[3] = {0.485f, 0.456f, 0.406f}, sd[3] = {0.229f, 0.224f, 0.225f};
+  for (int c = 0; c < 3; ++c) { m[c] = mean[c] * 255.0f; const float s = sd[c] * 255.0f; d[c] = 1.0f / s; }
+}
+
+static int preprocess_launch(mdc_ctx* ctx, const uint8_t* src, int B, int h, int w, int ch, float* out, int size, void* stream) {
+  MDC_CHECK_ARG(ctx && src && out && B >= 0 && h > 0 && w > 0 && size > 0 && h < 32768 && w < 32768 && B < 65536);
   MDC_CHECK_DEVICE(ctx);
   if (B == 0) return 0;
-  int grid = blocks_for((int64_t)B * size * size, 256, ctx->sm_count);
-  preprocess_gray_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(gray, B, h, w, out, size);
+  float m[3], d[3]; normalize_constants(m, d);
+  const dim3 grid(size, B); const int block = size < 256 ? ((size + 31) / 32) * 32 : 256;
+  if (ch == 1) preprocess_u8_kernel<1><<<grid, block, 0, (cudaStream_t)stream>>>(src, h, w, out, size, m[0], m[1], m[2], d[0], d[1], d[2]);
+  else preprocess_u8_kernel<3><<<grid, block, 0, (cudaStream_t)stream>>>(src, h, w, out, size, m[0], m[1], m[2], d[0], d[1], d[2]);
   MDC_LAUNCH_CHECK(ctx); return 0;
+}
+
+extern "C" int mdc_preprocess_gray(mdc_ctx* ctx, const uint8_t* gray, int B, int h, int w, float* out, int size, void* stream) {
+  return preprocess_launch(ctx, gray, B, h, w, 1, out, size, stream);
+}
+
+extern "C" int mdc_preprocess_bgr(mdc_ctx* ctx, const uint8_t* bgr, int B, int h, int w, float* out, int size, void* stream) {
+  return preprocess_launch(ctx, bgr, B, h, w, 3, out, size, stream);
 }
 
 extern "C" int mdc_interp_rows(mdc_ctx* ctx, const float* in, int n_in, float* out, int n_out, int dim, void* stream) {

@@ -42,38 +42,43 @@ __device__ __forceinline__ float score(float4 p, float4 g) {
 constexpr int IOU_THREADS = 256;
 
 // I = index type: 32-bit when B*N*M < 2^31 (the kernel is issue-bound, and three 64-bit integer divisions per thread were a third
-// of its instructions), 64-bit otherwise
-template <int MODE, typename I>
+// of its instructions), 64-bit otherwise.  STAGED: the GT boxes of the block's images and the block's 256 x M outputs go through
+// shared memory (coalesced write-back); shapes whose staging does not fit (many GT boxes per image: bbox_iou((N,4),(M,4)) with
+// M in the hundreds, or N = 1 with dozens of GT boxes) take the direct form: GT boxes by 128-bit read-only loads, outputs stored
+// straight to global memory.
+template <int MODE, typename I, bool STAGED>
 __global__ void __launch_bounds__(IOU_THREADS) iou_batch_kernel(const float4* __restrict__ pred,
                                                                 const float4* __restrict__ gt, int B, int N, int M,
                                                                 float* __restrict__ iou_out, float* __restrict__ max_out, int n_gt_cap) {
-  extern __shared__ float4 sgt[];   // GT boxes of the images this block touches, then the block's 256 x M outputs
+  extern __shared__ float4 sgt[];   // GT boxes of the images this block touches, then (when iou_out) the block's 256 x M outputs
   float* sout = reinterpret_cast<float*>(sgt + n_gt_cap);
   const I total = (I)B * N;
   const I first = (I)blockIdx.x * IOU_THREADS;
   const int img0 = (int)(first / N);
-  const I last = min(first + (I)IOU_THREADS, total) - 1;
-  const int img1 = (int)(last / N);
-  const int n_gt = (img1 - img0 + 1) * M;
-  for (int i = threadIdx.x; i < n_gt; i += IOU_THREADS) sgt[i] = __ldg(gt + (I)img0 * M + i);
-  __syncthreads();
+  if (STAGED) {
+    const I last = min(first + (I)IOU_THREADS, total) - 1;
+    const int img1 = (int)(last / N);
+    const int n_gt = (img1 - img0 + 1) * M;
+    for (int i = threadIdx.x; i < n_gt; i += IOU_THREADS) sgt[i] = __ldg(gt + (I)img0 * M + i);
+    __syncthreads();
+  }
   I idx = first + threadIdx.x;
   if (idx < total) {
     const int img = (int)(idx / N);
     const float4 p = __ldg(pred + idx);
-    const float4* g = sgt + (img - img0) * M;
+    const float4* g = STAGED ? sgt + (img - img0) * M : gt + (I)img * M;
     float best = -INFINITY;
     bool any_nan = false;
 #pragma unroll 4
     for (int j = 0; j < M; ++j) {
-      const float v = score<MODE>(p, g[j]);
-      sout[threadIdx.x * M + j] = v;
+      const float v = score<MODE>(p, STAGED ? g[j] : __ldg(g + j));
+      if (iou_out) { if (STAGED) sout[threadIdx.x * M + j] = v; else iou_out[idx * M + j] = v; }
       any_nan |= isnan(v);
       best = fmaxf(best, v);
     }
     if (max_out) max_out[idx] = any_nan ? NAN : best;   // torch.max propagates NaN
   }
-  if (iou_out) {
+  if (STAGED && iou_out) {
     // the block's outputs are one contiguous range of the (B,N,M) tensor: written back with consecutive lanes on consecutive floats
     // (M-strided 4-byte stores cost 17 L2 sectors per warp store)
     __syncthreads();
@@ -135,19 +140,21 @@ extern "C" int mdc_iou_batch(mdc_ctx* ctx, int mode, const float* pred, const fl
   MDC_CHECK_ARG(M > 0);
   int64_t total = (int64_t)B * N;
   int grid = (int)((total + IOU_THREADS - 1) / IOU_THREADS);
-  int imgs_per_block = IOU_THREADS / (N > 0 ? N : 1) + 2;
+  int imgs_per_block = IOU_THREADS / (N > 0 ? N : 1) + 2;       // images a 256-thread block can touch
+  if (imgs_per_block > B) imgs_per_block = B;
   const int n_gt_cap = imgs_per_block * M;
-  size_t smem = (size_t)n_gt_cap * sizeof(float4) + (size_t)IOU_THREADS * M * sizeof(float);
-  MDC_CHECK_ARG(smem <= 200 * 1024);
+  size_t smem = (size_t)n_gt_cap * sizeof(float4) + (iou_out ? (size_t)IOU_THREADS * M * sizeof(float) : 0);
+  const bool staged = smem <= 96 * 1024;                         // two blocks per SM keep their staging resident
+  if (!staged) smem = 0;
   const bool small = total * M < ((int64_t)1 << 31) - IOU_THREADS * (int64_t)M;
-#define MDC_IOU_LAUNCH(MODE_)                                                                                                                        \
-  if (small) {                                                                                                                                       \
-    MDC_ENSURE_SMEM((iou_batch_kernel<MODE_, int>), smem);                                                                                           \
-    iou_batch_kernel<MODE_, int><<<grid, IOU_THREADS, smem, (cudaStream_t)stream>>>((const float4*)pred, (const float4*)gt, B, N, M, iou_out, max_out, n_gt_cap); \
-  } else {                                                                                                                                           \
-    MDC_ENSURE_SMEM((iou_batch_kernel<MODE_, int64_t>), smem);                                                                                       \
-    iou_batch_kernel<MODE_, int64_t><<<grid, IOU_THREADS, smem, (cudaStream_t)stream>>>((const float4*)pred, (const float4*)gt, B, N, M, iou_out, max_out, n_gt_cap); \
+#define MDC_IOU_LAUNCH2(MODE_, I_, ST_)                                                                                                              \
+  {                                                                                                                                                  \
+    MDC_ENSURE_SMEM((iou_batch_kernel<MODE_, I_, ST_>), smem);                                                                                       \
+    iou_batch_kernel<MODE_, I_, ST_><<<grid, IOU_THREADS, smem, (cudaStream_t)stream>>>((const float4*)pred, (const float4*)gt, B, N, M, iou_out, max_out, n_gt_cap); \
   }
+#define MDC_IOU_LAUNCH(MODE_)                                                                                                                        \
+  if (small) { if (staged) MDC_IOU_LAUNCH2(MODE_, int, true) else MDC_IOU_LAUNCH2(MODE_, int, false) }                                               \
+  else { if (staged) MDC_IOU_LAUNCH2(MODE_, int64_t, true) else MDC_IOU_LAUNCH2(MODE_, int64_t, false) }
   switch (mode) {
     case MDC_IOU_EPS: MDC_IOU_LAUNCH(MDC_IOU_EPS) break;
     case MDC_IOU_PLAIN: MDC_IOU_LAUNCH(MDC_IOU_PLAIN) break;
@@ -155,6 +162,7 @@ extern "C" int mdc_iou_batch(mdc_ctx* ctx, int mode, const float* pred, const fl
     default: MDC_IOU_LAUNCH(MDC_IOU_GIOU) break;
   }
 #undef MDC_IOU_LAUNCH
+#undef MDC_IOU_LAUNCH2
   MDC_LAUNCH_CHECK(ctx); return 0;
 }
 

@@ -36,31 +36,43 @@ def generate(model, x, tokenizer, max_len=50, top_k=0, top_p=1, uniforms=None):
     return host.long(), [host_c[:, i].clone() for i in range(n_conf)]
 
 
-def preprocess_gray(gray_u8, size=None, out=None):
-    """The reference's image normalisation for NEU-DET-style grayscale inputs as ONE kernel (inference_p.py:148-158 /
-    dataset.py:109-113: cv2 BGR->RGB of a gray image = 3 equal channels, A.Resize(size, size) bilinear with half-pixel centres,
-    A.Normalize with the ImageNet mean / std): u8 (B,h,w) on the device (or pinned host: copied first) -> f32 (B,3,size,size).
-    40 KB per 200x200 image cross PCIe instead of 602 KB of float pixels."""
+def _preprocess_u8(img_u8, size, out, channels):
     from . import _lib as L
     size = int(size or CFG.img_size)
-    dev = gray_u8.device if gray_u8.is_cuda else torch.device(CFG.device)
+    dev = img_u8.device if img_u8.is_cuda else torch.device(CFG.device)
     if dev.type != "cuda":
-        raise L.MdcError("preprocess_gray runs on the GPU; there is no CPU fallback")
-    if gray_u8.dtype != torch.uint8 or gray_u8.dim() != 3:
-        raise ValueError("gray_u8 must be a uint8 (B,h,w) tensor")
-    g = gray_u8.to(dev, non_blocking=True).contiguous()
-    B, h, w = g.shape
+        raise L.MdcError("image preprocessing runs on the GPU; there is no CPU fallback")
+    want_dim = 3 if channels == 1 else 4
+    if img_u8.dtype != torch.uint8 or img_u8.dim() != want_dim or (channels == 3 and img_u8.shape[-1] != 3):
+        raise ValueError("expected a uint8 (B,h,w) gray batch" if channels == 1 else "expected a uint8 (B,h,w,3) BGR batch")
+    g = img_u8.to(dev, non_blocking=True).contiguous()
+    B, h, w = g.shape[:3]
     if out is None:
         out = torch.empty((B, 3, size, size), dtype=torch.float32, device=dev)
+    fn = L.lib().mdc_preprocess_gray if channels == 1 else L.lib().mdc_preprocess_bgr
     with torch.cuda.device(dev):
-        L.check(L.lib().mdc_preprocess_gray(L.ctx(dev), L.ptr(g), B, h, w, L.ptr(out), size, L.stream_ptr()))
+        L.check(fn(L.ctx(dev), L.ptr(g), B, h, w, L.ptr(out), size, L.stream_ptr(dev)))
     return out
 
 
-def postprocess(batch_preds, batch_confs, tokenizer):
-    """inference_trail_after_good_map.py:50-76 (caption-aware twin of inference_p.py:93-115): first EOS,
-    the reference's `(EOS-1) % 5` sanity rule (Q12, kept verbatim), then Tokenizer.decode of every sample -- as one
-    batched GPU scan (csrc/tokens.cu) when the tokenizer is the B200 one."""
+def preprocess_gray(gray_u8, size=None, out=None):
+    """The reference's image transform for NEU-DET-style grayscale inputs as ONE kernel (inference_p.py:148-158 / dataset.py:109-113):
+    cv2.imread of a gray file = 3 equal channels, A.Resize(size, size) = cv2.resize(uint8, INTER_LINEAR) -- fixed-point bilinear,
+    ROUNDED TO uint8, reproduced bit for bit -- then A.Normalize with the ImageNet mean / std in float32.
+    u8 (B,h,w) on the device (or pinned host: copied first) -> f32 (B,3,size,size).  40 KB per 200x200 image cross PCIe instead of
+    602 KB of float pixels."""
+    return _preprocess_u8(gray_u8, size, out, 1)
+
+
+def preprocess_bgr(bgr_u8, size=None, out=None):
+    """The same transform for colour inputs exactly as `cv2.imread(path)` returns them: u8 (B,h,w,3), channels B,G,R.  The kernel does
+    the `[..., ::-1]` flip (inference_p.py:152), the uint8 cv2 resize and A.Normalize; output f32 (B,3,size,size), channels R,G,B."""
+    return _preprocess_u8(bgr_u8, size, out, 3)
+
+
+def _postprocess(batch_preds, batch_confs, tokenizer):
+    """Shared body of postprocess / postprocess_with_captions: first EOS, the reference's `(EOS-1) % 5` sanity rule (Q12, kept
+    verbatim), then Tokenizer.decode of every sample -- as one batched GPU scan (csrc/tokens.cu) when the tokenizer is the B200 one."""
     EOS_idxs = (batch_preds == tokenizer.EOS_code).float().argmax(dim=-1)
     invalid_idxs = ((EOS_idxs - 1) % 5 != 0).nonzero().view(-1)
     EOS_idxs[invalid_idxs] = 0
@@ -90,3 +102,15 @@ def postprocess(batch_preds, batch_confs, tokenizer):
         confs = [round(batch_confs[j][i].item(), 3) for j in range(len(bboxes))]
         all_bboxes.append(bboxes); all_labels.append(labels); all_captions.append(captions); all_confs.append(confs)
     return all_bboxes, all_labels, all_captions, all_confs
+
+
+def postprocess(batch_preds, batch_confs, tokenizer):
+    """inference_p.py:93-115: returns THREE lists (all_bboxes, all_labels, all_confs) -- the call site at inference_p.py:225 unpacks
+    `bboxes, labels, confs = postprocess(...)`.  Entries are None for sequences the reference's sanity rule rejects."""
+    all_bboxes, all_labels, _, all_confs = _postprocess(batch_preds, batch_confs, tokenizer)
+    return all_bboxes, all_labels, all_confs
+
+
+def postprocess_with_captions(batch_preds, batch_confs, tokenizer):
+    """inference_trail_after_good_map.py:50-76, the caption-aware twin: FOUR lists (all_bboxes, all_labels, all_captions, all_confs)."""
+    return _postprocess(batch_preds, batch_confs, tokenizer)

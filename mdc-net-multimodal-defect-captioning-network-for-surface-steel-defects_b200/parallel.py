@@ -17,22 +17,22 @@ def shard_bounds(batch, rank, world):
 
 
 def pack_results(tokens, confs, boxes=None, max_iou=None):
-    """int32 tokens (b,T1), f32 confs (b,C) [, f32 boxes (b,N,4), f32 max_iou (b,N)] -> one f32 buffer
-    (b, T1 + C + 4N + N); token ids (< 2^24) are exact in f32."""
-    parts = [tokens.to(torch.float32), confs.to(torch.float32)]
+    """int32 tokens (b,T1), f32 confs (b,C) [, f32 boxes (b,N,4), f32 max_iou (b,N)] -> one int32 buffer (b, T1 + C + 4N + N):
+    the token ids as they are, the float fields as their bit patterns (a view, no conversion in either direction)."""
+    parts = [tokens.to(torch.int32), confs.to(torch.float32).contiguous().view(torch.int32)]
     if boxes is not None:
-        parts.append(boxes.reshape(boxes.shape[0], -1).to(torch.float32))
+        parts.append(boxes.reshape(boxes.shape[0], -1).to(torch.float32).contiguous().view(torch.int32))
     if max_iou is not None:
-        parts.append(max_iou.to(torch.float32))
+        parts.append(max_iou.to(torch.float32).contiguous().view(torch.int32))
     return torch.cat(parts, dim=1).contiguous()
 
 
 def unpack_results(buf, T1, C, N=0):
-    tokens = buf[:, :T1].round().to(torch.int32)
-    confs = buf[:, T1:T1 + C]
+    tokens = buf[:, :T1]
+    confs = buf[:, T1:T1 + C].contiguous().view(torch.float32)
     off = T1 + C
-    boxes = buf[:, off:off + 4 * N].reshape(buf.shape[0], N, 4) if N else None
-    max_iou = buf[:, off + 4 * N:off + 5 * N] if N else None
+    boxes = buf[:, off:off + 4 * N].contiguous().view(torch.float32).reshape(buf.shape[0], N, 4) if N else None
+    max_iou = buf[:, off + 4 * N:off + 5 * N].contiguous().view(torch.float32) if N else None
     return tokens, confs, boxes, max_iou
 
 

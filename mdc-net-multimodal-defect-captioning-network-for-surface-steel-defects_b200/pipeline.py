@@ -58,8 +58,9 @@ class GenerationPipeline:
         self.n = 0
 
     def submit(self, image, uniforms=None):
-        """image: f32 (B,3,H,W) on the device or in (pinned) host memory -- or raw grayscale u8 (B,h,w), which is normalised
-        on the device by the fused preprocessing kernel (inference.preprocess_gray) straight into the plan's input buffer.
+        """image: f32 (B,3,H,W) on the device or in (pinned) host memory -- or raw u8 images, grayscale (B,h,w) or BGR (B,h,w,3) as
+        cv2.imread returns them, which the fused preprocessing kernel (inference.preprocess_gray / preprocess_bgr: the reference's
+        cv2-resize + normalise transform, bit-exact in its uint8 part) turns into the plan's input buffer on the device.
         Returns a Ticket."""
         p = self.plans[self.n % self.depth]
         s_dec = self.s_decs[self.n % len(self.s_decs)]
@@ -67,8 +68,8 @@ class GenerationPipeline:
         dev = self.eng.device
         gray = image.dtype == torch.uint8
         if gray:
-            if image.dim() != 3 or image.shape[0] != self.B:
-                raise AssertionError("gray input must be uint8 (B,h,w)")
+            if image.dim() not in (3, 4) or image.shape[0] != self.B or (image.dim() == 4 and image.shape[-1] != 3):
+                raise AssertionError("raw input must be uint8 (B,h,w) gray or (B,h,w,3) BGR")
         elif tuple(image.shape) != tuple(p.x.shape):
             raise AssertionError("Input size doesn't match model")
         cur = torch.cuda.current_stream(dev)
@@ -77,8 +78,8 @@ class GenerationPipeline:
             if p.busy:
                 self.s_enc.wait_event(p.dec_done)                       # plan buffers are free again
             if gray:
-                from .inference import preprocess_gray
-                preprocess_gray(image, size=p.x.shape[-1], out=p.x)
+                from .inference import preprocess_gray, preprocess_bgr
+                (preprocess_gray if image.dim() == 3 else preprocess_bgr)(image, size=p.x.shape[-1], out=p.x)
             else:
                 p.x.copy_(image, non_blocking=True)
             if p.uniforms is not None:
@@ -130,7 +131,7 @@ def generate_stream(model, batches, tokenizer, max_len=50, top_k=0, top_p=1, dep
 
     for x in batches:
         dev = x.device if x.is_cuda else None
-        key = ((x.shape[0], str(x.dtype)) if x.dtype == torch.uint8 else tuple(x.shape), int(max_len), int(top_k), float(top_p), int(depth), str(dev))
+        key = ((x.shape[0], x.dim(), str(x.dtype)) if x.dtype == torch.uint8 else tuple(x.shape), int(max_len), int(top_k), float(top_p), int(depth), str(dev))
         if key not in pipes or pipes[key].eng is not model._engine(dev):      # new shape (e.g. the ragged last batch) / new weights
             pipes[key] = GenerationPipeline(model, x.shape[0], max_len, top_k=top_k, top_p=top_p, depth=depth, to_host=True, device=dev)
         if pipes[key] is not pipe:

@@ -66,7 +66,7 @@ def state_dict_of(model):
 
 
 def images(B, seed=1234):
-    return O.preprocess_gray(O.synth_gray_u8(B, seed=seed))
+    return O.synthetic_model_inputs(O.synth_gray_u8(B, seed=seed))
 
 
 PREFIX = torch.tensor([[300, 5, 302, 17], [300, 260, 100, 302]])      # PAD (302) inside the prefix exercises Q7

@@ -84,7 +84,52 @@ def tokens_case(R):
                os.path.join(OUT, "case_tokens.pt"))
 
 
+def preprocess_case():
+    """The reference's VOCDatasetTest transform (inference_p.py:145-158: cv2.imread(...)[..., ::-1] -> A.Resize -> A.Normalize ->
+    permute) on synthetic uint8 images with the REAL cv2 (4.13 in this container): `resized_*` are cv2.resize(uint8, INTER_LINEAR)
+    outputs -- the integer part of the transform, which the CUDA kernel and the oracle restatement must reproduce bit for bit.
+    albumentations is absent (requirements.txt: albumentations>=1.2.1), so A.Normalize is its published arithmetic
+    (functional.normalize / normalize_cv2: float32 mean*255 and 1/(std*255)) executed with cv2.subtract / cv2.multiply exactly as
+    normalize_cv2 does for 3-channel images, and cross-checked against the numpy form: parity of that step is restated, not pinned."""
+    import cv2
+    import numpy as np
+    print("case preprocess (cv2", cv2.__version__ + ")")
+    gray = O.synth_gray_u8(2, seed=4321)                       # (2,200,200) NEU-DET-shaped
+    bgr = O.synth_bgr_u8(1, h=150, w=190, seed=99)             # (1,150,190,3) as cv2.imread returns colour images
+    small = O.synth_bgr_u8(1, h=64, w=48, seed=5)              # upscaling by a large factor
+    big = O.synth_gray_u8(1, hw=300, seed=6)                   # downscaling
+
+    def transform(img_hwc_rgb_u8, size):
+        r = cv2.resize(img_hwc_rgb_u8, (size, size), interpolation=cv2.INTER_LINEAR)           # A.Resize on uint8
+        assert np.array_equal(r, O.cv2_resize_linear_u8(img_hwc_rgb_u8, size, size)), "cv2.resize restatement"
+        mean = np.array(O.IMAGENET_MEAN, dtype=np.float32); mean *= 255.0
+        std = np.array(O.IMAGENET_STD, dtype=np.float32); std *= 255.0
+        den = np.reciprocal(std, dtype=np.float32)
+        f = np.ascontiguousarray(r.astype("float32"))
+        cv2.subtract(f, np.array(mean.tolist() + [0], dtype=np.float64), f)                     # normalize_cv2
+        cv2.multiply(f, np.array(den.tolist() + [0], dtype=np.float64), f)
+        assert np.array_equal(f, O.albu_normalize(r)), "normalize restatement (cv2 form == numpy form)"
+        return torch.from_numpy(r.copy()), torch.from_numpy(f).permute(2, 0, 1).contiguous()
+
+    # kept small: the uint8 resize outputs of cv2 (one channel for gray inputs, whose three channels are equal) -- the float32
+    # normalisation of exactly these values is asserted above to be O.albu_normalize, which the tests re-apply
+    gold = {"gray": gray, "bgr": bgr, "small": small, "big": big}
+    for name, batch, size in (("gray", gray, 224), ("bgr", bgr, 224), ("small", small, 224), ("big", big, 224), ("gray320", gray[:1], 320)):
+        rs = []
+        for im in batch.numpy():
+            rgb = np.repeat(im[:, :, None], 3, axis=2) if im.ndim == 2 else np.ascontiguousarray(im[..., ::-1])
+            r, o = transform(np.ascontiguousarray(rgb), size)
+            assert torch.equal(o, O.preprocess_u8(torch.from_numpy(im)[None], size)[0]), "oracle preprocess_u8"
+            rs.append(r[..., 0].contiguous() if im.ndim == 2 else r)
+        gold["resized_" + name] = torch.stack(rs)               # uint8: (B,size,size) for gray inputs, (B,size,size,3) RGB for colour
+    torch.save(gold, os.path.join(OUT, "case_preprocess.pt"))
+    print("  saved case_preprocess.pt:", {k: tuple(v.shape) for k, v in gold.items()})
+
+
 def main():
+    if "--only-preprocess" in sys.argv:          # needs cv2 only, not the reference tree
+        os.makedirs(OUT, exist_ok=True)
+        return preprocess_case()
     assert ref_loader.available(), "needs /root/reference"
     os.makedirs(OUT, exist_ok=True)
     R = ref_loader.load()
@@ -180,6 +225,7 @@ def main():
     assert abs(gl.item() - O.giou_loss_with_scores(p, q)[0].item()) < 1e-6
     torch.save(gold, os.path.join(OUT, "case_iou.pt"))
     tokens_case(R)
+    preprocess_case()
     for f in sorted(os.listdir(OUT)):
         print(f"  {f}: {os.path.getsize(os.path.join(OUT, f)) / 1024:.0f} KiB")
 

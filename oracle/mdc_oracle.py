@@ -20,6 +20,7 @@ from __future__ import annotations
 import math
 from dataclasses import dataclass
 
+import numpy as np
 import torch
 import torch.nn.functional as F
 
@@ -459,16 +460,87 @@ def synth_gray_u8(B, hw=200, seed=1234):
     return torch.randint(0, 256, (B, hw, hw), generator=g, dtype=torch.uint8)
 
 
+def _cv2_linear_coeffs(src, dst, zero_outside):
+    """OpenCV imgproc/resize.cpp, 8-bit INTER_LINEAR tables: f = (float)((d + 0.5) * scale - 0.5) with scale = 1 / (dst / src) in
+    double, s = floor(f), fixed-point coefficients saturate_cast<short>(c * 2048) rounded half-to-even.  In x an index outside the
+    row gets (2048, 0) on the clamped pixel (`zero_outside`); in y the coefficients are kept and the two ROWS are clamped."""
+    scale = 1.0 / (float(dst) / float(src))
+    s_out = np.zeros(dst, np.int64); a = np.zeros((dst, 2), np.int64)
+    for d in range(dst):
+        f = np.float32((d + 0.5) * scale - 0.5)
+        s = int(np.floor(f)); f = np.float32(f - np.float32(s))
+        if zero_outside:
+            if s < 0:
+                f, s = np.float32(0), 0
+            if s >= src - 1:
+                f, s = np.float32(0), src - 1
+        s_out[d] = s
+        a[d, 0] = int(np.clip(np.rint(np.float32((np.float32(1.0) - f) * np.float32(2048))), -32768, 32767))
+        a[d, 1] = int(np.clip(np.rint(np.float32(f * np.float32(2048))), -32768, 32767))
+    return s_out, a
+
+
+def cv2_resize_linear_u8(img, W, H):
+    """cv2.resize(img, (W, H), interpolation=cv2.INTER_LINEAR) for a uint8 (h,w) or (h,w,c) numpy image, restated in integer
+    arithmetic -- what A.Resize(size, size) runs on the reference's uint8 images (inference_p.py:148, dataset.py:109-113).
+    Pinned bit-exact against cv2 4.13 in oracle/make_golden.py and tests/test_oracle_cpu.py."""
+    h, w = img.shape[:2]
+    sx, ax = _cv2_linear_coeffs(w, W, True)
+    sy, ay = _cv2_linear_coeffs(h, H, False)
+    im = img.astype(np.int64)
+    x1 = np.minimum(sx + 1, w - 1)
+    shx = (1, -1, 1) if img.ndim == 3 else (1, -1)
+    rows = im[:, sx] * ax[:, 0].reshape(shx) + im[:, x1] * ax[:, 1].reshape(shx)          # horizontal pass, int32 range
+    y0 = np.clip(sy, 0, h - 1); y1 = np.clip(sy + 1, 0, h - 1)
+    shy = (-1, 1, 1) if img.ndim == 3 else (-1, 1)
+    b0 = ay[:, 0].reshape(shy); b1 = ay[:, 1].reshape(shy)
+    out = (((b0 * (rows[y0] >> 4)) >> 16) + ((b1 * (rows[y1] >> 4)) >> 16) + 2) >> 2       # vertical pass (VResizeLinear, uchar)
+    return np.clip(out, 0, 255).astype(np.uint8)
+
+
+def albu_normalize(img_u8_hwc):
+    """albumentations.Normalize() defaults (functional.normalize, 1.x; third party, absent here -- restated, parity unpinned):
+    float32 mean * 255, reciprocal of float32 std * 255, img.astype(float32); img -= mean; img *= denominator."""
+    mean = np.array(IMAGENET_MEAN, dtype=np.float32); mean *= 255.0
+    std = np.array(IMAGENET_STD, dtype=np.float32); std *= 255.0
+    den = np.reciprocal(std, dtype=np.float32)
+    img = img_u8_hwc.astype(np.float32)
+    img -= mean
+    img *= den
+    return img
+
+
+def preprocess_u8(batch_u8, size=224):
+    """The reference's VOCDatasetTest transform (inference_p.py:145-158) for a batch: uint8 (B,h,w) gray images (cv2.imread gives
+    three equal channels) or (B,h,w,3) BGR images -> f32 (B,3,size,size): [..., ::-1] -> A.Resize -> A.Normalize -> permute(2,0,1)."""
+    arr = batch_u8.numpy()
+    outs = []
+    for im in arr:
+        rgb = np.repeat(im[:, :, None], 3, axis=2) if im.ndim == 2 else im[..., ::-1]
+        r = cv2_resize_linear_u8(np.ascontiguousarray(rgb), size, size)
+        outs.append(torch.from_numpy(albu_normalize(r)).permute(2, 0, 1))
+    return torch.stack(outs)
+
+
 def preprocess_gray(u8, size=224):
-    """u8 (B,h,w) gray -> 3 identical channels -> bilinear resize (half-pixel centres, the
-    cv2.INTER_LINEAR / A.Resize convention, dataset.py:109-113) -> /255, ImageNet normalise
-    (A.Normalize defaults) -> f32 (B,3,size,size)."""
+    return preprocess_u8(u8, size)
+
+
+def synthetic_model_inputs(u8, size=224):
+    """Generator of the seeded f32 (B,3,size,size) MODEL INPUTS the committed model goldens (case_P_*, case_S_*, case_axial) were
+    made with: float bilinear interpolation of the synthetic gray images + ImageNet normalisation.  NOT the reference transform
+    (that is preprocess_u8: uint8 cv2 resize) -- just a fixed, smooth-ish input distribution; kept so the goldens stay valid."""
     x = u8.to(torch.float32)[:, None]
     x = F.interpolate(x, size=(size, size), mode="bilinear", align_corners=False)
     x = x / 255.0
     mean = torch.tensor(IMAGENET_MEAN).view(1, 3, 1, 1)
     std = torch.tensor(IMAGENET_STD).view(1, 3, 1, 1)
     return (x.expand(-1, 3, -1, -1) - mean) / std
+
+
+def synth_bgr_u8(B, h=260, w=300, seed=99):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randint(0, 256, (B, h, w, 3), generator=g, dtype=torch.uint8)
 
 
 def to_dtype(sd, dtype):

@@ -36,7 +36,7 @@ def _model_512(seed=3, gamma_seed=8):
 def test_config4_encoder_stress_512_inputs():
     model = _model_512()
     sd, cfg = cases.state_dict_of(model), cases.oracle_cfg("P")
-    x = O.preprocess_gray(O.synth_gray_u8(2, hw=200, seed=91), size=512)
+    x = O.synthetic_model_inputs(O.synth_gray_u8(2, hw=200, seed=91), size=512)
     want_enc = O.encoder_forward(sd, x, cfg)
     assert want_enc.shape == (2, 1024, 256)
     model.to(DEV).set_precision("fp32")
@@ -54,8 +54,12 @@ def test_config4_encoder_stress_512_inputs():
     eb, lb = (encb.cpu() - want_enc).abs().max().item(), (logits_b.cpu() - want_logits).abs().max().item()
     print(f"config 4 bf16: encoder max|d| = {eb:.2e}, logits max|d| = {lb:.2e}, cosine = {G.cos(logits_b.cpu(), want_logits):.6f}")
     assert lb <= 2e-2 and G.cos(logits_b.cpu(), want_logits) >= 0.999
+    # the 1024 memory keys run through the fused cluster kernel (64 key chunks per layer); the per-operation kernels agree
+    with M.decode_options(per_op_kernels=True):
+        _, _, logits_g = model.generate_tokens(x.to(DEV), 8, return_logits=True)
+    assert not torch.equal(logits_g, logits_b) and (logits_g - logits_b).abs().max().item() < 1.5e-2
     # batch-size independence at a larger batch (B=128 of BASELINE is 34 GB of activations at 1025 tokens: property only, B=16)
-    x16 = O.preprocess_gray(O.synth_gray_u8(16, hw=200, seed=92), size=512).to(DEV)
+    x16 = O.synthetic_model_inputs(O.synth_gray_u8(16, hw=200, seed=92), size=512).to(DEV)
     t16, _ = model.generate_tokens(x16, 12)
     t3, _ = model.generate_tokens(x16[[15, 0, 7]], 12)
     assert torch.equal(t3, t16[[15, 0, 7]])

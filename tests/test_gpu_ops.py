@@ -140,6 +140,23 @@ def test_iou_full_size_properties():
     assert M.calculate_batch_max_iou(torch.zeros(2, 0, 4, device=DEV), torch.zeros(2, 3, 4, device=DEV)) == []
 
 
+def test_iou_shapes_beyond_the_shared_memory_staging():
+    """Shapes the reference accepts whose GT / output staging does not fit shared memory take the kernel's direct form:
+    bbox_iou((300,4),(300,4)); calculate_batch_max_iou_torchvision with pred (B,1,4) and 64 GT boxes per image (N = 1)."""
+    g = torch.Generator().manual_seed(8)
+    def boxes(*shape):
+        b = torch.rand(*shape, 4, generator=g) * 160; b[..., 2:] = b[..., :2] + 8 + torch.rand(*shape, 2, generator=g) * 56
+        return b
+    a, b = boxes(300), boxes(300)
+    assert torch.equal(M.bbox_iou(a.to(DEV), b.to(DEV)).cpu(), O.bbox_iou(a, b))
+    p, q = boxes(37, 1), boxes(37, 64)
+    q[::4, 50:] = 0
+    assert torch.equal(torch.tensor(M.calculate_batch_max_iou_torchvision(p.to(DEV), q.to(DEV))), O.batch_max_iou_torchvision(p, q).flatten())
+    assert torch.equal(torch.stack(M.calculate_batch_iou(p.to(DEV), q.to(DEV))).cpu(), O.batch_iou(p, q))
+    p2, q2 = boxes(2, 3), boxes(2, 700)                    # B = 2: the staging is sized for the images a block touches, not 258
+    assert torch.equal(torch.stack(M.calculate_batch_iou(p2.to(DEV), q2.to(DEV))).cpu(), O.batch_iou(p2, q2))
+
+
 def test_select_greedy_topk_topp_against_oracle():
     torch.manual_seed(0)
     logits = torch.randn(64, 305) * 3
@@ -157,12 +174,31 @@ def test_select_greedy_topk_topp_against_oracle():
         assert (conf.cpu() - torch.softmax(filt, -1).max(-1)[0]).abs().max() < 1e-6
 
 
-def test_preprocess_and_interp():
-    u8 = O.synth_gray_u8(3, hw=200, seed=9)
+def test_preprocess_is_bit_exact_against_cv2_goldens(golden):
+    """the fused transform kernel against tests/golden/case_preprocess.pt -- uint8 outputs of the REAL
+    cv2.resize(INTER_LINEAR) (what A.Resize runs on the reference's uint8 images, inference_p.py:148-158) for gray, BGR colour,
+    strong upscaling, downscaling and a second model size.  Integer work: the kernel's float32 output must be EXACTLY A.Normalize
+    of cv2's uint8 pixels (torch.equal), i.e. the uint8 rounding is reproduced bit for bit."""
+    g = golden("case_preprocess.pt")
+    import numpy as np
+    for name, src, size in (("gray", g["gray"], 224), ("bgr", g["bgr"], 224), ("small", g["small"], 224), ("big", g["big"], 224),
+                            ("gray320", g["gray"][:1], 320)):
+        r = g["resized_" + name].numpy()
+        want = torch.stack([torch.from_numpy(O.albu_normalize(np.repeat(im[:, :, None], 3, axis=2) if im.ndim == 2 else im)).permute(2, 0, 1)
+                            for im in r])
+        got = (M.preprocess_gray if src.dim() == 3 else M.preprocess_bgr)(src.to(DEV), size=size).cpu()
+        assert got.shape == want.shape and torch.equal(got, want), name
+        # and the uint8 pixel recovered from the kernel's output is cv2's
+        mean = torch.tensor(O.IMAGENET_MEAN).view(1, 3, 1, 1) * 255.0; std = torch.tensor(O.IMAGENET_STD).view(1, 3, 1, 1) * 255.0
+        px = torch.round(got * std + mean).to(torch.uint8).permute(0, 2, 3, 1)
+        assert torch.equal(px[..., 0] if src.dim() == 3 else px, g["resized_" + name]), name
     out = torch.empty((3, 3, 224, 224), dtype=torch.float32, device=DEV)
-    g = u8.to(DEV)
-    L.check(L.lib().mdc_preprocess_gray(L.ctx(DEV), L.ptr(g), 3, 200, 200, L.ptr(out), 224, L.stream_ptr()))
-    assert (out.cpu() - O.preprocess_gray(u8)).abs().max().item() < 1e-5
+    u8 = O.synth_gray_u8(3, hw=200, seed=9).to(DEV)
+    L.check(L.lib().mdc_preprocess_gray(L.ctx(DEV), L.ptr(u8), 3, 200, 200, L.ptr(out), 224, L.stream_ptr()))      # through the C ABI
+    assert torch.equal(out.cpu(), O.preprocess_u8(u8.cpu()))
+
+
+def test_interp_rows():
     pos = torch.randn(1, 99, 256)
     for n in (5, 13, 150, 257):
         got = torch.empty((n, 256), dtype=torch.float32, device=DEV)
@@ -224,7 +260,9 @@ def test_postprocess_batched_equals_per_sample_decode(golden):
     tk = M.Tokenizer(num_bins=224, width=224, height=224, vocab={i: f"w{i}" for i in range(270, 299)})
     toks = g["tokens"]
     confs = [torch.full((toks.shape[0],), 0.5 + 0.01 * j) for j in range(25)]
-    bboxes, labels, caps, cf = M.postprocess(toks, confs, tk)
+    bboxes, labels, caps, cf = M.postprocess_with_captions(toks, confs, tk)
+    b3, l3, c3 = M.postprocess(toks, confs, tk)            # the call site of inference_p.py:225 unpacks three lists
+    assert b3 == bboxes and l3 == labels and c3 == cf
     eos = (toks == 301).float().argmax(-1)
     for i in range(toks.shape[0]):
         e = int(eos[i])

@@ -120,3 +120,23 @@ def test_live_reference_agrees_with_oracle(case_p):
     with torch.no_grad(), cases.quiet():
         want = rm.predict(x[:1], cases.PREFIX[:1])
     assert (O.model_predict(sd, x[:1], cases.PREFIX[:1], cfg) - want).abs().max() < TOL
+
+
+def test_preprocess_restatement_against_cv2_goldens(golden):
+    """oracle.cv2_resize_linear_u8 (integer restatement of cv2.resize INTER_LINEAR on uint8, the A.Resize step of
+    inference_p.py:148-158) against the committed outputs of the real cv2 -- and against the live cv2 where it is installed."""
+    import numpy as np
+    g = golden("case_preprocess.pt")
+    for name, src, size in (("gray", g["gray"], 224), ("bgr", g["bgr"], 224), ("small", g["small"], 224), ("big", g["big"], 224),
+                            ("gray320", g["gray"][:1], 320)):
+        for im, want in zip(src.numpy(), g["resized_" + name].numpy()):
+            rgb = im if im.ndim == 2 else np.ascontiguousarray(im[..., ::-1])
+            assert np.array_equal(O.cv2_resize_linear_u8(rgb, size, size), want), name
+    try:
+        import cv2
+    except ImportError:
+        return
+    rng = np.random.default_rng(3)
+    for h, w, size, c in ((200, 200, 224, 1), (199, 201, 224, 3), (448, 448, 224, 3), (37, 53, 512, 1)):
+        im = rng.integers(0, 256, (h, w) if c == 1 else (h, w, c), dtype=np.uint8)
+        assert np.array_equal(O.cv2_resize_linear_u8(im, size, size), cv2.resize(im, (size, size), interpolation=cv2.INTER_LINEAR))
