@@ -265,6 +265,19 @@ int mdc_iou_batch(mdc_ctx* ctx, int mode, const float* pred, const float* gt, in
 int mdc_giou_loss(mdc_ctx* ctx, const float* pred, const float* gt, int B, int N, int M, float no_detection_penalty,
                   float* loss_per_image, float* giou_out, uint8_t* valid_out, void* stream);
 
+/* ---- detection metric: prediction <-> ground-truth matching ------------------------------------------------------------
+ * The per-image greedy assignment behind mAP (reference: train_val_epoch.py:205-231, torchmetrics MeanAveragePrecision with
+ * iou_thresholds = [0.3] -> pycocotools COCOeval.evaluateImg) for a batch in one launch: per image and class, detections in stable
+ * descending score order (at most max_det per class); each takes the unmatched ground-truth box of its class with the highest
+ * IoU >= iou_threshold.  pred_boxes f32 [B,N,4] xyxy, scores f32 [B,N], labels i32 [B,N], n_pred i32 [B] (valid rows per image);
+ * gt_boxes f32 [B,M,4], gt_labels i32 [B,M], n_gt i32 [B].  N <= 128, M <= 128.
+ * match_out i32 [B,N]: matched ground-truth index, -1 = false positive, -2 = not evaluated; order_out i32 [B,N]: position of the
+ * detection in its image's score order (-1 = not evaluated).  The precision/recall accumulation over the whole set is host-side
+ * (mdcnet_b200.metrics).  torchmetrics / pycocotools are absent here: restated from their published algorithm, parity unpinned. */
+int mdc_map_match(mdc_ctx* ctx, const float* pred_boxes, const float* scores, const int32_t* labels, const int32_t* n_pred,
+                  const float* gt_boxes, const int32_t* gt_labels, const int32_t* n_gt, int B, int N, int M, float iou_threshold,
+                  int max_det, int32_t* match_out, int32_t* order_out, void* stream);
+
 /* ---- token sequences -> labels / boxes / caption ids ---------------------------------------------------
  * The reference's per-sequence Python scans (with .item() syncs) between generate() and the IoU functions, as one launch.
  *   MDC_TOK_BBOXES  Tokenizer.decode_bboxes (data_processing.py:556-598): start after the first caption-end token (0 if none);

@@ -98,6 +98,7 @@ SIGNATURES = {
     "mdc_axial_embed": (_I, [_P, _P, _I, _I, _I, _P, _I, _P, _P, _SZ, _P]),
     "mdc_iou_batch": (_I, [_P, _I, _P, _P, _I, _I, _I, _P, _P, _P]),
     "mdc_giou_loss": (_I, [_P, _P, _P, _I, _I, _I, _F, _P, _P, _P, _P]),
+    "mdc_map_match": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _F, _I, _P, _P, _P]),
     "mdc_decode_tokens": (_I, [_P, _I, _P, _L, _I, _I, C.POINTER(TokenGrammar), _I, _P, _P, _P, _P, _P, _P]),
 }
 

@@ -448,15 +448,22 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(NT, MINB) decode_fu
           advance();
         }
       };
-      // chunk c (16 keys) of the K and V head slices of all images of the group: [image][k|v][16 keys][64 B], one 2 KB copy per image
+      // chunk c (16 keys) of the K and V head slices of all images of the group: [image][k|v][16 keys][64 B].  Self-KV: one 2 KB copy
+      // per image (its page of the pool).  Cross-K/V is packed in blocks of 8 images ([layer][image / 8][head][chunk][image % 8] x
+      // 2 KB), so a group of 8 or 16 images that starts on a multiple of 8 is fetched with one 16 KB copy per block.
+      const bool ckv_blocks = (img0 & 7) == 0 && (G & 7) == 0;
+      const int nb8 = (P.B + 7) >> 3;
       auto emit_kv = [&](bool cross, int l, int c) {
         const uint32_t st = acquire(); const uint32_t fb = bar(BAR_FULL + slot);
         if (lane == 0) mbar_expect_tx(fb, G * 2048);
         __syncwarp();
-        if (lane < G) {
-          const uint8_t* src = cross ? P.ckv_pack + ((((size_t)l * P.B + img0 + lane) * CS + rank) * nck + c) * 2048
-                                     : (const uint8_t*)P.kv_pool + (((size_t)pages[lane * 32 + c] * L + l) * CS + rank) * 2048;
-          bulk_g2s(st + lane * 2048, src, 2048, fb);
+        if (cross) {
+          const int img = img0 + (ckv_blocks ? lane * 8 : lane);
+          const uint8_t* src = P.ckv_pack + (((((size_t)l * nb8 + (img >> 3)) * CS + rank) * nck + c) * 8 + (img & 7)) * 2048;
+          if (ckv_blocks) { if (lane < (G >> 3)) bulk_g2s(st + lane * 16384, src, 16384, fb); }
+          else if (lane < G) bulk_g2s(st + lane * 2048, src, 2048, fb);
+        } else if (lane < G) {
+          bulk_g2s(st + lane * 2048, (const uint8_t*)P.kv_pool + (((size_t)pages[lane * 32 + c] * L + l) * CS + rank) * 2048, 2048, fb);
         }
         advance();
       };
@@ -633,6 +640,8 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(NT, MINB) decode_fu
           else { aq[nb][0][0] = aq[nb][0][1] = aq[nb][1][0] = aq[nb][1][1] = 0u; }
         }
         const bool two = NB == 2 && warp + 8 < G;
+        // (probing the next stage's barrier early, so that its ~150-cycle try_wait overlaps the current chunk's MMA chain, was
+        //  measured SLOWER: 12.73 -> 13.26 ms per launch, profiles/r2 notes)
         for (int c = 0; c < nchunk; ++c) {
           if (warp == 0 && c < 8) FINE(l_now, t_now, 20 + c * 3);
           const uint32_t st = stage_wait();
@@ -1018,16 +1027,20 @@ __global__ void pack_weights_kernel(PackArgs a, uint4* __restrict__ out, size_t 
   }
 }
 
-// cross-K/V [layer][B*S][K(DM) | V(DM)] -> [layer][image][head][16-key chunk][k|v][16 keys][32 channels], 16-byte chunk c of key r
-// at chunk c ^ ((r >> 1) & 3); keys >= S are zero rows (masked by the kernel)
+// cross-K/V [layer][B*S][K(DM) | V(DM)] -> [layer][image / 8][head][16-key chunk][image % 8][k|v][16 keys][32 channels] (blocks of 8
+// images: the 16 KB a cluster pass needs per chunk and 8 images are contiguous), 16-byte chunk c of key r at chunk c ^ ((r >> 1) & 3);
+// keys >= S and images >= B are zero rows (masked / never read)
 __global__ void pack_cross_kv_kernel(const uint4* __restrict__ ckv, uint4* __restrict__ out, int B, int S, int nck, size_t n_chunks) {
+  const int nb8 = (B + 7) >> 3;
   for (size_t id = (size_t)blockIdx.x * blockDim.x + threadIdx.x; id < n_chunks; id += (size_t)gridDim.x * blockDim.x) {
     const size_t cell = id / 128; const int within = (int)(id % 128);        // 128 chunks of 16 bytes per 2 KB cell
-    const int c = (int)(cell % nck), h = (int)((cell / nck) % CS); const size_t lb = cell / ((size_t)nck * CS);     // lb = layer * B + image
+    const int i8 = (int)(cell % 8), c = (int)((cell / 8) % nck), h = (int)((cell / (8 * (size_t)nck)) % CS);
+    const size_t lb8 = cell / (8 * (size_t)nck * CS);                         // layer * nb8 + image block
+    const int l = (int)(lb8 / nb8), b = (int)(lb8 % nb8) * 8 + i8;
     const int which = within / 64, r = (within % 64) / 4, pc = within % 4;
     const int key = c * 16 + r;
     uint4 v = make_uint4(0u, 0u, 0u, 0u);
-    if (key < S) v = ckv[((lb * S + key) * (2 * DM) + which * DM + h * HD) / 8 + (pc ^ ((r >> 1) & 3))];
+    if (key < S && b < B) v = ckv[((((size_t)l * B + b) * S + key) * (2 * DM) + which * DM + h * HD) / 8 + (pc ^ ((r >> 1) & 3))];
     out[id] = v;
   }
 }
@@ -1100,7 +1113,7 @@ int decode_cluster_pack(mdc_model* m, void* out, cudaStream_t s) {
 size_t decode_cluster_ckv_pack_bytes(const mdc_model* m, int B) {
   if (!geometry_ok(m->d)) return 0;
   const int nck = (m->d.n_patches + 15) / 16;
-  return (size_t)m->d.dec_layers * B * CS * nck * 2048;
+  return (size_t)m->d.dec_layers * ((B + 7) / 8) * 8 * CS * nck * 2048;      // images padded to blocks of 8
 }
 
 int decode_cluster_ckv_pack(mdc_model* m, const void* ckv_plain, int B, void* out, cudaStream_t s) {

@@ -140,7 +140,7 @@ def decoder_stack(sd, x, mem, tokens, cfg: OracleCfg, prefix="decoder.decoder.la
     """x (B,L,d) embedded targets, mem (B,S,d) memory WITH encoder_pos_embed added.
     Mask = causal(-inf above diag) + 1.0 at PAD keys (utils.py:7-12,26-30; Q7)."""
     B, L, d = x.shape
-    causal = torch.full((L, L), float("-inf"), dtype=x.dtype).triu(1)
+    causal = torch.full((L, L), float("-inf"), dtype=x.dtype, device=x.device).triu(1)
     padbias = (tokens == cfg.pad_idx).to(x.dtype)[:, None, None, :]      # (B,1,1,L) added to keys
     bias = causal[None, None] + padbias
     for i in range(_num_dec_layers(sd, prefix)):
@@ -160,13 +160,13 @@ def decoder_predict(sd, encoder_out, tgt, cfg: OracleCfg):
     """Decoder.predict, model.py:92-127: pad to max_len-1 with PAD, run all positions,
     prepend a constant row of float(bos_idx), drop the last row."""
     B, L = tgt.shape
-    pad = torch.full((B, cfg.max_len - 1 - L), cfg.pad_idx, dtype=tgt.dtype)
+    pad = torch.full((B, cfg.max_len - 1 - L), cfg.pad_idx, dtype=tgt.dtype, device=tgt.device)
     tokens = torch.cat([tgt, pad], dim=1)
     x = sd["decoder.embedding.weight"][tokens] + sd["decoder.decoder_pos_embed"]
     mem = encoder_out + sd["decoder.encoder_pos_embed"]
     y = decoder_stack(sd, x, mem, tokens, cfg)
     out = y @ sd["decoder.output.weight"].T + sd["decoder.output.bias"]
-    bos = torch.full((B, 1, out.shape[-1]), float(cfg.bos_idx), dtype=out.dtype)
+    bos = torch.full((B, 1, out.shape[-1]), float(cfg.bos_idx), dtype=out.dtype, device=out.device)
     return torch.cat([bos, out[:, :-1]], dim=1)
 
 
@@ -190,7 +190,7 @@ def interp_pos_embed(pos, length):
 def decoder_forward(sd, encoder_out, tgt, cfg: OracleCfg):
     """Decoder.forward, model.py:58-88: prepend BOS, interpolate pos-embed, return (B,L+1,V)."""
     B = tgt.shape[0]
-    tokens = torch.cat([torch.full((B, 1), cfg.bos_idx, dtype=tgt.dtype), tgt], dim=1)
+    tokens = torch.cat([torch.full((B, 1), cfg.bos_idx, dtype=tgt.dtype, device=tgt.device), tgt], dim=1)
     pos = interp_pos_embed(sd["decoder.decoder_pos_embed"], tokens.shape[1])
     x = sd["decoder.embedding.weight"][tokens] + pos
     mem = encoder_out + sd["decoder.encoder_pos_embed"]
@@ -277,7 +277,7 @@ def generate(sd, image, cfg: OracleCfg, max_len=50, top_k=0, top_p=1.0, uniforms
     """generate(), inference_p.py:69-90, with the Q5 row selection (`predict(...)[:, L]`).
     recompute_encoder=True reproduces the reference's per-step encoder pass (Q9) for timing."""
     B = image.shape[0]
-    toks = torch.full((B, 1), cfg.bos_idx, dtype=torch.long)
+    toks = torch.full((B, 1), cfg.bos_idx, dtype=torch.long, device=image.device)
     confs, all_logits = [], []
     enc = None if recompute_encoder else encoder_forward(sd, image, cfg)
     for i in range(max_len):
