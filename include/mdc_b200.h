@@ -71,6 +71,7 @@ int64_t mdc_ctx_launch_count(const mdc_ctx* ctx);
  * memory (torch functional.py multi_head_attention_forward, reached from model.py:110-113).
  *   A [M,K] row-major (lda elements), W [N,K] row-major (nn.Linear layout), bias f32 [N] or NULL.
  *   dtype: MDC_BF16 -> A,W bf16, tcgen05.mma kind::f16 with fp32 TMEM accumulators, TMA-fed;
+ *          MDC_F16  -> A,W and D IEEE half on the same kernel (bias / bias+ReLU epilogues only: the decoder prefill);
  *          MDC_F32  -> A,W f32, FFMA with fp32 accumulation in K order (the token-exact path).
  *   D is `dtype` for BIAS/GELU/RELU; for LS_RESIDUAL / PATCH the output is the f32 stream R.
  *   aux0: gamma f32[N] (LS_RESIDUAL) or pos f32[period,N] (PATCH); period: PATCH only.
@@ -233,6 +234,19 @@ int mdc_decode_pack(mdc_model* m, void* packed, void* stream);
 size_t mdc_kv_page_bytes(const mdc_model* m);
 /* steps t = t_begin .. t_end-1, back to back on `stream`, no host synchronisation inside. */
 int mdc_decode_steps(mdc_model* m, const mdc_decode_state* st, int t_begin, int t_end, void* stream);
+
+/* ---- teacher-forced decoder pass over all positions at once (Decoder.forward model.py:58-88, Decoder.predict model.py:92-127) ----
+ * tokens int32 [B, tokens_ld] (first n columns: the target sequence as the reference builds it -- BOS-prepended for forward, PAD-padded
+ * to max_len-1 for predict); pos f32 [n, dim] positional rows (NULL = decoder_pos_embed, n <= max_pos; forward passes the
+ * interpolated table, model.py:64-68); cross_kv from mdc_cross_kv_build.  Every layer runs over the B*n rows in parallel:
+ * tcgen05 GEMMs on the fp16 decode-loop weights, causal self-attention with the reference's float PAD-key mask (+1.0, utils.py:26-30),
+ * cross-attention over the resident cross-K/V, fused residual + LayerNorm; then the vocabulary head.
+ * logits f32 [B, logits_ld, vocab]: row (i + row_offset) receives the logits of position i for i < n_out (predict: row_offset 1,
+ * n_out n-1; forward: 0, n).  mdc_decoder_prefill_workspace_bytes() is 0 when the geometry is not covered (fp32 precision,
+ * head width != 32, ...): the caller then runs mdc_decode_steps in teacher-forced mode, which computes the same logits step by step. */
+size_t mdc_decoder_prefill_workspace_bytes(const mdc_model* m, int B, int n);
+int mdc_decoder_prefill(mdc_model* m, const int32_t* tokens, int tokens_ld, int B, int n, const float* pos, const void* cross_kv,
+                        float* logits, int logits_ld, int row_offset, int n_out, void* workspace, size_t workspace_bytes, void* stream);
 
 /* (d) head + select as a stand-alone op: logits f32 [B,V] -> token, max prob, probability of the selected token.
  * greedy: argmax(softmax(logits)) = first max index (inference_p.py:77);

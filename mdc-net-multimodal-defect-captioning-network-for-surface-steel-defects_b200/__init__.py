@@ -15,9 +15,11 @@ from .iou import (bbox_iou, calculate_batch_iou, calculate_batch_max_iou, calcul
                   calculate_batch_max_iou_masked, giou_pairwise, giou_loss_with_scores, calculate_iou, iou_loss)
 from .kvcache import PagedKVCache, PageAllocator
 from . import parallel
+from . import metrics
+from .metrics import MeanAveragePrecision, calculate_bleu_scores
 from . import _lib
 
 __all__ = ["CFG", "Tokenizer", "top_k_sampling", "top_k_sampling_with_scores_2d", "Encoder", "Decoder", "EncoderDecoder", "Engine", "decode_options", "AxialAttention", "axial_model",
            "generate", "postprocess", "postprocess_with_captions", "preprocess_gray", "preprocess_bgr", "GenerationPipeline", "generate_stream", "bbox_iou", "calculate_batch_iou", "calculate_batch_max_iou",
            "calculate_batch_max_iou_torchvision", "calculate_batch_max_iou_masked", "giou_pairwise",
-           "giou_loss_with_scores", "calculate_iou", "iou_loss", "PagedKVCache", "PageAllocator", "parallel"]
+           "giou_loss_with_scores", "calculate_iou", "iou_loss", "PagedKVCache", "PageAllocator", "parallel", "metrics", "MeanAveragePrecision", "calculate_bleu_scores"]

@@ -91,6 +91,8 @@ SIGNATURES = {
     "mdc_decode_pack": (_I, [_P, _P, _P]),
     "mdc_kv_page_bytes": (_SZ, [_P]),
     "mdc_decode_steps": (_I, [_P, C.POINTER(DecodeState), _I, _I, _P]),
+    "mdc_decoder_prefill_workspace_bytes": (_SZ, [_P, _I, _I]),
+    "mdc_decoder_prefill": (_I, [_P, _P, _I, _I, _I, _P, _P, _P, _I, _I, _I, _P, _SZ, _P]),
     "mdc_select": (_I, [_P, _P, _L, _I, _I, _I, _F, _P, _P, _P, _P, _P]),
     "mdc_axial_workspace_bytes": (_SZ, [_P, _I, _I]),
     "mdc_axial_attention": (_I, [_P, _P, _I, _I, _I, _P, _P, _SZ, _P]),

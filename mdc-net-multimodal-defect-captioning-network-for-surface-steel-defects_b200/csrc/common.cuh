@@ -120,7 +120,7 @@ int gemm_simt_launch(mdc_ctx* ctx, int dtype, int epilogue, const void* A, int64
                      cudaStream_t s);
 int gemm_tc_launch(mdc_ctx* ctx, int epilogue, const void* A, int64_t lda, const void* W, int64_t ldw,
                    void* D, int64_t ldd, const float* bias, const float* aux0, int period, int M, int N, int K,
-                   cudaStream_t s);
+                   cudaStream_t s, int f16 = 0);
 int gemm_tc_supported(int M, int N, int K, int64_t lda, int64_t ldw);
 void gemm_tc_ctx_destroy(mdc_ctx* ctx);
 int mdc_make_tmap_2d(mdc_ctx* ctx, const void* ptr, int64_t rows, int64_t cols, int64_t ld, int box_cols, int box_rows, int swizzle_mode, void* out_map);

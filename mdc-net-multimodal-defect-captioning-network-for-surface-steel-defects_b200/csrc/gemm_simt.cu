@@ -133,12 +133,16 @@ extern "C" int mdc_gemm(mdc_ctx* ctx, int dtype, int epilogue, const void* A, in
                         void* stream) {
   MDC_CHECK_ARG(ctx && A && W && D);
   MDC_CHECK_DEVICE(ctx);
-  MDC_CHECK_ARG(dtype == MDC_F32 || dtype == MDC_BF16);
+  MDC_CHECK_ARG(dtype == MDC_F32 || dtype == MDC_BF16 || dtype == MDC_F16);
   MDC_CHECK_ARG(M >= 0 && N > 0 && K > 0);
   if (epilogue == MDC_EPI_LS_RESIDUAL) MDC_CHECK_ARG(aux0 != nullptr);
   if (epilogue == MDC_EPI_PATCH) MDC_CHECK_ARG(aux0 != nullptr && period > 0);
   if (M == 0) return 0;
   cudaStream_t s = (cudaStream_t)stream;
+  if (dtype == MDC_F16) {      // IEEE-half operands and outputs: tensor-core kernel only (bias / bias+ReLU epilogues)
+    MDC_CHECK_ARG(gemm_tc_supported(M, N, K, lda, ldw));
+    return gemm_tc_launch(ctx, epilogue, A, lda, W, ldw, D, ldd, bias, aux0, period, M, N, K, s, 1);
+  }
   if (dtype == MDC_BF16 && !ctx->gemm_backend_simt && gemm_tc_supported(M, N, K, lda, ldw))
     return gemm_tc_launch(ctx, epilogue, A, lda, W, ldw, D, ldd, bias, aux0, period, M, N, K, s);
   return gemm_simt_launch(ctx, dtype, epilogue, A, lda, W, ldw, D, ldd, bias, aux0, period, M, N, K, s);

@@ -90,6 +90,11 @@ __device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, ui
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 __device__ __forceinline__ uint32_t pack2_bf16(float a, float b) { __nv_bfloat162 h = __floats2bfloat162_rn(a, b); return *reinterpret_cast<uint32_t*>(&h); }
+// IEEE half outputs (the decoder prefill path): clamped to the finite range first
+__device__ __forceinline__ uint32_t pack2_f16(float a, float b) {
+  __half2 h = __floats2half2_rn(fminf(fmaxf(a, -65504.f), 65504.f), fminf(fmaxf(b, -65504.f), 65504.f)); return *reinterpret_cast<uint32_t*>(&h);
+}
+template <bool F16> __device__ __forceinline__ uint32_t pack2_16(float a, float b) { return F16 ? pack2_f16(a, b) : pack2_bf16(a, b); }
 __device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
@@ -120,9 +125,9 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
   d |= (uint64_t)2 << 61;                          // layout type SWIZZLE_128B
   return d;
 }
-// kind::f16: D=f32 (bits 4-5 =1), A=B=bf16 (bits 7-9, 10-12 = 1), both K-major, N>>3 at 17, M>>4 at 24
-__host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+// kind::f16: D=f32 (bits 4-5 =1), A and B formats at bits 7-9 / 10-12 (0 = fp16, 1 = bf16), both K-major, N>>3 at 17, M>>4 at 24
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, bool f16 = false) {
+  return (1u << 4) | ((f16 ? 0u : 1u) << 7) | ((f16 ? 0u : 1u) << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
 struct EpiArgs {
@@ -154,7 +159,9 @@ __device__ __forceinline__ void gelu2(float x0, float x1, float& y0, float& y1) 
   y0 = fmaf(h0, e0, h0); y1 = fmaf(h1, e1, h1);
 }
 
-template <int BN, int EPI, int EW>
+// F16: A, W and the 16-bit outputs are IEEE half instead of bf16 (same bytes, same tensor-core rate, 11 significant bits: the
+// decoder's teacher-forced prefill runs on the fp16 decode-loop weights -- DESIGN.md precision policy)
+template <int BN, int EPI, int EW, bool F16 = false>
 __global__ void __launch_bounds__(64 + EW * 32, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_d,
                EpiArgs ep, int M, int N, int K) {
@@ -213,7 +220,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
-    constexpr uint32_t idesc = make_idesc(BLOCK_M, BN);
+    constexpr uint32_t idesc = make_idesc(BLOCK_M, BN, F16);
     int stage = 0; uint32_t phase = 0; int iter = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++iter) {
       const int as = iter & 1; const uint32_t aphase = (iter >> 1) & 1;
@@ -333,7 +340,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             } else {
               const int c = j >> 3;
               const int sw = (ROWB == 128) ? (lane & 7) : ((lane >> 1) & 3);
-              sts128(row_s + ((c ^ sw) << 4), pack2_bf16(o[0], o[1]), pack2_bf16(o[2], o[3]), pack2_bf16(o[4], o[5]), pack2_bf16(o[6], o[7]));
+              sts128(row_s + ((c ^ sw) << 4), pack2_16<F16>(o[0], o[1]), pack2_16<F16>(o[2], o[3]), pack2_16<F16>(o[4], o[5]), pack2_16<F16>(o[6], o[7]));
             }
           }
           fence_async_smem();
@@ -415,14 +422,14 @@ int make_out_tmap(mdc_ctx* ctx, const void* ptr, int64_t rows, int64_t cols, int
   return 0;
 }
 
-template <int BN, int EPI>
+template <int BN, int EPI, bool F16 = false>
 int launch_bn_epi(mdc_ctx* ctx, const CUtensorMap& ma, const CUtensorMap& mw, const EpiArgs& ep, int M, int N, int K, cudaStream_t s) {
   constexpr int EW = (BN == 256 && EPI == MDC_EPI_BIAS_GELU) ? 16 : 8;     // A/B on one box: fc1 34.0 -> 31.6 us; bias-only epilogues lose 3 %
   using C = Cfg<BN, EW>;
   static bool attr_set[MDC_MAX_DEVICES];      // the dynamic-smem opt-in is a per-device attribute of this instantiation
   if (ctx->device < 0 || ctx->device >= MDC_MAX_DEVICES) MDC_FAIL(-2, "device index %d out of range", ctx->device);
   if (!attr_set[ctx->device]) {
-    MDC_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
+    MDC_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI, EW, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
     attr_set[ctx->device] = true;
   }
   int tiles = ((M + BLOCK_M - 1) / BLOCK_M) * ((N + BN - 1) / BN);
@@ -434,7 +441,7 @@ int launch_bn_epi(mdc_ctx* ctx, const CUtensorMap& ma, const CUtensorMap& mw, co
     const int box_cols = f32 ? 32 : ((BN / (EW / 4) >= 64 && EW == 8) ? 64 : 32);
     MDC_TRY(make_out_tmap(ctx, ep.D, M, N, ep.ldd, f32, box_cols, &md));
   }
-  gemm_tc_kernel<BN, EPI, EW><<<grid, C::kThreads, C::kSmemBytes, s>>>(ma, mw, md, ep, M, N, K);
+  gemm_tc_kernel<BN, EPI, EW, F16><<<grid, C::kThreads, C::kSmemBytes, s>>>(ma, mw, md, ep, M, N, K);
   MDC_LAUNCH_CHECK(ctx);
   return 0;
 }
@@ -451,6 +458,15 @@ int launch_bn(mdc_ctx* ctx, const CUtensorMap& ma, const CUtensorMap& mw, const 
   MDC_FAIL(-2, "gemm: unknown epilogue %d", ep.epilogue);
 }
 
+template <int BN>
+int launch_bn_f16(mdc_ctx* ctx, const CUtensorMap& ma, const CUtensorMap& mw, const EpiArgs& ep, int M, int N, int K, cudaStream_t s) {
+  switch (ep.epilogue) {       // the epilogues the decoder prefill uses
+    case MDC_EPI_BIAS: return launch_bn_epi<BN, MDC_EPI_BIAS, true>(ctx, ma, mw, ep, M, N, K, s);
+    case MDC_EPI_BIAS_RELU: return launch_bn_epi<BN, MDC_EPI_BIAS_RELU, true>(ctx, ma, mw, ep, M, N, K, s);
+  }
+  MDC_FAIL(-2, "gemm (fp16 operands): epilogue %d is not available, only MDC_EPI_BIAS / MDC_EPI_BIAS_RELU", ep.epilogue);
+}
+
 }  // namespace
 
 int gemm_tc_supported(int M, int N, int K, int64_t lda, int64_t ldw) {
@@ -459,7 +475,7 @@ int gemm_tc_supported(int M, int N, int K, int64_t lda, int64_t ldw) {
 }
 
 int gemm_tc_launch(mdc_ctx* ctx, int epilogue, const void* A, int64_t lda, const void* W, int64_t ldw, void* D, int64_t ldd,
-                   const float* bias, const float* aux0, int period, int M, int N, int K, cudaStream_t s) {
+                   const float* bias, const float* aux0, int period, int M, int N, int K, cudaStream_t s, int f16) {
   MDC_CHECK_ARG(((uintptr_t)A & 15) == 0 && ((uintptr_t)W & 15) == 0 && ((uintptr_t)D & 15) == 0);
   MDC_CHECK_ARG(ldd % 8 == 0);
   // tile width: the widest tile that still gives every SM one tile (128 x 256 tiles need 1/3 less operand traffic per flop than
@@ -473,6 +489,11 @@ int gemm_tc_launch(mdc_ctx* ctx, int epilogue, const void* A, int64_t lda, const
   MDC_TRY(get_tmap(ctx, A, M, K, lda, BLOCK_M, &ma));
   MDC_TRY(get_tmap(ctx, W, N, K, ldw, bn, &mw));
   EpiArgs ep{D, ldd, bias, aux0, period, epilogue};
+  if (f16) {
+    if (bn == 256) return launch_bn_f16<256>(ctx, ma, mw, ep, M, N, K, s);
+    if (bn == 128) return launch_bn_f16<128>(ctx, ma, mw, ep, M, N, K, s);
+    return launch_bn_f16<64>(ctx, ma, mw, ep, M, N, K, s);
+  }
   if (bn == 256) return launch_bn<256>(ctx, ma, mw, ep, M, N, K, s);
   if (bn == 128) return launch_bn<128>(ctx, ma, mw, ep, M, N, K, s);
   return launch_bn<64>(ctx, ma, mw, ep, M, N, K, s);

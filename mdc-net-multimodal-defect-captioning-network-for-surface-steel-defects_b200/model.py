@@ -99,8 +99,9 @@ class VisionTransformerParams(_Holder):
 
 # Decode-kernel launch options (mdc_decode_state.images_per_cluster / ctas_per_sm / per_op_kernels).  None of them changes a
 # result bit (tests/test_gpu_model.py); they trade latency of one batch against SM-time per batch, and `per_op_kernels` lets the
-# parity tests run the per-operation kernels where the fused cluster kernel would be picked.
-_DECODE_OPTIONS = {"images_per_cluster": 0, "ctas_per_sm": 0, "per_op_kernels": False}
+# parity tests run the per-operation kernels where the fused cluster kernel would be picked; `prefill` = False makes
+# forward() / predict() run the autoregressive kernels teacher-forced, step by step, instead of the all-positions prefill pass.
+_DECODE_OPTIONS = {"images_per_cluster": 0, "ctas_per_sm": 0, "per_op_kernels": False, "prefill": True}
 
 
 class decode_options:
@@ -442,9 +443,22 @@ class Decoder(nn.Module, _EngineOwner):
 
     # -- shared driver ------------------------------------------------------------------------
     def _run_forced(self, eng, memory, tokens_i32, n_steps, out_rows, row_offset, pos_override=None, x_override=None):
-        B = tokens_i32.shape[0]
+        """Teacher-forced logits of positions [0, n_steps) into rows [row_offset, row_offset + n_steps) of a (B, out_rows, V) tensor.
+        Default: ONE pass over all positions (mdc_decoder_prefill: GEMMs over B*n rows + causal attention); where that does not
+        cover the model (fp32 token-exact mode, other geometries, the axial front end's precomputed embeddings) or with
+        decode_options(prefill=False): the autoregressive kernels, step by step, on the same tokens."""
+        B, n = tokens_i32.shape
         ckv = eng.cross_kv(memory)
         logits = torch.empty((B, out_rows, self.vocab_size), dtype=torch.float32, device=eng.device)
+        ws_bytes = 0
+        if x_override is None and _DECODE_OPTIONS["prefill"] and not _DECODE_OPTIONS["per_op_kernels"]:
+            ws_bytes = eng.lib.mdc_decoder_prefill_workspace_bytes(eng.handle, B, n)
+        if ws_bytes:
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=eng.device)
+            with torch.cuda.device(eng.device):
+                L.check(eng.lib.mdc_decoder_prefill(eng.handle, L.ptr(tokens_i32), tokens_i32.shape[1], B, n, L.ptr(pos_override), L.ptr(ckv),
+                                                    L.ptr(logits), out_rows, row_offset, n_steps, L.ptr(ws), ws_bytes, L.stream_ptr(eng.device)))
+            return logits
         eng.decode(ckv, tokens_i32, 0, n_steps, max_tokens=max(n_steps, 1), forced=True, logits=logits,
                    logits_row_offset=row_offset, pos_override=pos_override, x_override=x_override)
         return logits

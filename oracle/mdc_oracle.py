@@ -545,3 +545,65 @@ def synth_bgr_u8(B, h=260, w=300, seed=99):
 
 def to_dtype(sd, dtype):
     return {k: (v.to(dtype) if v.is_floating_point() else v) for k, v in sd.items()}
+
+
+# ----------------------------------------------------------------------------------------
+# detection metrics.  torchmetrics / pycocotools / nltk are absent here and not vendored by the reference
+# (train_val_epoch.py:12, utils.py:3): restated from their published algorithms -- PARITY UNPINNED.
+# ----------------------------------------------------------------------------------------
+def _iou_f64(a, b):
+    w = min(a[2], b[2]) - max(a[0], b[0]); h = min(a[3], b[3]) - max(a[1], b[1])
+    if w <= 0 or h <= 0:
+        return 0.0
+    inter = w * h
+    return inter / ((a[2] - a[0]) * (a[3] - a[1]) + (b[2] - b[0]) * (b[3] - b[1]) - inter)
+
+
+def mean_average_precision(preds, targets, iou_thresholds=(0.3,), max_det=100):
+    """torchmetrics MeanAveragePrecision(box_format='xyxy', iou_thresholds=[...]).compute()['map'] as the reference uses it
+    (train_val_epoch.py:205-231): pycocotools COCOeval evaluateImg (greedy matching per image and class in score order) +
+    accumulate (101 recall thresholds, area 'all', maxDets 100), mean over thresholds and classes with ground truth."""
+    classes = sorted({int(c) for t in targets for c in t["labels"].tolist()} | {int(c) for p in preds for c in p["labels"].tolist()})
+    rec_thrs = [i / 100.0 for i in range(101)]
+    vals = []
+    for thr in iou_thresholds:
+        for c in classes:
+            dets, npig = [], 0
+            for p, t in zip(preds, targets):
+                gts = [[float(v) for v in b] for b, l in zip(t["boxes"].tolist(), t["labels"].tolist()) if int(l) == c]
+                npig += len(gts)
+                d = [([float(v) for v in b], float(s)) for b, s, l in zip(p["boxes"].tolist(), p["scores"].tolist(), p["labels"].tolist()) if int(l) == c]
+                d = sorted(d, key=lambda x: -x[1])[:max_det]          # python's sort is stable, like numpy mergesort
+                taken = [False] * len(gts)
+                for box, score in d:
+                    best, m = min(thr, 1 - 1e-10), -1
+                    for j, g in enumerate(gts):
+                        if taken[j]:
+                            continue
+                        v = _iou_f64(box, g)
+                        if v < best:
+                            continue
+                        best, m = v, j
+                    if m >= 0:
+                        taken[m] = True
+                    dets.append((score, m >= 0))
+            if npig == 0:
+                continue
+            order = sorted(range(len(dets)), key=lambda i: -dets[i][0])
+            tp = fp = 0.0
+            rc, pr = [], []
+            for i in order:
+                if dets[i][1]:
+                    tp += 1
+                else:
+                    fp += 1
+                rc.append(tp / npig); pr.append(tp / (fp + tp + np.spacing(1)))
+            for i in range(len(pr) - 1, 0, -1):
+                if pr[i] > pr[i - 1]:
+                    pr[i - 1] = pr[i]
+            q = []
+            for r in rec_thrs:
+                k = next((i for i, x in enumerate(rc) if x >= r), None)
+                q.append(pr[k] if k is not None else 0.0)
+            vals.append(sum(q) / len(q))
+    return sum(vals) / len(vals) if vals else -1.0

@@ -107,6 +107,32 @@ def test_bf16_logits_within_contract(model_p, x2, golden):
     assert err2 <= BF16_MAXABS and G.cos(step_logits, g["logits"]) >= BF16_COS
 
 
+def test_prefill_forward_and_predict_bf16_vs_reference_golden(model_p, x2, golden):
+    """forward() (BOS prepend + interpolated positional table, model.py:58-88) and predict() through the
+    all-positions prefill pass against the unmodified reference's outputs, PAD-in-prefix (Q7) included; and its cost at B = 64."""
+    g = golden("case_P_gamma.pt")
+    model_p.set_precision("bf16")
+    pred = model_p.predict(x2, g["prefix"].to(DEV))
+    fwd = model_p(x2, g["prefix"][:, 1:].to(DEV))
+    assert pred.shape == (2, 99, 305) and torch.all(pred[:, 0] == 300.0) and fwd.shape == (2, 4, 305)
+    ep = (pred.cpu()[:, 1:] - g["predict"][:, 1:]).abs().max().item(); ef = (fwd.cpu() - g["forward"]).abs().max().item()
+    print(f"prefill bf16: predict max|d| = {ep:.3e}, forward max|d| = {ef:.3e}")
+    assert ep <= BF16_MAXABS and ef <= BF16_MAXABS and G.cos(pred.cpu()[:, 1:], g["predict"][:, 1:]) >= BF16_COS
+    with M.decode_options(prefill=False):
+        fwd_s = model_p(x2, g["prefix"][:, 1:].to(DEV))
+    assert (fwd_s - fwd).abs().max().item() < 1.5e-2
+    x = cases.images(64, seed=3).to(DEV)
+    toks = torch.randint(0, 300, (64, 99), device=DEV); toks[:, 0] = 300
+    eng = model_p._engine(torch.device(DEV))
+    _, memory = eng.encode(x, want_enc_out=False, want_memory=True)
+    for opts in ({"prefill": True}, {"prefill": False}):
+        with M.decode_options(**opts):
+            model_p.decoder._predict_with(eng, memory, toks); torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); model_p.decoder._predict_with(eng, memory, toks); b.record(); torch.cuda.synchronize()
+        print(f"predict() decoder part at B = 64, 99 positions, {opts}: {a.elapsed_time(b):.3f} ms (incl. cross-K/V build)")
+
+
 def test_bf16_contract_at_the_bench_operating_point():
     """The kernel instantiation the headline runs -- 16 images per cluster, full-length decode -- against the CPU oracle directly:
     B = 16 images, teacher-forced along the ORACLE's own greedy trajectory over the whole positional table (predict() rows 1..98 =
@@ -116,12 +142,12 @@ def test_bf16_contract_at_the_bench_operating_point():
     x = cases.images(16, seed=404)
     want_toks, _, want_logits = O.generate(sd, x, cfg, max_len=98, return_logits=True)       # (16, 99) tokens, (16, 98, V) logits
     m = m.to(DEV).set_precision("bf16")
-    for opts in ({"images_per_cluster": 16}, {"images_per_cluster": 8, "ctas_per_sm": 2}):
-        with M.decode_options(**opts):
+    for opts in ({"images_per_cluster": 16, "prefill": False}, {"images_per_cluster": 8, "ctas_per_sm": 2, "prefill": False}, {"prefill": True}):
+        with M.decode_options(**opts):          # prefill = False: the autoregressive kernel, teacher-forced; True: the all-positions pass
             full = m.predict(x.to(DEV), want_toks[:, :98].to(DEV))
         got = full[:, 1:99].cpu()
         err, c = (got - want_logits).abs().max().item(), G.cos(got, want_logits)
-        print(f"bf16 fused kernel {opts} vs oracle, B=16, 98 steps: logits max|d| = {err:.3e}, cosine = {c:.6f}")
+        print(f"bf16 {opts} vs oracle, B=16, 98 positions: logits max|d| = {err:.3e}, cosine = {c:.6f}")
         assert err <= BF16_MAXABS and c >= BF16_COS, opts
 
 
@@ -206,8 +232,13 @@ def test_cluster_decode_kernel_matches_generic_kernels(model_p, golden, B, T):
     with M.decode_options(per_op_kernels=True):
         tg, _ = model_p.generate_tokens(x, T, use_graph=False)
         lg = model_p.predict(x, tg[:, :T].long())[:, 1:T + 1]
-    lc = model_p.predict(x, tg[:, :T].long())[:, 1:T + 1]
+    with M.decode_options(prefill=False):
+        lc = model_p.predict(x, tg[:, :T].long())[:, 1:T + 1]
     tc, _ = model_p.generate_tokens(x, T, use_graph=False)
+    lp = model_p.predict(x, tg[:, :T].long())[:, 1:T + 1]            # the all-positions prefill pass on the same tokens
+    perr = (lp - lc).abs().max().item()
+    print(f"prefill vs autoregressive kernel: B={B} T={T} max|dlogit| = {perr:.2e}")
+    assert perr < 1.5e-2
     err = (lg - lc).abs().max().item()
     mean = (lg - lc).abs().mean().item()
     agree = (tg == tc).float().mean().item()
@@ -231,8 +262,9 @@ def test_cluster_decode_16_images_per_cluster_is_bitwise_the_8_image_kernel(mode
         t, c = model_p.generate_tokens(x, T, use_graph=False)
         ts, cs = model_p.generate_tokens(x, T, top_k=5, uniforms=u, use_graph=False)
         return t, c, ts, cs, model_p.predict(x, t[:, :T].long())
-    want = run()
-    for opts in ({"images_per_cluster": 16}, {"images_per_cluster": 8, "ctas_per_sm": 2}):
+    with M.decode_options(prefill=False):
+        want = run()
+    for opts in ({"images_per_cluster": 16, "prefill": False}, {"images_per_cluster": 8, "ctas_per_sm": 2, "prefill": False}):
         with M.decode_options(**opts):
             got = run()
         for a, b in zip(got, want):
@@ -268,9 +300,13 @@ def test_cluster_decode_is_run_to_run_deterministic(model_p):
     model_p.set_precision("bf16")
     x = cases.images(64, seed=33).to(DEV)
     toks, confs = model_p.generate_tokens(x, 99, use_graph=False)
-    ref = model_p.predict(x, toks[:, :99].long())
+    with M.decode_options(prefill=False):
+        ref = model_p.predict(x, toks[:, :99].long())
+    pre = model_p.predict(x, toks[:, :99].long())                 # prefill pass: deterministic too
     for _ in range(5):
-        assert torch.equal(model_p.predict(x, toks[:, :99].long()), ref)
+        with M.decode_options(prefill=False):
+            assert torch.equal(model_p.predict(x, toks[:, :99].long()), ref)
+        assert torch.equal(model_p.predict(x, toks[:, :99].long()), pre)
         t2, c2 = model_p.generate_tokens(x, 99, use_graph=False)
         assert torch.equal(t2, toks) and torch.equal(c2, confs)
 

@@ -288,3 +288,51 @@ def test_top_k_sampling_helpers_against_oracle():
     probs = torch.softmax(filt, dim=-1)
     assert idx.shape == (64, 1) and idx.dtype == torch.int64 and torch.equal(idx.cpu().view(-1), want.view(-1)) and torch.equal(idx, idx1)
     assert (score.cpu().view(-1) - probs.gather(1, want.view(-1, 1)).view(-1)).abs().max().item() < 1e-6
+
+
+def _det_case(seed, B=40, classes=6):
+    g = torch.Generator().manual_seed(seed)
+    preds, targets = [], []
+    for i in range(B):
+        m = int(torch.randint(0, 6, (1,), generator=g))
+        gb = torch.rand(m, 4, generator=g) * 160; gb[:, 2:] = gb[:, :2] + 8 + torch.rand(m, 2, generator=g) * 56
+        gl = torch.randint(0, classes, (m,), generator=g)
+        n = int(torch.randint(0, 12, (1,), generator=g))
+        pb = torch.rand(n, 4, generator=g) * 160; pb[:, 2:] = pb[:, :2] + 8 + torch.rand(n, 2, generator=g) * 56
+        pl = torch.randint(0, classes, (n,), generator=g)
+        k = min(n, m)
+        if k:                                       # some predictions are jittered copies of ground-truth boxes (true positives)
+            pb[:k] = gb[:k] + torch.randn(k, 4, generator=g) * 6; pl[:k] = gl[:k]
+        ps = torch.rand(n, generator=g)
+        if n > 3:
+            ps[1] = ps[3]                           # a score tie: the stable order decides
+        preds.append({"boxes": pb, "scores": ps, "labels": pl}); targets.append({"boxes": gb, "labels": gl})
+    return preds, targets
+
+
+def test_map_matching_kernel_and_accumulation_against_the_restated_coco_evaluation():
+    """MeanAveragePrecision (train_val_epoch.py:205-231, iou_thresholds = [0.3]) -- batched matching kernel +
+    host accumulation against the oracle's plain-Python restatement of COCOeval (parity unpinned: torchmetrics is absent)."""
+    for seed in (1, 2, 3):
+        preds, targets = _det_case(seed)
+        m = M.MeanAveragePrecision(box_format="xyxy", iou_thresholds=[0.3], class_metrics=True).to(DEV)
+        for p, t in zip(preds, targets):
+            if p["scores"].nelement() == 0:        # the reference's empty-prediction form (train_val_epoch.py:219-225)
+                p = {"boxes": torch.empty((0, 4)), "scores": torch.empty((0,)), "labels": torch.empty((0,), dtype=torch.int64)}
+            m.update([p], [t])
+        got = m.compute()
+        want = O.mean_average_precision(preds, targets, iou_thresholds=(0.3,))
+        assert abs(got["map"].item() - want) < 1e-6, (seed, got["map"].item(), want)      # the result tensor is float32, like torchmetrics'
+        assert got["map_per_class"].numel() == got["classes"].numel()
+    # known answers: perfect predictions -> 1, disjoint predictions -> 0, several thresholds -> their mean
+    gb = torch.tensor([[0., 0, 10, 10], [20, 20, 40, 40]]); gl = torch.tensor([1, 2])
+    m = M.MeanAveragePrecision(iou_thresholds=[0.3]).to(DEV)
+    m.update([{"boxes": gb.clone(), "scores": torch.tensor([0.9, 0.8]), "labels": gl.clone()}], [{"boxes": gb, "labels": gl}])
+    assert abs(m.compute()["map"].item() - 1.0) < 1e-6
+    m = M.MeanAveragePrecision(iou_thresholds=[0.3]).to(DEV)
+    m.update([{"boxes": gb + 100, "scores": torch.tensor([0.9, 0.8]), "labels": gl.clone()}], [{"boxes": gb, "labels": gl}])
+    assert m.compute()["map"].item() == 0.0
+    preds, targets = _det_case(9)
+    m = M.MeanAveragePrecision(iou_thresholds=[0.3, 0.5, 0.75]).to(DEV)
+    m.update(preds, targets)
+    assert abs(m.compute()["map"].item() - O.mean_average_precision(preds, targets, iou_thresholds=(0.3, 0.5, 0.75))) < 1e-6

@@ -140,3 +140,19 @@ def test_preprocess_restatement_against_cv2_goldens(golden):
     for h, w, size, c in ((200, 200, 224, 1), (199, 201, 224, 3), (448, 448, 224, 3), (37, 53, 512, 1)):
         im = rng.integers(0, 256, (h, w) if c == 1 else (h, w, c), dtype=np.uint8)
         assert np.array_equal(O.cv2_resize_linear_u8(im, size, size), cv2.resize(im, (size, size), interpolation=cv2.INTER_LINEAR))
+
+
+def test_metric_restatements_known_answers():
+    """mAP / BLEU restatements (third-party arithmetic absent: parity unpinned) on answers known in closed form."""
+    import mdcnet_b200 as M
+    gb = torch.tensor([[0., 0, 10, 10], [20, 20, 40, 40]]); gl = torch.tensor([1, 2])
+    perfect = [{"boxes": gb.clone(), "scores": torch.tensor([0.9, 0.8]), "labels": gl.clone()}]
+    assert abs(O.mean_average_precision(perfect, [{"boxes": gb, "labels": gl}]) - 1.0) < 1e-12
+    # one true positive ranked below one false positive of the same class: precision 1/2 at every recall level
+    p = [{"boxes": torch.tensor([[100., 100, 110, 110], [0, 0, 10, 10]]), "scores": torch.tensor([0.9, 0.5]), "labels": torch.tensor([1, 1])}]
+    assert abs(O.mean_average_precision(p, [{"boxes": gb[:1], "labels": gl[:1]}]) - 0.5) < 1e-9
+    ref = "the surface shows a long scratch".split()
+    assert M.calculate_bleu_scores([ref], [ref]) == [1.0]
+    assert M.calculate_bleu_scores([ref], [["unrelated"]]) == [0.0]
+    got = M.calculate_bleu_scores([list("abcde")], [list("abxde")])[0]
+    assert abs(got - (0.8 * 0.5 * (0.1 / 3) * (0.1 / 2)) ** 0.25) < 1e-12           # method1: zero counts -> epsilon 0.1
