@@ -564,7 +564,7 @@ def mean_average_precision(preds, targets, iou_thresholds=(0.3,), max_det=100):
     (train_val_epoch.py:205-231): pycocotools COCOeval evaluateImg (greedy matching per image and class in score order) +
     accumulate (101 recall thresholds, area 'all', maxDets 100), mean over thresholds and classes with ground truth."""
     classes = sorted({int(c) for t in targets for c in t["labels"].tolist()} | {int(c) for p in preds for c in p["labels"].tolist()})
-    rec_thrs = [i / 100.0 for i in range(101)]
+    rec_thrs = np.linspace(0.0, 1.0, 101).tolist()        # COCOeval Params.recThrs: the linspace values, not i / 100
     vals = []
     for thr in iou_thresholds:
         for c in classes:
