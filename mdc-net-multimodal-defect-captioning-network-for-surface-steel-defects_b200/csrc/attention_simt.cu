@@ -191,6 +191,10 @@ int attn_tc_supported(int strip_len, int head_dim);
 int attn_tc_launch(mdc_ctx* ctx, const void* qkv, int64_t ld, void* out, int64_t ldo, int n_strips, int strip_len, int heads,
                    int head_dim, float scale, cudaStream_t s);
 
+int attn_umma_supported(int strip_len, int head_dim, int64_t ld, int64_t ldo);
+int attn_umma_launch(mdc_ctx* ctx, const void* qkv, int64_t ld, void* out, int64_t ldo, int n_strips, int strip_len, int heads, float scale,
+                     cudaStream_t s);
+
 extern "C" int mdc_strip_attention(mdc_ctx* ctx, int dtype, const void* qkv, int64_t ld_qkv, void* out, int64_t ld_out,
                                    int n_strips, int strip_len, int heads, int head_dim, float scale,
                                    int softmax_over_queries, void* stream) {
@@ -207,6 +211,10 @@ extern "C" int mdc_strip_attention(mdc_ctx* ctx, int dtype, const void* qkv, int
                             : launch_cols<bf16>(ctx, qkv, ld_qkv, out, ld_out, n_strips, strip_len, heads, head_dim, scale, s);
   }
   MDC_CHECK_ARG(n_strips <= 65535);
+  // bf16, head width 64: strips of up to 256 tokens (the ViT's 197) on tcgen05 / TMEM / TMA (attention_umma.cu); longer strips on the
+  // chunked mma.sync kernel (attention_tc.cu); everything else (fp32, other head widths) on the SIMT kernel
+  if (dtype == MDC_BF16 && !ctx->attn_backend_simt && attn_umma_supported(strip_len, head_dim, ld_qkv, ld_out) && ((uintptr_t)out & 15) == 0)
+    return attn_umma_launch(ctx, qkv, ld_qkv, out, ld_out, n_strips, strip_len, heads, scale, s);
   if (dtype == MDC_BF16 && !ctx->attn_backend_simt && attn_tc_supported(strip_len, head_dim))
     return attn_tc_launch(ctx, qkv, ld_qkv, out, ld_out, n_strips, strip_len, heads, head_dim, scale, s);
   return dtype == MDC_F32 ? launch_rows<float>(ctx, qkv, ld_qkv, out, ld_out, n_strips, strip_len, heads, head_dim, scale, s)
