@@ -16,10 +16,11 @@ the timed region); the default line carries short runs of both under "other_conf
   e2e     : the public streaming API generate_stream(model, pinned host batches, tokenizer, max_len): H2D of every batch and D2H of
             its results inside; e2e_gray_u8: the same from raw 200x200 u8 images (fused transform kernel on the device)
   serial  : one batch at a time (generate_tokens / generate), 256 MiB L2 flush between steps
-  roofline: the dominant kernel (fused decode loop) in the instantiation the headline runs (16 images per cluster), timed alone with
-            CUDA events: algorithmic bytes / time against the measured HBM peak; `serial` = the low-latency
-            instantiation generate() uses; `in_pipeline` = the same bytes over the pipelined step; roofline_gemm: mlp.fc1 against the
-            measured bf16 tensor peak
+  roofline: the dominant kernel (fused decode loop): algorithmic bytes of one batch / pipelined ms_per_step against the
+            measured HBM peak (up to four launches of the kernel share the GPU with the encoder inside the timed region);
+            `launch_alone` = the same launch (16 images per cluster, 32 SMs) timed alone with CUDA events, `serial` = the low-latency
+            instantiation generate() uses, `full_gpu` = a B = 256 launch that fills the GPU with decode clusters;
+            roofline_gemm: mlp.fc1 against the measured bf16 tensor peak
   cpu_baseline: the oracle port of the reference's own loop (encoder recomputed every step, model.py:177-181) on the host cores,
             bounded sample (N = 1 only); gpu_eager_baseline: the same restated algorithm as plain PyTorch eager bf16 on this GPU.
   --impl reference prints only the CPU arm (rank 0).
@@ -224,7 +225,7 @@ def ncu_traffic(name):
         return None
 
 
-def decode_launch_ms(model, x_dev, dev, T, ipc, top_k=0, reps=3):
+def decode_launch_ms(model, x_dev, dev, T, ipc, top_k=0, reps=3, cps=0):
     """One decode launch (T steps, B images) timed alone with CUDA events on the launching stream."""
     eng = model._engine(dev)
     _, memory = eng.encode(x_dev, want_enc_out=False, want_memory=True)
@@ -232,13 +233,13 @@ def decode_launch_ms(model, x_dev, dev, T, ipc, top_k=0, reps=3):
     Bn = x_dev.shape[0]
     tokens = torch.full((Bn, T + 1), 302, dtype=torch.int32, device=dev); tokens[:, 0] = 300
     uni = torch.rand((Bn, T), device=dev) if top_k else None
-    kv, scratch = eng.decode(ckv, tokens, 0, T, max_tokens=T, forced=False, images_per_cluster=ipc, top_k=top_k, uniforms=uni)
+    kv, scratch = eng.decode(ckv, tokens, 0, T, max_tokens=T, forced=False, images_per_cluster=ipc, ctas_per_sm=cps, top_k=top_k, uniforms=uni)
     torch.cuda.synchronize()
     best = None
     for _ in range(reps):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-        eng.decode(ckv, tokens, 0, T, max_tokens=T, forced=False, kv=kv, scratch=scratch, images_per_cluster=ipc, top_k=top_k, uniforms=uni)
+        eng.decode(ckv, tokens, 0, T, max_tokens=T, forced=False, kv=kv, scratch=scratch, images_per_cluster=ipc, ctas_per_sm=cps, top_k=top_k, uniforms=uni)
         b.record()
         torch.cuda.synchronize()
         ms = a.elapsed_time(b)
@@ -246,13 +247,15 @@ def decode_launch_ms(model, x_dev, dev, T, ipc, top_k=0, reps=3):
     return best
 
 
-def decode_roofline(model, x_dev, dev, peaks, T, S, ipc, top_k=0):
+def decode_roofline(model, x_dev, dev, peaks, T, S, ipc, top_k=0, cps=0):
     B = x_dev.shape[0]
-    ms = decode_launch_ms(model, x_dev, dev, T, ipc, top_k)
+    ms = decode_launch_ms(model, x_dev, dev, T, ipc, top_k, cps=cps)
     nbytes = decode_algorithmic_bytes(B, T, S)
     ach = nbytes / (ms / 1e3) / 1e9
-    inst = "16 images per 8-CTA cluster (two column blocks per pass: the instantiation the batch pipeline runs)" if ipc > 8 else \
-           "spread over as many clusters as fit (the low-latency instantiation generate() runs)"
+    n_cl = -(-B // (16 if ipc > 8 else (ipc or 5)))
+    inst = (f"16 images per 8-CTA cluster, two column blocks per pass (the instantiation the batch pipeline runs): {n_cl} clusters = {8 * n_cl} of 148 SMs" if ipc > 8 else
+            (f"compact layout, 8 images per cluster, two clusters per SM: {n_cl} clusters on {4 * n_cl} SMs" if cps == 2 else
+             "spread over as many clusters as fit, one CTA per SM (the low-latency instantiation generate() runs)"))
     return {"kernel": f"decode_fused_kernel, {inst}; one launch = {T} decode steps x 6 layers, B={B}, S={S}", "bound": "hbm", "achieved": ach,
             "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"], "traffic": ncu_traffic("decode16" if ipc > 8 else "decode"),
             "algorithmic_bytes_per_launch": nbytes, "ms_per_launch": ms, "ms_per_decode_token": ms / T,
@@ -473,13 +476,27 @@ def main():
            "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "bf16",
            "data": "synthetic", "config": cfg, "clocks": res["clocks"], "e2e": res["e2e"], "gpu_launches": res["gpu_launches"]}
     if args.config == 1:
-        roof = decode_roofline(model, xs_dev[0], dev, peaks, wl["T"], wl["S"], 16)
-        roof["serial"] = decode_roofline(model, xs_dev[0], dev, peaks, wl["T"], wl["S"], 0)
-        # the same bytes against the pipelined step (four decode kernels and an encoder share the GPU): the rate the decode loops sustain
-        # together inside the headline region
-        roof["in_pipeline"] = {"achieved": roof["algorithmic_bytes_per_launch"] / (res["ms_per_step"] / 1e3) / 1e9, "unit": "GB/s",
-                               "note": "algorithmic decode bytes of one batch / pipelined ms_per_step (decode kernels overlap each other and the encoder)"}
-        roof["in_pipeline"]["frac"] = roof["in_pipeline"]["achieved"] / peaks["hbm_gbs"]
+        # The dominant kernel is the fused decode loop.  In the timed region four of its launches (32 SMs each) and the encoder share the
+        # GPU, so the figure that belongs to the headline is the rate at which the decode loops TOGETHER move their algorithmic bytes:
+        # bytes of one batch / pipelined ms_per_step.  Beside it: the same launch timed alone (a 32-SM launch: its fraction of the
+        # whole GPU's HBM peak says how small a slice of the GPU one batch is given), the low-latency instantiation generate() runs,
+        # and a launch that fills the GPU with decode clusters (B = 256, two clusters per SM).
+        alone = decode_roofline(model, xs_dev[0], dev, peaks, wl["T"], wl["S"], 16)
+        nbytes = alone["algorithmic_bytes_per_launch"]
+        ach = nbytes / (res["ms_per_step"] / 1e3) / 1e9
+        roof = {"kernel": "decode_fused_kernel (one launch = 99 decode steps x 6 layers of one 64-image batch; 16 images per 8-CTA cluster) as the "
+                          "timed region runs it: up to four launches in flight next to the encoder of the following batches",
+                "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"], "traffic": alone["traffic"],
+                "algorithmic_bytes_per_launch": nbytes, "ms_per_launch": res["ms_per_step"],
+                "how": "algorithmic decode bytes of one batch (SURVEY 8d: cross-K/V + self-K/V + decode-touched weights + logits, 11.28 GB) / pipelined "
+                       "ms_per_step; CUDA events around the timed region; `traffic` = DRAM bytes of one launch from the committed ncu capture",
+                "peak_src": peaks["src"] + " HBM copy bandwidth",
+                "launch_alone": alone,
+                "serial": decode_roofline(model, xs_dev[0], dev, peaks, wl["T"], wl["S"], 0)}
+        x256 = torch.cat([xs_dev[i % len(xs_dev)] for i in range(4)], dim=0)
+        roof["full_gpu"] = decode_roofline(model, x256, dev, peaks, wl["T"], wl["S"], 8, cps=2)
+        del x256
+        roof["ms_per_decode_token"] = alone["ms_per_decode_token"]
         out.update({"ms_per_decode_token": roof["ms_per_decode_token"], "roofline": roof, "roofline_gemm": roofline_probe(M, dev, peaks, B),
                     "e2e_gray_u8": res["e2e_gray_u8"], "serial": res["serial"]})
         del model
