@@ -17,6 +17,7 @@
 #include <mutex>
 #include <unordered_map>
 #include <string.h>
+#include <stdlib.h>
 
 namespace {
 
@@ -132,7 +133,13 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N, bool f16 = false
 
 struct EpiArgs {
   void* D; int64_t ldd; const float* bias; const float* aux0; int period; int epilogue;
+  int dbg;   // developer build only (MDC_GEMM_DBG): 1 = no epilogue body, 2 = every load from tile (0,0), 4 = no loads, 8 = no MMAs
 };
+#ifdef MDC_DEVTOOLS
+#define GEMM_DBG(ep, bit) ((ep).dbg & (bit))
+#else
+#define GEMM_DBG(ep, bit) 0
+#endif
 
 // packed fp32 pairs (sm_100 FFMA2 / FMUL2 / FADD2): the epilogue polynomial runs on two columns per instruction
 __device__ __forceinline__ uint64_t pk2(float a, float b) { uint64_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
@@ -211,9 +218,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(smem_u32(&empty[stage]), phase ^ 1);
           const uint32_t fb = smem_u32(&full[stage]);
+          if (GEMM_DBG(ep, 4)) { mbar_arrive(fb); }
+          else {
           mbar_expect_tx(fb, C::kStageBytes);
-          tma_load_2d(&map_a, fb, smem_u32(smem_a + stage * C::kABytes), kb * BLOCK_K, m0);
-          tma_load_2d(&map_w, fb, smem_u32(smem_b + stage * C::kBBytes), kb * BLOCK_K, n0);
+          tma_load_2d(&map_a, fb, smem_u32(smem_a + stage * C::kABytes), GEMM_DBG(ep, 2) ? 0 : kb * BLOCK_K, GEMM_DBG(ep, 2) ? 0 : m0);
+          tma_load_2d(&map_w, fb, smem_u32(smem_b + stage * C::kBBytes), GEMM_DBG(ep, 2) ? 0 : kb * BLOCK_K, GEMM_DBG(ep, 2) ? 0 : n0);
+          }
           if (++stage == C::kStages) { stage = 0; phase ^= 1; }
         }
       }
@@ -233,6 +243,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         if (elect_one()) {
           const uint64_t adesc = make_smem_desc(smem_u32(smem_a + stage * C::kABytes));
           const uint64_t bdesc = make_smem_desc(smem_u32(smem_b + stage * C::kBBytes));
+          if (!GEMM_DBG(ep, 8))
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k)   // +32 B per UMMA_K inside the swizzle atom -> +2 in the >>4 address field
             umma_f16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
@@ -272,7 +283,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + as * BN + half * HALF_COLS;
       const float* sb = s_bias + as * BN + half * HALF_COLS;
       const float* sg = s_gamma + as * BN + half * HALF_COLS;
-      if constexpr (EPI == MDC_EPI_PATCH) {
+      if (GEMM_DBG(ep, 1)) {
+      } else if constexpr (EPI == MDC_EPI_PATCH) {
         // rows are re-mapped past each image's cls slot, so a 32-row box is not contiguous in the output: direct stores
         const bool row_ok = row < M;
         const int img = row / ep.period;
@@ -488,7 +500,10 @@ int gemm_tc_launch(mdc_ctx* ctx, int epilogue, const void* A, int64_t lda, const
   CUtensorMap ma, mw;
   MDC_TRY(get_tmap(ctx, A, M, K, lda, BLOCK_M, &ma));
   MDC_TRY(get_tmap(ctx, W, N, K, ldw, bn, &mw));
-  EpiArgs ep{D, ldd, bias, aux0, period, epilogue};
+  EpiArgs ep{D, ldd, bias, aux0, period, epilogue, 0};
+#ifdef MDC_DEVTOOLS
+  if (const char* e = getenv("MDC_GEMM_DBG")) ep.dbg = atoi(e);
+#endif
   if (f16) {
     if (bn == 256) return launch_bn_f16<256>(ctx, ma, mw, ep, M, N, K, s);
     if (bn == 128) return launch_bn_f16<128>(ctx, ma, mw, ep, M, N, K, s);

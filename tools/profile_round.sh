@@ -17,7 +17,7 @@ python bench.py --profile > $o/${tag}_plain_profile.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 800 --csv --log-file $o/${tag}_launches.csv python bench.py --profile > $o/${tag}_ncu_launch.log 2>&1
 python tools/gemm_probe.py 64 1 fc1 > $o/${tag}_plain_gemm.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:gemm_tc_kernel -c 1 -f -o $o/${tag}_gemm_fc1 python tools/gemm_probe.py 64 1 fc1 > $o/${tag}_ncu_gemm.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:attn_tc_kernel -c 1 -f -o $o/${tag}_attn python bench.py --profile > $o/${tag}_ncu_attn.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:attn_umma_kernel -c 1 -f -o $o/${tag}_attn python bench.py --profile > $o/${tag}_ncu_attn.log 2>&1
 python tools/decode_variants.py 99 64,0,0 > $o/${tag}_plain_dec.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:decode_fused_kernel -s 1 -c 1 -f -o $o/${tag}_decode python tools/decode_variants.py 99 64,0,0 > $o/${tag}_ncu_decode.log 2>&1
 python tools/decode_variants.py 99 64,16,0 > $o/${tag}_plain_dec16.log 2>&1 &&

@@ -7,7 +7,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "mdc-net-multimodal-defect-captioning-network-for-surface-steel-defects_b200", "libmdc_b200.so")
 rnd = sys.argv[1] if len(sys.argv) > 1 else "r1"
 KERNELS = [("gemm_tc_kernelILi256ELi1E", "gemm_tc_kernel<256, BIAS_GELU> (mlp.fc1)"), ("gemm_tc_kernelILi128ELi3E", "gemm_tc_kernel<128, LS_RESIDUAL> (attn.proj / mlp.fc2)"),
-           ("decode_fused_kernelILb0E", "decode_fused_kernel<false>"), ("attn_tc_kernelILi416ELi2E", "attn_tc_kernel<416,2>"),
+           ("decode_fused_kernelILb0E", "decode_fused_kernel<false>"), ("attn_umma_kernel", "attn_umma_kernel (ViT strip attention, tcgen05)"), ("prefill_attn_kernel", "prefill_attn_kernel"),
            ("layernorm_rows_kernelI13__nv_bfloat16Li4E", "layernorm_rows_kernel<bf16,4>"), ("iou_batch_kernel", "iou_batch_kernel"),
            ("decode_tokens_kernel", "decode_tokens_kernel")]
 KEY = ["UTCHMMA", "UTCQMMA", "UTCBAR", "UTCCP", "LDTM", "STTM", "UTMALDG", "UTMASTG", "UTMAREDG", "UTMAPF", "UBLKCP", "SYNCS", "HMMA", "LDSM", "FFMA2", "FMUL2",
