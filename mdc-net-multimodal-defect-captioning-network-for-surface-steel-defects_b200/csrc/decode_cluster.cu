@@ -302,6 +302,12 @@ __device__ __forceinline__ void attn_tile(const uint32_t (&kp)[N], const uint32_
       sc[n][2 * j + 1] = c[1] + d[1];
     }
   }
+  // Softmax against a REFERENCE maximum instead of the running one: the reference m is the maximum of the image's first tile and is
+  // only raised (with the usual rescale of the state) when some score exceeds it by more than 64 log2-units -- p = 2^(s - m) then
+  // stays below 2^64, far inside fp32/bf16 range, and the final o / l is the same quotient.  The common path per tile has no
+  // cross-lane maximum (two shuffles), no rescale factor and no state rescale on the dependent chain ldmatrix -> MMA -> ex2 -> MMA; the
+  // guard costs one warp vote per image.  Every image decides alone (its own vote), so an image's arithmetic does not depend on the
+  // image it shares the warp with (the instantiations stay bitwise equal).
   float mx[N];
 #pragma unroll
   for (int n = 0; n < N; ++n) {
@@ -314,24 +320,28 @@ __device__ __forceinline__ void attn_tile(const uint32_t (&kp)[N], const uint32_
     mx[n] = fmaxf(fmaxf(sc[n][0], sc[n][1]), fmaxf(sc[n][2], sc[n][3]));
   }
 #pragma unroll
-  for (int n = 0; n < N; ++n) mx[n] = fmaxf(mx[n], __shfl_xor_sync(0xffffffffu, mx[n], 1));
+  for (int n = 0; n < N; ++n) {
+    // first tile: m = -inf, and the tile holds a valid key (key0 < nkeys), so some lane sees a finite score and votes
+    if (__any_sync(0xffffffffu, mx[n] > st[n].m + 64.0f)) {
+      float t = fmaxf(mx[n], __shfl_xor_sync(0xffffffffu, mx[n], 1));
+      t = fmaxf(t, __shfl_xor_sync(0xffffffffu, t, 2));          // the quad holds all 16 keys of the tile: the tile maximum, in every lane
+      const float m_new = fmaxf(st[n].m, t);
+      const float sf = ex2_approx(st[n].m - m_new);              // first tile: 2^-inf = 0 on a zero state
+      st[n].m = m_new;
+      st[n].ls *= sf;
 #pragma unroll
-  for (int n = 0; n < N; ++n) mx[n] = fmaxf(mx[n], __shfl_xor_sync(0xffffffffu, mx[n], 2));
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) st[n].o[mt][e] *= sf;
+    }
+  }
 #pragma unroll
   for (int n = 0; n < N; ++n) {
-    // key0 < nkeys: the tile holds a valid key, so the quad maximum is finite; the first tile meets m = -inf: factor 0 on a zero state
-    const float m_new = fmaxf(st[n].m, mx[n]);
-    const float sf = ex2_approx(st[n].m - m_new);
-    st[n].m = m_new;
     float p[4];
 #pragma unroll
-    for (int e = 0; e < 4; ++e) p[e] = ex2_approx(sc[n][e] - m_new);
-    st[n].ls = fmaf(st[n].ls, sf, (p[0] + p[1]) + (p[2] + p[3]));
+    for (int e = 0; e < 4; ++e) p[e] = ex2_approx(sc[n][e] - st[n].m);
+    st[n].ls += (p[0] + p[1]) + (p[2] + p[3]);
     const uint32_t b0 = pack_bf16(p[0], p[1]), b1 = pack_bf16(p[2], p[3]);
-#pragma unroll
-    for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-      for (int e = 0; e < 4; ++e) st[n].o[mt][e] *= sf;
     mma16816(st[n].o[0], va[n][0], b0, b1);
     mma16816(st[n].o[1], va[n][1], b0, b1);
   }
@@ -552,7 +562,8 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(NT, MINB) decode_fu
         xwait(BAR_Y, ph_y);
       };
       // x = LN(xres + yrecv): warp w owns images w (and w + 8); writes xres and the fp16 operand
-      auto layer_norm = [&](const float* lnw, const float* lnb, bool fence_appends = false) {
+      auto layer_norm = [&](const float* lnw, const float* lnb, bool fence_appends = false, int l_now = -1, int t_now = -1, int fi = 0) {
+        if (warp == 0) FINE(l_now, t_now, fi);
         // this layer's KV append: the generic->async proxy fence (~1200 cycles) of the appending threads overlaps the exchange latency
         if (fence_appends && tid >= APP0 && tid - APP0 < G * 8) asm volatile("fence.proxy.async;" ::: "memory");
         float gw[8], gb[8];
@@ -561,6 +572,7 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(NT, MINB) decode_fu
           for (int j = 0; j < 8; ++j) { gw[j] = __ldg(lnw + lane + 32 * j); gb[j] = __ldg(lnb + lane + 32 * j); }
         }
         wait_y();
+        if (warp == 0) FINE(l_now, t_now, fi + 1);
 #pragma unroll
         for (int nb = 0; nb < NB; ++nb) {
           const int img = warp + 8 * nb;
@@ -582,7 +594,9 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(NT, MINB) decode_fu
             }
           }
         }
+        if (warp == 0) FINE(l_now, t_now, fi + 2);
         cbar();
+        if (warp == 0) FINE(l_now, t_now, fi + 3);
       };
       // attention output of image `img` (lane = channel) -> fp16 pairs into every peer's oh columns [32*rank, +32); lane j < 16
       // sends channels 2j, 2j+1 to peers 0..3, lane 16 + j the same pair to peers 4..7
@@ -819,7 +833,7 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(NT, MINB) decode_fu
           TRACE(t);   // 9: o gathered
           proj32_push(sbase + Y::OFF_OH, P.b_co[l]);
           TRACE(t);   // 10: cross out-proj pushed
-          layer_norm(P.ln2w[l], P.ln2b[l]);
+          layer_norm(P.ln2w[l], P.ln2b[l], false, l, t, 60);
           TRACE(t);   // 11: LN2
 
           // ---- FFN1: own 256 hidden units as 8 blocks of 32 rows (block b -> warp pair b % 4), ReLU, kept local as the FFN2 operand ----
@@ -874,7 +888,7 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(NT, MINB) decode_fu
             }
           }
           TRACE(t);   // 14: FFN2 reduced + pushed
-          layer_norm(P.ln3w[l], P.ln3b[l]);
+          layer_norm(P.ln3w[l], P.ln3b[l], false, l, t, 64);
           TRACE(t);   // 15: LN3
 
         }

@@ -27,17 +27,24 @@ constexpr int UMMA_K = 16;
 // warp0 TMA, warp1 MMA, then EW epilogue warps: 8 (two per TMEM lane quadrant) or 16 (four per quadrant, for the 256-wide tiles
 // whose epilogue -- GELU over 128 x 256 values -- otherwise outlasts the tile's main loop at two warps per scheduler)
 
-template <int BN, int EW> struct Cfg {
+// CTAS = 2: a cluster of two CTAs computes a 256 x BN tile with tcgen05.mma.cta_group::2 -- each CTA stages its own 128 rows of A and
+// only HALF of the B tile (BN/2 rows of W); the pair's MMAs read both halves.  A third less shared-memory traffic per flop on both
+// sides (TMA writes and tensor-core operand reads): with one CTA per tile the 128 x 256 x 16 MMAs read 12 KB of operands each while the
+// TMA unit writes as much -- together with the epilogue's staging that is all of the 128 B/clk shared-memory pipe (ncu: tc + lsu
+// wavefronts + the TMA fills = ~100 % of the active cycles; the dev switches MDC_GEMM_DBG show any two of {loads, MMAs, epilogue}
+// running at the MMA-only rate and the three together 30 % slower).
+template <int BN, int EW, int CTAS = 1> struct Cfg {
   static constexpr int kEpiThreads = EW * 32;
   static constexpr int kThreads = 64 + kEpiThreads;
   static constexpr int kOutBufs = 2;                            // staging tiles per epilogue warp (double buffered)
   static constexpr int kOutBufBytes = (EW == 16) ? 2048 : 4096; // 32 rows x 64 B (16 warps: 32-column bf16 chunks) or 32 rows x 128 B
-  static constexpr int kStages = (BN == 256) ? 3 : (BN == 128 ? 4 : 6);
+  static constexpr int kStages = CTAS == 2 ? ((BN == 256) ? 4 : 6) : ((BN == 256) ? 3 : (BN == 128 ? 4 : 6));
   static constexpr int kABytes = BLOCK_M * BLOCK_K * 2;
-  static constexpr int kBBytes = BN * BLOCK_K * 2;
+  static constexpr int kBBytes = (BN / CTAS) * BLOCK_K * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kTmemCols = (2 * BN <= 32) ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));
   static constexpr int kStageOutBytes = EW * kOutBufs * kOutBufBytes;   // staging tiles for the TMA stores
+  static_assert(kStageBytes % 1024 == 0, "stage alignment");
   static constexpr int kSmemBytes = kStages * kStageBytes + kStageOutBytes + 1024 /*align slack*/ + 256 /*barriers*/ + 4 * BN * 4 /*bias+gamma x2 stages*/;
 };
 
@@ -105,6 +112,28 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64
   asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
                ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
+// ---- cta_group::2 forms (pair of CTAs; CTA rank 0 of the cluster is the leader that issues the MMAs) ----
+__device__ __forceinline__ void tma_load_2d_2sm(const CUtensorMap* map, uint32_t leader_bar, uint32_t dst, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               ::"r"(dst), "l"(map), "r"(leader_bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void umma_f16_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
+               ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm(uint32_t bar) {     // arrives on the barrier at this offset in BOTH CTAs of the pair
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t local_bar, uint32_t cta) {   // arrive on the same barrier in CTA `cta` of the cluster
+  uint32_t r; asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_bar), "r"(cta));
+  // default semantics (release at CTA scope): the arrival orders this warp's TMEM reads (tcgen05.fence::before_thread_sync) before the
+  // leader's next MMAs; .release.cluster would add a cluster-scope memory fence per warp and tile (~1 us per tile measured)
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(r) : "memory");
+}
 __device__ __forceinline__ void tmem_ld32(uint32_t addr, uint32_t* v) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -133,7 +162,7 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N, bool f16 = false
 
 struct EpiArgs {
   void* D; int64_t ldd; const float* bias; const float* aux0; int period; int epilogue;
-  int dbg;   // developer build only (MDC_GEMM_DBG): 1 = no epilogue body, 2 = every load from tile (0,0), 4 = no loads, 8 = no MMAs
+  int dbg;   // developer build only (MDC_GEMM_DBG): 1 = no epilogue body, 2 = every load from tile (0,0), 4 = no loads, 8 = no MMAs, 16 = no output stores, 32 = no TMEM reads
 };
 #ifdef MDC_DEVTOOLS
 #define GEMM_DBG(ep, bit) ((ep).dbg & (bit))
@@ -146,33 +175,38 @@ __device__ __forceinline__ uint64_t pk2(float a, float b) { uint64_t r; asm("mov
 __device__ __forceinline__ void upk2(uint64_t v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
 __device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) { uint64_t d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
 __device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) { uint64_t d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
-__device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 
-// exact-erf GELU of two values, branch-free: erf(z) = 1 - 1/(1 + a1 z + ... + a6 z^6)^16 for z >= 0 (Abramowitz-Stegun 7.1.28,
-// |err| <= 3e-7 -- four orders below the bf16 rounding of the output), odd extension by copysign.  One MUFU per value (the
-// epilogue of mlp.fc1 is MUFU/issue bound, not tensor bound, with the two-MUFU + IEEE-reciprocal form it replaces).
-__device__ __forceinline__ void gelu2(float x0, float x1, float& y0, float& y1) {
-  const uint64_t z = pk2(fabsf(x0) * 0.70710678118654752440f, fabsf(x1) * 0.70710678118654752440f);
-  uint64_t p = fma2(z, pk2(0.0000430638f, 0.0000430638f), pk2(0.0002765672f, 0.0002765672f));
-  p = fma2(p, z, pk2(0.0001520143f, 0.0001520143f));
-  p = fma2(p, z, pk2(0.0092705272f, 0.0092705272f));
-  p = fma2(p, z, pk2(0.0422820123f, 0.0422820123f));
-  p = fma2(p, z, pk2(0.0705230784f, 0.0705230784f));
-  p = fma2(p, z, pk2(1.0f, 1.0f));
-  p = mul2(p, p); p = mul2(p, p); p = mul2(p, p); p = mul2(p, p);          // ^16 (overflow -> inf -> 1/inf = 0 -> erf = 1)
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) { uint64_t d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
+// exact-erf GELU of two values, branch-free:  GELU(x) = x Phi(x) = max(x, 0) - a Phi(-a),  a = |x|,  and  Phi(-a) = 2^q(a)  with q a
+// degree-6 polynomial fitted to log2 Phi(-a) on [0, 6] (weighted minimax on the error of a 2^q(a); tools/gelu_fit.py).  |error| of
+// GELU <= 2.9e-7 for every x (float32 rounding level at |x| ~ 4; relative error <= 1e-5 down to x -> 0, because the error term carries
+// the factor a) -- the same accuracy as the Abramowitz-Stegun 7.1.28 form it replaces (1 - 1/(1+a1 z+...+a6 z^6)^16, 3e-7 on erf), at
+// 7 instead of 15 operations on the FP32 pipe per value: the mlp.fc1 epilogue alone took 27 us of a 33 us launch (dev switch
+// MDC_GEMM_DBG=12).  a is clamped to 6: beyond it a Phi(-a) < 6e-9.  One MUFU (ex2) per value.
+__device__ __forceinline__ void gelu2(uint64_t x, float& y0, float& y1) {
+  float x0, x1; upk2(x, x0, x1);
+  const float a0 = fminf(fabsf(x0), 6.0f), a1 = fminf(fabsf(x1), 6.0f);
+  const uint64_t a = pk2(a0, a1);
+  uint64_t p = fma2(a, pk2(3.309269595774822e-05f, 3.309269595774822e-05f), pk2(-0.000769218779169023f, -0.000769218779169023f));
+  p = fma2(p, a, pk2(0.008080713450908661f, 0.008080713450908661f));
+  p = fma2(p, a, pk2(-0.05341210216283798f, -0.05341210216283798f));
+  p = fma2(p, a, pk2(-0.4587709903717041f, -0.4587709903717041f));
+  p = fma2(p, a, pk2(-1.1512017250061035f, -1.1512017250061035f));
+  p = fma2(p, a, pk2(-0.999993085861206f, -0.999993085861206f));
   float p0, p1; upk2(p, p0, p1);
-  const float e0 = copysignf(1.0f - rcp_approx(p0), x0), e1 = copysignf(1.0f - rcp_approx(p1), x1);
-  const float h0 = 0.5f * x0, h1 = 0.5f * x1;
-  y0 = fmaf(h0, e0, h0); y1 = fmaf(h1, e1, h1);
+  y0 = fmaf(-a0, ex2_approx(p0), fmaxf(x0, 0.f));
+  y1 = fmaf(-a1, ex2_approx(p1), fmaxf(x1, 0.f));
 }
 
 // F16: A, W and the 16-bit outputs are IEEE half instead of bf16 (same bytes, same tensor-core rate, 11 significant bits: the
 // decoder's teacher-forced prefill runs on the fp16 decode-loop weights -- DESIGN.md precision policy)
-template <int BN, int EPI, int EW, bool F16 = false>
+template <int BN, int EPI, int EW, bool F16 = false, int CTAS = 1>
 __global__ void __launch_bounds__(64 + EW * 32, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_d,
                EpiArgs ep, int M, int N, int K) {
-  using C = Cfg<BN, EW>;
+  using C = Cfg<BN, EW, CTAS>;
   constexpr int EPI_THREADS = C::kEpiThreads;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -189,7 +223,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   float* s_gamma = s_bias + 2 * BN;                                      // [2][BN]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int tiles_n = (N + BN - 1) / BN, tiles_m = (M + BLOCK_M - 1) / BLOCK_M;
+  // a "tile" is 128*CTAS rows x BN columns, owned by a cluster of CTAS CTAs; this CTA computes rows [128*rank, +128) of it
+  const uint32_t rank = CTAS == 2 ? cluster_rank() : 0u;
+  const int first_tile = blockIdx.x / CTAS, tile_step = gridDim.x / CTAS;
+  const int tiles_n = (N + BN - 1) / BN, tiles_m = (M + BLOCK_M * CTAS - 1) / (BLOCK_M * CTAS);
   const int num_tiles = tiles_m * tiles_n;
   const int num_kb = (K + BLOCK_K - 1) / BLOCK_K;
 
@@ -198,14 +235,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
     if (EPI != MDC_EPI_PATCH) asm volatile("prefetch.tensormap [%0];" ::"l"(&map_d) : "memory");
     for (int i = 0; i < C::kStages; ++i) { mbar_init(smem_u32(&full[i]), 1); mbar_init(smem_u32(&empty[i]), 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&tmem_full[i]), 1); mbar_init(smem_u32(&tmem_empty[i]), EPI_THREADS); }
+    // the accumulator is released by one arrival per epilogue warp of every CTA of the cluster (the leader's barrier is the one waited on)
+    for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&tmem_full[i]), 1); mbar_init(smem_u32(&tmem_empty[i]), EW * CTAS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   } else if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "r"(C::kTmemCols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if constexpr (CTAS == 2) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "r"(C::kTmemCols) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "r"(C::kTmemCols) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tcgen05_fence_before();
   __syncthreads();
+  if constexpr (CTAS == 2) cluster_sync();      // the peer's barriers are initialised before anything can signal them
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
@@ -213,13 +257,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     // ===== TMA producer =====
     if (elect_one()) {
       int stage = 0; uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m0 = (tile / tiles_n) * BLOCK_M, n0 = (tile % tiles_n) * BN;
+      for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
+        const int m0 = (tile / tiles_n) * (BLOCK_M * CTAS) + rank * BLOCK_M, n0 = (tile % tiles_n) * BN + rank * (BN / CTAS);
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(smem_u32(&empty[stage]), phase ^ 1);
           const uint32_t fb = smem_u32(&full[stage]);
-          if (GEMM_DBG(ep, 4)) { mbar_arrive(fb); }
-          else {
+          if (GEMM_DBG(ep, 4)) { if (rank == 0) mbar_arrive(fb); }
+          else if constexpr (CTAS == 2) {
+            // both CTAs' loads complete on the LEADER's barrier, which expects the bytes of both
+            if (rank == 0) mbar_expect_tx(fb, 2 * C::kStageBytes);
+            uint32_t lb; asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(lb) : "r"(fb), "r"(0));
+            tma_load_2d_2sm(&map_a, lb, smem_u32(smem_a + stage * C::kABytes), GEMM_DBG(ep, 2) ? 0 : kb * BLOCK_K, GEMM_DBG(ep, 2) ? 0 : m0);
+            tma_load_2d_2sm(&map_w, lb, smem_u32(smem_b + stage * C::kBBytes), GEMM_DBG(ep, 2) ? 0 : kb * BLOCK_K, GEMM_DBG(ep, 2) ? 0 : n0);
+          } else {
           mbar_expect_tx(fb, C::kStageBytes);
           tma_load_2d(&map_a, fb, smem_u32(smem_a + stage * C::kABytes), GEMM_DBG(ep, 2) ? 0 : kb * BLOCK_K, GEMM_DBG(ep, 2) ? 0 : m0);
           tma_load_2d(&map_w, fb, smem_u32(smem_b + stage * C::kBBytes), GEMM_DBG(ep, 2) ? 0 : kb * BLOCK_K, GEMM_DBG(ep, 2) ? 0 : n0);
@@ -230,9 +280,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
-    constexpr uint32_t idesc = make_idesc(BLOCK_M, BN, F16);
+    constexpr uint32_t idesc = make_idesc(BLOCK_M * CTAS, BN, F16);
     int stage = 0; uint32_t phase = 0; int iter = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++iter) {
+    if (rank == 0)                                   // the leader CTA of a pair issues for both
+    for (int tile = first_tile; tile < num_tiles; tile += tile_step, ++iter) {
       const int as = iter & 1; const uint32_t aphase = (iter >> 1) & 1;
       mbar_wait(smem_u32(&tmem_empty[as]), aphase ^ 1);
       tcgen05_fence_after();
@@ -245,10 +296,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           const uint64_t bdesc = make_smem_desc(smem_u32(smem_b + stage * C::kBBytes));
           if (!GEMM_DBG(ep, 8))
 #pragma unroll
-          for (int k = 0; k < BLOCK_K / UMMA_K; ++k)   // +32 B per UMMA_K inside the swizzle atom -> +2 in the >>4 address field
-            umma_f16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
-          umma_commit(smem_u32(&empty[stage]));                       // frees the smem slot when these MMAs retire
-          if (kb == num_kb - 1) umma_commit(smem_u32(&tmem_full[as])); // accumulator ready for the epilogue
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) { // +32 B per UMMA_K inside the swizzle atom -> +2 in the >>4 address field
+            if constexpr (CTAS == 2) umma_f16_2sm(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+            else umma_f16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+          }
+          if constexpr (CTAS == 2) {
+            umma_commit_2sm(smem_u32(&empty[stage]));                       // frees the smem slot in both CTAs when these MMAs retire
+            if (kb == num_kb - 1) umma_commit_2sm(smem_u32(&tmem_full[as])); // accumulator ready for both CTAs' epilogues
+          } else {
+            umma_commit(smem_u32(&empty[stage]));                       // frees the smem slot when these MMAs retire
+            if (kb == num_kb - 1) umma_commit(smem_u32(&tmem_full[as])); // accumulator ready for the epilogue
+          }
         }
         __syncwarp();
         if (++stage == C::kStages) { stage = 0; phase ^= 1; }
@@ -267,9 +325,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const uint32_t stage_out = smem_u32(smem_out) + (warp - 2) * (C::kOutBufs * C::kOutBufBytes);
     int obuf = 0;
     int iter = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++iter) {
+    for (int tile = first_tile; tile < num_tiles; tile += tile_step, ++iter) {
       const int as = iter & 1; const uint32_t aphase = (iter >> 1) & 1;
-      const int m0 = (tile / tiles_n) * BLOCK_M, n0 = (tile % tiles_n) * BN;
+      const int m0 = (tile / tiles_n) * (BLOCK_M * CTAS) + rank * BLOCK_M, n0 = (tile % tiles_n) * BN;
       // stage this tile's bias (and LayerScale gamma) once; overlaps the wait for the accumulator
       for (int i = et; i < BN; i += EPI_THREADS) {
         const bool ok = n0 + i < N;
@@ -325,8 +383,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         for (int c0 = 0; c0 < HALF_COLS; c0 += CH) {
           const int col0 = n0 + half * HALF_COLS + c0;
           uint32_t v[CH];
+          if (GEMM_DBG(ep, 32)) {
+#pragma unroll
+            for (int i = 0; i < CH; ++i) v[i] = 0x3f800000u + lane + i;
+          } else {
           tmem_ld32(taddr + c0, v);
           if constexpr (CH == 64) tmem_ld32(taddr + c0 + 32, v + 32);
+          }
           if (lane == 0) bulk_wait_read<C::kOutBufs - 1>();   // the store last issued from this staging buffer has read it
           __syncwarp();
           tmem_ld_wait();
@@ -339,10 +402,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
             for (int jj = 0; jj < 8; jj += 2) {
-              float a0 = __uint_as_float(v[j + jj]) + bb[jj], a1 = __uint_as_float(v[j + jj + 1]) + bb[jj + 1];
-              if (EPI == MDC_EPI_BIAS_GELU) gelu2(a0, a1, a0, a1);
-              else if (EPI == MDC_EPI_BIAS_RELU) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); }
-              o[jj] = a0; o[jj + 1] = a1;
+              if constexpr (EPI == MDC_EPI_BIAS_GELU) {
+                gelu2(add2(pk2(__uint_as_float(v[j + jj]), __uint_as_float(v[j + jj + 1])), pk2(bb[jj], bb[jj + 1])), o[jj], o[jj + 1]);
+              } else {
+                float a0 = __uint_as_float(v[j + jj]) + bb[jj], a1 = __uint_as_float(v[j + jj + 1]) + bb[jj + 1];
+                if (EPI == MDC_EPI_BIAS_RELU) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); }
+                o[jj] = a0; o[jj + 1] = a1;
+              }
             }
             if constexpr (OUT_F32) {
               const float4 g0 = *reinterpret_cast<const float4*>(sg + c0 + j), g1 = *reinterpret_cast<const float4*>(sg + c0 + j + 4);
@@ -357,7 +423,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           }
           fence_async_smem();
           __syncwarp();
-          if (lane == 0 && row0 < M && col0 < N) {
+          if (lane == 0 && row0 < M && col0 < N && !GEMM_DBG(ep, 16)) {
             if constexpr (OUT_F32) tma_reduce_add_2d(&map_d, tile_s, col0, row0);
             else tma_store_2d(&map_d, tile_s, col0, row0);
           }
@@ -366,15 +432,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         }
       }
       tcgen05_fence_before();
-      mbar_arrive(smem_u32(&tmem_empty[as]));
+      __syncwarp();
+      if (lane == 0) {                                            // this warp's TMEM reads of the accumulator stage are done
+        if constexpr (CTAS == 2) mbar_arrive_cluster(smem_u32(&tmem_empty[as]), 0);
+        else mbar_arrive(smem_u32(&tmem_empty[as]));
+      }
     }
     if (EPI != MDC_EPI_PATCH && lane == 0) bulk_wait_read<0>();   // staging tiles must outlive the last stores' reads
   }
   tcgen05_fence_before();
   __syncthreads();
+  if constexpr (CTAS == 2) cluster_sync();      // no CTA leaves while its peer can still signal its barriers or read its operands
   if (warp == 1) {
     tcgen05_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(C::kTmemCols) : "memory");
+    if constexpr (CTAS == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(C::kTmemCols) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(C::kTmemCols) : "memory");
   }
 }
 
@@ -434,18 +506,19 @@ int make_out_tmap(mdc_ctx* ctx, const void* ptr, int64_t rows, int64_t cols, int
   return 0;
 }
 
-template <int BN, int EPI, bool F16 = false>
+template <int BN, int EPI, bool F16 = false, int CTAS = 1>
 int launch_bn_epi(mdc_ctx* ctx, const CUtensorMap& ma, const CUtensorMap& mw, const EpiArgs& ep, int M, int N, int K, cudaStream_t s) {
   constexpr int EW = (BN == 256 && EPI == MDC_EPI_BIAS_GELU) ? 16 : 8;     // A/B on one box: fc1 34.0 -> 31.6 us; bias-only epilogues lose 3 %
-  using C = Cfg<BN, EW>;
+  using C = Cfg<BN, EW, CTAS>;
   static bool attr_set[MDC_MAX_DEVICES];      // the dynamic-smem opt-in is a per-device attribute of this instantiation
   if (ctx->device < 0 || ctx->device >= MDC_MAX_DEVICES) MDC_FAIL(-2, "device index %d out of range", ctx->device);
   if (!attr_set[ctx->device]) {
-    MDC_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI, EW, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
+    MDC_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI, EW, F16, CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
     attr_set[ctx->device] = true;
   }
-  int tiles = ((M + BLOCK_M - 1) / BLOCK_M) * ((N + BN - 1) / BN);
-  int grid = tiles < ctx->sm_count ? tiles : ctx->sm_count;
+  const int tiles = ((M + BLOCK_M * CTAS - 1) / (BLOCK_M * CTAS)) * ((N + BN - 1) / BN);     // tiles of 128*CTAS rows, one cluster each
+  const int max_clusters = ctx->sm_count / CTAS;
+  const int grid = (tiles < max_clusters ? tiles : max_clusters) * CTAS;
   CUtensorMap md;
   memset(&md, 0, sizeof(md));
   if (EPI != MDC_EPI_PATCH) {
@@ -453,19 +526,28 @@ int launch_bn_epi(mdc_ctx* ctx, const CUtensorMap& ma, const CUtensorMap& mw, co
     const int box_cols = f32 ? 32 : ((BN / (EW / 4) >= 64 && EW == 8) ? 64 : 32);
     MDC_TRY(make_out_tmap(ctx, ep.D, M, N, ep.ldd, f32, box_cols, &md));
   }
-  gemm_tc_kernel<BN, EPI, EW, F16><<<grid, C::kThreads, C::kSmemBytes, s>>>(ma, mw, md, ep, M, N, K);
+  if constexpr (CTAS == 1) {
+    gemm_tc_kernel<BN, EPI, EW, F16, 1><<<grid, C::kThreads, C::kSmemBytes, s>>>(ma, mw, md, ep, M, N, K);
+  } else {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(C::kThreads); cfg.dynamicSmemBytes = C::kSmemBytes; cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = CTAS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    MDC_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, EPI, EW, F16, CTAS>, ma, mw, md, ep, M, N, K));
+  }
   MDC_LAUNCH_CHECK(ctx);
   return 0;
 }
 
-template <int BN>
+template <int BN, int CTAS = 1>
 int launch_bn(mdc_ctx* ctx, const CUtensorMap& ma, const CUtensorMap& mw, const EpiArgs& ep, int M, int N, int K, cudaStream_t s) {
   switch (ep.epilogue) {
-    case MDC_EPI_BIAS: return launch_bn_epi<BN, MDC_EPI_BIAS>(ctx, ma, mw, ep, M, N, K, s);
-    case MDC_EPI_BIAS_GELU: return launch_bn_epi<BN, MDC_EPI_BIAS_GELU>(ctx, ma, mw, ep, M, N, K, s);
-    case MDC_EPI_BIAS_RELU: return launch_bn_epi<BN, MDC_EPI_BIAS_RELU>(ctx, ma, mw, ep, M, N, K, s);
-    case MDC_EPI_LS_RESIDUAL: return launch_bn_epi<BN, MDC_EPI_LS_RESIDUAL>(ctx, ma, mw, ep, M, N, K, s);
-    case MDC_EPI_PATCH: return launch_bn_epi<BN, MDC_EPI_PATCH>(ctx, ma, mw, ep, M, N, K, s);
+    case MDC_EPI_BIAS: return launch_bn_epi<BN, MDC_EPI_BIAS, false, CTAS>(ctx, ma, mw, ep, M, N, K, s);
+    case MDC_EPI_BIAS_GELU: return launch_bn_epi<BN, MDC_EPI_BIAS_GELU, false, CTAS>(ctx, ma, mw, ep, M, N, K, s);
+    case MDC_EPI_BIAS_RELU: return launch_bn_epi<BN, MDC_EPI_BIAS_RELU, false, CTAS>(ctx, ma, mw, ep, M, N, K, s);
+    case MDC_EPI_LS_RESIDUAL: return launch_bn_epi<BN, MDC_EPI_LS_RESIDUAL, false, CTAS>(ctx, ma, mw, ep, M, N, K, s);
+    case MDC_EPI_PATCH: return launch_bn_epi<BN, MDC_EPI_PATCH, false, 1>(ctx, ma, mw, ep, M, N, K, s);     // direct-store epilogue: single-CTA tiles only
   }
   MDC_FAIL(-2, "gemm: unknown epilogue %d", ep.epilogue);
 }
@@ -497,9 +579,14 @@ int gemm_tc_launch(mdc_ctx* ctx, int epilogue, const void* A, int64_t lda, const
   int bn = 128;
   if (N % 256 == 0 && tiles_m * (N / 256) >= ctx->sm_count) bn = 256;
   if (N <= 64 || tiles_m * ((N + 127) / 128) < ctx->sm_count) bn = 64;
+  // CTA pairs (cta_group::2) for the wide tiles of tall problems: a third less shared-memory traffic per flop
+  int ctas = (!f16 && bn >= 128 && epilogue != MDC_EPI_PATCH && M >= 2 * BLOCK_M) ? 2 : 1;
+#ifdef MDC_DEVTOOLS
+  if (const char* e = getenv("MDC_GEMM_2CTA")) ctas = (e[0] == '0') ? 1 : ctas;
+#endif
   CUtensorMap ma, mw;
   MDC_TRY(get_tmap(ctx, A, M, K, lda, BLOCK_M, &ma));
-  MDC_TRY(get_tmap(ctx, W, N, K, ldw, bn, &mw));
+  MDC_TRY(get_tmap(ctx, W, N, K, ldw, bn / ctas, &mw));        // a CTA of a pair loads half of the B tile
   EpiArgs ep{D, ldd, bias, aux0, period, epilogue, 0};
 #ifdef MDC_DEVTOOLS
   if (const char* e = getenv("MDC_GEMM_DBG")) ep.dbg = atoi(e);
@@ -509,6 +596,7 @@ int gemm_tc_launch(mdc_ctx* ctx, int epilogue, const void* A, int64_t lda, const
     if (bn == 128) return launch_bn_f16<128>(ctx, ma, mw, ep, M, N, K, s);
     return launch_bn_f16<64>(ctx, ma, mw, ep, M, N, K, s);
   }
+  if (ctas == 2) return bn == 256 ? launch_bn<256, 2>(ctx, ma, mw, ep, M, N, K, s) : launch_bn<128, 2>(ctx, ma, mw, ep, M, N, K, s);
   if (bn == 256) return launch_bn<256>(ctx, ma, mw, ep, M, N, K, s);
   if (bn == 128) return launch_bn<128>(ctx, ma, mw, ep, M, N, K, s);
   return launch_bn<64>(ctx, ma, mw, ep, M, N, K, s);

@@ -33,7 +33,7 @@ for nm, v in zip(names, tot):
 print(f"  whole loop: consumer warp 0 blocked on ring stages {tr[200]} cyc, on exchanges {tr[201]} cyc; producer blocked on free slots {tr[202]} cyc")
 print(f"  layer total {sum(tot)/L:.0f} cyc; head {tr[L*16]-tr[L*16-1]} cyc; select+token exchange {tr[L*16+1]-tr[L*16]} cyc; step {tr[L*16+1]-tr[0]} cyc")
 
-f = tr[100:160]
+f = tr[100:180]
 print("fine stamps, layer 2 (cycles relative to FFN1 stage-0 start of warp 0): per FFN1 stage [enter, data ready, mma done, released]")
 for s4 in range(2):
     v = f[s4 * 4:s4 * 4 + 4]
@@ -44,6 +44,10 @@ for g in range(8):
     v = f[20 + g * 3:23 + g * 3]
     if v[0]:
         print(f"  cross image {g}: enter +{v[0]-f[20]:6d}  wait {v[1]-v[0]:5d}  attend+release {v[2]-v[1]:5d}")
+for nm, i in (("LN2", 60), ("LN3", 64)):
+    v = f[i:i + 4]
+    if v[0]:
+        print(f"  {nm} (warp 0, layer 2): wait for y {v[1]-v[0]:5d}  normalise own images {v[2]-v[1]:5d}  barrier {v[3]-v[2]:5d}")
 import sys; sys.exit(0)
 for g in range(8):
     v = tr[100 + g * 8:100 + g * 8 + 6]

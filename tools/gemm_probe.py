@@ -26,9 +26,14 @@ for name, Mr, N, K, epi in shapes:
         L.check(L.lib().mdc_gemm(L.ctx(dev), L.MDC_BF16, epi, L.ptr(A), K, L.ptr(W), K, L.ptr(D), N, L.ptr(bias), L.ptr(aux), period, Mr, N, K, L.stream_ptr()))
     for _ in range(3): run()
     torch.cuda.synchronize()
+    # the launches are replayed from a CUDA graph (as the encoder phase runs them): eager launches are host-bound at ~16 us each
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for _ in range(reps): run()
+    g.replay(); torch.cuda.synchronize()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
-    for _ in range(reps): run()
+    for _ in range(5): g.replay()
     b.record(); torch.cuda.synchronize()
-    ms = a.elapsed_time(b) / reps
+    ms = a.elapsed_time(b) / (5 * reps)
     print(f"{name:8s} M={Mr} N={N} K={K}: {ms*1e3:8.1f} us  {2.0*Mr*N*K/ms/1e9:8.1f} TFLOP/s")
