@@ -220,9 +220,29 @@ attn_umma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
         const bool live = __any_sync(0xffffffffu, t * 128 + row < S);
         float s[64];
         if (live) {
+          // the widest tcgen05.ld shapes that cover the thread's qc = 4 nch columns (52 = 32 + 16 + 4 for 197-token strips): thirteen
+          // 4-column loads per thread took 1600 cycles per tile -- bound by the number of TMEM load instructions, not by their bytes
+          uint32_t* sr = reinterpret_cast<uint32_t*>(s);
+          const uint32_t tcol = trow + part * qc;
+          if (nch >= 8) {
+            tmem_ld32(tcol, sr);
+            if (nch == 16) tmem_ld32(tcol + 32, sr + 32);
+            else if (nch >= 12) {
+              tmem_ld16(tcol + 32, sr + 32);
 #pragma unroll
-          for (int c = 0; c < 16; ++c)
-            if (c < nch) tmem_ld4(trow + part * qc + 4 * c, reinterpret_cast<uint32_t*>(s) + 4 * c);
+              for (int c = 12; c < 15; ++c) if (c < nch) tmem_ld4(tcol + 4 * c, sr + 4 * c);
+            } else {
+#pragma unroll
+              for (int c = 8; c < 11; ++c) if (c < nch) tmem_ld4(tcol + 4 * c, sr + 4 * c);
+            }
+          } else if (nch >= 4) {
+            tmem_ld16(tcol, sr);
+#pragma unroll
+            for (int c = 4; c < 7; ++c) if (c < nch) tmem_ld4(tcol + 4 * c, sr + 4 * c);
+          } else {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) if (c < nch) tmem_ld4(tcol + 4 * c, sr + 4 * c);
+          }
           tmem_ld_wait();
         }
         if (threadIdx.x == 64) STAMP(11 + 8 * t);

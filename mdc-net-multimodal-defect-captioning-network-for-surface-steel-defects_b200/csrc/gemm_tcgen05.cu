@@ -517,7 +517,10 @@ int launch_bn_epi(mdc_ctx* ctx, const CUtensorMap& ma, const CUtensorMap& mw, co
     attr_set[ctx->device] = true;
   }
   const int tiles = ((M + BLOCK_M * CTAS - 1) / (BLOCK_M * CTAS)) * ((N + BN - 1) / BN);     // tiles of 128*CTAS rows, one cluster each
-  const int max_clusters = ctx->sm_count / CTAS;
+  int max_clusters = ctx->sm_count / CTAS;
+#ifdef MDC_DEVTOOLS
+  if (const char* e = getenv("MDC_GEMM_GRID")) { const int g = atoi(e) / CTAS; if (g >= 1 && g < max_clusters) max_clusters = g; }
+#endif
   const int grid = (tiles < max_clusters ? tiles : max_clusters) * CTAS;
   CUtensorMap md;
   memset(&md, 0, sizeof(md));
