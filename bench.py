@@ -337,6 +337,9 @@ def run_workload(M, wl, B, steps, warmup, dev, rank, world, dist, peaks, full):
                 else:
                     sink[i * B:(i + 1) * B] = M.parallel.pack_results(t.tokens, t.confs)
         pipe.join()
+        pre = torch.cuda.Event(enable_timing=True)
+        pre.record()                                 # this rank's own work is enqueued behind this point; the gather follows
+        steps_pipelined.pre_gather = pre
         return M.parallel.all_gather_results(sink, k * B * world)
 
     sink_w = torch.zeros((max(8, warmup) * B, F), dtype=torch.int32, device=dev)
@@ -359,11 +362,18 @@ def run_workload(M, wl, B, steps, warmup, dev, rank, world, dist, peaks, full):
         dist.barrier()
     clocks = sampler.stop()
     t = torch.tensor([pa.elapsed_time(pb)], dtype=torch.float64, device=dev)
+    mine = torch.tensor([pa.elapsed_time(pb), pa.elapsed_time(steps_pipelined.pre_gather)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms = t.item()
     res = {"value": B * world * steps / (total_ms / 1e3), "ms_per_step": total_ms / steps, "clocks": clocks, "gpu_launches": int(n1 - n0),
            "gathered_rows": int(out.shape[0])}
+    if world > 1:
+        # where an N-GPU run loses against N independent GPUs: every rank's own time to finish its steps (before the gather) and its
+        # time including the one all-gather -- the gather completes when the SLOWEST rank arrives, so (max - own) is waiting, not work
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        res["per_rank_ms"] = {"own_steps": [round(v[1].item(), 3) for v in allr], "with_gather": [round(v[0].item(), 3) for v in allr]}
 
     # end-to-end through the public streaming API (generate_stream), HOST buffers: H2D of every batch + D2H of its results inside
     def e2e_run(batches_host, k):
@@ -483,6 +493,8 @@ def main():
     out = {"metric": METRIC, "value": res["value"], "unit": "images/s", "n_gpus": world, "steps": steps, "warmup": max(8, args.warmup),
            "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "bf16",
            "data": "synthetic", "config": cfg, "clocks": res["clocks"], "e2e": res["e2e"], "gpu_launches": res["gpu_launches"]}
+    if "per_rank_ms" in res:
+        out["per_rank_ms"] = res["per_rank_ms"]
     if args.config == 1:
         # The dominant kernel is the fused decode loop.  In the timed region four of its launches (32 SMs each) and the encoder share the
         # GPU, so the figure that belongs to the headline is the rate at which the decode loops TOGETHER move their algorithmic bytes:
