@@ -64,6 +64,47 @@ def test_gemm_layerscale_residual_and_patch_epilogues(dtype):
     assert (got[:, 1:].double() - want).abs().max().item() < (5e-4 if dtype == torch.float32 else 5e-3)
 
 
+@pytest.mark.parametrize("shape,epi", [((12608, 1536, 512), "bias"), ((12608, 2048, 512), "gelu"), ((12608, 512, 2048), "residual"),
+                                       ((12608, 512, 512), "residual"), ((9999, 2048, 512), "gelu")])
+def test_gemm_encoder_shapes_at_the_bench_batch(shape, epi):
+    """The encoder GEMMs at B = 64 -- the shapes that run as CTA pairs (tcgen05.mma.cta_group::2, 256 x 256 tiles, several tile waves per
+    CTA, a ragged last row pair) -- against fp64 on the same bf16 operands."""
+    Mr, N, K = shape
+    A, W = _mk((Mr, K), torch.bfloat16, 11), _mk((N, K), torch.bfloat16, 12) * 0.2
+    bias = _mk((N,), torch.float32, 13)
+    ref = A.double() @ W.double().T + bias.double()
+    if epi == "residual":
+        gamma, R0 = _mk((N,), torch.float32, 14), _mk((Mr, N), torch.float32, 15)
+        R = R0.clone()
+        G.gemm(A, W, torch.bfloat16, L.EPI_LS_RESIDUAL, bias=bias, aux0=gamma, R=R)
+        want = R0.double() + gamma.double() * ref
+        assert (R.double() - want).abs().max().item() < 5e-3
+    else:
+        D = G.gemm(A, W, torch.bfloat16, L.EPI_BIAS_GELU if epi == "gelu" else L.EPI_BIAS, bias=bias)
+        want = torch.nn.functional.gelu(ref) if epi == "gelu" else ref
+        err = (D.double() - want).abs()
+        assert (err <= 1e-3 + want.abs() * 2 ** -8).all(), err.max().item()
+
+
+def test_gemm_gelu_epilogue_is_the_exact_erf_form_to_output_rounding():
+    """GELU in the epilogue is max(x,0) - a 2^q(a) with a fitted polynomial q (|error| <= 3e-7, tools/gelu_fit.py): on a dense sweep of
+    x in [-9, 9] the bf16 result must be the correctly rounded exact-erf GELU up to one unit in the last place of bf16."""
+    Mr, N, K = 8192, 64, 64
+    x = torch.linspace(-9, 9, Mr, device=DEV).to(torch.bfloat16)
+    A = torch.zeros((Mr, K), dtype=torch.bfloat16, device=DEV); A[:, 0] = x
+    W = torch.zeros((N, K), dtype=torch.bfloat16, device=DEV); W[:, 0] = 1
+    D = G.gemm(A, W, torch.bfloat16, L.EPI_BIAS_GELU, bias=torch.zeros(N, device=DEV))
+    want = torch.nn.functional.gelu(x.double())
+    got = D[:, 0].double()
+    assert torch.equal(D[:, 0], D[:, N - 1])
+    assert ((got - want).abs() <= want.abs() * 2 ** -8 + 1e-6).all(), (got - want).abs().max().item()
+    # and against the correctly rounded value: equal almost everywhere (ties of the rounding can differ by one ulp)
+    # (where |GELU| > 1e-5, i.e. x > -4.4: below that the value is the difference of float32 roundings and, for x < -6, the clamp a <= 6)
+    exact_bf16 = want.to(torch.bfloat16)
+    sel = want.abs() > 1e-5
+    assert (D[:, 0][sel] == exact_bf16[sel]).float().mean().item() > 0.995
+
+
 def test_gemm_tcgen05_matches_ffma_on_same_bf16_inputs():
     """The tensor-core kernel and the FFMA kernel see identical bf16 operands; only the summation order differs."""
     A, W = _mk((1000, 512), torch.bfloat16, 1), _mk((1536, 512), torch.bfloat16, 2)
