@@ -20,6 +20,7 @@
 #include "select.cuh"
 #include <cuda_fp16.h>
 #include <float.h>
+#include <type_traits>
 
 int decode_cluster_supported(const mdc_model* m, const mdc_decode_state* st, int t_end);
 int decode_cluster_launch(mdc_model* m, const mdc_decode_state* st, int t_begin, int t_end, void* logits_scratch, cudaStream_t s);
@@ -30,7 +31,7 @@ constexpr int LIN_THREADS = 256;
 constexpr int LIN_WARPS = 8;
 constexpr int BT = 16;           // batch rows per CTA
 
-enum { XMODE_PLAIN = 0, XMODE_LN = 1, XMODE_EMBED = 2 };
+enum { XMODE_PLAIN = 0, XMODE_LN = 1, XMODE_EMBED = 2, XMODE_HALF = 3 };
 
 struct XSrc {
   int mode;
@@ -40,6 +41,7 @@ struct XSrc {
   const int32_t* tokens; int tokens_ld; int t;  // EMBED: emb[tokens[b,t]] + pos[t]
   const float* emb; const float* pos;
   float* xn_out;                                // where CTA column 0 publishes the operand rows (or NULL)
+  const __half* xh;                             // HALF: operand rows already built as IEEE half [B][K] (prep_x_half_kernel)
 };
 
 // Fill Xs[BT][K] (f32) for batch rows b0..b0+BT-1.
@@ -303,6 +305,177 @@ __global__ void __launch_bounds__(LIN_THREADS) dec_linear_generic_kernel(XSrc xs
   }
 }
 
+// ---- tensor-core form of the same linear for batches of 16 and more (fp16 decode-loop weights) ----------------------------------
+// Y[B,N] = act(Xeff[B,K] . W[N,K]^T + bias) with the WEIGHT rows as the M operand of mma.sync.m16n8k16 and the images as N = 8
+// column blocks, like the fused cluster kernel's projections: a CTA of 8 warps owns 64 weight rows (4 row groups of 16) x 64 images
+// (2 halves of 4 column blocks); every weight is read from global memory ONCE per 64 images (the FFMA kernel above re-streams the
+// weights per 16 images and does the arithmetic on the FP32 pipe: 2.6 ms per token-step at dim 1024 / 8 layers / B = 64).
+// The operand rows (plain / LayerNorm-on-load / embedding, the same three sources) are built once per CTA as IEEE half in shared
+// memory (the precision policy of the fused kernel: fp16 projection operands).  Weight fragments come straight from global memory:
+// lane (g, q) loads the 16 bytes W[row g (+8)][32 kb + 8 q .. +8) and uses them as the A fragments of two k-steps under the k
+// permutation logical (step s, 2q + j, +8 hi) <-> physical 8 q + 4 s + 2 hi + j, which the B fragment (one 8-byte shared load
+// X[image][32 kb + 8 q + 4 s .. +4)) follows -- a dot product does not care in which order k is enumerated.
+constexpr int MMA_ROWS = 64;       // weight rows per CTA
+constexpr int MMA_IMGS = 64;       // images per CTA
+constexpr int MMA_KC = 1024;       // operand columns held in shared memory at a time
+constexpr int MMA_PAD = 4;         // halves of row padding: row pitch = 2 words mod 32 (two-way conflicts at worst on the 8-byte loads)
+
+__device__ __forceinline__ void mma16816_f16(float* c, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack_half2(float a, float b) {
+  __half2 h = __floats2half2_rn(fminf(fmaxf(a, -65504.f), 65504.f), fminf(fmaxf(b, -65504.f), 65504.f)); return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// LayerNorm-on-load / embedding operand rows, built ONCE per linear (one warp per image, all images in parallel) as IEEE half in
+// global memory, and published as the next residual (xn_out, f32).  Building them inside every CTA of the linear -- eight rows per
+// warp, one after the other, three dependent memory round trips each -- was 75 % of that kernel's time (ncu, profiles/r2w).
+__global__ void __launch_bounds__(LIN_THREADS) prep_x_half_kernel(XSrc xs, __half* __restrict__ xh, int B, int K) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.x * LIN_WARPS + warp;
+  if (b >= B) return;
+  float v[MMA_KC / 32];                       // lane holds columns lane + 32 i
+  if (xs.mode == XMODE_EMBED) {
+    const int tok = xs.tokens[(int64_t)b * xs.tokens_ld + xs.t];
+    const float* e = xs.emb + (int64_t)tok * K; const float* pz = xs.pos + (int64_t)xs.t * K;
+#pragma unroll
+    for (int i = 0; i < MMA_KC / 32; ++i) { const int c = lane + 32 * i; v[i] = c < K ? __ldg(e + c) + __ldg(pz + c) : 0.f; }
+  } else {
+    const float* a = xs.resid + (int64_t)b * K; const float* d = xs.delta + (int64_t)b * K;
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < MMA_KC / 32; ++i) { const int c = lane + 32 * i; v[i] = c < K ? a[c] + d[c] : 0.f; sum += v[i]; }
+    const float mean = warp_sum(sum) / (float)K;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < MMA_KC / 32; ++i) { const int c = lane + 32 * i; const float t = c < K ? v[i] - mean : 0.f; q += t * t; }
+    const float rstd = 1.0f / sqrtf(warp_sum(q) / (float)K + xs.eps);
+#pragma unroll
+    for (int i = 0; i < MMA_KC / 32; ++i) { const int c = lane + 32 * i; if (c < K) v[i] = (v[i] - mean) * rstd * __ldg(xs.ln_w + c) + __ldg(xs.ln_b + c); }
+  }
+#pragma unroll
+  for (int i = 0; i < MMA_KC / 32; ++i) {
+    const int c = lane + 32 * i;
+    if (c < K) {
+      xh[(int64_t)b * K + c] = __float2half_rn(fminf(fmaxf(v[i], -65504.f), 65504.f));
+      if (xs.xn_out) xs.xn_out[(int64_t)b * K + c] = v[i];
+    }
+  }
+}
+
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+
+// operand rows b0 .. b0+63, columns [k0, k0+kc) -> Xh[64][kc + MMA_PAD] (fp16); rows >= B are zero.
+//   HALF : rows already in IEEE half (prep_x_half_kernel): 8-byte cp.async chunks, every row in flight at once
+//   PLAIN: f32 rows (attention outputs, the FFN hidden), converted on the way; two rows per warp in flight
+__device__ __forceinline__ void build_x_half(const XSrc& xs, __half* Xh, int b0, int B, int K, int k0, int kc, bool publish) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int pitch = kc + MMA_PAD;
+  if (xs.mode == XMODE_HALF) {
+    for (int r = warp; r < MMA_IMGS; r += LIN_WARPS) {          // a warp copies whole rows: 8-byte chunks, 256 bytes per instruction
+      const int b = b0 + r;
+      __half* dst = Xh + (size_t)r * pitch;
+      const __half* src = xs.xh + (int64_t)min(b, B - 1) * K + k0;
+      if (b < B) { for (int c = lane * 4; c < kc; c += 128) cp_async8(dst + c, src + c); }
+      else { for (int c = lane * 4; c < kc; c += 128) *reinterpret_cast<uint2*>(dst + c) = make_uint2(0u, 0u); }
+    }
+    cp_async_wait_all();
+    return;
+  }
+  for (int r = warp; r < MMA_IMGS; r += 2 * LIN_WARPS) {      // rows r and r + 8
+    float4 v[2][MMA_KC / 128];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int b = b0 + r + 8 * h;
+      const float* src = xs.x + (int64_t)min(b, B - 1) * xs.ldx + k0;
+#pragma unroll
+      for (int i = 0; i < MMA_KC / 128; ++i) { const int c = lane * 4 + 128 * i; if (c < kc) v[h][i] = *reinterpret_cast<const float4*>(src + c); }
+    }
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int b = b0 + r + 8 * h;
+      __half* row = Xh + (size_t)(r + 8 * h) * pitch;
+#pragma unroll
+      for (int i = 0; i < MMA_KC / 128; ++i) {
+        const int c = lane * 4 + 128 * i;
+        if (c < kc) {
+          *reinterpret_cast<uint2*>(row + c) = b < B ? make_uint2(pack_half2(v[h][i].x, v[h][i].y), pack_half2(v[h][i].z, v[h][i].w)) : make_uint2(0u, 0u);
+          if (publish && xs.xn_out && b < B) *reinterpret_cast<float4*>(xs.xn_out + (int64_t)b * K + k0 + c) = v[h][i];
+        }
+      }
+    }
+  }
+}
+
+template <bool RELU>
+__global__ void __launch_bounds__(LIN_THREADS) dec_linear_mma_kernel(XSrc xs, const __half* __restrict__ W, const float* __restrict__ bias,
+                                                                      float* __restrict__ Y, int64_t ldy, int B, int N, int K) {
+  extern __shared__ __align__(16) uint8_t mma_smem[];
+  __half* Xh = reinterpret_cast<__half*>(mma_smem);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, q = lane & 3;
+  const int b0 = blockIdx.y * MMA_IMGS;
+  const int r0 = blockIdx.x * MMA_ROWS + (warp & 3) * 16;           // this warp's 16 weight rows
+  const int nb0 = (warp >> 2) * 4;                                  // this warp's four 8-image column blocks
+  const int row_a = min(r0 + g, N - 1), row_b = min(r0 + g + 8, N - 1);   // rows past N are computed on a valid row and never stored
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f; }
+  for (int k0 = 0; k0 < K; k0 += MMA_KC) {
+    const int kc = min(MMA_KC, K - k0), pitch = kc + MMA_PAD;
+    if (k0) __syncthreads();
+    build_x_half(xs, Xh, b0, B, K, k0, kc, blockIdx.x == 0);
+    __syncthreads();
+    const __half* wa = W + (int64_t)row_a * K + k0 + 8 * q;
+    const __half* wb = W + (int64_t)row_b * K + k0 + 8 * q;
+    const __half* xb = Xh + (size_t)(8 * nb0 + g) * pitch + 8 * q;
+    const int nkb = kc >> 5;
+    constexpr int PF = 8;                                           // weight slices of eight 32-column blocks in flight per lane
+    uint4 alo[PF], ahi[PF];
+#pragma unroll
+    for (int i = 0; i < PF; ++i)
+      if (i < nkb) { alo[i] = __ldg(reinterpret_cast<const uint4*>(wa + 32 * i)); ahi[i] = __ldg(reinterpret_cast<const uint4*>(wb + 32 * i)); }
+    for (int kb0 = 0; kb0 < nkb; kb0 += PF) {
+#pragma unroll
+      for (int i = 0; i < PF; ++i) {
+        const int kb = kb0 + i;
+        if (kb < nkb) {
+          const uint4 lo = alo[i], hi = ahi[i];
+          if (kb + PF < nkb) { alo[i] = __ldg(reinterpret_cast<const uint4*>(wa + 32 * (kb + PF))); ahi[i] = __ldg(reinterpret_cast<const uint4*>(wb + 32 * (kb + PF))); }
+#pragma unroll
+          for (int nb = 0; nb < 4; ++nb) {
+            const uint2 x0 = *reinterpret_cast<const uint2*>(xb + (size_t)(8 * nb) * pitch + 32 * kb);
+            const uint2 x1 = *reinterpret_cast<const uint2*>(xb + (size_t)(8 * nb) * pitch + 32 * kb + 4);
+            mma16816_f16(acc[nb], lo.x, hi.x, lo.y, hi.y, x0.x, x0.y);
+            mma16816_f16(acc[nb], lo.z, hi.z, lo.w, hi.w, x1.x, x1.y);
+          }
+        }
+      }
+    }
+  }
+  // acc[nb][e]: row r0 + g + 8 (e >> 1), image 8 (nb0 + nb) + 2 q + (e & 1)
+#pragma unroll
+  for (int e2 = 0; e2 < 2; ++e2) {
+    const int n = r0 + g + 8 * e2;
+    if (n < N) {
+      const float bv = bias ? bias[n] : 0.f;
+#pragma unroll
+      for (int nb = 0; nb < 4; ++nb)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const int b = b0 + 8 * (nb0 + nb) + 2 * q + j;
+          if (b < B) {
+            float v = acc[nb][2 * e2 + j] + bv;
+            if (RELU) v = fmaxf(v, 0.f);
+            Y[(int64_t)b * ldy + n] = v;
+          }
+        }
+    }
+  }
+}
+
 // ---- attention of ONE query per (image, head) over a key/value set ---------------------------------
 // warp == head.  A key's HD channels are split over LPK = HD/8 lanes (one 128-bit load each), so a warp
 // covers 32/LPK keys per pass with fully-used sectors; passes are unrolled x4 with the loads issued first
@@ -484,8 +657,30 @@ int next_pow2(int v) { int p = 1; while (p < v) p <<= 1; return p; }
 
 template <typename TW>
 int launch_linear(mdc_ctx* ctx, const XSrc& xs, const void* W, const float* bias, float* Y, int64_t ldy, int B, int N, int K,
-                  bool relu, cudaStream_t s) {
+                  bool relu, cudaStream_t s, __half* xh_buf = nullptr) {
   MDC_CHECK_ARG(K % 8 == 0);
+  if constexpr (std::is_same<TW, __half>::value) {
+    // batches of 16 and more on the tensor cores (weights read once per 64 images); LayerNorm / embedding operands are model-width rows
+    const bool plain = xs.mode == XMODE_PLAIN;
+    if (xh_buf && B >= 16 && K % 32 == 0 && (plain ? (K <= MMA_KC || K % MMA_KC == 0) && xs.ldx % 4 == 0 && ((uintptr_t)xs.x & 15) == 0 : K <= MMA_KC)) {
+      XSrc src = xs;
+      if (!plain) {
+        prep_x_half_kernel<<<(B + LIN_WARPS - 1) / LIN_WARPS, LIN_THREADS, 0, s>>>(xs, xh_buf, B, K);
+        MDC_LAUNCH_CHECK(ctx);
+        src = XSrc{}; src.mode = XMODE_HALF; src.xh = xh_buf;
+      }
+      const size_t sm = (size_t)MMA_IMGS * (size_t)((K < MMA_KC ? K : MMA_KC) + MMA_PAD) * sizeof(__half);
+      dim3 grid((N + MMA_ROWS - 1) / MMA_ROWS, (B + MMA_IMGS - 1) / MMA_IMGS);
+      if (relu) {
+        MDC_ENSURE_SMEM(dec_linear_mma_kernel<true>, sm);
+        dec_linear_mma_kernel<true><<<grid, LIN_THREADS, sm, s>>>(src, (const __half*)W, bias, Y, ldy, B, N, K);
+      } else {
+        MDC_ENSURE_SMEM(dec_linear_mma_kernel<false>, sm);
+        dec_linear_mma_kernel<false><<<grid, LIN_THREADS, sm, s>>>(src, (const __half*)W, bias, Y, ldy, B, N, K);
+      }
+      MDC_LAUNCH_CHECK(ctx); return 0;
+    }
+  }
   const size_t smem = (size_t)BT * K * sizeof(float);
   dim3 block(LIN_THREADS);
   const int gy = (B + BT - 1) / BT;
@@ -520,16 +715,18 @@ int launch_linear(mdc_ctx* ctx, const XSrc& xs, const void* W, const float* bias
   MDC_LAUNCH_CHECK(ctx); return 0;
 }
 
-struct Scratch { float *xa, *xb, *xc, *y1, *y2, *y3, *qkv, *qc, *o, *oc, *f1, *lg; };
+struct Scratch { float *xa, *xb, *xc, *y1, *y2, *y3, *qkv, *qc, *o, *oc, *f1, *lg; __half* xh; };
 
 size_t scratch_floats(const mdc_dims& d, int B) {
-  return (size_t)B * ((size_t)d.dim * 9 + (size_t)d.dim * 3 + d.dec_ffn + d.vocab);
+  // + the fp16 operand rows of the tensor-core linears (B x dim halves, behind the step logits, 16-byte aligned)
+  return (size_t)B * ((size_t)d.dim * 9 + (size_t)d.dim * 3 + d.dec_ffn + d.vocab) + 4 + ((size_t)B * d.dim + 1) / 2;
 }
 
 Scratch carve(const mdc_dims& d, int B, void* p) {
   float* f = (float*)p; Scratch s; size_t bd = (size_t)B * d.dim;
   s.xa = f; f += bd; s.xb = f; f += bd; s.xc = f; f += bd; s.y1 = f; f += bd; s.y2 = f; f += bd; s.y3 = f; f += bd;
-  s.qc = f; f += bd; s.o = f; f += bd; s.oc = f; f += bd; s.qkv = f; f += 3 * bd; s.f1 = f; f += (size_t)B * d.dec_ffn; s.lg = f;
+  s.qc = f; f += bd; s.o = f; f += bd; s.oc = f; f += bd; s.qkv = f; f += 3 * bd; s.f1 = f; f += (size_t)B * d.dec_ffn; s.lg = f; f += (size_t)B * d.vocab;
+  s.xh = reinterpret_cast<__half*>((reinterpret_cast<uintptr_t>(f) + 15) & ~(uintptr_t)15);
   return s;
 }
 
@@ -552,7 +749,7 @@ int decode_step_typed(mdc_model* m, const mdc_decode_state* st, int t, cudaStrea
     const void** lw = lw0 + l * MDC_DEC_LAYER_SLOTS;
     // qkv = LNload(prev) . Ws^T + bs; publishes xa
     XSrc x1 = prev; x1.xn_out = sc.xa;
-    MDC_TRY(launch_linear<TW>(ctx, x1, lw[MDC_SA_IN_W], (const float*)lw[MDC_SA_IN_B], sc.qkv, 3 * dim, B, 3 * dim, dim, false, s));
+    MDC_TRY(launch_linear<TW>(ctx, x1, lw[MDC_SA_IN_W], (const float*)lw[MDC_SA_IN_B], sc.qkv, 3 * dim, B, 3 * dim, dim, false, s, sc.xh));
     {
       size_t smem = (size_t)d.dec_heads * (hd + t + 1 + st->pages_per_seq) * sizeof(float);
 #define MDC_SA(HD_)                                                                                                      \
@@ -567,11 +764,11 @@ int decode_step_typed(mdc_model* m, const mdc_decode_state* st, int t, cudaStrea
       MDC_LAUNCH_CHECK(ctx);
     }
     XSrc xo{}; xo.mode = XMODE_PLAIN; xo.x = sc.o; xo.ldx = dim;
-    MDC_TRY(launch_linear<TW>(ctx, xo, lw[MDC_SA_OUT_W], (const float*)lw[MDC_SA_OUT_B], sc.y1, dim, B, dim, dim, false, s));
+    MDC_TRY(launch_linear<TW>(ctx, xo, lw[MDC_SA_OUT_W], (const float*)lw[MDC_SA_OUT_B], sc.y1, dim, B, dim, dim, false, s, sc.xh));
     // cross-attention query from LN1(xa + y1); publishes xb
     XSrc x2{}; x2.mode = XMODE_LN; x2.resid = sc.xa; x2.delta = sc.y1; x2.ln_w = (const float*)lw[MDC_LN1_W]; x2.ln_b = (const float*)lw[MDC_LN1_B];
     x2.eps = 1e-5f; x2.xn_out = sc.xb;
-    MDC_TRY(launch_linear<TW>(ctx, x2, lw[MDC_CA_IN_W], (const float*)lw[MDC_CA_IN_B], sc.qc, dim, B, dim, dim, false, s));
+    MDC_TRY(launch_linear<TW>(ctx, x2, lw[MDC_CA_IN_W], (const float*)lw[MDC_CA_IN_B], sc.qc, dim, B, dim, dim, false, s, sc.xh));
     {
       size_t smem = (size_t)d.dec_heads * (hd + d.n_patches) * sizeof(float);
       const T* ckv = (const T*)st->cross_kv + (int64_t)l * B * d.n_patches * 2 * dim;
@@ -585,19 +782,19 @@ int decode_step_typed(mdc_model* m, const mdc_decode_state* st, int t, cudaStrea
       MDC_LAUNCH_CHECK(ctx);
     }
     XSrc xco{}; xco.mode = XMODE_PLAIN; xco.x = sc.oc; xco.ldx = dim;
-    MDC_TRY(launch_linear<TW>(ctx, xco, lw[MDC_CA_OUT_W], (const float*)lw[MDC_CA_OUT_B], sc.y2, dim, B, dim, dim, false, s));
+    MDC_TRY(launch_linear<TW>(ctx, xco, lw[MDC_CA_OUT_W], (const float*)lw[MDC_CA_OUT_B], sc.y2, dim, B, dim, dim, false, s, sc.xh));
     // FFN
     XSrc x3{}; x3.mode = XMODE_LN; x3.resid = sc.xb; x3.delta = sc.y2; x3.ln_w = (const float*)lw[MDC_LN2_W]; x3.ln_b = (const float*)lw[MDC_LN2_B];
     x3.eps = 1e-5f; x3.xn_out = sc.xc;
-    MDC_TRY(launch_linear<TW>(ctx, x3, lw[MDC_FF1_W], (const float*)lw[MDC_FF1_B], sc.f1, d.dec_ffn, B, d.dec_ffn, dim, true, s));
+    MDC_TRY(launch_linear<TW>(ctx, x3, lw[MDC_FF1_W], (const float*)lw[MDC_FF1_B], sc.f1, d.dec_ffn, B, d.dec_ffn, dim, true, s, sc.xh));
     XSrc xf{}; xf.mode = XMODE_PLAIN; xf.x = sc.f1; xf.ldx = d.dec_ffn;
-    MDC_TRY(launch_linear<TW>(ctx, xf, lw[MDC_FF2_W], (const float*)lw[MDC_FF2_B], sc.y3, dim, B, dim, d.dec_ffn, false, s));
+    MDC_TRY(launch_linear<TW>(ctx, xf, lw[MDC_FF2_W], (const float*)lw[MDC_FF2_B], sc.y3, dim, B, dim, d.dec_ffn, false, s, sc.xh));
     prev = XSrc{}; prev.mode = XMODE_LN; prev.resid = sc.xc; prev.delta = sc.y3; prev.ln_w = (const float*)lw[MDC_LN3_W];
     prev.ln_b = (const float*)lw[MDC_LN3_B]; prev.eps = 1e-5f;
   }
   {
     const int V = d.vocab, Vp2 = next_pow2(V);
-    MDC_TRY(launch_linear<TW>(ctx, prev, gw[MDC_OUT_W], (const float*)gw[MDC_OUT_B], sc.lg, V, B, V, dim, false, s));
+    MDC_TRY(launch_linear<TW>(ctx, prev, gw[MDC_OUT_W], (const float*)gw[MDC_OUT_B], sc.lg, V, B, V, dim, false, s, sc.xh));
     size_t smem = (size_t)(V + Vp2) * sizeof(float);
     MDC_ENSURE_SMEM(dec_select_kernel, smem);
     dec_select_kernel<<<B, SEL_THREADS, smem, s>>>(sc.lg, V, Vp2, t, st->logits, (int64_t)st->logits_ld * V, t + st->logits_row_offset,

@@ -424,8 +424,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           fence_async_smem();
           __syncwarp();
           if (lane == 0 && row0 < M && col0 < N && !GEMM_DBG(ep, 16)) {
-            if constexpr (OUT_F32) tma_reduce_add_2d(&map_d, tile_s, col0, row0);
-            else tma_store_2d(&map_d, tile_s, col0, row0);
+            const int sc = GEMM_DBG(ep, 64) ? 0 : col0, sr = GEMM_DBG(ep, 64) ? 0 : row0;      // 64: every store to tile (0,0)
+            if constexpr (OUT_F32) tma_reduce_add_2d(&map_d, tile_s, sc, sr);
+            else tma_store_2d(&map_d, tile_s, sc, sr);
           }
           if (lane == 0) bulk_commit();
           if (C::kOutBufs == 2) obuf ^= 1;
