@@ -573,22 +573,42 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(NT, MINB) decode_fu
         }
         wait_y();
         if (warp == 0) FINE(l_now, t_now, fi + 1);
+        // the warp's two images in lockstep: each image keeps its own operation sequence (results unchanged), but the two shuffle
+        // butterflies and the two reciprocal square roots overlap instead of running one after the other (900 cycles per image)
+        float v[NB][8], sm[NB], mean[NB], rstd[NB];
+#pragma unroll
+        for (int nb = 0; nb < NB; ++nb) {
+          const int img = min(warp + 8 * nb, GMX - 1);
+          sm[nb] = 0.f;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { v[nb][j] = xres[img * DM + lane + 32 * j] + yrecv[img * DM + lane + 32 * j]; sm[nb] += v[nb][j]; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+          for (int nb = 0; nb < NB; ++nb) sm[nb] += __shfl_xor_sync(0xffffffffu, sm[nb], o);
+#pragma unroll
+        for (int nb = 0; nb < NB; ++nb) {
+          mean[nb] = sm[nb] * (1.0f / DM);
+          float q = 0.f;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { const float d = v[nb][j] - mean[nb]; q += d * d; }
+          sm[nb] = q;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+          for (int nb = 0; nb < NB; ++nb) sm[nb] += __shfl_xor_sync(0xffffffffu, sm[nb], o);
+#pragma unroll
+        for (int nb = 0; nb < NB; ++nb) rstd[nb] = 1.0f / sqrtf(sm[nb] * (1.0f / DM) + 1e-5f);
 #pragma unroll
         for (int nb = 0; nb < NB; ++nb) {
           const int img = warp + 8 * nb;
           if (img < G) {
-            float v[8]; float s = 0.f;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) { v[j] = xres[img * DM + lane + 32 * j] + yrecv[img * DM + lane + 32 * j]; s += v[j]; }
-            const float mean = warp_sum(s) * (1.0f / DM);
-            float q = 0.f;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) { const float d = v[j] - mean; q += d * d; }
-            const float rstd = 1.0f / sqrtf(warp_sum(q) * (1.0f / DM) + 1e-5f);
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               const int c = lane + 32 * j;
-              const float xn = (v[j] - mean) * rstd * gw[j] + gb[j];
+              const float xn = (v[nb][j] - mean[nb]) * rstd[nb] * gw[j] + gb[j];
               xres[img * DM + c] = xn;
               store_h(xh, img * XP + c, xn);
             }
