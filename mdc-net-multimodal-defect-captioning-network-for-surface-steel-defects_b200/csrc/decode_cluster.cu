@@ -114,6 +114,7 @@ struct __align__(64) FusedParams {
   const float* uniforms; int uniforms_ld; int top_k; float top_p; int forced;
   int t_begin, t_end;
   long long* trace; int trace_t;           // developer aid: phase timestamps of CTA 0 at step trace_t (MDC_DECODE_TRACE_PTR)
+  float ref_margin;                        // developer build: softmax reference-maximum margin (MDC_DECODE_REF_MARGIN; the product build uses 64)
 };
 
 // ---- PTX helpers ------------------------------------------------------------------------------------------
@@ -273,7 +274,7 @@ struct AttnState { float m, ls; float o[2][4]; };
 // >= nkeys are masked; padw: PAD bit rows (or null).
 template <int N>
 __device__ __forceinline__ void attn_tile(const uint32_t (&kp)[N], const uint32_t (&vp)[N], const uint32_t (&aq)[N][2][2], int key0, int nkeys,
-                                          const uint32_t* const (&padw)[N], AttnState (&st)[N]) {
+                                          const uint32_t* const (&padw)[N], AttnState (&st)[N], float margin) {
   const int lane = threadIdx.x & 31, q4 = lane & 3;
   uint32_t kb[N][2][4], va[N][2][4];
 #pragma unroll
@@ -322,7 +323,7 @@ __device__ __forceinline__ void attn_tile(const uint32_t (&kp)[N], const uint32_
 #pragma unroll
   for (int n = 0; n < N; ++n) {
     // first tile: m = -inf, and the tile holds a valid key (key0 < nkeys), so some lane sees a finite score and votes
-    if (__any_sync(0xffffffffu, mx[n] > st[n].m + 64.0f)) {
+    if (__any_sync(0xffffffffu, mx[n] > st[n].m + margin)) {
       float t = fmaxf(mx[n], __shfl_xor_sync(0xffffffffu, mx[n], 1));
       t = fmaxf(t, __shfl_xor_sync(0xffffffffu, t, 2));          // the quad holds all 16 keys of the tile: the tile maximum, in every lane
       const float m_new = fmaxf(st[n].m, t);
@@ -402,6 +403,11 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(NT, MINB) decode_fu
   cluster_sync_all();
 
   const float scale = rsqrtf((float)HD) * LOG2E;      // scores in log2 units: p = exp2(s - m)
+#ifdef MDC_DEVTOOLS
+  const float ref_margin = P.ref_margin;               // tools/ref_margin_check.py: margin 0 = a running maximum, the rescale path on every new maximum
+#else
+  constexpr float ref_margin = 64.0f;
+#endif
   const int L = P.layers, S = P.S;
   const int nck = (S + 15) >> 4;                      // cross-attention key chunks (16 keys each)
 
@@ -686,7 +692,7 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(NT, MINB) decode_fu
               if (two) {
                 const uint32_t kp[2] = {st + warp * 2048u, st + (warp + 8) * 2048u};
                 const uint32_t vp[2] = {kp[0] + 1024u, kp[1] + 1024u};
-                attn_tile<2>(kp, vp, aq, c * 16, nkeys, padw, as);
+                attn_tile<2>(kp, vp, aq, c * 16, nkeys, padw, as, ref_margin);
                 done = true;
               }
             }
@@ -695,7 +701,7 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(NT, MINB) decode_fu
               const uint32_t aq1[1][2][2] = {{{aq[0][0][0], aq[0][0][1]}, {aq[0][1][0], aq[0][1][1]}}};
               const uint32_t* pw1[1] = {padw[0]};
               AttnState a1[1] = {as[0]};
-              attn_tile<1>(kp, vp, aq1, c * 16, nkeys, pw1, a1);
+              attn_tile<1>(kp, vp, aq1, c * 16, nkeys, pw1, a1, ref_margin);
               as[0] = a1[0];
             }
           }
@@ -1198,10 +1204,11 @@ int decode_cluster_launch(mdc_model* m, const mdc_decode_state* st, int t_begin,
   P.confs = st->confs; P.confs_ld = st->confs_ld;
   P.uniforms = st->uniforms; P.uniforms_ld = st->uniforms_ld; P.top_k = st->top_k; P.top_p = st->top_p; P.forced = st->forced;
   P.t_begin = t_begin; P.t_end = t_end;
-  P.trace = nullptr; P.trace_t = -1;
+  P.trace = nullptr; P.trace_t = -1; P.ref_margin = 64.0f;
   int ipc = st->images_per_cluster, cps = st->ctas_per_sm;
 #ifdef MDC_DEVTOOLS   // developer build only (tools/decode_trace.py): phase-trace buffer and variant overrides from the environment
   if (const char* tp = getenv("MDC_DECODE_TRACE_PTR")) { P.trace = (long long*)strtoull(tp, nullptr, 0); const char* tt = getenv("MDC_DECODE_TRACE_T"); P.trace_t = tt ? atoi(tt) : t_begin; }
+  if (const char* e = getenv("MDC_DECODE_REF_MARGIN")) P.ref_margin = (float)atof(e);
   if (const char* e = getenv("MDC_DECODE_IPC")) ipc = atoi(e);
   if (const char* e = getenv("MDC_DECODE_CPS")) cps = atoi(e);
 #endif

@@ -249,6 +249,47 @@ def test_cluster_decode_kernel_matches_generic_kernels(model_p, golden, B, T):
     assert agree > 0.5, agree
 
 
+def test_cluster_decode_with_runaway_attention_scores_stays_finite_and_consistent():
+    """The fused kernel's attention keeps the maximum of an image's FIRST key tile as the softmax reference and raises it (rescaling the
+    running state) only when a later score exceeds it by 64 log2-units.  With ordinary weights that path never runs, so force it: the
+    attention in-projections of two layers scaled by 16 (scores x 256: one-hot-like softmax, score ranges of hundreds of nats).
+    The 8- and 16-image instantiations must stay finite and bitwise equal; against the per-operation kernels (true maximum, fp32
+    queries) only a loose bound holds -- a bf16 rounding of a score of 300 nats moves a softmax weight by e^0.6."""
+    m = cases.build_product_model("P", seed=3, gamma_seed=5)
+    with torch.no_grad():
+        for l in (0, 3):
+            layer = m.decoder.decoder.layers[l]
+            layer.self_attn.in_proj_weight[:512] *= 16.0          # q and k rows
+            layer.multihead_attn.in_proj_weight[:512] *= 16.0
+    m = m.to(DEV).set_precision("bf16")
+    B, T = 16, 40
+    x = cases.images(B, seed=33).to(DEV)
+    with M.decode_options(per_op_kernels=True):
+        tg, _ = m.generate_tokens(x, T, use_graph=False)
+        lg = m.predict(x, tg[:, :T].long())[:, 1:T + 1]
+    outs = []
+    for ipc in (8, 16):
+        with M.decode_options(prefill=False, images_per_cluster=ipc):
+            outs.append(m.predict(x, tg[:, :T].long())[:, 1:T + 1])
+    assert torch.isfinite(outs[0]).all() and torch.equal(outs[0], outs[1])
+    err, mean = (lg - outs[0]).abs().max().item(), (lg - outs[0]).abs().mean().item()
+    print(f"runaway scores: fused vs per-operation kernels max|dlogit| = {err:.2e}, mean = {mean:.2e}")
+    assert mean < 3e-2 and G.cos(outs[0], lg) > 0.999, (err, mean)
+
+
+def test_softmax_rescale_path_against_a_running_maximum_in_the_developer_build():
+    """tools/ref_margin_check.py: the developer build of the library reads the reference-maximum margin from the environment; margin 0
+    turns the same code into a running maximum (the rescale path on every new maximum).  Both are exact softmax evaluations."""
+    import os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    dev = os.path.join(root, "mdc-net-multimodal-defect-captioning-network-for-surface-steel-defects_b200", "libmdc_b200_dev.so")
+    if not os.path.exists(dev):
+        pytest.skip("developer build (build.py --devtools) not present")
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "ref_margin_check.py")], capture_output=True, text=True, timeout=600)
+    print(r.stdout[-400:], r.stderr[-400:])
+    assert r.returncode == 0 and "ok" in r.stdout
+
+
 @pytest.mark.parametrize("B,T", [(13, 30), (37, 40), (64, 99)])
 def test_cluster_decode_16_images_per_cluster_is_bitwise_the_8_image_kernel(model_p, B, T):
     """The two-column-block instantiation of the fused kernel (up to 16 images per cluster pass: what the batch pipeline asks
