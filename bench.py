@@ -301,6 +301,9 @@ def roofline_probe(M, dev, peaks, B):
 
 
 # ---- one workload through the batch pipeline ------------------------------------------------------------------------------------
+PIPE_KW = {}          # --decode-streams / --depth: GenerationPipeline operating point (defaults: 4 streams, 6 plans)
+
+
 def run_workload(M, wl, B, steps, warmup, dev, rank, world, dist, peaks, full):
     """Returns the fields of one bench line for workload `wl` at per-rank batch B.  full: also serial / e2e / roofline extras."""
     T, S, img, top_k = wl["T"], wl["S"], wl["img"], wl["top_k"]
@@ -321,7 +324,7 @@ def run_workload(M, wl, B, steps, warmup, dev, rank, world, dist, peaks, full):
         gt[..., 2:] = gt[..., :2] + 8 + torch.rand(B, 5, 2, generator=gg) * 56
         gt[torch.rand(B, 5, generator=gg) < 0.3] = 0
         gt = gt.to(dev)
-    pipe = M.GenerationPipeline(model, B, T, top_k=top_k)
+    pipe = M.GenerationPipeline(model, B, T, top_k=top_k, **PIPE_KW)
     F = T1 + C + ((5 * max(1, (T1 + 4) // 5)) if with_boxes else 0)
 
     def steps_pipelined(k, sink):
@@ -428,6 +431,8 @@ def run_workload(M, wl, B, steps, warmup, dev, rank, world, dist, peaks, full):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--decode-streams", type=int, default=0)
+    ap.add_argument("--depth", type=int, default=0)
     ap.add_argument("--steps", type=int, default=100)      # 100 steps ~ 0.5 s pipelined: the fill and drain of the 6-deep pipeline (~8 ms) stay below 2 %
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
@@ -437,6 +442,10 @@ def main():
     ap.add_argument("--no-other-configs", action="store_true")
     ap.add_argument("--profile", action="store_true", help="1 warm-up + 1 serial step only (for an ncu launch list)")
     args = ap.parse_args()
+    if args.decode_streams:
+        PIPE_KW["decode_streams"] = args.decode_streams
+    if args.depth:
+        PIPE_KW["depth"] = args.depth
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
