@@ -818,12 +818,15 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(NT, MINB) decode_fu
             }
             push_o(img, out);
           }
+          // this layer's KV append: the generic->async proxy fence (~1200 cycles) of the appending threads runs while they wait for the
+          // attention-output gather (it used to sit at the head of LayerNorm 1, which was ~1000 cycles longer than LayerNorm 2)
+          if (tid >= APP0 && tid - APP0 < G * 8) asm volatile("fence.proxy.async;" ::: "memory");
           wait_o();
           TRACE(t);   // 4: o gathered
           // ---- self out-proj slice -> all-gather -> LN1 ------------------------------------------------------------
           proj32_push(sbase + Y::OFF_OH, P.b_so[l]);
           TRACE(t);   // 5: out-proj pushed
-          layer_norm(P.ln1w[l], P.ln1b[l], true);
+          layer_norm(P.ln1w[l], P.ln1b[l]);
           TRACE(t);   // 6: LN1
 
           // ---- cross-attention query slice -------------------------------------------------------------------------
