@@ -101,6 +101,49 @@ __global__ void __launch_bounds__(256) layernorm_rows_kernel(const float* __rest
 
 // ---- encoder tail: final LN (eps 1e-6), drop cls (model.py:23 features[:,1:]), AdaptiveAvgPool1d over
 // channels (model.py:19), + encoder_pos_embed (model.py:103-105).  Warp per patch token.
+// D = NV * 128 channels pooled in adjacent pairs (AdaptiveAvgPool1d(D / 2)): the row stays in registers (one read of the residual
+// stream instead of three), a lane's float4 yields two pooled outputs.  Same arithmetic as the generic kernel below.
+template <typename TO, int NV>
+__global__ void __launch_bounds__(256) encoder_tail_pairs_kernel(const float* __restrict__ h, const float* __restrict__ w, const float* __restrict__ b,
+                                                                 float eps, const float* __restrict__ enc_pos, float* __restrict__ enc_out,
+                                                                 TO* __restrict__ memory, int B, int n) {
+  constexpr int D = NV * 128, OD = D / 2;
+  const int lane = threadIdx.x & 31;
+  const int warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (warp >= B * n) return;
+  const int bi = warp / n, pi = warp % n;
+  const float* xr = h + ((int64_t)bi * (n + 1) + 1 + pi) * D;
+  float4 v[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) v[i] = *reinterpret_cast<const float4*>(xr + i * 128 + lane * 4);
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  const float mean = warp_sum(s) / (float)D;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const float a0 = v[i].x - mean, a1 = v[i].y - mean, a2 = v[i].z - mean, a3 = v[i].w - mean;
+    q += (a0 * a0 + a1 * a1) + (a2 * a2 + a3 * a3);
+  }
+  const float rstd = 1.0f / sqrtf(warp_sum(q) / (float)D + eps);
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = i * 128 + lane * 4;
+    const float4 g = __ldg(reinterpret_cast<const float4*>(w + c)), bb = __ldg(reinterpret_cast<const float4*>(b + c));
+    const float y0 = (v[i].x - mean) * rstd * g.x + bb.x, y1 = (v[i].y - mean) * rstd * g.y + bb.y;
+    const float y2 = (v[i].z - mean) * rstd * g.z + bb.z, y3 = (v[i].w - mean) * rstd * g.w + bb.w;
+    const float p0 = (0.f + y0 + y1) / 2.0f, p1 = (0.f + y2 + y3) / 2.0f;
+    const int o = c >> 1;
+    const int64_t oi = ((int64_t)bi * n + pi) * OD + o;
+    if (enc_out) *reinterpret_cast<float2*>(enc_out + oi) = make_float2(p0, p1);
+    if (memory) {
+      const float2 ep = __ldg(reinterpret_cast<const float2*>(enc_pos + (int64_t)pi * OD + o));
+      memory[oi] = from_f<TO>(p0 + ep.x); memory[oi + 1] = from_f<TO>(p1 + ep.y);
+    }
+  }
+}
+
 template <typename TO>
 __global__ void encoder_tail_kernel(const float* __restrict__ h, const float* __restrict__ w, const float* __restrict__ b,
                                     float eps, const float* __restrict__ enc_pos, float* __restrict__ enc_out,
@@ -238,6 +281,11 @@ int k_encoder_tail(mdc_ctx* ctx, int dtype, const float* h, const float* w, cons
   const int wpb = 8;
   int grid = (B * n + wpb - 1) / wpb;
   size_t smem = (size_t)wpb * D * sizeof(float);
+  if (D == 512 && out_dim == 256) {       // deit3_medium -> 256: rows in registers, one pass over the residual stream
+    if (dtype == MDC_F32) encoder_tail_pairs_kernel<float, 4><<<grid, wpb * 32, 0, s>>>(h, w, b, eps, enc_pos, enc_out, (float*)memory, B, n);
+    else encoder_tail_pairs_kernel<bf16, 4><<<grid, wpb * 32, 0, s>>>(h, w, b, eps, enc_pos, enc_out, (bf16*)memory, B, n);
+    MDC_LAUNCH_CHECK(ctx); return 0;
+  }
   if (dtype == MDC_F32) encoder_tail_kernel<float><<<grid, wpb * 32, smem, s>>>(h, w, b, eps, enc_pos, enc_out, (float*)memory, B, n, D, out_dim);
   else encoder_tail_kernel<bf16><<<grid, wpb * 32, smem, s>>>(h, w, b, eps, enc_pos, enc_out, (bf16*)memory, B, n, D, out_dim);
   MDC_LAUNCH_CHECK(ctx); return 0;
