@@ -343,37 +343,42 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const float* sg = s_gamma + as * BN + half * HALF_COLS;
       if (GEMM_DBG(ep, 1)) {
       } else if constexpr (EPI == MDC_EPI_PATCH) {
-        // rows are re-mapped past each image's cls slot, so a 32-row box is not contiguous in the output: direct stores
-        const bool row_ok = row < M;
-        const int img = row / ep.period;
-        const int64_t orow = row + img + 1;
-        const float* posrow = ep.aux0 + (int64_t)(row - img * ep.period) * ep.ldd;
+        // rows are re-mapped past each image's cls slot, so a 32-row box is not contiguous in the output (no TMA store).  The chunk goes
+        // through the warp's swizzled staging tile and leaves it in ROW-COALESCED order: eight lanes cover the 128 bytes of a row (four
+        // rows per instruction) for the positional-table load and the store -- the thread-per-row form touched 32 lines per instruction
+        // and made this epilogue three times the main loop (35 us for a 10 GFLOP GEMM).
+        const uint32_t stage_out = smem_u32(smem_out) + (warp - 2) * (C::kOutBufs * C::kOutBufBytes);
+        static_assert(C::kOutBufBytes >= 4096, "one 32-row x 128-byte staging tile per epilogue warp");
 #pragma unroll 1
         for (int c0 = 0; c0 < HALF_COLS; c0 += 32) {
           const int col0 = n0 + half * HALF_COLS + c0;
-          const bool any = row_ok && col0 < N;
-          const bool full32 = (col0 + 32 <= N);
-          float4 rz[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) rz[j] = (any && full32) ? *reinterpret_cast<const float4*>(posrow + col0 + 4 * j) : make_float4(0, 0, 0, 0);
           uint32_t v[32];
           tmem_ld32(taddr + c0, v);
           tmem_ld_wait();
-          if (any) {
-            float* dst = reinterpret_cast<float*>(ep.D) + orow * ep.ldd + col0;
-            if (full32) {
+          const uint32_t row_s = stage_out + lane * 128;
 #pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const float4 b4 = *reinterpret_cast<const float4*>(sb + c0 + 4 * j);
-                float4 o;
-                o.x = __uint_as_float(v[4 * j]) + b4.x + rz[j].x; o.y = __uint_as_float(v[4 * j + 1]) + b4.y + rz[j].y;
-                o.z = __uint_as_float(v[4 * j + 2]) + b4.z + rz[j].z; o.w = __uint_as_float(v[4 * j + 3]) + b4.w + rz[j].w;
-                *reinterpret_cast<float4*>(dst + 4 * j) = o;
-              }
-            } else {
-              for (int jj = 0; jj < 32 && col0 + jj < N; ++jj) dst[jj] = __uint_as_float(v[jj]) + sb[c0 + jj] + posrow[col0 + jj];
+          for (int j = 0; j < 8; ++j) {
+            const float4 b4 = *reinterpret_cast<const float4*>(sb + c0 + 4 * j);
+            sts128(row_s + ((j ^ (lane & 7)) << 4), __float_as_uint(__uint_as_float(v[4 * j]) + b4.x), __float_as_uint(__uint_as_float(v[4 * j + 1]) + b4.y),
+                   __float_as_uint(__uint_as_float(v[4 * j + 2]) + b4.z), __float_as_uint(__uint_as_float(v[4 * j + 3]) + b4.w));
+          }
+          __syncwarp();
+          const int ch = lane & 7, col = col0 + 4 * ch;
+          const int img0 = row0 / ep.period;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int rl = i * 4 + (lane >> 3), r = row0 + rl;
+            float4 x;
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w) : "r"(stage_out + rl * 128 + ((ch ^ (rl & 7)) << 4)));
+            if (r < M && col < N) {
+              int img = img0, pr = r - img0 * ep.period;
+              if (pr >= ep.period) { pr -= ep.period; ++img; }                     // a 32-row chunk crosses at most one image boundary
+              const float4 pz = __ldg(reinterpret_cast<const float4*>(ep.aux0 + (int64_t)pr * ep.ldd + col));
+              *reinterpret_cast<float4*>(reinterpret_cast<float*>(ep.D) + (int64_t)(r + img + 1) * ep.ldd + col) =
+                  make_float4(x.x + pz.x, x.y + pz.y, x.z + pz.z, x.w + pz.w);
             }
           }
+          __syncwarp();
         }
       } else {
         // TMEM -> registers -> epilogue math -> swizzled staging tile in shared memory -> one TMA store (bf16 outputs) or TMA
@@ -576,6 +581,7 @@ int gemm_tc_launch(mdc_ctx* ctx, int epilogue, const void* A, int64_t lda, const
                    const float* bias, const float* aux0, int period, int M, int N, int K, cudaStream_t s, int f16) {
   MDC_CHECK_ARG(((uintptr_t)A & 15) == 0 && ((uintptr_t)W & 15) == 0 && ((uintptr_t)D & 15) == 0);
   MDC_CHECK_ARG(ldd % 8 == 0);
+  if (epilogue == MDC_EPI_PATCH) MDC_CHECK_ARG(period >= 32);      // a 32-row epilogue chunk crosses at most one image boundary
   // tile width: the widest tile that still gives every SM one tile (128 x 256 tiles need 1/3 less operand traffic per flop than
   // 128 x 128 ones; with N = 512 that is 1.3 waves instead of 2.7 -- the same time for the kernel alone, ~1 % more images/s in the
   // batch pipeline, where co-scheduled kernels fill the tail and SM-time is what counts); narrow N uses narrow tiles
