@@ -372,6 +372,9 @@ template <bool kTrace, int NB, int NSTG, int MINB>
 __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(NT, MINB) decode_fused_kernel(const __grid_constant__ FusedParams P) {
   using Y = Lay<NB, NSTG, NB == 2 || MINB == 2>;
   constexpr int GMX = Y::GMX, NS = Y::NS, STAGE = Y::STAGE;
+  // paired K/V hand-overs need ring depth: with four slots the producer can only run one pair ahead and the copies become visible
+  // (measured: 10-slot ring 7.95 -> 7.48 ms per launch, 4-slot rings 12.2 -> 13.3 ms)
+  constexpr bool KV_PAIRS = NS >= 6;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);      // pointer arithmetic keeps the shared address space
@@ -483,15 +486,44 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(NT, MINB) decode_fu
         }
         advance();
       };
+      // (deep rings only, KV_PAIRS) Two consecutive chunks as ONE hand-over: both slots' copies complete on the first slot's barrier (the second slot's barrier
+      // gets a plain arrival so that its phase keeps step with the ring); the consumers wait once per 32 keys instead of once per 16
+      // (a wait on an already complete barrier plus the release and loop cost ~235 of the ~745 cycles a 16-key tile took).
+      auto kv_copy = [&](bool cross, int l, int c, uint32_t st, uint32_t fb) {
+        if (cross) {
+          const int img = img0 + (ckv_blocks ? lane * 8 : lane);
+          const uint8_t* src = P.ckv_pack + (((((size_t)l * nb8 + (img >> 3)) * CS + rank) * nck + c) * 8 + (img & 7)) * 2048;
+          if (ckv_blocks) { if (lane < (G >> 3)) bulk_g2s(st + lane * 16384, src, 16384, fb); }
+          else if (lane < G) bulk_g2s(st + lane * 2048, src, 2048, fb);
+        } else if (lane < G) {
+          bulk_g2s(st + lane * 2048, (const uint8_t*)P.kv_pool + (((size_t)pages[lane * 32 + c] * L + l) * CS + rank) * 2048, 2048, fb);
+        }
+      };
+      auto emit_kv2 = [&](bool cross, int l, int c) {
+        const uint32_t st0 = acquire(); const uint32_t fb0 = bar(BAR_FULL + slot);
+        advance();
+        const uint32_t st1 = acquire(); const uint32_t fb1 = bar(BAR_FULL + slot);
+        advance();
+        if (lane == 0) { mbar_expect_tx(fb0, 2 * G * 2048); mbar_arrive(fb1); }
+        __syncwarp();
+        kv_copy(cross, l, c, st0, fb0);
+        kv_copy(cross, l, c + 1, st1, fb0);
+      };
+      auto emit_kv_all = [&](bool cross, int l, int n) {
+        int c = 0;
+        if (KV_PAIRS)
+          for (; c + 1 < n; c += 2) emit_kv2(cross, l, c);
+        for (; c < n; ++c) emit_kv(cross, l, c);
+      };
       for (int t = P.t_begin; t < P.t_end; ++t) {
         const int npg = (t + P.PT - 1) / P.PT;     // pages (= 16-key chunks) holding keys 0..t-1
         for (int l = 0; l < L; ++l) {
           wl = P.wpack + ((size_t)l * CS + rank) * BLOCKS_PER_LAYER * BLK_BYTES;
           emit_proj(0, 3);                                            // in-proj: own head's q rows, k rows, v rows
-          for (int c = 0; c < npg; ++c) emit_kv(false, l, c);        // self-KV pages
+          emit_kv_all(false, l, npg);                                 // self-KV pages
           emit_proj(3, 1);                                            // self out-proj rows
           emit_proj(4, 1);                                            // cross-q rows
-          for (int c = 0; c < nck; ++c) emit_kv(true, l, c);         // cross K/V chunks
+          emit_kv_all(true, l, nck);                                  // cross K/V chunks
           emit_proj(5, 1);                                            // cross out-proj rows
           emit_proj(6, 8);                                            // FFN1: own hidden rows
           emit_proj(14, 8);                                           // FFN2: K-split over the own hidden columns
@@ -682,10 +714,7 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(NT, MINB) decode_fu
         const bool two = NB == 2 && warp + 8 < G;
         // (probing the next stage's barrier early, so that its ~150-cycle try_wait overlaps the current chunk's MMA chain, was
         //  measured SLOWER: 12.73 -> 13.26 ms per launch, profiles/r2 notes)
-        for (int c = 0; c < nchunk; ++c) {
-          if (warp == 0 && c < 8) FINE(l_now, t_now, 20 + c * 3);
-          const uint32_t st = stage_wait();
-          if (warp == 0 && c < 8) FINE(l_now, t_now, 21 + c * 3);
+        auto tile = [&](uint32_t st, int c) {          // one 16-key tile of the warp's images from the stage at `st`
           if (warp < G) {
             bool done = false;
             if constexpr (NB == 2) {
@@ -705,8 +734,24 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(NT, MINB) decode_fu
               as[0] = a1[0];
             }
           }
+        };
+        int c = 0;
+        if (KV_PAIRS)
+        for (; c + 1 < nchunk; c += 2) {               // two chunks per hand-over: one wait (the first slot's barrier covers both copies)
+          if (warp == 0 && c < 16) FINE(l_now, t_now, 20 + (c >> 1) * 3);
+          const uint32_t st0 = stage_wait();
+          const uint32_t st1 = sbase + Y::OFF_RING + (slot + 1 == NS ? 0u : slot + 1) * STAGE;
+          if (warp == 0 && c < 16) FINE(l_now, t_now, 21 + (c >> 1) * 3);
+          tile(st0, c);
+          tile(st1, c + 1);
           stage_release();
-          if (warp == 0 && c < 8) FINE(l_now, t_now, 22 + c * 3);
+          stage_release();
+          if (warp == 0 && c < 16) FINE(l_now, t_now, 22 + (c >> 1) * 3);
+        }
+        for (; c < nchunk; ++c) {
+          const uint32_t st = stage_wait();
+          tile(st, c);
+          stage_release();
         }
 #pragma unroll
         for (int nb = 0; nb < NB; ++nb) {
