@@ -163,6 +163,12 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
+// L2 prefetch of a contiguous block (no shared memory involved): the producer warp pulls the cross-K/V chunks it will copy a few
+// stages later from HBM into L2, so that the copies themselves meet L2 latency -- the ring holds at most three stages ahead, which
+// at HBM latency is the per-SM streaming rate the cross-attention phase ran at (~40 B/clk)
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void ldsm_x4(uint32_t* r, uint32_t addr) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
 }
@@ -509,17 +515,27 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(NT, MINB) decode_fu
         kv_copy(cross, l, c, st0, fb0);
         kv_copy(cross, l, c + 1, st1, fb0);
       };
+      constexpr int PF_AHEAD = 4;                  // chunks of cross-K/V prefetched into L2 ahead of the ring
+      auto prefetch_ckv = [&](int l, int c) {
+        if (c < nck) {
+          const int img = img0 + (ckv_blocks ? lane * 8 : lane);
+          const uint8_t* src = P.ckv_pack + (((((size_t)l * nb8 + (img >> 3)) * CS + rank) * nck + c) * 8 + (img & 7)) * 2048;
+          if (ckv_blocks) { if (lane < (G >> 3)) bulk_prefetch_l2(src, 16384); }
+          else if (lane < G) bulk_prefetch_l2(src, 2048);
+        }
+      };
       auto emit_kv_all = [&](bool cross, int l, int n) {
         int c = 0;
         if (KV_PAIRS)
-          for (; c + 1 < n; c += 2) emit_kv2(cross, l, c);
-        for (; c < n; ++c) emit_kv(cross, l, c);
+          for (; c + 1 < n; c += 2) { emit_kv2(cross, l, c); if (cross) { prefetch_ckv(l, c + PF_AHEAD); prefetch_ckv(l, c + PF_AHEAD + 1); } }
+        for (; c < n; ++c) { emit_kv(cross, l, c); if (cross) prefetch_ckv(l, c + PF_AHEAD); }
       };
       for (int t = P.t_begin; t < P.t_end; ++t) {
         const int npg = (t + P.PT - 1) / P.PT;     // pages (= 16-key chunks) holding keys 0..t-1
         for (int l = 0; l < L; ++l) {
           wl = P.wpack + ((size_t)l * CS + rank) * BLOCKS_PER_LAYER * BLK_BYTES;
           emit_proj(0, 3);                                            // in-proj: own head's q rows, k rows, v rows
+          for (int c = 0; c < PF_AHEAD; ++c) prefetch_ckv(l, c);      // this layer's first cross-K/V chunks: into L2 during self-attention
           emit_kv_all(false, l, npg);                                 // self-KV pages
           emit_proj(3, 1);                                            // self out-proj rows
           emit_proj(4, 1);                                            // cross-q rows
