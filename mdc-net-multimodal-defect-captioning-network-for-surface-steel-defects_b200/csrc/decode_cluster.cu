@@ -562,10 +562,11 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(NT, MINB) decode_fu
     } else {
       // =================================== CONSUMER WARPS ==================================================
       long long cons_wait = 0, exch_wait = 0;
+      int wait_phase = 0;                       // trace build: which phase the stage waits of warp 0 are charged to (trace[210 + phase])
       auto stage_wait = [&]() -> uint32_t {
         const long long c0 = kTrace ? clock64() : 0;
         mbar_wait(bar(BAR_FULL + slot), phase);
-        if (kTrace) cons_wait += clock64() - c0;
+        if (kTrace) { const long long d = clock64() - c0; cons_wait += d; if (tid == 0 && blockIdx.x == 0) P.trace[210 + wait_phase] += d; }
         return sbase + Y::OFF_RING + slot * STAGE;
       };
       auto xwait = [&](int which, uint32_t& ph) {    // wait for a push-style exchange
@@ -810,6 +811,7 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(NT, MINB) decode_fu
         cbar();
         for (int l = 0; l < L; ++l) {
           TRACE(t);   // 0: layer start
+          if (kTrace) wait_phase = 0;
           // ---- self-attention in-proj: own head's q (warps 0-1), k (warps 2-3), v (warps 4-5), one 32-row block each ------
           {
             const float* bi = P.b_in[l];
@@ -858,6 +860,7 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(NT, MINB) decode_fu
           TRACE(t);   // 2: append
           // ---- self-attention, head `rank`: keys [0,t) from the paged cache in chunks of one page, then the step's own key (still in
           //      shared memory) joins as one more online-softmax term ---------------------------------------------------------------
+          if (kTrace) wait_phase = 1;
           attention(npg, t, true, -1, t);
           TRACE(t);   // 3: self attention
 #pragma unroll
@@ -885,11 +888,13 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(NT, MINB) decode_fu
           wait_o();
           TRACE(t);   // 4: o gathered
           // ---- self out-proj slice -> all-gather -> LN1 ------------------------------------------------------------
+          if (kTrace) wait_phase = 2;
           proj32_push(sbase + Y::OFF_OH, P.b_so[l]);
           TRACE(t);   // 5: out-proj pushed
           layer_norm(P.ln1w[l], P.ln1b[l]);
           TRACE(t);   // 6: LN1
 
+          if (kTrace) wait_phase = 3;
           // ---- cross-attention query slice -------------------------------------------------------------------------
           {
             const float* bc = P.b_ca[l];
@@ -910,6 +915,7 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(NT, MINB) decode_fu
           cbar();
           TRACE(t);   // 7: cross q
           // ---- cross-attention over the S memory keys (HBM/L2-resident cross-K/V), 16-key chunks ------------------------------
+          if (kTrace) wait_phase = 4;
           attention(nck, S, false, l, t);
           TRACE(t);   // 8: cross attention
 #pragma unroll
@@ -921,11 +927,13 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(NT, MINB) decode_fu
           }
           wait_o();
           TRACE(t);   // 9: o gathered
+          if (kTrace) wait_phase = 5;
           proj32_push(sbase + Y::OFF_OH, P.b_co[l]);
           TRACE(t);   // 10: cross out-proj pushed
           layer_norm(P.ln2w[l], P.ln2b[l], false, l, t, 60);
           TRACE(t);   // 11: LN2
 
+          if (kTrace) wait_phase = 6;
           // ---- FFN1: own 256 hidden units as 8 blocks of 32 rows (block b -> warp pair b % 4), ReLU, kept local as the FFN2 operand ----
           {
             const float* bf = P.b_f1[l] + rank * FS + (warp & 1) * 16 + fg;
@@ -946,6 +954,7 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(NT, MINB) decode_fu
           }
           cbar();
           TRACE(t);   // 12: FFN1
+          if (kTrace) wait_phase = 7;
           // ---- FFN2 as a K-split, 32 output features per block: partial sums pushed straight to the CTA that owns the columns ----
           proj_blocks(8, [&](int b, uint32_t blk, int mt) {
             float acc[NB][4];
@@ -982,6 +991,7 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(NT, MINB) decode_fu
           TRACE(t);   // 15: LN3
 
         }
+          if (kTrace) wait_phase = 8;
         // ---- vocabulary head: own 40 rows -> logits to the caller's tensor and to the CTA that selects for the image ---
         const bool want_conf = P.confs && (t % 4 == 0);
         const bool need_select = !P.forced || want_conf;

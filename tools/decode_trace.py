@@ -31,6 +31,8 @@ print("mean per layer:")
 for nm, v in zip(names, tot):
     print(f"  {nm:22s} {v / L:8.0f} cyc")
 print(f"  whole loop: consumer warp 0 blocked on ring stages {tr[200]} cyc, on exchanges {tr[201]} cyc; producer blocked on free slots {tr[202]} cyc")
+wn = ["in-proj", "self K/V", "self out-proj", "cross q", "cross K/V", "cross out-proj", "FFN1", "FFN2", "head"]
+print("  ring-stage waits of warp 0 by phase (whole loop, cycles): " + ", ".join(f"{n} {tr[210 + i]}" for i, n in enumerate(wn)))
 print(f"  layer total {sum(tot)/L:.0f} cyc; head {tr[L*16]-tr[L*16-1]} cyc; select+token exchange {tr[L*16+1]-tr[L*16]} cyc; step {tr[L*16+1]-tr[0]} cyc")
 
 f = tr[100:180]
