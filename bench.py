@@ -52,6 +52,10 @@ WORKLOADS = {
     5: dict(name="configs[4]", img=224, S=196, B=256, T=256, top_k=5, max_len=257,
             text="long decode: 256 new tokens, top-k 5 sampling (seeded uniforms), batch 256, paged KV cache (17 pages of 16 tokens per image), "
                  "then token->box decode and batched max-IoU against synthetic ground truth, all inside the timed region"),
+    # not a BASELINE.json config: the geometry the reference was TRAINED with (trail_01.py:158-160), outside the fused decode kernel's shape
+    6: dict(name="geometry T", img=224, S=196, B=64, T=99, top_k=0, max_len=100, dim=1024, heads=8, layers=8, vocab=332,
+            text="trained geometry (trail_01.py:158-160): deit3_medium 224 + 8-layer dim-1024 decoder (8 heads x 128, FFN 2048, V=332), batch 64, "
+                 "99 greedy tokens; decode = the per-operation chain (weight-streaming tensor-core linears, key-split cross-attention), 8 decode streams"),
 }
 
 
@@ -130,13 +134,13 @@ def synth_gray_u8(B, hw=200, seed=1234):
     return torch.randint(0, 256, (B, hw, hw), generator=g, dtype=torch.uint8)
 
 
-def build_model(M, img=224, S=196, max_len=100, seed=0, gamma_seed=5):
+def build_model(M, img=224, S=196, max_len=100, seed=0, gamma_seed=5, dim=256, heads=8, layers=6, vocab=305):
     """Random-init MDC-Net config P through the product constructors (inference_p.py:126-129: dim 256, 8 heads, 6 layers, V = 305),
     LayerScale gammas redrawn from U(0.5, 1.5) (random-init DeiT-III has gamma = 1e-6, which would make the encoder a no-op)."""
     M.CFG.max_len, M.CFG.pad_idx, M.CFG.bos_idx = max_len, 302, 300
     torch.manual_seed(seed)
-    enc = M.Encoder(model_name=VIT, pretrained=False, out_dim=256, img_size=img)
-    dec = M.Decoder(305, S, 256, 8, 6)
+    enc = M.Encoder(model_name=VIT, pretrained=False, out_dim=dim, img_size=img)
+    dec = M.Decoder(vocab, S, dim, heads, layers)
     model = M.EncoderDecoder(enc, dec)
     g = torch.Generator().manual_seed(gamma_seed)
     with torch.no_grad():
@@ -247,9 +251,17 @@ def decode_launch_ms(model, x_dev, dev, T, ipc, top_k=0, reps=3, cps=0):
     return best
 
 
-def decode_roofline(model, x_dev, dev, peaks, T, S, ipc, top_k=0, cps=0):
+def decode_roofline(model, x_dev, dev, peaks, T, S, ipc, top_k=0, cps=0, geo=None):
     B = x_dev.shape[0]
     ms = decode_launch_ms(model, x_dev, dev, T, ipc, top_k, cps=cps)
+    if geo:                                             # a geometry outside the fused kernel: the per-operation chain, one batch alone
+        nbytes = decode_algorithmic_bytes(B, T, S, dim=geo["dim"], layers=geo["layers"], ffn=2048, vocab=geo["vocab"])
+        ach = nbytes / (ms / 1e3) / 1e9
+        return {"kernel": f"per-operation decode chain (prep_x_half / dec_linear_stream / dec_self_attn / dec_cross_attn_split / dec_select kernels, "
+                          f"{11 * geo['layers'] + 3} launches per token), one batch alone, eager launches; {T} decode steps x {geo['layers']} layers, B={B}, S={S}",
+                "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"], "traffic": None,
+                "algorithmic_bytes_per_launch": nbytes, "ms_per_launch": ms, "ms_per_decode_token": ms / T,
+                "peak_src": peaks["src"] + " HBM copy bandwidth (chain timed alone, CUDA events)"}
     nbytes = decode_algorithmic_bytes(B, T, S)
     ach = nbytes / (ms / 1e3) / 1e9
     n_cl = -(-B // (16 if ipc > 8 else (ipc or 5)))
@@ -307,7 +319,8 @@ PIPE_KW = {}          # --decode-streams / --depth: GenerationPipeline operating
 def run_workload(M, wl, B, steps, warmup, dev, rank, world, dist, peaks, full):
     """Returns the fields of one bench line for workload `wl` at per-rank batch B.  full: also serial / e2e / roofline extras."""
     T, S, img, top_k = wl["T"], wl["S"], wl["img"], wl["top_k"]
-    model = build_model(M, img=img, S=S, max_len=wl["max_len"]).to(dev).set_precision("bf16")
+    geo = {k: wl[k] for k in ("dim", "heads", "layers", "vocab") if k in wl}
+    model = build_model(M, img=img, S=S, max_len=wl["max_len"], **geo).to(dev).set_precision("bf16")
     tok = M.Tokenizer(num_bins=224, width=img, height=img, max_len=wl["max_len"])
     NROT = 4                                         # rotating input batches (4 x 38.5 MB > the 126 MB L2 at the default shape)
     gs_host = [synth_gray_u8(B, seed=4321 + 17 * rank + i).pin_memory() for i in range(NROT)]
@@ -401,7 +414,7 @@ def run_workload(M, wl, B, steps, warmup, dev, rank, world, dist, peaks, full):
     res["e2e"] = {"value": timed_e2e(xs_host), "unit": "images/s", "h2d_bytes_per_step": xs_host[0].numel() * 4, "d2h_bytes_per_step": B * (T1 * 4 + C * 4)}
     if not full:
         if rank == 0:
-            res["roofline"] = decode_roofline(model, xs_dev[0], dev, peaks, T, S, 16, top_k)
+            res["roofline"] = decode_roofline(model, xs_dev[0], dev, peaks, T, S, 16, top_k, geo=geo)
         return res, model, xs_dev
     res["e2e_gray_u8"] = {"value": timed_e2e(gs_host), "unit": "images/s", "h2d_bytes_per_step": B * 200 * 200, "d2h_bytes_per_step": B * (T1 * 4 + C * 4),
                           "note": "generate_stream over raw u8 200x200 host images; the reference transform (cv2-exact uint8 resize + normalise) runs on the device"}
@@ -436,7 +449,7 @@ def main():
     ap.add_argument("--steps", type=int, default=100)      # 100 steps ~ 0.5 s pipelined: the fill and drain of the 6-deep pipeline (~8 ms) stay below 2 %
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--config", type=int, default=1, choices=[1, 4, 5], help="1: BASELINE configs[1] (default; configs[2] under torchrun), 4: configs[3], 5: configs[4]")
+    ap.add_argument("--config", type=int, default=1, choices=[1, 4, 5, 6], help="1: BASELINE configs[1] (default; configs[2] under torchrun), 4: configs[3], 5: configs[4], 6: the trained geometry (dim 1024)")
     ap.add_argument("--global-batch", type=int, default=0, help="total images per step, split over the ranks (configs[2]: 512); default 64 per rank")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-other-configs", action="store_true")
@@ -455,9 +468,10 @@ def main():
     if args.global_batch:
         assert args.global_batch % world == 0, "--global-batch must divide evenly over the ranks"
         B, scaling = args.global_batch // world, "strong"
-    cfg = {"workload": f"BASELINE {wl['name']}: {wl['text']}", "global_batch": B * world, "batch_per_gpu": B, "new_tokens": wl["T"],
+    cfg = {"workload": (f"BASELINE {wl['name']}: " if args.config != 6 else "") + wl["text"], "global_batch": B * world, "batch_per_gpu": B, "new_tokens": wl["T"],
            "parallelism": f"dp{world}", "sampler": "greedy" if not wl["top_k"] else f"top-k {wl['top_k']} (seeded uniforms)",
-           "pipeline": "batch pipeline (GenerationPipeline / generate_stream): 6 plans, 4 decode streams at 16 images per 8-CTA cluster + 1 encoder stream; steps overlap, every step does all of its work inside the timed region",
+           "pipeline": ("batch pipeline (GenerationPipeline / generate_stream): 6 plans, 4 decode streams at 16 images per 8-CTA cluster + 1 encoder stream; steps overlap, every step does all of its work inside the timed region"
+                        if args.config != 6 else "batch pipeline (GenerationPipeline / generate_stream): 10 plans, 8 decode streams (per-operation decode graphs) + 1 encoder stream"),
            "collective": "ONE all-gather of every rank's packed results (all steps) at the end of the timed region; none inside the decode loop",
            "l2": "no flush inside the pipelined region: 4 rotating input batches and a per-step working set (activations, cross-K/V, KV pages) well above the 126 MB L2"}
 
@@ -531,7 +545,7 @@ def main():
         del model
         if world == 1 and not args.no_other_configs:       # short runs of configs[3] / configs[4] so that their lines are in the record
             other = {}
-            for cid in (4, 5):
+            for cid in (4, 5, 6):
                 w2 = WORKLOADS[cid]
                 try:
                     r2, m2, _ = run_workload(M, w2, w2["B"], 6, 3, dev, rank, world, dist, peaks, full=False)

@@ -41,7 +41,9 @@ struct XSrc {
   const int32_t* tokens; int tokens_ld; int t;  // EMBED: emb[tokens[b,t]] + pos[t]
   const float* emb; const float* pos;
   float* xn_out;                                // where CTA column 0 publishes the operand rows (or NULL)
-  const __half* xh;                             // HALF: operand rows already built as IEEE half [B][K] (prep_x_half_kernel)
+  const __half* xh;                             // HALF: operand rows already built as IEEE half [B][K] (prep_x_half_kernel);
+                                                // PLAIN: optional IEEE-half twin of the f32 rows, written by the producer (row pitch ldxh)
+  int64_t ldxh;
 };
 
 // Fill Xs[BT][K] (f32) for batch rows b0..b0+BT-1.
@@ -476,6 +478,115 @@ __global__ void __launch_bounds__(LIN_THREADS) dec_linear_mma_kernel(XSrc xs, co
   }
 }
 
+// ---- weight-streaming form of the tensor-core linear (wide geometries: dim 1024 / 8 layers, trail_01.py:158-160) ----------------
+// dec_linear_mma_kernel gives a CTA 64 weight rows: N = 1024 is 16 CTAs, each pulling 128 KB of weights through eight loads per lane
+// after it has staged all 64 operand rows in shared memory -- 16 of 148 SMs stream the weights (25-36 us per linear, 72 GB/s in ncu,
+// profiles/r2y).  Here a CTA owns only 16 weight rows (one MMA row tile) and its eight warps split K: warp w takes the 32-column
+// blocks w, w+8, ... of those rows for all 64 images, so N = 1024 is 64 CTAs, every weight byte of the linear is requested in the
+// first few hundred cycles of the launch (32-64 KB in flight per CTA), nothing waits for a staged operand tile, and there is no
+// barrier before the cross-warp sum.  Operand rows are IEEE half in global memory (L2-resident: B x K halves, written by
+// prep_x_half_kernel, by the attention kernels or by the previous linear of this kind) and are loaded straight into the B fragments:
+// lane (g, q) reads the 16 bytes X[image 8 nb + g][32 kb + 8 q .. +8) = both k-steps of the block under the same k permutation as
+// above.  The eight K-partials of the 16 x 64 tile are summed through shared memory in warp order (deterministic, batch-invariant).
+constexpr int STREAM_ROWS = 16;
+constexpr int STREAM_PITCH = MMA_IMGS + 8;   // floats per row of a warp's partial tile
+constexpr int STREAM_SLOTS = 4;              // 32-column operand blocks in flight per warp (K = 1024: the warp's whole share)
+constexpr int STREAM_SLOT_BYTES = MMA_IMGS * 64;                                   // [64 images][32 halves]
+constexpr int STREAM_SMEM = LIN_WARPS * STREAM_SLOTS * STREAM_SLOT_BYTES;          // 128 KB; the partial tiles alias it afterwards
+static_assert(LIN_WARPS * STREAM_ROWS * STREAM_PITCH * 4 <= STREAM_SMEM, "partial tiles must fit into the operand ring");
+
+__device__ __forceinline__ void cp_async16_cg(uint32_t smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_dst), "l"(gsrc) : "memory");
+}
+
+template <bool RELU>
+__global__ void __launch_bounds__(LIN_THREADS) dec_linear_stream_kernel(const __half* __restrict__ X, int64_t ldx, const __half* __restrict__ W,
+                                                                         const float* __restrict__ bias, float* __restrict__ Y, int64_t ldy,
+                                                                         __half* __restrict__ Yh, int64_t ldyh, int B, int N, int K) {
+  extern __shared__ __align__(128) uint8_t stream_smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, q = lane & 3;
+  const int b0 = blockIdx.y * MMA_IMGS, r0 = blockIdx.x * STREAM_ROWS;
+  const int row_a = min(r0 + g, N - 1), row_b = min(r0 + g + 8, N - 1);     // rows past N: computed on a valid row, never stored
+  const __half* wa = W + (int64_t)row_a * K + 32 * warp + 8 * q;            // block i of this warp: + 256 i
+  const __half* wb = W + (int64_t)row_b * K + 32 * warp + 8 * q;
+  const int nkb = K >> 8;                                                   // 32-column blocks per warp (K % 256 == 0)
+  constexpr int PF = 8;
+  uint4 alo[PF], ahi[PF];
+#pragma unroll
+  for (int i = 0; i < PF; ++i)
+    if (i < nkb) { alo[i] = __ldg(reinterpret_cast<const uint4*>(wa + 256 * i)); ahi[i] = __ldg(reinterpret_cast<const uint4*>(wb + 256 * i)); }
+  // operand ring of this warp: slot = [64 images][4 x 16 bytes]; lane l copies the 16-byte pieces l, l + 32, ... (piece = 4 image + part)
+  const uint32_t ring = (uint32_t)__cvta_generic_to_shared(stream_smem) + warp * (STREAM_SLOTS * STREAM_SLOT_BYTES);
+  const __half* xsrc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int piece = lane + 32 * j, img = piece >> 2, part = piece & 3;
+    xsrc[j] = X + (int64_t)min(b0 + img, B - 1) * ldx + 32 * warp + 8 * part;
+  }
+  auto fetch = [&](int it) {
+    if (it < nkb) {
+      const uint32_t dst = ring + (it % STREAM_SLOTS) * STREAM_SLOT_BYTES + lane * 16;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) cp_async16_cg(dst + 512 * j, xsrc[j] + 256 * it);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");                    // one group per block, empty past the end
+  };
+#pragma unroll
+  for (int i = 0; i < STREAM_SLOTS; ++i) fetch(i);
+  float acc[8][4];
+#pragma unroll
+  for (int nb = 0; nb < 8; ++nb) { acc[nb][0] = acc[nb][1] = acc[nb][2] = acc[nb][3] = 0.f; }
+  for (int i0 = 0; i0 < nkb; i0 += PF) {
+#pragma unroll
+    for (int i = 0; i < PF; ++i) {
+      const int it = i0 + i;
+      if (it < nkb) {
+        const uint4 lo = alo[i], hi = ahi[i];
+        if (it + PF < nkb) { alo[i] = __ldg(reinterpret_cast<const uint4*>(wa + 256 * (it + PF))); ahi[i] = __ldg(reinterpret_cast<const uint4*>(wb + 256 * (it + PF))); }
+        asm volatile("cp.async.wait_group %0;" ::"n"(STREAM_SLOTS - 1) : "memory");
+        __syncwarp();
+        const uint32_t src = ring + (it % STREAM_SLOTS) * STREAM_SLOT_BYTES + g * 64 + q * 16;
+#pragma unroll
+        for (int nb = 0; nb < 8; ++nb) {
+          uint4 xv;
+          asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(xv.x), "=r"(xv.y), "=r"(xv.z), "=r"(xv.w) : "r"(src + 512 * nb));
+          mma16816_f16(acc[nb], lo.x, hi.x, lo.y, hi.y, xv.x, xv.y);
+          mma16816_f16(acc[nb], lo.z, hi.z, lo.w, hi.w, xv.z, xv.w);
+        }
+        __syncwarp();
+        fetch(it + STREAM_SLOTS);
+      }
+    }
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();                                                          // every warp is done with its ring: the partial tiles alias it
+  float (*red)[STREAM_ROWS][STREAM_PITCH] = reinterpret_cast<float (*)[STREAM_ROWS][STREAM_PITCH]>(stream_smem);
+  // acc[nb][e]: row g + 8 (e >> 1), image 8 nb + 2 q + (e & 1)
+#pragma unroll
+  for (int nb = 0; nb < 8; ++nb) {
+    *reinterpret_cast<float2*>(&red[warp][g][8 * nb + 2 * q]) = make_float2(acc[nb][0], acc[nb][1]);
+    *reinterpret_cast<float2*>(&red[warp][g + 8][8 * nb + 2 * q]) = make_float2(acc[nb][2], acc[nb][3]);
+  }
+  __syncthreads();
+  const int row = threadIdx.x & (STREAM_ROWS - 1), n = r0 + row;
+  if (n < N) {
+    const float bv = bias ? bias[n] : 0.f;
+#pragma unroll
+    for (int j = 0; j < MMA_IMGS / (LIN_THREADS / STREAM_ROWS); ++j) {
+      const int img = (threadIdx.x >> 4) + (LIN_THREADS / STREAM_ROWS) * j, b = b0 + img;
+      if (b < B) {
+        float v = red[0][row][img];
+#pragma unroll
+        for (int w = 1; w < LIN_WARPS; ++w) v += red[w][row][img];
+        v += bv;
+        if (RELU) v = fmaxf(v, 0.f);
+        if (Y) Y[(int64_t)b * ldy + n] = v;
+        if (Yh) Yh[(int64_t)b * ldyh + n] = __float2half_rn(fminf(fmaxf(v, -65504.f), 65504.f));
+      }
+    }
+  }
+}
+
 // ---- attention of ONE query per (image, head) over a key/value set ---------------------------------
 // warp == head.  A key's HD channels are split over LPK = HD/8 lanes (one 128-bit load each), so a warp
 // covers 32/LPK keys per pass with fully-used sectors; passes are unrolled x4 with the loads issued first
@@ -483,7 +594,7 @@ __global__ void __launch_bounds__(LIN_THREADS) dec_linear_mma_kernel(XSrc xs, co
 // shuffles; P.V uses the same (key slot, 8-channel chunk) lane mapping.
 template <typename TKV, int HD, typename KeyPtr, typename Bias>
 __device__ __forceinline__ void attend_one(const float* q /*smem, HD, pre-scaled*/, float* sc /*smem, nkeys*/, int nkeys,
-                                           KeyPtr kv_ptr, Bias bias, float* out /*HD*/) {
+                                           KeyPtr kv_ptr, Bias bias, float* out /*HD*/, __half* outh = nullptr /*HD, IEEE-half twin*/) {
   constexpr int LPK = HD / 8, KPI = 32 / LPK, UN = 4;
   const int lane = threadIdx.x & 31, sub = lane % LPK, kslot = lane / LPK;
   float qv[8];
@@ -545,6 +656,10 @@ __device__ __forceinline__ void attend_one(const float* q /*smem, HD, pre-scaled
     const float inv = 1.0f / sum;
 #pragma unroll
     for (int j = 0; j < 8; ++j) out[sub * 8 + j] = acc[j] * inv;
+    if (outh) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) outh[sub * 8 + j] = __float2half_rn(fminf(fmaxf(acc[j] * inv, -65504.f), 65504.f));
+    }
   }
   __syncwarp();
 }
@@ -561,7 +676,7 @@ template <typename TKV, int HD>
 __global__ void dec_self_attn_kernel(const float* __restrict__ qkv /*[B,3d]*/, TKV* __restrict__ pool,
                                      const int32_t* __restrict__ page_table, int pages_per_seq, int PT, int n_layers, int layer,
                                      const int32_t* __restrict__ tokens, int tokens_ld, int pad_idx, int t, int d,
-                                     float scale, float* __restrict__ o /*[B,d]*/) {
+                                     float scale, float* __restrict__ o /*[B,d]*/, __half* __restrict__ oh /*[B,d] or NULL*/) {
   constexpr int hd = HD;
   extern __shared__ float sm[];
   const int b = blockIdx.x, head = threadIdx.x >> 5, lane = threadIdx.x & 31, heads = blockDim.x >> 5;
@@ -588,7 +703,7 @@ __global__ void dec_self_attn_kernel(const float* __restrict__ qkv /*[B,3d]*/, T
   __syncwarp();
   auto kv_ptr = [&](int u, int which, int sub) -> const TKV* { return kv_base(u, which) + kv_chunk<TKV, HD>(u % PT, sub) * 8; };
   auto bias = [&](int u) -> float { return tokens[(int64_t)b * tokens_ld + u] == pad_idx ? 1.0f : 0.0f; };
-  attend_one<TKV, HD>(q, sc, t + 1, kv_ptr, bias, o + (int64_t)b * d + head * hd);
+  attend_one<TKV, HD>(q, sc, t + 1, kv_ptr, bias, o + (int64_t)b * d + head * hd, oh ? oh + (int64_t)b * d + head * hd : nullptr);
 }
 
 // cross-attention over the S memory keys of image b; cross_kv layer plane: [B*S][2d] (K | V)
@@ -606,6 +721,104 @@ __global__ void dec_cross_attn_kernel(const float* __restrict__ qc /*[B,d]*/, co
   auto kv_ptr = [&](int u, int which, int sub) -> const TKV* { return base + (int64_t)u * 2 * d + which * d + sub * 8; };
   auto bias = [&](int) -> float { return 0.f; };
   attend_one<TKV, HD>(q, sc, S, kv_ptr, bias, o + (int64_t)b * d + head * hd);
+}
+
+// cross-attention of ONE query per (image, head) with the memory keys split over the eight warps of a CTA (grid = heads x B).
+// dec_cross_attn_kernel walks the keys of a head with one warp: at head width 128 that is two keys per pass, 98 dependent round
+// trips of 2 KB each for S = 196 (45 us per layer at B = 64, 1.1 TB/s).  Here warp w takes the passes w, w + 8, ..., all 512 CTAs of
+// a B = 64 launch are resident and every K (then V) byte of the layer is requested within four rounds.  Scores go through shared
+// memory; max / sum / the eight partial outputs are combined in warp order (deterministic).  Output as IEEE half = the operand of
+// the out-projection (and optionally f32).
+template <typename TKV, int HD>
+__global__ void __launch_bounds__(LIN_THREADS) dec_cross_attn_split_kernel(const float* __restrict__ qc /*[B,d]*/, const TKV* __restrict__ ckv_layer,
+                                                                            int S, int d, float scale, float* __restrict__ o, __half* __restrict__ oh) {
+  constexpr int LPK = HD / 8, KPI = 32 / LPK, UN = 4;
+  extern __shared__ float sm[];
+  float* qs = sm;                       // HD
+  float* part = qs + HD;                // LIN_WARPS x HD
+  float* wred = part + LIN_WARPS * HD;  // 2 x LIN_WARPS
+  float* sc = wred + 2 * LIN_WARPS;     // S
+  const int head = blockIdx.x, b = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, sub = lane % LPK, kslot = lane / LPK;
+  const TKV* base = ckv_layer + (int64_t)b * S * 2 * d + head * HD + sub * 8;
+  constexpr int STEP = LIN_WARPS * KPI;                 // keys per CTA pass
+  const int ufirst = warp * KPI + kslot;
+  Raw8<TKV> r[UN], rn[UN];
+#pragma unroll
+  for (int i = 0; i < UN; ++i) { const int u = ufirst + i * STEP; if (u < S) r[i].load(base + (int64_t)u * 2 * d); else r[i].zero(); }
+  for (int c = threadIdx.x; c < HD; c += LIN_THREADS) qs[c] = qc[(int64_t)b * d + head * HD + c] * scale;
+  __syncthreads();
+  float qv[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) qv[j] = qs[sub * 8 + j];
+  float mx = -INFINITY;
+  for (int u0 = ufirst; u0 < S; u0 += STEP * UN) {
+    const int un = u0 + STEP * UN;
+    if (un < S) {
+#pragma unroll
+      for (int i = 0; i < UN; ++i) { const int u = un + i * STEP; if (u < S) rn[i].load(base + (int64_t)u * 2 * d); else rn[i].zero(); }
+    }
+#pragma unroll
+    for (int i = 0; i < UN; ++i) {
+      const int u = u0 + i * STEP;
+      float kf[8]; r[i].unpack(kf);
+      float sdot = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) sdot = fmaf(qv[j], kf[j], sdot);
+#pragma unroll
+      for (int of = 1; of < LPK; of <<= 1) sdot += __shfl_xor_sync(0xffffffffu, sdot, of);
+      if (u < S) { if (sub == 0) sc[u] = sdot; mx = fmaxf(mx, sdot); }
+    }
+#pragma unroll
+    for (int i = 0; i < UN; ++i) r[i] = rn[i];
+  }
+  mx = warp_max(mx);
+  if (lane == 0) wred[warp] = mx;
+  __syncthreads();
+  mx = wred[0];
+#pragma unroll
+  for (int w = 1; w < LIN_WARPS; ++w) mx = fmaxf(mx, wred[w]);
+  float sum = 0.f;
+  for (int u = threadIdx.x; u < S; u += LIN_THREADS) { const float e = expf(sc[u] - mx); sc[u] = e; sum += e; }
+  sum = warp_sum(sum);
+  if (lane == 0) wred[LIN_WARPS + warp] = sum;
+  __syncthreads();
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (int u0 = warp * KPI + kslot; u0 < S; u0 += STEP * UN) {
+    Raw8<TKV> r[UN];
+#pragma unroll
+    for (int i = 0; i < UN; ++i) { const int u = u0 + i * STEP; if (u < S) r[i].load(base + (int64_t)u * 2 * d + d); else r[i].zero(); }
+#pragma unroll
+    for (int i = 0; i < UN; ++i) {
+      const int u = u0 + i * STEP;
+      const float p = (u < S) ? sc[u] : 0.f;
+      float vf[8]; r[i].unpack(vf);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = fmaf(p, vf[j], acc[j]);
+    }
+  }
+#pragma unroll
+  for (int of = LPK; of < 32; of <<= 1) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], of);
+  }
+  if (kslot == 0) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) part[warp * HD + sub * 8 + j] = acc[j];
+  }
+  __syncthreads();
+  float tot = wred[LIN_WARPS];
+#pragma unroll
+  for (int w = 1; w < LIN_WARPS; ++w) tot += wred[LIN_WARPS + w];
+  const float inv = 1.0f / tot;
+  for (int c = threadIdx.x; c < HD; c += LIN_THREADS) {
+    float v = part[c];
+#pragma unroll
+    for (int w = 1; w < LIN_WARPS; ++w) v += part[w * HD + c];
+    v *= inv;
+    if (o) o[(int64_t)b * d + head * HD + c] = v;
+    if (oh) oh[(int64_t)b * d + head * HD + c] = __float2half_rn(fminf(fmaxf(v, -65504.f), 65504.f));
+  }
 }
 
 using namespace mdcsel;
@@ -655,11 +868,33 @@ __global__ void __launch_bounds__(SEL_THREADS) select_kernel(const float* __rest
 
 int next_pow2(int v) { int p = 1; while (p < v) p <<= 1; return p; }
 
+// batches of 16 and more with K a multiple of 256 (eight warps x 32-column blocks) take the weight-streaming linear
+inline bool stream_linears(int B, int K) { return B >= 16 && K % 256 == 0; }
+
 template <typename TW>
 int launch_linear(mdc_ctx* ctx, const XSrc& xs, const void* W, const float* bias, float* Y, int64_t ldy, int B, int N, int K,
-                  bool relu, cudaStream_t s, __half* xh_buf = nullptr) {
+                  bool relu, cudaStream_t s, __half* xh_buf = nullptr, __half* yh = nullptr, int64_t ldyh = 0) {
   MDC_CHECK_ARG(K % 8 == 0);
   if constexpr (std::is_same<TW, __half>::value) {
+    // weight-streaming form: operand rows available as IEEE half (built here by prep_x_half_kernel, or the producer's half twin)
+    if (stream_linears(B, K) && xh_buf && (xs.mode != XMODE_PLAIN || (xs.xh && xs.ldxh % 8 == 0 && ((uintptr_t)xs.xh & 15) == 0))) {
+      const __half* X = xs.xh; int64_t ldx = xs.ldxh;
+      if (xs.mode != XMODE_PLAIN) {
+        prep_x_half_kernel<<<(B + LIN_WARPS - 1) / LIN_WARPS, LIN_THREADS, 0, s>>>(xs, xh_buf, B, K);
+        MDC_LAUNCH_CHECK(ctx);
+        X = xh_buf; ldx = K;
+      }
+      dim3 grid((N + STREAM_ROWS - 1) / STREAM_ROWS, (B + MMA_IMGS - 1) / MMA_IMGS);
+      if (relu) {
+        MDC_ENSURE_SMEM(dec_linear_stream_kernel<true>, STREAM_SMEM);
+        dec_linear_stream_kernel<true><<<grid, LIN_THREADS, STREAM_SMEM, s>>>(X, ldx, (const __half*)W, bias, Y, ldy, yh, ldyh, B, N, K);
+      } else {
+        MDC_ENSURE_SMEM(dec_linear_stream_kernel<false>, STREAM_SMEM);
+        dec_linear_stream_kernel<false><<<grid, LIN_THREADS, STREAM_SMEM, s>>>(X, ldx, (const __half*)W, bias, Y, ldy, yh, ldyh, B, N, K);
+      }
+      MDC_LAUNCH_CHECK(ctx); return 0;
+    }
+    MDC_CHECK_ARG(Y != nullptr && yh == nullptr);
     // batches of 16 and more on the tensor cores (weights read once per 64 images); LayerNorm / embedding operands are model-width rows
     const bool plain = xs.mode == XMODE_PLAIN;
     if (xh_buf && B >= 16 && K % 32 == 0 && (plain ? (K <= MMA_KC || K % MMA_KC == 0) && xs.ldx % 4 == 0 && ((uintptr_t)xs.x & 15) == 0 : K <= MMA_KC)) {
@@ -715,11 +950,13 @@ int launch_linear(mdc_ctx* ctx, const XSrc& xs, const void* W, const float* bias
   MDC_LAUNCH_CHECK(ctx); return 0;
 }
 
-struct Scratch { float *xa, *xb, *xc, *y1, *y2, *y3, *qkv, *qc, *o, *oc, *f1, *lg; __half* xh; };
+struct Scratch { float *xa, *xb, *xc, *y1, *y2, *y3, *qkv, *qc, *o, *oc, *f1, *lg; __half *xh, *oh, *f1h; };
 
 size_t scratch_floats(const mdc_dims& d, int B) {
   // + the fp16 operand rows of the tensor-core linears (B x dim halves, behind the step logits, 16-byte aligned)
-  return (size_t)B * ((size_t)d.dim * 9 + (size_t)d.dim * 3 + d.dec_ffn + d.vocab) + 4 + ((size_t)B * d.dim + 1) / 2;
+  // + the IEEE-half twins of the attention output and of the FFN hidden (operands of the weight-streaming linears)
+  return (size_t)B * ((size_t)d.dim * 9 + (size_t)d.dim * 3 + d.dec_ffn + d.vocab) + 4 + ((size_t)B * d.dim + 1) / 2
+         + 8 + ((size_t)B * d.dim + 1) / 2 + ((size_t)B * d.dec_ffn + 1) / 2;
 }
 
 Scratch carve(const mdc_dims& d, int B, void* p) {
@@ -727,6 +964,8 @@ Scratch carve(const mdc_dims& d, int B, void* p) {
   s.xa = f; f += bd; s.xb = f; f += bd; s.xc = f; f += bd; s.y1 = f; f += bd; s.y2 = f; f += bd; s.y3 = f; f += bd;
   s.qc = f; f += bd; s.o = f; f += bd; s.oc = f; f += bd; s.qkv = f; f += 3 * bd; s.f1 = f; f += (size_t)B * d.dec_ffn; s.lg = f; f += (size_t)B * d.vocab;
   s.xh = reinterpret_cast<__half*>((reinterpret_cast<uintptr_t>(f) + 15) & ~(uintptr_t)15);
+  s.oh = reinterpret_cast<__half*>((reinterpret_cast<uintptr_t>(s.xh + bd) + 15) & ~(uintptr_t)15);
+  s.f1h = reinterpret_cast<__half*>((reinterpret_cast<uintptr_t>(s.oh + bd) + 15) & ~(uintptr_t)15);
   return s;
 }
 
@@ -739,6 +978,8 @@ int decode_step_typed(mdc_model* m, const mdc_decode_state* st, int t, cudaStrea
   const void** lw0 = gw + MDC_DEC_GLOBAL_SLOTS;
   Scratch sc = carve(d, B, st->scratch);
   const float scale = 1.0f / sqrtf((float)hd);
+  // wide batches on fp16 decode-loop weights: weight-streaming linears fed with IEEE-half operands by their producers
+  const bool stream = std::is_same<TW, __half>::value && stream_linears(B, dim) && stream_linears(B, d.dec_ffn) && dim % 8 == 0;
   XSrc prev{};   // how the next consumer obtains the layer input
   if (st->x_override) { prev.mode = XMODE_PLAIN; prev.x = st->x_override + (int64_t)t * dim; prev.ldx = (int64_t)st->x_override_ld * dim; }
   else {
@@ -756,7 +997,7 @@ int decode_step_typed(mdc_model* m, const mdc_decode_state* st, int t, cudaStrea
   {                                                                                                                      \
     MDC_ENSURE_SMEM((dec_self_attn_kernel<T, HD_>), smem);                                                               \
     dec_self_attn_kernel<T, HD_><<<B, d.dec_heads * 32, smem, s>>>(sc.qkv, (T*)st->kv_pool, st->page_table, st->pages_per_seq, \
-        d.page_tokens, d.dec_layers, l, st->tokens, st->tokens_ld, d.pad_idx, t, dim, scale, sc.o);                      \
+        d.page_tokens, d.dec_layers, l, st->tokens, st->tokens_ld, d.pad_idx, t, dim, scale, sc.o, stream ? sc.oh : nullptr); \
   }
       if (hd == 32) MDC_SA(32) else if (hd == 64) MDC_SA(64) else if (hd == 128) MDC_SA(128)
       else MDC_FAIL(-2, "decode: head width %d not in {32,64,128}", hd);
@@ -764,6 +1005,7 @@ int decode_step_typed(mdc_model* m, const mdc_decode_state* st, int t, cudaStrea
       MDC_LAUNCH_CHECK(ctx);
     }
     XSrc xo{}; xo.mode = XMODE_PLAIN; xo.x = sc.o; xo.ldx = dim;
+    if (stream) { xo.xh = sc.oh; xo.ldxh = dim; }
     MDC_TRY(launch_linear<TW>(ctx, xo, lw[MDC_SA_OUT_W], (const float*)lw[MDC_SA_OUT_B], sc.y1, dim, B, dim, dim, false, s, sc.xh));
     // cross-attention query from LN1(xa + y1); publishes xb
     XSrc x2{}; x2.mode = XMODE_LN; x2.resid = sc.xa; x2.delta = sc.y1; x2.ln_w = (const float*)lw[MDC_LN1_W]; x2.ln_b = (const float*)lw[MDC_LN1_B];
@@ -777,17 +1019,28 @@ int decode_step_typed(mdc_model* m, const mdc_decode_state* st, int t, cudaStrea
     MDC_ENSURE_SMEM((dec_cross_attn_kernel<T, HD_>), smem);                                                 \
     dec_cross_attn_kernel<T, HD_><<<B, d.dec_heads * 32, smem, s>>>(sc.qc, ckv, d.n_patches, dim, scale, sc.oc); \
   }
-      if (hd == 32) MDC_CA(32) else if (hd == 64) MDC_CA(64) else MDC_CA(128)
+#define MDC_CAS(HD_)                                                                                        \
+  {                                                                                                         \
+    const size_t smem_s = (size_t)(HD_ + LIN_WARPS * HD_ + 2 * LIN_WARPS + d.n_patches) * sizeof(float);   \
+    MDC_ENSURE_SMEM((dec_cross_attn_split_kernel<T, HD_>), smem_s);                                         \
+    dec_cross_attn_split_kernel<T, HD_><<<dim3(d.dec_heads, B), LIN_THREADS, smem_s, s>>>(sc.qc, ckv, d.n_patches, dim, scale, nullptr, sc.oh); \
+  }
+      if (stream) { if (hd == 32) MDC_CAS(32) else if (hd == 64) MDC_CAS(64) else MDC_CAS(128) }
+      else if (hd == 32) MDC_CA(32) else if (hd == 64) MDC_CA(64) else MDC_CA(128)
 #undef MDC_CA
+#undef MDC_CAS
       MDC_LAUNCH_CHECK(ctx);
     }
     XSrc xco{}; xco.mode = XMODE_PLAIN; xco.x = sc.oc; xco.ldx = dim;
+    if (stream) { xco.xh = sc.oh; xco.ldxh = dim; }
     MDC_TRY(launch_linear<TW>(ctx, xco, lw[MDC_CA_OUT_W], (const float*)lw[MDC_CA_OUT_B], sc.y2, dim, B, dim, dim, false, s, sc.xh));
     // FFN
     XSrc x3{}; x3.mode = XMODE_LN; x3.resid = sc.xb; x3.delta = sc.y2; x3.ln_w = (const float*)lw[MDC_LN2_W]; x3.ln_b = (const float*)lw[MDC_LN2_B];
     x3.eps = 1e-5f; x3.xn_out = sc.xc;
-    MDC_TRY(launch_linear<TW>(ctx, x3, lw[MDC_FF1_W], (const float*)lw[MDC_FF1_B], sc.f1, d.dec_ffn, B, d.dec_ffn, dim, true, s, sc.xh));
+    if (stream) MDC_TRY(launch_linear<TW>(ctx, x3, lw[MDC_FF1_W], (const float*)lw[MDC_FF1_B], nullptr, 0, B, d.dec_ffn, dim, true, s, sc.xh, sc.f1h, d.dec_ffn));
+    else MDC_TRY(launch_linear<TW>(ctx, x3, lw[MDC_FF1_W], (const float*)lw[MDC_FF1_B], sc.f1, d.dec_ffn, B, d.dec_ffn, dim, true, s, sc.xh));
     XSrc xf{}; xf.mode = XMODE_PLAIN; xf.x = sc.f1; xf.ldx = d.dec_ffn;
+    if (stream) { xf.xh = sc.f1h; xf.ldxh = d.dec_ffn; }
     MDC_TRY(launch_linear<TW>(ctx, xf, lw[MDC_FF2_W], (const float*)lw[MDC_FF2_B], sc.y3, dim, B, dim, d.dec_ffn, false, s, sc.xh));
     prev = XSrc{}; prev.mode = XMODE_LN; prev.resid = sc.xc; prev.delta = sc.y3; prev.ln_w = (const float*)lw[MDC_LN3_W];
     prev.ln_b = (const float*)lw[MDC_LN3_B]; prev.eps = 1e-5f;

@@ -37,7 +37,7 @@ class Ticket:
 
 
 class GenerationPipeline:
-    def __init__(self, model, batch, max_new_tokens, top_k=0, top_p=1.0, depth=6, decode_streams=4, images_per_cluster=16,
+    def __init__(self, model, batch, max_new_tokens, top_k=0, top_p=1.0, depth=None, decode_streams=None, images_per_cluster=16,
                  ctas_per_sm=0, to_host=False, device=None):
         from .model import GenerationPlan
         if not hasattr(model, "_engine"):
@@ -47,6 +47,14 @@ class GenerationPipeline:
         T = int(max_new_tokens)
         if T > d.max_pos:
             raise RuntimeError(f"max_len {T} exceeds CFG.max_len-1 = {d.max_pos} (model.py:93, Q6)")
+        # operating point: the fused decode kernel holds 32 SMs for ~12 ms per batch -> 4 decode streams, 6 plans; geometries it does not
+        # cover (dim 1024 of trail_01.py:158-160) decode as a chain of ~100 few-microsecond kernels per token on at most 64-192 CTAs,
+        # which leaves most of the GPU idle per batch -> 8 decode streams, 10 plans (tools/config_t_probe.py: 720 -> 1 900 img/s)
+        fused = getattr(eng, "dec_pack", None) is not None
+        if decode_streams is None:
+            decode_streams = 4 if fused else 8
+        if depth is None:
+            depth = 6 if fused else int(decode_streams) + 2
         self.eng, self.B, self.T, self.depth, self.to_host = eng, int(batch), T, int(depth), bool(to_host)
         self.sampling = (top_k != 0 or top_p != 1)
         dev = eng.device
@@ -125,7 +133,7 @@ class GenerationPipeline:
 
 
 @torch.no_grad()
-def generate_stream(model, batches, tokenizer, max_len=50, top_k=0, top_p=1, depth=6):
+def generate_stream(model, batches, tokenizer, max_len=50, top_k=0, top_p=1, depth=None):
     """The reference's inference loop as ONE pipelined call: yields, per batch and in order, what `generate(model, x, tokenizer,
     max_len, top_k, top_p)` returns -- (LongTensor (B,1+max_len) on CPU, list of ceil(max_len/4) float tensors (B,) on CPU).
     `batches` is any iterable of f32 (B,3,H,W) tensors (host, ideally pinned, or device) -- or of raw grayscale u8 (B,h,w)
@@ -142,7 +150,7 @@ def generate_stream(model, batches, tokenizer, max_len=50, top_k=0, top_p=1, dep
 
     for x in batches:
         dev = x.device if x.is_cuda else None
-        key = ((x.shape[0], x.dim(), str(x.dtype)) if x.dtype == torch.uint8 else tuple(x.shape), int(max_len), int(top_k), float(top_p), int(depth), str(dev))
+        key = ((x.shape[0], x.dim(), str(x.dtype)) if x.dtype == torch.uint8 else tuple(x.shape), int(max_len), int(top_k), float(top_p), depth, str(dev))
         if key not in pipes or pipes[key].eng is not model._engine(dev):      # new shape (e.g. the ragged last batch) / new weights
             pipes[key] = GenerationPipeline(model, x.shape[0], max_len, top_k=top_k, top_p=top_p, depth=depth, to_host=True, device=dev)
         if pipes[key] is not pipe:
@@ -150,7 +158,7 @@ def generate_stream(model, batches, tokenizer, max_len=50, top_k=0, top_p=1, dep
                 yield finish(pending.pop(0))
             pipe = pipes[key]
         pending.append(pipe.submit(x))
-        if len(pending) > depth:                 # keep `depth` batches in flight, hand out the oldest
+        if len(pending) > pipe.depth:            # keep `depth` batches in flight, hand out the oldest
             yield finish(pending.pop(0))
     while pending:
         yield finish(pending.pop(0))

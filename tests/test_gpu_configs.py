@@ -117,7 +117,7 @@ def test_config5_long_decode_topk_paged_kv_and_iou(restore_cfg):
     assert torch.equal(got, O.batch_max_iou(want_boxes, gt).flatten())
 
 
-def test_config_T_trained_geometry_runs_on_the_generic_kernels():
+def test_config_T_trained_geometry_runs_on_the_per_operation_kernels():
     """The geometry the reference was actually trained with (trail_01.py:158-160 / inference_code_craeted_me_gpt.py:128-130: dim 1024,
     8 heads x 128, 8 layers, vocab 332) is outside the fused cluster kernel's shape (dim 256); it must run -- and match -- on the
     generic decode kernels: fp32 tokens exact, bf16 logits within the contract."""
@@ -144,3 +144,15 @@ def test_config_T_trained_geometry_runs_on_the_generic_kernels():
     eb = (logits_b.cpu() - want_logits).abs().max().item()
     print(f"config T: fp32 logits max|d| = {e32:.2e}; bf16 max|d| = {eb:.2e}, cosine = {G.cos(logits_b.cpu(), want_logits):.6f}")
     assert eb <= 2e-2 and G.cos(logits_b.cpu(), want_logits) >= 0.999
+    # batches of 16 and more take the weight-streaming linears + the key-split cross-attention (decode.cu: dec_linear_stream_kernel,
+    # dec_cross_attn_split_kernel): the same two images inside a batch of 16 against the oracle, and batch invariance of that path
+    x16 = torch.cat([x, cases.images(14, seed=62)])
+    toks_s, _, logits_s = model.generate_tokens(x16.to(DEV), 10, return_logits=True)
+    es = (logits_s[:2].cpu() - want_logits).abs().max().item()
+    print(f"config T, streaming linears (B = 16): bf16 max|d| = {es:.2e}, cosine = {G.cos(logits_s[:2].cpu(), want_logits):.6f}")
+    assert es <= 2e-2 and G.cos(logits_s[:2].cpu(), want_logits) >= 0.999
+    x40 = torch.cat([x16, cases.images(24, seed=63)])
+    toks_w, _, logits_w = model.generate_tokens(x40.to(DEV), 10, return_logits=True)
+    assert torch.equal(toks_w[:16], toks_s) and torch.equal(logits_w[:16], logits_s)
+    toks_w2, _, logits_w2 = model.generate_tokens(x40.to(DEV), 10, return_logits=True)
+    assert torch.equal(toks_w2, toks_w) and torch.equal(logits_w2, logits_w)

@@ -20,3 +20,19 @@ for _ in range(3): model.generate_tokens(x, T)
 b.record(); torch.cuda.synchronize()
 ms = a.elapsed_time(b) / 3
 print(f"config T, B={B}, {T} greedy tokens, bf16: {ms:.2f} ms per batch = {B / ms * 1e3:.0f} img/s, {ms / T * 1e3:.0f} us per token-step (encoder included)")
+# the batch pipeline on the same geometry: the per-operation decode graphs of several batches overlap (each kernel of the chain is
+# a few microseconds on at most 64-192 CTAs, so one batch alone leaves most of the GPU idle)
+K = 12
+for ndec in ((4, 8, 12) if "--pipeline" in sys.argv else ()):
+    pipe = M.GenerationPipeline(model, B, T, depth=ndec + 2, decode_streams=ndec)
+    for _ in range(ndec + 2): pipe.submit(x)
+    pipe.join(); torch.cuda.synchronize()
+    a.record()
+    ts = [pipe.submit(x) for _ in range(K)]
+    pipe.join()
+    b.record(); torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / K
+    ref = model.generate_tokens(x, T)[0]
+    ok = all(torch.equal(t.tokens, ref) for t in ts)
+    print(f"config T, batch pipeline, {ndec} decode streams: {ms:.2f} ms per batch = {B / ms * 1e3:.0f} img/s  (tokens equal to generate_tokens: {ok})")
+    del pipe

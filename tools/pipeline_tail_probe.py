@@ -1,0 +1,58 @@
+"""Probe of the batch pipeline's DRAIN: with a known number of batches, the decode loops of the last G batches are held back until the
+encoder pass of the very last batch is enqueued, so that the final decode kernels run side by side instead of one after the other
+next to an otherwise idle GPU.  usage: pipeline_tail_probe.py K  G,depth[,streams] ..."""
+import os, sys, torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from oracle import cases
+import mdcnet_b200 as M
+from mdcnet_b200.model import GenerationPlan
+B, T, K = 64, 99, int(sys.argv[1]) if len(sys.argv) > 1 else 20
+m = cases.build_product_model("P", seed=0, gamma_seed=5).to("cuda").set_precision("bf16")
+eng = m._engine(torch.device("cuda", 0))
+xs = [cases.images(B, seed=100 + i).to("cuda") for i in range(4)]
+for _ in range(3): m.generate_tokens(xs[0], T)
+torch.cuda.synchronize()
+outs = [m.generate_tokens(xs[i], T)[0] for i in range(4)]
+a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+cfgs = [tuple(int(v) for v in c.split(',')) for c in sys.argv[2:]] or [(0, 6), (4, 6), (3, 6), (4, 8), (6, 8)]
+for cfg in cfgs:
+    G, depth = cfg[:2]; ndec = cfg[2] if len(cfg) > 2 else 4
+    plans = [GenerationPlan(eng, B, T, 0, 1.0, False, False, True, split=True, images_per_cluster=16, ctas_per_sm=0) for _ in range(depth)]
+    s_enc = torch.cuda.Stream(priority=0)
+    s_decs = [torch.cuda.Stream(priority=-1) for _ in range(max(ndec, G))]
+    def run(K):
+        res, held = [], []
+        def dec(i, p, gate):
+            s_dec = s_decs[i % len(s_decs)] if gate is not None else s_decs[i % ndec]
+            with torch.cuda.stream(s_dec):
+                s_dec.wait_event(gate if gate is not None else p.enc_done)
+                p.dec_graph.replay()
+                res.append(p.tokens.clone())
+                p.dec_done.record(s_dec)
+        for i in range(K):
+            p = plans[i % depth]
+            with torch.cuda.stream(s_enc):
+                if p.busy: s_enc.wait_event(p.dec_done)
+                p.x.copy_(xs[i % 4], non_blocking=True)
+                p.enc_graph.replay()
+                p.enc_done.record(s_enc)
+            p.busy = True
+            if K - 1 - i < G: held.append((i, p))
+            else: dec(i, p, None)
+        for i, p in held: dec(i, p, plans[(K - 1) % depth].enc_done)
+        return res
+    run(2 * depth); torch.cuda.synchronize()
+    best = 1e9
+    for rep in range(3):
+        cur = torch.cuda.current_stream()
+        a.record()
+        s_enc.wait_stream(cur)
+        for s in s_decs: s.wait_stream(cur)
+        res = run(K)
+        for s in s_decs: cur.wait_stream(s)
+        cur.wait_stream(s_enc)
+        b.record(); torch.cuda.synchronize()
+        best = min(best, a.elapsed_time(b))
+    ok = all(torch.equal(r, outs[i % 4]) for i, r in enumerate(res))
+    print(f"K {K} held tail {G} depth {depth} decode streams {ndec}: {B * K / (best / 1e3):9.1f} img/s  ({best:.2f} ms total, {best / K:.3f} ms/batch)  equal: {ok}", flush=True)
+    del plans
