@@ -333,6 +333,63 @@ __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
 // LayerNorm-on-load / embedding operand rows, built ONCE per linear (one warp per image, all images in parallel) as IEEE half in
 // global memory, and published as the next residual (xn_out, f32).  Building them inside every CTA of the linear -- eight rows per
 // warp, one after the other, three dependent memory round trips each -- was 75 % of that kernel's time (ncu, profiles/r2w).
+// K % 128 == 0 (every model width on the path): 128-bit loads and stores, lane holds columns 128 i + 4 lane .. +4 -- the scalar form below
+// issues 128 loads and 64 stores per lane for a 1024-wide row and was LSU-latency bound (7.9 us per launch at B = 64, a quarter of a
+// dim-1024 token-step)
+template <int NV>
+__global__ void __launch_bounds__(LIN_THREADS) prep_x_half_vec_kernel(XSrc xs, __half* __restrict__ xh, int B) {
+  constexpr int K = NV * 128;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.x * LIN_WARPS + warp;
+  if (b >= B) return;
+  float4 v[NV];
+  if (xs.mode == XMODE_EMBED) {
+    const int tok = xs.tokens[(int64_t)b * xs.tokens_ld + xs.t];
+    const float4* e = reinterpret_cast<const float4*>(xs.emb + (int64_t)tok * K) + lane;
+    const float4* pz = reinterpret_cast<const float4*>(xs.pos + (int64_t)xs.t * K) + lane;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const float4 a = __ldg(e + 32 * i), c = __ldg(pz + 32 * i);
+      v[i] = make_float4(a.x + c.x, a.y + c.y, a.z + c.z, a.w + c.w);
+    }
+  } else {
+    const float4* a = reinterpret_cast<const float4*>(xs.resid + (int64_t)b * K) + lane;
+    const float4* d = reinterpret_cast<const float4*>(xs.delta + (int64_t)b * K) + lane;
+    float4 dl[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) { v[i] = a[32 * i]; dl[i] = d[32 * i]; }
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      v[i].x += dl[i].x; v[i].y += dl[i].y; v[i].z += dl[i].z; v[i].w += dl[i].w;
+      sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+    const float4* gw = reinterpret_cast<const float4*>(xs.ln_w) + lane;
+    const float4* gb = reinterpret_cast<const float4*>(xs.ln_b) + lane;
+    const float mean = warp_sum(sum) / (float)K;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const float a0 = v[i].x - mean, a1 = v[i].y - mean, a2 = v[i].z - mean, a3 = v[i].w - mean;
+      q += (a0 * a0 + a1 * a1) + (a2 * a2 + a3 * a3);
+    }
+    const float rstd = 1.0f / sqrtf(warp_sum(q) / (float)K + xs.eps);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const float4 g = __ldg(gw + 32 * i), be = __ldg(gb + 32 * i);
+      v[i].x = (v[i].x - mean) * rstd * g.x + be.x; v[i].y = (v[i].y - mean) * rstd * g.y + be.y;
+      v[i].z = (v[i].z - mean) * rstd * g.z + be.z; v[i].w = (v[i].w - mean) * rstd * g.w + be.w;
+    }
+  }
+  uint2* oh = reinterpret_cast<uint2*>(xh + (int64_t)b * K) + lane;
+  float4* of = xs.xn_out ? reinterpret_cast<float4*>(xs.xn_out + (int64_t)b * K) + lane : nullptr;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    oh[32 * i] = make_uint2(pack_half2(v[i].x, v[i].y), pack_half2(v[i].z, v[i].w));
+    if (of) of[32 * i] = v[i];
+  }
+}
+
 __global__ void __launch_bounds__(LIN_THREADS) prep_x_half_kernel(XSrc xs, __half* __restrict__ xh, int B, int K) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.x * LIN_WARPS + warp;
@@ -517,17 +574,27 @@ __global__ void __launch_bounds__(LIN_THREADS) dec_linear_stream_kernel(const __
     if (i < nkb) { alo[i] = __ldg(reinterpret_cast<const uint4*>(wa + 256 * i)); ahi[i] = __ldg(reinterpret_cast<const uint4*>(wb + 256 * i)); }
   // operand ring of this warp: slot = [64 images][4 x 16 bytes]; lane l copies the 16-byte pieces l, l + 32, ... (piece = 4 image + part)
   const uint32_t ring = (uint32_t)__cvta_generic_to_shared(stream_smem) + warp * (STREAM_SLOTS * STREAM_SLOT_BYTES);
+  // image slots past the batch are zeroed once and never copied (clamping them to the last row made thousands of L2 requests hit the
+  // same two sectors: a B = 16 step was twice as slow as a B = 64 step)
   const __half* xsrc[8];
+  uint32_t live = 0;
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const int piece = lane + 32 * j, img = piece >> 2, part = piece & 3;
     xsrc[j] = X + (int64_t)min(b0 + img, B - 1) * ldx + 32 * warp + 8 * part;
+    if (b0 + img < B) live |= 1u << j;
+    else {
+#pragma unroll
+      for (int sl = 0; sl < STREAM_SLOTS; ++sl)
+        asm volatile("st.shared.v4.b32 [%0], {%1,%1,%1,%1};" ::"r"(ring + sl * STREAM_SLOT_BYTES + piece * 16), "r"(0u) : "memory");
+    }
   }
   auto fetch = [&](int it) {
     if (it < nkb) {
       const uint32_t dst = ring + (it % STREAM_SLOTS) * STREAM_SLOT_BYTES + lane * 16;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) cp_async16_cg(dst + 512 * j, xsrc[j] + 256 * it);
+      for (int j = 0; j < 8; ++j)
+        if (live >> j & 1) cp_async16_cg(dst + 512 * j, xsrc[j] + 256 * it);
     }
     asm volatile("cp.async.commit_group;" ::: "memory");                    // one group per block, empty past the end
   };
@@ -868,6 +935,18 @@ __global__ void __launch_bounds__(SEL_THREADS) select_kernel(const float* __rest
 
 int next_pow2(int v) { int p = 1; while (p < v) p <<= 1; return p; }
 
+// operand rows of a LayerNorm-on-load / embedding source as IEEE half (+ the f32 residual copy), one warp per image
+int launch_prep(mdc_ctx* ctx, const XSrc& xs, __half* xh, int B, int K, cudaStream_t s) {
+  const dim3 grid((B + LIN_WARPS - 1) / LIN_WARPS);
+  const bool al = (((uintptr_t)xh | (uintptr_t)xs.xn_out | (uintptr_t)xs.resid | (uintptr_t)xs.delta | (uintptr_t)xs.ln_w | (uintptr_t)xs.ln_b |
+                    (uintptr_t)xs.emb | (uintptr_t)xs.pos) & 15) == 0;
+  if (al && K == 256) prep_x_half_vec_kernel<2><<<grid, LIN_THREADS, 0, s>>>(xs, xh, B);
+  else if (al && K == 512) prep_x_half_vec_kernel<4><<<grid, LIN_THREADS, 0, s>>>(xs, xh, B);
+  else if (al && K == 1024) prep_x_half_vec_kernel<8><<<grid, LIN_THREADS, 0, s>>>(xs, xh, B);
+  else prep_x_half_kernel<<<grid, LIN_THREADS, 0, s>>>(xs, xh, B, K);
+  MDC_LAUNCH_CHECK(ctx); return 0;
+}
+
 // batches of 16 and more with K a multiple of 256 (eight warps x 32-column blocks) take the weight-streaming linear
 inline bool stream_linears(int B, int K) { return B >= 16 && K % 256 == 0; }
 
@@ -880,8 +959,7 @@ int launch_linear(mdc_ctx* ctx, const XSrc& xs, const void* W, const float* bias
     if (stream_linears(B, K) && xh_buf && (xs.mode != XMODE_PLAIN || (xs.xh && xs.ldxh % 8 == 0 && ((uintptr_t)xs.xh & 15) == 0))) {
       const __half* X = xs.xh; int64_t ldx = xs.ldxh;
       if (xs.mode != XMODE_PLAIN) {
-        prep_x_half_kernel<<<(B + LIN_WARPS - 1) / LIN_WARPS, LIN_THREADS, 0, s>>>(xs, xh_buf, B, K);
-        MDC_LAUNCH_CHECK(ctx);
+        MDC_TRY(launch_prep(ctx, xs, xh_buf, B, K, s));
         X = xh_buf; ldx = K;
       }
       dim3 grid((N + STREAM_ROWS - 1) / STREAM_ROWS, (B + MMA_IMGS - 1) / MMA_IMGS);
@@ -900,8 +978,7 @@ int launch_linear(mdc_ctx* ctx, const XSrc& xs, const void* W, const float* bias
     if (xh_buf && B >= 16 && K % 32 == 0 && (plain ? (K <= MMA_KC || K % MMA_KC == 0) && xs.ldx % 4 == 0 && ((uintptr_t)xs.x & 15) == 0 : K <= MMA_KC)) {
       XSrc src = xs;
       if (!plain) {
-        prep_x_half_kernel<<<(B + LIN_WARPS - 1) / LIN_WARPS, LIN_THREADS, 0, s>>>(xs, xh_buf, B, K);
-        MDC_LAUNCH_CHECK(ctx);
+        MDC_TRY(launch_prep(ctx, xs, xh_buf, B, K, s));
         src = XSrc{}; src.mode = XMODE_HALF; src.xh = xh_buf;
       }
       const size_t sm = (size_t)MMA_IMGS * (size_t)((K < MMA_KC ? K : MMA_KC) + MMA_PAD) * sizeof(__half);
