@@ -546,32 +546,45 @@ __global__ void __launch_bounds__(LIN_THREADS) dec_linear_mma_kernel(XSrc xs, co
 // lane (g, q) reads the 16 bytes X[image 8 nb + g][32 kb + 8 q .. +8) = both k-steps of the block under the same k permutation as
 // above.  The eight K-partials of the 16 x 64 tile are summed through shared memory in warp order (deterministic, batch-invariant).
 constexpr int STREAM_ROWS = 16;
+#ifndef MDC_STREAM_MT2_MIN_N
+#define MDC_STREAM_MT2_MIN_N 2048          // linears at least this wide take two 16-row tiles per CTA (A/B on B200, B = 64: every linear: serial
+                                           // token-step +10 %, pipeline +9 %; N >= 2048 only: serial -0.5 %, pipeline +5 %)
+#endif
 constexpr int STREAM_PITCH = MMA_IMGS + 8;   // floats per row of a warp's partial tile
 constexpr int STREAM_SLOTS = 4;              // 32-column operand blocks in flight per warp (K = 1024: the warp's whole share)
 constexpr int STREAM_SLOT_BYTES = MMA_IMGS * 64;                                   // [64 images][32 halves]
 constexpr int STREAM_SMEM = LIN_WARPS * STREAM_SLOTS * STREAM_SLOT_BYTES;          // 128 KB; the partial tiles alias it afterwards
-static_assert(LIN_WARPS * STREAM_ROWS * STREAM_PITCH * 4 <= STREAM_SMEM, "partial tiles must fit into the operand ring");
 
 __device__ __forceinline__ void cp_async16_cg(uint32_t smem_dst, const void* gsrc) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_dst), "l"(gsrc) : "memory");
 }
 
-template <bool RELU>
+// MT = 16-row tiles per CTA.  Two tiles share every operand fragment read and halve the CTA count: the same kernel latency for half the SM
+// residency, which is what the batch pipeline (several batches' chains side by side, one such CTA per SM) is bound by.
+template <bool RELU, int MT>
 __global__ void __launch_bounds__(LIN_THREADS) dec_linear_stream_kernel(const __half* __restrict__ X, int64_t ldx, const __half* __restrict__ W,
                                                                          const float* __restrict__ bias, float* __restrict__ Y, int64_t ldy,
                                                                          __half* __restrict__ Yh, int64_t ldyh, int B, int N, int K) {
+  constexpr int ROWS = STREAM_ROWS * MT;
+  static_assert(LIN_WARPS * ROWS * STREAM_PITCH * 4 <= STREAM_SMEM, "partial tiles must fit into the operand ring");
   extern __shared__ __align__(128) uint8_t stream_smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, q = lane & 3;
-  const int b0 = blockIdx.y * MMA_IMGS, r0 = blockIdx.x * STREAM_ROWS;
-  const int row_a = min(r0 + g, N - 1), row_b = min(r0 + g + 8, N - 1);     // rows past N: computed on a valid row, never stored
-  const __half* wa = W + (int64_t)row_a * K + 32 * warp + 8 * q;            // block i of this warp: + 256 i
-  const __half* wb = W + (int64_t)row_b * K + 32 * warp + 8 * q;
+  const int b0 = blockIdx.y * MMA_IMGS, r0 = blockIdx.x * ROWS;
+  const __half* wa[MT]; const __half* wb[MT];                               // rows past N: computed on a valid row, never stored
+#pragma unroll
+  for (int m = 0; m < MT; ++m) {
+    wa[m] = W + (int64_t)min(r0 + 16 * m + g, N - 1) * K + 32 * warp + 8 * q;      // block i of this warp: + 256 i
+    wb[m] = W + (int64_t)min(r0 + 16 * m + g + 8, N - 1) * K + 32 * warp + 8 * q;
+  }
   const int nkb = K >> 8;                                                   // 32-column blocks per warp (K % 256 == 0)
-  constexpr int PF = 8;
-  uint4 alo[PF], ahi[PF];
+  constexpr int PF = 8 / MT;
+  uint4 alo[MT][PF], ahi[MT][PF];
 #pragma unroll
   for (int i = 0; i < PF; ++i)
-    if (i < nkb) { alo[i] = __ldg(reinterpret_cast<const uint4*>(wa + 256 * i)); ahi[i] = __ldg(reinterpret_cast<const uint4*>(wb + 256 * i)); }
+    if (i < nkb) {
+#pragma unroll
+      for (int m = 0; m < MT; ++m) { alo[m][i] = __ldg(reinterpret_cast<const uint4*>(wa[m] + 256 * i)); ahi[m][i] = __ldg(reinterpret_cast<const uint4*>(wb[m] + 256 * i)); }
+    }
   // operand ring of this warp: slot = [64 images][4 x 16 bytes]; lane l copies the 16-byte pieces l, l + 32, ... (piece = 4 image + part)
   const uint32_t ring = (uint32_t)__cvta_generic_to_shared(stream_smem) + warp * (STREAM_SLOTS * STREAM_SLOT_BYTES);
   // image slots past the batch are zeroed once and never copied (clamping them to the last row made thousands of L2 requests hit the
@@ -600,16 +613,22 @@ __global__ void __launch_bounds__(LIN_THREADS) dec_linear_stream_kernel(const __
   };
 #pragma unroll
   for (int i = 0; i < STREAM_SLOTS; ++i) fetch(i);
-  float acc[8][4];
+  float acc[MT][8][4];
 #pragma unroll
-  for (int nb = 0; nb < 8; ++nb) { acc[nb][0] = acc[nb][1] = acc[nb][2] = acc[nb][3] = 0.f; }
+  for (int m = 0; m < MT; ++m)
+#pragma unroll
+    for (int nb = 0; nb < 8; ++nb) { acc[m][nb][0] = acc[m][nb][1] = acc[m][nb][2] = acc[m][nb][3] = 0.f; }
   for (int i0 = 0; i0 < nkb; i0 += PF) {
 #pragma unroll
     for (int i = 0; i < PF; ++i) {
       const int it = i0 + i;
       if (it < nkb) {
-        const uint4 lo = alo[i], hi = ahi[i];
-        if (it + PF < nkb) { alo[i] = __ldg(reinterpret_cast<const uint4*>(wa + 256 * (it + PF))); ahi[i] = __ldg(reinterpret_cast<const uint4*>(wb + 256 * (it + PF))); }
+        uint4 lo[MT], hi[MT];
+#pragma unroll
+        for (int m = 0; m < MT; ++m) {
+          lo[m] = alo[m][i]; hi[m] = ahi[m][i];
+          if (it + PF < nkb) { alo[m][i] = __ldg(reinterpret_cast<const uint4*>(wa[m] + 256 * (it + PF))); ahi[m][i] = __ldg(reinterpret_cast<const uint4*>(wb[m] + 256 * (it + PF))); }
+        }
         asm volatile("cp.async.wait_group %0;" ::"n"(STREAM_SLOTS - 1) : "memory");
         __syncwarp();
         const uint32_t src = ring + (it % STREAM_SLOTS) * STREAM_SLOT_BYTES + g * 64 + q * 16;
@@ -617,8 +636,11 @@ __global__ void __launch_bounds__(LIN_THREADS) dec_linear_stream_kernel(const __
         for (int nb = 0; nb < 8; ++nb) {
           uint4 xv;
           asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(xv.x), "=r"(xv.y), "=r"(xv.z), "=r"(xv.w) : "r"(src + 512 * nb));
-          mma16816_f16(acc[nb], lo.x, hi.x, lo.y, hi.y, xv.x, xv.y);
-          mma16816_f16(acc[nb], lo.z, hi.z, lo.w, hi.w, xv.z, xv.w);
+#pragma unroll
+          for (int m = 0; m < MT; ++m) {
+            mma16816_f16(acc[m][nb], lo[m].x, hi[m].x, lo[m].y, hi[m].y, xv.x, xv.y);
+            mma16816_f16(acc[m][nb], lo[m].z, hi[m].z, lo[m].w, hi[m].w, xv.z, xv.w);
+          }
         }
         __syncwarp();
         fetch(it + STREAM_SLOTS);
@@ -627,20 +649,23 @@ __global__ void __launch_bounds__(LIN_THREADS) dec_linear_stream_kernel(const __
   }
   asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncthreads();                                                          // every warp is done with its ring: the partial tiles alias it
-  float (*red)[STREAM_ROWS][STREAM_PITCH] = reinterpret_cast<float (*)[STREAM_ROWS][STREAM_PITCH]>(stream_smem);
-  // acc[nb][e]: row g + 8 (e >> 1), image 8 nb + 2 q + (e & 1)
+  float (*red)[ROWS][STREAM_PITCH] = reinterpret_cast<float (*)[ROWS][STREAM_PITCH]>(stream_smem);
+  // acc[m][nb][e]: row 16 m + g + 8 (e >> 1), image 8 nb + 2 q + (e & 1)
 #pragma unroll
-  for (int nb = 0; nb < 8; ++nb) {
-    *reinterpret_cast<float2*>(&red[warp][g][8 * nb + 2 * q]) = make_float2(acc[nb][0], acc[nb][1]);
-    *reinterpret_cast<float2*>(&red[warp][g + 8][8 * nb + 2 * q]) = make_float2(acc[nb][2], acc[nb][3]);
-  }
+  for (int m = 0; m < MT; ++m)
+#pragma unroll
+    for (int nb = 0; nb < 8; ++nb) {
+      *reinterpret_cast<float2*>(&red[warp][16 * m + g][8 * nb + 2 * q]) = make_float2(acc[m][nb][0], acc[m][nb][1]);
+      *reinterpret_cast<float2*>(&red[warp][16 * m + g + 8][8 * nb + 2 * q]) = make_float2(acc[m][nb][2], acc[m][nb][3]);
+    }
   __syncthreads();
-  const int row = threadIdx.x & (STREAM_ROWS - 1), n = r0 + row;
+  const int row = threadIdx.x & (ROWS - 1), n = r0 + row;
   if (n < N) {
     const float bv = bias ? bias[n] : 0.f;
+    constexpr int IPP = LIN_THREADS / ROWS;                                 // images per pass
 #pragma unroll
-    for (int j = 0; j < MMA_IMGS / (LIN_THREADS / STREAM_ROWS); ++j) {
-      const int img = (threadIdx.x >> 4) + (LIN_THREADS / STREAM_ROWS) * j, b = b0 + img;
+    for (int j = 0; j < MMA_IMGS / IPP; ++j) {
+      const int img = (threadIdx.x / ROWS) + IPP * j, b = b0 + img;
       if (b < B) {
         float v = red[0][row][img];
 #pragma unroll
@@ -962,14 +987,16 @@ int launch_linear(mdc_ctx* ctx, const XSrc& xs, const void* W, const float* bias
         MDC_TRY(launch_prep(ctx, xs, xh_buf, B, K, s));
         X = xh_buf; ldx = K;
       }
-      dim3 grid((N + STREAM_ROWS - 1) / STREAM_ROWS, (B + MMA_IMGS - 1) / MMA_IMGS);
-      if (relu) {
-        MDC_ENSURE_SMEM(dec_linear_stream_kernel<true>, STREAM_SMEM);
-        dec_linear_stream_kernel<true><<<grid, LIN_THREADS, STREAM_SMEM, s>>>(X, ldx, (const __half*)W, bias, Y, ldy, yh, ldyh, B, N, K);
-      } else {
-        MDC_ENSURE_SMEM(dec_linear_stream_kernel<false>, STREAM_SMEM);
-        dec_linear_stream_kernel<false><<<grid, LIN_THREADS, STREAM_SMEM, s>>>(X, ldx, (const __half*)W, bias, Y, ldy, yh, ldyh, B, N, K);
-      }
+      const int mt = N >= MDC_STREAM_MT2_MIN_N ? 2 : 1;
+      dim3 grid((N + STREAM_ROWS * mt - 1) / (STREAM_ROWS * mt), (B + MMA_IMGS - 1) / MMA_IMGS);
+#define MDC_STREAM(RELU_, MT_)                                                                                                              \
+  {                                                                                                                                         \
+    MDC_ENSURE_SMEM((dec_linear_stream_kernel<RELU_, MT_>), STREAM_SMEM);                                                                   \
+    dec_linear_stream_kernel<RELU_, MT_><<<grid, LIN_THREADS, STREAM_SMEM, s>>>(X, ldx, (const __half*)W, bias, Y, ldy, yh, ldyh, B, N, K);  \
+  }
+      if (relu) { if (mt == 2) MDC_STREAM(true, 2) else MDC_STREAM(true, 1) }
+      else { if (mt == 2) MDC_STREAM(false, 2) else MDC_STREAM(false, 1) }
+#undef MDC_STREAM
       MDC_LAUNCH_CHECK(ctx); return 0;
     }
     MDC_CHECK_ARG(Y != nullptr && yh == nullptr);
