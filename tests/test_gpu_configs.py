@@ -156,3 +156,20 @@ def test_config_T_trained_geometry_runs_on_the_per_operation_kernels():
     assert torch.equal(toks_w[:16], toks_s) and torch.equal(logits_w[:16], logits_s)
     toks_w2, _, logits_w2 = model.generate_tokens(x40.to(DEV), 10, return_logits=True)
     assert torch.equal(toks_w2, toks_w) and torch.equal(logits_w2, logits_w)
+    # predict() on this geometry = the all-positions prefill pass (prefill.cu: head width 128, dim 1024) against the oracle's step logits
+    # and against the autoregressive per-operation kernels on the same tokens; and its cost against theirs at B = 64
+    lp = model.predict(x.to(DEV), want_toks[:, :10].to(DEV))[:, 1:11]
+    ep = (lp.cpu() - want_logits).abs().max().item()
+    with M.decode_options(prefill=False):
+        la = model.predict(x.to(DEV), want_toks[:, :10].to(DEV))[:, 1:11]
+    epa = (lp - la).abs().max().item()
+    print(f"config T, prefill pass: bf16 max|d| vs the oracle = {ep:.2e}, vs the autoregressive kernels = {epa:.2e}")
+    assert ep <= 2e-2 and epa <= 1.5e-2 and G.cos(lp.cpu(), want_logits) >= 0.999
+    x64 = cases.images(64, seed=64).to(DEV)
+    tg, _ = model.generate_tokens(x64, 99)
+    for opts in ({"prefill": True}, {"prefill": False}):
+        with M.decode_options(**opts):
+            model.predict(x64, tg[:, :99].long()); torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); out = model.predict(x64, tg[:, :99].long()); b.record(); torch.cuda.synchronize()
+            print(f"config T predict() at B = 64, 99 positions, {opts}: {a.elapsed_time(b):.2f} ms (encoder included)")
