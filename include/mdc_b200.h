@@ -242,8 +242,9 @@ int mdc_decode_steps(mdc_model* m, const mdc_decode_state* st, int t_begin, int 
  * tcgen05 GEMMs on the fp16 decode-loop weights, causal self-attention with the reference's float PAD-key mask (+1.0, utils.py:26-30),
  * cross-attention over the resident cross-K/V, fused residual + LayerNorm; then the vocabulary head.
  * logits f32 [B, logits_ld, vocab]: row (i + row_offset) receives the logits of position i for i < n_out (predict: row_offset 1,
- * n_out n-1; forward: 0, n).  mdc_decoder_prefill_workspace_bytes() is 0 when the geometry is not covered (fp32 precision,
- * head width != 32, ...): the caller then runs mdc_decode_steps in teacher-forced mode, which computes the same logits step by step. */
+ * n_out n-1; forward: 0, n).  Covered: the bf16 path (fp16 decode-loop weights) at model widths 256 / 512 / 1024 with head widths
+ * 32 / 64 / 128 (configs P and T).  mdc_decoder_prefill_workspace_bytes() is 0 when the geometry is not covered (fp32 precision, width 64,
+ * ...): the caller then runs mdc_decode_steps in teacher-forced mode, which computes the same logits step by step. */
 size_t mdc_decoder_prefill_workspace_bytes(const mdc_model* m, int B, int n);
 int mdc_decoder_prefill(mdc_model* m, const int32_t* tokens, int tokens_ld, int B, int n, const float* pos, const void* cross_kv,
                         float* logits, int logits_ld, int row_offset, int n_out, void* workspace, size_t workspace_bytes, void* stream);
