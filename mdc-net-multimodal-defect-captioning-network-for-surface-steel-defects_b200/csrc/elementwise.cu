@@ -62,39 +62,58 @@ __global__ void layernorm_kernel(const float* __restrict__ x, int64_t ldx, const
 
 // Fast path for cols = NV * 128 <= 1024: the row lives in registers (one global read), statistics in the same two-pass order
 // (mean, then centred variance), 8-byte packed stores for bf16 output.
+// A warp normalises TWO rows in lockstep (both rows' loads in flight first, the two shuffle butterflies interleaved): 12 608 rows are 788
+// CTAs = one wave at the kernel's occupancy instead of 1 576 CTAs = 1.33 waves, and every warp has twice the bytes in flight.  Each
+// row's own operation sequence -- and so every result bit -- is what the one-row form computed.
 template <typename TO, int NV>
 __global__ void __launch_bounds__(256) layernorm_rows_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict__ w,
                                                               const float* __restrict__ b, float eps, TO* __restrict__ out, int64_t ldo, int rows) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (warp >= rows) return;
-  const float* xr = x + (int64_t)warp * ldx;
-  float4 v[NV];
+  const int r0 = 2 * warp;
+  if (r0 >= rows) return;
+  const bool two = r0 + 1 < rows;
+  const float* xr[2] = {x + (int64_t)r0 * ldx, x + (int64_t)(two ? r0 + 1 : r0) * ldx};
+  float4 v[2][NV];
 #pragma unroll
-  for (int i = 0; i < NV; ++i) v[i] = *reinterpret_cast<const float4*>(xr + i * 128 + lane * 4);
-  float s = 0.f;
+  for (int h = 0; h < 2; ++h)
 #pragma unroll
-  for (int i = 0; i < NV; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
-  const float mean = warp_sum(s) / (float)(NV * 128);
-  float q = 0.f;
+    for (int i = 0; i < NV; ++i) v[h][i] = *reinterpret_cast<const float4*>(xr[h] + i * 128 + lane * 4);
+  float s[2] = {0.f, 0.f};
 #pragma unroll
-  for (int i = 0; i < NV; ++i) {
-    const float a0 = v[i].x - mean, a1 = v[i].y - mean, a2 = v[i].z - mean, a3 = v[i].w - mean;
-    q += (a0 * a0 + a1 * a1) + (a2 * a2 + a3 * a3);
-  }
-  const float rstd = 1.0f / sqrtf(warp_sum(q) / (float)(NV * 128) + eps);
-  TO* orow = out + (int64_t)warp * ldo;
+  for (int h = 0; h < 2; ++h)
+#pragma unroll
+    for (int i = 0; i < NV; ++i) s[h] += (v[h][i].x + v[h][i].y) + (v[h][i].z + v[h][i].w);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { s[0] += __shfl_xor_sync(0xffffffffu, s[0], o); s[1] += __shfl_xor_sync(0xffffffffu, s[1], o); }
+  const float mean[2] = {s[0] / (float)(NV * 128), s[1] / (float)(NV * 128)};
+  float q[2] = {0.f, 0.f};
+#pragma unroll
+  for (int h = 0; h < 2; ++h)
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const float a0 = v[h][i].x - mean[h], a1 = v[h][i].y - mean[h], a2 = v[h][i].z - mean[h], a3 = v[h][i].w - mean[h];
+      q[h] += (a0 * a0 + a1 * a1) + (a2 * a2 + a3 * a3);
+    }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { q[0] += __shfl_xor_sync(0xffffffffu, q[0], o); q[1] += __shfl_xor_sync(0xffffffffu, q[1], o); }
+  const float rstd[2] = {1.0f / sqrtf(q[0] / (float)(NV * 128) + eps), 1.0f / sqrtf(q[1] / (float)(NV * 128) + eps)};
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     const int c = i * 128 + lane * 4;
     const float4 g = __ldg(reinterpret_cast<const float4*>(w + c)), bb = __ldg(reinterpret_cast<const float4*>(b + c));
-    const float o0 = (v[i].x - mean) * rstd * g.x + bb.x, o1 = (v[i].y - mean) * rstd * g.y + bb.y;
-    const float o2 = (v[i].z - mean) * rstd * g.z + bb.z, o3 = (v[i].w - mean) * rstd * g.w + bb.w;
-    if constexpr (sizeof(TO) == 2) {
-      __nv_bfloat162 lo = __floats2bfloat162_rn(o0, o1), hi = __floats2bfloat162_rn(o2, o3);
-      uint2 pk; pk.x = *reinterpret_cast<uint32_t*>(&lo); pk.y = *reinterpret_cast<uint32_t*>(&hi);
-      *reinterpret_cast<uint2*>(orow + c) = pk;
-    } else {
-      *reinterpret_cast<float4*>(orow + c) = make_float4(o0, o1, o2, o3);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      if (h == 1 && !two) break;
+      TO* orow = out + (int64_t)(r0 + h) * ldo;
+      const float o0 = (v[h][i].x - mean[h]) * rstd[h] * g.x + bb.x, o1 = (v[h][i].y - mean[h]) * rstd[h] * g.y + bb.y;
+      const float o2 = (v[h][i].z - mean[h]) * rstd[h] * g.z + bb.z, o3 = (v[h][i].w - mean[h]) * rstd[h] * g.w + bb.w;
+      if constexpr (sizeof(TO) == 2) {
+        __nv_bfloat162 lo = __floats2bfloat162_rn(o0, o1), hi = __floats2bfloat162_rn(o2, o3);
+        uint2 pk; pk.x = *reinterpret_cast<uint32_t*>(&lo); pk.y = *reinterpret_cast<uint32_t*>(&hi);
+        *reinterpret_cast<uint2*>(orow + c) = pk;
+      } else {
+        *reinterpret_cast<float4*>(orow + c) = make_float4(o0, o1, o2, o3);
+      }
     }
   }
 }
@@ -309,8 +328,9 @@ extern "C" int mdc_layernorm(mdc_ctx* ctx, const float* x, int64_t ldx, const fl
   const bool vec_ok = ldo % 4 == 0 && ((uintptr_t)out & 15) == 0 && ((uintptr_t)x & 15) == 0 && ((uintptr_t)w & 15) == 0 && ((uintptr_t)b & 15) == 0;
 #define MDC_LN_FAST(NV_)                                                                                                        \
   if (vec_ok && cols == NV_ * 128) {                                                                                            \
-    if (out_dtype == MDC_F32) layernorm_rows_kernel<float, NV_><<<grid, 256, 0, s>>>(x, ldx, w, b, eps, (float*)out, ldo, rows);  \
-    else if (out_dtype == MDC_BF16) layernorm_rows_kernel<bf16, NV_><<<grid, 256, 0, s>>>(x, ldx, w, b, eps, (bf16*)out, ldo, rows); \
+    const int grid2 = (rows + 15) / 16;           /* two rows per warp */                                                        \
+    if (out_dtype == MDC_F32) layernorm_rows_kernel<float, NV_><<<grid2, 256, 0, s>>>(x, ldx, w, b, eps, (float*)out, ldo, rows);  \
+    else if (out_dtype == MDC_BF16) layernorm_rows_kernel<bf16, NV_><<<grid2, 256, 0, s>>>(x, ldx, w, b, eps, (bf16*)out, ldo, rows); \
     else MDC_FAIL(-2, "layernorm: bad out_dtype %d", out_dtype);                                                                \
     MDC_LAUNCH_CHECK(ctx); return 0;                                                                                            \
   }
