@@ -864,6 +864,9 @@ __global__ void __launch_bounds__(LIN_THREADS) dec_cross_attn_split_kernel(const
 #pragma unroll
     for (int i = 0; i < UN; ++i) r[i] = rn[i];
   }
+  // the first round of V slices is requested before the softmax statistics: its round trip overlaps the two barriers and the exponentials
+#pragma unroll
+  for (int i = 0; i < UN; ++i) { const int u = ufirst + i * STEP; if (u < S) r[i].load(base + (int64_t)u * 2 * d + d); else r[i].zero(); }
   mx = warp_max(mx);
   if (lane == 0) wred[warp] = mx;
   __syncthreads();
@@ -876,10 +879,12 @@ __global__ void __launch_bounds__(LIN_THREADS) dec_cross_attn_split_kernel(const
   if (lane == 0) wred[LIN_WARPS + warp] = sum;
   __syncthreads();
   float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  for (int u0 = warp * KPI + kslot; u0 < S; u0 += STEP * UN) {
-    Raw8<TKV> r[UN];
+  for (int u0 = ufirst; u0 < S; u0 += STEP * UN) {
+    const int un = u0 + STEP * UN;
+    if (un < S) {
 #pragma unroll
-    for (int i = 0; i < UN; ++i) { const int u = u0 + i * STEP; if (u < S) r[i].load(base + (int64_t)u * 2 * d + d); else r[i].zero(); }
+      for (int i = 0; i < UN; ++i) { const int u = un + i * STEP; if (u < S) rn[i].load(base + (int64_t)u * 2 * d + d); else rn[i].zero(); }
+    }
 #pragma unroll
     for (int i = 0; i < UN; ++i) {
       const int u = u0 + i * STEP;
@@ -888,6 +893,8 @@ __global__ void __launch_bounds__(LIN_THREADS) dec_cross_attn_split_kernel(const
 #pragma unroll
       for (int j = 0; j < 8; ++j) acc[j] = fmaf(p, vf[j], acc[j]);
     }
+#pragma unroll
+    for (int i = 0; i < UN; ++i) r[i] = rn[i];
   }
 #pragma unroll
   for (int of = LPK; of < 32; of <<= 1) {
