@@ -212,7 +212,9 @@ typedef struct mdc_decode_state {
   int32_t images_per_cluster;       /* 0 = spread the batch over as many 8-SM clusters as fit (lowest latency of ONE batch); 1..16 =
                                        at least that many images per cluster, i.e. fewer SMs per batch, so that several batches in
                                        flight (pipeline.py) share the GPU; more than 8 selects the kernel instantiation with two
-                                       8-image column blocks per cluster pass.  Does not change results (bitwise). */
+                                       8-image column blocks per cluster pass.  On the per-operation path (geometries outside the fused
+                                       kernel) 16 and more = "SM-time over latency": every weight-streaming linear takes two row tiles per
+                                       CTA.  Does not change results (bitwise). */
   int32_t ctas_per_sm;              /* 0 / 1 = one decode CTA per SM (deep TMA ring); 2 (with images_per_cluster <= 8) = the compact
                                        shared-memory layout that lets two clusters -- two independent image groups -- share each
                                        SM, so that one group's dependent phase chain fills the other's stalls.  Bitwise the same

@@ -984,7 +984,7 @@ inline bool stream_linears(int B, int K) { return B >= 16 && K % 256 == 0; }
 
 template <typename TW>
 int launch_linear(mdc_ctx* ctx, const XSrc& xs, const void* W, const float* bias, float* Y, int64_t ldy, int B, int N, int K,
-                  bool relu, cudaStream_t s, __half* xh_buf = nullptr, __half* yh = nullptr, int64_t ldyh = 0) {
+                  bool relu, cudaStream_t s, __half* xh_buf = nullptr, __half* yh = nullptr, int64_t ldyh = 0, int mt2_min_n = MDC_STREAM_MT2_MIN_N) {
   MDC_CHECK_ARG(K % 8 == 0);
   if constexpr (std::is_same<TW, __half>::value) {
     // weight-streaming form: operand rows available as IEEE half (built here by prep_x_half_kernel, or the producer's half twin)
@@ -994,7 +994,7 @@ int launch_linear(mdc_ctx* ctx, const XSrc& xs, const void* W, const float* bias
         MDC_TRY(launch_prep(ctx, xs, xh_buf, B, K, s));
         X = xh_buf; ldx = K;
       }
-      const int mt = N >= MDC_STREAM_MT2_MIN_N ? 2 : 1;
+      const int mt = N >= mt2_min_n ? 2 : 1;
       dim3 grid((N + STREAM_ROWS * mt - 1) / (STREAM_ROWS * mt), (B + MMA_IMGS - 1) / MMA_IMGS);
 #define MDC_STREAM(RELU_, MT_)                                                                                                              \
   {                                                                                                                                         \
@@ -1091,6 +1091,9 @@ int decode_step_typed(mdc_model* m, const mdc_decode_state* st, int t, cudaStrea
   const float scale = 1.0f / sqrtf((float)hd);
   // wide batches on fp16 decode-loop weights: weight-streaming linears fed with IEEE-half operands by their producers
   const bool stream = std::is_same<TW, __half>::value && stream_linears(B, dim) && stream_linears(B, d.dec_ffn) && dim % 8 == 0;
+  // the batch pipeline asks for 16 images per cluster = "SM-time over latency": there every linear takes two row tiles per CTA (half the
+  // CTAs; same bits -- the tile count does not enter any element's arithmetic).  A/B at B = 64: serial token-step +10 %, pipeline +9 %.
+  const int mt2 = st->images_per_cluster >= 16 ? 512 : MDC_STREAM_MT2_MIN_N;
   XSrc prev{};   // how the next consumer obtains the layer input
   if (st->x_override) { prev.mode = XMODE_PLAIN; prev.x = st->x_override + (int64_t)t * dim; prev.ldx = (int64_t)st->x_override_ld * dim; }
   else {
@@ -1101,7 +1104,7 @@ int decode_step_typed(mdc_model* m, const mdc_decode_state* st, int t, cudaStrea
     const void** lw = lw0 + l * MDC_DEC_LAYER_SLOTS;
     // qkv = LNload(prev) . Ws^T + bs; publishes xa
     XSrc x1 = prev; x1.xn_out = sc.xa;
-    MDC_TRY(launch_linear<TW>(ctx, x1, lw[MDC_SA_IN_W], (const float*)lw[MDC_SA_IN_B], sc.qkv, 3 * dim, B, 3 * dim, dim, false, s, sc.xh));
+    MDC_TRY(launch_linear<TW>(ctx, x1, lw[MDC_SA_IN_W], (const float*)lw[MDC_SA_IN_B], sc.qkv, 3 * dim, B, 3 * dim, dim, false, s, sc.xh, nullptr, 0, mt2));
     {
       size_t smem = (size_t)d.dec_heads * (hd + t + 1 + st->pages_per_seq) * sizeof(float);
 #define MDC_SA(HD_)                                                                                                      \
@@ -1117,11 +1120,11 @@ int decode_step_typed(mdc_model* m, const mdc_decode_state* st, int t, cudaStrea
     }
     XSrc xo{}; xo.mode = XMODE_PLAIN; xo.x = sc.o; xo.ldx = dim;
     if (stream) { xo.xh = sc.oh; xo.ldxh = dim; }
-    MDC_TRY(launch_linear<TW>(ctx, xo, lw[MDC_SA_OUT_W], (const float*)lw[MDC_SA_OUT_B], sc.y1, dim, B, dim, dim, false, s, sc.xh));
+    MDC_TRY(launch_linear<TW>(ctx, xo, lw[MDC_SA_OUT_W], (const float*)lw[MDC_SA_OUT_B], sc.y1, dim, B, dim, dim, false, s, sc.xh, nullptr, 0, mt2));
     // cross-attention query from LN1(xa + y1); publishes xb
     XSrc x2{}; x2.mode = XMODE_LN; x2.resid = sc.xa; x2.delta = sc.y1; x2.ln_w = (const float*)lw[MDC_LN1_W]; x2.ln_b = (const float*)lw[MDC_LN1_B];
     x2.eps = 1e-5f; x2.xn_out = sc.xb;
-    MDC_TRY(launch_linear<TW>(ctx, x2, lw[MDC_CA_IN_W], (const float*)lw[MDC_CA_IN_B], sc.qc, dim, B, dim, dim, false, s, sc.xh));
+    MDC_TRY(launch_linear<TW>(ctx, x2, lw[MDC_CA_IN_W], (const float*)lw[MDC_CA_IN_B], sc.qc, dim, B, dim, dim, false, s, sc.xh, nullptr, 0, mt2));
     {
       size_t smem = (size_t)d.dec_heads * (hd + d.n_patches) * sizeof(float);
       const T* ckv = (const T*)st->cross_kv + (int64_t)l * B * d.n_patches * 2 * dim;
@@ -1144,21 +1147,21 @@ int decode_step_typed(mdc_model* m, const mdc_decode_state* st, int t, cudaStrea
     }
     XSrc xco{}; xco.mode = XMODE_PLAIN; xco.x = sc.oc; xco.ldx = dim;
     if (stream) { xco.xh = sc.oh; xco.ldxh = dim; }
-    MDC_TRY(launch_linear<TW>(ctx, xco, lw[MDC_CA_OUT_W], (const float*)lw[MDC_CA_OUT_B], sc.y2, dim, B, dim, dim, false, s, sc.xh));
+    MDC_TRY(launch_linear<TW>(ctx, xco, lw[MDC_CA_OUT_W], (const float*)lw[MDC_CA_OUT_B], sc.y2, dim, B, dim, dim, false, s, sc.xh, nullptr, 0, mt2));
     // FFN
     XSrc x3{}; x3.mode = XMODE_LN; x3.resid = sc.xb; x3.delta = sc.y2; x3.ln_w = (const float*)lw[MDC_LN2_W]; x3.ln_b = (const float*)lw[MDC_LN2_B];
     x3.eps = 1e-5f; x3.xn_out = sc.xc;
-    if (stream) MDC_TRY(launch_linear<TW>(ctx, x3, lw[MDC_FF1_W], (const float*)lw[MDC_FF1_B], nullptr, 0, B, d.dec_ffn, dim, true, s, sc.xh, sc.f1h, d.dec_ffn));
-    else MDC_TRY(launch_linear<TW>(ctx, x3, lw[MDC_FF1_W], (const float*)lw[MDC_FF1_B], sc.f1, d.dec_ffn, B, d.dec_ffn, dim, true, s, sc.xh));
+    if (stream) MDC_TRY(launch_linear<TW>(ctx, x3, lw[MDC_FF1_W], (const float*)lw[MDC_FF1_B], nullptr, 0, B, d.dec_ffn, dim, true, s, sc.xh, sc.f1h, d.dec_ffn, mt2));
+    else MDC_TRY(launch_linear<TW>(ctx, x3, lw[MDC_FF1_W], (const float*)lw[MDC_FF1_B], sc.f1, d.dec_ffn, B, d.dec_ffn, dim, true, s, sc.xh, nullptr, 0, mt2));
     XSrc xf{}; xf.mode = XMODE_PLAIN; xf.x = sc.f1; xf.ldx = d.dec_ffn;
     if (stream) { xf.xh = sc.f1h; xf.ldxh = d.dec_ffn; }
-    MDC_TRY(launch_linear<TW>(ctx, xf, lw[MDC_FF2_W], (const float*)lw[MDC_FF2_B], sc.y3, dim, B, dim, d.dec_ffn, false, s, sc.xh));
+    MDC_TRY(launch_linear<TW>(ctx, xf, lw[MDC_FF2_W], (const float*)lw[MDC_FF2_B], sc.y3, dim, B, dim, d.dec_ffn, false, s, sc.xh, nullptr, 0, mt2));
     prev = XSrc{}; prev.mode = XMODE_LN; prev.resid = sc.xc; prev.delta = sc.y3; prev.ln_w = (const float*)lw[MDC_LN3_W];
     prev.ln_b = (const float*)lw[MDC_LN3_B]; prev.eps = 1e-5f;
   }
   {
     const int V = d.vocab, Vp2 = next_pow2(V);
-    MDC_TRY(launch_linear<TW>(ctx, prev, gw[MDC_OUT_W], (const float*)gw[MDC_OUT_B], sc.lg, V, B, V, dim, false, s, sc.xh));
+    MDC_TRY(launch_linear<TW>(ctx, prev, gw[MDC_OUT_W], (const float*)gw[MDC_OUT_B], sc.lg, V, B, V, dim, false, s, sc.xh, nullptr, 0, mt2));
     size_t smem = (size_t)(V + Vp2) * sizeof(float);
     MDC_ENSURE_SMEM(dec_select_kernel, smem);
     dec_select_kernel<<<B, SEL_THREADS, smem, s>>>(sc.lg, V, Vp2, t, st->logits, (int64_t)st->logits_ld * V, t + st->logits_row_offset,
