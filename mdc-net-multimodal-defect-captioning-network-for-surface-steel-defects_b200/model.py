@@ -558,6 +558,12 @@ class GenerationPlan:
     encoder -> memory -> cross-K/V -> T decode steps, no host synchronisation anywhere inside."""
 
     def __init__(self, eng, B, T, top_k, top_p, sampling, want_logits, use_graph, split=False, images_per_cluster=None, ctas_per_sm=None):
+        # everything below (allocations, warm-up launches, graph capture) on the ENGINE's device: torch.cuda.graph captures the current
+        # device's stream, so with another device current the capture came back empty and replays did nothing (two-device test)
+        with torch.cuda.device(eng.device):
+            self._build(eng, B, T, top_k, top_p, sampling, want_logits, use_graph, split, images_per_cluster, ctas_per_sm)
+
+    def _build(self, eng, B, T, top_k, top_p, sampling, want_logits, use_graph, split, images_per_cluster, ctas_per_sm):
         d = eng.dims
         dev = eng.device
         self.eng, self.B, self.T = eng, B, T
@@ -589,10 +595,11 @@ class GenerationPlan:
             torch.cuda.synchronize(dev)
             self.enc_graph, self.dec_graph = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
             n0 = L.launch_count(dev)
-            with torch.cuda.graph(self.enc_graph):
+            with torch.cuda.graph(self.enc_graph, stream=side):     # an explicit capture stream of THIS device (torch's default one is a
+                                                                    # process-wide singleton on whichever device captured first)
                 self._launch_encode()
             n1 = L.launch_count(dev)
-            with torch.cuda.graph(self.dec_graph):
+            with torch.cuda.graph(self.dec_graph, stream=side):
                 self._launch_decode()
             self.enc_kernels, self.dec_kernels = n1 - n0, L.launch_count(dev) - n1
             self.enc_done, self.dec_done = torch.cuda.Event(), torch.cuda.Event()
@@ -607,7 +614,7 @@ class GenerationPlan:
             torch.cuda.synchronize(dev)
             g = torch.cuda.CUDAGraph()
             n0 = L.launch_count(dev)
-            with torch.cuda.graph(g):
+            with torch.cuda.graph(g, stream=side):
                 self._launch()
             self.graph_kernels = L.launch_count(dev) - n0      # kernels of libmdc_b200.so inside one replay
             self.graph = g
@@ -634,12 +641,13 @@ class GenerationPlan:
         d = self.eng.dims
         if tuple(image.shape) != tuple(self.x.shape):
             raise AssertionError("Input size doesn't match model")
-        self.x.copy_(image, non_blocking=True)               # H2D from (pinned) host memory or D2D
-        if self.uniforms is not None:
-            self.uniforms.copy_(uniforms.to(torch.float32), non_blocking=True)
-        if self.graph is not None:
-            self.graph.replay()
-            L.note_graph_replay(self.eng.device, self.graph_kernels)
-        else:
-            self._launch()
+        with torch.cuda.device(self.eng.device):
+            self.x.copy_(image, non_blocking=True)               # H2D from (pinned) host memory or D2D
+            if self.uniforms is not None:
+                self.uniforms.copy_(uniforms.to(torch.float32), non_blocking=True)
+            if self.graph is not None:
+                self.graph.replay()
+                L.note_graph_replay(self.eng.device, self.graph_kernels)
+            else:
+                self._launch()
         return self.tokens, self.confs, self.logits

@@ -20,6 +20,14 @@ def test_model_on_second_device_with_first_device_current():
     assert t1.device.index == 1 and torch.equal(t0.cpu(), t1.cpu()) and torch.equal(c0.cpu(), c1.cpu())
     p0 = m0.predict(x.to("cuda:0"), t0[:, :8].long()); p1 = m1.predict(x.to("cuda:1"), t1[:, :8].long())
     assert torch.equal(p0.cpu(), p1.cpu())
+    # the batch pipeline on the second device (plans, graphs and streams of cuda:1 while cuda:0 is current)
+    tok = M.Tokenizer()
+    xs = [cases.images(5, seed=40 + i) for i in range(3)]
+    got1 = list(M.generate_stream(m1, (v.to("cuda:1") for v in xs), tok, max_len=12))
+    got0 = list(M.generate_stream(m0, (v.to("cuda:0") for v in xs), tok, max_len=12))
+    assert all(torch.equal(a[0], b[0]) for a, b in zip(got0, got1))
+    assert torch.equal(got1[0][0], M.generate(m1, xs[0].to("cuda:1"), tok, max_len=12)[0])
+    assert torch.cuda.current_device() == 0
     boxes = torch.rand(3, 4, 4); boxes[..., 2:] += boxes[..., :2]
     assert torch.equal(torch.stack(M.calculate_batch_iou(boxes.to("cuda:1"), boxes.to("cuda:1"))).cpu(),
                        torch.stack(M.calculate_batch_iou(boxes.to("cuda:0"), boxes.to("cuda:0"))).cpu())
