@@ -156,6 +156,9 @@ def test_config_T_trained_geometry_runs_on_the_per_operation_kernels():
     assert torch.equal(toks_w[:16], toks_s) and torch.equal(logits_w[:16], logits_s)
     toks_w2, _, logits_w2 = model.generate_tokens(x40.to(DEV), 10, return_logits=True)
     assert torch.equal(toks_w2, toks_w) and torch.equal(logits_w2, logits_w)
+    x80 = torch.cat([x40, x40])                  # more than 64 images: the second image block of the streaming linears (grid.y = 2)
+    toks_x, _, logits_x = model.generate_tokens(x80.to(DEV), 10, return_logits=True)
+    assert torch.equal(toks_x[:40], toks_w) and torch.equal(toks_x[40:], toks_w) and torch.equal(logits_x[40:], logits_w)
     # predict() on this geometry = the all-positions prefill pass (prefill.cu: head width 128, dim 1024) against the oracle's step logits
     # and against the autoregressive per-operation kernels on the same tokens; and its cost against theirs at B = 64
     lp = model.predict(x.to(DEV), want_toks[:, :10].to(DEV))[:, 1:11]
