@@ -16,6 +16,11 @@
 // re-normalises the few rows it needs; CTA column 0 also publishes the normalised rows as the
 // next residual), so no projection needs a full-row epilogue and all of them spread over the SMs.
 // The head kernel fuses LN3 + vocab projection + greedy / top-k / top-p select + max-prob.
+// Batches of 16 and more on fp16 decode-loop weights (the wide geometry of trail_01.py:158-160 -- dim 1024, 8 x 128, 8 layers -- and the
+// dim-256 geometry when the per-operation path is asked for) take a second form of the same data flow: the operand rows are built ONCE
+// per linear as IEEE half (prep_x_half_vec_kernel: LayerNorm-on-load / embedding, also publishes the f32 residual), the linears are
+// dec_linear_stream_kernel (weight rows as the MMA M operand, 16-32 rows per CTA, K split over the warps), the attention kernels write
+// the half operand of their out-projection, and cross-attention splits the memory keys over a CTA (dec_cross_attn_split_kernel).
 #include "common.cuh"
 #include "select.cuh"
 #include <cuda_fp16.h>
