@@ -78,6 +78,12 @@ __global__ void __launch_bounds__(256) layernorm_rows_kernel(const float* __rest
   for (int h = 0; h < 2; ++h)
 #pragma unroll
     for (int i = 0; i < NV; ++i) v[h][i] = *reinterpret_cast<const float4*>(xr[h] + i * 128 + lane * 4);
+  float4 gq[NV], bq[NV];               // weight / bias requested with the rows: one memory round trip per warp instead of two
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    gq[i] = __ldg(reinterpret_cast<const float4*>(w + i * 128 + lane * 4));
+    bq[i] = __ldg(reinterpret_cast<const float4*>(b + i * 128 + lane * 4));
+  }
   float s[2] = {0.f, 0.f};
 #pragma unroll
   for (int h = 0; h < 2; ++h)
@@ -100,7 +106,7 @@ __global__ void __launch_bounds__(256) layernorm_rows_kernel(const float* __rest
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     const int c = i * 128 + lane * 4;
-    const float4 g = __ldg(reinterpret_cast<const float4*>(w + c)), bb = __ldg(reinterpret_cast<const float4*>(b + c));
+    const float4 g = gq[i], bb = bq[i];
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       if (h == 1 && !two) break;
