@@ -572,7 +572,8 @@ __device__ __forceinline__ void cp_async16_cg(uint32_t smem_dst, const void* gsr
 template <bool RELU, int MT>
 __global__ void __launch_bounds__(LIN_THREADS) dec_linear_stream_kernel(const __half* __restrict__ X, int64_t ldx, const __half* __restrict__ W,
                                                                          const float* __restrict__ bias, float* __restrict__ Y, int64_t ldy,
-                                                                         __half* __restrict__ Yh, int64_t ldyh, int B, int N, int K) {
+                                                                         __half* __restrict__ Yh, int64_t ldyh, int B, int N, int K,
+                                                                         const uint8_t* __restrict__ pf, int pf_lines) {
   constexpr int ROWS = STREAM_ROWS * MT;
   static_assert(LIN_WARPS * ROWS * STREAM_PITCH * 4 <= STREAM_SMEM, "partial tiles must fit into the operand ring");
   extern __shared__ __align__(128) uint8_t stream_smem[];
@@ -593,6 +594,11 @@ __global__ void __launch_bounds__(LIN_THREADS) dec_linear_stream_kernel(const __
 #pragma unroll
       for (int m = 0; m < MT; ++m) { alo[m][i] = __ldg(reinterpret_cast<const uint4*>(wa[m] + 256 * i)); ahi[m][i] = __ldg(reinterpret_cast<const uint4*>(wb[m] + 256 * i)); }
     }
+  // the NEXT linear's weights (168 MB of decode-loop weights per token-step do not stay in the 126 MB L2) are pulled into L2 while this
+  // linear and the one or two small kernels behind it run: its weight requests then cost an L2 round trip instead of an HBM one
+  if (pf != nullptr && blockIdx.y == 0)
+    for (int i = blockIdx.x * LIN_THREADS + threadIdx.x; i < pf_lines; i += gridDim.x * LIN_THREADS)
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(pf + (size_t)i * 128));
   // operand ring of this warp: slot = [64 images][4 x 16 bytes]; lane l copies the 16-byte pieces l, l + 32, ... (piece = 4 image + part)
   const uint32_t ring = (uint32_t)__cvta_generic_to_shared(stream_smem) + warp * (STREAM_SLOTS * STREAM_SLOT_BYTES);
   // image slots past the batch are zeroed once and never copied (clamping them to the last row made thousands of L2 requests hit the
@@ -992,7 +998,8 @@ inline bool stream_linears(int B, int K) { return B >= 16 && K % 256 == 0; }
 
 template <typename TW>
 int launch_linear(mdc_ctx* ctx, const XSrc& xs, const void* W, const float* bias, float* Y, int64_t ldy, int B, int N, int K,
-                  bool relu, cudaStream_t s, __half* xh_buf = nullptr, __half* yh = nullptr, int64_t ldyh = 0, int mt2_min_n = MDC_STREAM_MT2_MIN_N) {
+                  bool relu, cudaStream_t s, __half* xh_buf = nullptr, __half* yh = nullptr, int64_t ldyh = 0, int mt2_min_n = MDC_STREAM_MT2_MIN_N,
+                  const void* next_w = nullptr, size_t next_w_bytes = 0) {
   MDC_CHECK_ARG(K % 8 == 0);
   if constexpr (std::is_same<TW, __half>::value) {
     // weight-streaming form: operand rows available as IEEE half (built here by prep_x_half_kernel, or the producer's half twin)
@@ -1007,7 +1014,8 @@ int launch_linear(mdc_ctx* ctx, const XSrc& xs, const void* W, const float* bias
 #define MDC_STREAM(RELU_, MT_)                                                                                                              \
   {                                                                                                                                         \
     MDC_ENSURE_SMEM((dec_linear_stream_kernel<RELU_, MT_>), STREAM_SMEM);                                                                   \
-    dec_linear_stream_kernel<RELU_, MT_><<<grid, LIN_THREADS, STREAM_SMEM, s>>>(X, ldx, (const __half*)W, bias, Y, ldy, yh, ldyh, B, N, K);  \
+    dec_linear_stream_kernel<RELU_, MT_><<<grid, LIN_THREADS, STREAM_SMEM, s>>>(X, ldx, (const __half*)W, bias, Y, ldy, yh, ldyh, B, N, K,   \
+                                                                                (const uint8_t*)next_w, (int)(next_w_bytes / 128));           \
   }
       if (relu) { if (mt == 2) MDC_STREAM(true, 2) else MDC_STREAM(true, 1) }
       else { if (mt == 2) MDC_STREAM(false, 2) else MDC_STREAM(false, 1) }
@@ -1112,7 +1120,7 @@ int decode_step_typed(mdc_model* m, const mdc_decode_state* st, int t, cudaStrea
     const void** lw = lw0 + l * MDC_DEC_LAYER_SLOTS;
     // qkv = LNload(prev) . Ws^T + bs; publishes xa
     XSrc x1 = prev; x1.xn_out = sc.xa;
-    MDC_TRY(launch_linear<TW>(ctx, x1, lw[MDC_SA_IN_W], (const float*)lw[MDC_SA_IN_B], sc.qkv, 3 * dim, B, 3 * dim, dim, false, s, sc.xh, nullptr, 0, mt2));
+    MDC_TRY(launch_linear<TW>(ctx, x1, lw[MDC_SA_IN_W], (const float*)lw[MDC_SA_IN_B], sc.qkv, 3 * dim, B, 3 * dim, dim, false, s, sc.xh, nullptr, 0, mt2, lw[MDC_SA_OUT_W], (size_t)dim * dim * sizeof(TW)));
     {
       size_t smem = (size_t)d.dec_heads * (hd + t + 1 + st->pages_per_seq) * sizeof(float);
 #define MDC_SA(HD_)                                                                                                      \
@@ -1128,11 +1136,11 @@ int decode_step_typed(mdc_model* m, const mdc_decode_state* st, int t, cudaStrea
     }
     XSrc xo{}; xo.mode = XMODE_PLAIN; xo.x = sc.o; xo.ldx = dim;
     if (stream) { xo.xh = sc.oh; xo.ldxh = dim; }
-    MDC_TRY(launch_linear<TW>(ctx, xo, lw[MDC_SA_OUT_W], (const float*)lw[MDC_SA_OUT_B], sc.y1, dim, B, dim, dim, false, s, sc.xh, nullptr, 0, mt2));
+    MDC_TRY(launch_linear<TW>(ctx, xo, lw[MDC_SA_OUT_W], (const float*)lw[MDC_SA_OUT_B], sc.y1, dim, B, dim, dim, false, s, sc.xh, nullptr, 0, mt2, lw[MDC_CA_IN_W], (size_t)dim * dim * sizeof(TW)));
     // cross-attention query from LN1(xa + y1); publishes xb
     XSrc x2{}; x2.mode = XMODE_LN; x2.resid = sc.xa; x2.delta = sc.y1; x2.ln_w = (const float*)lw[MDC_LN1_W]; x2.ln_b = (const float*)lw[MDC_LN1_B];
     x2.eps = 1e-5f; x2.xn_out = sc.xb;
-    MDC_TRY(launch_linear<TW>(ctx, x2, lw[MDC_CA_IN_W], (const float*)lw[MDC_CA_IN_B], sc.qc, dim, B, dim, dim, false, s, sc.xh, nullptr, 0, mt2));
+    MDC_TRY(launch_linear<TW>(ctx, x2, lw[MDC_CA_IN_W], (const float*)lw[MDC_CA_IN_B], sc.qc, dim, B, dim, dim, false, s, sc.xh, nullptr, 0, mt2, lw[MDC_CA_OUT_W], (size_t)dim * dim * sizeof(TW)));
     {
       size_t smem = (size_t)d.dec_heads * (hd + d.n_patches) * sizeof(float);
       const T* ckv = (const T*)st->cross_kv + (int64_t)l * B * d.n_patches * 2 * dim;
@@ -1155,21 +1163,24 @@ int decode_step_typed(mdc_model* m, const mdc_decode_state* st, int t, cudaStrea
     }
     XSrc xco{}; xco.mode = XMODE_PLAIN; xco.x = sc.oc; xco.ldx = dim;
     if (stream) { xco.xh = sc.oh; xco.ldxh = dim; }
-    MDC_TRY(launch_linear<TW>(ctx, xco, lw[MDC_CA_OUT_W], (const float*)lw[MDC_CA_OUT_B], sc.y2, dim, B, dim, dim, false, s, sc.xh, nullptr, 0, mt2));
+    MDC_TRY(launch_linear<TW>(ctx, xco, lw[MDC_CA_OUT_W], (const float*)lw[MDC_CA_OUT_B], sc.y2, dim, B, dim, dim, false, s, sc.xh, nullptr, 0, mt2, lw[MDC_FF1_W], (size_t)d.dec_ffn * dim * sizeof(TW)));
     // FFN
     XSrc x3{}; x3.mode = XMODE_LN; x3.resid = sc.xb; x3.delta = sc.y2; x3.ln_w = (const float*)lw[MDC_LN2_W]; x3.ln_b = (const float*)lw[MDC_LN2_B];
     x3.eps = 1e-5f; x3.xn_out = sc.xc;
-    if (stream) MDC_TRY(launch_linear<TW>(ctx, x3, lw[MDC_FF1_W], (const float*)lw[MDC_FF1_B], nullptr, 0, B, d.dec_ffn, dim, true, s, sc.xh, sc.f1h, d.dec_ffn, mt2));
+    if (stream) MDC_TRY(launch_linear<TW>(ctx, x3, lw[MDC_FF1_W], (const float*)lw[MDC_FF1_B], nullptr, 0, B, d.dec_ffn, dim, true, s, sc.xh, sc.f1h, d.dec_ffn, mt2, lw[MDC_FF2_W], (size_t)d.dec_ffn * dim * sizeof(TW)));
     else MDC_TRY(launch_linear<TW>(ctx, x3, lw[MDC_FF1_W], (const float*)lw[MDC_FF1_B], sc.f1, d.dec_ffn, B, d.dec_ffn, dim, true, s, sc.xh, nullptr, 0, mt2));
     XSrc xf{}; xf.mode = XMODE_PLAIN; xf.x = sc.f1; xf.ldx = d.dec_ffn;
+    // what the linear after FFN2 streams: the next layer's in-projection, or the vocabulary head
+    const void* next_in_w = l + 1 < d.dec_layers ? (lw + MDC_DEC_LAYER_SLOTS)[MDC_SA_IN_W] : gw[MDC_OUT_W];
+    const size_t next_in_bytes = l + 1 < d.dec_layers ? 3 * (size_t)dim * dim * sizeof(TW) : (size_t)d.vocab * dim * sizeof(TW);
     if (stream) { xf.xh = sc.f1h; xf.ldxh = d.dec_ffn; }
-    MDC_TRY(launch_linear<TW>(ctx, xf, lw[MDC_FF2_W], (const float*)lw[MDC_FF2_B], sc.y3, dim, B, dim, d.dec_ffn, false, s, sc.xh, nullptr, 0, mt2));
+    MDC_TRY(launch_linear<TW>(ctx, xf, lw[MDC_FF2_W], (const float*)lw[MDC_FF2_B], sc.y3, dim, B, dim, d.dec_ffn, false, s, sc.xh, nullptr, 0, mt2, next_in_w, next_in_bytes));
     prev = XSrc{}; prev.mode = XMODE_LN; prev.resid = sc.xc; prev.delta = sc.y3; prev.ln_w = (const float*)lw[MDC_LN3_W];
     prev.ln_b = (const float*)lw[MDC_LN3_B]; prev.eps = 1e-5f;
   }
   {
     const int V = d.vocab, Vp2 = next_pow2(V);
-    MDC_TRY(launch_linear<TW>(ctx, prev, gw[MDC_OUT_W], (const float*)gw[MDC_OUT_B], sc.lg, V, B, V, dim, false, s, sc.xh, nullptr, 0, mt2));
+    MDC_TRY(launch_linear<TW>(ctx, prev, gw[MDC_OUT_W], (const float*)gw[MDC_OUT_B], sc.lg, V, B, V, dim, false, s, sc.xh, nullptr, 0, mt2, lw0[MDC_SA_IN_W], 3 * (size_t)dim * dim * sizeof(TW)));
     size_t smem = (size_t)(V + Vp2) * sizeof(float);
     MDC_ENSURE_SMEM(dec_select_kernel, smem);
     dec_select_kernel<<<B, SEL_THREADS, smem, s>>>(sc.lg, V, Vp2, t, st->logits, (int64_t)st->logits_ld * V, t + st->logits_row_offset,
