@@ -24,3 +24,7 @@ python tools/decode_variants.py 99 64,16,0 > $o/${tag}_plain_dec16.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:decode_fused_kernel -s 1 -c 1 -f -o $o/${tag}_decode16 python tools/decode_variants.py 99 64,16,0 > $o/${tag}_ncu_decode16.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:layernorm_rows_kernel -c 1 -f -o $o/${tag}_ln python bench.py --profile > $o/${tag}_ncu_ln.log 2>&1
 python tools/iou_probe.py > $o/${tag}_iou.log 2>&1
+# the trained geometry T on the per-operation chain: timing, pipeline, launch list
+python tools/config_t_probe.py 64 99 --pipeline > $o/${tag}_cfgt.log 2>&1
+python tools/config_t_probe.py 64 4 > $o/${tag}_plain_cfgt.log 2>&1 &&
+ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file $o/${tag}_cfgt_launches.csv python tools/config_t_probe.py 64 4 > $o/${tag}_ncu_cfgt.log 2>&1
